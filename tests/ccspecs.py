@@ -1,0 +1,33 @@
+"""Architecture variants exercised by the parity tests (sizes observed in the reference)."""
+from oracle import np_oracle as O
+
+
+def model_variants():
+    v = {}
+    # notebook-3 / end_to_end_learning compact model: S=50, depth 0, arctan, pre-step readout
+    v["compact_s50_d0"] = O.make_node(50, 1, 1, f_depth=0, readout_pre_step=True, u_transform=O.UT_ARCTAN)
+    # test_trainer.py model: S=1, depth 0, time-variant f, arctan, post-step readout
+    v["full_s1_tv"] = O.make_node(1, 1, 1, f_depth=0, f_time_variant=True, u_transform=O.UT_ARCTAN)
+    # defaults of make_neural_ode_model: width 10, depth 2, relu
+    v["full_s5_w10_d2"] = O.make_node(5, 1, 1, f_width=10, f_depth=2)
+    # tanh final activation, depth 1, width 25, two inputs / two outputs, g depth 1, time-variant g
+    v["full_s12_w25_d1_tanh"] = O.make_node(12, 2, 2, f_width=25, f_depth=1, f_act_final=O.ACT_TANH,
+                                            g_width=7, g_depth=1, g_time_variant=True,
+                                            u_transform=O.UT_KTANH, u_scale=6.0)
+    v["euler_s9"] = O.make_node(9, 1, 1, f_depth=1, f_width=11, integrator=O.INT_EE, f_act=O.ACT_TANH)
+    v["noint_s4_nobias"] = O.make_node(4, 1, 3, f_depth=0, integrator=O.INT_NONE, f_use_bias=False,
+                                       g_use_bias=False, f_act_final=O.ACT_TANH)
+    return v
+
+
+def controller_variants(R=1, O_obs=1, I_m=1):
+    v = {}
+    din = R + O_obs
+    # notebook-4 compact controller: S_c=5, depth 0, pre-step readout, alpha = sigmoid(0) = 0.5
+    v["compact_s5_d0"] = O.make_node(5, din, I_m, f_depth=0, readout_pre_step=True, out_scale=0.5)
+    # CLI default full controller: S_c=25, W=10, depth 2
+    v["full_s25_w10_d2"] = O.make_node(25, din, I_m, f_width=10, f_depth=2)
+    # feed-through + time-variant
+    v["full_s6_ft_tv"] = O.make_node(6, din, I_m, f_width=8, f_depth=1, g_feedthrough_u=True,
+                                     f_time_variant=True, g_time_variant=True, f_act=O.ACT_TANH)
+    return v
