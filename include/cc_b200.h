@@ -1,0 +1,137 @@
+/*
+ * cc_b200.h — C ABI of the B200-native neural-ODE rollout path of chain_control.
+ *
+ * The reference (simon-bachhuber/chain_control) is pure Python/JAX and has no FFI; the seam this
+ * library replaces is the *batched* unroll that the train step builds with
+ *     eqx.filter_vmap(model.unroll)(inputs)                       cc/train/step_fn.py:124,136
+ *     eqx.filter_vmap(controller.unroll(model, merge_x_y, noise))(refss, keys)   step_fn.py:234-236,257-259
+ * and its reverse-mode gradient taken by eqx.filter_value_and_grad   step_fn.py:133,249-252.
+ * Each entry point below is what a `jax.ffi.ffi_call` (forward) / `jax.custom_vjp` (backward) pair
+ * would bind; src/xla_ffi_shim.cc wraps exactly these functions.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch / XLA types.  All array pointers are DEVICE pointers,
+ *     fp32, C-contiguous, owned by the caller.  Kernels never allocate; scratch comes from `ws`.
+ *   - asynchronous on `stream` (a cudaStream_t passed as void*).
+ *   - return 0 on success, a negative CcStatus otherwise; cc_last_error() gives a thread-local
+ *     message.  An unsupported architecture is an ERROR — there is no fallback path.
+ *   - deterministic: fixed reduction order, reruns are bit-identical.
+ *   - flat parameter vector `theta` is in the reference's flatten_module order
+ *     (cc/core/module_utils.py:20-24): f.layers[0].weight[out,in] row-major, f.layers[0].bias,
+ *     f.layers[1]..., then g likewise.
+ */
+#ifndef CC_B200_H_
+#define CC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CC_MAX_LAYERS 4 /* MLP depth <= 3 hidden layers */
+
+enum CcAct { CC_ACT_IDENTITY = 0, CC_ACT_RELU = 1, CC_ACT_TANH = 2 };
+enum CcUTransform { CC_UT_IDENTITY = 0, CC_UT_ARCTAN = 1, CC_UT_KTANH = 2 /* k*tanh(u/k) */ };
+enum CcIntegrator { CC_INT_RK4 = 0, CC_INT_EE = 1, CC_INT_NONE = 2 }; /* nn_lib/integrate.py:16-28 */
+
+enum CcStatus {
+  CC_OK = 0,
+  CC_ERR_INVALID_ARG = -1,
+  CC_ERR_UNSUPPORTED = -2, /* architecture does not fit the kernels (never falls back) */
+  CC_ERR_WORKSPACE = -3,   /* ws_bytes too small: see cc_*_workspace_bytes */
+  CC_ERR_CUDA = -4
+};
+
+/* eqx.nn.Sequential([Linear, Lambda(act), ..., Linear, Lambda(act_final)])  nn_lib/mlp_network.py:5-35 */
+typedef struct CcMlp {
+  int32_t n_layers;                 /* depth + 1 */
+  int32_t sizes[CC_MAX_LAYERS + 1]; /* [in] + depth*[width] + [out] */
+  int32_t act;                      /* CcAct after every layer but the last */
+  int32_t act_final;                /* CcAct after the last layer */
+  int32_t use_bias;
+} CcMlp;
+
+/* One neural-ODE module: NeuralOdeModel (cc/examples/neural_ode_model.py:97-177, compact
+ * neural_ode_model_compact_example.py:85-124) or NeuralOdeController (neural_ode_controller.py:99-160,
+ * compact neural_ode_controller_compact_example.py:88-181). */
+typedef struct CcModule {
+  int32_t state_dim;  /* S */
+  int32_t input_dim;  /* I: model input u / controller input [ref;obs] */
+  int32_t output_dim; /* O */
+  CcMlp f;            /* [S (+1 if f_time_variant) + I] -> S ; input order [x ; t ; u~] */
+  CcMlp g;            /* [S (+1 if g_time_variant) (+I if g_feedthrough_u)] -> O */
+  int32_t integrator;        /* CcIntegrator */
+  int32_t f_time_variant;    /* neural_ode_model.py:122-125 */
+  int32_t g_time_variant;    /* :129-133 (the PRE-step time is fed) */
+  int32_t g_feedthrough_u;   /* controllers only, neural_ode_controller.py:129-134 */
+  int32_t readout_pre_step;  /* compact variants: y = g(x) with the state BEFORE the update */
+  int32_t u_transform;       /* CcUTransform applied to the module input before f (models) */
+  float u_scale;             /* k of k*tanh(u/k) */
+  float out_scale;           /* compact controller: sigmoid(alpha) (=0.5) with the zero secondary */
+  float dt;                  /* control_timestep */
+} CcModule;
+
+/* ---- introspection ------------------------------------------------------------------------- */
+int32_t cc_abi_version(void);
+const char* cc_last_error(void);
+/* number of trainable scalars P of a module (length of theta / theta_bar) */
+int64_t cc_param_count(const CcModule* m);
+/* 0 if the kernels support this module (with_grad: also the BPTT kernels), else a CcStatus */
+int32_t cc_module_supported(const CcModule* m, int32_t with_grad);
+
+/* ---- K1/K2: open-loop batched unroll and its VJP  (replaces step_fn.py:136 + abstract.py:54-70) ---
+ * u      [B,T,I]      inputs
+ * x0     [B,S] or NULL (zeros = reset(), neural_ode_model.py:103-104)
+ * y      [B,T+1,O]    outputs incl. y0 (include_y0=True)
+ * tape   forward->backward residuals (module states every `ckpt_every` steps), opaque layout,
+ *        cc_rollout_tape_bytes() bytes; NULL for inference.
+ * x_final [B,S] or NULL: state after the last step (lets step() be served by T=1 calls).
+ */
+size_t cc_rollout_tape_bytes(const CcModule* m, int64_t B, int32_t T, int32_t ckpt_every);
+size_t cc_rollout_workspace_bytes(const CcModule* m, int64_t B, int32_t T, int32_t ckpt_every);
+int32_t cc_rollout_fwd(const CcModule* m, const float* theta, const float* u, const float* x0,
+                       float* y, float* x_final, void* tape, int32_t ckpt_every, int64_t B,
+                       int32_t T, void* stream);
+/* ybar [B,T+1,O] -> theta_bar [P] (overwritten), ubar [B,T,I] or NULL.  Needs the tape written by
+ * cc_rollout_fwd with the same (theta,u,x0,B,T,ckpt_every). */
+int32_t cc_rollout_bwd(const CcModule* m, const float* theta, const float* u, const float* x0,
+                       const void* tape, int32_t ckpt_every, const float* ybar, float* theta_bar,
+                       float* ubar, int64_t B, int32_t T, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- K3/K4: closed-loop batched unroll and its VJP (replaces step_fn.py:257-259 + abstract.py:97-127)
+ * refs   [B,Tr,R]     reference series; controller input is [ref ; y_prev] (merge_x_y, step_fn.py:187-192)
+ * noise  [B,Tr,O] or NULL: additive observation noise, already scaled (abstract.py:77-79,112-114)
+ * yhat   [B,Tr,O]     closed-loop outputs (what unroll_closed_loop returns, abstract.py:125)
+ * u_out  [B,Tr,I_m] or NULL: the control series (discarded by the reference, kept for diagnostics)
+ * theta_c_bar [P_c]: gradient w.r.t. the controller only; the model is frozen (step_fn.py:249-252).
+ */
+size_t cc_closedloop_tape_bytes(const CcModule* ctrl, const CcModule* model, int64_t B, int32_t Tr,
+                                int32_t ckpt_every);
+size_t cc_closedloop_workspace_bytes(const CcModule* ctrl, const CcModule* model, int64_t B,
+                                     int32_t Tr, int32_t ckpt_every);
+int32_t cc_closedloop_fwd(const CcModule* ctrl, const CcModule* model, const float* theta_c,
+                          const float* theta_m, const float* refs, const float* noise, float* yhat,
+                          float* u_out, void* tape, int32_t ckpt_every, int64_t B, int32_t Tr,
+                          void* stream);
+int32_t cc_closedloop_bwd(const CcModule* ctrl, const CcModule* model, const float* theta_c,
+                          const float* theta_m, const float* refs, const float* noise,
+                          const void* tape, int32_t ckpt_every, const float* ybar,
+                          float* theta_c_bar, int64_t B, int32_t Tr, void* ws, size_t ws_bytes,
+                          void* stream);
+
+/* ---- K6: default loss (cc/utils/utils.py:53-55) fused with its cotangent ----------------------
+ * loss_partial[0] = sum((yhat-y)^2) * inv_n  ;  ybar = 2*(yhat-y)*inv_n   (inv_n = 1/global count) */
+int32_t cc_mse_value_and_cotangent(const float* y, const float* yhat, float* ybar,
+                                   float* loss_partial, int64_t n, float inv_n, void* stream);
+
+/* ---- measurement helper: register-resident FFMA chain, returns nothing; time it with events ---- */
+int32_t cc_fp32_peak_probe(float* sink, int32_t iters, void* stream);
+/* number of kernel launches issued through this library since load (bench.py's gpu_launches) */
+int64_t cc_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CC_B200_H_ */

@@ -262,7 +262,7 @@ def node_step(spec: NodeSpec, fl, gl, x, t, v):
     """x[B,S], t scalar (dtype), v[B,I] -> x_next, out[B,O], cache.
     neural_ode_model.py:106-149 / compact :94-110; integrate.py:6-13 (operation order kept)."""
     dt_ = x.dtype.type
-    h = dt_(spec.dt)
+    h = dt_(np.float32(spec.dt))  # the reference's fp32 path sees f32(control_timestep)
     ut = _ut(spec.u_transform, spec.u_scale, v)
     c = {"x": x, "t": t, "v": v, "stages": []}
 
@@ -296,7 +296,7 @@ def node_step_bwd(spec: NodeSpec, fl, gl, c, out_bar, lam_next, fgrads, ggrads):
     """VJP of node_step: (out_bar[B,O], lam_next[B,S]) -> lam[B,S], v_bar[B,I].  SURVEY §9.4."""
     x, v = c["x"], c["v"]
     dt_ = x.dtype.type
-    h = dt_(spec.dt)
+    h = dt_(np.float32(spec.dt))
     S, I = spec.state_dim, spec.input_dim
     v_bar = np.zeros_like(v)
     ut_bar = np.zeros_like(v)
@@ -382,7 +382,7 @@ def rollout_fwd(spec: NodeSpec, theta, u, dtype=np.float64, x0=None, return_tape
         if return_tape:
             tape.append(c)
         if spec.has_time:
-            t = t + dtype(spec.dt)
+            t = t + dtype(np.float32(spec.dt))
     if return_tape:
         return y, xs, (tape, g0)
     return y, xs
@@ -441,9 +441,9 @@ def closedloop_fwd(cspec: NodeSpec, mspec: NodeSpec, theta_c, theta_m, refs, noi
         if return_tape:
             tape.append((cc_, mc_))
         if cspec.has_time:
-            tc = tc + dtype(cspec.dt)
+            tc = tc + dtype(np.float32(cspec.dt))
         if mspec.has_time:
-            tm = tm + dtype(mspec.dt)
+            tm = tm + dtype(np.float32(mspec.dt))
     if return_tape:
         return yhat, us, tape
     return yhat, us

@@ -2,6 +2,7 @@
 hand-derived reverse pass.  Written directly from the reference files (neural_ode_model.py:106-149,
 neural_ode_controller_compact_example.py:106-129, abstract.py:54-127, integrate.py:1-28); shares no
 code with oracle/np_oracle.py except the spec dataclasses."""
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -49,7 +50,7 @@ def step(spec, fl, gl, x, t, v):
     tcol = lambda tt: torch.full((B, 1), float(tt), dtype=x.dtype)
     ut = _ut(spec, v)
     rhs = lambda tt, z: _mlp(spec.f, fl, _cat([z, tcol(tt) if spec.f_time_variant else None, ut]))
-    h = spec.dt
+    h = float(np.float32(spec.dt))
     if spec.integrator == O.INT_RK4:
         k1 = rhs(t, x)
         k2 = rhs(t + h / 2, x + h * k1 / 2)
@@ -82,7 +83,7 @@ def rollout(spec, theta, u):
         x, y = step(spec, fl, gl, x, t, u[:, k])
         ys.append(y)
         if spec.has_time:
-            t = t + spec.dt
+            t = t + float(np.float32(spec.dt))
     return torch.stack(ys, 1)
 
 
@@ -104,7 +105,7 @@ def closedloop(cspec, mspec, theta_c, theta_m, refs, noise=None):
             y = y + noise[:, k]
         ys.append(y)
         if cspec.has_time:
-            tc += cspec.dt
+            tc += float(np.float32(cspec.dt))
         if mspec.has_time:
-            tm += mspec.dt
+            tm += float(np.float32(mspec.dt))
     return torch.stack(ys, 1)
