@@ -83,3 +83,41 @@ def closedloop_fwd(cspec: NodeSpec, mspec: NodeSpec, theta_c, theta_m, refs, noi
                              _ptr(us), _ptr(tape), ckpt_every, B, Tr, _stream())
     L.check(rc, "cc_closedloop_fwd")
     return yhat, us, tape
+
+
+def rollout_bwd(spec: NodeSpec, theta, u, tape, ybar, x0=None, *, ckpt_every=1, want_ubar=False):
+    """VJP of rollout_fwd: ybar[B,T+1,O] -> theta_bar[P] (and ubar[B,T,I])."""
+    L = _lib.lib()
+    m = spec.to_c()
+    B, T, I = u.shape
+    theta = _check(theta, "theta", (spec.n_params(),))
+    u = _check(u, "u")
+    x0 = _check(x0, "x0", (B, spec.state_dim))
+    ybar = _check(ybar, "ybar", (B, T + 1, spec.output_dim))
+    nws = L.cc_rollout_workspace_bytes(C.byref(m), B, T, ckpt_every)
+    ws = torch.empty(max(nws // 4, 1), device=u.device, dtype=torch.float32)
+    tb = torch.empty(spec.n_params(), device=u.device, dtype=torch.float32)
+    ub = torch.empty_like(u) if want_ubar else None
+    rc = L.cc_rollout_bwd(C.byref(m), _ptr(theta), _ptr(u), _ptr(x0), _ptr(tape), ckpt_every, _ptr(ybar), _ptr(tb),
+                          _ptr(ub), B, T, _ptr(ws), ws.numel() * 4, _stream())
+    L.check(rc, "cc_rollout_bwd")
+    return tb, ub
+
+
+def closedloop_bwd(cspec: NodeSpec, mspec: NodeSpec, theta_c, theta_m, refs, tape, ybar, noise=None, *, ckpt_every=1):
+    """VJP of closedloop_fwd w.r.t. the controller parameters: ybar[B,Tr,O] -> theta_c_bar[P_c]."""
+    L = _lib.lib()
+    c, m = cspec.to_c(), mspec.to_c()
+    B, Tr, R = refs.shape
+    theta_c = _check(theta_c, "theta_c", (cspec.n_params(),))
+    theta_m = _check(theta_m, "theta_m", (mspec.n_params(),))
+    refs = _check(refs, "refs")
+    noise = _check(noise, "noise", (B, Tr, mspec.output_dim))
+    ybar = _check(ybar, "ybar", (B, Tr, mspec.output_dim))
+    nws = L.cc_closedloop_workspace_bytes(C.byref(c), C.byref(m), B, Tr, ckpt_every)
+    ws = torch.empty(max(nws // 4, 1), device=refs.device, dtype=torch.float32)
+    tb = torch.empty(cspec.n_params(), device=refs.device, dtype=torch.float32)
+    rc = L.cc_closedloop_bwd(C.byref(c), C.byref(m), _ptr(theta_c), _ptr(theta_m), _ptr(refs), _ptr(noise), _ptr(tape),
+                             ckpt_every, _ptr(ybar), _ptr(tb), B, Tr, _ptr(ws), ws.numel() * 4, _stream())
+    L.check(rc, "cc_closedloop_bwd")
+    return tb

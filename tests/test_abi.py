@@ -1,0 +1,70 @@
+"""The C-ABI library loads and exports every symbol include/cc_b200.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "cc_b200.h")
+LIB = os.path.join(ROOT, "chain_control_b200", "csrc", "libccb200.so")
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cc_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_the_hot_path():
+    fns = declared_functions()
+    for f in ["cc_rollout_fwd", "cc_rollout_bwd", "cc_closedloop_fwd", "cc_closedloop_bwd", "cc_param_count",
+              "cc_last_error", "cc_rollout_workspace_bytes", "cc_closedloop_workspace_bytes",
+              "cc_rollout_tape_bytes", "cc_closedloop_tape_bytes", "cc_mse_value_and_cotangent"]:
+        assert f in fns
+
+
+@pytest.mark.skipif(not os.path.exists(LIB), reason="libccb200.so not built (run __graft_entry__.build())")
+def test_library_exports_every_declared_symbol():
+    out = subprocess.run(["nm", "-D", "--defined-only", LIB], capture_output=True, text=True, check=True).stdout
+    exported = set(line.split()[-1] for line in out.splitlines() if line.strip())
+    missing = [f for f in declared_functions() if f not in exported]
+    assert not missing, missing
+
+
+def test_struct_layout_matches_header():
+    from chain_control_b200.arch import CC_MAX_LAYERS, CcMlp, CcModule
+
+    assert CC_MAX_LAYERS == int(re.search(r"#define CC_MAX_LAYERS (\d+)", open(HEADER).read()).group(1))
+    assert ctypes.sizeof(CcMlp) == 4 * (1 + CC_MAX_LAYERS + 1 + 3)
+    assert ctypes.sizeof(CcModule) == 4 * 3 + 2 * ctypes.sizeof(CcMlp) + 4 * 6 + 4 * 3
+
+
+def test_emulated_library_has_same_abi():
+    import emu_lib
+
+    L = emu_lib.emu()
+    assert L.cc_abi_version() == 1
+    from ccspecs import model_variants
+    from cchelpers import conv
+
+    spec = conv(model_variants()["compact_s50_d0"])
+    m = spec.to_c()
+    assert L.cc_param_count(ctypes.byref(m)) == spec.n_params() == 2651
+    assert L.cc_module_supported(ctypes.byref(m), 1) == 0
+
+
+def test_unsupported_architectures_fail_loudly():
+    import emu_lib
+    from chain_control_b200 import arch as A
+
+    L = emu_lib.emu()
+    bad = A.make_node_spec(5, 1, 1, 0.01, f_depth=0)
+    bad.f.act_final = 7  # unknown activation
+    m = bad.to_c()
+    assert L.cc_module_supported(ctypes.byref(m), 0) != 0
+    assert "activation" in L.last_error()
+    huge = A.make_node_spec(512, 1, 1, 0.01, f_width=512, f_depth=2)  # weights do not fit in smem
+    m = huge.to_c()
+    assert L.cc_module_supported(ctypes.byref(m), 0) == -2

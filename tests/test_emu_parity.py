@@ -1,0 +1,92 @@
+"""CPU (no GPU): the device code of chain_control_b200/csrc compiled against the fiber emulation in
+tests/emu, called through the same C ABI, compared with the oracle.  Catches indexing / barrier /
+layout errors before any GPU time is spent.  Sizes are tiny because every CUDA thread is a fiber."""
+import numpy as np
+import pytest
+
+import emu_lib as E
+from cchelpers import TOL_GRAD, TOL_STATE, conv, l2rel, normwise
+from ccspecs import controller_variants, model_variants
+from oracle import np_oracle as O
+
+
+def _u(B, T, I, seed=0):
+    return np.random.default_rng(seed).uniform(-1, 1, size=(B, T, I)).astype(np.float32)
+
+
+@pytest.mark.parametrize("name", list(model_variants()))
+def test_emu_rollout_fwd_bwd(name):
+    spec = model_variants()[name]
+    B, T = 7, 21  # ragged: not a multiple of the 4-trajectory thread tile nor of the 16-step I/O chunk
+    theta = O.init_params(spec, 1).astype(np.float32)
+    u = _u(B, T, spec.input_dim)
+    x0 = (0.1 * np.random.default_rng(3).normal(size=(B, spec.state_dim))).astype(np.float32)
+    ybar = np.random.default_rng(5).normal(size=(B, T + 1, spec.output_dim)).astype(np.float32)
+    y64, xs = O.rollout_fwd(spec, theta, u, x0=x0)
+    tb64, ub64 = O.rollout_bwd(spec, theta, u, ybar, x0=x0)
+    y, tb, ub = E.np_rollout_bwd(E.emu(), conv(spec), theta, u, ybar, x0)
+    assert normwise(y, y64) < TOL_STATE
+    assert l2rel(tb, tb64) < TOL_GRAD
+    assert l2rel(ub, ub64) < TOL_GRAD
+    _, xf, _ = E.np_rollout_fwd(E.emu(), conv(spec), theta, u, x0)
+    assert normwise(xf, xs[:, -1]) < TOL_STATE
+
+
+@pytest.mark.parametrize("cname", list(controller_variants()))
+@pytest.mark.parametrize("mname", ["compact_s50_d0", "full_s5_w10_d2", "full_s1_tv"])
+def test_emu_closedloop_fwd_bwd(cname, mname):
+    mspec, cspec = model_variants()[mname], controller_variants()[cname]
+    B, Tr = 6, 19
+    thc, thm = O.init_params(cspec, 2).astype(np.float32), O.init_params(mspec, 1).astype(np.float32)
+    refs = 3 * _u(B, Tr, 1)
+    noise = (0.02 * np.random.default_rng(1).normal(size=(B, Tr, 1))).astype(np.float32)
+    ybar = np.random.default_rng(6).normal(size=(B, Tr, 1)).astype(np.float32)
+    y64, us64 = O.closedloop_fwd(cspec, mspec, thc, thm, refs, noise)
+    tb64 = O.closedloop_bwd(cspec, mspec, thc, thm, refs, ybar, noise)
+    yhat, us, _ = E.np_closedloop_fwd(E.emu(), conv(cspec), conv(mspec), thc, thm, refs, noise)
+    assert normwise(yhat, y64) < TOL_STATE
+    assert normwise(us, us64) < TOL_STATE
+    _, tb = E.np_closedloop_bwd(E.emu(), conv(cspec), conv(mspec), thc, thm, refs, ybar, noise)
+    assert l2rel(tb, tb64) < TOL_GRAD
+
+
+def test_emu_edge_cases():
+    L = E.emu()
+    spec = model_variants()["full_s5_w10_d2"]
+    theta = O.init_params(spec, 1).astype(np.float32)
+    # T = 0: only y0
+    y, xf, _ = E.np_rollout_fwd(L, conv(spec), theta, np.zeros((3, 0, 1), np.float32))
+    y64, _ = O.rollout_fwd(spec, theta, np.zeros((3, 0, 1)))
+    np.testing.assert_allclose(y, y64, rtol=1e-6, atol=1e-7)
+    # B = 1, T = exactly one I/O chunk, and one chunk + 1
+    for T in (16, 17):
+        u = _u(1, T, 1, seed=T)
+        y, _, _ = E.np_rollout_fwd(L, conv(spec), theta, u)
+        assert normwise(y, O.rollout_fwd(spec, theta, u)[0]) < TOL_STATE
+    # two tiles with a ragged tail (forces more than one CTA)
+    import os
+    os.environ["CC_B200_BT"] = "4"
+    try:
+        u = _u(6, 9, 1, seed=4)
+        ybar = np.random.default_rng(5).normal(size=(6, 10, 1)).astype(np.float32)
+        y, tb, ub = E.np_rollout_bwd(L, conv(spec), theta, u, ybar)
+        tb64, ub64 = O.rollout_bwd(spec, theta, u, ybar)
+        assert normwise(y, O.rollout_fwd(spec, theta, u)[0]) < TOL_STATE
+        assert l2rel(tb, tb64) < TOL_GRAD and l2rel(ub, ub64) < TOL_GRAD
+    finally:
+        del os.environ["CC_B200_BT"]
+
+
+def test_emu_mse_value_and_cotangent():
+    import ctypes as C
+
+    L = E.emu()
+    rng = np.random.default_rng(0)
+    y, yhat = rng.normal(size=5000).astype(np.float32), rng.normal(size=5000).astype(np.float32)
+    ybar = np.empty_like(y)
+    part = np.zeros(512, np.float32)
+    rc = L.cc_mse_value_and_cotangent(y.ctypes.data, yhat.ctypes.data, ybar.ctypes.data, part.ctypes.data, y.size,
+                                      C.c_float(1.0 / y.size), None)
+    L.check(rc, "mse")
+    assert abs(part[0] - O.mse(y.astype(np.float64), yhat.astype(np.float64))) < 1e-6
+    np.testing.assert_allclose(ybar, O.mse_cotangent(y, yhat), rtol=1e-6, atol=1e-9)

@@ -1,0 +1,164 @@
+"""GPU parity tests proper (-m gpu): the CUDA path, called through the C ABI (chain_control_b200.ops is a
+thin ctypes wrapper), against the oracle on the same seeded inputs, plus size-independent properties at
+BASELINE.json's full sizes.  Tolerances (written here, from BASELINE.json north_star):
+  outputs/states: normwise 1e-5 (per-trajectory max-abs error / max-abs value), fp32 vs the fp64 oracle
+  gradients:      L2-normwise 1e-4
+"""
+import os
+
+import numpy as np
+import pytest
+
+from cchelpers import TOL_GRAD, TOL_STATE, conv, l2rel, normwise
+from ccspecs import controller_variants, model_variants
+from oracle import c_oracle as CO
+from oracle import np_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def T_():
+    import torch
+
+    return lambda a: torch.tensor(np.asarray(a, np.float32), device="cuda")
+
+
+def _u(B, T, I, seed=0):
+    return np.random.default_rng(seed).uniform(-1, 1, size=(B, T, I)).astype(np.float32)
+
+
+@pytest.mark.parametrize("name", list(model_variants()))
+def test_rollout_fwd_bwd_vs_oracle(name, T_):
+    from chain_control_b200 import ops
+
+    spec = model_variants()[name]
+    B, T = 301, 203
+    theta = O.init_params(spec, 1).astype(np.float32)
+    u = _u(B, T, spec.input_dim)
+    x0 = (0.1 * np.random.default_rng(3).normal(size=(B, spec.state_dim))).astype(np.float32)
+    ybar = np.random.default_rng(5).normal(size=(B, T + 1, spec.output_dim)).astype(np.float32)
+    ref = CO.rollout(spec, theta, u, x0=x0, ybar=ybar, want_ubar=True, dtype=np.float64)
+    y, xf, tape = ops.rollout_fwd(conv(spec), T_(theta), T_(u), T_(x0), want_tape=True, want_x_final=True)
+    tb, ub = ops.rollout_bwd(conv(spec), T_(theta), T_(u), tape, T_(ybar), T_(x0), want_ubar=True)
+    assert normwise(y.cpu().numpy(), ref["y"]) < TOL_STATE
+    assert l2rel(tb.cpu().numpy(), ref["theta_bar"]) < TOL_GRAD
+    # relu kinks make the input cotangent of deep relu nets sensitive to fp32 mask flips: 5x slack
+    assert l2rel(ub.cpu().numpy(), ref["ubar"]) < 5 * TOL_GRAD
+
+
+@pytest.mark.parametrize("cname", list(controller_variants()))
+@pytest.mark.parametrize("mname", ["compact_s50_d0", "full_s5_w10_d2", "full_s1_tv"])
+def test_closedloop_fwd_bwd_vs_oracle(cname, mname, T_):
+    from chain_control_b200 import ops
+
+    mspec, cspec = model_variants()[mname], controller_variants()[cname]
+    B, Tr = 290, 201
+    thc, thm = O.init_params(cspec, 2).astype(np.float32), O.init_params(mspec, 1).astype(np.float32)
+    refs = 3 * _u(B, Tr, 1)
+    noise = (0.02 * np.random.default_rng(1).normal(size=(B, Tr, 1))).astype(np.float32)
+    ybar = np.random.default_rng(6).normal(size=(B, Tr, 1)).astype(np.float32)
+    ref = CO.closedloop(cspec, mspec, thc, thm, refs, noise, ybar=ybar, dtype=np.float64)
+    yh, us, tape = ops.closedloop_fwd(conv(cspec), conv(mspec), T_(thc), T_(thm), T_(refs), T_(noise), want_tape=True,
+                                      want_u=True)
+    tb = ops.closedloop_bwd(conv(cspec), conv(mspec), T_(thc), T_(thm), T_(refs), tape, T_(ybar), T_(noise))
+    assert normwise(yh.cpu().numpy(), ref["yhat"]) < TOL_STATE
+    assert normwise(us.cpu().numpy(), ref["u"]) < TOL_STATE
+    assert l2rel(tb.cpu().numpy(), ref["theta_c_bar"]) < TOL_GRAD
+
+
+def test_cfg1_model_trainer_shapes(T_):
+    """configs[0]: 8 trajectories x 1000 steps (outputs 1001), notebook-3 model, T=1000 horizon."""
+    from chain_control_b200 import ops
+
+    spec = model_variants()["compact_s50_d0"]
+    theta = O.init_params(spec, 1).astype(np.float32)
+    u = _u(8, 1000, 1)
+    targets = np.random.default_rng(2).normal(size=(8, 1001, 1)).astype(np.float32)
+    ref = CO.rollout(spec, theta, u, targets=targets, dtype=np.float64)
+    y, _, tape = ops.rollout_fwd(conv(spec), T_(theta), T_(u), want_tape=True)
+    ybar = O.mse_cotangent(targets, y.cpu().numpy())
+    tb, _ = ops.rollout_bwd(conv(spec), T_(theta), T_(u), tape, T_(ybar))
+    assert tuple(y.shape) == (8, 1001, 1)
+    assert normwise(y.cpu().numpy(), ref["y"]) < TOL_STATE
+    assert l2rel(tb.cpu().numpy(), ref["theta_bar"]) < TOL_GRAD
+
+
+def test_cfg2_controller_trainer_64x1001(T_):
+    """configs[1]: closed-loop BPTT over 64 reference trajectories x 1001 steps (mse(refs, yhat))."""
+    from chain_control_b200 import ops
+
+    mspec, cspec = model_variants()["compact_s50_d0"], controller_variants()["compact_s5_d0"]
+    thc = O.init_params(cspec, 2).astype(np.float32)
+    thm = O.init_params(mspec, 1, stable=True).astype(np.float32)
+    rng = np.random.default_rng(0)
+    refs = (np.sign(rng.normal(size=(64, 1, 1))) * rng.uniform(0, 3, size=(64, 1, 1)) * np.ones((64, 1001, 1))).astype(np.float32)
+    ref = CO.closedloop(cspec, mspec, thc, thm, refs, mse_loss=True, dtype=np.float64)
+    yh, _, tape = ops.closedloop_fwd(conv(cspec), conv(mspec), T_(thc), T_(thm), T_(refs), want_tape=True)
+    ybar = O.mse_cotangent(refs, yh.cpu().numpy())
+    tb = ops.closedloop_bwd(conv(cspec), conv(mspec), T_(thc), T_(thm), T_(refs), tape, T_(ybar))
+    assert normwise(yh.cpu().numpy(), ref["yhat"]) < TOL_STATE
+    assert l2rel(tb.cpu().numpy(), ref["theta_c_bar"]) < TOL_GRAD
+
+
+def test_full_size_properties(T_):
+    """B = 65,536 (configs[3]) is too big for the oracle; check size-independent properties instead."""
+    import torch
+
+    from chain_control_b200 import ops
+
+    spec = conv(model_variants()["compact_s50_d0"])
+    theta = T_(O.init_params(model_variants()["compact_s50_d0"], 1, stable=True))
+    B, T = 65536, 128
+    u = torch.rand(B, T, 1, device="cuda") * 2 - 1
+    y, _, tape = ops.rollout_fwd(spec, theta, u, want_tape=True)
+    # 1. batch independence: any sub-batch alone reproduces its rows (different tiling of the batch)
+    idx = torch.arange(1000, 1300, device="cuda")
+    ys, _, _ = ops.rollout_fwd(spec, theta, u[idx].contiguous())
+    assert normwise(ys.cpu().numpy(), y[idx].cpu().numpy()) < 2e-6
+    # 2. determinism: reruns are bit-identical (fixed reduction order)
+    ybar = torch.randn(B, T + 1, 1, device="cuda") / B
+    tb1, _ = ops.rollout_bwd(spec, theta, u, tape, ybar)
+    tb2, _ = ops.rollout_bwd(spec, theta, u, tape, ybar)
+    assert torch.equal(tb1, tb2)
+    # 3. the VJP is linear in the cotangent, and additive over batch shards (what the NCCL allreduce relies on)
+    tb3, _ = ops.rollout_bwd(spec, theta, u, tape, 2 * ybar)
+    assert l2rel(tb3.cpu().numpy(), 2 * tb1.cpu().numpy()) < 1e-6
+    h = B // 2
+    ya, _, ta = ops.rollout_fwd(spec, theta, u[:h].contiguous(), want_tape=True)
+    yb, _, tb_ = ops.rollout_fwd(spec, theta, u[h:].contiguous(), want_tape=True)
+    ga, _ = ops.rollout_bwd(spec, theta, u[:h].contiguous(), ta, ybar[:h].contiguous())
+    gb, _ = ops.rollout_bwd(spec, theta, u[h:].contiguous(), tb_, ybar[h:].contiguous())
+    assert l2rel((ga + gb).cpu().numpy(), tb1.cpu().numpy()) < 1e-5
+    # 4. tile-size independence (CC_B200_BT override = a different CTA decomposition)
+    os.environ["CC_B200_BT"] = "64"
+    try:
+        y64, _, _ = ops.rollout_fwd(spec, theta, u[:4096].contiguous())
+    finally:
+        del os.environ["CC_B200_BT"]
+    assert normwise(y64.cpu().numpy(), y[:4096].cpu().numpy()) < 2e-6
+
+
+def test_zero_controller_equals_open_loop(T_):
+    import torch
+
+    from chain_control_b200 import ops
+
+    mspec, cspec = model_variants()["full_s5_w10_d2"], controller_variants()["compact_s5_d0"]
+    thm = T_(O.init_params(mspec, 1))
+    thc = torch.zeros(cspec.n_params(), device="cuda")
+    refs = T_(_u(33, 77, 1))
+    yh, us, _ = ops.closedloop_fwd(conv(cspec), conv(mspec), thc, thm, refs, want_u=True)
+    y, _, _ = ops.rollout_fwd(conv(mspec), thm, torch.zeros(33, 77, 1, device="cuda"))
+    assert float(us.abs().max()) == 0.0
+    np.testing.assert_allclose(yh.cpu().numpy(), y[:, 1:].cpu().numpy(), rtol=1e-6, atol=1e-7)
+
+
+def test_product_path_has_no_cpu_fallback():
+    import torch
+
+    from chain_control_b200 import _lib, ops
+
+    spec = conv(model_variants()["full_s5_w10_d2"])
+    with pytest.raises(_lib.CcError):
+        ops.rollout_fwd(spec, torch.zeros(spec.n_params()), torch.zeros(2, 3, 1))
