@@ -31,7 +31,7 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
-constexpr int kSmemBudget = 227 * 1024;
+constexpr int kSmemBudget = 227 * 1024 - 2560;  // minus the plan copy at the head of dynamic smem
 constexpr int kMaxIO = 16;
 
 int num_sms() {
@@ -96,7 +96,7 @@ struct Alloc {
 };
 
 // fills the size-independent part of a node
-void describe_node(const CcModule* m, CcNodeDev* nd, bool trainable, int* theta_off_io) {
+void describe_node(const CcModule* m, CcNodeDev* nd, bool trainable, int TN) {
   memset(nd, 0, sizeof(*nd));
   nd->S = m->state_dim; nd->I = m->input_dim; nd->O = m->output_dim;
   nd->has_t = (m->f_time_variant || m->g_time_variant) ? 1 : 0;
@@ -122,10 +122,10 @@ void describe_node(const CcModule* m, CcNodeDev* nd, bool trainable, int* theta_
       L.in_log = mlp->sizes[l];
       L.N = mlp->sizes[l + 1];
       L.K = L.first ? nd->K0 : L.in_log + 1;
-      L.CG = ceil_div(L.N, CC_TN);
-      L.Np = CC_TN * L.CG;
-      L.CGk = ceil_div(L.K, CC_TN);
-      L.Kp = CC_TN * L.CGk;
+      L.CG = ceil_div(L.N, TN);
+      L.Np = (TN * L.CG + 3) / 4 * 4;  // row stride of Wt: keeps every LDS.128 16-byte aligned
+      L.CGk = ceil_div(L.K, TN);
+      L.Kp = (TN * L.CGk + 3) / 4 * 4;
       L.act = l < mlp->n_layers - 1 ? mlp->act : mlp->act_final;
       L.use_t = L.first ? (w == 0 ? m->f_time_variant : m->g_time_variant) : 0;
       L.use_v = L.first ? (w == 0 ? 1 : m->g_feedthrough_u) : 0;
@@ -137,7 +137,6 @@ void describe_node(const CcModule* m, CcNodeDev* nd, bool trainable, int* theta_
     }
   }
   nd->CGs = nd->f.layer[nd->f.L - 1].CG;
-  (void)theta_off_io;
 }
 
 int max_cg(const CcNodeDev& nd, bool bwd) {
@@ -168,6 +167,7 @@ int layout(CcKParams* p, int BT, bool bwd, bool want_uout, bool want_noise, bool
   for (int n = 0; n < p->n_nodes; ++n) { const int c = max_cg(p->nd[n], bwd); if (c > cgt) cgt = c; }
   p->CGT = cgt;
   p->nthreads = (p->RG * p->CGT + 31) / 32 * 32;
+  if (p->nthreads < (BT + 31) / 32 * 32) p->nthreads = (BT + 31) / 32 * 32;  // one thread per trajectory in the I/O phases
   const int BTP = p->BTP;
   Alloc a;
   int gw = 0;
@@ -237,9 +237,10 @@ struct PlanOpts {
   bool bwd = false, want_uout = false, want_noise = false, want_ubar = false;
 };
 
-// chooses the tile size: fill all SMs, then prefer >= 8 warps per SM, then few waves
+// chooses the tile size BT.  Cost model: waves x (work per wave on one SM), with penalties for
+// idle lanes (RG*CGT not a multiple of 32) and for fewer than 8 resident warps per SM.
 int choose_tile(CcKParams* p, const PlanOpts& o) {
-  static const int cands[] = {4, 8, 16, 32, 48, 64, 80, 96, 112, 128, 160, 192, 224, 256};
+  static const int cands[] = {256, 224, 192, 160, 128, 112, 96, 80, 64, 48, 32, 16, 8, 4};
   const char* env = getenv("CC_B200_BT");
   const int forced = env ? atoi(env) : 0;
   const int sms = num_sms();
@@ -249,21 +250,21 @@ int choose_tile(CcKParams* p, const PlanOpts& o) {
     if (forced && c != forced) continue;
     const int fl = layout(p, c, o.bwd, o.want_uout, o.want_noise, o.want_ubar);
     const long long bytes = (long long)fl * 4;
-    if (bytes > kSmemBudget || p->nthreads > 512) continue;
+    if (bytes > kSmemBudget || p->nthreads > 320) continue;
     const int occ_smem = (int)(kSmemBudget / (bytes + 1024));
-    const int occ_thr = 1536 / p->nthreads;  // keeps >= 40 registers... conservative: regs ~ 168/thread max
-    int occ = occ_smem < occ_thr ? occ_smem : occ_thr;
-    const int occ_regs = 65536 / (p->nthreads * 168);
-    if (occ_regs < occ) occ = occ_regs;
+    const int occ_regs = 65536 / (p->nthreads * 200);
+    int occ = occ_smem < occ_regs ? occ_smem : occ_regs;
     if (occ < 1) occ = 1;
+    if (occ > 8) occ = 8;
     const long long tiles = (p->B + c - 1) / c;
     const long long per_sm = (tiles + sms - 1) / sms;
     const int oe = (int)(per_sm < occ ? per_sm : occ);
     const long long waves = (tiles + (long long)sms * occ - 1) / ((long long)sms * occ);
+    const double lane_eff = (double)(p->RG * p->CGT) / p->nthreads;
     const double warps = (double)oe * p->nthreads / 32.0;
-    const double thr = warps >= 8.0 ? 1.0 : warps / 8.0;
+    const double thr = (warps >= 8.0 ? 1.0 : warps / 8.0) * lane_eff;
     const double cost = (double)waves * c * oe / thr;
-    if (cost < best * 0.999) { best = cost; best_bt = c; }
+    if (cost < best * 0.98) { best = cost; best_bt = c; }
   }
   if (!best_bt) return 0;
   layout(p, best_bt, o.bwd, o.want_uout, o.want_noise, o.want_ubar);
@@ -276,9 +277,31 @@ int make_plan(const CcModule* const* mods, int n_nodes, long long B, int T, cons
   p->B = B;
   p->T = T;
   p->Bpad = (B + 255) / 256 * 256;
+  // thread-tile width: the one that wastes fewer padded columns, weighted by layer work
+  int tn = 8;
+  {
+    const char* env = getenv("CC_B200_TN");
+    if (env && (atoi(env) == 8 || atoi(env) == 10)) tn = atoi(env);
+    else {
+      double w8 = 0, w10 = 0;
+      for (int n = 0; n < n_nodes; ++n) {
+        const CcMlp* mlps[2] = {&mods[n]->f, &mods[n]->g};
+        for (int w = 0; w < 2; ++w)
+          for (int l = 0; l < mlps[w]->n_layers; ++l) {
+            const int N = mlps[w]->sizes[l + 1], K = mlps[w]->sizes[l] + 1;
+            if (N <= CC_MAX_SKINNY) continue;
+            const double reps = w == 0 ? (mods[n]->integrator == CC_INT_RK4 ? 4 : 1) : 1;
+            w8 += reps * K * ceil_div(N, 8) * 8;
+            w10 += reps * K * ceil_div(N, 10) * 10;
+          }
+      }
+      tn = w10 < w8 ? 10 : 8;
+    }
+  }
+  p->TN = tn;
   for (int n = 0; n < n_nodes; ++n) {
     const bool trainable = o.bwd && (n_nodes == 1 || n == 0);
-    describe_node(mods[n], &p->nd[n], trainable, nullptr);
+    describe_node(mods[n], &p->nd[n], trainable, tn);
   }
   if (n_nodes == 2) {
     p->R = mods[0]->input_dim - mods[1]->output_dim;
@@ -289,7 +312,11 @@ int make_plan(const CcModule* const* mods, int n_nodes, long long B, int T, cons
     p->nd[0].tape_row = 0;
     p->tape_rows = p->nd[0].S;
   }
-  if (!choose_tile(p, o)) return fail(CC_ERR_UNSUPPORTED, "architecture does not fit in %d KB of shared memory per CTA (weights must be smem-resident in this version)", kSmemBudget / 1024);
+  const int chosen = choose_tile(p, o);
+  if (chosen && getenv("CC_B200_VERBOSE"))
+    fprintf(stderr, "[ccb200] plan: nodes=%d bwd=%d B=%lld T=%d TN=%d BT=%d BTP=%d RG=%d CGT=%d threads=%d smem=%d B tiles=%lld\n",
+            n_nodes, (int)o.bwd, B, T, p->TN, p->BT, p->BTP, p->RG, p->CGT, p->nthreads, p->smem_floats * 4, (B + p->BT - 1) / p->BT);
+  if (!chosen) return fail(CC_ERR_UNSUPPORTED, "architecture does not fit in %d KB of shared memory per CTA (weights must be smem-resident in this version)", kSmemBudget / 1024);
   return CC_OK;
 }
 
@@ -302,20 +329,23 @@ int make_plan(const CcModule* const* mods, int n_nodes, long long B, int T, cons
 #endif
 
 template <class Kern>
-int launch(Kern kern, const CcKParams& p, long long grid, void* stream) {
+int launch1(Kern kern, const CcKParams& p, long long grid, void* stream) {
   g_launches.fetch_add(1);
 #ifdef CC_EMULATE
   (void)stream;
-  ccemu::launch((int)grid, p.nthreads, (size_t)p.smem_floats * 4, [&]() { kern(p); });
+  ccemu::launch((int)grid, p.nthreads, ((size_t)p.smem_floats + CC_PARAM_FLOATS) * 4, [&]() { kern(p); });
   return CC_OK;
 #else
-  const size_t smem = (size_t)p.smem_floats * 4;
+  const size_t smem = ((size_t)p.smem_floats + CC_PARAM_FLOATS) * 4;
   CC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)grid, p.nthreads, smem, (cudaStream_t)stream>>>(p);
   CC_CUDA_OK(cudaGetLastError());
   return CC_OK;
 #endif
 }
+
+#define CC_LAUNCH_TN(kern, p, grid, stream) \
+  ((p).TN == 10 ? launch1(kern<10>, p, grid, stream) : launch1(kern<8>, p, grid, stream))
 
 int n_ckpt_of(int T, int every) { return (T + every - 1) / every; }
 
@@ -370,7 +400,7 @@ int32_t cc_rollout_fwd(const CcModule* m, const float* theta, const float* u, co
   p.tape = (float*)tape;
   p.ckpt_every = tape ? ckpt_every : 1;
   p.n_ckpt = n_ckpt_of(T, p.ckpt_every);
-  return launch(cc_rollout_fwd_kernel, p, (B + p.BT - 1) / p.BT, stream);
+  return CC_LAUNCH_TN(cc_rollout_fwd_kernel, p, (B + p.BT - 1) / p.BT, stream);
 }
 
 int32_t cc_closedloop_fwd(const CcModule* c, const CcModule* m, const float* theta_c, const float* theta_m,
@@ -399,7 +429,7 @@ int32_t cc_closedloop_fwd(const CcModule* c, const CcModule* m, const float* the
   p.tape = (float*)tape;
   p.ckpt_every = tape ? ckpt_every : 1;
   p.n_ckpt = n_ckpt_of(Tr, p.ckpt_every);
-  return launch(cc_rollout_fwd_kernel, p, (B + p.BT - 1) / p.BT, stream);
+  return CC_LAUNCH_TN(cc_rollout_fwd_kernel, p, (B + p.BT - 1) / p.BT, stream);
 }
 
 #include "cc_abi_bwd.inc"

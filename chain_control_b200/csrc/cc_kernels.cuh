@@ -16,9 +16,14 @@
 
 #ifndef CC_EMULATE
 #define CC_DEV __device__ __forceinline__
+#define CC_DEV_NOINLINE __device__ __noinline__
+#define CC_GRID_CONSTANT __grid_constant__
 #else
 #define CC_DEV static inline
+#define CC_DEV_NOINLINE static
+#define CC_GRID_CONSTANT
 #endif
+#define CC_TILE float (&)[CC_TM][TN]
 
 // ------------------------------------------------------------------------------------------------
 // elementwise pieces
@@ -96,57 +101,106 @@ CC_DEV void cc_stage_mlp(const CcNodeDev& nd, const CcMlpDev& mlp, const float* 
 
 // ------------------------------------------------------------------------------------------------
 // register-tiled SGEMM out of shared memory:  acc[i][j] += sum_k A[k][4rg+i] * Bm[k][col(j)]
-//   col(j) = 4cg + j (j<4) | 4CG + 4cg + (j-4)   -> every LDS.128 of a warp is conflict-free
+//   col(j) = 4cg + j (j<4) | 4CG + 4cg + (j-4) (j<8) | 8CG + 2cg + (j-8) (TN == 10)
+// so that every LDS.128 / LDS.64 of a warp reads one contiguous, conflict-free span.  The operands
+// of step k+1 are fetched while the FMAs of step k issue (register double buffering).
 // ------------------------------------------------------------------------------------------------
-CC_DEV void cc_gemm_tile(const float* A, int lda, const float* Bm, int ldb, int K, int cgoff,
-                         float (&acc)[CC_TM][CC_TN]) {
-#pragma unroll 4
-  for (int k = 0; k < K; ++k) {
-    const float4 a = *reinterpret_cast<const float4*>(A + k * lda);
-    const float4 b0 = *reinterpret_cast<const float4*>(Bm + k * ldb);
-    const float4 b1 = *reinterpret_cast<const float4*>(Bm + k * ldb + cgoff);
-    const float av[4] = {a.x, a.y, a.z, a.w};
-    const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-    for (int i = 0; i < CC_TM; ++i)
-#pragma unroll
-      for (int j = 0; j < CC_TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+template <int TN>
+struct CcFrag {
+  float4 a, b0, b1;
+  float b2x, b2y;
+};
+#ifdef CC_EMULATE
+#define CC_ASSERT_ALIGNED(ptr, n)                                                          \
+  do {                                                                                     \
+    if (reinterpret_cast<uintptr_t>(ptr) % (n)) {                                          \
+      fprintf(stderr, "ccemu: misaligned %d-byte access at %s:%d\n", (n), __FILE__, __LINE__); \
+      abort();                                                                             \
+    }                                                                                      \
+  } while (0)
+#else
+#define CC_ASSERT_ALIGNED(ptr, n)
+#endif
+template <int TN>
+CC_DEV void cc_frag_load(CcFrag<TN>& f, const float* A, const float* B0, const float* B1, const float* B2) {
+  CC_ASSERT_ALIGNED(A, 16); CC_ASSERT_ALIGNED(B0, 16); CC_ASSERT_ALIGNED(B1, 16);
+  if (TN == 10) CC_ASSERT_ALIGNED(B2, 8);
+  f.a = *reinterpret_cast<const float4*>(A);
+  f.b0 = *reinterpret_cast<const float4*>(B0);
+  f.b1 = *reinterpret_cast<const float4*>(B1);
+  if (TN == 10) {
+    f.b2x = B2[0];
+    f.b2y = B2[1];
   }
 }
-
-CC_DEV int cc_col(int CG, int cg, int j) { return j < 4 ? 4 * cg + j : 4 * CG + 4 * cg + (j - 4); }
-
-CC_DEV void cc_zero_tile(float (&t)[CC_TM][CC_TN]) {
+template <int TN>
+CC_DEV void cc_frag_fma(const CcFrag<TN>& f, float (&acc)[CC_TM][TN]) {
+  const float av[4] = {f.a.x, f.a.y, f.a.z, f.a.w};
+  float bv[10] = {f.b0.x, f.b0.y, f.b0.z, f.b0.w, f.b1.x, f.b1.y, f.b1.z, f.b1.w, 0.f, 0.f};
+  if (TN == 10) { bv[8] = f.b2x; bv[9] = f.b2y; }
 #pragma unroll
   for (int i = 0; i < CC_TM; ++i)
 #pragma unroll
-    for (int j = 0; j < CC_TN; ++j) t[i][j] = 0.f;
+    for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+}
+// A -> &A[0][4rg]; Bm -> &Bm[0][0]; CG = column groups of Bm; cg = this thread's group
+template <int TN>
+CC_DEV void cc_gemm_tile(const float* A, int lda, const float* Bm, int ldb, int K, int CG, int cg,
+                         float (&acc)[CC_TM][TN]) {
+  const float* B0 = Bm + 4 * cg;
+  const float* B1 = Bm + 4 * CG + 4 * cg;
+  const float* B2 = Bm + 8 * CG + 2 * cg;
+  CcFrag<TN> cur, nxt;
+  cc_frag_load<TN>(cur, A, B0, B1, B2);
+#pragma unroll 2
+  for (int k = 1; k < K; ++k) {
+    cc_frag_load<TN>(nxt, A + k * lda, B0 + k * ldb, B1 + k * ldb, B2 + k * ldb);
+    cc_frag_fma<TN>(cur, acc);
+    cur = nxt;
+  }
+  cc_frag_fma<TN>(cur, acc);
+}
+
+template <int TN>
+CC_DEV int cc_col(int CG, int cg, int j) {
+  return j < 4 ? 4 * cg + j : (j < 8 ? 4 * CG + 4 * cg + (j - 4) : 8 * CG + 2 * cg + (j - 8));
+}
+
+template <int TN>
+CC_DEV void cc_zero_tile(float (&t)[CC_TM][TN]) {
+#pragma unroll
+  for (int i = 0; i < CC_TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) t[i][j] = 0.f;
 }
 
 // tile <-> feature-major buffer rows [n][BTP]
-CC_DEV void cc_load_tile(const float* buf, int BTP, int N, int CG, const CcThread& th, float (&t)[CC_TM][CC_TN]) {
+template <int TN>
+CC_DEV void cc_load_tile(const float* buf, int BTP, int N, int CG, const CcThread& th, float (&t)[CC_TM][TN]) {
 #pragma unroll
-  for (int j = 0; j < CC_TN; ++j) {
-    const int n = cc_col(CG, th.cg, j);
+  for (int j = 0; j < TN; ++j) {
+    const int n = cc_col<TN>(CG, th.cg, j);
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (n < N) v = *reinterpret_cast<const float4*>(buf + n * BTP + 4 * th.rg);
+    if (n < N) { CC_ASSERT_ALIGNED(buf + n * BTP + 4 * th.rg, 16); v = *reinterpret_cast<const float4*>(buf + n * BTP + 4 * th.rg); }
     t[0][j] = v.x; t[1][j] = v.y; t[2][j] = v.z; t[3][j] = v.w;
   }
 }
-CC_DEV void cc_store_tile(float* buf, int BTP, int N, int CG, const CcThread& th, const float (&t)[CC_TM][CC_TN]) {
+template <int TN>
+CC_DEV void cc_store_tile(float* buf, int BTP, int N, int CG, const CcThread& th, const float (&t)[CC_TM][TN]) {
 #pragma unroll
-  for (int j = 0; j < CC_TN; ++j) {
-    const int n = cc_col(CG, th.cg, j);
+  for (int j = 0; j < TN; ++j) {
+    const int n = cc_col<TN>(CG, th.cg, j);
     if (n < N) *reinterpret_cast<float4*>(buf + n * BTP + 4 * th.rg) = make_float4(t[0][j], t[1][j], t[2][j], t[3][j]);
   }
 }
 
 // one layer as a tile GEMM; leaves the raw accumulators (bias included via the 1-row) in acc
+template <int TN>
 CC_DEV void cc_layer_gemm(const CcKParams& p, const CcLayerDev& L, const float* src, const float* smem,
-                          const CcThread& th, float (&acc)[CC_TM][CC_TN]) {
-  cc_zero_tile(acc);
+                          const CcThread& th, float (&acc)[CC_TM][TN]) {
+  cc_zero_tile<TN>(acc);
   if (th.rg_ok && th.cg < L.CG)
-    cc_gemm_tile(src + 4 * th.rg, p.BTP, smem + L.s_wt + 4 * th.cg, L.Np, L.K, 4 * L.CG, acc);
+    cc_gemm_tile<TN>(src + 4 * th.rg, p.BTP, smem + L.s_wt, L.Np, L.K, L.CG, th.cg, acc);
 }
 
 // split-K path for very narrow layers (N <= CC_MAX_SKINNY): every thread sums a strided slice of K
@@ -199,22 +253,23 @@ CC_DEV void cc_layer_skinny(const CcKParams& p, const CcLayerDev& L, const float
 
 // hidden layers of an MLP (all but the last): src -> hidden buffers.  returns the input buffer of
 // the last layer.  hbuf[l] overrides the hidden buffer of layer l (backward keeps them per stage).
+template <int TN>
 CC_DEV const float* cc_mlp_hidden(const CcKParams& p, const CcMlpDev& mlp, const float* src, float* smem,
                                   const int* hbuf, const CcThread& th) {
-  float acc[CC_TM][CC_TN];
+  float acc[CC_TM][TN];
   for (int l = 0; l < mlp.L - 1; ++l) {
     const CcLayerDev& L = mlp.layer[l];
     float* dst = smem + (hbuf ? hbuf[l] : L.s_out);
     if (L.N <= CC_MAX_SKINNY) {
       cc_layer_skinny(p, L, src, smem, smem + p.nd[0].s_P, dst, 1.f, th);
     } else {
-      cc_layer_gemm(p, L, src, smem, th, acc);
+      cc_layer_gemm<TN>(p, L, src, smem, th, acc);
       if (th.rg_ok && th.cg < L.CG) {
 #pragma unroll
         for (int i = 0; i < CC_TM; ++i)
 #pragma unroll
-          for (int j = 0; j < CC_TN; ++j) acc[i][j] = cc_act(L.act, acc[i][j]);
-        cc_store_tile(dst, p.BTP, L.N, L.CG, th, acc);
+          for (int j = 0; j < TN; ++j) acc[i][j] = cc_act(L.act, acc[i][j]);
+        cc_store_tile<TN>(dst, p.BTP, L.N, L.CG, th, acc);
       }
       __syncthreads();
     }
@@ -224,49 +279,52 @@ CC_DEV const float* cc_mlp_hidden(const CcKParams& p, const CcMlpDev& mlp, const
 }
 
 // readout: OUT = out_scale * g(src rows).  Ends with a barrier.
-CC_DEV void cc_readout(const CcKParams& p, const CcNodeDev& nd, const float* src, float* smem, const int* ghbuf,
+template <int TN>
+CC_DEV_NOINLINE void cc_readout(const CcKParams& p, const CcNodeDev& nd, const float* src, float* smem, const int* ghbuf,
                        const CcThread& th) {
-  const float* in = cc_mlp_hidden(p, nd.g, src, smem, ghbuf, th);
+  const float* in = cc_mlp_hidden<TN>(p, nd.g, src, smem, ghbuf, th);
   const CcLayerDev& L = nd.g.layer[nd.g.L - 1];
   float* OUT = smem + nd.s_OUT;
   if (L.N <= CC_MAX_SKINNY) {
     cc_layer_skinny(p, L, in, smem, smem + p.nd[0].s_P, OUT, nd.out_scale, th);
   } else {
-    float acc[CC_TM][CC_TN];
-    cc_layer_gemm(p, L, in, smem, th, acc);
+    float acc[CC_TM][TN];
+    cc_layer_gemm<TN>(p, L, in, smem, th, acc);
     if (th.rg_ok && th.cg < L.CG) {
 #pragma unroll
       for (int i = 0; i < CC_TM; ++i)
 #pragma unroll
-        for (int j = 0; j < CC_TN; ++j) acc[i][j] = nd.out_scale * cc_act(L.act, acc[i][j]);
-      cc_store_tile(OUT, p.BTP, L.N, L.CG, th, acc);
+        for (int j = 0; j < TN; ++j) acc[i][j] = nd.out_scale * cc_act(L.act, acc[i][j]);
+      cc_store_tile<TN>(OUT, p.BTP, L.N, L.CG, th, acc);
     }
     __syncthreads();
   }
 }
 
 // k = f(src): hidden layers to smem, last layer into registers (activation applied)
+template <int TN>
 CC_DEV void cc_rhs(const CcKParams& p, const CcNodeDev& nd, const float* src, float* smem, const int* hbuf,
-                   const CcThread& th, float (&k)[CC_TM][CC_TN]) {
-  const float* in = cc_mlp_hidden(p, nd.f, src, smem, hbuf, th);
+                   const CcThread& th, float (&k)[CC_TM][TN]) {
+  const float* in = cc_mlp_hidden<TN>(p, nd.f, src, smem, hbuf, th);
   const CcLayerDev& L = nd.f.layer[nd.f.L - 1];
-  cc_layer_gemm(p, L, in, smem, th, k);
+  cc_layer_gemm<TN>(p, L, in, smem, th, k);
   if (L.act != CC_ACT_IDENTITY) {
 #pragma unroll
     for (int i = 0; i < CC_TM; ++i)
 #pragma unroll
-      for (int j = 0; j < CC_TN; ++j) k[i][j] = cc_act(L.act, k[i][j]);
+      for (int j = 0; j < TN; ++j) k[i][j] = cc_act(L.act, k[i][j]);
   }
 }
 
 // write the node's state tile into the tape record of checkpoint `ck`
+template <int TN>
 CC_DEV void cc_tape_store(const CcKParams& p, const CcNodeDev& nd, long long tile, int ck, const CcThread& th,
-                          const float (&x)[CC_TM][CC_TN]) {
+                          const float (&x)[CC_TM][TN]) {
   float* rec = p.tape + ((long long)ck * p.tape_rows + nd.tape_row) * p.Bpad + tile * p.BT;
   if (th.rg_ok && th.cg < nd.CGs) {
 #pragma unroll
-    for (int j = 0; j < CC_TN; ++j) {
-      const int n = cc_col(nd.CGs, th.cg, j);
+    for (int j = 0; j < TN; ++j) {
+      const int n = cc_col<TN>(nd.CGs, th.cg, j);
       if (n < nd.S) *reinterpret_cast<float4*>(rec + (long long)n * p.Bpad + 4 * th.rg) = make_float4(x[0][j], x[1][j], x[2][j], x[3][j]);
     }
   }
@@ -276,17 +334,18 @@ CC_DEV void cc_tape_store(const CcKParams& p, const CcNodeDev& nd, long long til
 // On exit X holds x_next, OUT holds the readout.  `stage_bufs`: when non-null (backward recompute)
 // the stage inputs are kept in s_Z[1..3] instead of the ZA/ZB ping-pong and hidden activations /
 // k_i are kept per stage.  Ends with a barrier.
-CC_DEV void cc_node_step(const CcKParams& p, const CcNodeDev& nd, float* smem, const CcThread& th, float t,
+template <int TN>
+CC_DEV_NOINLINE void cc_node_step(const CcKParams& p, const CcNodeDev& nd, float* smem, const CcThread& th, float t,
                          bool keep, bool do_readout, bool write_tape, long long tile, int ck) {
   float* X = smem + nd.s_X;
   const float h = nd.dt;
   const bool own = th.rg_ok && th.cg < nd.CGs;
-  if (nd.pre && do_readout) cc_readout(p, nd, X, smem, keep ? nd.s_GH : nullptr, th);
-  float xr[CC_TM][CC_TN], k[CC_TM][CC_TN];
-  cc_load_tile(X, p.BTP, own ? nd.S : 0, nd.CGs, th, xr);
-  if (write_tape) cc_tape_store(p, nd, tile, ck, th, xr);
+  if (nd.pre && do_readout) cc_readout<TN>(p, nd, X, smem, keep ? nd.s_GH : nullptr, th);
+  float xr[CC_TM][TN], k[CC_TM][TN];
+  cc_load_tile<TN>(X, p.BTP, own ? nd.S : 0, nd.CGs, th, xr);
+  if (write_tape) cc_tape_store<TN>(p, nd, tile, ck, th, xr);
   if (nd.integrator == CC_INT_RK4) {
-    float ks[CC_TM][CC_TN];
+    float ks[CC_TM][TN];
     for (int s = 0; s < 4; ++s) {
       float* src;
       float* dst;
@@ -299,13 +358,13 @@ CC_DEV void cc_node_step(const CcKParams& p, const CcNodeDev& nd, float* smem, c
         // stage 3 reads ZA again, now at time t + h (ZA is idle during stage 2)
         if (s == 2 && nd.has_t && th.tid < p.BT) smem[nd.s_ZA + nd.row_t * p.BTP + th.tid] = t + h;
       }
-      cc_rhs(p, nd, src, smem, keep ? nd.s_HS[s] : nullptr, th, k);
+      cc_rhs<TN>(p, nd, src, smem, keep ? nd.s_HS[s] : nullptr, th, k);
       if (own) {
-        if (keep && nd.s_KS[s] >= 0) cc_store_tile(smem + nd.s_KS[s], p.BTP, nd.S, nd.CGs, th, k);
+        if (keep && nd.s_KS[s] >= 0) cc_store_tile<TN>(smem + nd.s_KS[s], p.BTP, nd.S, nd.CGs, th, k);
 #pragma unroll
         for (int i = 0; i < CC_TM; ++i)
 #pragma unroll
-          for (int j = 0; j < CC_TN; ++j) {
+          for (int j = 0; j < TN; ++j) {
             const float kk = k[i][j];
             if (s == 0) {
               ks[i][j] = kk;
@@ -320,22 +379,22 @@ CC_DEV void cc_node_step(const CcKParams& p, const CcNodeDev& nd, float* smem, c
               k[i][j] = xr[i][j] + h * ((1.f / 6.f) * (ks[i][j] + kk));
             }
           }
-        if (!(keep && s == 3)) cc_store_tile(dst, p.BTP, nd.S, nd.CGs, th, k);
+        if (!(keep && s == 3)) cc_store_tile<TN>(dst, p.BTP, nd.S, nd.CGs, th, k);
       }
       __syncthreads();
     }
   } else {
-    cc_rhs(p, nd, X, smem, keep ? nd.s_HS[0] : nullptr, th, k);
+    cc_rhs<TN>(p, nd, X, smem, keep ? nd.s_HS[0] : nullptr, th, k);
     if (own) {
-      if (keep && nd.s_KS[0] >= 0) cc_store_tile(smem + nd.s_KS[0], p.BTP, nd.S, nd.CGs, th, k);
+      if (keep && nd.s_KS[0] >= 0) cc_store_tile<TN>(smem + nd.s_KS[0], p.BTP, nd.S, nd.CGs, th, k);
 #pragma unroll
       for (int i = 0; i < CC_TM; ++i)
 #pragma unroll
-        for (int j = 0; j < CC_TN; ++j)
+        for (int j = 0; j < TN; ++j)
           k[i][j] = nd.integrator == CC_INT_EE ? xr[i][j] + h * k[i][j] : k[i][j];
     }
     __syncthreads();  // everyone finished reading X
-    if (own && !keep) cc_store_tile(X, p.BTP, nd.S, nd.CGs, th, k);
+    if (own && !keep) cc_store_tile<TN>(X, p.BTP, nd.S, nd.CGs, th, k);
     __syncthreads();
   }
   if (!nd.pre && do_readout) {
@@ -343,11 +402,11 @@ CC_DEV void cc_node_step(const CcKParams& p, const CcNodeDev& nd, float* smem, c
     // it), so x_next goes to ZA's state rows, whose t / v / 1 rows equal X's up to t (set by caller)
     if (keep) {
       float* XN = smem + nd.s_ZA;
-      if (own) cc_store_tile(XN, p.BTP, nd.S, nd.CGs, th, k);
+      if (own) cc_store_tile<TN>(XN, p.BTP, nd.S, nd.CGs, th, k);
       __syncthreads();
-      cc_readout(p, nd, XN, smem, nd.s_GH, th);
+      cc_readout<TN>(p, nd, XN, smem, nd.s_GH, th);
     } else {
-      cc_readout(p, nd, X, smem, nullptr, th);
+      cc_readout<TN>(p, nd, X, smem, nullptr, th);
     }
   }
 }
@@ -433,17 +492,32 @@ CC_DEV void cc_set_inputs(const CcKParams& p, const CcNodeDev& nd, float* smem, 
   }
 }
 
+// The launch plan is copied once into the head of dynamic shared memory; all device code reads it
+// from there (the node-level functions are not inlined, and a by-reference kernel parameter would
+// otherwise be spilled to local memory or read through generic loads).
+#define CC_PARAM_FLOATS ((int)((sizeof(CcKParams) + 15) / 16 * 4))
 #ifndef CC_EMULATE
-#define CC_SMEM_DECL extern __shared__ __align__(16) float cc_smem[]; float* smem = cc_smem;
+#define CC_SMEM_BASE extern __shared__ __align__(16) float cc_smem[];
 #else
-#define CC_SMEM_DECL float* smem = ccemu::st().smem;
+#define CC_SMEM_BASE float* cc_smem = ccemu::st().smem;
 #endif
+#define CC_KERNEL_PROLOGUE(gp)                                                      \
+  CC_SMEM_BASE                                                                      \
+  {                                                                                 \
+    const int* src_ = reinterpret_cast<const int*>(&(gp));                          \
+    int* dst_ = reinterpret_cast<int*>(cc_smem);                                    \
+    for (int i_ = threadIdx.x; i_ < (int)(sizeof(CcKParams) / 4); i_ += blockDim.x) dst_[i_] = src_[i_]; \
+  }                                                                                 \
+  __syncthreads();                                                                  \
+  const CcKParams& p = *reinterpret_cast<const CcKParams*>(cc_smem);                \
+  float* smem = cc_smem + CC_PARAM_FLOATS;
 
 // ------------------------------------------------------------------------------------------------
 // K1 + K3: forward rollout (open loop: n_nodes == 1; closed loop: nd[0] controller, nd[1] model)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512, 1) cc_rollout_fwd_kernel(const CcKParams p) {
-  CC_SMEM_DECL
+template <int TN>
+__global__ void __launch_bounds__(320, 1) cc_rollout_fwd_kernel(const CC_GRID_CONSTANT CcKParams gp) {
+  CC_KERNEL_PROLOGUE(gp)
   CcThread th;
   th.tid = threadIdx.x;
   th.rg = th.tid / p.CGT;
@@ -470,7 +544,7 @@ __global__ void __launch_bounds__(512, 1) cc_rollout_fwd_kernel(const CcKParams 
     __syncthreads();
   }
   // y0 = out_scale * g([x0 ; 0 ; (no feed-through for models)])     neural_ode_model.py:160-175
-  cc_readout(p, M, smem + M.s_X, smem, nullptr, th);
+  cc_readout<TN>(p, M, smem + M.s_X, smem, nullptr, th);
   if (th.tid < p.BT) {
     for (int o = 0; o < M.O; ++o) {
       const float y0 = smem[M.s_OUT + o * p.BTP + th.tid];
@@ -508,7 +582,7 @@ __global__ void __launch_bounds__(512, 1) cc_rollout_fwd_kernel(const CcKParams 
           cc_set_inputs(p, C, smem, th.tid, v, tc, false);
         }
         __syncthreads();
-        cc_node_step(p, C, smem, th, tc, false, true, wt, tile, ck);
+        cc_node_step<TN>(p, C, smem, th, tc, false, true, wt, tile, ck);
         if (th.tid < p.BT) {
           float a[16];
           for (int i = 0; i < M.I; ++i) {
@@ -518,7 +592,7 @@ __global__ void __launch_bounds__(512, 1) cc_rollout_fwd_kernel(const CcKParams 
           cc_set_inputs(p, M, smem, th.tid, a, tm, false);
         }
         __syncthreads();
-        cc_node_step(p, M, smem, th, tm, false, true, wt, tile, ck);
+        cc_node_step<TN>(p, M, smem, th, tm, false, true, wt, tile, ck);
         if (th.tid < p.BT) {
           for (int o = 0; o < M.O; ++o) {
             float y = smem[M.s_OUT + o * p.BTP + th.tid];
@@ -536,7 +610,7 @@ __global__ void __launch_bounds__(512, 1) cc_rollout_fwd_kernel(const CcKParams 
           cc_set_inputs(p, M, smem, th.tid, v, tm, false);
         }
         __syncthreads();
-        cc_node_step(p, M, smem, th, tm, false, true, wt, tile, ck);
+        cc_node_step<TN>(p, M, smem, th, tm, false, true, wt, tile, ck);
         if (th.tid < p.BT)
           for (int o = 0; o < M.O; ++o) smem[p.s_out + (kk * M.O + o) * p.BTP + th.tid] = smem[M.s_OUT + o * p.BTP + th.tid];
         if (M.has_t) tm = tm + M.dt;

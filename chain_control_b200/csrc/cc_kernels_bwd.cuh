@@ -21,7 +21,7 @@
 CC_DEV void cc_wgrad(const CcKParams& p, const CcLayerDev& L, const float* D, const float* A, float* smem,
                      const CcThread& th) {
   const int NT = (L.N + CC_WN - 1) / CC_WN;
-  const int KT = L.CGk;
+  const int KT = (L.K + CC_WK - 1) / CC_WK;
   float* G = smem + L.s_gw;
   for (int tile = th.tid; tile < NT * KT; tile += p.nthreads) {
     const int nt = tile / KT, kt = tile % KT;
@@ -72,15 +72,16 @@ CC_DEV void cc_wgrad(const CcKParams& p, const CcLayerDev& L, const float* D, co
 
 // dst[r][traj] = (sum_n W[n][r] * D[n][traj]) * act'(H[r][traj])   for r < K  (H may be null)
 // tile over (traj, r) with CGk column groups.  No trailing barrier.
+template <int TN>
 CC_DEV void cc_igrad(const CcKParams& p, const CcLayerDev& L, const float* D, float* dst, const float* H, int hact,
                      const float* smem, const CcThread& th) {
   if (!(th.rg_ok && th.cg < L.CGk)) return;
-  float acc[CC_TM][CC_TN];
-  cc_zero_tile(acc);
-  cc_gemm_tile(D + 4 * th.rg, p.BTP, smem + L.s_w + 4 * th.cg, L.Kp, L.N, 4 * L.CGk, acc);
+  float acc[CC_TM][TN];
+  cc_zero_tile<TN>(acc);
+  cc_gemm_tile<TN>(D + 4 * th.rg, p.BTP, smem + L.s_w, L.Kp, L.N, L.CGk, th.cg, acc);
 #pragma unroll
-  for (int j = 0; j < CC_TN; ++j) {
-    const int r = cc_col(L.CGk, th.cg, j);
+  for (int j = 0; j < TN; ++j) {
+    const int r = cc_col<TN>(L.CGk, th.cg, j);
     if (r < L.K) {
       float4 v = make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
       if (H && r < L.in_log) {
@@ -96,6 +97,7 @@ CC_DEV void cc_igrad(const CcKParams& p, const CcLayerDev& L, const float* D, fl
 // reverse pass of one MLP.  `cur` (DA) holds the cotangent of the last layer's PRE-activation
 // [N_L][BTP].  in0 = input buffer of layer 0; hid[l] = smem offset of layer l's hidden output.
 // Returns the buffer holding the cotangent of the MLP input (rows < K of layer 0).  Ends with a barrier.
+template <int TN>
 CC_DEV float* cc_mlp_bwd(const CcKParams& p, const CcNodeDev& nd, const CcMlpDev& mlp, float* cur, float* other,
                          const float* in0, const int* hid, float* smem, const CcThread& th) {
   for (int l = mlp.L - 1; l >= 0; --l) {
@@ -103,7 +105,7 @@ CC_DEV float* cc_mlp_bwd(const CcKParams& p, const CcNodeDev& nd, const CcMlpDev
     const float* in_l = l == 0 ? in0 : smem + hid[l - 1];
     if (nd.trainable) cc_wgrad(p, L, cur, in_l, smem, th);
     const float* H = l > 0 ? smem + hid[l - 1] : nullptr;
-    cc_igrad(p, L, cur, other, H, l > 0 ? mlp.layer[l - 1].act : CC_ACT_IDENTITY, smem, th);
+    cc_igrad<TN>(p, L, cur, other, H, l > 0 ? mlp.layer[l - 1].act : CC_ACT_IDENTITY, smem, th);
     __syncthreads();
     float* t = cur; cur = other; other = t;
   }
@@ -112,8 +114,9 @@ CC_DEV float* cc_mlp_bwd(const CcKParams& p, const CcNodeDev& nd, const CcMlpDev
 
 // cotangent of the readout: OB[O][BTP] -> adds to xrb tile (state part) and VB (input rows).
 // gsrc = the buffer g read ([x or x_next ; t ; v ; 1]).  Ends with a barrier.
+template <int TN>
 CC_DEV void cc_readout_bwd(const CcKParams& p, const CcNodeDev& nd, const float* gsrc, float* smem, const CcThread& th,
-                           float (&xrb)[CC_TM][CC_TN], bool want_input_grad) {
+                           float (&xrb)[CC_TM][TN], bool want_input_grad) {
   const CcLayerDev& LL = nd.g.layer[nd.g.L - 1];
   float* DA = smem + nd.s_DA;
   float* DB = smem + nd.s_DB;
@@ -129,10 +132,10 @@ CC_DEV void cc_readout_bwd(const CcKParams& p, const CcNodeDev& nd, const float*
     DA[o * p.BTP + traj] = d;
   }
   __syncthreads();
-  float* cur = cc_mlp_bwd(p, nd, nd.g, DA, DB, gsrc, nd.s_GH, smem, th);
+  float* cur = cc_mlp_bwd<TN>(p, nd, nd.g, DA, DB, gsrc, nd.s_GH, smem, th);
   if (want_input_grad) {
     const bool own = th.rg_ok && th.cg < nd.CGs;
-    cc_load_tile(cur, p.BTP, own ? nd.S : 0, nd.CGs, th, xrb);
+    cc_load_tile<TN>(cur, p.BTP, own ? nd.S : 0, nd.CGs, th, xrb);
     if (th.tid < p.BT)
       for (int i = 0; i < nd.I; ++i) smem[nd.s_VB + i * p.BTP + th.tid] += cur[(nd.row_v + i) * p.BTP + th.tid];
   }
@@ -143,7 +146,8 @@ CC_DEV void cc_readout_bwd(const CcKParams& p, const CcNodeDev& nd, const float*
 // LAM = cotangent of the next state, stage intermediates recomputed (if nd.recompute) by
 // cc_node_step(keep=true).  vraw[i*BTP + traj] = raw node input (for u_transform'), or null.
 // On exit: LAM = cotangent of the state at step start, VB = cotangent of the raw input.
-CC_DEV void cc_node_bwd(const CcKParams& p, const CcNodeDev& nd, float* smem, const CcThread& th, const float* vraw) {
+template <int TN>
+CC_DEV_NOINLINE void cc_node_bwd(const CcKParams& p, const CcNodeDev& nd, float* smem, const CcThread& th, const float* vraw) {
   const float h = nd.dt;
   const bool own = th.rg_ok && th.cg < nd.CGs;
   float* X = smem + nd.s_X;
@@ -152,31 +156,31 @@ CC_DEV void cc_node_bwd(const CcKParams& p, const CcNodeDev& nd, float* smem, co
   float* DB = smem + nd.s_DB;
   for (int i = th.tid; i < nd.I * p.BT; i += p.nthreads) smem[nd.s_VB + (i / p.BT) * p.BTP + (i % p.BT)] = 0.f;
   __syncthreads();
-  float xrb[CC_TM][CC_TN], lam[CC_TM][CC_TN];
-  cc_zero_tile(xrb);
-  cc_readout_bwd(p, nd, nd.pre ? X : smem + nd.s_ZA, smem, th, xrb, true);
-  cc_load_tile(LAM, p.BTP, own ? nd.S : 0, nd.CGs, th, lam);
+  float xrb[CC_TM][TN], lam[CC_TM][TN];
+  cc_zero_tile<TN>(xrb);
+  cc_readout_bwd<TN>(p, nd, nd.pre ? X : smem + nd.s_ZA, smem, th, xrb, true);
+  cc_load_tile<TN>(LAM, p.BTP, own ? nd.S : 0, nd.CGs, th, lam);
   if (!nd.pre) {
 #pragma unroll
     for (int i = 0; i < CC_TM; ++i)
 #pragma unroll
-      for (int j = 0; j < CC_TN; ++j) lam[i][j] += xrb[i][j];
+      for (int j = 0; j < TN; ++j) lam[i][j] += xrb[i][j];
   }
   const CcLayerDev& FL = nd.f.layer[nd.f.L - 1];
   if (nd.integrator == CC_INT_RK4) {
     const float c6 = h / 6.f, c3 = h / 3.f, c2 = h / 2.f;
-    float zsum[CC_TM][CC_TN], zb[CC_TM][CC_TN];
-    cc_zero_tile(zsum);
-    cc_zero_tile(zb);
+    float zsum[CC_TM][TN], zb[CC_TM][TN];
+    cc_zero_tile<TN>(zsum);
+    cc_zero_tile<TN>(zb);
     for (int s = 3; s >= 0; --s) {
       if (own) {
-        float d[CC_TM][CC_TN];
-        float ks[CC_TM][CC_TN];
-        if (FL.act != CC_ACT_IDENTITY) cc_load_tile(smem + nd.s_KS[s], p.BTP, nd.S, nd.CGs, th, ks);
+        float d[CC_TM][TN];
+        float ks[CC_TM][TN];
+        if (FL.act != CC_ACT_IDENTITY) cc_load_tile<TN>(smem + nd.s_KS[s], p.BTP, nd.S, nd.CGs, th, ks);
 #pragma unroll
         for (int i = 0; i < CC_TM; ++i)
 #pragma unroll
-          for (int j = 0; j < CC_TN; ++j) {
+          for (int j = 0; j < TN; ++j) {
             float kb;
             if (s == 3) kb = c6 * lam[i][j];
             else if (s == 2) kb = c3 * lam[i][j] + h * zb[i][j];
@@ -185,57 +189,57 @@ CC_DEV void cc_node_bwd(const CcKParams& p, const CcNodeDev& nd, float* smem, co
             if (FL.act != CC_ACT_IDENTITY) kb *= cc_act_grad(FL.act, ks[i][j]);
             d[i][j] = kb;
           }
-        cc_store_tile(DA, p.BTP, nd.S, nd.CGs, th, d);
+        cc_store_tile<TN>(DA, p.BTP, nd.S, nd.CGs, th, d);
       }
       __syncthreads();
       const float* in0 = nd.recompute ? smem + nd.s_Z[s] : X;
-      float* cur = cc_mlp_bwd(p, nd, nd.f, DA, DB, in0, nd.s_HS[s], smem, th);
-      cc_load_tile(cur, p.BTP, own ? nd.S : 0, nd.CGs, th, zb);
+      float* cur = cc_mlp_bwd<TN>(p, nd, nd.f, DA, DB, in0, nd.s_HS[s], smem, th);
+      cc_load_tile<TN>(cur, p.BTP, own ? nd.S : 0, nd.CGs, th, zb);
       if (th.tid < p.BT)
         for (int i = 0; i < nd.I; ++i) smem[nd.s_VB + i * p.BTP + th.tid] += cur[(nd.row_v + i) * p.BTP + th.tid];
 #pragma unroll
       for (int i = 0; i < CC_TM; ++i)
 #pragma unroll
-        for (int j = 0; j < CC_TN; ++j) zsum[i][j] += zb[i][j];
+        for (int j = 0; j < TN; ++j) zsum[i][j] += zb[i][j];
       __syncthreads();
     }
 #pragma unroll
     for (int i = 0; i < CC_TM; ++i)
 #pragma unroll
-      for (int j = 0; j < CC_TN; ++j) lam[i][j] += zsum[i][j];
+      for (int j = 0; j < TN; ++j) lam[i][j] += zsum[i][j];
   } else {
     if (own) {
-      float d[CC_TM][CC_TN], ks[CC_TM][CC_TN];
-      if (FL.act != CC_ACT_IDENTITY) cc_load_tile(smem + nd.s_KS[0], p.BTP, nd.S, nd.CGs, th, ks);
+      float d[CC_TM][TN], ks[CC_TM][TN];
+      if (FL.act != CC_ACT_IDENTITY) cc_load_tile<TN>(smem + nd.s_KS[0], p.BTP, nd.S, nd.CGs, th, ks);
 #pragma unroll
       for (int i = 0; i < CC_TM; ++i)
 #pragma unroll
-        for (int j = 0; j < CC_TN; ++j) {
+        for (int j = 0; j < TN; ++j) {
           float kb = nd.integrator == CC_INT_EE ? h * lam[i][j] : lam[i][j];
           if (FL.act != CC_ACT_IDENTITY) kb *= cc_act_grad(FL.act, ks[i][j]);
           d[i][j] = kb;
         }
-      cc_store_tile(DA, p.BTP, nd.S, nd.CGs, th, d);
+      cc_store_tile<TN>(DA, p.BTP, nd.S, nd.CGs, th, d);
     }
     __syncthreads();
-    float* cur = cc_mlp_bwd(p, nd, nd.f, DA, DB, X, nd.s_HS[0], smem, th);
-    float zb[CC_TM][CC_TN];
-    cc_load_tile(cur, p.BTP, own ? nd.S : 0, nd.CGs, th, zb);
+    float* cur = cc_mlp_bwd<TN>(p, nd, nd.f, DA, DB, X, nd.s_HS[0], smem, th);
+    float zb[CC_TM][TN];
+    cc_load_tile<TN>(cur, p.BTP, own ? nd.S : 0, nd.CGs, th, zb);
     if (th.tid < p.BT)
       for (int i = 0; i < nd.I; ++i) smem[nd.s_VB + i * p.BTP + th.tid] += cur[(nd.row_v + i) * p.BTP + th.tid];
 #pragma unroll
     for (int i = 0; i < CC_TM; ++i)
 #pragma unroll
-      for (int j = 0; j < CC_TN; ++j) lam[i][j] = nd.integrator == CC_INT_EE ? lam[i][j] + zb[i][j] : zb[i][j];
+      for (int j = 0; j < TN; ++j) lam[i][j] = nd.integrator == CC_INT_EE ? lam[i][j] + zb[i][j] : zb[i][j];
     __syncthreads();
   }
   if (nd.pre) {
 #pragma unroll
     for (int i = 0; i < CC_TM; ++i)
 #pragma unroll
-      for (int j = 0; j < CC_TN; ++j) lam[i][j] += xrb[i][j];
+      for (int j = 0; j < TN; ++j) lam[i][j] += xrb[i][j];
   }
-  if (own) cc_store_tile(LAM, p.BTP, nd.S, nd.CGs, th, lam);
+  if (own) cc_store_tile<TN>(LAM, p.BTP, nd.S, nd.CGs, th, lam);
   if (vraw && nd.ut != CC_UT_IDENTITY && th.tid < p.BT)
     for (int i = 0; i < nd.I; ++i)
       smem[nd.s_VB + i * p.BTP + th.tid] *= cc_ut_grad(nd.ut, nd.u_scale, vraw[i * p.BTP + th.tid]);
@@ -254,8 +258,9 @@ CC_DEV void cc_tape_load(const CcKParams& p, const CcNodeDev& nd, long long b0, 
 // ------------------------------------------------------------------------------------------------
 // K2 + K4: reverse time loop
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512, 1) cc_rollout_bwd_kernel(const CcKParams p) {
-  CC_SMEM_DECL
+template <int TN>
+__global__ void __launch_bounds__(320, 1) cc_rollout_bwd_kernel(const CC_GRID_CONSTANT CcKParams gp) {
+  CC_KERNEL_PROLOGUE(gp)
   CcThread th;
   th.tid = threadIdx.x;
   th.rg = th.tid / p.CGT;
@@ -307,7 +312,7 @@ __global__ void __launch_bounds__(512, 1) cc_rollout_bwd_kernel(const CcKParams 
           cc_set_inputs(p, C, smem, th.tid, v, tc, true);
         }
         __syncthreads();
-        cc_node_step(p, C, smem, th, tc, true, true, false, 0, 0);  // controller always recomputes: a_k is needed
+        cc_node_step<TN>(p, C, smem, th, tc, true, true, false, 0, 0);  // controller always recomputes: a_k is needed
         if (th.tid < p.BT) {
           float a[16];
           for (int i = 0; i < M.I; ++i) {
@@ -319,14 +324,14 @@ __global__ void __launch_bounds__(512, 1) cc_rollout_bwd_kernel(const CcKParams 
             smem[M.s_OB + o * p.BTP + th.tid] = smem[p.s_yb + (kk * M.O + o) * p.BTP + th.tid] + smem[p.s_yfb + o * p.BTP + th.tid];
         }
         __syncthreads();
-        if (M.recompute) cc_node_step(p, M, smem, th, tm, true, true, false, 0, 0);
-        cc_node_bwd(p, M, smem, th, smem + p.s_araw);
+        if (M.recompute) cc_node_step<TN>(p, M, smem, th, tm, true, true, false, 0, 0);
+        cc_node_bwd<TN>(p, M, smem, th, smem + p.s_araw);
         for (int i = th.tid; i < M.I * p.BT; i += p.nthreads) {
           const int r = i / p.BT, traj = i % p.BT;
           smem[C.s_OB + r * p.BTP + traj] = smem[M.s_VB + r * p.BTP + traj];
         }
         __syncthreads();
-        cc_node_bwd(p, C, smem, th, nullptr);
+        cc_node_bwd<TN>(p, C, smem, th, nullptr);
         for (int i = th.tid; i < M.O * p.BT; i += p.nthreads) {
           const int o = i / p.BT, traj = i % p.BT;
           smem[p.s_yfb + o * p.BTP + traj] = smem[C.s_VB + (p.R + o) * p.BTP + traj];
@@ -342,8 +347,8 @@ __global__ void __launch_bounds__(512, 1) cc_rollout_bwd_kernel(const CcKParams 
           for (int o = 0; o < M.O; ++o) smem[M.s_OB + o * p.BTP + th.tid] = smem[p.s_yb + (kk * M.O + o) * p.BTP + th.tid];
         }
         __syncthreads();
-        if (M.recompute) cc_node_step(p, M, smem, th, tm, true, true, false, 0, 0);
-        cc_node_bwd(p, M, smem, th, smem + p.s_in + kk * M.I * p.BTP);
+        if (M.recompute) cc_node_step<TN>(p, M, smem, th, tm, true, true, false, 0, 0);
+        cc_node_bwd<TN>(p, M, smem, th, smem + p.s_in + kk * M.I * p.BTP);
         if (p.ubar && th.tid < p.BT)
           for (int i = 0; i < M.I; ++i) smem[p.s_ub + (kk * M.I + i) * p.BTP + th.tid] = smem[M.s_VB + i * p.BTP + th.tid];
       }
@@ -369,9 +374,9 @@ __global__ void __launch_bounds__(512, 1) cc_rollout_bwd_kernel(const CcKParams 
         smem[M.s_OB + o * p.BTP + th.tid] = (b0 + th.tid < p.B) ? __ldg(p.ybar + (b0 + th.tid) * (long long)(p.T + 1) * M.O + o) : 0.f;
     }
     __syncthreads();
-    cc_readout(p, M, smem + M.s_X, smem, M.s_GH, th);
-    float dummy[CC_TM][CC_TN];
-    cc_readout_bwd(p, M, smem + M.s_X, smem, th, dummy, false);
+    cc_readout<TN>(p, M, smem + M.s_X, smem, M.s_GH, th);
+    float dummy[CC_TM][TN];
+    cc_readout_bwd<TN>(p, M, smem + M.s_X, smem, th, dummy, false);
   }
 
   // per-CTA gradient block -> workspace (reduced over tiles in fixed order by cc_reduce_grad_kernel)

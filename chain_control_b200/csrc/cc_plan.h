@@ -9,14 +9,13 @@
 // (neural_ode_model.py:122-133, neural_ode_controller.py:121-134); weights are staged once per CTA
 // as Wt[row][Np] (k-major) with zero rows where an MLP does not consume t / v and the bias as the
 // row multiplying the constant-1 row.  Each layer evaluation is then a register-tiled SGEMM
-//     C[BT x N] = A[K x BT]^T . Wt[K x N],   thread tile TM x TN = 4 trajectories x 8 outputs.
+//     C[BT x N] = A[K x BT]^T . Wt[K x N],   thread tile TM x TN = 4 trajectories x 8 (or 10) outputs.
 #pragma once
 #include <stdint.h>
 
 #include "../../include/cc_b200.h"
 
 #define CC_TM 4
-#define CC_TN 8
 #define CC_TC 16        /* time steps staged per I/O chunk */
 #define CC_MAX_SKINNY 4 /* layers with N <= this use the split-K path */
 
@@ -24,8 +23,8 @@ struct CcLayerDev {
   int K;       // contraction rows read from the source buffer (incl. the constant-1 row)
   int N;       // outputs
   int CG;      // column groups = ceil(N / TN)
-  int Np;      // TN * CG (padded outputs)
-  int Kp;      // K rounded up to a multiple of TN (row stride of the row-major copy)
+  int Np;      // TN * CG rounded up to a multiple of 4 (row stride of Wt)
+  int Kp;      // TN * CGk rounded up to a multiple of 4 (row stride of the row-major copy)
   int CGk;     // column groups over K (input-gradient GEMM)
   int act;     // activation applied to this layer's output
   int in_log;  // logical input width = row stride of the weight in theta
@@ -77,6 +76,7 @@ struct CcNodeDev {
 struct CcKParams {
   CcNodeDev nd[2];  // closed loop: nd[0] = controller, nd[1] = model; open loop: nd[0] = model
   int n_nodes;
+  int TN;  // thread-tile width over outputs: 8 or 10 (chosen to minimise column padding)
   int BT, BTP, RG, CGT, nthreads;
   long long B;
   int T;  // number of steps: T (open loop) or Tr (closed loop)

@@ -25,6 +25,12 @@ struct Fiber {
   std::vector<char> stack;
   uint3e tid;
   bool done = false;
+  int wait_kind = 0;  // 0 runnable, 1 waiting at __syncthreads, 2 waiting at a warp barrier
+};
+struct WarpState {
+  int arrived = 0;
+  unsigned gen = 0;
+  float xchg[32];
 };
 struct State {
   ucontext_t sched;
@@ -32,6 +38,11 @@ struct State {
   uint3e bid{0, 0, 0}, bdim{1, 1, 1}, gdim{1, 1, 1};
   float* smem = nullptr;
   std::function<void()> body;
+  std::vector<WarpState> warps;
+  int cta_arrived = 0;
+  unsigned cta_gen = 0;
+  int alive = 0;
+  long progress = 0;  // bumped whenever a thread passes a barrier or exits
 };
 inline State& st() {
   static thread_local State s;
@@ -66,20 +77,24 @@ inline void launch(int grid, int block, size_t smem_bytes, F f) {
       fb.ctx.uc_link = nullptr;
       makecontext(&fb.ctx, (void (*)())trampoline, 0);
     }
-    int alive = block;
-    while (alive > 0) {
-      int finished_now = 0, yielded = 0;
+    s.warps.assign((block + 31) / 32, WarpState());
+    s.cta_arrived = 0;
+    s.alive = block;
+    // round-robin: a fiber runs until it blocks at a barrier (it re-checks its condition itself)
+    // or finishes.  Deadlock (nobody can progress) = barrier divergence in the kernel.
+    long idle_rounds = 0;
+    while (s.alive > 0) {
+      const long before = s.progress;
       for (int t = 0; t < block; ++t) {
         Fiber& fb = fibers[t];
         if (fb.done) continue;
         s.cur = &fb;
         swapcontext(&s.sched, &fb.ctx);
-        if (fb.done) ++finished_now; else ++yielded;
+        if (fb.done) { --s.alive; ++s.progress; }
       }
-      alive -= finished_now;
-      if (finished_now && yielded) {
-        fprintf(stderr, "ccemu: barrier divergence: %d threads exited while %d wait at __syncthreads\n",
-                finished_now, yielded);
+      idle_rounds = s.progress != before ? 0 : idle_rounds + 1;
+      if (idle_rounds > 4) {
+        fprintf(stderr, "ccemu: deadlock: %d threads wait at a barrier that can never complete\n", s.alive);
         abort();
       }
     }
@@ -100,6 +115,56 @@ inline void launch(int grid, int block, size_t smem_bytes, F f) {
 #define gridDim (ccemu::st().gdim)
 static inline void __syncthreads() {
   ccemu::State& s = ccemu::st();
-  swapcontext(&s.cur->ctx, &s.sched);
+  ccemu::Fiber* me = s.cur;
+  const unsigned gen = s.cta_gen;
+  ++s.progress;
+  if (++s.cta_arrived == (int)s.bdim.x) {  // every thread of the CTA must arrive (exited threads = bug)
+    s.cta_arrived = 0;
+    ++s.cta_gen;
+    return;
+  }
+  me->wait_kind = 1;
+  while (s.cta_gen == gen) swapcontext(&me->ctx, &s.sched);
+  me->wait_kind = 0;
+}
+static inline int ccemu_warp_size_of(int warp) {
+  const int n = (int)ccemu::st().bdim.x - warp * 32;
+  return n < 32 ? n : 32;
+}
+static inline void __syncwarp(unsigned mask = 0xffffffffu) {
+  (void)mask;
+  ccemu::State& s = ccemu::st();
+  ccemu::Fiber* me = s.cur;
+  const int w = me->tid.x / 32;
+  ccemu::WarpState& ws = s.warps[w];
+  const unsigned gen = ws.gen;
+  ++s.progress;
+  if (++ws.arrived == ccemu_warp_size_of(w)) {
+    ws.arrived = 0;
+    ++ws.gen;
+    return;
+  }
+  me->wait_kind = 2;
+  while (ws.gen == gen) swapcontext(&me->ctx, &s.sched);
+  me->wait_kind = 0;
+}
+// full-mask shuffles (all lanes of the warp must participate)
+static inline float __shfl_xor_sync(unsigned mask, float v, int lane_mask) {
+  ccemu::State& s = ccemu::st();
+  const int w = s.cur->tid.x / 32, l = s.cur->tid.x % 32;
+  s.warps[w].xchg[l] = v;
+  __syncwarp(mask);
+  const float r = s.warps[w].xchg[l ^ lane_mask];
+  __syncwarp(mask);
+  return r;
+}
+static inline float __shfl_sync(unsigned mask, float v, int src) {
+  ccemu::State& s = ccemu::st();
+  const int w = s.cur->tid.x / 32, l = s.cur->tid.x % 32;
+  s.warps[w].xchg[l] = v;
+  __syncwarp(mask);
+  const float r = s.warps[w].xchg[src & 31];
+  __syncwarp(mask);
+  return r;
 }
 static inline float __ldg(const float* p) { return *p; }
