@@ -32,7 +32,7 @@ int fail(int code, const char* fmt, ...) {
 }
 
 constexpr int kSmemBudget = 227 * 1024 - 2560;  // minus the plan copy at the head of dynamic smem
-constexpr int kMaxIO = 16;
+constexpr int kMaxIO = CC_TINY_K;
 
 int num_sms() {
 #ifdef CC_EMULATE
@@ -95,8 +95,35 @@ struct Alloc {
   }
 };
 
+struct PlanOpts {
+  bool bwd = false;
+};
+
+bool node_is_tiny(const CcModule* m) {
+  const int K0 = m->state_dim + ((m->f_time_variant || m->g_time_variant) ? 1 : 0) + m->input_dim + 1;
+  return m->f.n_layers == 1 && m->g.n_layers == 1 && m->state_dim <= CC_TINY_S && K0 <= CC_TINY_K &&
+         m->output_dim <= CC_TINY_O && m->input_dim <= 4;
+}
+
+// column-group stride of a weight row for register-tile width TN: >= TN, a multiple of 4 and such
+// that the 4 column groups of a warp start in disjoint bank quads
+int group_stride(int TN) { return TN <= 8 ? 8 : 20; }
+
+int tile_width_for(int cpt) { return cpt <= 8 ? 8 : (cpt <= 13 ? 13 : (cpt <= 16 ? 16 : 0)); }
+
+int node_max_cpt(const CcModule* m) {
+  int c = ceil_div(m->state_dim, 4);
+  const CcMlp* mlps[2] = {&m->f, &m->g};
+  for (int w = 0; w < 2; ++w)
+    for (int l = 1; l <= mlps[w]->n_layers; ++l) {
+      const int cc = ceil_div(mlps[w]->sizes[l], 4);
+      if (cc > c) c = cc;
+    }
+  return c;
+}
+
 // fills the size-independent part of a node
-void describe_node(const CcModule* m, CcNodeDev* nd, bool trainable, int TN) {
+void describe_node(const CcModule* m, CcNodeDev* nd, bool trainable, bool tiny, int TN) {
   memset(nd, 0, sizeof(*nd));
   nd->S = m->state_dim; nd->I = m->input_dim; nd->O = m->output_dim;
   nd->has_t = (m->f_time_variant || m->g_time_variant) ? 1 : 0;
@@ -106,10 +133,12 @@ void describe_node(const CcModule* m, CcNodeDev* nd, bool trainable, int TN) {
   nd->u_scale = m->u_scale; nd->out_scale = m->out_scale; nd->dt = m->dt;
   nd->K0 = nd->S + nd->has_t + nd->I + 1;
   nd->row_t = nd->S; nd->row_v = nd->S + nd->has_t; nd->row_one = nd->S + nd->has_t + nd->I;
+  nd->cptS = ceil_div(nd->S, 4);
+  nd->tiny = tiny ? 1 : 0;
   nd->P = (int)param_count(m);
   nd->trainable = trainable;
   nd->recompute = (trainable || !mlp_linear(m->f) || !mlp_linear(m->g)) ? 1 : 0;
-  int off = 0;
+  int off = 0, goff = 0;
   const CcMlp* mlps[2] = {&m->f, &m->g};
   CcMlpDev* devs[2] = {&nd->f, &nd->g};
   for (int w = 0; w < 2; ++w) {
@@ -122,10 +151,19 @@ void describe_node(const CcModule* m, CcNodeDev* nd, bool trainable, int TN) {
       L.in_log = mlp->sizes[l];
       L.N = mlp->sizes[l + 1];
       L.K = L.first ? nd->K0 : L.in_log + 1;
-      L.CG = ceil_div(L.N, TN);
-      L.Np = (TN * L.CG + 3) / 4 * 4;  // row stride of Wt: keeps every LDS.128 16-byte aligned
-      L.CGk = ceil_div(L.K, TN);
-      L.Kp = (TN * L.CGk + 3) / 4 * 4;
+      if (tiny) {
+        L.cpt = L.N;
+        L.GS = (L.N + 3) / 4 * 4;
+        L.ldw = L.GS;
+      } else {
+        L.cpt = ceil_div(L.N, 4);
+        L.GS = group_stride(TN);
+        L.ldw = 4 * L.GS;
+      }
+      L.Kin = L.first ? nd->S : L.in_log;
+      L.kcpt = L.first ? nd->cptS : ceil_div(L.in_log, 4);
+      L.GSk = group_stride(TN);
+      L.ldk = 4 * L.GSk;
       L.act = l < mlp->n_layers - 1 ? mlp->act : mlp->act_final;
       L.use_t = L.first ? (w == 0 ? m->f_time_variant : m->g_time_variant) : 0;
       L.use_v = L.first ? (w == 0 ? 1 : m->g_feedthrough_u) : 0;
@@ -133,142 +171,77 @@ void describe_node(const CcModule* m, CcNodeDev* nd, bool trainable, int TN) {
       off += L.in_log * L.N;
       L.b_off = -1;
       if (mlp->use_bias) { L.b_off = off; off += L.N; }
-      L.s_wt = L.s_w = L.s_gw = L.s_out = -1;
+      L.s_wt = L.s_w = L.s_wv = L.w_gw = L.w_out = -1;
+      L.g_off = goff;
+      goff += L.N * L.K;
     }
   }
-  nd->CGs = nd->f.layer[nd->f.L - 1].CG;
+  nd->g_total = goff;
 }
 
-int max_cg(const CcNodeDev& nd, bool bwd) {
-  int cg = 1;
-  const CcMlpDev* devs[2] = {&nd.f, &nd.g};
-  for (int w = 0; w < 2; ++w)
-    for (int l = 0; l < devs[w]->L; ++l) {
-      const CcLayerDev& L = devs[w]->layer[l];
-      if (L.N > CC_MAX_SKINNY && L.CG > cg) cg = L.CG;
-      if (bwd && L.CGk > cg) cg = L.CGk;
-    }
-  if (nd.CGs > cg) cg = nd.CGs;
-  return cg;
-}
-
-int pad_bt(int BT) {
-  int btp = BT;
-  while ((btp / 4) % 2 == 0) btp += 4;  // BTP/4 odd -> rows land on distinct bank quads
-  return btp;
-}
-
-// lays out shared memory for tile size BT; returns total floats
-int layout(CcKParams* p, int BT, bool bwd, bool want_uout, bool want_noise, bool want_ubar) {
-  p->BT = BT;
-  p->BTP = pad_bt(BT);
-  p->RG = BT / CC_TM;
-  int cgt = 1;
-  for (int n = 0; n < p->n_nodes; ++n) { const int c = max_cg(p->nd[n], bwd); if (c > cgt) cgt = c; }
-  p->CGT = cgt;
-  p->nthreads = (p->RG * p->CGT + 31) / 32 * 32;
-  if (p->nthreads < (BT + 31) / 32 * 32) p->nthreads = (BT + 31) / 32 * 32;  // one thread per trajectory in the I/O phases
-  const int BTP = p->BTP;
-  Alloc a;
-  int gw = 0;
+// lays out the CTA-shared (weights) and per-warp (activations) shared memory
+void layout(CcKParams* p, bool bwd) {
+  Alloc cs, ws;
+  int grec = 0;
   for (int n = 0; n < p->n_nodes; ++n) {
     CcNodeDev& nd = p->nd[n];
     CcMlpDev* devs[2] = {&nd.f, &nd.g};
+    const bool need_fwd = !bwd || nd.recompute || nd.tiny;  // forward evaluation of this node happens in this kernel
     for (int w = 0; w < 2; ++w)
       for (int l = 0; l < devs[w]->L; ++l) {
         CcLayerDev& L = devs[w]->layer[l];
-        L.s_wt = a.take(L.K * L.Np);
-        L.s_w = bwd ? a.take(L.N * L.Kp) : -1;
-        L.s_gw = (bwd && nd.trainable) ? a.take(L.N * L.Kp) : -1;
-        L.s_out = (l < devs[w]->L - 1) ? a.take((L.N + 1) * BTP) : -1;
+        L.s_wt = (need_fwd || nd.tiny) ? cs.take(L.K * L.ldw) : -1;
+        L.s_w = (bwd && !nd.tiny) ? cs.take(L.N * L.ldk) : -1;
+        L.s_wv = (bwd && !nd.tiny && L.first && L.use_v && nd.I > 0) ? cs.take(nd.I * L.N) : -1;
+        L.w_out = (!nd.tiny && need_fwd && !bwd && l < devs[w]->L - 1) ? ws.take((L.N + 1) * CC_LD) : -1;
+        L.w_gw = (bwd && nd.trainable && !nd.tiny) ? ws.take(L.N * L.K) : -1;
       }
-    nd.s_X = a.take(nd.K0 * BTP);
-    nd.s_ZA = a.take(nd.K0 * BTP);
-    nd.s_ZB = a.take(nd.K0 * BTP);
-    nd.s_OUT = a.take(nd.O * BTP);
-    nd.gw_off = gw;
+    nd.w_X = nd.w_Z = nd.w_OUT = nd.w_XN = nd.w_LAM = nd.w_DA = nd.w_DB = nd.w_VB = nd.w_OB = nd.w_GP = -1;
+    for (int s = 0; s < 4; ++s) {
+      nd.w_ZS[s] = nd.w_KS[s] = -1;
+      for (int l = 0; l < CC_MAX_LAYERS; ++l) nd.w_HS[s][l] = -1;
+    }
+    for (int l = 0; l < CC_MAX_LAYERS; ++l) nd.w_GH[l] = -1;
+    nd.g_base = grec;
+    if (nd.tiny) {
+      if (bwd && nd.trainable) { nd.w_GP = ws.take(nd.g_total * CC_LD); grec += nd.g_total; }
+      continue;
+    }
+    if (need_fwd) {
+      nd.w_X = ws.take(nd.K0 * CC_LD);
+      nd.w_OUT = ws.take(nd.O * CC_LD);
+      if (!bwd) nd.w_Z = ws.take(nd.K0 * CC_LD);
+    }
     if (bwd) {
-      nd.s_Z[0] = nd.s_X;
-      for (int s = 1; s < 4; ++s) nd.s_Z[s] = (nd.recompute && nd.integrator == CC_INT_RK4) ? a.take(nd.K0 * BTP) : -1;
-      for (int s = 0; s < 4; ++s) {
-        for (int l = 0; l < CC_MAX_LAYERS; ++l) nd.s_HS[s][l] = -1;
-        nd.s_KS[s] = -1;
-        if (s < nd.n_stages && nd.recompute) {
-          for (int l = 0; l < nd.f.L - 1; ++l) nd.s_HS[s][l] = a.take((nd.f.layer[l].N + 1) * BTP);
-          if (nd.f.layer[nd.f.L - 1].act != CC_ACT_IDENTITY) nd.s_KS[s] = a.take(nd.S * BTP);
+      if (nd.recompute) {
+        nd.w_ZS[0] = nd.w_X;
+        if (nd.integrator == CC_INT_RK4)
+          for (int s = 1; s < 4; ++s) nd.w_ZS[s] = ws.take(nd.K0 * CC_LD);
+        if (!nd.pre) nd.w_XN = ws.take(nd.K0 * CC_LD);
+        for (int s = 0; s < nd.n_stages; ++s) {
+          for (int l = 0; l < nd.f.L - 1; ++l) nd.w_HS[s][l] = ws.take((nd.f.layer[l].N + 1) * CC_LD);
+          if (nd.f.layer[nd.f.L - 1].act != CC_ACT_IDENTITY) nd.w_KS[s] = ws.take(nd.S * CC_LD);
         }
+        for (int l = 0; l < nd.g.L - 1; ++l) nd.w_GH[l] = ws.take((nd.g.layer[l].N + 1) * CC_LD);
       }
-      for (int l = 0; l < CC_MAX_LAYERS; ++l) nd.s_GH[l] = (l < nd.g.L - 1) ? a.take((nd.g.layer[l].N + 1) * BTP) : -1;
-      int maxd = nd.K0;
+      int maxn = nd.O;
       for (int w = 0; w < 2; ++w)
-        for (int l = 0; l < devs[w]->L; ++l) {
-          if (devs[w]->layer[l].Np > maxd) maxd = devs[w]->layer[l].Np;
-          if (devs[w]->layer[l].Kp > maxd) maxd = devs[w]->layer[l].Kp;
-        }
-      nd.s_LAM = a.take(nd.S * BTP);
-      nd.s_DA = a.take(maxd * BTP);
-      nd.s_DB = a.take(maxd * BTP);
-      nd.s_VB = a.take((nd.I > 0 ? nd.I : 1) * BTP);
-      nd.s_OB = a.take(nd.O * BTP);
-      if (nd.trainable)
-        for (int w = 0; w < 2; ++w)
-          for (int l = 0; l < devs[w]->L; ++l) gw += devs[w]->layer[l].N * devs[w]->layer[l].Kp;
+        for (int l = 0; l < devs[w]->L; ++l)
+          if (devs[w]->layer[l].N > maxn) maxn = devs[w]->layer[l].N;
+      nd.w_LAM = ws.take(nd.S * CC_LD);
+      nd.w_DA = ws.take(maxn * CC_LD);
+      nd.w_VB = ws.take((nd.I > 0 ? nd.I : 1) * CC_LD);
+      nd.w_OB = ws.take(nd.O * CC_LD);
+      if (nd.trainable) grec += nd.g_total;
     }
   }
-  p->gw_total = gw;
-  p->nd[0].s_P = a.take(p->CGT * CC_MAX_SKINNY * BTP);
-  for (int n = 1; n < p->n_nodes; ++n) p->nd[n].s_P = p->nd[0].s_P;
   const CcNodeDev& M = p->nd[p->n_nodes - 1];
-  const int Win = p->n_nodes == 2 ? p->R : M.I;
-  p->s_in = a.take(CC_TC * (Win > 0 ? Win : 1) * BTP);
-  p->s_out = bwd ? -1 : a.take(CC_TC * M.O * BTP);
-  p->s_uo = (want_uout && !bwd) ? a.take(CC_TC * M.I * BTP) : -1;
-  p->s_noise = want_noise ? a.take(CC_TC * M.O * BTP) : -1;
-  p->s_yprev = p->n_nodes == 2 ? a.take(M.O * BTP) : -1;
-  p->s_yb = bwd ? a.take(CC_TC * M.O * BTP) : -1;
-  p->s_ub = (bwd && want_ubar) ? a.take(CC_TC * (M.I > 0 ? M.I : 1) * BTP) : -1;
-  p->s_yfb = (bwd && p->n_nodes == 2) ? a.take(M.O * BTP) : -1;
-  p->s_araw = (bwd && p->n_nodes == 2) ? a.take((M.I > 0 ? M.I : 1) * BTP) : -1;
-  p->smem_floats = a.off;
-  return a.off;
-}
-
-struct PlanOpts {
-  bool bwd = false, want_uout = false, want_noise = false, want_ubar = false;
-};
-
-// chooses the tile size BT.  Cost model: waves x (work per wave on one SM), with penalties for
-// idle lanes (RG*CGT not a multiple of 32) and for fewer than 8 resident warps per SM.
-int choose_tile(CcKParams* p, const PlanOpts& o) {
-  static const int cands[] = {256, 224, 192, 160, 128, 112, 96, 80, 64, 48, 32, 16, 8, 4};
-  const char* env = getenv("CC_B200_BT");
-  const int forced = env ? atoi(env) : 0;
-  const int sms = num_sms();
-  double best = 1e300;
-  int best_bt = 0;
-  for (int c : cands) {
-    if (forced && c != forced) continue;
-    const int fl = layout(p, c, o.bwd, o.want_uout, o.want_noise, o.want_ubar);
-    const long long bytes = (long long)fl * 4;
-    if (bytes > kSmemBudget || p->nthreads > 320) continue;
-    const int occ_smem = (int)(kSmemBudget / (bytes + 1024));
-    const int occ_regs = 65536 / (p->nthreads * 200);
-    int occ = occ_smem < occ_regs ? occ_smem : occ_regs;
-    if (occ < 1) occ = 1;
-    if (occ > 8) occ = 8;
-    const long long tiles = (p->B + c - 1) / c;
-    const long long per_sm = (tiles + sms - 1) / sms;
-    const int oe = (int)(per_sm < occ ? per_sm : occ);
-    const long long waves = (tiles + (long long)sms * occ - 1) / ((long long)sms * occ);
-    const double lane_eff = (double)(p->RG * p->CGT) / p->nthreads;
-    const double warps = (double)oe * p->nthreads / 32.0;
-    const double thr = (warps >= 8.0 ? 1.0 : warps / 8.0) * lane_eff;
-    const double cost = (double)waves * c * oe / thr;
-    if (cost < best * 0.98) { best = cost; best_bt = c; }
-  }
-  if (!best_bt) return 0;
-  layout(p, best_bt, o.bwd, o.want_uout, o.want_noise, o.want_ubar);
-  return best_bt;
+  p->w_yprev = (!bwd && p->n_nodes == 2) ? ws.take(M.O * CC_LD) : -1;
+  p->w_yfb = (bwd && p->n_nodes == 2) ? ws.take(M.O * CC_LD) : -1;
+  p->w_araw = bwd ? ws.take((M.I > 0 ? M.I : 1) * CC_LD) : -1;
+  p->g_rec = grec;
+  p->cta_floats = cs.off;
+  p->warp_floats = ws.off;
 }
 
 int make_plan(const CcModule* const* mods, int n_nodes, long long B, int T, const PlanOpts& o, CcKParams* p) {
@@ -276,32 +249,27 @@ int make_plan(const CcModule* const* mods, int n_nodes, long long B, int T, cons
   p->n_nodes = n_nodes;
   p->B = B;
   p->T = T;
-  p->Bpad = (B + 255) / 256 * 256;
-  // thread-tile width: the one that wastes fewer padded columns, weighted by layer work
-  int tn = 8;
-  {
-    const char* env = getenv("CC_B200_TN");
-    if (env && (atoi(env) == 8 || atoi(env) == 10)) tn = atoi(env);
+  p->Bpad = (B + 31) / 32 * 32;
+  p->n_wtiles = (B + 31) / 32;
+  const CcModule* model = mods[n_nodes - 1];
+  p->TN = tile_width_for(node_max_cpt(model));
+  if (!p->TN) return fail(CC_ERR_UNSUPPORTED, "model layers wider than 64 are not supported yet (register tile 4 x 16 per thread)");
+  p->ctrl_mode = CC_CTRL_NONE;
+  if (n_nodes == 2) {
+    if (node_is_tiny(mods[0])) p->ctrl_mode = CC_CTRL_TINY;
     else {
-      double w8 = 0, w10 = 0;
-      for (int n = 0; n < n_nodes; ++n) {
-        const CcMlp* mlps[2] = {&mods[n]->f, &mods[n]->g};
-        for (int w = 0; w < 2; ++w)
-          for (int l = 0; l < mlps[w]->n_layers; ++l) {
-            const int N = mlps[w]->sizes[l + 1], K = mlps[w]->sizes[l] + 1;
-            if (N <= CC_MAX_SKINNY) continue;
-            const double reps = w == 0 ? (mods[n]->integrator == CC_INT_RK4 ? 4 : 1) : 1;
-            w8 += reps * K * ceil_div(N, 8) * 8;
-            w10 += reps * K * ceil_div(N, 10) * 10;
-          }
-      }
-      tn = w10 < w8 ? 10 : 8;
+      if (tile_width_for(node_max_cpt(mods[0])) != 8) return fail(CC_ERR_UNSUPPORTED, "controller layers wider than 32 are not supported yet");
+      p->ctrl_mode = CC_CTRL_TILE;
     }
+    if (mods[1]->input_dim > CC_TINY_O || mods[1]->output_dim > CC_TINY_O) return fail(CC_ERR_UNSUPPORTED, "closed loop: model input/output dims > %d", CC_TINY_O);
+    if (mods[0]->input_dim > CC_TINY_K) return fail(CC_ERR_UNSUPPORTED, "closed loop: controller input dim > %d", CC_TINY_K);
+  } else if (model->input_dim > CC_TINY_K) {
+    return fail(CC_ERR_UNSUPPORTED, "input dim > %d", CC_TINY_K);
   }
-  p->TN = tn;
   for (int n = 0; n < n_nodes; ++n) {
     const bool trainable = o.bwd && (n_nodes == 1 || n == 0);
-    describe_node(mods[n], &p->nd[n], trainable, tn);
+    const bool is_ctrl = n_nodes == 2 && n == 0;
+    describe_node(mods[n], &p->nd[n], trainable, is_ctrl && p->ctrl_mode == CC_CTRL_TINY, is_ctrl ? 8 : p->TN);
   }
   if (n_nodes == 2) {
     p->R = mods[0]->input_dim - mods[1]->output_dim;
@@ -312,11 +280,33 @@ int make_plan(const CcModule* const* mods, int n_nodes, long long B, int T, cons
     p->nd[0].tape_row = 0;
     p->tape_rows = p->nd[0].S;
   }
-  const int chosen = choose_tile(p, o);
-  if (chosen && getenv("CC_B200_VERBOSE"))
-    fprintf(stderr, "[ccb200] plan: nodes=%d bwd=%d B=%lld T=%d TN=%d BT=%d BTP=%d RG=%d CGT=%d threads=%d smem=%d B tiles=%lld\n",
-            n_nodes, (int)o.bwd, B, T, p->TN, p->BT, p->BTP, p->RG, p->CGT, p->nthreads, p->smem_floats * 4, (B + p->BT - 1) / p->BT);
-  if (!chosen) return fail(CC_ERR_UNSUPPORTED, "architecture does not fit in %d KB of shared memory per CTA (weights must be smem-resident in this version)", kSmemBudget / 1024);
+  layout(p, o.bwd);
+  // warps per CTA: as many as shared memory / registers allow (<= 10 at ~200 registers per thread),
+  // then the count that minimises waves x warps (whole-SM throughput bound), larger on ties
+  const long long cta_bytes = (long long)p->cta_floats * 4;
+  const long long warp_bytes = (long long)p->warp_floats * 4;
+  if (cta_bytes + warp_bytes > kSmemBudget)
+    return fail(CC_ERR_UNSUPPORTED, "architecture does not fit in %d KB of shared memory per CTA (weights %lld B + %lld B per warp)", kSmemBudget / 1024, cta_bytes, warp_bytes);
+  int cap = (int)((kSmemBudget - cta_bytes) / (warp_bytes > 0 ? warp_bytes : 1));
+  if (cap > 10) cap = 10;
+  const char* env = getenv("CC_B200_WPC");
+  int best = 1;
+  if (env && atoi(env) >= 1 && atoi(env) <= cap) best = atoi(env);
+  else {
+    const int sms = num_sms();
+    double best_cost = 1e300;
+    for (int wpc = 1; wpc <= cap; ++wpc) {
+      const long long ctas = (p->n_wtiles + wpc - 1) / wpc;
+      const long long waves = (ctas + sms - 1) / sms;
+      const long long used = ctas < sms ? (p->n_wtiles + ctas - 1) / ctas : wpc;  // warps actually resident per SM
+      const double cost = (double)waves * (double)(used < 4 ? 4 : used);          // < 4 warps cannot fill the 4 schedulers
+      if (cost < best_cost) { best_cost = cost; best = wpc; }  // ties: fewer warps per CTA
+    }
+  }
+  p->wpc = best;
+  if (getenv("CC_B200_VERBOSE"))
+    fprintf(stderr, "[ccb200] plan: nodes=%d bwd=%d B=%lld T=%d TN=%d ctrl=%d wpc=%d cta_smem=%lld B warp_smem=%lld B ctas=%lld\n",
+            n_nodes, (int)o.bwd, B, T, p->TN, p->ctrl_mode, p->wpc, cta_bytes, warp_bytes, (p->n_wtiles + p->wpc - 1) / p->wpc);
   return CC_OK;
 }
 
@@ -329,23 +319,35 @@ int make_plan(const CcModule* const* mods, int n_nodes, long long B, int T, cons
 #endif
 
 template <class Kern>
-int launch1(Kern kern, const CcKParams& p, long long grid, void* stream) {
+int launch1(Kern kern, const CcKParams& p, void* stream) {
   g_launches.fetch_add(1);
+  const long long grid = (p.n_wtiles + p.wpc - 1) / p.wpc;
+  const size_t smem = ((size_t)p.cta_floats + (size_t)p.wpc * p.warp_floats + CC_PARAM_FLOATS) * 4;
 #ifdef CC_EMULATE
   (void)stream;
-  ccemu::launch((int)grid, p.nthreads, ((size_t)p.smem_floats + CC_PARAM_FLOATS) * 4, [&]() { kern(p); });
+  ccemu::launch((int)grid, p.wpc * 32, smem, [&]() { kern(p); });
   return CC_OK;
 #else
-  const size_t smem = ((size_t)p.smem_floats + CC_PARAM_FLOATS) * 4;
   CC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(unsigned)grid, p.nthreads, smem, (cudaStream_t)stream>>>(p);
+  kern<<<(unsigned)grid, p.wpc * 32, smem, (cudaStream_t)stream>>>(p);
   CC_CUDA_OK(cudaGetLastError());
   return CC_OK;
 #endif
 }
 
-#define CC_LAUNCH_TN(kern, p, grid, stream) \
-  ((p).TN == 10 ? launch1(kern<10>, p, grid, stream) : launch1(kern<8>, p, grid, stream))
+// dispatch on (model tile width, controller mode)
+#define CC_LAUNCH_CM(kern, TNV, p, stream)                                                              \
+  ((p).ctrl_mode == CC_CTRL_NONE ? launch1(kern<TNV, CC_CTRL_NONE>, p, stream)                          \
+   : (p).ctrl_mode == CC_CTRL_TINY ? launch1(kern<TNV, CC_CTRL_TINY>, p, stream)                        \
+                                   : launch1(kern<TNV, CC_CTRL_TILE>, p, stream))
+#ifdef CC_DEV_BUILD_TN13  /* development builds: only the TN = 13 kernels (much faster to compile) */
+#define CC_LAUNCH(kern, p, stream) \
+  ((p).TN == 13 ? CC_LAUNCH_CM(kern, 13, p, stream) : fail(CC_ERR_UNSUPPORTED, "dev build: TN=13 only"))
+#else
+#define CC_LAUNCH(kern, p, stream)                                        \
+  ((p).TN == 8 ? CC_LAUNCH_CM(kern, 8, p, stream)                         \
+   : (p).TN == 13 ? CC_LAUNCH_CM(kern, 13, p, stream) : CC_LAUNCH_CM(kern, 16, p, stream))
+#endif
 
 int n_ckpt_of(int T, int every) { return (T + every - 1) / every; }
 
@@ -371,13 +373,13 @@ int32_t cc_module_supported(const CcModule* m, int32_t with_grad) {
 
 size_t cc_rollout_tape_bytes(const CcModule* m, int64_t B, int32_t T, int32_t ckpt_every) {
   if (!m || B <= 0 || T < 0 || ckpt_every < 1) return 0;
-  const long long Bpad = (B + 255) / 256 * 256;
+  const long long Bpad = (B + 31) / 32 * 32;
   return ((size_t)n_ckpt_of(T, ckpt_every) * m->state_dim * Bpad + 2 * (size_t)T) * sizeof(float);
 }
 
 size_t cc_closedloop_tape_bytes(const CcModule* c, const CcModule* m, int64_t B, int32_t Tr, int32_t ckpt_every) {
   if (!c || !m || B <= 0 || Tr < 0 || ckpt_every < 1) return 0;
-  const long long Bpad = (B + 255) / 256 * 256;
+  const long long Bpad = (B + 31) / 32 * 32;
   return ((size_t)n_ckpt_of(Tr, ckpt_every) * (c->state_dim + m->state_dim + m->output_dim) * Bpad + 2 * (size_t)Tr) * sizeof(float);
 }
 
@@ -400,7 +402,7 @@ int32_t cc_rollout_fwd(const CcModule* m, const float* theta, const float* u, co
   p.tape = (float*)tape;
   p.ckpt_every = tape ? ckpt_every : 1;
   p.n_ckpt = n_ckpt_of(T, p.ckpt_every);
-  return CC_LAUNCH_TN(cc_rollout_fwd_kernel, p, (B + p.BT - 1) / p.BT, stream);
+  return CC_LAUNCH(cc_rollout_fwd_kernel, p, stream);
 }
 
 int32_t cc_closedloop_fwd(const CcModule* c, const CcModule* m, const float* theta_c, const float* theta_m,
@@ -419,8 +421,6 @@ int32_t cc_closedloop_fwd(const CcModule* c, const CcModule* m, const float* the
   if (B == 0 || Tr == 0) return CC_OK;
   CcKParams p;
   PlanOpts o;
-  o.want_uout = u_out != nullptr;
-  o.want_noise = noise != nullptr;
   const CcModule* mods[2] = {c, m};
   rc = make_plan(mods, 2, B, Tr, o, &p);
   if (rc) return rc;
@@ -429,7 +429,7 @@ int32_t cc_closedloop_fwd(const CcModule* c, const CcModule* m, const float* the
   p.tape = (float*)tape;
   p.ckpt_every = tape ? ckpt_every : 1;
   p.n_ckpt = n_ckpt_of(Tr, p.ckpt_every);
-  return CC_LAUNCH_TN(cc_rollout_fwd_kernel, p, (B + p.BT - 1) / p.BT, stream);
+  return CC_LAUNCH(cc_rollout_fwd_kernel, p, stream);
 }
 
 #include "cc_abi_bwd.inc"

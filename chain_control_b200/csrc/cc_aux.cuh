@@ -33,31 +33,29 @@ __global__ void cc_sum_partials_kernel(const float* part, int n, float* out) {
   }
 }
 
-// theta_bar[j] = sum over tiles (fixed order) of the per-CTA partial that maps to parameter j.
-// One thread per (layer, n, r) element of the padded [N][Kp] gradient block.
+// theta_bar[j] = sum over warp tiles (fixed order) of the gradient-record entry that maps to
+// parameter j.  One thread per (layer, n, r) entry of the node's record ([N][K] blocks).
 __global__ void cc_reduce_grad_kernel(const CcKParams p, int node, float* theta_bar, int n_tiles) {
   const CcNodeDev& nd = p.nd[node];
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  int off = nd.gw_off;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // index inside the node's record
+  if (idx >= nd.g_total) return;
   for (int w = 0; w < 2; ++w) {
     const CcMlpDev& mlp = w ? nd.g : nd.f;
     for (int l = 0; l < mlp.L; ++l) {
       const CcLayerDev& L = mlp.layer[l];
-      const int sz = L.N * L.Kp;
-      if (idx >= off && idx < off + sz) {
-        const int n = (idx - off) / L.Kp, r = (idx - off) % L.Kp;
-        if (r >= L.K) return;
+      const int sz = L.N * L.K;
+      if (idx >= L.g_off && idx < L.g_off + sz) {
+        const int n = (idx - L.g_off) / L.K, r = (idx - L.g_off) % L.K;
         const int lc = cc_row_to_logical(nd, L, r);
         int dst = -1;
         if (lc >= 0) dst = L.w_off + n * L.in_log + lc;
         else if (lc == -2 && L.b_off >= 0) dst = L.b_off + n;
         if (dst < 0) return;
         float s = 0.f;
-        for (int t = 0; t < n_tiles; ++t) s += p.gpart[(long long)t * p.gw_total + idx];
+        for (int t = 0; t < n_tiles; ++t) s += p.gpart[(long long)t * p.g_rec + nd.g_base + idx];
         theta_bar[dst] = s;
         return;
       }
-      off += sz;
     }
   }
 }

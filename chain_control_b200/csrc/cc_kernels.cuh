@@ -1,8 +1,9 @@
 // cc_kernels.cuh — device code of the fused neural-ODE rollout (forward) for sm_100a.
 //
-// One persistent CTA per trajectory tile runs the whole time loop: weights are staged once in
-// shared memory, the state tile and the RK4 stage sum live in registers, every layer evaluation is
-// a register-tiled FP32 SGEMM out of shared memory (see cc_plan.h for the layout).
+// Each warp runs the whole time loop for its 32 trajectories (see cc_plan.h): weights are staged once
+// per CTA in shared memory, the state tile and the RK4 stage sum live in registers, every layer
+// evaluation is a register-tiled FP32 SGEMM out of shared memory, and __syncwarp() is the only
+// synchronisation inside the time loop.
 //
 // Restates (no code shared with the reference, which is JAX):
 //   AbstractModel.unroll            cc/core/abstract.py:54-70
@@ -18,12 +19,20 @@
 #define CC_DEV __device__ __forceinline__
 #define CC_DEV_NOINLINE __device__ __noinline__
 #define CC_GRID_CONSTANT __grid_constant__
+#define CC_ASSERT_ALIGNED(ptr, n)
 #else
 #define CC_DEV static inline
 #define CC_DEV_NOINLINE static
 #define CC_GRID_CONSTANT
+#define CC_ASSERT_ALIGNED(ptr, n)                                                          \
+  do {                                                                                     \
+    if (reinterpret_cast<uintptr_t>(ptr) % (n)) {                                          \
+      fprintf(stderr, "ccemu: misaligned %d-byte access at %s:%d\n", (n), __FILE__, __LINE__); \
+      abort();                                                                             \
+    }                                                                                      \
+  } while (0)
 #endif
-#define CC_TILE float (&)[CC_TM][TN]
+#define CC_FULL 0xffffffffu
 
 // ------------------------------------------------------------------------------------------------
 // elementwise pieces
@@ -53,10 +62,28 @@ CC_DEV float cc_ut_grad(int kind, float scale, float u) {
   return 1.f;
 }
 
-struct CcThread {
-  int tid, rg, cg;
-  bool rg_ok;
+// Dynamic shared memory is declared at file scope and every pointer into it is rebuilt from this
+// symbol inside the function that uses it: a shared pointer that travels through a struct or a
+// non-inlined call degrades to a GENERIC pointer (LD.E instead of LDS, ~2x the latency).
+#ifndef CC_EMULATE
+extern __shared__ __align__(16) float cc_smem_[];
+#define CC_SMEM_PTR cc_smem_
+#else
+#define CC_SMEM_PTR (ccemu::st().smem)
+#endif
+
+// per-warp execution context
+struct CcWarp {
+  int lane, rg, cg;  // lane = cg * 8 + rg
+  long long wt;      // warp-tile index
+  long long b0;      // first trajectory of the tile
+  int nact;          // active trajectories (<= 32)
+  int ws_off;        // this warp's shared-memory region (floats from the start of dynamic smem)
+  int cs_off;        // CTA-shared region (weights)
 };
+CC_DEV const CcKParams& cc_params() { return *reinterpret_cast<const CcKParams*>(CC_SMEM_PTR); }
+CC_DEV float* cc_ws(const CcWarp& w) { return CC_SMEM_PTR + w.ws_off; }
+CC_DEV float* cc_cs(const CcWarp& w) { return CC_SMEM_PTR + w.cs_off; }
 
 // physical row of a first-layer source buffer -> logical input column of the MLP
 // (>= 0), -1 = not consumed (zero weight), -2 = bias row.
@@ -81,89 +108,82 @@ CC_DEV float cc_weight_at(const CcNodeDev& nd, const CcLayerDev& L, const float*
   return 0.f;
 }
 
-// stage the weights of one MLP: Wt[K][Np] always, W[N][Kp] and zeroed Wbar[N][Kp] when present
-CC_DEV void cc_stage_mlp(const CcNodeDev& nd, const CcMlpDev& mlp, const float* theta, float* smem, int tid,
+// stage the weights of one MLP into the CTA-shared region (all threads of the CTA):
+//   Wt[K][ldw]: element (k, n) at k*ldw + (n/cpt)*GS + n%cpt, zero padding elsewhere
+//   W[N][ldk] : element (n, r) at n*ldk + (r/kcpt)*GSk + r%kcpt for r < Kin            (backward)
+//   WV[I][N]  : weights of the input rows                                               (backward)
+CC_DEV void cc_stage_mlp(const CcNodeDev& nd, const CcMlpDev& mlp, const float* theta, float* cs, int tid,
                          int nthreads) {
   for (int l = 0; l < mlp.L; ++l) {
     const CcLayerDev& L = mlp.layer[l];
-    float* Wt = smem + L.s_wt;
-    for (int i = tid; i < L.K * L.Np; i += nthreads) Wt[i] = cc_weight_at(nd, L, theta, i % L.Np, i / L.Np);
-    if (L.s_w >= 0) {
-      float* W = smem + L.s_w;
-      for (int i = tid; i < L.N * L.Kp; i += nthreads) W[i] = cc_weight_at(nd, L, theta, i / L.Kp, i % L.Kp);
+    if (L.s_wt >= 0) {
+      float* Wt = cs + L.s_wt;
+      for (int i = tid; i < L.K * L.ldw; i += nthreads) {
+        const int k = i / L.ldw, c = i % L.ldw;
+        const int g = c / L.GS, j = c % L.GS;
+        Wt[i] = (j < L.cpt) ? cc_weight_at(nd, L, theta, g * L.cpt + j, k) : 0.f;
+      }
     }
-    if (L.s_gw >= 0) {
-      float* G = smem + L.s_gw;
-      for (int i = tid; i < L.N * L.Kp; i += nthreads) G[i] = 0.f;
+    if (L.s_w >= 0) {
+      float* W = cs + L.s_w;
+      for (int i = tid; i < L.N * L.ldk; i += nthreads) {
+        const int n = i / L.ldk, c = i % L.ldk;
+        const int g = c / L.GSk, j = c % L.GSk;
+        const int r = g * L.kcpt + j;
+        W[i] = (j < L.kcpt && r < L.Kin) ? cc_weight_at(nd, L, theta, n, r) : 0.f;
+      }
+    }
+    if (L.s_wv >= 0) {
+      float* WV = cs + L.s_wv;
+      for (int i = tid; i < nd.I * L.N; i += nthreads) WV[i] = cc_weight_at(nd, L, theta, i % L.N, nd.row_v + i / L.N);
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// register-tiled SGEMM out of shared memory:  acc[i][j] += sum_k A[k][4rg+i] * Bm[k][col(j)]
-//   col(j) = 4cg + j (j<4) | 4CG + 4cg + (j-4) (j<8) | 8CG + 2cg + (j-8) (TN == 10)
-// so that every LDS.128 / LDS.64 of a warp reads one contiguous, conflict-free span.  The operands
-// of step k+1 are fetched while the FMAs of step k issue (register double buffering).
+// register-tiled SGEMM out of shared memory:  acc[i][j] += sum_k A[k][4rg+i] * Bm[k][cg*GS + j]
+// The operands of step k+1 are fetched while the FMAs of step k issue (register double buffering).
 // ------------------------------------------------------------------------------------------------
 template <int TN>
 struct CcFrag {
-  float4 a, b0, b1;
-  float b2x, b2y;
+  float4 a;
+  float b[TN];
 };
-#ifdef CC_EMULATE
-#define CC_ASSERT_ALIGNED(ptr, n)                                                          \
-  do {                                                                                     \
-    if (reinterpret_cast<uintptr_t>(ptr) % (n)) {                                          \
-      fprintf(stderr, "ccemu: misaligned %d-byte access at %s:%d\n", (n), __FILE__, __LINE__); \
-      abort();                                                                             \
-    }                                                                                      \
-  } while (0)
-#else
-#define CC_ASSERT_ALIGNED(ptr, n)
-#endif
 template <int TN>
-CC_DEV void cc_frag_load(CcFrag<TN>& f, const float* A, const float* B0, const float* B1, const float* B2) {
-  CC_ASSERT_ALIGNED(A, 16); CC_ASSERT_ALIGNED(B0, 16); CC_ASSERT_ALIGNED(B1, 16);
-  if (TN == 10) CC_ASSERT_ALIGNED(B2, 8);
+CC_DEV void cc_frag_load(CcFrag<TN>& f, const float* A, const float* Bp) {
+  CC_ASSERT_ALIGNED(A, 16);
+  CC_ASSERT_ALIGNED(Bp, 16);
   f.a = *reinterpret_cast<const float4*>(A);
-  f.b0 = *reinterpret_cast<const float4*>(B0);
-  f.b1 = *reinterpret_cast<const float4*>(B1);
-  if (TN == 10) {
-    f.b2x = B2[0];
-    f.b2y = B2[1];
+#pragma unroll
+  for (int q = 0; q < TN / 4; ++q) {
+    const float4 v = *reinterpret_cast<const float4*>(Bp + 4 * q);
+    f.b[4 * q + 0] = v.x; f.b[4 * q + 1] = v.y; f.b[4 * q + 2] = v.z; f.b[4 * q + 3] = v.w;
   }
+#pragma unroll
+  for (int j = TN / 4 * 4; j < TN; ++j) f.b[j] = Bp[j];
 }
 template <int TN>
 CC_DEV void cc_frag_fma(const CcFrag<TN>& f, float (&acc)[CC_TM][TN]) {
   const float av[4] = {f.a.x, f.a.y, f.a.z, f.a.w};
-  float bv[10] = {f.b0.x, f.b0.y, f.b0.z, f.b0.w, f.b1.x, f.b1.y, f.b1.z, f.b1.w, 0.f, 0.f};
-  if (TN == 10) { bv[8] = f.b2x; bv[9] = f.b2y; }
 #pragma unroll
   for (int i = 0; i < CC_TM; ++i)
 #pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], f.b[j], acc[i][j]);
 }
-// A -> &A[0][4rg]; Bm -> &Bm[0][0]; CG = column groups of Bm; cg = this thread's group
+// A -> &A[0][4rg] (row stride 32); Bp -> &Bm[0][cg*GS] (row stride ldb)
 template <int TN>
-CC_DEV void cc_gemm_tile(const float* A, int lda, const float* Bm, int ldb, int K, int CG, int cg,
-                         float (&acc)[CC_TM][TN]) {
-  const float* B0 = Bm + 4 * cg;
-  const float* B1 = Bm + 4 * CG + 4 * cg;
-  const float* B2 = Bm + 8 * CG + 2 * cg;
+CC_DEV void cc_gemm_tile(const float* A, const float* Bp, int ldb, int K, float (&acc)[CC_TM][TN]) {
   CcFrag<TN> cur, nxt;
-  cc_frag_load<TN>(cur, A, B0, B1, B2);
+  cc_frag_load<TN>(cur, A, Bp);
 #pragma unroll 2
   for (int k = 1; k < K; ++k) {
-    cc_frag_load<TN>(nxt, A + k * lda, B0 + k * ldb, B1 + k * ldb, B2 + k * ldb);
+    A += CC_LD;
+    Bp += ldb;
+    cc_frag_load<TN>(nxt, A, Bp);
     cc_frag_fma<TN>(cur, acc);
     cur = nxt;
   }
   cc_frag_fma<TN>(cur, acc);
-}
-
-template <int TN>
-CC_DEV int cc_col(int CG, int cg, int j) {
-  return j < 4 ? 4 * cg + j : (j < 8 ? 4 * CG + 4 * cg + (j - 4) : 8 * CG + 2 * cg + (j - 8));
 }
 
 template <int TN>
@@ -174,140 +194,126 @@ CC_DEV void cc_zero_tile(float (&t)[CC_TM][TN]) {
     for (int j = 0; j < TN; ++j) t[i][j] = 0.f;
 }
 
-// tile <-> feature-major buffer rows [n][BTP]
+// tile <-> feature-major buffer rows [n][32]; thread owns rows cg*cpt + j (j < cpt), columns 4rg..4rg+3
 template <int TN>
-CC_DEV void cc_load_tile(const float* buf, int BTP, int N, int CG, const CcThread& th, float (&t)[CC_TM][TN]) {
+CC_DEV void cc_load_tile(const float* buf, int N, int cpt, const CcWarp& w, float (&t)[CC_TM][TN]) {
 #pragma unroll
   for (int j = 0; j < TN; ++j) {
-    const int n = cc_col<TN>(CG, th.cg, j);
+    const int n = w.cg * cpt + j;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (n < N) { CC_ASSERT_ALIGNED(buf + n * BTP + 4 * th.rg, 16); v = *reinterpret_cast<const float4*>(buf + n * BTP + 4 * th.rg); }
+    if (j < cpt && n < N) v = *reinterpret_cast<const float4*>(buf + n * CC_LD + 4 * w.rg);
     t[0][j] = v.x; t[1][j] = v.y; t[2][j] = v.z; t[3][j] = v.w;
   }
 }
 template <int TN>
-CC_DEV void cc_store_tile(float* buf, int BTP, int N, int CG, const CcThread& th, const float (&t)[CC_TM][TN]) {
+CC_DEV void cc_store_tile(float* buf, int N, int cpt, const CcWarp& w, const float (&t)[CC_TM][TN]) {
 #pragma unroll
   for (int j = 0; j < TN; ++j) {
-    const int n = cc_col<TN>(CG, th.cg, j);
-    if (n < N) *reinterpret_cast<float4*>(buf + n * BTP + 4 * th.rg) = make_float4(t[0][j], t[1][j], t[2][j], t[3][j]);
+    const int n = w.cg * cpt + j;
+    if (j < cpt && n < N) *reinterpret_cast<float4*>(buf + n * CC_LD + 4 * w.rg) = make_float4(t[0][j], t[1][j], t[2][j], t[3][j]);
   }
 }
 
 // one layer as a tile GEMM; leaves the raw accumulators (bias included via the 1-row) in acc
 template <int TN>
-CC_DEV void cc_layer_gemm(const CcKParams& p, const CcLayerDev& L, const float* src, const float* smem,
-                          const CcThread& th, float (&acc)[CC_TM][TN]) {
+CC_DEV void cc_layer_gemm(const CcLayerDev& L, const float* src, const CcWarp& w, float (&acc)[CC_TM][TN]) {
   cc_zero_tile<TN>(acc);
-  if (th.rg_ok && th.cg < L.CG)
-    cc_gemm_tile<TN>(src + 4 * th.rg, p.BTP, smem + L.s_wt, L.Np, L.K, L.CG, th.cg, acc);
+  cc_gemm_tile<TN>(src + 4 * w.rg, cc_cs(w) + L.s_wt + w.cg * L.GS, L.ldw, L.K, acc);
 }
 
-// split-K path for very narrow layers (N <= CC_MAX_SKINNY): every thread sums a strided slice of K
-// for its 4 trajectories, partials meet in P[cg][n][BTP], then a fixed-order reduction.
-// dst[n][traj] = scale * act(sum).  Ends with a barrier.
-CC_DEV void cc_layer_skinny(const CcKParams& p, const CcLayerDev& L, const float* src, float* smem, float* P,
-                            float* dst, float scale, const CcThread& th) {
+// very narrow layers (N <= CC_MAX_SKINNY): the 4 column groups split K, partial sums meet through
+// two shuffles (lane bits 3,4 = cg); fixed order -> deterministic.  dst[n][traj] = scale*act(sum).
+// Ends with __syncwarp().
+CC_DEV void cc_layer_skinny(const CcLayerDev& L, const float* src, float* dst, float scale, const CcWarp& w) {
   float part[CC_MAX_SKINNY][CC_TM];
 #pragma unroll
   for (int n = 0; n < CC_MAX_SKINNY; ++n)
 #pragma unroll
     for (int i = 0; i < CC_TM; ++i) part[n][i] = 0.f;
-  const float* Wt = smem + L.s_wt;
-  if (th.rg_ok) {
-    for (int k = th.cg; k < L.K; k += p.CGT) {
-      const float4 a = *reinterpret_cast<const float4*>(src + k * p.BTP + 4 * th.rg);
+  const float* Wt = cc_cs(w) + L.s_wt;
+  for (int k = w.cg; k < L.K; k += 4) {
+    const float4 a = *reinterpret_cast<const float4*>(src + k * CC_LD + 4 * w.rg);
 #pragma unroll
-      for (int n = 0; n < CC_MAX_SKINNY; ++n) {
-        if (n < L.N) {
-          const float w = Wt[k * L.Np + n];
-          part[n][0] = fmaf(a.x, w, part[n][0]);
-          part[n][1] = fmaf(a.y, w, part[n][1]);
-          part[n][2] = fmaf(a.z, w, part[n][2]);
-          part[n][3] = fmaf(a.w, w, part[n][3]);
-        }
+    for (int n = 0; n < CC_MAX_SKINNY; ++n) {
+      if (n < L.N) {
+        const float wv = Wt[k * L.ldw + (n / L.cpt) * L.GS + n % L.cpt];
+        part[n][0] = fmaf(a.x, wv, part[n][0]);
+        part[n][1] = fmaf(a.y, wv, part[n][1]);
+        part[n][2] = fmaf(a.z, wv, part[n][2]);
+        part[n][3] = fmaf(a.w, wv, part[n][3]);
       }
     }
+  }
 #pragma unroll
-    for (int n = 0; n < CC_MAX_SKINNY; ++n)
-      if (n < L.N)
-        *reinterpret_cast<float4*>(P + (th.cg * CC_MAX_SKINNY + n) * p.BTP + 4 * th.rg) =
-            make_float4(part[n][0], part[n][1], part[n][2], part[n][3]);
-  }
-  __syncthreads();
-  for (int idx = th.tid; idx < L.N * p.RG; idx += p.nthreads) {
-    const int n = idx / p.RG, r = idx % p.RG;
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int c = 0; c < p.CGT; ++c) {
-      const float4 v = *reinterpret_cast<const float4*>(P + (c * CC_MAX_SKINNY + n) * p.BTP + 4 * r);
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  for (int n = 0; n < CC_MAX_SKINNY; ++n) {
+    if (n < L.N) {
+#pragma unroll
+      for (int i = 0; i < CC_TM; ++i) {
+        float v = part[n][i];
+        v += __shfl_xor_sync(CC_FULL, v, 8);
+        v += __shfl_xor_sync(CC_FULL, v, 16);
+        part[n][i] = scale * cc_act(L.act, v);
+      }
+      if (w.cg == 0)
+        *reinterpret_cast<float4*>(dst + n * CC_LD + 4 * w.rg) = make_float4(part[n][0], part[n][1], part[n][2], part[n][3]);
     }
-    s.x = scale * cc_act(L.act, s.x);
-    s.y = scale * cc_act(L.act, s.y);
-    s.z = scale * cc_act(L.act, s.z);
-    s.w = scale * cc_act(L.act, s.w);
-    *reinterpret_cast<float4*>(dst + n * p.BTP + 4 * r) = s;
   }
-  __syncthreads();
+  __syncwarp();
 }
 
-// hidden layers of an MLP (all but the last): src -> hidden buffers.  returns the input buffer of
-// the last layer.  hbuf[l] overrides the hidden buffer of layer l (backward keeps them per stage).
+// hidden layers of an MLP (all but the last): src -> hidden buffers (per warp).  Returns the input
+// buffer of the last layer.  hbuf[l] overrides the hidden buffer of layer l (backward keeps them
+// per stage).
 template <int TN>
-CC_DEV const float* cc_mlp_hidden(const CcKParams& p, const CcMlpDev& mlp, const float* src, float* smem,
-                                  const int* hbuf, const CcThread& th) {
+CC_DEV const float* cc_mlp_hidden(const CcMlpDev& mlp, const float* src, const int* hbuf, const CcWarp& w) {
   float acc[CC_TM][TN];
   for (int l = 0; l < mlp.L - 1; ++l) {
     const CcLayerDev& L = mlp.layer[l];
-    float* dst = smem + (hbuf ? hbuf[l] : L.s_out);
+    float* dst = cc_ws(w) + (hbuf ? hbuf[l] : L.w_out);
     if (L.N <= CC_MAX_SKINNY) {
-      cc_layer_skinny(p, L, src, smem, smem + p.nd[0].s_P, dst, 1.f, th);
+      cc_layer_skinny(L, src, dst, 1.f, w);
     } else {
-      cc_layer_gemm<TN>(p, L, src, smem, th, acc);
-      if (th.rg_ok && th.cg < L.CG) {
+      cc_layer_gemm<TN>(L, src, w, acc);
 #pragma unroll
-        for (int i = 0; i < CC_TM; ++i)
+      for (int i = 0; i < CC_TM; ++i)
 #pragma unroll
-          for (int j = 0; j < TN; ++j) acc[i][j] = cc_act(L.act, acc[i][j]);
-        cc_store_tile<TN>(dst, p.BTP, L.N, L.CG, th, acc);
-      }
-      __syncthreads();
+        for (int j = 0; j < TN; ++j) acc[i][j] = cc_act(L.act, acc[i][j]);
+      cc_store_tile<TN>(dst, L.N, L.cpt, w, acc);
+      __syncwarp();
     }
     src = dst;
   }
   return src;
 }
 
-// readout: OUT = out_scale * g(src rows).  Ends with a barrier.
+// readout: OUT = out_scale * g(src rows).  Ends with __syncwarp().
 template <int TN>
-CC_DEV_NOINLINE void cc_readout(const CcKParams& p, const CcNodeDev& nd, const float* src, float* smem, const int* ghbuf,
-                       const CcThread& th) {
-  const float* in = cc_mlp_hidden<TN>(p, nd.g, src, smem, ghbuf, th);
+CC_DEV_NOINLINE void cc_readout(int node, int src_off, bool keep_gh, const CcWarp w) {
+  const CcNodeDev& nd = cc_params().nd[node];
+  const int* ghbuf = keep_gh ? nd.w_GH : nullptr;
+  const float* in = cc_mlp_hidden<TN>(nd.g, cc_ws(w) + src_off, ghbuf, w);
   const CcLayerDev& L = nd.g.layer[nd.g.L - 1];
-  float* OUT = smem + nd.s_OUT;
+  float* OUT = cc_ws(w) + nd.w_OUT;
   if (L.N <= CC_MAX_SKINNY) {
-    cc_layer_skinny(p, L, in, smem, smem + p.nd[0].s_P, OUT, nd.out_scale, th);
+    cc_layer_skinny(L, in, OUT, nd.out_scale, w);
   } else {
     float acc[CC_TM][TN];
-    cc_layer_gemm<TN>(p, L, in, smem, th, acc);
-    if (th.rg_ok && th.cg < L.CG) {
+    cc_layer_gemm<TN>(L, in, w, acc);
 #pragma unroll
-      for (int i = 0; i < CC_TM; ++i)
+    for (int i = 0; i < CC_TM; ++i)
 #pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = nd.out_scale * cc_act(L.act, acc[i][j]);
-      cc_store_tile<TN>(OUT, p.BTP, L.N, L.CG, th, acc);
-    }
-    __syncthreads();
+      for (int j = 0; j < TN; ++j) acc[i][j] = nd.out_scale * cc_act(L.act, acc[i][j]);
+    cc_store_tile<TN>(OUT, L.N, L.cpt, w, acc);
+    __syncwarp();
   }
 }
 
 // k = f(src): hidden layers to smem, last layer into registers (activation applied)
 template <int TN>
-CC_DEV void cc_rhs(const CcKParams& p, const CcNodeDev& nd, const float* src, float* smem, const int* hbuf,
-                   const CcThread& th, float (&k)[CC_TM][TN]) {
-  const float* in = cc_mlp_hidden<TN>(p, nd.f, src, smem, hbuf, th);
+CC_DEV void cc_rhs(const CcNodeDev& nd, const float* src, const int* hbuf, const CcWarp& w, float (&k)[CC_TM][TN]) {
+  const float* in = cc_mlp_hidden<TN>(nd.f, src, hbuf, w);
   const CcLayerDev& L = nd.f.layer[nd.f.L - 1];
-  cc_layer_gemm<TN>(p, L, in, smem, th, k);
+  cc_layer_gemm<TN>(L, in, w, k);
   if (L.act != CC_ACT_IDENTITY) {
 #pragma unroll
     for (int i = 0; i < CC_TM; ++i)
@@ -316,193 +322,282 @@ CC_DEV void cc_rhs(const CcKParams& p, const CcNodeDev& nd, const float* src, fl
   }
 }
 
-// write the node's state tile into the tape record of checkpoint `ck`
+// the node's state tile -> tape record `ck` (128-byte coalesced float4 stores)
 template <int TN>
-CC_DEV void cc_tape_store(const CcKParams& p, const CcNodeDev& nd, long long tile, int ck, const CcThread& th,
-                          const float (&x)[CC_TM][TN]) {
-  float* rec = p.tape + ((long long)ck * p.tape_rows + nd.tape_row) * p.Bpad + tile * p.BT;
-  if (th.rg_ok && th.cg < nd.CGs) {
+CC_DEV void cc_tape_store(const CcKParams& p, const CcNodeDev& nd, int ck, const CcWarp& w, const float (&x)[CC_TM][TN]) {
+  float* rec = p.tape + ((long long)ck * p.tape_rows + nd.tape_row) * p.Bpad + w.b0;
 #pragma unroll
-    for (int j = 0; j < TN; ++j) {
-      const int n = cc_col<TN>(nd.CGs, th.cg, j);
-      if (n < nd.S) *reinterpret_cast<float4*>(rec + (long long)n * p.Bpad + 4 * th.rg) = make_float4(x[0][j], x[1][j], x[2][j], x[3][j]);
-    }
+  for (int j = 0; j < TN; ++j) {
+    const int n = w.cg * nd.cptS + j;
+    if (j < nd.cptS && n < nd.S) *reinterpret_cast<float4*>(rec + (long long)n * p.Bpad + 4 * w.rg) = make_float4(x[0][j], x[1][j], x[2][j], x[3][j]);
   }
 }
 
-// One step of a node.  On entry X holds [x ; t ; v ; 1], ZA/ZB hold the same t(+h/2)/v/1 rows.
-// On exit X holds x_next, OUT holds the readout.  `stage_bufs`: when non-null (backward recompute)
-// the stage inputs are kept in s_Z[1..3] instead of the ZA/ZB ping-pong and hidden activations /
-// k_i are kept per stage.  Ends with a barrier.
+// One step of a tile-path node.  On entry X holds [x ; t ; v ; 1] and Z the same v / 1 rows.
+// On exit X holds x_next and OUT the readout.  keep (backward recompute): stage inputs stay in
+// ZS[0..3], hidden activations / k_i are kept per stage, X keeps x.  Ends with __syncwarp().
 template <int TN>
-CC_DEV_NOINLINE void cc_node_step(const CcKParams& p, const CcNodeDev& nd, float* smem, const CcThread& th, float t,
-                         bool keep, bool do_readout, bool write_tape, long long tile, int ck) {
-  float* X = smem + nd.s_X;
+CC_DEV_NOINLINE void cc_node_step(int node, const CcWarp w, float t, bool keep, bool do_readout, bool write_tape,
+                                  int ck) {
+  const CcKParams& p = cc_params();
+  const CcNodeDev& nd = p.nd[node];
+  float* X = cc_ws(w) + nd.w_X;
+  float* Z = cc_ws(w) + nd.w_Z;
   const float h = nd.dt;
-  const bool own = th.rg_ok && th.cg < nd.CGs;
-  if (nd.pre && do_readout) cc_readout<TN>(p, nd, X, smem, keep ? nd.s_GH : nullptr, th);
+  if (nd.pre && do_readout) cc_readout<TN>(node, nd.w_X, keep, w);
   float xr[CC_TM][TN], k[CC_TM][TN];
-  cc_load_tile<TN>(X, p.BTP, own ? nd.S : 0, nd.CGs, th, xr);
-  if (write_tape) cc_tape_store<TN>(p, nd, tile, ck, th, xr);
+  cc_load_tile<TN>(X, nd.S, nd.cptS, w, xr);
+  if (write_tape) cc_tape_store<TN>(p, nd, ck, w, xr);
   if (nd.integrator == CC_INT_RK4) {
     float ks[CC_TM][TN];
     for (int s = 0; s < 4; ++s) {
-      float* src;
-      float* dst;
-      if (keep) {
-        src = smem + nd.s_Z[s];
-        dst = s < 3 ? smem + nd.s_Z[s + 1] : X;
-      } else {
-        src = s == 0 ? X : (s == 2 ? smem + nd.s_ZB : smem + nd.s_ZA);
-        dst = s == 0 ? smem + nd.s_ZA : (s == 1 ? smem + nd.s_ZB : (s == 2 ? smem + nd.s_ZA : X));
-        // stage 3 reads ZA again, now at time t + h (ZA is idle during stage 2)
-        if (s == 2 && nd.has_t && th.tid < p.BT) smem[nd.s_ZA + nd.row_t * p.BTP + th.tid] = t + h;
+      float* src = keep ? cc_ws(w) + nd.w_ZS[s] : ((s & 1) ? Z : X);
+      float* dst = keep ? (s < 3 ? cc_ws(w) + nd.w_ZS[s + 1] : nullptr) : ((s & 1) ? X : Z);
+      if (nd.has_t && !keep && s > 0) {  // stage times t, t+h/2, t+h/2, t+h  (integrate.py:6-13)
+        src[nd.row_t * CC_LD + w.lane] = s == 3 ? t + h : t + h / 2.f;
+        __syncwarp();
       }
-      cc_rhs<TN>(p, nd, src, smem, keep ? nd.s_HS[s] : nullptr, th, k);
-      if (own) {
-        if (keep && nd.s_KS[s] >= 0) cc_store_tile<TN>(smem + nd.s_KS[s], p.BTP, nd.S, nd.CGs, th, k);
-#pragma unroll
-        for (int i = 0; i < CC_TM; ++i)
-#pragma unroll
-          for (int j = 0; j < TN; ++j) {
-            const float kk = k[i][j];
-            if (s == 0) {
-              ks[i][j] = kk;
-              k[i][j] = xr[i][j] + h * kk / 2.f;
-            } else if (s == 1) {
-              ks[i][j] = ks[i][j] + 2.f * kk;
-              k[i][j] = xr[i][j] + h * kk / 2.f;
-            } else if (s == 2) {
-              ks[i][j] = ks[i][j] + 2.f * kk;
-              k[i][j] = xr[i][j] + h * kk;
-            } else {
-              k[i][j] = xr[i][j] + h * ((1.f / 6.f) * (ks[i][j] + kk));
-            }
-          }
-        if (!(keep && s == 3)) cc_store_tile<TN>(dst, p.BTP, nd.S, nd.CGs, th, k);
-      }
-      __syncthreads();
-    }
-  } else {
-    cc_rhs<TN>(p, nd, X, smem, keep ? nd.s_HS[0] : nullptr, th, k);
-    if (own) {
-      if (keep && nd.s_KS[0] >= 0) cc_store_tile<TN>(smem + nd.s_KS[0], p.BTP, nd.S, nd.CGs, th, k);
+      cc_rhs<TN>(nd, src, keep ? nd.w_HS[s] : nullptr, w, k);
+      if (keep && nd.w_KS[s] >= 0) cc_store_tile<TN>(cc_ws(w) + nd.w_KS[s], nd.S, nd.cptS, w, k);
 #pragma unroll
       for (int i = 0; i < CC_TM; ++i)
 #pragma unroll
-        for (int j = 0; j < TN; ++j)
-          k[i][j] = nd.integrator == CC_INT_EE ? xr[i][j] + h * k[i][j] : k[i][j];
+        for (int j = 0; j < TN; ++j) {
+          const float kk = k[i][j];
+          if (s == 0) {
+            ks[i][j] = kk;
+            k[i][j] = xr[i][j] + h * kk / 2.f;
+          } else if (s == 1) {
+            ks[i][j] = ks[i][j] + 2.f * kk;
+            k[i][j] = xr[i][j] + h * kk / 2.f;
+          } else if (s == 2) {
+            ks[i][j] = ks[i][j] + 2.f * kk;
+            k[i][j] = xr[i][j] + h * kk;
+          } else {
+            k[i][j] = xr[i][j] + h * ((1.f / 6.f) * (ks[i][j] + kk));
+          }
+        }
+      if (dst) cc_store_tile<TN>(dst, nd.S, nd.cptS, w, k);
+      __syncwarp();
     }
-    __syncthreads();  // everyone finished reading X
-    if (own && !keep) cc_store_tile<TN>(X, p.BTP, nd.S, nd.CGs, th, k);
-    __syncthreads();
+  } else {
+    cc_rhs<TN>(nd, X, keep ? nd.w_HS[0] : nullptr, w, k);
+    if (keep && nd.w_KS[0] >= 0) cc_store_tile<TN>(cc_ws(w) + nd.w_KS[0], nd.S, nd.cptS, w, k);
+#pragma unroll
+    for (int i = 0; i < CC_TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) k[i][j] = nd.integrator == CC_INT_EE ? xr[i][j] + h * k[i][j] : k[i][j];
+    __syncwarp();  // every lane finished reading X
+    if (!keep) cc_store_tile<TN>(X, nd.S, nd.cptS, w, k);
+    __syncwarp();
   }
   if (!nd.pre && do_readout) {
-    // post-step readout g([x_next ; t ; v]); in `keep` mode X must stay x (the reverse pass needs
-    // it), so x_next goes to ZA's state rows, whose t / v / 1 rows equal X's up to t (set by caller)
+    // post-step readout g([x_next ; t ; v]) with the PRE-step time (neural_ode_model.py:129-133)
     if (keep) {
-      float* XN = smem + nd.s_ZA;
-      if (own) cc_store_tile<TN>(XN, p.BTP, nd.S, nd.CGs, th, k);
-      __syncthreads();
-      cc_readout<TN>(p, nd, XN, smem, nd.s_GH, th);
+      float* XN = cc_ws(w) + nd.w_XN;  // t / v / 1 rows were set by cc_set_inputs
+      cc_store_tile<TN>(XN, nd.S, nd.cptS, w, k);
+      __syncwarp();
+      cc_readout<TN>(node, nd.w_XN, true, w);
     } else {
-      cc_readout<TN>(p, nd, X, smem, nullptr, th);
+      if (nd.has_t) {
+        X[nd.row_t * CC_LD + w.lane] = t;
+        __syncwarp();
+      }
+      cc_readout<TN>(node, nd.w_X, false, w);
     }
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// I/O staging: global [B][Tlen][W] (trajectory-major, as the reference lays it out) <-> smem
-// [e][BTP] with e = (step - k0) * W + w.  Global accesses are coalesced along e.
-// ------------------------------------------------------------------------------------------------
-CC_DEV void cc_stage_in(const CcKParams& p, const float* g, int ne, long long rowlen, long long eoff, int nvalid,
-                        long long b0, float* s, int tid) {
-  for (int idx = tid; idx < p.BT * ne; idx += p.nthreads) {
-    const int traj = idx / ne, e = idx % ne;
-    float v = 0.f;
-    if (b0 + traj < p.B && e < nvalid) v = __ldg(g + (b0 + traj) * rowlen + eoff + e);
-    s[e * p.BTP + traj] = v;
-  }
-}
-CC_DEV void cc_stage_out(const CcKParams& p, float* g, int ne, long long rowlen, long long eoff, int nvalid,
-                         long long b0, const float* s, int tid) {
-  for (int idx = tid; idx < p.BT * ne; idx += p.nthreads) {
-    const int traj = idx / ne, e = idx % ne;
-    if (b0 + traj < p.B && e < nvalid) g[(b0 + traj) * rowlen + eoff + e] = s[e * p.BTP + traj];
-  }
-}
-
-// zero the stage buffers, set the constant-1 rows
-CC_DEV void cc_init_node_buffers(const CcKParams& p, const CcNodeDev& nd, float* smem, int tid, bool bwd) {
-  const int nbuf = 3;
-  const int bufs[3] = {nd.s_X, nd.s_ZA, nd.s_ZB};
-  for (int b = 0; b < nbuf; ++b) {
-    float* buf = smem + bufs[b];
-    for (int i = tid; i < nd.K0 * p.BTP; i += p.nthreads) buf[i] = (i / p.BTP == nd.row_one) ? 1.f : 0.f;
-  }
-  if (bwd) {
-    for (int s = 1; s < 4; ++s) {
-      if (nd.s_Z[s] < 0) continue;
-      float* buf = smem + nd.s_Z[s];
-      for (int i = tid; i < nd.K0 * p.BTP; i += p.nthreads) buf[i] = (i / p.BTP == nd.row_one) ? 1.f : 0.f;
+// zero a node's per-warp buffers and set the constant-1 rows (one warp)
+CC_DEV void cc_init_node_buffers(const CcNodeDev& nd, const CcWarp& w, bool bwd) {
+  if (nd.tiny && !bwd) return;
+  auto init = [&](int off, int rows, int one_row) {
+    if (off < 0) return;
+    float* buf = cc_ws(w) + off;
+    for (int r = 0; r < rows; ++r) buf[r * CC_LD + w.lane] = (r == one_row) ? 1.f : 0.f;
+  };
+  if (!nd.tiny) {
+    init(nd.w_X, nd.K0, nd.row_one);
+    init(nd.w_Z, nd.K0, nd.row_one);
+    init(nd.w_OUT, nd.O, -1);
+    for (int which = 0; which < 2; ++which) {
+      const CcMlpDev& mlp = which ? nd.g : nd.f;
+      for (int l = 0; l < mlp.L - 1; ++l) init(mlp.layer[l].w_out, mlp.layer[l].N + 1, mlp.layer[l].N);
     }
   }
-  for (int which = 0; which < 2; ++which) {
-    const CcMlpDev& mlp = which ? nd.g : nd.f;
-    for (int l = 0; l < mlp.L - 1; ++l) {
-      const CcLayerDev& L = mlp.layer[l];
-      const int rows = L.N + 1;
-      const int nst = bwd ? (which ? 1 : nd.n_stages) : 1;
-      for (int s = 0; s < nst; ++s) {
-        const int off = bwd ? (which ? nd.s_GH[l] : nd.s_HS[s][l]) : L.s_out;
-        float* buf = smem + off;
-        for (int i = tid; i < rows * p.BTP; i += p.nthreads) buf[i] = (i / p.BTP == L.N) ? 1.f : 0.f;
+  if (bwd && !nd.tiny) {
+    for (int s = 1; s < 4; ++s) init(nd.w_ZS[s], nd.K0, nd.row_one);
+    init(nd.w_XN, nd.K0, nd.row_one);
+    for (int s = 0; s < 4; ++s)
+      for (int l = 0; l < nd.f.L - 1; ++l) init(nd.w_HS[s][l], nd.f.layer[l].N + 1, nd.f.layer[l].N);
+    for (int l = 0; l < nd.g.L - 1; ++l) init(nd.w_GH[l], nd.g.layer[l].N + 1, nd.g.layer[l].N);
+    init(nd.w_LAM, nd.S, -1);
+    init(nd.w_VB, nd.I > 0 ? nd.I : 1, -1);
+    init(nd.w_OB, nd.O, -1);
+    for (int which = 0; which < 2; ++which) {
+      const CcMlpDev& mlp = which ? nd.g : nd.f;
+      for (int l = 0; l < mlp.L; ++l) {
+        const CcLayerDev& L = mlp.layer[l];
+        if (L.w_gw >= 0)
+          for (int i = w.lane; i < L.N * L.K; i += 32) cc_ws(w)[L.w_gw + i] = 0.f;
       }
     }
   }
+  if (bwd && nd.tiny && nd.w_GP >= 0) init(nd.w_GP, nd.g_total, -1);
 }
 
-// set the t / v rows of a node's stage buffers for the coming step (thread `traj` of the tile)
-CC_DEV void cc_set_inputs(const CcKParams& p, const CcNodeDev& nd, float* smem, int traj, const float* v, float t,
-                          bool keep) {
+// set the t / v rows of a tile-path node's stage buffers for the coming step (lane = trajectory).
+// mode 0: forward (X and Z); 1: keep / backward recompute (X, ZS[1..3], XN); 2: X only
+CC_DEV void cc_set_inputs(const CcNodeDev& nd, const CcWarp& w, const float (&v)[CC_TINY_K], float t, int mode) {
   const float h = nd.dt;
-  float* X = smem + nd.s_X;
-  float* B1 = smem + (keep ? nd.s_Z[1] : nd.s_ZA);
-  float* B2 = smem + (keep ? nd.s_Z[2] : nd.s_ZB);
-  for (int i = 0; i < nd.I; ++i) {
-    const float ut = cc_ut(nd.ut, nd.u_scale, v[i]);
-    const int o = (nd.row_v + i) * p.BTP + traj;
-    X[o] = ut;
-    if (nd.integrator == CC_INT_RK4) {
-      B1[o] = ut;
-      B2[o] = ut;
-      if (keep) smem[nd.s_Z[3] + o] = ut;
+  float* X = cc_ws(w) + nd.w_X;
+#pragma unroll
+  for (int i = 0; i < CC_TINY_K; ++i) {
+    if (i < nd.I) {
+      const float ut = cc_ut(nd.ut, nd.u_scale, v[i]);
+      const int o = (nd.row_v + i) * CC_LD + w.lane;
+      X[o] = ut;
+      if (mode == 1) {
+        if (nd.integrator == CC_INT_RK4)
+          for (int s = 1; s < 4; ++s) cc_ws(w)[nd.w_ZS[s] + o] = ut;
+        if (nd.w_XN >= 0) cc_ws(w)[nd.w_XN + o] = ut;
+      } else if (mode == 0 && nd.integrator == CC_INT_RK4) {
+        cc_ws(w)[nd.w_Z + o] = ut;
+      }
     }
-    if (keep && !nd.pre) smem[nd.s_ZA + o] = ut;  // post-step readout source in keep mode
   }
   if (nd.has_t) {
-    const int o = nd.row_t * p.BTP + traj;
+    const int o = nd.row_t * CC_LD + w.lane;
     X[o] = t;
-    if (nd.integrator == CC_INT_RK4) {
-      B1[o] = t + h / 2.f;
-      B2[o] = t + h / 2.f;
-      if (keep) smem[nd.s_Z[3] + o] = t + h;
+    if (mode == 1) {
+      if (nd.integrator == CC_INT_RK4) {
+        cc_ws(w)[nd.w_ZS[1] + o] = t + h / 2.f;
+        cc_ws(w)[nd.w_ZS[2] + o] = t + h / 2.f;
+        cc_ws(w)[nd.w_ZS[3] + o] = t + h;
+      }
+      if (nd.w_XN >= 0) cc_ws(w)[nd.w_XN + o] = t;
     }
-    if (keep && !nd.pre) smem[nd.s_ZA + o] = t;
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// "tiny" nodes (single-layer f and g, S <= 8, rows <= 12, O <= 4): one trajectory per LANE, the
+// whole step in registers, weights read as warp-uniform (broadcast) shared-memory loads.
+// Used for the compact feedback controller (neural_ode_controller_compact_example.py:106-129),
+// whose arithmetic is ~1% of the closed loop but would otherwise idle 3 of 4 column groups.
+// ------------------------------------------------------------------------------------------------
+struct CcTinyStage {
+  float in[CC_TINY_K];  // [z ; t ; v~ ; 1]
+};
+
+CC_DEV void cc_tiny_build_in(const CcNodeDev& nd, const float (&z)[CC_TINY_S], float t, const float* vt, float (&in)[CC_TINY_K]) {
+#pragma unroll
+  for (int r = 0; r < CC_TINY_K; ++r) {
+    float val = 0.f;
+    if (r < nd.S) {
+#pragma unroll
+      for (int s = 0; s < CC_TINY_S; ++s)
+        if (s == r) val = z[s];
+    } else if (nd.has_t && r == nd.row_t) val = t;
+    else if (r >= nd.row_v && r < nd.row_v + nd.I) val = vt[r - nd.row_v];
+    else if (r == nd.row_one) val = 1.f;
+    in[r] = val;
+  }
+}
+// out[n] = act(sum_k in[k] * Wt[k][n])   (Wt compact: ldw = round4(N), column n at n)
+template <int NMAX>
+CC_DEV void cc_tiny_matvec(const CcLayerDev& L, const float* cs, const float (&in)[CC_TINY_K], float (&out)[NMAX]) {
+  const float* Wt = cs + L.s_wt;
+#pragma unroll
+  for (int n = 0; n < NMAX; ++n) out[n] = 0.f;
+#pragma unroll
+  for (int k = 0; k < CC_TINY_K; ++k) {
+    if (k < L.K) {
+#pragma unroll
+      for (int n = 0; n < NMAX; ++n)
+        if (n < L.N) out[n] = fmaf(in[k], Wt[k * L.ldw + n], out[n]);
+    }
+  }
+  if (L.act != CC_ACT_IDENTITY) {
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n) out[n] = cc_act(L.act, out[n]);
+  }
+}
+
+// one step of a tiny node for this lane's trajectory.  x: state (in/out); v: raw input [I];
+// out: readout [O].  stages (optional): the four stage inputs, kept for the reverse pass.
+CC_DEV void cc_tiny_step(const CcNodeDev& nd, const float* cs, float (&x)[CC_TINY_S], float t, const float* v,
+                         float (&out)[CC_TINY_O], CcTinyStage* stages, float (*kout)[CC_TINY_S], float (&gin)[CC_TINY_K]) {
+  const float h = nd.dt;
+  float vt[CC_TINY_K];
+#pragma unroll
+  for (int i = 0; i < CC_TINY_K; ++i) vt[i] = (i < nd.I) ? cc_ut(nd.ut, nd.u_scale, v[i]) : 0.f;
+  const CcLayerDev& F = nd.f.layer[0];
+  const CcLayerDev& G = nd.g.layer[0];
+  float in[CC_TINY_K];
+  if (nd.pre) {
+    cc_tiny_build_in(nd, x, t, vt, gin);
+    cc_tiny_matvec<CC_TINY_O>(G, cs, gin, out);
+  }
+  float k[CC_TINY_S], ks[CC_TINY_S], z[CC_TINY_S], xn[CC_TINY_S];
+  if (nd.integrator == CC_INT_RK4) {
+#pragma unroll
+    for (int s = 0; s < CC_TINY_S; ++s) z[s] = x[s];
+#pragma unroll
+    for (int st = 0; st < 4; ++st) {
+      const float ts = st == 0 ? t : (st == 3 ? t + h : t + h / 2.f);
+      cc_tiny_build_in(nd, z, ts, vt, in);
+      if (stages) {
+#pragma unroll
+        for (int r = 0; r < CC_TINY_K; ++r) stages[st].in[r] = in[r];
+      }
+      cc_tiny_matvec<CC_TINY_S>(F, cs, in, k);
+      if (kout) {
+#pragma unroll
+        for (int s = 0; s < CC_TINY_S; ++s) kout[st][s] = k[s];
+      }
+#pragma unroll
+      for (int s = 0; s < CC_TINY_S; ++s) {
+        if (st == 0) { ks[s] = k[s]; z[s] = x[s] + h * k[s] / 2.f; }
+        else if (st == 1) { ks[s] = ks[s] + 2.f * k[s]; z[s] = x[s] + h * k[s] / 2.f; }
+        else if (st == 2) { ks[s] = ks[s] + 2.f * k[s]; z[s] = x[s] + h * k[s]; }
+        else xn[s] = x[s] + h * ((1.f / 6.f) * (ks[s] + k[s]));
+      }
+    }
+  } else {
+    cc_tiny_build_in(nd, x, t, vt, in);
+    if (stages) {
+#pragma unroll
+      for (int r = 0; r < CC_TINY_K; ++r) stages[0].in[r] = in[r];
+    }
+    cc_tiny_matvec<CC_TINY_S>(F, cs, in, k);
+    if (kout) {
+#pragma unroll
+      for (int s = 0; s < CC_TINY_S; ++s) kout[0][s] = k[s];
+    }
+#pragma unroll
+    for (int s = 0; s < CC_TINY_S; ++s) xn[s] = nd.integrator == CC_INT_EE ? x[s] + h * k[s] : k[s];
+  }
+  if (!nd.pre) {
+    // the readout sees the raw input (feed-through) and the pre-step time
+    float vraw[CC_TINY_K];
+#pragma unroll
+    for (int i = 0; i < CC_TINY_K; ++i) vraw[i] = (i < nd.I) ? v[i] : 0.f;
+    cc_tiny_build_in(nd, xn, t, vraw, gin);
+    cc_tiny_matvec<CC_TINY_O>(G, cs, gin, out);
+  }
+#pragma unroll
+  for (int o = 0; o < CC_TINY_O; ++o) out[o] *= nd.out_scale;
+#pragma unroll
+  for (int s = 0; s < CC_TINY_S; ++s) x[s] = (s < nd.S) ? xn[s] : 0.f;
 }
 
 // The launch plan is copied once into the head of dynamic shared memory; all device code reads it
-// from there (the node-level functions are not inlined, and a by-reference kernel parameter would
-// otherwise be spilled to local memory or read through generic loads).
+// from there (node-level functions are not inlined; a by-reference kernel parameter would otherwise
+// be spilled to local memory or read through generic loads).
 #define CC_PARAM_FLOATS ((int)((sizeof(CcKParams) + 15) / 16 * 4))
-#ifndef CC_EMULATE
-#define CC_SMEM_BASE extern __shared__ __align__(16) float cc_smem[];
-#else
-#define CC_SMEM_BASE float* cc_smem = ccemu::st().smem;
-#endif
 #define CC_KERNEL_PROLOGUE(gp)                                                      \
-  CC_SMEM_BASE                                                                      \
+  float* cc_smem = CC_SMEM_PTR;                                                     \
   {                                                                                 \
     const int* src_ = reinterpret_cast<const int*>(&(gp));                          \
     int* dst_ = reinterpret_cast<int*>(cc_smem);                                    \
@@ -510,127 +605,141 @@ CC_DEV void cc_set_inputs(const CcKParams& p, const CcNodeDev& nd, float* smem, 
   }                                                                                 \
   __syncthreads();                                                                  \
   const CcKParams& p = *reinterpret_cast<const CcKParams*>(cc_smem);                \
-  float* smem = cc_smem + CC_PARAM_FLOATS;
+  float* cta_smem = cc_smem + CC_PARAM_FLOATS;
+
+CC_DEV void cc_make_warp(const CcKParams& p, float* cta_smem, CcWarp& w) {
+  const int tid = threadIdx.x;
+  const int wid = tid / 32;
+  w.lane = tid % 32;
+  w.cg = w.lane / 8;
+  w.rg = w.lane % 8;
+  w.wt = (long long)blockIdx.x * p.wpc + wid;
+  w.b0 = w.wt * 32;
+  const long long rem = p.B - w.b0;
+  w.nact = rem >= 32 ? 32 : (rem > 0 ? (int)rem : 0);
+  (void)cta_smem;
+  w.cs_off = CC_PARAM_FLOATS;
+  w.ws_off = CC_PARAM_FLOATS + p.cta_floats + wid * p.warp_floats;
+}
 
 // ------------------------------------------------------------------------------------------------
 // K1 + K3: forward rollout (open loop: n_nodes == 1; closed loop: nd[0] controller, nd[1] model)
+// TN: register-tile width of the model; CM: controller mode (none / tiny / tile with TN = 8)
 // ------------------------------------------------------------------------------------------------
-template <int TN>
+template <int TN, int CM>
 __global__ void __launch_bounds__(320, 1) cc_rollout_fwd_kernel(const CC_GRID_CONSTANT CcKParams gp) {
   CC_KERNEL_PROLOGUE(gp)
-  CcThread th;
-  th.tid = threadIdx.x;
-  th.rg = th.tid / p.CGT;
-  th.cg = th.tid % p.CGT;
-  th.rg_ok = th.rg < p.RG;
-  const long long tile = blockIdx.x;
-  const long long b0 = tile * p.BT;
-  const bool closed = p.n_nodes == 2;
-  const CcNodeDev& M = p.nd[p.n_nodes - 1];  // the model
-  const CcNodeDev& C = p.nd[0];              // the controller (closed loop only)
-  const bool tape = p.tape != nullptr;
-
+  const bool closed = CM != CC_CTRL_NONE;
+  const CcNodeDev& M = p.nd[closed ? 1 : 0];
+  const CcNodeDev& C = p.nd[0];
   for (int n = 0; n < p.n_nodes; ++n) {
-    cc_stage_mlp(p.nd[n], p.nd[n].f, p.theta[n], smem, th.tid, p.nthreads);
-    cc_stage_mlp(p.nd[n], p.nd[n].g, p.theta[n], smem, th.tid, p.nthreads);
-    cc_init_node_buffers(p, p.nd[n], smem, th.tid, false);
+    cc_stage_mlp(p.nd[n], p.nd[n].f, p.theta[n], cta_smem, threadIdx.x, blockDim.x);
+    cc_stage_mlp(p.nd[n], p.nd[n].g, p.theta[n], cta_smem, threadIdx.x, blockDim.x);
   }
-  __syncthreads();
+  __syncthreads();  // the only CTA-level barrier: weights are staged
+  CcWarp w;
+  cc_make_warp(p, cta_smem, w);
+  if (w.nact == 0) return;
+  const bool act = w.lane < w.nact;
+  const long long b = w.b0 + w.lane;  // this lane's trajectory in the per-lane I/O phases
+  const bool tape = p.tape != nullptr;
+  for (int n = 0; n < p.n_nodes; ++n) cc_init_node_buffers(p.nd[n], w, false);
+  __syncwarp();
+
   if (!closed && p.x0) {
-    for (int i = th.tid; i < M.S * p.BT; i += p.nthreads) {
-      const int traj = i / M.S, s = i % M.S;
-      smem[M.s_X + s * p.BTP + traj] = (b0 + traj < p.B) ? __ldg(p.x0 + (b0 + traj) * M.S + s) : 0.f;
-    }
-    __syncthreads();
+    for (int s = 0; s < M.S; ++s) cc_ws(w)[M.w_X + s * CC_LD + w.lane] = act ? __ldg(p.x0 + b * M.S + s) : 0.f;
+    __syncwarp();
   }
-  // y0 = out_scale * g([x0 ; 0 ; (no feed-through for models)])     neural_ode_model.py:160-175
-  cc_readout<TN>(p, M, smem + M.s_X, smem, nullptr, th);
-  if (th.tid < p.BT) {
-    for (int o = 0; o < M.O; ++o) {
-      const float y0 = smem[M.s_OUT + o * p.BTP + th.tid];
-      if (closed) smem[p.s_yprev + o * p.BTP + th.tid] = y0;
-      else if (b0 + th.tid < p.B) p.out[(b0 + th.tid) * (long long)(p.T + 1) * M.O + o] = y0;
-    }
+  // y0 = out_scale * g([x0 ; 0])     neural_ode_model.py:160-175 (models have no feed-through)
+  cc_readout<TN>(closed ? 1 : 0, M.w_X, false, w);
+  for (int o = 0; o < M.O; ++o) {
+    const float y0 = cc_ws(w)[M.w_OUT + o * CC_LD + w.lane];
+    if (closed) cc_ws(w)[p.w_yprev + o * CC_LD + w.lane] = y0;
+    else if (act) p.out[b * (long long)(p.T + 1) * M.O + o] = y0;
   }
-  __syncthreads();
+  __syncwarp();
 
   float tc = 0.f, tm = 0.f;
+  float xc[CC_TINY_S];
+#pragma unroll
+  for (int s = 0; s < CC_TINY_S; ++s) xc[s] = 0.f;
   const int Win = closed ? p.R : M.I;
-  for (int k0 = 0; k0 < p.T; k0 += CC_TC) {
-    const int kend = (p.T - k0) < CC_TC ? (p.T - k0) : CC_TC;
-    cc_stage_in(p, p.in, CC_TC * Win, (long long)p.T * Win, (long long)k0 * Win, kend * Win, b0, smem + p.s_in, th.tid);
-    if (closed && p.noise)
-      cc_stage_in(p, p.noise, CC_TC * M.O, (long long)p.T * M.O, (long long)k0 * M.O, kend * M.O, b0, smem + p.s_noise, th.tid);
-    __syncthreads();
-    for (int kk = 0; kk < kend; ++kk) {
-      const int k = k0 + kk;
-      const bool wt = tape && (k % p.ckpt_every == 0);
-      const int ck = k / p.ckpt_every;
-      if (tape && tile == 0 && th.tid == 0) {  // step times for the reverse pass (fp32 accumulation is not invertible)
-        float* ttab = p.tape + (long long)p.n_ckpt * p.tape_rows * p.Bpad;
-        if (closed) { ttab[k] = tc; ttab[p.T + k] = tm; } else { ttab[k] = tm; }
-      }
-      if (closed) {
-        if (th.tid < p.BT) {
-          float v[16];
-          for (int r = 0; r < p.R; ++r) v[r] = smem[p.s_in + (kk * p.R + r) * p.BTP + th.tid];
-          for (int o = 0; o < M.O; ++o) {
-            const float yp = smem[p.s_yprev + o * p.BTP + th.tid];
-            v[p.R + o] = yp;
-            if (wt) p.tape[((long long)ck * p.tape_rows + C.S + M.S + o) * p.Bpad + b0 + th.tid] = yp;
-          }
-          cc_set_inputs(p, C, smem, th.tid, v, tc, false);
-        }
-        __syncthreads();
-        cc_node_step<TN>(p, C, smem, th, tc, false, true, wt, tile, ck);
-        if (th.tid < p.BT) {
-          float a[16];
-          for (int i = 0; i < M.I; ++i) {
-            a[i] = smem[C.s_OUT + i * p.BTP + th.tid];
-            if (p.u_out) smem[p.s_uo + (kk * M.I + i) * p.BTP + th.tid] = a[i];
-          }
-          cc_set_inputs(p, M, smem, th.tid, a, tm, false);
-        }
-        __syncthreads();
-        cc_node_step<TN>(p, M, smem, th, tm, false, true, wt, tile, ck);
-        if (th.tid < p.BT) {
-          for (int o = 0; o < M.O; ++o) {
-            float y = smem[M.s_OUT + o * p.BTP + th.tid];
-            if (p.noise) y += smem[p.s_noise + (kk * M.O + o) * p.BTP + th.tid];
-            smem[p.s_yprev + o * p.BTP + th.tid] = y;
-            smem[p.s_out + (kk * M.O + o) * p.BTP + th.tid] = y;
-          }
-        }
-        if (C.has_t) tc = tc + C.dt;
-        if (M.has_t) tm = tm + M.dt;
-      } else {
-        if (th.tid < p.BT) {
-          float v[16];
-          for (int i = 0; i < M.I; ++i) v[i] = smem[p.s_in + (kk * M.I + i) * p.BTP + th.tid];
-          cc_set_inputs(p, M, smem, th.tid, v, tm, false);
-        }
-        __syncthreads();
-        cc_node_step<TN>(p, M, smem, th, tm, false, true, wt, tile, ck);
-        if (th.tid < p.BT)
-          for (int o = 0; o < M.O; ++o) smem[p.s_out + (kk * M.O + o) * p.BTP + th.tid] = smem[M.s_OUT + o * p.BTP + th.tid];
-        if (M.has_t) tm = tm + M.dt;
-      }
+  float vin[CC_TINY_K];  // this step's external input (u or ref), prefetched one step ahead
+#pragma unroll
+  for (int i = 0; i < CC_TINY_K; ++i) vin[i] = (i < Win && act && p.T > 0) ? __ldg(p.in + b * (long long)p.T * Win + i) : 0.f;
+
+  for (int k = 0; k < p.T; ++k) {
+    const bool wt = tape && (k % p.ckpt_every == 0);
+    const int ck = k / p.ckpt_every;
+    if (tape && w.wt == 0 && w.lane == 0) {  // step times for the reverse pass (fp32 accumulation is not invertible)
+      float* ttab = p.tape + (long long)p.n_ckpt * p.tape_rows * p.Bpad;
+      if (closed) { ttab[k] = tc; ttab[p.T + k] = tm; } else { ttab[k] = tm; }
     }
-    __syncthreads();
+    float vcur[CC_TINY_K];
+#pragma unroll
+    for (int i = 0; i < CC_TINY_K; ++i) vcur[i] = vin[i];
+    if (k + 1 < p.T) {
+#pragma unroll
+      for (int i = 0; i < CC_TINY_K; ++i)
+        if (i < Win && act) vin[i] = __ldg(p.in + b * (long long)p.T * Win + (long long)(k + 1) * Win + i);
+    }
     if (closed) {
-      cc_stage_out(p, p.out, CC_TC * M.O, (long long)p.T * M.O, (long long)k0 * M.O, kend * M.O, b0, smem + p.s_out, th.tid);
-      if (p.u_out)
-        cc_stage_out(p, p.u_out, CC_TC * M.I, (long long)p.T * M.I, (long long)k0 * M.I, kend * M.I, b0, smem + p.s_uo, th.tid);
+      // controller input = merge_x_y(ref, y_prev) = [ref ; obs]     step_fn.py:187-192
+      float vc[CC_TINY_K];
+#pragma unroll
+      for (int i = 0; i < CC_TINY_K; ++i) vc[i] = vcur[i];
+      for (int o = 0; o < M.O; ++o) {
+        const float yp = cc_ws(w)[p.w_yprev + o * CC_LD + w.lane];
+#pragma unroll
+        for (int i = 0; i < CC_TINY_K; ++i)
+          if (i == p.R + o) vc[i] = yp;
+        if (wt) p.tape[((long long)ck * p.tape_rows + C.S + M.S + o) * p.Bpad + b] = yp;
+      }
+      float a[CC_TINY_O];
+      if (CM == CC_CTRL_TINY) {
+        if (wt)
+          for (int s = 0; s < C.S; ++s) {
+            float xs = 0.f;
+#pragma unroll
+            for (int q = 0; q < CC_TINY_S; ++q)
+              if (q == s) xs = xc[q];
+            p.tape[((long long)ck * p.tape_rows + C.tape_row + s) * p.Bpad + b] = xs;
+          }
+        float gin[CC_TINY_K];
+        cc_tiny_step(C, cc_cs(w), xc, tc, vc, a, nullptr, nullptr, gin);
+      } else {
+        cc_set_inputs(C, w, vc, tc, 0);
+        __syncwarp();
+        cc_node_step<8>(0, w, tc, false, true, wt, ck);
+#pragma unroll
+        for (int i = 0; i < CC_TINY_O; ++i) a[i] = (i < M.I) ? cc_ws(w)[C.w_OUT + i * CC_LD + w.lane] : 0.f;
+      }
+      if (p.u_out && act)
+#pragma unroll
+        for (int i = 0; i < CC_TINY_O; ++i)
+          if (i < M.I) p.u_out[b * (long long)p.T * M.I + (long long)k * M.I + i] = a[i];
+      float am[CC_TINY_K];
+#pragma unroll
+      for (int i = 0; i < CC_TINY_K; ++i) am[i] = (i < CC_TINY_O) ? a[i < CC_TINY_O ? i : 0] : 0.f;
+      cc_set_inputs(M, w, am, tm, 0);
+      __syncwarp();
+      cc_node_step<TN>(closed ? 1 : 0, w, tm, false, true, wt, ck);
+      for (int o = 0; o < M.O; ++o) {
+        float y = cc_ws(w)[M.w_OUT + o * CC_LD + w.lane];
+        if (p.noise && act) y += __ldg(p.noise + b * (long long)p.T * M.O + (long long)k * M.O + o);
+        cc_ws(w)[p.w_yprev + o * CC_LD + w.lane] = y;
+        if (act) p.out[b * (long long)p.T * M.O + (long long)k * M.O + o] = y;
+      }
+      if (C.has_t) tc = tc + C.dt;
     } else {
-      // step k produces output index k + 1
-      cc_stage_out(p, p.out, CC_TC * M.O, (long long)(p.T + 1) * M.O, (long long)(k0 + 1) * M.O, kend * M.O, b0, smem + p.s_out, th.tid);
+      cc_set_inputs(M, w, vcur, tm, 0);
+      __syncwarp();
+      cc_node_step<TN>(closed ? 1 : 0, w, tm, false, true, wt, ck);
+      if (act)
+        for (int o = 0; o < M.O; ++o) p.out[b * (long long)(p.T + 1) * M.O + (long long)(k + 1) * M.O + o] = cc_ws(w)[M.w_OUT + o * CC_LD + w.lane];
     }
-    __syncthreads();
+    if (M.has_t) tm = tm + M.dt;
   }
-  if (!closed && p.x_final) {
-    for (int i = th.tid; i < M.S * p.BT; i += p.nthreads) {
-      const int traj = i / M.S, s = i % M.S;
-      if (b0 + traj < p.B) p.x_final[(b0 + traj) * M.S + s] = smem[M.s_X + s * p.BTP + traj];
-    }
-  }
+  if (!closed && p.x_final && act)
+    for (int s = 0; s < M.S; ++s) p.x_final[b * M.S + s] = cc_ws(w)[M.w_X + s * CC_LD + w.lane];
 }

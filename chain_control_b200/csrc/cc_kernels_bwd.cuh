@@ -1,29 +1,30 @@
-// cc_kernels_bwd.cuh — BPTT of the fused rollout (K2 / K4) for sm_100a.
+// cc_kernels_bwd.cuh — BPTT of the fused rollout (K2 / K4) for sm_100a, one autonomous warp per 32
+// trajectories (see cc_plan.h).
 //
 // What eqx.filter_value_and_grad derives for cc/train/step_fn.py:133-146 (open loop, gradient w.r.t.
 // the model) and :249-283 (closed loop, gradient w.r.t. the controller only; the model is frozen).
 // The reverse time loop reads the carry (module states, fed-back output) of every checkpointed step
 // from the tape the forward kernel wrote, recomputes the RK4 stage intermediates of that step in
-// shared memory where the reverse pass needs them (trainable or non-linear networks), and runs the
-// reverse pass as three kinds of register-tiled SGEMMs out of shared memory:
+// shared memory only where the reverse pass needs them (trainable or non-linear networks; a frozen
+// linear model needs none), and runs the reverse pass as register-tiled SGEMMs out of shared memory:
 //   forward recompute   C[traj][n]  = sum_k  A[k][traj] * Wt[k][n]
-//   input gradient      C[traj][k]  = sum_n  D[n][traj] * W[n][k]
-//   weight gradient     G[n][k]    += sum_traj D[n][traj] * A[k][traj]      (accumulated in smem)
-// Per-CTA gradient blocks are written once at the end and reduced in fixed tile order.
+//   input gradient      C[traj][r]  = sum_n  D[n][traj] * W[n][r]
+//   weight gradient     G[n][r]    += sum_traj D[n][traj] * A[r][traj]   (per-warp accumulator in smem)
+// Gradient records are written once per warp tile and reduced in fixed order (deterministic).
 #pragma once
 #include "cc_kernels.cuh"
 
 #define CC_WN 2 /* weight-gradient thread tile: 2 outputs x 8 inputs */
 #define CC_WK 8
 
-// G[n][r] += sum_traj D[n][traj] * A[r][traj]; rows are owned interleaved (n = nt + NT*i,
-// r = kt + KT*j) so that the LDS.128 of a warp hit distinct bank quads.
-CC_DEV void cc_wgrad(const CcKParams& p, const CcLayerDev& L, const float* D, const float* A, float* smem,
-                     const CcThread& th) {
+// G[n][r] += sum_{traj<32} D[n][traj] * A[r][traj].  Tiles are dealt to the 32 lanes; each lane
+// walks the 8 trajectory quads in a lane-rotated order so that the LDS.128 of a quarter-warp hit 8
+// different bank quads whatever rows they touch.
+CC_DEV void cc_wgrad(const CcLayerDev& L, const float* D, const float* A, const CcWarp& w) {
   const int NT = (L.N + CC_WN - 1) / CC_WN;
   const int KT = (L.K + CC_WK - 1) / CC_WK;
-  float* G = smem + L.s_gw;
-  for (int tile = th.tid; tile < NT * KT; tile += p.nthreads) {
+  float* G = cc_ws(w) + L.w_gw;
+  for (int tile = w.lane; tile < NT * KT; tile += 32) {
     const int nt = tile / KT, kt = tile % KT;
     float acc[CC_WN][CC_WK];
 #pragma unroll
@@ -37,16 +38,17 @@ CC_DEV void cc_wgrad(const CcKParams& p, const CcLayerDev& L, const float* D, co
     for (int i = 0; i < CC_WN; ++i) {
       const int n = nt + NT * i;
       nok[i] = n < L.N;
-      dptr[i] = D + (nok[i] ? n : 0) * p.BTP;
+      dptr[i] = D + (nok[i] ? n : 0) * CC_LD;
     }
 #pragma unroll
     for (int j = 0; j < CC_WK; ++j) {
       const int r = kt + KT * j;
       rok[j] = r < L.K;
-      aptr[j] = A + (rok[j] ? r : 0) * p.BTP;
+      aptr[j] = A + (rok[j] ? r : 0) * CC_LD;
     }
 #pragma unroll 2
-    for (int q = 0; q < p.BT; q += 4) {
+    for (int qq = 0; qq < 8; ++qq) {
+      const int q = 4 * ((qq + w.lane) & 7);
       float4 d[CC_WN], a[CC_WK];
 #pragma unroll
       for (int i = 0; i < CC_WN; ++i) d[i] = *reinterpret_cast<const float4*>(dptr[i] + q);
@@ -66,100 +68,108 @@ CC_DEV void cc_wgrad(const CcKParams& p, const CcLayerDev& L, const float* D, co
     for (int i = 0; i < CC_WN; ++i)
 #pragma unroll
       for (int j = 0; j < CC_WK; ++j)
-        if (nok[i] && rok[j]) G[(nt + NT * i) * L.Kp + kt + KT * j] += acc[i][j];
+        if (nok[i] && rok[j]) G[(nt + NT * i) * L.K + kt + KT * j] += acc[i][j];
   }
 }
 
-// dst[r][traj] = (sum_n W[n][r] * D[n][traj]) * act'(H[r][traj])   for r < K  (H may be null)
-// tile over (traj, r) with CGk column groups.  No trailing barrier.
+// VB[iv][traj] += sum_n WV[iv][n] * d[traj][n]  with d the register tile of layer-0 cotangents:
+// per-thread partial over its columns, then the 4 column groups meet through two shuffles.
 template <int TN>
-CC_DEV void cc_igrad(const CcKParams& p, const CcLayerDev& L, const float* D, float* dst, const float* H, int hact,
-                     const float* smem, const CcThread& th) {
-  if (!(th.rg_ok && th.cg < L.CGk)) return;
-  float acc[CC_TM][TN];
-  cc_zero_tile<TN>(acc);
-  cc_gemm_tile<TN>(D + 4 * th.rg, p.BTP, smem + L.s_w, L.Kp, L.N, L.CGk, th.cg, acc);
+CC_DEV void cc_vgrad(const CcNodeDev& nd, const CcLayerDev& L, const float (&d)[CC_TM][TN], const CcWarp& w) {
+  const float* WV = cc_cs(w) + L.s_wv;
+  for (int iv = 0; iv < nd.I; ++iv) {
+    float part[CC_TM] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int j = 0; j < TN; ++j) {
-    const int r = cc_col<TN>(L.CGk, th.cg, j);
-    if (r < L.K) {
-      float4 v = make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
-      if (H && r < L.in_log) {
-        const float4 hv = *reinterpret_cast<const float4*>(H + r * p.BTP + 4 * th.rg);
-        v.x *= cc_act_grad(hact, hv.x); v.y *= cc_act_grad(hact, hv.y);
-        v.z *= cc_act_grad(hact, hv.z); v.w *= cc_act_grad(hact, hv.w);
+    for (int j = 0; j < TN; ++j) {
+      const int n = w.cg * L.cpt + j;
+      if (j < L.cpt && n < L.N) {
+        const float wv = WV[iv * L.N + n];
+#pragma unroll
+        for (int i = 0; i < CC_TM; ++i) part[i] = fmaf(wv, d[i][j], part[i]);
       }
-      *reinterpret_cast<float4*>(dst + r * p.BTP + 4 * th.rg) = v;
+    }
+#pragma unroll
+    for (int i = 0; i < CC_TM; ++i) {
+      part[i] += __shfl_xor_sync(CC_FULL, part[i], 8);
+      part[i] += __shfl_xor_sync(CC_FULL, part[i], 16);
+    }
+    if (w.cg == 0) {
+      float4* dst = reinterpret_cast<float4*>(cc_ws(w) + nd.w_VB + iv * CC_LD + 4 * w.rg);
+      float4 v = *dst;
+      v.x += part[0]; v.y += part[1]; v.z += part[2]; v.w += part[3];
+      *dst = v;
     }
   }
 }
 
-// reverse pass of one MLP.  `cur` (DA) holds the cotangent of the last layer's PRE-activation
-// [N_L][BTP].  in0 = input buffer of layer 0; hid[l] = smem offset of layer l's hidden output.
-// Returns the buffer holding the cotangent of the MLP input (rows < K of layer 0).  Ends with a barrier.
+// Reverse pass of one MLP.  d: cotangent of the last layer's PRE-activation (register tile, column
+// mapping of that layer).  in0: input buffer of layer 0; hid[l]: offset of layer l's hidden output.
+// din: cotangent of the first Kin input rows (column mapping of the source buffer).  Input-row
+// cotangents are accumulated into VB when the first layer consumes v.  Ends with __syncwarp().
 template <int TN>
-CC_DEV float* cc_mlp_bwd(const CcKParams& p, const CcNodeDev& nd, const CcMlpDev& mlp, float* cur, float* other,
-                         const float* in0, const int* hid, float* smem, const CcThread& th) {
+CC_DEV void cc_mlp_bwd(const CcNodeDev& nd, const CcMlpDev& mlp, float (&d)[CC_TM][TN], const float* in0,
+                       const int* hid, const CcWarp& w, float (&din)[CC_TM][TN]) {
+  float* DA = cc_ws(w) + nd.w_DA;
   for (int l = mlp.L - 1; l >= 0; --l) {
     const CcLayerDev& L = mlp.layer[l];
-    const float* in_l = l == 0 ? in0 : smem + hid[l - 1];
-    if (nd.trainable) cc_wgrad(p, L, cur, in_l, smem, th);
-    const float* H = l > 0 ? smem + hid[l - 1] : nullptr;
-    cc_igrad<TN>(p, L, cur, other, H, l > 0 ? mlp.layer[l - 1].act : CC_ACT_IDENTITY, smem, th);
-    __syncthreads();
-    float* t = cur; cur = other; other = t;
-  }
-  return cur;
-}
-
-// cotangent of the readout: OB[O][BTP] -> adds to xrb tile (state part) and VB (input rows).
-// gsrc = the buffer g read ([x or x_next ; t ; v ; 1]).  Ends with a barrier.
-template <int TN>
-CC_DEV void cc_readout_bwd(const CcKParams& p, const CcNodeDev& nd, const float* gsrc, float* smem, const CcThread& th,
-                           float (&xrb)[CC_TM][TN], bool want_input_grad) {
-  const CcLayerDev& LL = nd.g.layer[nd.g.L - 1];
-  float* DA = smem + nd.s_DA;
-  float* DB = smem + nd.s_DB;
-  const float* OB = smem + nd.s_OB;
-  const float* OUT = smem + nd.s_OUT;
-  for (int i = th.tid; i < nd.O * p.BT; i += p.nthreads) {
-    const int o = i / p.BT, traj = i % p.BT;
-    float d = nd.out_scale * OB[o * p.BTP + traj];
-    if (LL.act != CC_ACT_IDENTITY) {
-      const float y = nd.out_scale != 0.f ? OUT[o * p.BTP + traj] / nd.out_scale : 0.f;
-      d *= cc_act_grad(LL.act, y);
+    cc_store_tile<TN>(DA, L.N, L.cpt, w, d);
+    __syncwarp();
+    if (nd.trainable) cc_wgrad(L, DA, l == 0 ? in0 : cc_ws(w) + hid[l - 1], w);
+    if (l == 0 && L.s_wv >= 0 && L.use_v) cc_vgrad<TN>(nd, L, d, w);
+    cc_zero_tile<TN>(din);
+    cc_gemm_tile<TN>(DA + 4 * w.rg, cc_cs(w) + L.s_w + w.cg * L.GSk, L.ldk, L.N, din);
+    if (l > 0) {
+      const CcLayerDev& Lp = mlp.layer[l - 1];
+      float hv[CC_TM][TN];
+      cc_load_tile<TN>(cc_ws(w) + hid[l - 1], Lp.N, Lp.cpt, w, hv);
+#pragma unroll
+      for (int i = 0; i < CC_TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) d[i][j] = din[i][j] * cc_act_grad(Lp.act, hv[i][j]);
     }
-    DA[o * p.BTP + traj] = d;
+    __syncwarp();  // DA is rewritten by the next layer
   }
-  __syncthreads();
-  float* cur = cc_mlp_bwd<TN>(p, nd, nd.g, DA, DB, gsrc, nd.s_GH, smem, th);
-  if (want_input_grad) {
-    const bool own = th.rg_ok && th.cg < nd.CGs;
-    cc_load_tile<TN>(cur, p.BTP, own ? nd.S : 0, nd.CGs, th, xrb);
-    if (th.tid < p.BT)
-      for (int i = 0; i < nd.I; ++i) smem[nd.s_VB + i * p.BTP + th.tid] += cur[(nd.row_v + i) * p.BTP + th.tid];
-  }
-  __syncthreads();
 }
 
-// Reverse pass of one node step.  On entry: OB = cotangent of the node output,
-// LAM = cotangent of the next state, stage intermediates recomputed (if nd.recompute) by
-// cc_node_step(keep=true).  vraw[i*BTP + traj] = raw node input (for u_transform'), or null.
+// cotangent of the readout: OB[O][32] -> xrb (state rows) and VB (feed-through rows).
+// gsrc = the buffer g read ([x or x_next ; t ; v ; 1]).
+template <int TN>
+CC_DEV void cc_readout_bwd(const CcNodeDev& nd, const float* gsrc, const CcWarp& w, float (&xrb)[CC_TM][TN]) {
+  const CcLayerDev& LL = nd.g.layer[nd.g.L - 1];
+  float d[CC_TM][TN];
+  cc_load_tile<TN>(cc_ws(w) + nd.w_OB, LL.N, LL.cpt, w, d);
+  if (LL.act != CC_ACT_IDENTITY) {
+    float y[CC_TM][TN];
+    cc_load_tile<TN>(cc_ws(w) + nd.w_OUT, LL.N, LL.cpt, w, y);
+    const float inv = nd.out_scale != 0.f ? 1.f / nd.out_scale : 0.f;
+#pragma unroll
+    for (int i = 0; i < CC_TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) d[i][j] *= cc_act_grad(LL.act, y[i][j] * inv);
+  }
+#pragma unroll
+  for (int i = 0; i < CC_TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) d[i][j] *= nd.out_scale;
+  cc_mlp_bwd<TN>(nd, nd.g, d, gsrc, nd.w_GH, w, xrb);
+}
+
+// Reverse pass of one tile-path node step.  On entry: OB = cotangent of the node
+// output, LAM = cotangent of the next state, stage intermediates recomputed (if nd.recompute) by
+// cc_node_step(keep=true).  vraw[i*32 + traj] = raw node input (for u_transform'), or null.
 // On exit: LAM = cotangent of the state at step start, VB = cotangent of the raw input.
 template <int TN>
-CC_DEV_NOINLINE void cc_node_bwd(const CcKParams& p, const CcNodeDev& nd, float* smem, const CcThread& th, const float* vraw) {
+CC_DEV_NOINLINE void cc_node_bwd(int node, const CcWarp w, int vraw_off) {
+  const CcNodeDev& nd = cc_params().nd[node];
+  const float* vraw = vraw_off >= 0 ? cc_ws(w) + vraw_off : nullptr;
   const float h = nd.dt;
-  const bool own = th.rg_ok && th.cg < nd.CGs;
-  float* X = smem + nd.s_X;
-  float* LAM = smem + nd.s_LAM;
-  float* DA = smem + nd.s_DA;
-  float* DB = smem + nd.s_DB;
-  for (int i = th.tid; i < nd.I * p.BT; i += p.nthreads) smem[nd.s_VB + (i / p.BT) * p.BTP + (i % p.BT)] = 0.f;
-  __syncthreads();
+  float* X = cc_ws(w) + nd.w_X;
+  float* LAM = cc_ws(w) + nd.w_LAM;
+  for (int i = 0; i < nd.I; ++i) cc_ws(w)[nd.w_VB + i * CC_LD + w.lane] = 0.f;
+  __syncwarp();
   float xrb[CC_TM][TN], lam[CC_TM][TN];
-  cc_zero_tile<TN>(xrb);
-  cc_readout_bwd<TN>(p, nd, nd.pre ? X : smem + nd.s_ZA, smem, th, xrb, true);
-  cc_load_tile<TN>(LAM, p.BTP, own ? nd.S : 0, nd.CGs, th, lam);
+  cc_readout_bwd<TN>(nd, nd.pre ? X : (nd.w_XN >= 0 ? cc_ws(w) + nd.w_XN : X), w, xrb);
+  cc_load_tile<TN>(LAM, nd.S, nd.cptS, w, lam);
   if (!nd.pre) {
 #pragma unroll
     for (int i = 0; i < CC_TM; ++i)
@@ -173,65 +183,47 @@ CC_DEV_NOINLINE void cc_node_bwd(const CcKParams& p, const CcNodeDev& nd, float*
     cc_zero_tile<TN>(zsum);
     cc_zero_tile<TN>(zb);
     for (int s = 3; s >= 0; --s) {
-      if (own) {
-        float d[CC_TM][TN];
-        float ks[CC_TM][TN];
-        if (FL.act != CC_ACT_IDENTITY) cc_load_tile<TN>(smem + nd.s_KS[s], p.BTP, nd.S, nd.CGs, th, ks);
+      float d[CC_TM][TN];
+      float ks[CC_TM][TN];
+      if (FL.act != CC_ACT_IDENTITY) cc_load_tile<TN>(cc_ws(w) + nd.w_KS[s], nd.S, nd.cptS, w, ks);
 #pragma unroll
-        for (int i = 0; i < CC_TM; ++i)
+      for (int i = 0; i < CC_TM; ++i)
 #pragma unroll
-          for (int j = 0; j < TN; ++j) {
-            float kb;
-            if (s == 3) kb = c6 * lam[i][j];
-            else if (s == 2) kb = c3 * lam[i][j] + h * zb[i][j];
-            else if (s == 1) kb = c3 * lam[i][j] + c2 * zb[i][j];
-            else kb = c6 * lam[i][j] + c2 * zb[i][j];
-            if (FL.act != CC_ACT_IDENTITY) kb *= cc_act_grad(FL.act, ks[i][j]);
-            d[i][j] = kb;
-          }
-        cc_store_tile<TN>(DA, p.BTP, nd.S, nd.CGs, th, d);
-      }
-      __syncthreads();
-      const float* in0 = nd.recompute ? smem + nd.s_Z[s] : X;
-      float* cur = cc_mlp_bwd<TN>(p, nd, nd.f, DA, DB, in0, nd.s_HS[s], smem, th);
-      cc_load_tile<TN>(cur, p.BTP, own ? nd.S : 0, nd.CGs, th, zb);
-      if (th.tid < p.BT)
-        for (int i = 0; i < nd.I; ++i) smem[nd.s_VB + i * p.BTP + th.tid] += cur[(nd.row_v + i) * p.BTP + th.tid];
+        for (int j = 0; j < TN; ++j) {
+          float kb;
+          if (s == 3) kb = c6 * lam[i][j];
+          else if (s == 2) kb = c3 * lam[i][j] + h * zb[i][j];
+          else if (s == 1) kb = c3 * lam[i][j] + c2 * zb[i][j];
+          else kb = c6 * lam[i][j] + c2 * zb[i][j];
+          if (FL.act != CC_ACT_IDENTITY) kb *= cc_act_grad(FL.act, ks[i][j]);
+          d[i][j] = kb;
+        }
+      cc_mlp_bwd<TN>(nd, nd.f, d, nd.recompute ? cc_ws(w) + nd.w_ZS[s] : X, nd.w_HS[s], w, zb);
 #pragma unroll
       for (int i = 0; i < CC_TM; ++i)
 #pragma unroll
         for (int j = 0; j < TN; ++j) zsum[i][j] += zb[i][j];
-      __syncthreads();
     }
 #pragma unroll
     for (int i = 0; i < CC_TM; ++i)
 #pragma unroll
       for (int j = 0; j < TN; ++j) lam[i][j] += zsum[i][j];
   } else {
-    if (own) {
-      float d[CC_TM][TN], ks[CC_TM][TN];
-      if (FL.act != CC_ACT_IDENTITY) cc_load_tile<TN>(smem + nd.s_KS[0], p.BTP, nd.S, nd.CGs, th, ks);
+    float d[CC_TM][TN], ks[CC_TM][TN], zb[CC_TM][TN];
+    if (FL.act != CC_ACT_IDENTITY) cc_load_tile<TN>(cc_ws(w) + nd.w_KS[0], nd.S, nd.cptS, w, ks);
 #pragma unroll
-      for (int i = 0; i < CC_TM; ++i)
+    for (int i = 0; i < CC_TM; ++i)
 #pragma unroll
-        for (int j = 0; j < TN; ++j) {
-          float kb = nd.integrator == CC_INT_EE ? h * lam[i][j] : lam[i][j];
-          if (FL.act != CC_ACT_IDENTITY) kb *= cc_act_grad(FL.act, ks[i][j]);
-          d[i][j] = kb;
-        }
-      cc_store_tile<TN>(DA, p.BTP, nd.S, nd.CGs, th, d);
-    }
-    __syncthreads();
-    float* cur = cc_mlp_bwd<TN>(p, nd, nd.f, DA, DB, X, nd.s_HS[0], smem, th);
-    float zb[CC_TM][TN];
-    cc_load_tile<TN>(cur, p.BTP, own ? nd.S : 0, nd.CGs, th, zb);
-    if (th.tid < p.BT)
-      for (int i = 0; i < nd.I; ++i) smem[nd.s_VB + i * p.BTP + th.tid] += cur[(nd.row_v + i) * p.BTP + th.tid];
+      for (int j = 0; j < TN; ++j) {
+        float kb = nd.integrator == CC_INT_EE ? h * lam[i][j] : lam[i][j];
+        if (FL.act != CC_ACT_IDENTITY) kb *= cc_act_grad(FL.act, ks[i][j]);
+        d[i][j] = kb;
+      }
+    cc_mlp_bwd<TN>(nd, nd.f, d, X, nd.w_HS[0], w, zb);
 #pragma unroll
     for (int i = 0; i < CC_TM; ++i)
 #pragma unroll
       for (int j = 0; j < TN; ++j) lam[i][j] = nd.integrator == CC_INT_EE ? lam[i][j] + zb[i][j] : zb[i][j];
-    __syncthreads();
   }
   if (nd.pre) {
 #pragma unroll
@@ -239,158 +231,306 @@ CC_DEV_NOINLINE void cc_node_bwd(const CcKParams& p, const CcNodeDev& nd, float*
 #pragma unroll
       for (int j = 0; j < TN; ++j) lam[i][j] += xrb[i][j];
   }
-  if (own) cc_store_tile<TN>(LAM, p.BTP, nd.S, nd.CGs, th, lam);
-  if (vraw && nd.ut != CC_UT_IDENTITY && th.tid < p.BT)
+  cc_store_tile<TN>(LAM, nd.S, nd.cptS, w, lam);
+  __syncwarp();
+  if (vraw && nd.ut != CC_UT_IDENTITY)
     for (int i = 0; i < nd.I; ++i)
-      smem[nd.s_VB + i * p.BTP + th.tid] *= cc_ut_grad(nd.ut, nd.u_scale, vraw[i * p.BTP + th.tid]);
-  __syncthreads();
+      cc_ws(w)[nd.w_VB + i * CC_LD + w.lane] *= cc_ut_grad(nd.ut, nd.u_scale, vraw[i * CC_LD + w.lane]);
+  __syncwarp();
 }
 
-// state rows of X <- tape record `ck`
-CC_DEV void cc_tape_load(const CcKParams& p, const CcNodeDev& nd, long long b0, int ck, float* smem, int tid) {
-  const float* rec = p.tape + ((long long)ck * p.tape_rows + nd.tape_row) * p.Bpad + b0;
-  for (int i = tid; i < nd.S * p.BT; i += p.nthreads) {
-    const int s = i / p.BT, traj = i % p.BT;
-    smem[nd.s_X + s * p.BTP + traj] = (b0 + traj < p.B) ? rec[(long long)s * p.Bpad + traj] : 0.f;
+// state rows of X <- tape record `ck` (coalesced float4 loads through the state tile)
+template <int TN>
+CC_DEV void cc_tape_load(const CcKParams& p, const CcNodeDev& nd, int ck, const CcWarp& w) {
+  const float* rec = p.tape + ((long long)ck * p.tape_rows + nd.tape_row) * p.Bpad + w.b0;
+  float* X = cc_ws(w) + nd.w_X;
+#pragma unroll
+  for (int j = 0; j < TN; ++j) {
+    const int n = w.cg * nd.cptS + j;
+    if (j < nd.cptS && n < nd.S) {
+      float4 v = *reinterpret_cast<const float4*>(rec + (long long)n * p.Bpad + 4 * w.rg);
+      // trajectories beyond B carry whatever the forward pass left there: force them to zero
+      const int t0 = 4 * w.rg;
+      if (t0 + 0 >= w.nact) v.x = 0.f;
+      if (t0 + 1 >= w.nact) v.y = 0.f;
+      if (t0 + 2 >= w.nact) v.z = 0.f;
+      if (t0 + 3 >= w.nact) v.w = 0.f;
+      *reinterpret_cast<float4*>(X + n * CC_LD + 4 * w.rg) = v;
+    }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// reverse pass of a "tiny" node for this lane's trajectory (see cc_tiny_step)
+//   x: state at step start; v: raw input; ob: cotangent of the output; lam: cotangent of the next
+//   state (in) / of x (out); vb: cotangent of the raw input (out).  Parameter gradients go to the
+//   lane-private accumulators GP[entry][lane] (reduced over lanes once, at the end of the kernel).
+// ------------------------------------------------------------------------------------------------
+CC_DEV void cc_tiny_bwd(const CcNodeDev& nd, const CcWarp& w, const float (&x0)[CC_TINY_S], float t, const float* v,
+                        const float (&ob)[CC_TINY_O], float (&lam)[CC_TINY_S], float (&vb)[CC_TINY_K]) {
+  const float h = nd.dt;
+  const CcLayerDev& F = nd.f.layer[0];
+  const CcLayerDev& G = nd.g.layer[0];
+  const float* WtF = cc_cs(w) + F.s_wt;
+  const float* WtG = cc_cs(w) + G.s_wt;
+  float* GP = cc_ws(w) + nd.w_GP;
+  // recompute the step, keeping stage inputs / outputs
+  CcTinyStage st[4];
+  float kout[4][CC_TINY_S];
+  float out[CC_TINY_O], gin[CC_TINY_K];
+  float x[CC_TINY_S];
+#pragma unroll
+  for (int s = 0; s < CC_TINY_S; ++s) x[s] = x0[s];
+  cc_tiny_step(nd, cc_cs(w), x, t, v, out, st, kout, gin);
+  float utb[CC_TINY_K];
+#pragma unroll
+  for (int i = 0; i < CC_TINY_K; ++i) { vb[i] = 0.f; utb[i] = 0.f; }
+  // readout
+  float xrb[CC_TINY_S];
+#pragma unroll
+  for (int s = 0; s < CC_TINY_S; ++s) xrb[s] = 0.f;
+#pragma unroll
+  for (int o = 0; o < CC_TINY_O; ++o) {
+    if (o < nd.O) {
+      float d = nd.out_scale * ob[o];
+      if (G.act != CC_ACT_IDENTITY) d *= cc_act_grad(G.act, nd.out_scale != 0.f ? out[o] / nd.out_scale : 0.f);
+#pragma unroll
+      for (int k = 0; k < CC_TINY_K; ++k) {
+        if (k < G.K) {
+          const float wv = WtG[k * G.ldw + o];
+          GP[(G.g_off + o * G.K + k) * CC_LD + w.lane] += d * gin[k];
+          if (k < nd.S) {
+#pragma unroll
+            for (int s = 0; s < CC_TINY_S; ++s)
+              if (s == k) xrb[s] = fmaf(wv, d, xrb[s]);
+          } else if (k >= nd.row_v && k < nd.row_v + nd.I) {
+#pragma unroll
+            for (int i = 0; i < CC_TINY_K; ++i)
+              if (i == k - nd.row_v) vb[i] = fmaf(wv, d, vb[i]);  // feed-through: raw input
+          }
+        }
+      }
+    }
+  }
+  if (!nd.pre) {
+#pragma unroll
+    for (int s = 0; s < CC_TINY_S; ++s) lam[s] += xrb[s];
+  }
+  const int nst = nd.integrator == CC_INT_RK4 ? 4 : 1;
+  float zsum[CC_TINY_S], zb[CC_TINY_S];
+#pragma unroll
+  for (int s = 0; s < CC_TINY_S; ++s) { zsum[s] = 0.f; zb[s] = 0.f; }
+  const float c6 = h / 6.f, c3 = h / 3.f, c2 = h / 2.f;
+#pragma unroll
+  for (int sti = 3; sti >= 0; --sti) {
+    if (sti < nst) {
+      float d[CC_TINY_S];
+#pragma unroll
+      for (int s = 0; s < CC_TINY_S; ++s) {
+        float kb;
+        if (nd.integrator == CC_INT_RK4) {
+          if (sti == 3) kb = c6 * lam[s];
+          else if (sti == 2) kb = c3 * lam[s] + h * zb[s];
+          else if (sti == 1) kb = c3 * lam[s] + c2 * zb[s];
+          else kb = c6 * lam[s] + c2 * zb[s];
+        } else {
+          kb = nd.integrator == CC_INT_EE ? h * lam[s] : lam[s];
+        }
+        if (F.act != CC_ACT_IDENTITY) kb *= cc_act_grad(F.act, kout[sti][s]);
+        d[s] = (s < nd.S) ? kb : 0.f;
+      }
+#pragma unroll
+      for (int s = 0; s < CC_TINY_S; ++s) zb[s] = 0.f;
+#pragma unroll
+      for (int k = 0; k < CC_TINY_K; ++k) {
+        if (k < F.K) {
+          float acc = 0.f;
+#pragma unroll
+          for (int n = 0; n < CC_TINY_S; ++n) {
+            if (n < nd.S) {
+              acc = fmaf(WtF[k * F.ldw + n], d[n], acc);
+              GP[(F.g_off + n * F.K + k) * CC_LD + w.lane] += d[n] * st[sti].in[k];
+            }
+          }
+          if (k < nd.S) {
+#pragma unroll
+            for (int s = 0; s < CC_TINY_S; ++s)
+              if (s == k) zb[s] = acc;
+          } else if (k >= nd.row_v && k < nd.row_v + nd.I) {
+#pragma unroll
+            for (int i = 0; i < CC_TINY_K; ++i)
+              if (i == k - nd.row_v) utb[i] += acc;
+          }
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < CC_TINY_S; ++s) zsum[s] += zb[s];
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < CC_TINY_S; ++s) {
+    if (nd.integrator == CC_INT_NONE) lam[s] = zb[s];
+    else lam[s] += zsum[s];
+    if (nd.pre) lam[s] += xrb[s];
+  }
+#pragma unroll
+  for (int i = 0; i < CC_TINY_K; ++i)
+    if (i < nd.I) vb[i] += utb[i] * cc_ut_grad(nd.ut, nd.u_scale, v[i]);
 }
 
 // ------------------------------------------------------------------------------------------------
 // K2 + K4: reverse time loop
 // ------------------------------------------------------------------------------------------------
-template <int TN>
+template <int TN, int CM>
 __global__ void __launch_bounds__(320, 1) cc_rollout_bwd_kernel(const CC_GRID_CONSTANT CcKParams gp) {
   CC_KERNEL_PROLOGUE(gp)
-  CcThread th;
-  th.tid = threadIdx.x;
-  th.rg = th.tid / p.CGT;
-  th.cg = th.tid % p.CGT;
-  th.rg_ok = th.rg < p.RG;
-  const long long tile = blockIdx.x;
-  const long long b0 = tile * p.BT;
-  const bool closed = p.n_nodes == 2;
-  const CcNodeDev& M = p.nd[p.n_nodes - 1];
+  const bool closed = CM != CC_CTRL_NONE;
+  const CcNodeDev& M = p.nd[closed ? 1 : 0];
   const CcNodeDev& C = p.nd[0];
-  const float* ttab = p.tape + (long long)p.n_ckpt * p.tape_rows * p.Bpad;  // [2][T] step times
-
   for (int n = 0; n < p.n_nodes; ++n) {
-    const CcNodeDev& nd = p.nd[n];
-    cc_stage_mlp(nd, nd.f, p.theta[n], smem, th.tid, p.nthreads);
-    cc_stage_mlp(nd, nd.g, p.theta[n], smem, th.tid, p.nthreads);
-    cc_init_node_buffers(p, nd, smem, th.tid, true);
-    for (int i = th.tid; i < nd.S * p.BTP; i += p.nthreads) smem[nd.s_LAM + i] = 0.f;
-    for (int i = th.tid; i < nd.O * p.BTP; i += p.nthreads) smem[nd.s_OUT + i] = 0.f;
+    cc_stage_mlp(p.nd[n], p.nd[n].f, p.theta[n], cta_smem, threadIdx.x, blockDim.x);
+    cc_stage_mlp(p.nd[n], p.nd[n].g, p.theta[n], cta_smem, threadIdx.x, blockDim.x);
   }
-  if (closed)
-    for (int i = th.tid; i < M.O * p.BTP; i += p.nthreads) smem[p.s_yfb + i] = 0.f;
   __syncthreads();
+  CcWarp w;
+  cc_make_warp(p, cta_smem, w);
+  if (w.nact == 0) return;
+  const bool act = w.lane < w.nact;
+  const long long b = w.b0 + w.lane;
+  const float* ttab = p.tape + (long long)p.n_ckpt * p.tape_rows * p.Bpad;  // [2][T] step times
+  for (int n = 0; n < p.n_nodes; ++n) cc_init_node_buffers(p.nd[n], w, true);
+  if (closed)
+    for (int o = 0; o < M.O; ++o) cc_ws(w)[p.w_yfb + o * CC_LD + w.lane] = 0.f;
+  __syncwarp();
 
+  float lamc[CC_TINY_S];
+#pragma unroll
+  for (int s = 0; s < CC_TINY_S; ++s) lamc[s] = 0.f;
   const int Win = closed ? p.R : M.I;
-  const int nchunk = (p.T + CC_TC - 1) / CC_TC;
-  for (int c = nchunk - 1; c >= 0; --c) {
-    const int k0 = c * CC_TC;
-    const int kend = (p.T - k0) < CC_TC ? (p.T - k0) : CC_TC;
-    if (Win > 0)
-      cc_stage_in(p, p.in, CC_TC * Win, (long long)p.T * Win, (long long)k0 * Win, kend * Win, b0, smem + p.s_in, th.tid);
-    if (closed)
-      cc_stage_in(p, p.ybar, CC_TC * M.O, (long long)p.T * M.O, (long long)k0 * M.O, kend * M.O, b0, smem + p.s_yb, th.tid);
-    else
-      cc_stage_in(p, p.ybar, CC_TC * M.O, (long long)(p.T + 1) * M.O, (long long)(k0 + 1) * M.O, kend * M.O, b0, smem + p.s_yb, th.tid);
-    __syncthreads();
-    for (int kk = kend - 1; kk >= 0; --kk) {
-      const int k = k0 + kk;  // ckpt_every == 1: the tape holds the carry of every step
-      if (closed) {
-        const float tc = C.has_t ? ttab[k] : 0.f;
-        const float tm = M.has_t ? ttab[p.T + k] : 0.f;
-        cc_tape_load(p, C, b0, k, smem, th.tid);
-        if (M.recompute) cc_tape_load(p, M, b0, k, smem, th.tid);
-        if (th.tid < p.BT) {
-          float v[16];
-          for (int r = 0; r < p.R; ++r) v[r] = smem[p.s_in + (kk * p.R + r) * p.BTP + th.tid];
-          for (int o = 0; o < M.O; ++o)
-            v[p.R + o] = (b0 + th.tid < p.B) ? p.tape[((long long)k * p.tape_rows + C.S + M.S + o) * p.Bpad + b0 + th.tid] : 0.f;
-          cc_set_inputs(p, C, smem, th.tid, v, tc, true);
-        }
-        __syncthreads();
-        cc_node_step<TN>(p, C, smem, th, tc, true, true, false, 0, 0);  // controller always recomputes: a_k is needed
-        if (th.tid < p.BT) {
-          float a[16];
-          for (int i = 0; i < M.I; ++i) {
-            a[i] = smem[C.s_OUT + i * p.BTP + th.tid];
-            smem[p.s_araw + i * p.BTP + th.tid] = a[i];
-          }
-          cc_set_inputs(p, M, smem, th.tid, a, tm, M.recompute != 0);
-          for (int o = 0; o < M.O; ++o)
-            smem[M.s_OB + o * p.BTP + th.tid] = smem[p.s_yb + (kk * M.O + o) * p.BTP + th.tid] + smem[p.s_yfb + o * p.BTP + th.tid];
-        }
-        __syncthreads();
-        if (M.recompute) cc_node_step<TN>(p, M, smem, th, tm, true, true, false, 0, 0);
-        cc_node_bwd<TN>(p, M, smem, th, smem + p.s_araw);
-        for (int i = th.tid; i < M.I * p.BT; i += p.nthreads) {
-          const int r = i / p.BT, traj = i % p.BT;
-          smem[C.s_OB + r * p.BTP + traj] = smem[M.s_VB + r * p.BTP + traj];
-        }
-        __syncthreads();
-        cc_node_bwd<TN>(p, C, smem, th, nullptr);
-        for (int i = th.tid; i < M.O * p.BT; i += p.nthreads) {
-          const int o = i / p.BT, traj = i % p.BT;
-          smem[p.s_yfb + o * p.BTP + traj] = smem[C.s_VB + (p.R + o) * p.BTP + traj];
-        }
-        __syncthreads();
-      } else {
-        const float tm = M.has_t ? ttab[k] : 0.f;
-        cc_tape_load(p, M, b0, k, smem, th.tid);
-        if (th.tid < p.BT) {
-          float v[16];
-          for (int i = 0; i < M.I; ++i) v[i] = smem[p.s_in + (kk * M.I + i) * p.BTP + th.tid];
-          cc_set_inputs(p, M, smem, th.tid, v, tm, M.recompute != 0);
-          for (int o = 0; o < M.O; ++o) smem[M.s_OB + o * p.BTP + th.tid] = smem[p.s_yb + (kk * M.O + o) * p.BTP + th.tid];
-        }
-        __syncthreads();
-        if (M.recompute) cc_node_step<TN>(p, M, smem, th, tm, true, true, false, 0, 0);
-        cc_node_bwd<TN>(p, M, smem, th, smem + p.s_in + kk * M.I * p.BTP);
-        if (p.ubar && th.tid < p.BT)
-          for (int i = 0; i < M.I; ++i) smem[p.s_ub + (kk * M.I + i) * p.BTP + th.tid] = smem[M.s_VB + i * p.BTP + th.tid];
+  const long long yrow = closed ? (long long)p.T * M.O : (long long)(p.T + 1) * M.O;
+
+  for (int k = p.T - 1; k >= 0; --k) {  // ckpt_every == 1: the tape holds the carry of every step
+    float vin[CC_TINY_K];
+#pragma unroll
+    for (int i = 0; i < CC_TINY_K; ++i) vin[i] = (i < Win && act) ? __ldg(p.in + b * (long long)p.T * Win + (long long)k * Win + i) : 0.f;
+    const long long yoff = closed ? (long long)k * M.O : (long long)(k + 1) * M.O;
+    if (closed) {
+      const float tc = C.has_t ? ttab[k] : 0.f;
+      const float tm = M.has_t ? ttab[p.T + k] : 0.f;
+      // carry of step k: (x_c, x_m, y_prev)
+      float vc[CC_TINY_K];
+#pragma unroll
+      for (int i = 0; i < CC_TINY_K; ++i) vc[i] = vin[i];
+      for (int o = 0; o < M.O; ++o) {
+        const float yp = act ? p.tape[((long long)k * p.tape_rows + C.S + M.S + o) * p.Bpad + b] : 0.f;
+#pragma unroll
+        for (int i = 0; i < CC_TINY_K; ++i)
+          if (i == p.R + o) vc[i] = yp;
       }
+      float a[CC_TINY_O];
+      float xc[CC_TINY_S];
+      if (CM == CC_CTRL_TINY) {
+#pragma unroll
+        for (int s = 0; s < CC_TINY_S; ++s)
+          xc[s] = (s < C.S && act) ? p.tape[((long long)k * p.tape_rows + C.tape_row + s) * p.Bpad + b] : 0.f;
+        float xt[CC_TINY_S], gin[CC_TINY_K];
+#pragma unroll
+        for (int s = 0; s < CC_TINY_S; ++s) xt[s] = xc[s];
+        cc_tiny_step(C, cc_cs(w), xt, tc, vc, a, nullptr, nullptr, gin);  // a_k is needed for u_transform'
+      } else {
+        cc_tape_load<8>(p, C, k, w);
+        cc_set_inputs(C, w, vc, tc, 1);
+        __syncwarp();
+        cc_node_step<8>(0, w, tc, true, true, false, 0);
+#pragma unroll
+        for (int i = 0; i < CC_TINY_O; ++i) a[i] = (i < M.I) ? cc_ws(w)[C.w_OUT + i * CC_LD + w.lane] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < CC_TINY_O; ++i)
+        if (i < M.I) cc_ws(w)[p.w_araw + i * CC_LD + w.lane] = a[i];
+      if (M.recompute) {
+        cc_tape_load<TN>(p, M, k, w);
+        float am[CC_TINY_K];
+#pragma unroll
+        for (int i = 0; i < CC_TINY_K; ++i) am[i] = (i < CC_TINY_O) ? a[i < CC_TINY_O ? i : 0] : 0.f;
+        cc_set_inputs(M, w, am, tm, 1);
+      }
+      for (int o = 0; o < M.O; ++o) {
+        const float yb = act ? __ldg(p.ybar + b * yrow + yoff + o) : 0.f;
+        cc_ws(w)[M.w_OB + o * CC_LD + w.lane] = yb + cc_ws(w)[p.w_yfb + o * CC_LD + w.lane];
+      }
+      __syncwarp();
+      if (M.recompute) cc_node_step<TN>(closed ? 1 : 0, w, tm, true, true, false, 0);
+      cc_node_bwd<TN>(closed ? 1 : 0, w, p.w_araw);
+      // cotangent of the controller output = cotangent of the model input
+      if (CM == CC_CTRL_TINY) {
+        float ob[CC_TINY_O], vb[CC_TINY_K];
+#pragma unroll
+        for (int i = 0; i < CC_TINY_O; ++i) ob[i] = (i < M.I) ? cc_ws(w)[M.w_VB + i * CC_LD + w.lane] : 0.f;
+        cc_tiny_bwd(C, w, xc, tc, vc, ob, lamc, vb);
+        for (int o = 0; o < M.O; ++o) {
+          float fb = 0.f;
+#pragma unroll
+          for (int i = 0; i < CC_TINY_K; ++i)
+            if (i == p.R + o) fb = vb[i];
+          cc_ws(w)[p.w_yfb + o * CC_LD + w.lane] = fb;
+        }
+      } else {
+        for (int i = 0; i < M.I; ++i) cc_ws(w)[C.w_OB + i * CC_LD + w.lane] = cc_ws(w)[M.w_VB + i * CC_LD + w.lane];
+        __syncwarp();
+        cc_node_bwd<8>(0, w, -1);
+        for (int o = 0; o < M.O; ++o) cc_ws(w)[p.w_yfb + o * CC_LD + w.lane] = cc_ws(w)[C.w_VB + (p.R + o) * CC_LD + w.lane];
+      }
+      __syncwarp();
+    } else {
+      const float tm = M.has_t ? ttab[k] : 0.f;
+      cc_tape_load<TN>(p, M, k, w);
+      cc_set_inputs(M, w, vin, tm, 1);
+#pragma unroll
+      for (int i = 0; i < CC_TINY_K; ++i)
+        if (i < M.I) cc_ws(w)[p.w_araw + i * CC_LD + w.lane] = vin[i];
+      for (int o = 0; o < M.O; ++o) cc_ws(w)[M.w_OB + o * CC_LD + w.lane] = act ? __ldg(p.ybar + b * yrow + yoff + o) : 0.f;
+      __syncwarp();
+      if (M.recompute) cc_node_step<TN>(closed ? 1 : 0, w, tm, true, true, false, 0);
+      cc_node_bwd<TN>(closed ? 1 : 0, w, p.w_araw);
+      if (p.ubar && act)
+        for (int i = 0; i < M.I; ++i) p.ubar[b * (long long)p.T * M.I + (long long)k * M.I + i] = cc_ws(w)[M.w_VB + i * CC_LD + w.lane];
     }
-    __syncthreads();
-    if (!closed && p.ubar)
-      cc_stage_out(p, p.ubar, CC_TC * M.I, (long long)p.T * M.I, (long long)k0 * M.I, kend * M.I, b0, smem + p.s_ub, th.tid);
-    __syncthreads();
   }
 
   if (!closed) {
     // y0 = out_scale * g([x0 ; 0]) only feeds g's parameters (x0 is not trained, neural_ode_model.py:151-158)
-    for (int i = th.tid; i < M.S * p.BT; i += p.nthreads) {
-      const int traj = i / M.S, s = i % M.S;
-      smem[M.s_X + s * p.BTP + traj] = (p.x0 && b0 + traj < p.B) ? __ldg(p.x0 + (b0 + traj) * M.S + s) : 0.f;
-    }
-    if (th.tid < p.BT) {
-      float v[16];
-      for (int i = 0; i < M.I; ++i) v[i] = 0.f;
-      cc_set_inputs(p, M, smem, th.tid, v, 0.f, false);
-      // cc_set_inputs applies u_transform(0), harmless: models have no feed-through
-      for (int o = 0; o < M.O; ++o)
-        smem[M.s_OB + o * p.BTP + th.tid] = (b0 + th.tid < p.B) ? __ldg(p.ybar + (b0 + th.tid) * (long long)(p.T + 1) * M.O + o) : 0.f;
-    }
-    __syncthreads();
-    cc_readout<TN>(p, M, smem + M.s_X, smem, M.s_GH, th);
+    for (int s = 0; s < M.S; ++s) cc_ws(w)[M.w_X + s * CC_LD + w.lane] = (p.x0 && act) ? __ldg(p.x0 + b * M.S + s) : 0.f;
+    float v0[CC_TINY_K];
+#pragma unroll
+    for (int i = 0; i < CC_TINY_K; ++i) v0[i] = 0.f;
+    cc_set_inputs(M, w, v0, 0.f, 2);  // u_transform(0) in the v rows is harmless: models have no feed-through
+    for (int o = 0; o < M.O; ++o) cc_ws(w)[M.w_OB + o * CC_LD + w.lane] = act ? __ldg(p.ybar + b * yrow + o) : 0.f;
+    __syncwarp();
+    cc_readout<TN>(0, M.w_X, true, w);
     float dummy[CC_TM][TN];
-    cc_readout_bwd<TN>(p, M, smem + M.s_X, smem, th, dummy, false);
+    cc_readout_bwd<TN>(M, cc_ws(w) + M.w_X, w, dummy);
   }
 
-  // per-CTA gradient block -> workspace (reduced over tiles in fixed order by cc_reduce_grad_kernel)
+  // gradient record of this warp tile -> workspace (reduced over tiles in fixed order afterwards)
+  __syncwarp();
+  float* rec = p.gpart + w.wt * p.g_rec;
   for (int n = 0; n < p.n_nodes; ++n) {
     const CcNodeDev& nd = p.nd[n];
     if (!nd.trainable) continue;
-    int off = nd.gw_off;
-    for (int w = 0; w < 2; ++w) {
-      const CcMlpDev& mlp = w ? nd.g : nd.f;
-      for (int l = 0; l < mlp.L; ++l) {
-        const CcLayerDev& L = mlp.layer[l];
-        const int sz = L.N * L.Kp;
-        for (int i = th.tid; i < sz; i += p.nthreads) p.gpart[tile * p.gw_total + off + i] = smem[L.s_gw + i];
-        off += sz;
+    if (nd.tiny) {
+      for (int e = w.lane; e < nd.g_total; e += 32) {
+        float s = 0.f;
+        for (int j = 0; j < 32; ++j) s += cc_ws(w)[nd.w_GP + e * CC_LD + ((j + w.lane) & 31)];
+        rec[nd.g_base + e] = s;
+      }
+    } else {
+      for (int which = 0; which < 2; ++which) {
+        const CcMlpDev& mlp = which ? nd.g : nd.f;
+        for (int l = 0; l < mlp.L; ++l) {
+          const CcLayerDev& L = mlp.layer[l];
+          for (int i = w.lane; i < L.N * L.K; i += 32) rec[nd.g_base + L.g_off + i] = cc_ws(w)[L.w_gw + i];
+        }
       }
     }
   }

@@ -1,31 +1,51 @@
 // cc_plan.h — host-built launch plan shared by the forward and backward kernels.
 //
-// Data layout.  A CTA owns a tile of BT trajectories for the whole time loop.  Every
-// activation buffer in shared memory is feature-major: buf[row][BTP] with the BT trajectories
-// contiguous (BTP = padded row stride), so that a thread's TM=4 trajectories are one float4.
-// A module ("node") keeps three stage buffers X / ZA / ZB whose rows are
-//     [ x (S) ; t (1, iff the module tracks time) ; v (I, the transformed input) ; 1 (bias row) ]
-// which is exactly the reference's batch_concat order of f's and g's inputs
-// (neural_ode_model.py:122-133, neural_ode_controller.py:121-134); weights are staged once per CTA
-// as Wt[row][Np] (k-major) with zero rows where an MLP does not consume t / v and the bias as the
-// row multiplying the constant-1 row.  Each layer evaluation is then a register-tiled SGEMM
-//     C[BT x N] = A[K x BT]^T . Wt[K x N],   thread tile TM x TN = 4 trajectories x 8 (or 10) outputs.
+// Execution model.  A WARP is an autonomous solver for 32 trajectories for the whole
+// time loop; a CTA is just `wpc` such warps sharing one staged copy of the weights.  After the
+// prologue there is no CTA-level barrier: a warp only ever reads activations it wrote itself, so
+// __syncwarp() is the only synchronisation in the time loop and warps drift freely (one warp's
+// epilogue / shuffle phase overlaps another warp's FFMA stream).
+//
+// Lane mapping: lane = cg * 8 + rg, 4 column groups (cg) x 8 row groups (rg).  A thread owns the
+// TM = 4 trajectories 4rg..4rg+3 of its warp and, for a layer with N outputs, the cpt = ceil(N/4)
+// consecutive outputs cg*cpt .. cg*cpt+cpt-1  ->  register tile [4][TN], TN >= cpt.
+//
+// Shared-memory layout.  Every activation buffer of a warp is feature-major, buf[row][32]
+// (32 = the warp's trajectories): a thread's 4 trajectories are one float4, a quarter-warp
+// (fixed cg, rg = 0..7) reads/writes 128 contiguous bytes -> every LDS.128/STS.128 is conflict free.
+// A module ("node") keeps two stage buffers X / Z whose rows are
+//     [ x (S) ; t (1, iff the module tracks time) ; v (I, transformed input) ; 1 (bias row) ]
+// = the reference's batch_concat order of f's and g's inputs (neural_ode_model.py:122-133,
+// neural_ode_controller.py:121-134).  Weights are staged once per CTA as Wt[row][4*GS]
+// (contraction-major; column n at (n / cpt) * GS + n % cpt; GS chosen so that the 4 column groups of
+// a warp hit disjoint banks) with zero rows where an MLP does not consume t / v and the bias as the
+// row that multiplies the constant-1 row.  Each layer evaluation is then a register-tiled SGEMM
+//     C[32 x N] = A[K x 32]^T . Wt[K x N]
+// RK4 ping-pongs X -> Z -> X -> Z -> X with the state tile and the stage sum in registers.
 #pragma once
 #include <stdint.h>
 
 #include "../../include/cc_b200.h"
 
 #define CC_TM 4
-#define CC_TC 16        /* time steps staged per I/O chunk */
-#define CC_MAX_SKINNY 4 /* layers with N <= this use the split-K path */
+#define CC_LD 32         /* floats per activation-buffer row = trajectories per warp */
+#define CC_MAX_SKINNY 4  /* layers with N <= this use the split-K + shuffle path */
+#define CC_TINY_S 8      /* per-lane ("tiny") node path: state_dim <= 8, rows <= 12, outputs <= 4 */
+#define CC_TINY_K 12
+#define CC_TINY_O 4
+
+enum CcCtrlMode { CC_CTRL_NONE = 0, CC_CTRL_TINY = 1, CC_CTRL_TILE = 2 };
 
 struct CcLayerDev {
   int K;       // contraction rows read from the source buffer (incl. the constant-1 row)
   int N;       // outputs
-  int CG;      // column groups = ceil(N / TN)
-  int Np;      // TN * CG rounded up to a multiple of 4 (row stride of Wt)
-  int Kp;      // TN * CGk rounded up to a multiple of 4 (row stride of the row-major copy)
-  int CGk;     // column groups over K (input-gradient GEMM)
+  int cpt;     // output columns per thread = ceil(N / 4)
+  int GS;      // column-group stride inside a Wt row (floats)
+  int ldw;     // Wt row stride = 4 * GS
+  int Kin;     // input rows whose cotangent goes through the tile path (state rows / hidden units)
+  int kcpt;    // columns per thread of the input-gradient tile = cpt of the source buffer
+  int GSk;     // group stride / row stride of the row-major copy W[n][...] used by the input gradient
+  int ldk;
   int act;     // activation applied to this layer's output
   int in_log;  // logical input width = row stride of the weight in theta
   int w_off;   // offset of weight[N][in_log] in theta
@@ -33,10 +53,12 @@ struct CcLayerDev {
   int first;   // first layer of its MLP: physical->logical row map goes through the node layout
   int use_t;   // (first layers) this MLP consumes the time row
   int use_v;   // (first layers) this MLP consumes the input rows
-  int s_wt;    // smem offset (floats) of Wt[K][Np]
-  int s_w;     // smem offset of W[N][Kp]      (backward only, else -1)
-  int s_gw;    // smem offset of Wbar[N][Kp]   (backward & trainable only, else -1)
-  int s_out;   // smem offset of the hidden output buffer [N+1][BTP] (hidden layers), else -1
+  int s_wt;    // CTA-shared: Wt[K][ldw]
+  int s_w;     // CTA-shared: W[N][ldk] (backward only, else -1)
+  int s_wv;    // CTA-shared: WV[I][N] weights of the input rows (backward, first layers), else -1
+  int w_gw;    // per-warp: Wbar[N][K] accumulator (backward & trainable, tile path), else -1
+  int w_out;   // per-warp: hidden output buffer [(N+1)][32] (hidden layers), else -1
+  int g_off;   // offset of this layer's [N][K] block inside the node's gradient record
 };
 
 struct CcMlpDev {
@@ -48,37 +70,44 @@ struct CcNodeDev {
   int S, I, O;
   int has_t, pre, ut, integrator, n_stages;
   float u_scale, out_scale, dt;
-  int K0;       // rows of X/ZA/ZB: S + has_t + I + 1
+  int K0;       // rows of X/Z: S + has_t + I + 1
   int row_t;    // row index of t (valid iff has_t)
   int row_v;    // first input row
   int row_one;  // constant-1 row
-  int CGs;      // column groups over the state (== f.layer[L-1].CG)
+  int cptS;     // state columns per thread = ceil(S / 4)
+  int tiny;     // evaluated per lane in registers (one trajectory per lane) instead of as tiles
   CcMlpDev f, g;
-  int s_X, s_ZA, s_ZB;  // stage buffers [K0][BTP]
-  int s_OUT;            // [O][BTP]
-  int s_P;              // split-K scratch [CGT][CC_MAX_SKINNY][BTP]
-  int tape_row;         // first row of this node's state inside a tape record
-  int P;                // parameter count
+  int w_X, w_Z;  // per-warp stage buffers [K0][32]
+  int w_OUT;     // per-warp [O][32]
+  int tape_row;  // first row of this node's state inside a tape record
+  int P;         // parameter count
   // backward only
-  int trainable;    // accumulate parameter gradients
-  int recompute;    // stage intermediates must be recomputed (trainable or non-linear f)
-  int s_Z[4];       // stage inputs kept for the reverse pass (Z[0] aliases X)
-  int s_HS[4][CC_MAX_LAYERS];  // hidden activations per stage
-  int s_KS[4];      // stage outputs k_i (only if act_final is non-linear), else -1
-  int s_GH[CC_MAX_LAYERS];     // g hidden activations
-  int s_LAM;        // adjoint of the state [S][BTP]
-  int s_DA, s_DB;   // cotangent ping-pong buffers [maxN+?][BTP]
-  int s_VB;         // input cotangent [I][BTP]
-  int s_OB;         // output cotangent [O][BTP]
-  int gw_off;       // offset of this node's gradient block inside a per-CTA partial record
+  int trainable;  // accumulate parameter gradients
+  int recompute;  // stage intermediates must be recomputed (trainable or non-linear networks)
+  int w_ZS[4];    // stage inputs kept for the reverse pass (ZS[0] aliases X)
+  int w_HS[4][CC_MAX_LAYERS];  // hidden activations per stage
+  int w_KS[4];    // stage outputs k_i (only if act_final is non-linear), else -1
+  int w_XN;       // [K0][32] post-step readout source in keep mode (x_next ; t ; v ; 1), else -1
+  int w_GH[CC_MAX_LAYERS];     // g hidden activations
+  int w_LAM;      // adjoint of the state [S][32]
+  int w_DA, w_DB; // cotangent ping-pong buffers [maxN][32]
+  int w_VB;       // input cotangent [I][32]
+  int w_OB;       // output cotangent [O][32]
+  int w_GP;       // tiny nodes: lane-private gradient accumulators [g_total][32]
+  int g_total;    // floats of this node's gradient record (sum of N*K over layers)
+  int g_base;     // offset of this node's record inside a per-warp gradient record
 };
 
 struct CcKParams {
   CcNodeDev nd[2];  // closed loop: nd[0] = controller, nd[1] = model; open loop: nd[0] = model
   int n_nodes;
-  int TN;  // thread-tile width over outputs: 8 or 10 (chosen to minimise column padding)
-  int BT, BTP, RG, CGT, nthreads;
+  int TN;           // register-tile width of the model kernels (8, 13 or 16)
+  int ctrl_mode;    // CcCtrlMode
+  int wpc;          // warps per CTA
+  int warp_floats;  // per-warp shared memory (floats)
+  int cta_floats;   // CTA-shared floats (weights) preceding the per-warp regions
   long long B;
+  long long n_wtiles;  // ceil(B / 32)
   int T;  // number of steps: T (open loop) or Tr (closed loop)
   int R;  // closed loop: reference width
   const float* theta[2];
@@ -88,15 +117,13 @@ struct CcKParams {
   float* out;          // y[B,T+1,O] or yhat[B,Tr,O]
   float* u_out;        // closed loop, optional
   float* x_final;      // open loop, optional
-  float* tape;         // [n_ckpt][tape_rows][Bpad]  (feature-major, independent of the tile size)
+  float* tape;         // [n_ckpt][tape_rows][Bpad] (feature-major); then float ttab[2][T] (step times)
   int ckpt_every, n_ckpt, tape_rows;
-  long long Bpad;      // B rounded up to a multiple of 256; after the records: float ttab[2][T] (step times)
+  long long Bpad;      // B rounded up to a multiple of 32
   // backward
   const float* ybar;   // [B,T+1,O] or [B,Tr,O]
   float* ubar;         // open loop, optional [B,T,I]
-  float* gpart;        // per-CTA gradient partials [n_tiles][gw_total]
-  int gw_total;
-  // I/O staging (floats)
-  int s_in, s_out, s_uo, s_noise, s_yprev, s_yb, s_ub, s_yfb, s_araw;
-  int smem_floats;
+  float* gpart;        // per-warp-tile gradient records [n_wtiles][g_rec]
+  int g_rec;
+  int w_yprev, w_yfb, w_araw;  // per-warp closed-loop scratch rows
 };
