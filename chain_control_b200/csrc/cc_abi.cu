@@ -102,7 +102,7 @@ struct PlanOpts {
 bool node_is_tiny(const CcModule* m) {
   const int K0 = m->state_dim + ((m->f_time_variant || m->g_time_variant) ? 1 : 0) + m->input_dim + 1;
   return m->f.n_layers == 1 && m->g.n_layers == 1 && m->state_dim <= CC_TINY_S && K0 <= CC_TINY_K &&
-         m->output_dim <= CC_TINY_O && m->input_dim <= 4;
+         m->output_dim <= CC_TINY_O && m->input_dim <= CC_TINY_O;
 }
 
 // column-group stride of a weight row for register-tile width TN: >= TN, a multiple of 4 and such
@@ -151,10 +151,10 @@ void describe_node(const CcModule* m, CcNodeDev* nd, bool trainable, bool tiny, 
       L.in_log = mlp->sizes[l];
       L.N = mlp->sizes[l + 1];
       L.K = L.first ? nd->K0 : L.in_log + 1;
-      if (tiny) {
+      if (tiny) {  // row-major W[n][CC_TINY_K]
         L.cpt = L.N;
-        L.GS = (L.N + 3) / 4 * 4;
-        L.ldw = L.GS;
+        L.GS = CC_TINY_K;
+        L.ldw = CC_TINY_K;
       } else {
         L.cpt = ceil_div(L.N, 4);
         L.GS = group_stride(TN);
@@ -190,7 +190,7 @@ void layout(CcKParams* p, bool bwd) {
     for (int w = 0; w < 2; ++w)
       for (int l = 0; l < devs[w]->L; ++l) {
         CcLayerDev& L = devs[w]->layer[l];
-        L.s_wt = (need_fwd || nd.tiny) ? cs.take(L.K * L.ldw) : -1;
+        L.s_wt = nd.tiny ? cs.take(L.N * CC_TINY_K) : (need_fwd ? cs.take(L.K * L.ldw) : -1);
         L.s_w = (bwd && !nd.tiny) ? cs.take(L.N * L.ldk) : -1;
         L.s_wv = (bwd && !nd.tiny && L.first && L.use_v && nd.I > 0) ? cs.take(nd.I * L.N) : -1;
         L.w_out = (!nd.tiny && need_fwd && !bwd && l < devs[w]->L - 1) ? ws.take((L.N + 1) * CC_LD) : -1;
@@ -203,8 +203,19 @@ void layout(CcKParams* p, bool bwd) {
     }
     for (int l = 0; l < CC_MAX_LAYERS; ++l) nd.w_GH[l] = -1;
     nd.g_base = grec;
-    if (nd.tiny) {
-      if (bwd && nd.trainable) { nd.w_GP = ws.take(nd.g_total * CC_LD); grec += nd.g_total; }
+    if (nd.tiny) {  // lane-private columns
+      nd.w_X = ws.take(nd.S * CC_LD);
+      nd.w_Z = ws.take(nd.K0 * CC_LD);
+      nd.w_XN = ws.take(nd.K0 * CC_LD);
+      nd.w_DB = ws.take(nd.S * CC_LD);
+      if (bwd) {
+        for (int s = 0; s < 4; ++s) { nd.w_ZS[s] = ws.take(nd.K0 * CC_LD); nd.w_KS[s] = ws.take(nd.S * CC_LD); }
+        nd.w_LAM = ws.take(nd.S * CC_LD);
+        nd.w_OB = ws.take(3 * nd.S * CC_LD);
+        nd.w_DA = ws.take((nd.S > nd.O ? nd.S : nd.O) * CC_LD);
+        nd.w_GP = ws.take(nd.g_total);
+        grec += nd.g_total;
+      }
       continue;
     }
     if (need_fwd) {

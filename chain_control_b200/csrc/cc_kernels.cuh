@@ -116,7 +116,10 @@ CC_DEV void cc_stage_mlp(const CcNodeDev& nd, const CcMlpDev& mlp, const float* 
                          int nthreads) {
   for (int l = 0; l < mlp.L; ++l) {
     const CcLayerDev& L = mlp.layer[l];
-    if (L.s_wt >= 0) {
+    if (L.s_wt >= 0 && nd.tiny) {  // row-major W[n][CC_TINY_K], zero padded
+      float* W = cs + L.s_wt;
+      for (int i = tid; i < L.N * CC_TINY_K; i += nthreads) W[i] = cc_weight_at(nd, L, theta, i / CC_TINY_K, i % CC_TINY_K);
+    } else if (L.s_wt >= 0) {
       float* Wt = cs + L.s_wt;
       for (int i = tid; i < L.K * L.ldw; i += nthreads) {
         const int k = i / L.ldw, c = i % L.ldw;
@@ -267,6 +270,7 @@ CC_DEV void cc_layer_skinny(const CcLayerDev& L, const float* src, float* dst, f
 template <int TN>
 CC_DEV const float* cc_mlp_hidden(const CcMlpDev& mlp, const float* src, const int* hbuf, const CcWarp& w) {
   float acc[CC_TM][TN];
+#pragma unroll 1
   for (int l = 0; l < mlp.L - 1; ++l) {
     const CcLayerDev& L = mlp.layer[l];
     float* dst = cc_ws(w) + (hbuf ? hbuf[l] : L.w_out);
@@ -350,6 +354,7 @@ CC_DEV_NOINLINE void cc_node_step(int node, const CcWarp w, float t, bool keep, 
   if (write_tape) cc_tape_store<TN>(p, nd, ck, w, xr);
   if (nd.integrator == CC_INT_RK4) {
     float ks[CC_TM][TN];
+#pragma unroll 1
     for (int s = 0; s < 4; ++s) {
       float* src = keep ? cc_ws(w) + nd.w_ZS[s] : ((s & 1) ? Z : X);
       float* dst = keep ? (s < 3 ? cc_ws(w) + nd.w_ZS[s + 1] : nullptr) : ((s & 1) ? X : Z);
@@ -410,7 +415,6 @@ CC_DEV_NOINLINE void cc_node_step(int node, const CcWarp w, float t, bool keep, 
 
 // zero a node's per-warp buffers and set the constant-1 rows (one warp)
 CC_DEV void cc_init_node_buffers(const CcNodeDev& nd, const CcWarp& w, bool bwd) {
-  if (nd.tiny && !bwd) return;
   auto init = [&](int off, int rows, int one_row) {
     if (off < 0) return;
     float* buf = cc_ws(w) + off;
@@ -443,7 +447,19 @@ CC_DEV void cc_init_node_buffers(const CcNodeDev& nd, const CcWarp& w, bool bwd)
       }
     }
   }
-  if (bwd && nd.tiny && nd.w_GP >= 0) init(nd.w_GP, nd.g_total, -1);
+  if (nd.tiny) {
+    init(nd.w_X, nd.S, -1);
+    init(nd.w_Z, nd.K0, -1);
+    init(nd.w_XN, nd.K0, -1);
+    init(nd.w_DB, nd.S, -1);
+    if (bwd) {
+      for (int s = 0; s < 4; ++s) { init(nd.w_ZS[s], nd.K0, -1); init(nd.w_KS[s], nd.S, -1); }
+      init(nd.w_LAM, nd.S, -1);
+      init(nd.w_OB, 3 * nd.S, -1);
+      init(nd.w_DA, nd.S > nd.O ? nd.S : nd.O, -1);
+      for (int e = w.lane; e < nd.g_total; e += 32) cc_ws(w)[nd.w_GP + e] = 0.f;
+    }
+  }
 }
 
 // set the t / v rows of a tile-path node's stage buffers for the coming step (lane = trajectory).
@@ -481,115 +497,103 @@ CC_DEV void cc_set_inputs(const CcNodeDev& nd, const CcWarp& w, const float (&v)
 }
 
 // ------------------------------------------------------------------------------------------------
-// "tiny" nodes (single-layer f and g, S <= 8, rows <= 12, O <= 4): one trajectory per LANE, the
-// whole step in registers, weights read as warp-uniform (broadcast) shared-memory loads.
-// Used for the compact feedback controller (neural_ode_controller_compact_example.py:106-129),
-// whose arithmetic is ~1% of the closed loop but would otherwise idle 3 of 4 column groups.
+// "tiny" nodes (single-layer f and g, S <= 8, rows <= 12, O <= 4, I <= 4): one trajectory per LANE.
+// All per-trajectory vectors live in lane-private columns of per-warp shared memory (buf[row][lane],
+// conflict free); the current stage input is gathered into 12 registers and every output is one
+// 12-term dot product against a weight row read as three warp-uniform LDS.128.  Compact code (the
+// loops over outputs are not unrolled) - the step of the compact feedback controller
+// (neural_ode_controller_compact_example.py:106-129) is ~1% of the closed loop's arithmetic.
+// Weights of tiny nodes are staged row-major: W[n][CC_TINY_K] (zero padded).
 // ------------------------------------------------------------------------------------------------
-struct CcTinyStage {
-  float in[CC_TINY_K];  // [z ; t ; v~ ; 1]
-};
-
-CC_DEV void cc_tiny_build_in(const CcNodeDev& nd, const float (&z)[CC_TINY_S], float t, const float* vt, float (&in)[CC_TINY_K]) {
+CC_DEV void cc_tiny_load_in(const float* IN, int K, float (&in)[CC_TINY_K]) {
 #pragma unroll
-  for (int r = 0; r < CC_TINY_K; ++r) {
-    float val = 0.f;
-    if (r < nd.S) {
+  for (int k = 0; k < CC_TINY_K; ++k) in[k] = (k < K) ? IN[k * CC_LD] : 0.f;
+}
+CC_DEV void cc_tiny_load_row(const float* Wrow, float (&wr)[CC_TINY_K]) {
 #pragma unroll
-      for (int s = 0; s < CC_TINY_S; ++s)
-        if (s == r) val = z[s];
-    } else if (nd.has_t && r == nd.row_t) val = t;
-    else if (r >= nd.row_v && r < nd.row_v + nd.I) val = vt[r - nd.row_v];
-    else if (r == nd.row_one) val = 1.f;
-    in[r] = val;
+  for (int q = 0; q < CC_TINY_K / 4; ++q) {
+    const float4 v = *reinterpret_cast<const float4*>(Wrow + 4 * q);
+    wr[4 * q + 0] = v.x; wr[4 * q + 1] = v.y; wr[4 * q + 2] = v.z; wr[4 * q + 3] = v.w;
   }
 }
-// out[n] = act(sum_k in[k] * Wt[k][n])   (Wt compact: ldw = round4(N), column n at n)
-template <int NMAX>
-CC_DEV void cc_tiny_matvec(const CcLayerDev& L, const float* cs, const float (&in)[CC_TINY_K], float (&out)[NMAX]) {
-  const float* Wt = cs + L.s_wt;
+CC_DEV float cc_tiny_dot(const float* Wrow, const float (&in)[CC_TINY_K]) {
+  float wr[CC_TINY_K];
+  cc_tiny_load_row(Wrow, wr);
+  float acc = 0.f;
 #pragma unroll
-  for (int n = 0; n < NMAX; ++n) out[n] = 0.f;
-#pragma unroll
-  for (int k = 0; k < CC_TINY_K; ++k) {
-    if (k < L.K) {
-#pragma unroll
-      for (int n = 0; n < NMAX; ++n)
-        if (n < L.N) out[n] = fmaf(in[k], Wt[k * L.ldw + n], out[n]);
-    }
-  }
-  if (L.act != CC_ACT_IDENTITY) {
-#pragma unroll
-    for (int n = 0; n < NMAX; ++n) out[n] = cc_act(L.act, out[n]);
-  }
+  for (int k = 0; k < CC_TINY_K; ++k) acc = fmaf(in[k], wr[k], acc);
+  return acc;
 }
-
-// one step of a tiny node for this lane's trajectory.  x: state (in/out); v: raw input [I];
-// out: readout [O].  stages (optional): the four stage inputs, kept for the reverse pass.
-CC_DEV void cc_tiny_step(const CcNodeDev& nd, const float* cs, float (&x)[CC_TINY_S], float t, const float* v,
-                         float (&out)[CC_TINY_O], CcTinyStage* stages, float (*kout)[CC_TINY_S], float (&gin)[CC_TINY_K]) {
-  const float h = nd.dt;
-  float vt[CC_TINY_K];
+// t / v~ / 1 rows of a lane-private input column
+CC_DEV void cc_tiny_fill_tv(const CcNodeDev& nd, float* IN, float ts, const float (&vt)[CC_TINY_O]) {
+  if (nd.has_t) IN[nd.row_t * CC_LD] = ts;
 #pragma unroll
-  for (int i = 0; i < CC_TINY_K; ++i) vt[i] = (i < nd.I) ? cc_ut(nd.ut, nd.u_scale, v[i]) : 0.f;
-  const CcLayerDev& F = nd.f.layer[0];
-  const CcLayerDev& G = nd.g.layer[0];
+  for (int i = 0; i < CC_TINY_O; ++i)
+    if (i < nd.I) IN[(nd.row_v + i) * CC_LD] = vt[i];
+  IN[nd.row_one * CC_LD] = 1.f;
+}
+CC_DEV void cc_tiny_readout(const CcNodeDev& nd, const float* WG, const float* GIN, float (&out)[CC_TINY_O]) {
   float in[CC_TINY_K];
-  if (nd.pre) {
-    cc_tiny_build_in(nd, x, t, vt, gin);
-    cc_tiny_matvec<CC_TINY_O>(G, cs, gin, out);
-  }
-  float k[CC_TINY_S], ks[CC_TINY_S], z[CC_TINY_S], xn[CC_TINY_S];
-  if (nd.integrator == CC_INT_RK4) {
+  cc_tiny_load_in(GIN, nd.K0, in);
+  const int act = nd.g.layer[0].act;
 #pragma unroll
-    for (int s = 0; s < CC_TINY_S; ++s) z[s] = x[s];
+  for (int o = 0; o < CC_TINY_O; ++o) out[o] = (o < nd.O) ? nd.out_scale * cc_act(act, cc_tiny_dot(WG + o * CC_TINY_K, in)) : 0.f;
+}
+
+// One step of a tiny node for this lane's trajectory.  The state lives in TX = ws[w_X][lane].
+// v: raw input.  out: readout.  KEEP (backward): stage inputs stay in ZS[0..3], stage outputs in
+// KS[0..3], the post-step readout input in XN, and TX keeps x.
+template <bool KEEP>
+CC_DEV void cc_tiny_step(const CcNodeDev& nd, const CcWarp& w, float t, const float (&v)[CC_TINY_O], float (&out)[CC_TINY_O]) {
+  float* ws = cc_ws(w) + w.lane;
+  const float* cs = cc_cs(w);
+  const CcLayerDev& F = nd.f.layer[0];
+  const float* WF = cs + F.s_wt;
+  const float* WG = cs + nd.g.layer[0].s_wt;
+  float* TX = ws + nd.w_X;
+  float* TKS = ws + nd.w_DB;
+  float* INA = ws + nd.w_Z;
+  float* INB = ws + nd.w_XN;
+  const float h = nd.dt;
+  float vt[CC_TINY_O];
 #pragma unroll
-    for (int st = 0; st < 4; ++st) {
-      const float ts = st == 0 ? t : (st == 3 ? t + h : t + h / 2.f);
-      cc_tiny_build_in(nd, z, ts, vt, in);
-      if (stages) {
-#pragma unroll
-        for (int r = 0; r < CC_TINY_K; ++r) stages[st].in[r] = in[r];
-      }
-      cc_tiny_matvec<CC_TINY_S>(F, cs, in, k);
-      if (kout) {
-#pragma unroll
-        for (int s = 0; s < CC_TINY_S; ++s) kout[st][s] = k[s];
-      }
-#pragma unroll
-      for (int s = 0; s < CC_TINY_S; ++s) {
-        if (st == 0) { ks[s] = k[s]; z[s] = x[s] + h * k[s] / 2.f; }
-        else if (st == 1) { ks[s] = ks[s] + 2.f * k[s]; z[s] = x[s] + h * k[s] / 2.f; }
-        else if (st == 2) { ks[s] = ks[s] + 2.f * k[s]; z[s] = x[s] + h * k[s]; }
-        else xn[s] = x[s] + h * ((1.f / 6.f) * (ks[s] + k[s]));
+  for (int i = 0; i < CC_TINY_O; ++i) vt[i] = (i < nd.I) ? cc_ut(nd.ut, nd.u_scale, v[i]) : 0.f;
+  float* IN0 = KEEP ? ws + nd.w_ZS[0] : INA;
+  for (int s = 0; s < nd.S; ++s) IN0[s * CC_LD] = TX[s * CC_LD];
+  cc_tiny_fill_tv(nd, IN0, t, vt);
+  if (nd.pre) cc_tiny_readout(nd, WG, IN0, out);
+  const int nst = nd.integrator == CC_INT_RK4 ? 4 : 1;
+  float* XNEXT = KEEP ? INB : TX;  // where x_next goes (keep mode: state rows of XN)
+#pragma unroll 1
+  for (int st = 0; st < nst; ++st) {
+    float* IN = KEEP ? ws + nd.w_ZS[st] : ((st & 1) ? INB : INA);
+    float* INn = (st + 1 < nst) ? (KEEP ? ws + nd.w_ZS[st + 1] : ((st & 1) ? INA : INB)) : nullptr;
+    float in[CC_TINY_K];
+    cc_tiny_load_in(IN, nd.K0, in);
+    if (INn) cc_tiny_fill_tv(nd, INn, st == 2 ? t + h : t + h / 2.f, vt);
+#pragma unroll 1
+    for (int n = 0; n < nd.S; ++n) {
+      const float k = cc_act(F.act, cc_tiny_dot(WF + n * CC_TINY_K, in));
+      if (KEEP) (ws + nd.w_KS[st])[n * CC_LD] = k;
+      const float x = TX[n * CC_LD];
+      if (nd.integrator == CC_INT_RK4) {
+        if (st == 0) { TKS[n * CC_LD] = k; INn[n * CC_LD] = x + h * k / 2.f; }
+        else if (st == 1) { TKS[n * CC_LD] = TKS[n * CC_LD] + 2.f * k; INn[n * CC_LD] = x + h * k / 2.f; }
+        else if (st == 2) { TKS[n * CC_LD] = TKS[n * CC_LD] + 2.f * k; INn[n * CC_LD] = x + h * k; }
+        else XNEXT[n * CC_LD] = x + h * ((1.f / 6.f) * (TKS[n * CC_LD] + k));
+      } else {
+        XNEXT[n * CC_LD] = nd.integrator == CC_INT_EE ? x + h * k : k;
       }
     }
-  } else {
-    cc_tiny_build_in(nd, x, t, vt, in);
-    if (stages) {
-#pragma unroll
-      for (int r = 0; r < CC_TINY_K; ++r) stages[0].in[r] = in[r];
-    }
-    cc_tiny_matvec<CC_TINY_S>(F, cs, in, k);
-    if (kout) {
-#pragma unroll
-      for (int s = 0; s < CC_TINY_S; ++s) kout[0][s] = k[s];
-    }
-#pragma unroll
-    for (int s = 0; s < CC_TINY_S; ++s) xn[s] = nd.integrator == CC_INT_EE ? x[s] + h * k[s] : k[s];
   }
   if (!nd.pre) {
-    // the readout sees the raw input (feed-through) and the pre-step time
-    float vraw[CC_TINY_K];
-#pragma unroll
-    for (int i = 0; i < CC_TINY_K; ++i) vraw[i] = (i < nd.I) ? v[i] : 0.f;
-    cc_tiny_build_in(nd, xn, t, vraw, gin);
-    cc_tiny_matvec<CC_TINY_O>(G, cs, gin, out);
+    // post-step readout g([x_next ; t ; v ; 1]) with the pre-step time
+    float* GIN = KEEP ? INB : INA;
+    if (!KEEP)
+      for (int s = 0; s < nd.S; ++s) GIN[s * CC_LD] = TX[s * CC_LD];
+    cc_tiny_fill_tv(nd, GIN, t, vt);
+    cc_tiny_readout(nd, WG, GIN, out);
   }
-#pragma unroll
-  for (int o = 0; o < CC_TINY_O; ++o) out[o] *= nd.out_scale;
-#pragma unroll
-  for (int s = 0; s < CC_TINY_S; ++s) x[s] = (s < nd.S) ? xn[s] : 0.f;
 }
 
 // The launch plan is copied once into the head of dynamic shared memory; all device code reads it
@@ -660,9 +664,6 @@ __global__ void __launch_bounds__(320, 1) cc_rollout_fwd_kernel(const CC_GRID_CO
   __syncwarp();
 
   float tc = 0.f, tm = 0.f;
-  float xc[CC_TINY_S];
-#pragma unroll
-  for (int s = 0; s < CC_TINY_S; ++s) xc[s] = 0.f;
   const int Win = closed ? p.R : M.I;
   float vin[CC_TINY_K];  // this step's external input (u or ref), prefetched one step ahead
 #pragma unroll
@@ -698,15 +699,11 @@ __global__ void __launch_bounds__(320, 1) cc_rollout_fwd_kernel(const CC_GRID_CO
       float a[CC_TINY_O];
       if (CM == CC_CTRL_TINY) {
         if (wt)
-          for (int s = 0; s < C.S; ++s) {
-            float xs = 0.f;
+          for (int s = 0; s < C.S; ++s) p.tape[((long long)ck * p.tape_rows + C.tape_row + s) * p.Bpad + b] = cc_ws(w)[C.w_X + s * CC_LD + w.lane];
+        float vcc[CC_TINY_O];
 #pragma unroll
-            for (int q = 0; q < CC_TINY_S; ++q)
-              if (q == s) xs = xc[q];
-            p.tape[((long long)ck * p.tape_rows + C.tape_row + s) * p.Bpad + b] = xs;
-          }
-        float gin[CC_TINY_K];
-        cc_tiny_step(C, cc_cs(w), xc, tc, vc, a, nullptr, nullptr, gin);
+        for (int i = 0; i < CC_TINY_O; ++i) vcc[i] = vc[i];
+        cc_tiny_step<false>(C, w, tc, vcc, a);
       } else {
         cc_set_inputs(C, w, vc, tc, 0);
         __syncwarp();

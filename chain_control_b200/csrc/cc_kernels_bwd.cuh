@@ -24,6 +24,7 @@ CC_DEV void cc_wgrad(const CcLayerDev& L, const float* D, const float* A, const 
   const int NT = (L.N + CC_WN - 1) / CC_WN;
   const int KT = (L.K + CC_WK - 1) / CC_WK;
   float* G = cc_ws(w) + L.w_gw;
+#pragma unroll 1
   for (int tile = w.lane; tile < NT * KT; tile += 32) {
     const int nt = tile / KT, kt = tile % KT;
     float acc[CC_WN][CC_WK];
@@ -110,6 +111,7 @@ template <int TN>
 CC_DEV void cc_mlp_bwd(const CcNodeDev& nd, const CcMlpDev& mlp, float (&d)[CC_TM][TN], const float* in0,
                        const int* hid, const CcWarp& w, float (&din)[CC_TM][TN]) {
   float* DA = cc_ws(w) + nd.w_DA;
+#pragma unroll 1
   for (int l = mlp.L - 1; l >= 0; --l) {
     const CcLayerDev& L = mlp.layer[l];
     cc_store_tile<TN>(DA, L.N, L.cpt, w, d);
@@ -182,6 +184,7 @@ CC_DEV_NOINLINE void cc_node_bwd(int node, const CcWarp w, int vraw_off) {
     float zsum[CC_TM][TN], zb[CC_TM][TN];
     cc_zero_tile<TN>(zsum);
     cc_zero_tile<TN>(zb);
+#pragma unroll 1
     for (int s = 3; s >= 0; --s) {
       float d[CC_TM][TN];
       float ks[CC_TM][TN];
@@ -261,120 +264,126 @@ CC_DEV void cc_tape_load(const CcKParams& p, const CcNodeDev& nd, int ck, const 
 }
 
 // ------------------------------------------------------------------------------------------------
-// reverse pass of a "tiny" node for this lane's trajectory (see cc_tiny_step)
-//   x: state at step start; v: raw input; ob: cotangent of the output; lam: cotangent of the next
-//   state (in) / of x (out); vb: cotangent of the raw input (out).  Parameter gradients go to the
+// reverse pass of a "tiny" node for this lane's trajectory.  Expects cc_tiny_step<true> to have just
+// run for this step (stage inputs in ZS, stage outputs in KS, readout input in ZS[0] / XN, `out`).
+//   v: raw input; ob: cotangent of the output; LAM (smem, lane-private): cotangent of the next state
+//   (in) / of x (out); vb: cotangent of the raw input (out).  Parameter gradients go to the
 //   lane-private accumulators GP[entry][lane] (reduced over lanes once, at the end of the kernel).
 // ------------------------------------------------------------------------------------------------
-CC_DEV void cc_tiny_bwd(const CcNodeDev& nd, const CcWarp& w, const float (&x0)[CC_TINY_S], float t, const float* v,
-                        const float (&ob)[CC_TINY_O], float (&lam)[CC_TINY_S], float (&vb)[CC_TINY_K]) {
-  const float h = nd.dt;
+// G[e] += sum_{lane} D[n][lane] * IN[k][lane] for the entries e = n*K0 + k of one tiny layer: the
+// outer products of all 32 trajectories are contracted across the warp (entries dealt to lanes,
+// lane-rotated quad order -> conflict-free LDS.128); one owner lane per entry -> deterministic.
+CC_DEV void cc_tiny_wgrad(const float* D, const float* IN, int N, int K0, float* G, int lane) {
+  for (int e = lane; e < N * K0; e += 32) {
+    const float* dr = D + (e / K0) * CC_LD;
+    const float* ir = IN + (e % K0) * CC_LD;
+    float s = 0.f;
+#pragma unroll
+    for (int qq = 0; qq < 8; ++qq) {
+      const int q = 4 * ((qq + lane) & 7);
+      const float4 a = *reinterpret_cast<const float4*>(dr + q);
+      const float4 b = *reinterpret_cast<const float4*>(ir + q);
+      s = fmaf(a.x, b.x, s); s = fmaf(a.y, b.y, s); s = fmaf(a.z, b.z, s); s = fmaf(a.w, b.w, s);
+    }
+    G[e] += s;
+  }
+}
+
+CC_DEV void cc_tiny_bwd(const CcNodeDev& nd, const CcWarp& w, const float (&v)[CC_TINY_O], const float (&out)[CC_TINY_O],
+                        const float (&ob)[CC_TINY_O], float (&vb)[CC_TINY_O]) {
+  float* wsb = cc_ws(w);
+  float* ws = wsb + w.lane;
+  const float* cs = cc_cs(w);
   const CcLayerDev& F = nd.f.layer[0];
   const CcLayerDev& G = nd.g.layer[0];
-  const float* WtF = cc_cs(w) + F.s_wt;
-  const float* WtG = cc_cs(w) + G.s_wt;
-  float* GP = cc_ws(w) + nd.w_GP;
-  // recompute the step, keeping stage inputs / outputs
-  CcTinyStage st[4];
-  float kout[4][CC_TINY_S];
-  float out[CC_TINY_O], gin[CC_TINY_K];
-  float x[CC_TINY_S];
+  const float* WF = cs + F.s_wt;
+  const float* WG = cs + G.s_wt;
+  float* GP = wsb + nd.w_GP;  // [g_total] per warp
+  float* LAM = ws + nd.w_LAM;
+  float* D = ws + nd.w_DA;
+  float* ZB = ws + nd.w_OB;
+  float* ZSUM = ZB + nd.S * CC_LD;
+  float* XRB = ZSUM + nd.S * CC_LD;
+  const float h = nd.dt;
+  const int K0 = nd.K0;
+  float acc[CC_TINY_K], wr[CC_TINY_K];
+  float utb[CC_TINY_O];
 #pragma unroll
-  for (int s = 0; s < CC_TINY_S; ++s) x[s] = x0[s];
-  cc_tiny_step(nd, cc_cs(w), x, t, v, out, st, kout, gin);
-  float utb[CC_TINY_K];
-#pragma unroll
-  for (int i = 0; i < CC_TINY_K; ++i) { vb[i] = 0.f; utb[i] = 0.f; }
+  for (int i = 0; i < CC_TINY_O; ++i) { vb[i] = 0.f; utb[i] = 0.f; }
   // readout
-  float xrb[CC_TINY_S];
+  const int gin_off = nd.pre ? nd.w_ZS[0] : nd.w_XN;
 #pragma unroll
-  for (int s = 0; s < CC_TINY_S; ++s) xrb[s] = 0.f;
+  for (int k = 0; k < CC_TINY_K; ++k) acc[k] = 0.f;
 #pragma unroll
   for (int o = 0; o < CC_TINY_O; ++o) {
     if (o < nd.O) {
       float d = nd.out_scale * ob[o];
       if (G.act != CC_ACT_IDENTITY) d *= cc_act_grad(G.act, nd.out_scale != 0.f ? out[o] / nd.out_scale : 0.f);
+      D[o * CC_LD] = d;
+      cc_tiny_load_row(WG + o * CC_TINY_K, wr);
 #pragma unroll
-      for (int k = 0; k < CC_TINY_K; ++k) {
-        if (k < G.K) {
-          const float wv = WtG[k * G.ldw + o];
-          GP[(G.g_off + o * G.K + k) * CC_LD + w.lane] += d * gin[k];
-          if (k < nd.S) {
-#pragma unroll
-            for (int s = 0; s < CC_TINY_S; ++s)
-              if (s == k) xrb[s] = fmaf(wv, d, xrb[s]);
-          } else if (k >= nd.row_v && k < nd.row_v + nd.I) {
-#pragma unroll
-            for (int i = 0; i < CC_TINY_K; ++i)
-              if (i == k - nd.row_v) vb[i] = fmaf(wv, d, vb[i]);  // feed-through: raw input
-          }
-        }
-      }
+      for (int k = 0; k < CC_TINY_K; ++k) acc[k] = fmaf(wr[k], d, acc[k]);
     }
   }
-  if (!nd.pre) {
+  __syncwarp();
+  cc_tiny_wgrad(wsb + nd.w_DA, wsb + gin_off, nd.O, K0, GP + G.g_off, w.lane);
+  __syncwarp();
 #pragma unroll
-    for (int s = 0; s < CC_TINY_S; ++s) lam[s] += xrb[s];
+  for (int k = 0; k < CC_TINY_K; ++k) {
+    if (k < nd.S) XRB[k * CC_LD] = acc[k];
+#pragma unroll
+    for (int i = 0; i < CC_TINY_O; ++i)
+      if (i < nd.I && k == nd.row_v + i) vb[i] += acc[k];  // feed-through rows
   }
+  if (!nd.pre)
+    for (int n = 0; n < nd.S; ++n) LAM[n * CC_LD] += XRB[n * CC_LD];
   const int nst = nd.integrator == CC_INT_RK4 ? 4 : 1;
-  float zsum[CC_TINY_S], zb[CC_TINY_S];
-#pragma unroll
-  for (int s = 0; s < CC_TINY_S; ++s) { zsum[s] = 0.f; zb[s] = 0.f; }
   const float c6 = h / 6.f, c3 = h / 3.f, c2 = h / 2.f;
+  for (int n = 0; n < nd.S; ++n) { ZB[n * CC_LD] = 0.f; ZSUM[n * CC_LD] = 0.f; }
+#pragma unroll 1
+  for (int st = nst - 1; st >= 0; --st) {
 #pragma unroll
-  for (int sti = 3; sti >= 0; --sti) {
-    if (sti < nst) {
-      float d[CC_TINY_S];
+    for (int k = 0; k < CC_TINY_K; ++k) acc[k] = 0.f;
+    const float* KS = ws + nd.w_KS[st];
+#pragma unroll 1
+    for (int n = 0; n < nd.S; ++n) {
+      const float lam = LAM[n * CC_LD], zb = ZB[n * CC_LD];
+      float kb;
+      if (nd.integrator == CC_INT_RK4) {
+        if (st == 3) kb = c6 * lam;
+        else if (st == 2) kb = c3 * lam + h * zb;
+        else if (st == 1) kb = c3 * lam + c2 * zb;
+        else kb = c6 * lam + c2 * zb;
+      } else {
+        kb = nd.integrator == CC_INT_EE ? h * lam : lam;
+      }
+      if (F.act != CC_ACT_IDENTITY) kb *= cc_act_grad(F.act, KS[n * CC_LD]);
+      D[n * CC_LD] = kb;
+      cc_tiny_load_row(WF + n * CC_TINY_K, wr);
 #pragma unroll
-      for (int s = 0; s < CC_TINY_S; ++s) {
-        float kb;
-        if (nd.integrator == CC_INT_RK4) {
-          if (sti == 3) kb = c6 * lam[s];
-          else if (sti == 2) kb = c3 * lam[s] + h * zb[s];
-          else if (sti == 1) kb = c3 * lam[s] + c2 * zb[s];
-          else kb = c6 * lam[s] + c2 * zb[s];
-        } else {
-          kb = nd.integrator == CC_INT_EE ? h * lam[s] : lam[s];
-        }
-        if (F.act != CC_ACT_IDENTITY) kb *= cc_act_grad(F.act, kout[sti][s]);
-        d[s] = (s < nd.S) ? kb : 0.f;
+      for (int k = 0; k < CC_TINY_K; ++k) acc[k] = fmaf(wr[k], kb, acc[k]);
+    }
+    __syncwarp();
+    cc_tiny_wgrad(wsb + nd.w_DA, wsb + nd.w_ZS[st], nd.S, K0, GP + F.g_off, w.lane);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < CC_TINY_K; ++k) {
+      if (k < nd.S) {
+        ZB[k * CC_LD] = acc[k];
+        ZSUM[k * CC_LD] += acc[k];
       }
 #pragma unroll
-      for (int s = 0; s < CC_TINY_S; ++s) zb[s] = 0.f;
-#pragma unroll
-      for (int k = 0; k < CC_TINY_K; ++k) {
-        if (k < F.K) {
-          float acc = 0.f;
-#pragma unroll
-          for (int n = 0; n < CC_TINY_S; ++n) {
-            if (n < nd.S) {
-              acc = fmaf(WtF[k * F.ldw + n], d[n], acc);
-              GP[(F.g_off + n * F.K + k) * CC_LD + w.lane] += d[n] * st[sti].in[k];
-            }
-          }
-          if (k < nd.S) {
-#pragma unroll
-            for (int s = 0; s < CC_TINY_S; ++s)
-              if (s == k) zb[s] = acc;
-          } else if (k >= nd.row_v && k < nd.row_v + nd.I) {
-#pragma unroll
-            for (int i = 0; i < CC_TINY_K; ++i)
-              if (i == k - nd.row_v) utb[i] += acc;
-          }
-        }
-      }
-#pragma unroll
-      for (int s = 0; s < CC_TINY_S; ++s) zsum[s] += zb[s];
+      for (int i = 0; i < CC_TINY_O; ++i)
+        if (i < nd.I && k == nd.row_v + i) utb[i] += acc[k];
     }
   }
-#pragma unroll
-  for (int s = 0; s < CC_TINY_S; ++s) {
-    if (nd.integrator == CC_INT_NONE) lam[s] = zb[s];
-    else lam[s] += zsum[s];
-    if (nd.pre) lam[s] += xrb[s];
+  for (int n = 0; n < nd.S; ++n) {
+    float l = nd.integrator == CC_INT_NONE ? ZB[n * CC_LD] : LAM[n * CC_LD] + ZSUM[n * CC_LD];
+    if (nd.pre) l += XRB[n * CC_LD];
+    LAM[n * CC_LD] = l;
   }
 #pragma unroll
-  for (int i = 0; i < CC_TINY_K; ++i)
+  for (int i = 0; i < CC_TINY_O; ++i)
     if (i < nd.I) vb[i] += utb[i] * cc_ut_grad(nd.ut, nd.u_scale, v[i]);
 }
 
@@ -403,17 +412,35 @@ __global__ void __launch_bounds__(320, 1) cc_rollout_bwd_kernel(const CC_GRID_CO
     for (int o = 0; o < M.O; ++o) cc_ws(w)[p.w_yfb + o * CC_LD + w.lane] = 0.f;
   __syncwarp();
 
-  float lamc[CC_TINY_S];
-#pragma unroll
-  for (int s = 0; s < CC_TINY_S; ++s) lamc[s] = 0.f;
   const int Win = closed ? p.R : M.I;
   const long long yrow = closed ? (long long)p.T * M.O : (long long)(p.T + 1) * M.O;
 
-  for (int k = p.T - 1; k >= 0; --k) {  // ckpt_every == 1: the tape holds the carry of every step
-    float vin[CC_TINY_K];
-#pragma unroll
-    for (int i = 0; i < CC_TINY_K; ++i) vin[i] = (i < Win && act) ? __ldg(p.in + b * (long long)p.T * Win + (long long)k * Win + i) : 0.f;
+  // per-lane scalars of a step (input, cotangent, fed-back output, tiny-controller state) are
+  // fetched one step ahead so that their global-memory latency hides behind a whole step of work
+  float n_vin[CC_TINY_K], n_yb[CC_TINY_O], n_yp[CC_TINY_O], n_xc[CC_TINY_S];
+  auto fetch = [&](int k) {
     const long long yoff = closed ? (long long)k * M.O : (long long)(k + 1) * M.O;
+#pragma unroll
+    for (int i = 0; i < CC_TINY_K; ++i) n_vin[i] = (i < Win && act) ? __ldg(p.in + b * (long long)p.T * Win + (long long)k * Win + i) : 0.f;
+#pragma unroll
+    for (int o = 0; o < CC_TINY_O; ++o) {
+      n_yb[o] = (o < M.O && act) ? __ldg(p.ybar + b * yrow + yoff + o) : 0.f;
+      n_yp[o] = (closed && o < M.O && act) ? p.tape[((long long)k * p.tape_rows + C.S + M.S + o) * p.Bpad + b] : 0.f;
+    }
+#pragma unroll
+    for (int s = 0; s < CC_TINY_S; ++s)
+      n_xc[s] = (CM == CC_CTRL_TINY && s < C.S && act) ? p.tape[((long long)k * p.tape_rows + C.tape_row + s) * p.Bpad + b] : 0.f;
+  };
+  if (p.T > 0) fetch(p.T - 1);
+  for (int k = p.T - 1; k >= 0; --k) {  // ckpt_every == 1: the tape holds the carry of every step
+    float vin[CC_TINY_K], yb[CC_TINY_O], ypv[CC_TINY_O], xcv[CC_TINY_S];
+#pragma unroll
+    for (int i = 0; i < CC_TINY_K; ++i) vin[i] = n_vin[i];
+#pragma unroll
+    for (int o = 0; o < CC_TINY_O; ++o) { yb[o] = n_yb[o]; ypv[o] = n_yp[o]; }
+#pragma unroll
+    for (int s = 0; s < CC_TINY_S; ++s) xcv[s] = n_xc[s];
+    if (k > 0) fetch(k - 1);
     if (closed) {
       const float tc = C.has_t ? ttab[k] : 0.f;
       const float tm = M.has_t ? ttab[p.T + k] : 0.f;
@@ -421,22 +448,20 @@ __global__ void __launch_bounds__(320, 1) cc_rollout_bwd_kernel(const CC_GRID_CO
       float vc[CC_TINY_K];
 #pragma unroll
       for (int i = 0; i < CC_TINY_K; ++i) vc[i] = vin[i];
-      for (int o = 0; o < M.O; ++o) {
-        const float yp = act ? p.tape[((long long)k * p.tape_rows + C.S + M.S + o) * p.Bpad + b] : 0.f;
+#pragma unroll
+      for (int o = 0; o < CC_TINY_O; ++o)
 #pragma unroll
         for (int i = 0; i < CC_TINY_K; ++i)
-          if (i == p.R + o) vc[i] = yp;
-      }
+          if (o < M.O && i == p.R + o) vc[i] = ypv[o];
       float a[CC_TINY_O];
-      float xc[CC_TINY_S];
+      float vcc[CC_TINY_O];
+#pragma unroll
+      for (int i = 0; i < CC_TINY_O; ++i) vcc[i] = vc[i];
       if (CM == CC_CTRL_TINY) {
 #pragma unroll
         for (int s = 0; s < CC_TINY_S; ++s)
-          xc[s] = (s < C.S && act) ? p.tape[((long long)k * p.tape_rows + C.tape_row + s) * p.Bpad + b] : 0.f;
-        float xt[CC_TINY_S], gin[CC_TINY_K];
-#pragma unroll
-        for (int s = 0; s < CC_TINY_S; ++s) xt[s] = xc[s];
-        cc_tiny_step(C, cc_cs(w), xt, tc, vc, a, nullptr, nullptr, gin);  // a_k is needed for u_transform'
+          if (s < C.S) cc_ws(w)[C.w_X + s * CC_LD + w.lane] = xcv[s];
+        cc_tiny_step<true>(C, w, tc, vcc, a);  // recompute with the stage intermediates kept; a_k feeds u_transform'
       } else {
         cc_tape_load<8>(p, C, k, w);
         cc_set_inputs(C, w, vc, tc, 1);
@@ -455,23 +480,22 @@ __global__ void __launch_bounds__(320, 1) cc_rollout_bwd_kernel(const CC_GRID_CO
         for (int i = 0; i < CC_TINY_K; ++i) am[i] = (i < CC_TINY_O) ? a[i < CC_TINY_O ? i : 0] : 0.f;
         cc_set_inputs(M, w, am, tm, 1);
       }
-      for (int o = 0; o < M.O; ++o) {
-        const float yb = act ? __ldg(p.ybar + b * yrow + yoff + o) : 0.f;
-        cc_ws(w)[M.w_OB + o * CC_LD + w.lane] = yb + cc_ws(w)[p.w_yfb + o * CC_LD + w.lane];
-      }
+#pragma unroll
+      for (int o = 0; o < CC_TINY_O; ++o)
+        if (o < M.O) cc_ws(w)[M.w_OB + o * CC_LD + w.lane] = yb[o] + cc_ws(w)[p.w_yfb + o * CC_LD + w.lane];
       __syncwarp();
       if (M.recompute) cc_node_step<TN>(closed ? 1 : 0, w, tm, true, true, false, 0);
       cc_node_bwd<TN>(closed ? 1 : 0, w, p.w_araw);
       // cotangent of the controller output = cotangent of the model input
       if (CM == CC_CTRL_TINY) {
-        float ob[CC_TINY_O], vb[CC_TINY_K];
+        float ob[CC_TINY_O], vb[CC_TINY_O];
 #pragma unroll
         for (int i = 0; i < CC_TINY_O; ++i) ob[i] = (i < M.I) ? cc_ws(w)[M.w_VB + i * CC_LD + w.lane] : 0.f;
-        cc_tiny_bwd(C, w, xc, tc, vc, ob, lamc, vb);
+        cc_tiny_bwd(C, w, vcc, a, ob, vb);
         for (int o = 0; o < M.O; ++o) {
           float fb = 0.f;
 #pragma unroll
-          for (int i = 0; i < CC_TINY_K; ++i)
+          for (int i = 0; i < CC_TINY_O; ++i)
             if (i == p.R + o) fb = vb[i];
           cc_ws(w)[p.w_yfb + o * CC_LD + w.lane] = fb;
         }
@@ -489,7 +513,9 @@ __global__ void __launch_bounds__(320, 1) cc_rollout_bwd_kernel(const CC_GRID_CO
 #pragma unroll
       for (int i = 0; i < CC_TINY_K; ++i)
         if (i < M.I) cc_ws(w)[p.w_araw + i * CC_LD + w.lane] = vin[i];
-      for (int o = 0; o < M.O; ++o) cc_ws(w)[M.w_OB + o * CC_LD + w.lane] = act ? __ldg(p.ybar + b * yrow + yoff + o) : 0.f;
+#pragma unroll
+      for (int o = 0; o < CC_TINY_O; ++o)
+        if (o < M.O) cc_ws(w)[M.w_OB + o * CC_LD + w.lane] = yb[o];
       __syncwarp();
       if (M.recompute) cc_node_step<TN>(closed ? 1 : 0, w, tm, true, true, false, 0);
       cc_node_bwd<TN>(closed ? 1 : 0, w, p.w_araw);
@@ -519,11 +545,7 @@ __global__ void __launch_bounds__(320, 1) cc_rollout_bwd_kernel(const CC_GRID_CO
     const CcNodeDev& nd = p.nd[n];
     if (!nd.trainable) continue;
     if (nd.tiny) {
-      for (int e = w.lane; e < nd.g_total; e += 32) {
-        float s = 0.f;
-        for (int j = 0; j < 32; ++j) s += cc_ws(w)[nd.w_GP + e * CC_LD + ((j + w.lane) & 31)];
-        rec[nd.g_base + e] = s;
-      }
+      for (int e = w.lane; e < nd.g_total; e += 32) rec[nd.g_base + e] = cc_ws(w)[nd.w_GP + e];
     } else {
       for (int which = 0; which < 2; ++which) {
         const CcMlpDev& mlp = which ? nd.g : nd.f;
