@@ -299,7 +299,7 @@ int make_plan(const CcModule* const* mods, int n_nodes, long long B, int T, cons
   if (cta_bytes + warp_bytes > kSmemBudget)
     return fail(CC_ERR_UNSUPPORTED, "architecture does not fit in %d KB of shared memory per CTA (weights %lld B + %lld B per warp)", kSmemBudget / 1024, cta_bytes, warp_bytes);
   int cap = (int)((kSmemBudget - cta_bytes) / (warp_bytes > 0 ? warp_bytes : 1));
-  if (cap > 10) cap = 10;
+  if (cap > 8) cap = 8;  // __launch_bounds__(256, 1): up to 255 registers per thread
   const char* env = getenv("CC_B200_WPC");
   int best = 1;
   if (env && atoi(env) >= 1 && atoi(env) <= cap) best = atoi(env);

@@ -217,6 +217,37 @@ CC_DEV void cc_store_tile(float* buf, int N, int cpt, const CcWarp& w, const flo
   }
 }
 
+// tile-wide activation / activation-derivative with the kind test hoisted out of the element loops
+template <int TN>
+CC_DEV void cc_act_tile(int kind, float (&t)[CC_TM][TN]) {
+  if (kind == CC_ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < CC_TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) t[i][j] = fmaxf(t[i][j], 0.f);
+  } else if (kind == CC_ACT_TANH) {
+#pragma unroll
+    for (int i = 0; i < CC_TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) t[i][j] = tanhf(t[i][j]);
+  }
+}
+// d *= act'(y) with y the activation output
+template <int TN>
+CC_DEV void cc_act_grad_tile(int kind, float (&d)[CC_TM][TN], const float (&y)[CC_TM][TN]) {
+  if (kind == CC_ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < CC_TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) d[i][j] = y[i][j] > 0.f ? d[i][j] : 0.f;
+  } else if (kind == CC_ACT_TANH) {
+#pragma unroll
+    for (int i = 0; i < CC_TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) d[i][j] *= 1.f - y[i][j] * y[i][j];
+  }
+}
+
 // one layer as a tile GEMM; leaves the raw accumulators (bias included via the 1-row) in acc
 template <int TN>
 CC_DEV void cc_layer_gemm(const CcLayerDev& L, const float* src, const CcWarp& w, float (&acc)[CC_TM][TN]) {
@@ -278,10 +309,7 @@ CC_DEV const float* cc_mlp_hidden(const CcMlpDev& mlp, const float* src, const i
       cc_layer_skinny(L, src, dst, 1.f, w);
     } else {
       cc_layer_gemm<TN>(L, src, w, acc);
-#pragma unroll
-      for (int i = 0; i < CC_TM; ++i)
-#pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = cc_act(L.act, acc[i][j]);
+      cc_act_tile<TN>(L.act, acc);
       cc_store_tile<TN>(dst, L.N, L.cpt, w, acc);
       __syncwarp();
     }
@@ -303,10 +331,11 @@ CC_DEV_NOINLINE void cc_readout(int node, int src_off, bool keep_gh, const CcWar
   } else {
     float acc[CC_TM][TN];
     cc_layer_gemm<TN>(L, in, w, acc);
+    cc_act_tile<TN>(L.act, acc);
 #pragma unroll
     for (int i = 0; i < CC_TM; ++i)
 #pragma unroll
-      for (int j = 0; j < TN; ++j) acc[i][j] = nd.out_scale * cc_act(L.act, acc[i][j]);
+      for (int j = 0; j < TN; ++j) acc[i][j] *= nd.out_scale;
     cc_store_tile<TN>(OUT, L.N, L.cpt, w, acc);
     __syncwarp();
   }
@@ -318,12 +347,7 @@ CC_DEV void cc_rhs(const CcNodeDev& nd, const float* src, const int* hbuf, const
   const float* in = cc_mlp_hidden<TN>(nd.f, src, hbuf, w);
   const CcLayerDev& L = nd.f.layer[nd.f.L - 1];
   cc_layer_gemm<TN>(L, in, w, k);
-  if (L.act != CC_ACT_IDENTITY) {
-#pragma unroll
-    for (int i = 0; i < CC_TM; ++i)
-#pragma unroll
-      for (int j = 0; j < TN; ++j) k[i][j] = cc_act(L.act, k[i][j]);
-  }
+  cc_act_tile<TN>(L.act, k);
 }
 
 // the node's state tile -> tape record `ck` (128-byte coalesced float4 stores)
@@ -364,24 +388,25 @@ CC_DEV_NOINLINE void cc_node_step(int node, const CcWarp w, float t, bool keep, 
       }
       cc_rhs<TN>(nd, src, keep ? nd.w_HS[s] : nullptr, w, k);
       if (keep && nd.w_KS[s] >= 0) cc_store_tile<TN>(cc_ws(w) + nd.w_KS[s], nd.S, nd.cptS, w, k);
+      // ks = k1 + 2 k2 + 2 k3 (+ k4); stage input x + h k / 2 (s = 0, 1), x + h k (s = 2);
+      // x_next = x + h (1/6 (ks + k4))  -- the reference's operation order (integrate.py:6-13)
+      if (s < 3) {
+        const float wk = s == 0 ? 1.f : 2.f;   // exact scalings: identical rounding to the reference
+        const float cz = s == 2 ? 1.f : 0.5f;
 #pragma unroll
-      for (int i = 0; i < CC_TM; ++i)
+        for (int i = 0; i < CC_TM; ++i)
 #pragma unroll
-        for (int j = 0; j < TN; ++j) {
-          const float kk = k[i][j];
-          if (s == 0) {
-            ks[i][j] = kk;
-            k[i][j] = xr[i][j] + h * kk / 2.f;
-          } else if (s == 1) {
-            ks[i][j] = ks[i][j] + 2.f * kk;
-            k[i][j] = xr[i][j] + h * kk / 2.f;
-          } else if (s == 2) {
-            ks[i][j] = ks[i][j] + 2.f * kk;
-            k[i][j] = xr[i][j] + h * kk;
-          } else {
-            k[i][j] = xr[i][j] + h * ((1.f / 6.f) * (ks[i][j] + kk));
+          for (int j = 0; j < TN; ++j) {
+            const float kk = k[i][j];
+            ks[i][j] = s == 0 ? kk : ks[i][j] + wk * kk;
+            k[i][j] = xr[i][j] + (h * kk) * cz;
           }
-        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < CC_TM; ++i)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) k[i][j] = xr[i][j] + h * ((1.f / 6.f) * (ks[i][j] + k[i][j]));
+      }
       if (dst) cc_store_tile<TN>(dst, nd.S, nd.cptS, w, k);
       __syncwarp();
     }
@@ -631,7 +656,7 @@ CC_DEV void cc_make_warp(const CcKParams& p, float* cta_smem, CcWarp& w) {
 // TN: register-tile width of the model; CM: controller mode (none / tiny / tile with TN = 8)
 // ------------------------------------------------------------------------------------------------
 template <int TN, int CM>
-__global__ void __launch_bounds__(320, 1) cc_rollout_fwd_kernel(const CC_GRID_CONSTANT CcKParams gp) {
+__global__ void __launch_bounds__(256, 1) cc_rollout_fwd_kernel(const CC_GRID_CONSTANT CcKParams gp) {
   CC_KERNEL_PROLOGUE(gp)
   const bool closed = CM != CC_CTRL_NONE;
   const CcNodeDev& M = p.nd[closed ? 1 : 0];

@@ -127,7 +127,8 @@ CC_DEV void cc_mlp_bwd(const CcNodeDev& nd, const CcMlpDev& mlp, float (&d)[CC_T
 #pragma unroll
       for (int i = 0; i < CC_TM; ++i)
 #pragma unroll
-        for (int j = 0; j < TN; ++j) d[i][j] = din[i][j] * cc_act_grad(Lp.act, hv[i][j]);
+        for (int j = 0; j < TN; ++j) d[i][j] = din[i][j];
+      cc_act_grad_tile<TN>(Lp.act, d, hv);
     }
     __syncwarp();  // DA is rewritten by the next layer
   }
@@ -187,20 +188,18 @@ CC_DEV_NOINLINE void cc_node_bwd(int node, const CcWarp w, int vraw_off) {
 #pragma unroll 1
     for (int s = 3; s >= 0; --s) {
       float d[CC_TM][TN];
-      float ks[CC_TM][TN];
-      if (FL.act != CC_ACT_IDENTITY) cc_load_tile<TN>(cc_ws(w) + nd.w_KS[s], nd.S, nd.cptS, w, ks);
+      // k_bar_s = a_s * lam + b_s * z_bar_{s+1}     
+      const float ca = (s == 3 || s == 0) ? c6 : c3;
+      const float cb = s == 3 ? 0.f : (s == 2 ? h : c2);
 #pragma unroll
       for (int i = 0; i < CC_TM; ++i)
 #pragma unroll
-        for (int j = 0; j < TN; ++j) {
-          float kb;
-          if (s == 3) kb = c6 * lam[i][j];
-          else if (s == 2) kb = c3 * lam[i][j] + h * zb[i][j];
-          else if (s == 1) kb = c3 * lam[i][j] + c2 * zb[i][j];
-          else kb = c6 * lam[i][j] + c2 * zb[i][j];
-          if (FL.act != CC_ACT_IDENTITY) kb *= cc_act_grad(FL.act, ks[i][j]);
-          d[i][j] = kb;
-        }
+        for (int j = 0; j < TN; ++j) d[i][j] = ca * lam[i][j] + cb * zb[i][j];
+      if (FL.act != CC_ACT_IDENTITY) {
+        float ks[CC_TM][TN];
+        cc_load_tile<TN>(cc_ws(w) + nd.w_KS[s], nd.S, nd.cptS, w, ks);
+        cc_act_grad_tile<TN>(FL.act, d, ks);
+      }
       cc_mlp_bwd<TN>(nd, nd.f, d, nd.recompute ? cc_ws(w) + nd.w_ZS[s] : X, nd.w_HS[s], w, zb);
 #pragma unroll
       for (int i = 0; i < CC_TM; ++i)
@@ -391,7 +390,7 @@ CC_DEV void cc_tiny_bwd(const CcNodeDev& nd, const CcWarp& w, const float (&v)[C
 // K2 + K4: reverse time loop
 // ------------------------------------------------------------------------------------------------
 template <int TN, int CM>
-__global__ void __launch_bounds__(320, 1) cc_rollout_bwd_kernel(const CC_GRID_CONSTANT CcKParams gp) {
+__global__ void __launch_bounds__(256, 1) cc_rollout_bwd_kernel(const CC_GRID_CONSTANT CcKParams gp) {
   CC_KERNEL_PROLOGUE(gp)
   const bool closed = CM != CC_CTRL_NONE;
   const CcNodeDev& M = p.nd[closed ? 1 : 0];
