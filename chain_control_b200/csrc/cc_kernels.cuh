@@ -596,18 +596,24 @@ CC_DEV void cc_tiny_step(const CcNodeDev& nd, const CcWarp& w, float t, const fl
     float in[CC_TINY_K];
     cc_tiny_load_in(IN, nd.K0, in);
     if (INn) cc_tiny_fill_tv(nd, INn, st == 2 ? t + h : t + h / 2.f, vt);
-#pragma unroll 1
-    for (int n = 0; n < nd.S; ++n) {
-      const float k = cc_act(F.act, cc_tiny_dot(WF + n * CC_TINY_K, in));
-      if (KEEP) (ws + nd.w_KS[st])[n * CC_LD] = k;
-      const float x = TX[n * CC_LD];
-      if (nd.integrator == CC_INT_RK4) {
-        if (st == 0) { TKS[n * CC_LD] = k; INn[n * CC_LD] = x + h * k / 2.f; }
-        else if (st == 1) { TKS[n * CC_LD] = TKS[n * CC_LD] + 2.f * k; INn[n * CC_LD] = x + h * k / 2.f; }
-        else if (st == 2) { TKS[n * CC_LD] = TKS[n * CC_LD] + 2.f * k; INn[n * CC_LD] = x + h * k; }
-        else XNEXT[n * CC_LD] = x + h * ((1.f / 6.f) * (TKS[n * CC_LD] + k));
-      } else {
-        XNEXT[n * CC_LD] = nd.integrator == CC_INT_EE ? x + h * k : k;
+    // all S outputs as independent 12-term chains (ILP across outputs hides the FMA latency)
+    float kk[CC_TINY_S];
+#pragma unroll
+    for (int n = 0; n < CC_TINY_S; ++n) kk[n] = (n < nd.S) ? cc_tiny_dot(WF + n * CC_TINY_K, in) : 0.f;
+#pragma unroll
+    for (int n = 0; n < CC_TINY_S; ++n) {
+      if (n < nd.S) {
+        const float k = cc_act(F.act, kk[n]);
+        if (KEEP) (ws + nd.w_KS[st])[n * CC_LD] = k;
+        const float x = TX[n * CC_LD];
+        if (nd.integrator == CC_INT_RK4) {
+          if (st == 0) { TKS[n * CC_LD] = k; INn[n * CC_LD] = x + h * k / 2.f; }
+          else if (st == 1) { TKS[n * CC_LD] = TKS[n * CC_LD] + 2.f * k; INn[n * CC_LD] = x + h * k / 2.f; }
+          else if (st == 2) { TKS[n * CC_LD] = TKS[n * CC_LD] + 2.f * k; INn[n * CC_LD] = x + h * k; }
+          else XNEXT[n * CC_LD] = x + h * ((1.f / 6.f) * (TKS[n * CC_LD] + k));
+        } else {
+          XNEXT[n * CC_LD] = nd.integrator == CC_INT_EE ? x + h * k : k;
+        }
       }
     }
   }

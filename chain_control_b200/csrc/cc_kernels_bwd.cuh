@@ -276,15 +276,15 @@ CC_DEV void cc_tiny_wgrad(const float* D, const float* IN, int N, int K0, float*
   for (int e = lane; e < N * K0; e += 32) {
     const float* dr = D + (e / K0) * CC_LD;
     const float* ir = IN + (e % K0) * CC_LD;
-    float s = 0.f;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;  // four independent chains
 #pragma unroll
     for (int qq = 0; qq < 8; ++qq) {
       const int q = 4 * ((qq + lane) & 7);
       const float4 a = *reinterpret_cast<const float4*>(dr + q);
       const float4 b = *reinterpret_cast<const float4*>(ir + q);
-      s = fmaf(a.x, b.x, s); s = fmaf(a.y, b.y, s); s = fmaf(a.z, b.z, s); s = fmaf(a.w, b.w, s);
+      s0 = fmaf(a.x, b.x, s0); s1 = fmaf(a.y, b.y, s1); s2 = fmaf(a.z, b.z, s2); s3 = fmaf(a.w, b.w, s3);
     }
-    G[e] += s;
+    G[e] += (s0 + s1) + (s2 + s3);
   }
 }
 
@@ -344,23 +344,18 @@ CC_DEV void cc_tiny_bwd(const CcNodeDev& nd, const CcWarp& w, const float (&v)[C
 #pragma unroll
     for (int k = 0; k < CC_TINY_K; ++k) acc[k] = 0.f;
     const float* KS = ws + nd.w_KS[st];
-#pragma unroll 1
-    for (int n = 0; n < nd.S; ++n) {
-      const float lam = LAM[n * CC_LD], zb = ZB[n * CC_LD];
-      float kb;
-      if (nd.integrator == CC_INT_RK4) {
-        if (st == 3) kb = c6 * lam;
-        else if (st == 2) kb = c3 * lam + h * zb;
-        else if (st == 1) kb = c3 * lam + c2 * zb;
-        else kb = c6 * lam + c2 * zb;
-      } else {
-        kb = nd.integrator == CC_INT_EE ? h * lam : lam;
-      }
-      if (F.act != CC_ACT_IDENTITY) kb *= cc_act_grad(F.act, KS[n * CC_LD]);
-      D[n * CC_LD] = kb;
-      cc_tiny_load_row(WF + n * CC_TINY_K, wr);
+    const float ca = nd.integrator == CC_INT_RK4 ? ((st == 3 || st == 0) ? c6 : c3) : (nd.integrator == CC_INT_EE ? h : 1.f);
+    const float cb = nd.integrator == CC_INT_RK4 ? (st == 3 ? 0.f : (st == 2 ? h : c2)) : 0.f;
 #pragma unroll
-      for (int k = 0; k < CC_TINY_K; ++k) acc[k] = fmaf(wr[k], kb, acc[k]);
+    for (int n = 0; n < CC_TINY_S; ++n) {
+      if (n < nd.S) {
+        float kb = ca * LAM[n * CC_LD] + cb * ZB[n * CC_LD];
+        if (F.act != CC_ACT_IDENTITY) kb *= cc_act_grad(F.act, KS[n * CC_LD]);
+        D[n * CC_LD] = kb;
+        cc_tiny_load_row(WF + n * CC_TINY_K, wr);
+#pragma unroll
+        for (int k = 0; k < CC_TINY_K; ++k) acc[k] = fmaf(wr[k], kb, acc[k]);
+      }
     }
     __syncwarp();
     cc_tiny_wgrad(wsb + nd.w_DA, wsb + nd.w_ZS[st], nd.S, K0, GP + F.g_off, w.lane);
