@@ -15,8 +15,18 @@
 #include <string>
 
 #include "cc_kernels.cuh"
-#include "cc_kernels_bwd.cuh"
 #include "cc_aux.cuh"
+#ifdef CC_EMULATE
+#define CC_TN_VALUE 8
+#include "cc_tn.cu"
+#undef CC_TN_VALUE
+#define CC_TN_VALUE 13
+#include "cc_tn.cu"
+#undef CC_TN_VALUE
+#define CC_TN_VALUE 16
+#include "cc_tn.cu"
+#undef CC_TN_VALUE
+#endif
 
 namespace {
 
@@ -329,36 +339,25 @@ int make_plan(const CcModule* const* mods, int n_nodes, long long B, int T, cons
   } while (0)
 #endif
 
-template <class Kern>
-int launch1(Kern kern, const CcKParams& p, void* stream) {
+}  // namespace
+// per-TN launchers (cc_tn.cu, compiled once per register-tile width)
+int cc_launch_fwd_tn8(const CcKParams& p, void* stream, char* err, int errlen);
+int cc_launch_bwd_tn8(const CcKParams& p, void* stream, char* err, int errlen);
+int cc_launch_fwd_tn13(const CcKParams& p, void* stream, char* err, int errlen);
+int cc_launch_bwd_tn13(const CcKParams& p, void* stream, char* err, int errlen);
+int cc_launch_fwd_tn16(const CcKParams& p, void* stream, char* err, int errlen);
+int cc_launch_bwd_tn16(const CcKParams& p, void* stream, char* err, int errlen);
+namespace {
+int launch_fwd(const CcKParams& p, void* stream) {
   g_launches.fetch_add(1);
-  const long long grid = (p.n_wtiles + p.wpc - 1) / p.wpc;
-  const size_t smem = ((size_t)p.cta_floats + (size_t)p.wpc * p.warp_floats + CC_PARAM_FLOATS) * 4;
-#ifdef CC_EMULATE
-  (void)stream;
-  ccemu::launch((int)grid, p.wpc * 32, smem, [&]() { kern(p); });
-  return CC_OK;
-#else
-  CC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(unsigned)grid, p.wpc * 32, smem, (cudaStream_t)stream>>>(p);
-  CC_CUDA_OK(cudaGetLastError());
-  return CC_OK;
-#endif
+  return p.TN == 8 ? cc_launch_fwd_tn8(p, stream, g_err, sizeof(g_err))
+         : p.TN == 13 ? cc_launch_fwd_tn13(p, stream, g_err, sizeof(g_err)) : cc_launch_fwd_tn16(p, stream, g_err, sizeof(g_err));
 }
-
-// dispatch on (model tile width, controller mode)
-#define CC_LAUNCH_CM(kern, TNV, p, stream)                                                              \
-  ((p).ctrl_mode == CC_CTRL_NONE ? launch1(kern<TNV, CC_CTRL_NONE>, p, stream)                          \
-   : (p).ctrl_mode == CC_CTRL_TINY ? launch1(kern<TNV, CC_CTRL_TINY>, p, stream)                        \
-                                   : launch1(kern<TNV, CC_CTRL_TILE>, p, stream))
-#ifdef CC_DEV_BUILD_TN13  /* development builds: only the TN = 13 kernels (much faster to compile) */
-#define CC_LAUNCH(kern, p, stream) \
-  ((p).TN == 13 ? CC_LAUNCH_CM(kern, 13, p, stream) : fail(CC_ERR_UNSUPPORTED, "dev build: TN=13 only"))
-#else
-#define CC_LAUNCH(kern, p, stream)                                        \
-  ((p).TN == 8 ? CC_LAUNCH_CM(kern, 8, p, stream)                         \
-   : (p).TN == 13 ? CC_LAUNCH_CM(kern, 13, p, stream) : CC_LAUNCH_CM(kern, 16, p, stream))
-#endif
+int launch_bwd(const CcKParams& p, void* stream) {
+  g_launches.fetch_add(1);
+  return p.TN == 8 ? cc_launch_bwd_tn8(p, stream, g_err, sizeof(g_err))
+         : p.TN == 13 ? cc_launch_bwd_tn13(p, stream, g_err, sizeof(g_err)) : cc_launch_bwd_tn16(p, stream, g_err, sizeof(g_err));
+}
 
 int n_ckpt_of(int T, int every) { return (T + every - 1) / every; }
 
@@ -413,7 +412,7 @@ int32_t cc_rollout_fwd(const CcModule* m, const float* theta, const float* u, co
   p.tape = (float*)tape;
   p.ckpt_every = tape ? ckpt_every : 1;
   p.n_ckpt = n_ckpt_of(T, p.ckpt_every);
-  return CC_LAUNCH(cc_rollout_fwd_kernel, p, stream);
+  return launch_fwd(p, stream);
 }
 
 int32_t cc_closedloop_fwd(const CcModule* c, const CcModule* m, const float* theta_c, const float* theta_m,
@@ -440,7 +439,7 @@ int32_t cc_closedloop_fwd(const CcModule* c, const CcModule* m, const float* the
   p.tape = (float*)tape;
   p.ckpt_every = tape ? ckpt_every : 1;
   p.n_ckpt = n_ckpt_of(Tr, p.ckpt_every);
-  return CC_LAUNCH(cc_rollout_fwd_kernel, p, stream);
+  return launch_fwd(p, stream);
 }
 
 #include "cc_abi_bwd.inc"

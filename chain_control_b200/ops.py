@@ -121,3 +121,69 @@ def closedloop_bwd(cspec: NodeSpec, mspec: NodeSpec, theta_c, theta_m, refs, tap
                              ckpt_every, _ptr(ybar), _ptr(tb), B, Tr, _ptr(ws), ws.numel() * 4, _stream())
     L.check(rc, "cc_closedloop_bwd")
     return tb
+
+
+def mse_value_and_cotangent(y, yhat, n_total: Optional[int] = None):
+    """default loss of the trainers (cc/utils/utils.py:53-55) fused with its cotangent:
+    returns (loss[1] = sum((yhat-y)^2)/n_total over THIS shard, ybar = 2 (yhat-y)/n_total)."""
+    L = _lib.lib()
+    y = _check(y, "y")
+    yhat = _check(yhat, "yhat", tuple(y.shape))
+    n = y.numel()
+    inv_n = 1.0 / float(n_total if n_total is not None else n)
+    ybar = torch.empty_like(yhat)
+    part = torch.empty(1 + 296, device=y.device, dtype=torch.float32)
+    rc = L.cc_mse_value_and_cotangent(_ptr(y), _ptr(yhat), _ptr(ybar), _ptr(part), n, C.c_float(inv_n), _stream())
+    L.check(rc, "cc_mse_value_and_cotangent")
+    return part[:1], ybar
+
+
+class _RolloutFn(torch.autograd.Function):
+    """y = vmap(model.unroll)(u); backward = the BPTT kernel (custom VJP, generic cotangent)."""
+
+    @staticmethod
+    def forward(ctx, theta, u, x0, spec):
+        need_grad = theta.requires_grad or u.requires_grad
+        y, _, tape = rollout_fwd(spec, theta, u, x0, want_tape=need_grad)
+        ctx.spec, ctx.tape = spec, tape
+        ctx.save_for_backward(theta, u, x0 if x0 is not None else torch.empty(0, device=u.device))
+        ctx.has_x0 = x0 is not None
+        ctx.want_ubar = u.requires_grad
+        return y
+
+    @staticmethod
+    def backward(ctx, ybar):
+        theta, u, x0 = ctx.saved_tensors
+        tb, ub = rollout_bwd(ctx.spec, theta, u, ctx.tape, ybar.contiguous(), x0 if ctx.has_x0 else None,
+                             want_ubar=ctx.want_ubar)
+        return tb, ub, None, None
+
+
+class _ClosedLoopFn(torch.autograd.Function):
+    """yhat = vmap(controller.unroll(model, merge_x_y, noise))(refs); gradient w.r.t. the controller only."""
+
+    @staticmethod
+    def forward(ctx, theta_c, theta_m, refs, noise, cspec, mspec):
+        yhat, _, tape = closedloop_fwd(cspec, mspec, theta_c, theta_m, refs, noise, want_tape=theta_c.requires_grad)
+        ctx.cspec, ctx.mspec, ctx.tape = cspec, mspec, tape
+        ctx.save_for_backward(theta_c, theta_m, refs, noise if noise is not None else torch.empty(0, device=refs.device))
+        ctx.has_noise = noise is not None
+        return yhat
+
+    @staticmethod
+    def backward(ctx, ybar):
+        theta_c, theta_m, refs, noise = ctx.saved_tensors
+        tb = closedloop_bwd(ctx.cspec, ctx.mspec, theta_c, theta_m, refs, ctx.tape, ybar.contiguous(),
+                            noise if ctx.has_noise else None)
+        return tb, None, None, None, None, None
+
+
+def batched_unroll(spec: NodeSpec, theta, u, x0=None):
+    """differentiable drop-in for eqx.filter_vmap(model.unroll)(inputs)   (cc/train/step_fn.py:124,136)."""
+    return _RolloutFn.apply(theta, u, x0, spec)
+
+
+def batched_closed_loop(cspec: NodeSpec, mspec: NodeSpec, theta_c, theta_m, refs, noise=None):
+    """differentiable drop-in for eqx.filter_vmap(controller.unroll(model, merge_x_y, noise))(refss, keys)
+    (cc/train/step_fn.py:234-236,257-259); `noise` is the already-scaled additive output noise."""
+    return _ClosedLoopFn.apply(theta_c, theta_m, refs, noise, cspec, mspec)
