@@ -29,7 +29,7 @@ class CcModule(C.Structure):
                 ("f", CcMlp), ("g", CcMlp), ("integrator", C.c_int32), ("f_time_variant", C.c_int32),
                 ("g_time_variant", C.c_int32), ("g_feedthrough_u", C.c_int32),
                 ("readout_pre_step", C.c_int32), ("u_transform", C.c_int32), ("u_scale", C.c_float),
-                ("out_scale", C.c_float), ("dt", C.c_float)]
+                ("out_scale", C.c_float), ("dt", C.c_float), ("t0", C.c_float)]
 
 
 @dataclass
@@ -77,6 +77,7 @@ class NodeSpec:
     u_transform: int = UT_IDENTITY
     u_scale: float = 1.0
     out_scale: float = 1.0
+    t0: float = 0.0  # time component of init_state
 
     def n_params(self) -> int:
         return self.f.n_params() + self.g.n_params()
@@ -94,6 +95,7 @@ class NodeSpec:
         c.g_feedthrough_u, c.readout_pre_step = int(self.g_feedthrough_u), int(self.readout_pre_step)
         c.u_transform, c.u_scale = int(self.u_transform), float(self.u_scale)
         c.out_scale, c.dt = float(self.out_scale), float(self.dt)
+        c.t0 = float(self.t0)
         return c
 
 

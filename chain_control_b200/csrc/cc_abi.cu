@@ -140,7 +140,7 @@ void describe_node(const CcModule* m, CcNodeDev* nd, bool trainable, bool tiny, 
   nd->pre = m->readout_pre_step ? 1 : 0;
   nd->ut = m->u_transform; nd->integrator = m->integrator;
   nd->n_stages = m->integrator == CC_INT_RK4 ? 4 : 1;
-  nd->u_scale = m->u_scale; nd->out_scale = m->out_scale; nd->dt = m->dt;
+  nd->u_scale = m->u_scale; nd->out_scale = m->out_scale; nd->dt = m->dt; nd->t0 = m->t0;
   nd->K0 = nd->S + nd->has_t + nd->I + 1;
   nd->row_t = nd->S; nd->row_v = nd->S + nd->has_t; nd->row_one = nd->S + nd->has_t + nd->I;
   nd->cptS = ceil_div(nd->S, 4);
@@ -400,7 +400,6 @@ int32_t cc_rollout_fwd(const CcModule* m, const float* theta, const float* u, co
   if (!theta || !y || (T > 0 && m->input_dim > 0 && !u)) return fail(CC_ERR_INVALID_ARG, "null pointer argument");
   if (B < 0 || T < 0) return fail(CC_ERR_INVALID_ARG, "negative size");
   if (tape && ckpt_every < 1) return fail(CC_ERR_INVALID_ARG, "ckpt_every must be >= 1");
-  if (m->g_feedthrough_u) return fail(CC_ERR_UNSUPPORTED, "open-loop unroll of a feed-through module (y0 undefined)");
   if (B == 0) return CC_OK;
   CcKParams p;
   PlanOpts o;

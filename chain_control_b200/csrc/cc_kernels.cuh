@@ -685,7 +685,11 @@ __global__ void __launch_bounds__(256, 1) cc_rollout_fwd_kernel(const CC_GRID_CO
     for (int s = 0; s < M.S; ++s) cc_ws(w)[M.w_X + s * CC_LD + w.lane] = act ? __ldg(p.x0 + b * M.S + s) : 0.f;
     __syncwarp();
   }
-  // y0 = out_scale * g([x0 ; 0])     neural_ode_model.py:160-175 (models have no feed-through)
+  // y0 = out_scale * g([x0 ; t0])     neural_ode_model.py:160-175 (models have no feed-through)
+  if (M.has_t) {
+    cc_ws(w)[M.w_X + M.row_t * CC_LD + w.lane] = M.t0;
+    __syncwarp();
+  }
   cc_readout<TN>(closed ? 1 : 0, M.w_X, false, w);
   for (int o = 0; o < M.O; ++o) {
     const float y0 = cc_ws(w)[M.w_OUT + o * CC_LD + w.lane];
@@ -694,7 +698,7 @@ __global__ void __launch_bounds__(256, 1) cc_rollout_fwd_kernel(const CC_GRID_CO
   }
   __syncwarp();
 
-  float tc = 0.f, tm = 0.f;
+  float tc = closed ? C.t0 : 0.f, tm = M.t0;
   const int Win = closed ? p.R : M.I;
   float vin[CC_TINY_K];  // this step's external input (u or ref), prefetched one step ahead
 #pragma unroll

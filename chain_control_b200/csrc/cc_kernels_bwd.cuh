@@ -524,7 +524,7 @@ __global__ void __launch_bounds__(256, 1) cc_rollout_bwd_kernel(const CC_GRID_CO
     float v0[CC_TINY_K];
 #pragma unroll
     for (int i = 0; i < CC_TINY_K; ++i) v0[i] = 0.f;
-    cc_set_inputs(M, w, v0, 0.f, 2);  // u_transform(0) in the v rows is harmless: models have no feed-through
+    cc_set_inputs(M, w, v0, M.t0, 2);  // u_transform(0) in the v rows is harmless: models have no feed-through
     for (int o = 0; o < M.O; ++o) cc_ws(w)[M.w_OB + o * CC_LD + w.lane] = act ? __ldg(p.ybar + b * yrow + o) : 0.f;
     __syncwarp();
     cc_readout<TN>(0, M.w_X, true, w);

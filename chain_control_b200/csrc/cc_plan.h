@@ -69,7 +69,7 @@ struct CcMlpDev {
 struct CcNodeDev {
   int S, I, O;
   int has_t, pre, ut, integrator, n_stages;
-  float u_scale, out_scale, dt;
+  float u_scale, out_scale, dt, t0;
   int K0;       // rows of X/Z: S + has_t + I + 1
   int row_t;    // row index of t (valid iff has_t)
   int row_v;    // first input row

@@ -71,6 +71,7 @@ typedef struct CcModule {
   float u_scale;             /* k of k*tanh(u/k) */
   float out_scale;           /* compact controller: sigmoid(alpha) (=0.5) with the zero secondary */
   float dt;                  /* control_timestep */
+  float t0;                  /* time component of init_state (0 in the reference; lets step() resume at t) */
 } CcModule;
 
 /* ---- introspection ------------------------------------------------------------------------- */

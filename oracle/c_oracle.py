@@ -24,7 +24,7 @@ class CcModule(C.Structure):
                 ("f", CcMlp), ("g", CcMlp), ("integrator", C.c_int32), ("f_time_variant", C.c_int32),
                 ("g_time_variant", C.c_int32), ("g_feedthrough_u", C.c_int32),
                 ("readout_pre_step", C.c_int32), ("u_transform", C.c_int32), ("u_scale", C.c_float),
-                ("out_scale", C.c_float), ("dt", C.c_float)]
+                ("out_scale", C.c_float), ("dt", C.c_float), ("t0", C.c_float)]
 
 
 def to_c_module(spec) -> CcModule:
@@ -46,6 +46,7 @@ def to_c_module(spec) -> CcModule:
     c.g_feedthrough_u, c.readout_pre_step = int(spec.g_feedthrough_u), int(spec.readout_pre_step)
     c.u_transform, c.u_scale = int(spec.u_transform), float(spec.u_scale)
     c.out_scale, c.dt = float(spec.out_scale), float(spec.dt)
+    c.t0 = float(getattr(spec, 't0', 0.0))
     return c
 
 

@@ -309,7 +309,7 @@ static size_t FN(bwd_scratch_rows)(const CcModule* m) {
 
 /* y0 = out_scale * g([x0 ; 0]) */
 static void FN(node_y0)(const CcModule* m, const FN(Params) * p, const REAL* x, REAL* out, REAL* gcache) {
-  FN(fill_gin)(m, gcache, x, (REAL)0, NULL);
+  FN(fill_gin)(m, gcache, x, (REAL)m->t0, NULL);
   const REAL* o = FN(mlp_fwd)(&m->g, p->g, gcache);
   for (int i = 0; i < m->output_dim * NB; ++i) out[i] = (REAL)m->out_scale * o[i];
 }
@@ -364,7 +364,7 @@ int FN(cco_rollout)(const CcModule* m, const REAL* theta, const REAL* u, const R
         FN(node_y0)(m, &p, x, out, g0c);
         for (int o = 0; o < O; ++o)
           for (int j = 0; j < nact; ++j) y[((b0 + j) * (T + 1) + 0) * O + o] = out[(size_t)o * NB + j];
-        REAL t = 0;
+        REAL t = (REAL)m->t0;
         for (int k = 0; k < T; ++k) {
           for (int i = 0; i < I; ++i)
             for (int j = 0; j < NB; ++j) v[(size_t)i * NB + j] = j < nact ? u[((b0 + j) * T + k) * I + i] : (REAL)0;
@@ -483,7 +483,7 @@ int FN(cco_closedloop)(const CcModule* c, const CcModule* m, const REAL* theta_c
         for (int i = 0; i < Sc * NB; ++i) xc[i] = 0;
         for (int i = 0; i < Sm * NB; ++i) xm[i] = 0;
         FN(node_y0)(m, &pm, xm, yv, g0c);
-        REAL tc = 0, tm = 0;
+        REAL tc = (REAL)c->t0, tm = (REAL)m->t0;
         for (int k = 0; k < Tr; ++k) {
           for (int r = 0; r < R; ++r)
             for (int j = 0; j < NB; ++j) v[(size_t)r * NB + j] = j < nact ? refs[((b0 + j) * Tr + k) * R + r] : (REAL)0;

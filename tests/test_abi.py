@@ -38,7 +38,7 @@ def test_struct_layout_matches_header():
 
     assert CC_MAX_LAYERS == int(re.search(r"#define CC_MAX_LAYERS (\d+)", open(HEADER).read()).group(1))
     assert ctypes.sizeof(CcMlp) == 4 * (1 + CC_MAX_LAYERS + 1 + 3)
-    assert ctypes.sizeof(CcModule) == 4 * 3 + 2 * ctypes.sizeof(CcMlp) + 4 * 6 + 4 * 3
+    assert ctypes.sizeof(CcModule) == 4 * 3 + 2 * ctypes.sizeof(CcMlp) + 4 * 6 + 4 * 4
 
 
 def test_emulated_library_has_same_abi():

@@ -1,0 +1,116 @@
+"""GPU tests of the host-side mirrors, modelled on the reference's own tests for this path:
+cc/train/test_trainer.py:25-147 (one step of each trainer, log keys, trackers, multi-model dict) and
+cc/core/test_module.py:84-103 (the scan contract: unroll == successive steps, include_y0)."""
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+from cchelpers import TOL_GRAD, TOL_STATE, l2rel, normwise
+from oracle import c_oracle as CO
+from oracle import np_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _data(B, T, seed):
+    rng = np.random.default_rng(seed)
+    t = np.arange(T)[None, :, None] * 0.01
+    u = (np.cos(2 * np.pi * rng.uniform(1, 6, size=(B, 1, 1)) * t / 10) * 0.5).astype(np.float32)
+    return u
+
+
+def test_trainer_steps_and_log_keys():
+    from chain_control_b200.examples.neural_ode_controller_compact_example import make_neural_ode_controller
+    from chain_control_b200.examples.neural_ode_model import make_neural_ode_model
+    from chain_control_b200.train import (DictLogger, EvaluationMetrices, ModelControllerTrainer, Regularisation,
+                                          SupervisedDataset, Tracker, TrainingOptionsController, TrainingOptionsModel,
+                                          UnsupervisedDataset, make_dataloader, optim)
+    from chain_control_b200.utils import l2_norm, rmse
+
+    T = 200
+    act_spec, obs_spec = 1, OrderedDict(xpos_of_segment_end=1)
+    model = make_neural_ode_model(act_spec, obs_spec, 0.01, state_dim=1, f_depth=0, u_transform=np.arctan, f_time_invariant=False)
+    u_tr, u_va = _data(2, T, 0), _data(2, T, 1)
+    teacher = make_neural_ode_model(act_spec, obs_spec, 0.01, state_dim=3, f_depth=0, key=7, u_transform=np.arctan)
+    with torch.no_grad():
+        y_tr, y_va = teacher.unroll_batched(u_tr), teacher.unroll_batched(u_va)
+    assert tuple(y_tr["xpos_of_segment_end"].shape) == (2, T + 1, 1)
+
+    opts = TrainingOptionsModel(
+        make_dataloader(SupervisedDataset(u_tr, y_tr), key=2, n_minibatches=1),
+        optim.chain(optim.clip_by_global_norm(1.0), optim.adam(3e-3)),
+        regularisers=(Regularisation(0.5, lambda v: {"l2_norm": l2_norm(v)}),),
+        metrices=(EvaluationMetrices(data=(u_va, y_va), metrices=(lambda y, yhat: {"val_rmse": rmse(y, yhat)},)),))
+    trainer = ModelControllerTrainer(model, model_train_options=opts, loggers=[DictLogger()], trackers=[Tracker("val_rmse")])
+    trainer.run(2)
+    logs = trainer.get_logs()[0]
+    for k in ("train_loss", "train_mse", "l2_norm", "val_rmse"):
+        assert k in logs and logs[k].shape[0] == 2 and np.all(np.isfinite(logs[k]))
+    fitted = trainer.trackers[0].best_model_or_controller()
+    assert fitted is not None
+
+    refs = OrderedDict(xpos_of_segment_end=(np.sign(np.random.default_rng(0).normal(size=(4, 1, 1))) * np.ones((4, T + 1, 1))).astype(np.float32))
+    controller = make_neural_ode_controller(2, act_spec, 0.01, 1, f_depth=0)
+    copts = TrainingOptionsController(make_dataloader(UnsupervisedDataset(refs), key=1, n_minibatches=1),
+                                      optim.chain(optim.clip_by_global_norm(1.0), optim.adam(1e-3)))
+    ct = ModelControllerTrainer(fitted, controller, controller_train_options=copts, trackers=[Tracker("model0", "train_mse")])
+    logs = ct.step()
+    for k in ("train_loss", "loss", "loss_without_regu", "model0_train_mse"):
+        assert k in logs
+    model2 = make_neural_ode_model(act_spec, obs_spec, 0.01, state_dim=2, f_depth=0, u_transform=np.arctan)
+    ct = ModelControllerTrainer(dict(m1=fitted, m2=model2), controller, controller_train_options=copts,
+                                trackers=[Tracker("m2", "train_mse"), Tracker("loss_without_regu")])
+    logs = ct.step()
+    assert "m1_train_mse" in logs and "m2_train_mse" in logs
+    assert abs(logs["loss_without_regu"] - 0.5 * (logs["m1_train_mse"] + logs["m2_train_mse"])) < 1e-6
+
+
+def test_model_train_step_gradient_matches_oracle():
+    """value_and_grad(mse(vmap(unroll))) through the mirror == the oracle's fp64 gradient."""
+    from chain_control_b200.examples.neural_ode_model_compact_example import make_neural_ode_model
+    from chain_control_b200.utils import mse
+
+    model = make_neural_ode_model(1, 1, 0.01, state_dim=50, f_depth=0, u_transform=np.arctan, key=3)
+    u = _data(8, 300, 4)
+    targets = np.random.default_rng(2).normal(size=(8, 301, 1)).astype(np.float32)
+    theta = model.flat_params().detach().requires_grad_(True)
+    loss = mse(torch.tensor(targets, device="cuda"), model.with_params(theta).unroll_batched(u))
+    (g,) = torch.autograd.grad(loss, theta)
+    ref = CO.rollout(model.spec, theta.detach().cpu().numpy(), u, targets=targets, dtype=np.float64)
+    assert abs(float(loss.detach()) - ref["loss"]) < 1e-5 * max(1.0, ref["loss"])
+    assert l2rel(g.cpu().numpy(), ref["theta_bar"]) < TOL_GRAD
+
+
+def test_unroll_equals_successive_steps():
+    """scan contract of cc/core/test_module.py:84-103 on a neural ODE: unroll == step, step, ...; include_y0."""
+    from chain_control_b200.examples.neural_ode_model import make_neural_ode_model
+
+    for kw in (dict(f_depth=1, f_width_size=7), dict(f_depth=0, f_time_invariant=False, g_time_invariant=False)):
+        model = make_neural_ode_model(1, 2, 0.01, state_dim=4, key=5, **kw)
+        u = _data(1, 6, 9)[0]
+        y = model.unroll(u)
+        assert tuple(y.shape) == (7, 2)
+        np.testing.assert_allclose(model.unroll(u, include_y0=False).cpu().numpy(), y[1:].cpu().numpy(), rtol=0, atol=0)
+        np.testing.assert_allclose(y[0].cpu().numpy(), model.y0().cpu().numpy(), rtol=1e-6, atol=1e-7)
+        m = model.reset()
+        for k in range(6):
+            m, yk = m.step(u[k])
+            np.testing.assert_allclose(yk.cpu().numpy(), y[k + 1].cpu().numpy(), rtol=2e-6, atol=1e-7)
+
+
+def test_closed_loop_mirror_matches_oracle():
+    from chain_control_b200.core import filter_vmap
+    from chain_control_b200.examples.neural_ode_controller import make_neural_ode_controller
+    from chain_control_b200.examples.neural_ode_model_compact_example import make_neural_ode_model
+    from chain_control_b200.train import merge_x_y
+
+    model = make_neural_ode_model(1, 1, 0.01, state_dim=10, f_depth=0, u_transform=np.arctan, key=3)
+    controller = make_neural_ode_controller(2, 1, 0.01, state_dim=25, f_width_size=10, f_depth=2, key=4)  # CLI defaults
+    refs = (np.random.default_rng(1).uniform(-2, 2, size=(16, 1, 1)) * np.ones((16, 151, 1))).astype(np.float32)
+    yhat = filter_vmap(controller.unroll(model, merge_x_y))(refs, 0)
+    ref = CO.closedloop(controller.spec, model.spec, controller.theta.cpu().numpy(), model.theta.cpu().numpy(), refs, dtype=np.float64)
+    assert normwise(yhat.detach().cpu().numpy(), ref["yhat"]) < TOL_STATE
+    single = controller.unroll(model, merge_x_y)(refs[3], 0)
+    np.testing.assert_allclose(single.detach().cpu().numpy(), yhat[3].detach().cpu().numpy(), rtol=1e-6, atol=1e-7)
