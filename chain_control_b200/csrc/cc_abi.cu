@@ -249,8 +249,8 @@ void layout(CcKParams* p, bool bwd) {
       for (int w = 0; w < 2; ++w)
         for (int l = 0; l < devs[w]->L; ++l)
           if (devs[w]->layer[l].N > maxn) maxn = devs[w]->layer[l].N;
-      nd.w_LAM = ws.take(nd.S * CC_LD);
       nd.w_DA = ws.take(maxn * CC_LD);
+      nd.w_LAM = nd.w_DA;  // the state adjoint lives in registers inside a step and in DA's rows between steps
       nd.w_VB = ws.take((nd.I > 0 ? nd.I : 1) * CC_LD);
       nd.w_OB = ws.take(nd.O * CC_LD);
       if (nd.trainable) grec += nd.g_total;
@@ -294,9 +294,12 @@ int make_plan(const CcModule* const* mods, int n_nodes, long long B, int T, cons
   }
   if (n_nodes == 2) {
     p->R = mods[0]->input_dim - mods[1]->output_dim;
+    // closed-loop carry on the tape: x_c, (x_m only if the frozen model's reverse pass needs it), y_prev
+    const int sm_rows = (mlp_linear(mods[1]->f) && mlp_linear(mods[1]->g)) ? 0 : p->nd[1].S;
     p->nd[0].tape_row = 0;
-    p->nd[1].tape_row = p->nd[0].S;
-    p->tape_rows = p->nd[0].S + p->nd[1].S + p->nd[1].O;
+    p->nd[1].tape_row = sm_rows ? p->nd[0].S : -1;
+    p->tape_yrow = p->nd[0].S + sm_rows;
+    p->tape_rows = p->nd[0].S + sm_rows + p->nd[1].O;
   } else {
     p->nd[0].tape_row = 0;
     p->tape_rows = p->nd[0].S;
@@ -390,7 +393,8 @@ size_t cc_rollout_tape_bytes(const CcModule* m, int64_t B, int32_t T, int32_t ck
 size_t cc_closedloop_tape_bytes(const CcModule* c, const CcModule* m, int64_t B, int32_t Tr, int32_t ckpt_every) {
   if (!c || !m || B <= 0 || Tr < 0 || ckpt_every < 1) return 0;
   const long long Bpad = (B + 31) / 32 * 32;
-  return ((size_t)n_ckpt_of(Tr, ckpt_every) * (c->state_dim + m->state_dim + m->output_dim) * Bpad + 2 * (size_t)Tr) * sizeof(float);
+  const int sm_rows = (mlp_linear(m->f) && mlp_linear(m->g)) ? 0 : m->state_dim;
+  return ((size_t)n_ckpt_of(Tr, ckpt_every) * (c->state_dim + sm_rows + m->output_dim) * Bpad + 2 * (size_t)Tr) * sizeof(float);
 }
 
 int32_t cc_rollout_fwd(const CcModule* m, const float* theta, const float* u, const float* x0, float* y,

@@ -375,7 +375,7 @@ CC_DEV_NOINLINE void cc_node_step(int node, const CcWarp w, float t, bool keep, 
   if (nd.pre && do_readout) cc_readout<TN>(node, nd.w_X, keep, w);
   float xr[CC_TM][TN], k[CC_TM][TN];
   cc_load_tile<TN>(X, nd.S, nd.cptS, w, xr);
-  if (write_tape) cc_tape_store<TN>(p, nd, ck, w, xr);
+  if (write_tape && nd.tape_row >= 0) cc_tape_store<TN>(p, nd, ck, w, xr);
   if (nd.integrator == CC_INT_RK4) {
     float ks[CC_TM][TN];
 #pragma unroll 1
@@ -729,7 +729,7 @@ __global__ void __launch_bounds__(256, 1) cc_rollout_fwd_kernel(const CC_GRID_CO
 #pragma unroll
         for (int i = 0; i < CC_TINY_K; ++i)
           if (i == p.R + o) vc[i] = yp;
-        if (wt) p.tape[((long long)ck * p.tape_rows + C.S + M.S + o) * p.Bpad + b] = yp;
+        if (wt) p.tape[((long long)ck * p.tape_rows + p.tape_yrow + o) * p.Bpad + b] = yp;
       }
       float a[CC_TINY_O];
       if (CM == CC_CTRL_TINY) {

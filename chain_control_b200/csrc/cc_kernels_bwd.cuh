@@ -14,12 +14,34 @@
 #pragma once
 #include "cc_kernels.cuh"
 
-#define CC_WN 2 /* weight-gradient thread tile: 2 outputs x 8 inputs */
+#define CC_WN 4 /* weight-gradient thread tile: 4 outputs x 8 inputs */
 #define CC_WK 8
 
-// G[n][r] += sum_{traj<32} D[n][traj] * A[r][traj].  Tiles are dealt to the 32 lanes; each lane
-// walks the 8 trajectory quads in a lane-rotated order so that the LDS.128 of a quarter-warp hit 8
-// different bank quads whatever rows they touch.
+struct CcWFrag {
+  float4 d[CC_WN], a[CC_WK];
+};
+CC_DEV void cc_wfrag_load(CcWFrag& f, const float* const (&dptr)[CC_WN], const float* const (&aptr)[CC_WK], int q) {
+#pragma unroll
+  for (int i = 0; i < CC_WN; ++i) f.d[i] = *reinterpret_cast<const float4*>(dptr[i] + q);
+#pragma unroll
+  for (int j = 0; j < CC_WK; ++j) f.a[j] = *reinterpret_cast<const float4*>(aptr[j] + q);
+}
+CC_DEV void cc_wfrag_fma(const CcWFrag& f, float (&acc)[CC_WN][CC_WK]) {
+#pragma unroll
+  for (int i = 0; i < CC_WN; ++i)
+#pragma unroll
+    for (int j = 0; j < CC_WK; ++j) {
+      acc[i][j] = fmaf(f.d[i].x, f.a[j].x, acc[i][j]);
+      acc[i][j] = fmaf(f.d[i].y, f.a[j].y, acc[i][j]);
+      acc[i][j] = fmaf(f.d[i].z, f.a[j].z, acc[i][j]);
+      acc[i][j] = fmaf(f.d[i].w, f.a[j].w, acc[i][j]);
+    }
+}
+
+// G[n][r] += sum_{traj<32} D[n][traj] * A[r][traj].  4x8 output tiles are dealt to the 32 lanes; each
+// lane walks the 8 trajectory quads in a lane-rotated order so that the LDS.128 of a quarter-warp hit 8
+// different bank quads whatever rows they touch; the operands of quad q+1 are fetched while the FMAs of
+// quad q issue.
 CC_DEV void cc_wgrad(const CcLayerDev& L, const float* D, const float* A, const CcWarp& w) {
   const int NT = (L.N + CC_WN - 1) / CC_WN;
   const int KT = (L.K + CC_WK - 1) / CC_WK;
@@ -47,24 +69,15 @@ CC_DEV void cc_wgrad(const CcLayerDev& L, const float* D, const float* A, const 
       rok[j] = r < L.K;
       aptr[j] = A + (rok[j] ? r : 0) * CC_LD;
     }
-#pragma unroll 2
-    for (int qq = 0; qq < 8; ++qq) {
-      const int q = 4 * ((qq + w.lane) & 7);
-      float4 d[CC_WN], a[CC_WK];
+    CcWFrag cur, nxt;
+    cc_wfrag_load(cur, dptr, aptr, 4 * (w.lane & 7));
 #pragma unroll
-      for (int i = 0; i < CC_WN; ++i) d[i] = *reinterpret_cast<const float4*>(dptr[i] + q);
-#pragma unroll
-      for (int j = 0; j < CC_WK; ++j) a[j] = *reinterpret_cast<const float4*>(aptr[j] + q);
-#pragma unroll
-      for (int i = 0; i < CC_WN; ++i)
-#pragma unroll
-        for (int j = 0; j < CC_WK; ++j) {
-          acc[i][j] = fmaf(d[i].x, a[j].x, acc[i][j]);
-          acc[i][j] = fmaf(d[i].y, a[j].y, acc[i][j]);
-          acc[i][j] = fmaf(d[i].z, a[j].z, acc[i][j]);
-          acc[i][j] = fmaf(d[i].w, a[j].w, acc[i][j]);
-        }
+    for (int qq = 1; qq < 8; ++qq) {
+      cc_wfrag_load(nxt, dptr, aptr, 4 * ((qq + w.lane) & 7));
+      cc_wfrag_fma(cur, acc);
+      cur = nxt;
     }
+    cc_wfrag_fma(cur, acc);
 #pragma unroll
     for (int i = 0; i < CC_WN; ++i)
 #pragma unroll
@@ -171,8 +184,9 @@ CC_DEV_NOINLINE void cc_node_bwd(int node, const CcWarp w, int vraw_off) {
   for (int i = 0; i < nd.I; ++i) cc_ws(w)[nd.w_VB + i * CC_LD + w.lane] = 0.f;
   __syncwarp();
   float xrb[CC_TM][TN], lam[CC_TM][TN];
+  cc_load_tile<TN>(LAM, nd.S, nd.cptS, w, lam);  // LAM shares its buffer with DA: read it before DA is written
+  __syncwarp();
   cc_readout_bwd<TN>(nd, nd.pre ? X : (nd.w_XN >= 0 ? cc_ws(w) + nd.w_XN : X), w, xrb);
-  cc_load_tile<TN>(LAM, nd.S, nd.cptS, w, lam);
   if (!nd.pre) {
 #pragma unroll
     for (int i = 0; i < CC_TM; ++i)
@@ -419,7 +433,7 @@ __global__ void __launch_bounds__(256, 1) cc_rollout_bwd_kernel(const CC_GRID_CO
 #pragma unroll
     for (int o = 0; o < CC_TINY_O; ++o) {
       n_yb[o] = (o < M.O && act) ? __ldg(p.ybar + b * yrow + yoff + o) : 0.f;
-      n_yp[o] = (closed && o < M.O && act) ? p.tape[((long long)k * p.tape_rows + C.S + M.S + o) * p.Bpad + b] : 0.f;
+      n_yp[o] = (closed && o < M.O && act) ? p.tape[((long long)k * p.tape_rows + p.tape_yrow + o) * p.Bpad + b] : 0.f;
     }
 #pragma unroll
     for (int s = 0; s < CC_TINY_S; ++s)

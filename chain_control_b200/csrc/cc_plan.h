@@ -79,7 +79,7 @@ struct CcNodeDev {
   CcMlpDev f, g;
   int w_X, w_Z;  // per-warp stage buffers [K0][32]
   int w_OUT;     // per-warp [O][32]
-  int tape_row;  // first row of this node's state inside a tape record
+  int tape_row;  // first row of this node's state inside a tape record (-1: not on the tape)
   int P;         // parameter count
   // backward only
   int trainable;  // accumulate parameter gradients
@@ -119,6 +119,7 @@ struct CcKParams {
   float* x_final;      // open loop, optional
   float* tape;         // [n_ckpt][tape_rows][Bpad] (feature-major); then float ttab[2][T] (step times)
   int ckpt_every, n_ckpt, tape_rows;
+  int tape_yrow;       // closed loop: first row of the fed-back output inside a tape record
   long long Bpad;      // B rounded up to a multiple of 32
   // backward
   const float* ybar;   // [B,T+1,O] or [B,Tr,O]
