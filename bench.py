@@ -189,7 +189,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from chain_control_b200 import _lib, ops
+    from chain_control_b200 import _lib, ops, parallel
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -236,9 +236,8 @@ def main():
             if timed: e[2].record()
             g, _ = ops.rollout_bwd(model, theta, xdev, tape, ybar)
         if timed: e[3].record()
-        gl = torch.cat([g, loss])
-        if world > 1:
-            dist.all_reduce(gl)  # NCCL over NVLink: P+1 floats
+        gsum, lsum = parallel.allreduce_grad_and_loss(g, loss)  # N > 1: one NCCL allreduce of P+1 floats over NVLink
+        gl = torch.cat([gsum, lsum.reshape(1)])
         step_no[0] += 1
         t = step_no[0]
         gg = gl[:P]

@@ -1,0 +1,40 @@
+"""Data-parallel sharding of the hot path across the GPUs of one box.
+
+Trajectories never interact in the forward pass (eqx.filter_vmap, cc/train/step_fn.py:136,257); the only
+coupling is the sum over the batch inside the mean loss / gradient (cc/utils/utils.py:53-55).  Each rank takes
+a contiguous slice of the batch, scales its cotangent by the GLOBAL element count (so no communication before
+the backward pass), and one allreduce(sum) of the P+1 vector [gradient ; loss partial] per step makes every
+rank apply the identical optimiser update (no parameter broadcast).  One process per GPU, NCCL over
+NVLink/NVSwitch (gloo in the CPU tests)."""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_bounds(B: int, rank: int, world_size: int):
+    """contiguous split of the batch axis; the first (B % world) ranks get one extra trajectory"""
+    base, rem = divmod(B, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_batch(tree, rank: int, world_size: int):
+    from .utils import tree_map, tree_shape
+
+    lo, hi = shard_bounds(tree_shape(tree), rank, world_size)
+    return tree_map(lambda a: a[lo:hi], tree)
+
+
+def allreduce_grad_and_loss(grad: torch.Tensor, loss_partial: torch.Tensor):
+    """sum over ranks of [theta_bar ; loss partial] in ONE collective of P+1 floats"""
+    buf = torch.cat([grad.reshape(-1), loss_partial.reshape(-1)])
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+    return buf[:-1].reshape(grad.shape), buf[-1]
