@@ -310,6 +310,13 @@ def main():
     torch.cuda.synchronize()
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     peak_tflops = sms * 4 * 512 * iters * 16 * 8 * 2 / (p0.elapsed_time(p1) * 1e-3) / 1e12
+    zin = torch.zeros(1024, device=dev)
+    for _ in range(2):
+        p0.record()
+        L.check(L.cc_fp32_tile_probe(sink.data_ptr(), zin.data_ptr(), iters, torch.cuda.current_stream().cuda_stream), "tile probe")
+        p1.record()
+        torch.cuda.synchronize()
+    regtile_tflops = sms * 4 * 512 * iters * 4 * 32 * 2 / (p0.elapsed_time(p1) * 1e-3) / 1e12
 
     if rank == 0:
         fwd_f, tot_f = alg_flops(closed)
@@ -323,7 +330,7 @@ def main():
             peaks = {}
         hbm = peaks.get("hbm_gbs", 6650.0)
         # algorithmic HBM bytes per trajectory-step of the whole step: inputs/outputs/cotangent + tape write+read
-        tape_rows = (5 + 50 + 1) if closed else 50
+        tape_rows = (5 + 1) if closed else 50  # closed loop: x_c and y_prev (the frozen linear model needs no state)
         bytes_ts = 4 * (1 + 1 + 1 + 1 + 1) + 2 * 4 * tape_rows
         out = {
             "metric": ("closed-loop " if closed else "") + "neural-ODE traj-steps/s (fwd+BPTT)",
@@ -344,6 +351,8 @@ def main():
             "roofline": {"bound": "fp32", "kernel": "cc_rollout_bwd_kernel", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
                          "frac": achieved / peak_tflops, "traffic": None,
                          "peak_source": "FFMA-chain probe measured live in this run (MEASURED_PEAKS.json carries no FP32 figure; nominal 74.4)",
+                         "peak_register_tile": regtile_tflops,
+                         "peak_register_tile_note": "same probe with three register operands per FFMA (acc[i][j] += x[i]*y[j]): the practical ceiling of any register-tiled CUDA-core kernel on this part",
                          "alg_flops_per_traj_step": tot_f - fwd_f, "launch_ms": bwd_ms,
                          "fwd_kernel": {"achieved": units * fwd_f / (fwd_ms * 1e-3) / 1e12, "launch_ms": fwd_ms, "alg_flops_per_traj_step": fwd_f},
                          "step": {"achieved": units * tot_f / ((fwd_ms + bwd_ms) * 1e-3) / 1e12, "alg_flops_per_traj_step": tot_f},

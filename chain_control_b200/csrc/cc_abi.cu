@@ -465,6 +465,19 @@ int32_t cc_mse_value_and_cotangent(const float* y, const float* yhat, float* yba
   return CC_OK;
 }
 
+int32_t cc_fp32_tile_probe(float* sink, const float* in, int32_t iters, void* stream) {
+  if (!sink || !in || iters < 1) return fail(CC_ERR_INVALID_ARG, "bad probe arguments");
+  g_launches.fetch_add(1);
+#ifdef CC_EMULATE
+  (void)stream;
+  return fail(CC_ERR_UNSUPPORTED, "probe is GPU-only");
+#else
+  cc_fp32_tile_probe_kernel<<<num_sms() * 4, 512, 0, (cudaStream_t)stream>>>(sink, in, iters);  // `in`: >= 524 zero floats
+  CC_CUDA_OK(cudaGetLastError());
+  return CC_OK;
+#endif
+}
+
 int32_t cc_fp32_peak_probe(float* sink, int32_t iters, void* stream) {
   if (!sink || iters < 1) return fail(CC_ERR_INVALID_ARG, "bad probe arguments");
   g_launches.fetch_add(1);

@@ -74,3 +74,28 @@ __global__ void cc_fp32_probe_kernel(float* sink, int iters) {
   const float s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
   if (s == 123.456f) sink[0] = s;
 }
+
+// acc[i][j] += x[i] * y[j]: the SGEMM register-tile pattern (3 register operands, operand reuse possible)
+__global__ void cc_fp32_tile_probe_kernel(float* sink, const float* in, int iters) {
+  float acc[4][8];
+  float x[4], y[8];
+  for (int i = 0; i < 4; ++i) x[i] = in[threadIdx.x + i];
+  for (int j = 0; j < 8; ++j) y[j] = in[threadIdx.x + 4 + j];
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(x[i], y[j], acc[i][j]);
+      x[u & 3] += 1e-7f;
+      y[u & 7] -= 1e-7f;
+    }
+  }
+  float s = 0.f;
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 8; ++j) s += acc[i][j];
+  if (s == 123.456f) sink[0] = s;
+}

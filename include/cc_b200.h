@@ -129,6 +129,9 @@ int32_t cc_mse_value_and_cotangent(const float* y, const float* yhat, float* yba
 
 /* ---- measurement helper: register-resident FFMA chain, returns nothing; time it with events ---- */
 int32_t cc_fp32_peak_probe(float* sink, int32_t iters, void* stream);
+/* same, but the SGEMM register-tile pattern acc[i][j] += x[i]*y[j] (three register operands per FFMA):
+ * the practical CUDA-core ceiling of a register-tiled kernel; 4*32*4 FMAs per thread per iteration */
+int32_t cc_fp32_tile_probe(float* sink, const float* in, int32_t iters, void* stream);
 /* number of kernel launches issued through this library since load (bench.py's gpu_launches) */
 int64_t cc_launch_count(void);
 
