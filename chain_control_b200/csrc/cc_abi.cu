@@ -96,6 +96,30 @@ int64_t param_count(const CcModule* m) {
 
 bool mlp_linear(const CcMlp& m) { return m.n_layers == 1 && m.act_final == CC_ACT_IDENTITY; }
 
+bool node_is_tiny(const CcModule* m);
+
+// tcgen05 path (cc_tc_kernels.cuh): the model's f and g are single Linear layers, time-invariant, S <= 56;
+// closed loop additionally needs the tiny controller, the reverse pass a LINEAR (identity final activation)
+// frozen model.  Everything else runs on the FFMA kernels.  CC_B200_TC=0 disables the path.
+bool tc_model_ok(const CcModule* m) {
+  return m->f.n_layers == 1 && m->g.n_layers == 1 && !m->f_time_variant && !m->g_time_variant && !m->g_feedthrough_u &&
+         m->integrator != CC_INT_NONE && m->state_dim <= 56 && m->input_dim >= 1 && m->input_dim <= CC_TINY_O && m->output_dim <= CC_TINY_O;
+}
+bool tc_eligible(const CcModule* const* mods, int n_nodes, bool bwd) {
+#ifdef CC_EMULATE
+  return false;  // tcgen05 has no CPU emulation
+#endif
+  const char* env = getenv("CC_B200_TC");
+  if (env && atoi(env) == 0) return false;
+  const CcModule* model = mods[n_nodes - 1];
+  if (!tc_model_ok(model)) return false;
+  if (n_nodes == 1) return !bwd;  // the trainable open-loop reverse pass (weight gradients) stays on the FFMA kernels
+  if (!node_is_tiny(mods[0])) return false;
+  if (mods[0]->input_dim > CC_TINY_O) return false;
+  if (bwd && !(mlp_linear(model->f) && mlp_linear(model->g))) return false;
+  return true;
+}
+
 struct Alloc {
   int off = 0;
   int take(int nfloats) {
@@ -196,6 +220,11 @@ void layout(CcKParams* p, bool bwd) {
   for (int n = 0; n < p->n_nodes; ++n) {
     CcNodeDev& nd = p->nd[n];
     CcMlpDev* devs[2] = {&nd.f, &nd.g};
+    if (p->tc && n == p->n_nodes - 1) {  // the model node lives in TMEM / registers (cc_tc_kernels.cuh)
+      nd.w_X = nd.w_Z = nd.w_OUT = nd.w_XN = nd.w_LAM = nd.w_DA = nd.w_DB = nd.w_VB = nd.w_OB = nd.w_GP = -1;
+      nd.g_base = grec;
+      continue;
+    }
     const bool need_fwd = !bwd || nd.recompute || nd.tiny;  // forward evaluation of this node happens in this kernel
     for (int w = 0; w < 2; ++w)
       for (int l = 0; l < devs[w]->L; ++l) {
@@ -257,9 +286,9 @@ void layout(CcKParams* p, bool bwd) {
     }
   }
   const CcNodeDev& M = p->nd[p->n_nodes - 1];
-  p->w_yprev = (!bwd && p->n_nodes == 2) ? ws.take(M.O * CC_LD) : -1;
-  p->w_yfb = (bwd && p->n_nodes == 2) ? ws.take(M.O * CC_LD) : -1;
-  p->w_araw = bwd ? ws.take((M.I > 0 ? M.I : 1) * CC_LD) : -1;
+  p->w_yprev = (!p->tc && !bwd && p->n_nodes == 2) ? ws.take(M.O * CC_LD) : -1;
+  p->w_yfb = (!p->tc && bwd && p->n_nodes == 2) ? ws.take(M.O * CC_LD) : -1;
+  p->w_araw = (!p->tc && bwd) ? ws.take((M.I > 0 ? M.I : 1) * CC_LD) : -1;
   p->g_rec = grec;
   p->cta_floats = cs.off;
   p->warp_floats = ws.off;
@@ -273,6 +302,7 @@ int make_plan(const CcModule* const* mods, int n_nodes, long long B, int T, cons
   p->Bpad = (B + 31) / 32 * 32;
   p->n_wtiles = (B + 31) / 32;
   const CcModule* model = mods[n_nodes - 1];
+  p->tc = tc_eligible(mods, n_nodes, o.bwd) ? 1 : 0;
   p->TN = tile_width_for(node_max_cpt(model));
   if (!p->TN) return fail(CC_ERR_UNSUPPORTED, "model layers wider than 64 are not supported yet (register tile 4 x 16 per thread)");
   p->ctrl_mode = CC_CTRL_NONE;
@@ -305,6 +335,30 @@ int make_plan(const CcModule* const* mods, int n_nodes, long long B, int T, cons
     p->tape_rows = p->nd[0].S;
   }
   layout(p, o.bwd);
+  if (p->tc) {
+    // one CTA = 128 trajectories (4 worker warps, thread = trajectory) + the MMA-issuing warp
+    p->tc_nch = model->state_dim <= 32 ? 4 : 7;
+    const int SR = 8 * p->tc_nch;
+    if (!o.bwd) {
+      p->tc_KP = (model->state_dim + 5 <= SR) ? SR : SR + 8;
+      p->tc_NP = (SR + 15) / 16 * 16;
+    } else {
+      p->tc_KP = SR;
+      p->tc_NP = (SR + CC_TINY_O + 15) / 16 * 16;
+    }
+    p->wpc = 4;
+    const int head = (int)((sizeof(CcKParams) + 15) / 16 * 4);
+    p->tc_off = (head + p->cta_floats + 4 * p->warp_floats + 15) / 16 * 16;
+    p->tc_sms = num_sms();
+    const char* st = getenv("CC_B200_TC_STAGGER");
+    p->tc_stagger = st ? atoi(st) : 900;
+    const long long bytes = ((long long)p->tc_off + 2LL * p->tc_KP * p->tc_NP + CC_TINY_O * (SR + 4) + 8) * 4;
+    if (bytes > 110 * 1024) return fail(CC_ERR_UNSUPPORTED, "tcgen05 path: %lld B of shared memory per CTA do not allow two CTAs per SM", bytes);
+    if (getenv("CC_B200_VERBOSE"))
+      fprintf(stderr, "[ccb200] tcgen05 plan: nodes=%d bwd=%d B=%lld T=%d nch=%d KP=%d NP=%d smem=%lld B ctas=%lld\n", n_nodes, (int)o.bwd, B, T,
+              p->tc_nch, p->tc_KP, p->tc_NP, bytes, (B + 127) / 128);
+    return CC_OK;
+  }
   // warps per CTA: as many as shared memory / registers allow (<= 10 at ~200 registers per thread),
   // then the count that minimises waves x warps (whole-SM throughput bound), larger on ties
   const long long cta_bytes = (long long)p->cta_floats * 4;
@@ -350,14 +404,24 @@ int cc_launch_fwd_tn13(const CcKParams& p, void* stream, char* err, int errlen);
 int cc_launch_bwd_tn13(const CcKParams& p, void* stream, char* err, int errlen);
 int cc_launch_fwd_tn16(const CcKParams& p, void* stream, char* err, int errlen);
 int cc_launch_bwd_tn16(const CcKParams& p, void* stream, char* err, int errlen);
+#ifndef CC_EMULATE
+int cc_launch_fwd_tc(const CcKParams& p, void* stream, char* err, int errlen);
+int cc_launch_bwd_tc(const CcKParams& p, void* stream, char* err, int errlen);
+#endif
 namespace {
 int launch_fwd(const CcKParams& p, void* stream) {
   g_launches.fetch_add(1);
+#ifndef CC_EMULATE
+  if (p.tc) return cc_launch_fwd_tc(p, stream, g_err, sizeof(g_err));
+#endif
   return p.TN == 8 ? cc_launch_fwd_tn8(p, stream, g_err, sizeof(g_err))
          : p.TN == 13 ? cc_launch_fwd_tn13(p, stream, g_err, sizeof(g_err)) : cc_launch_fwd_tn16(p, stream, g_err, sizeof(g_err));
 }
 int launch_bwd(const CcKParams& p, void* stream) {
   g_launches.fetch_add(1);
+#ifndef CC_EMULATE
+  if (p.tc) return cc_launch_bwd_tc(p, stream, g_err, sizeof(g_err));
+#endif
   return p.TN == 8 ? cc_launch_bwd_tn8(p, stream, g_err, sizeof(g_err))
          : p.TN == 13 ? cc_launch_bwd_tn13(p, stream, g_err, sizeof(g_err)) : cc_launch_bwd_tn16(p, stream, g_err, sizeof(g_err));
 }

@@ -127,4 +127,13 @@ struct CcKParams {
   float* gpart;        // per-warp-tile gradient records [n_wtiles][g_rec]
   int g_rec;
   int w_yprev, w_yfb, w_araw;  // per-warp closed-loop scratch rows
+  // tensor-core path (cc_tc_kernels.cuh): the MODEL node's f runs on tcgen05 (TMEM-resident stage inputs,
+  // 3xTF32 split), one trajectory per thread; only the (tiny) controller uses the per-warp regions above
+  int tc;          // 0: FFMA kernels, 1: tcgen05 kernels
+  int tc_nch;      // state register chunks of 8 per thread (4 or 7): S <= 8 * tc_nch
+  int tc_KP;       // A columns (contraction, multiple of 8): fwd [x ; v ; 1], bwd [kbar]
+  int tc_NP;       // D columns (multiple of 16): fwd k (S), bwd [zbar (8*nch) ; vbar (I)]
+  int tc_off;      // float offset of the tcgen05 region inside dynamic shared memory
+  int tc_sms;      // SM count (CTA start stagger: CTAs b and b + sms share an SM in the first wave)
+  int tc_stagger;  // cycles the second CTA of an SM waits before its first step
 };

@@ -1,0 +1,35 @@
+// cc_tc.cu -- translation unit of the tcgen05 rollout kernels (cc_tc_kernels.cuh); exposes cc_launch_{fwd,bwd}_tc.
+#include <cuda_runtime.h>
+#include <cstdio>
+
+#include "cc_tc_kernels.cuh"
+
+namespace {
+template <class Kern>
+int launch_tc(Kern kern, const CcKParams& p, void* stream, char* err, int errlen) {
+  const int SR = 8 * p.tc_nch;
+  const long long grid = (p.B + 127) / 128;
+  const size_t smem = ((size_t)p.tc_off + CC_TC_REGION_FLOATS(SR, p.tc_KP, p.tc_NP)) * 4;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) {
+    kern<<<(unsigned)grid, CC_TC_THREADS, smem, (cudaStream_t)stream>>>(p);
+    e = cudaGetLastError();
+  }
+  if (e != cudaSuccess) {
+    snprintf(err, errlen, "tcgen05 kernel launch failed: %s", cudaGetErrorString(e));
+    return CC_ERR_CUDA;
+  }
+  return CC_OK;
+}
+}  // namespace
+
+int cc_launch_fwd_tc(const CcKParams& p, void* stream, char* err, int errlen) {
+  const bool closed = p.n_nodes == 2;
+  if (p.tc_nch == 4)
+    return closed ? launch_tc(cc_tc_fwd_kernel<4, CC_CTRL_TINY>, p, stream, err, errlen) : launch_tc(cc_tc_fwd_kernel<4, CC_CTRL_NONE>, p, stream, err, errlen);
+  return closed ? launch_tc(cc_tc_fwd_kernel<7, CC_CTRL_TINY>, p, stream, err, errlen) : launch_tc(cc_tc_fwd_kernel<7, CC_CTRL_NONE>, p, stream, err, errlen);
+}
+int cc_launch_bwd_tc(const CcKParams& p, void* stream, char* err, int errlen) {
+  if (p.tc_nch == 4) return launch_tc(cc_tc_bwd_kernel<4, CC_CTRL_TINY>, p, stream, err, errlen);
+  return launch_tc(cc_tc_bwd_kernel<7, CC_CTRL_TINY>, p, stream, err, errlen);
+}
