@@ -31,3 +31,27 @@ def controller_variants(R=1, O_obs=1, I_m=1):
     v["full_s6_ft_tv"] = O.make_node(6, din, I_m, f_width=8, f_depth=1, g_feedthrough_u=True,
                                      f_time_variant=True, g_time_variant=True, f_act=O.ACT_TANH)
     return v
+
+
+def tc_model_variants():
+    """depth-0 models: the architectures the tcgen05 kernels (cc_tc_kernels.cuh) take over."""
+    v = {}
+    v["compact_s50_d0"] = model_variants()["compact_s50_d0"]
+    # full model (post-step readout), S <= 32 -> 4 register chunks
+    v["full_s20_d0"] = O.make_node(20, 1, 1, f_depth=0, u_transform=O.UT_KTANH, u_scale=6.0)
+    # S = 56: v~ / 1 columns need the extra A chunk
+    v["compact_s56_d0"] = O.make_node(56, 1, 1, f_depth=0, readout_pre_step=True, u_transform=O.UT_ARCTAN)
+    # explicit Euler, tanh final activation (forward on tcgen05, reverse pass on the FFMA kernels)
+    v["euler_s30_d0_tanh"] = O.make_node(30, 1, 1, f_depth=0, integrator=O.INT_EE, f_act_final=O.ACT_TANH)
+    v["full_s33_d0_nobias"] = O.make_node(33, 1, 1, f_depth=0, f_use_bias=False, g_use_bias=False)
+    return v
+
+
+def tc_controller_variants(R=1, O_obs=1, I_m=1):
+    v = {}
+    din = R + O_obs
+    v["compact_s5_d0"] = controller_variants()["compact_s5_d0"]
+    # full (post-step readout) depth-0 controller with feed-through: still the per-lane "tiny" path
+    v["full_s6_d0_ft"] = O.make_node(6, din, I_m, f_depth=0, g_feedthrough_u=True)
+    v["euler_s3_d0"] = O.make_node(3, din, I_m, f_depth=0, integrator=O.INT_EE, readout_pre_step=True, out_scale=0.5)
+    return v

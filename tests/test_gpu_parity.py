@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from cchelpers import TOL_GRAD, TOL_STATE, conv, l2rel, normwise
-from ccspecs import controller_variants, model_variants
+from ccspecs import controller_variants, model_variants, tc_controller_variants, tc_model_variants
 from oracle import c_oracle as CO
 from oracle import np_oracle as O
 
@@ -22,6 +22,18 @@ def T_():
     import torch
 
     return lambda a: torch.tensor(np.asarray(a, np.float32), device="cuda")
+
+
+@pytest.fixture(params=["tcgen05", "ffma"])
+def path(request):
+    """run the test once per kernel family: CC_B200_TC=0 forces the FFMA kernels where tcgen05 would be chosen"""
+    old = os.environ.get("CC_B200_TC")
+    os.environ["CC_B200_TC"] = "1" if request.param == "tcgen05" else "0"
+    yield request.param
+    if old is None:
+        del os.environ["CC_B200_TC"]
+    else:
+        os.environ["CC_B200_TC"] = old
 
 
 def _u(B, T, I, seed=0):
@@ -71,7 +83,64 @@ def test_closedloop_fwd_bwd_vs_oracle(cname, mname, T_):
     assert l2rel(tb.cpu().numpy(), ref["theta_c_bar"]) < max(TOL_GRAD, 2 * floor), (floor,)
 
 
-def test_cfg1_model_trainer_shapes(T_):
+@pytest.mark.parametrize("name", list(tc_model_variants()))
+def test_tc_rollout_vs_oracle(name, path, T_):
+    """depth-0 models, open loop: forward on tcgen05 (3xTF32), reverse pass on the FFMA kernels from the tape it wrote"""
+    from chain_control_b200 import ops
+
+    spec = tc_model_variants()[name]
+    B, T = 301, 203
+    theta = O.init_params(spec, 1).astype(np.float32)
+    u = _u(B, T, spec.input_dim)
+    x0 = (0.1 * np.random.default_rng(3).normal(size=(B, spec.state_dim))).astype(np.float32)
+    ybar = np.random.default_rng(5).normal(size=(B, T + 1, spec.output_dim)).astype(np.float32)
+    ref = CO.rollout(spec, theta, u, x0=x0, ybar=ybar, want_ubar=True, dtype=np.float64)
+    y, xf, tape = ops.rollout_fwd(conv(spec), T_(theta), T_(u), T_(x0), want_tape=True, want_x_final=True)
+    tb, ub = ops.rollout_bwd(conv(spec), T_(theta), T_(u), tape, T_(ybar), T_(x0), want_ubar=True)
+    assert normwise(y.cpu().numpy(), ref["y"]) < TOL_STATE
+    assert bool(np.isfinite(xf.cpu().numpy()).all())
+    assert l2rel(tb.cpu().numpy(), ref["theta_bar"]) < TOL_GRAD
+    assert l2rel(ub.cpu().numpy(), ref["ubar"]) < TOL_GRAD
+
+
+@pytest.mark.parametrize("cname", list(tc_controller_variants()))
+@pytest.mark.parametrize("mname", list(tc_model_variants()))
+def test_tc_closedloop_vs_oracle(cname, mname, path, T_):
+    """depth-0 models in closed loop with the tiny controllers: forward and (linear models) reverse pass on tcgen05"""
+    from chain_control_b200 import ops
+
+    mspec, cspec = tc_model_variants()[mname], tc_controller_variants()[cname]
+    B, Tr = 290, 201
+    thc, thm = O.init_params(cspec, 2).astype(np.float32), O.init_params(mspec, 1).astype(np.float32)
+    refs = 3 * _u(B, Tr, 1)
+    noise = (0.02 * np.random.default_rng(1).normal(size=(B, Tr, 1))).astype(np.float32)
+    ybar = np.random.default_rng(6).normal(size=(B, Tr, 1)).astype(np.float32)
+    ref = CO.closedloop(cspec, mspec, thc, thm, refs, noise, ybar=ybar, dtype=np.float64)
+    yh, us, tape = ops.closedloop_fwd(conv(cspec), conv(mspec), T_(thc), T_(thm), T_(refs), T_(noise), want_tape=True,
+                                      want_u=True)
+    tb = ops.closedloop_bwd(conv(cspec), conv(mspec), T_(thc), T_(thm), T_(refs), tape, T_(ybar), T_(noise))
+    assert normwise(yh.cpu().numpy(), ref["yhat"]) < TOL_STATE
+    assert normwise(us.cpu().numpy(), ref["u"]) < TOL_STATE
+    assert l2rel(tb.cpu().numpy(), ref["theta_c_bar"]) < TOL_GRAD
+
+
+def test_tc_partial_tile_and_empty(T_):
+    """B not a multiple of the 128-trajectory tile, B = 1, T = 0 (only y0) on the tcgen05 path"""
+    import torch
+
+    from chain_control_b200 import ops
+
+    spec = tc_model_variants()["compact_s50_d0"]
+    theta = O.init_params(spec, 1).astype(np.float32)
+    for B, T in [(1, 17), (129, 5), (3, 0)]:
+        u = _u(B, T, 1)
+        ref = CO.rollout(spec, theta, u, dtype=np.float64)
+        y, _, _ = ops.rollout_fwd(conv(spec), T_(theta), torch.tensor(u, device="cuda").reshape(B, T, 1))
+        assert tuple(y.shape) == (B, T + 1, 1)
+        assert normwise(y.cpu().numpy(), ref["y"]) < TOL_STATE
+
+
+def test_cfg1_model_trainer_shapes(path, T_):
     """configs[0]: 8 trajectories x 1000 steps (outputs 1001), notebook-3 model, T=1000 horizon."""
     from chain_control_b200 import ops
 
@@ -91,7 +160,7 @@ def test_cfg1_model_trainer_shapes(T_):
     assert l2rel(tb.cpu().numpy(), ref["theta_bar"]) < TOL_GRAD
 
 
-def test_cfg2_controller_trainer_64x1001(T_):
+def test_cfg2_controller_trainer_64x1001(path, T_):
     """configs[1]: closed-loop BPTT over 64 reference trajectories x 1001 steps (mse(refs, yhat))."""
     from chain_control_b200 import ops
 
@@ -108,7 +177,7 @@ def test_cfg2_controller_trainer_64x1001(T_):
     assert l2rel(tb.cpu().numpy(), ref["theta_c_bar"]) < TOL_GRAD
 
 
-def test_full_size_properties(T_):
+def test_full_size_properties(path, T_):
     """B = 65,536 (configs[3]) is too big for the oracle; check size-independent properties instead."""
     import torch
 
