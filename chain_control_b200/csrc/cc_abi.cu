@@ -348,12 +348,13 @@ int make_plan(const CcModule* const* mods, int n_nodes, long long B, int T, cons
     }
     p->wpc = 4;
     const int head = (int)((sizeof(CcKParams) + 15) / 16 * 4);
-    p->tc_off = (head + p->cta_floats + 4 * p->warp_floats + 15) / 16 * 16;
+    p->tc_off = (head + 15) / 16 * 16;  // the per-warp controller regions of the FFMA kernels are not used
     p->tc_sms = num_sms();
     const char* st = getenv("CC_B200_TC_STAGGER");
     p->tc_stagger = st ? atoi(st) : 900;
-    const long long bytes = ((long long)p->tc_off + 2LL * p->tc_KP * p->tc_NP + CC_TINY_O * (SR + 4) + 8) * 4;
-    if (bytes > 110 * 1024) return fail(CC_ERR_UNSUPPORTED, "tcgen05 path: %lld B of shared memory per CTA do not allow two CTAs per SM", bytes);
+    const long long gp = (o.bwd && n_nodes == 2) ? (long long)(p->nd[0].S + p->nd[0].O) * 14 * 128 + (long long)(p->nd[0].f.layer[0].act != CC_ACT_IDENTITY ? 9 : 5) * CC_TINY_S * 128 : 0;
+    const long long bytes = ((long long)p->tc_off + 2LL * p->tc_KP * p->tc_NP + CC_TINY_O * (SR + 4) + (CC_TINY_S + CC_TINY_O) * 16 + 8 + gp) * 4;
+    if (bytes > kSmemBudget) return fail(CC_ERR_UNSUPPORTED, "tcgen05 path: %lld B of shared memory per CTA", bytes);
     if (getenv("CC_B200_VERBOSE"))
       fprintf(stderr, "[ccb200] tcgen05 plan: nodes=%d bwd=%d B=%lld T=%d nch=%d KP=%d NP=%d smem=%lld B ctas=%lld\n", n_nodes, (int)o.bwd, B, T,
               p->tc_nch, p->tc_KP, p->tc_NP, bytes, (B + 127) / 128);

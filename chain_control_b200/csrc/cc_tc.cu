@@ -6,10 +6,11 @@
 
 namespace {
 template <class Kern>
-int launch_tc(Kern kern, const CcKParams& p, void* stream, char* err, int errlen) {
+int launch_tc(Kern kern, const CcKParams& p, bool bwd, void* stream, char* err, int errlen) {
   const int SR = 8 * p.tc_nch;
   const long long grid = (p.B + 127) / 128;
-  const size_t smem = ((size_t)p.tc_off + CC_TC_REGION_FLOATS(SR, p.tc_KP, p.tc_NP)) * 4;
+  const size_t gp = bwd ? (size_t)(p.nd[0].S + p.nd[0].O) * CC_CKU * 128 + (size_t)(p.nd[0].f.layer[0].act != CC_ACT_IDENTITY ? 9 : 5) * CC_TINY_S * 128 : 0;  // lane-private controller gradient accumulators + stage record
+  const size_t smem = ((size_t)p.tc_off + CC_TC_REGION_FLOATS(SR, p.tc_KP, p.tc_NP) + gp) * 4;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e == cudaSuccess) {
     kern<<<(unsigned)grid, CC_TC_THREADS, smem, (cudaStream_t)stream>>>(p);
@@ -23,13 +24,18 @@ int launch_tc(Kern kern, const CcKParams& p, void* stream, char* err, int errlen
 }
 }  // namespace
 
+#define CC_TC_FWD(NCH, CM, FACT) launch_tc(cc_tc_fwd_kernel<NCH, CM, FACT>, p, false, stream, err, errlen)
 int cc_launch_fwd_tc(const CcKParams& p, void* stream, char* err, int errlen) {
   const bool closed = p.n_nodes == 2;
-  if (p.tc_nch == 4)
-    return closed ? launch_tc(cc_tc_fwd_kernel<4, CC_CTRL_TINY>, p, stream, err, errlen) : launch_tc(cc_tc_fwd_kernel<4, CC_CTRL_NONE>, p, stream, err, errlen);
-  return closed ? launch_tc(cc_tc_fwd_kernel<7, CC_CTRL_TINY>, p, stream, err, errlen) : launch_tc(cc_tc_fwd_kernel<7, CC_CTRL_NONE>, p, stream, err, errlen);
+  const bool fact = p.nd[p.n_nodes - 1].f.layer[0].act != CC_ACT_IDENTITY;  // non-linear final activation of f: separate instantiation
+  if (p.tc_nch == 4) {
+    if (fact) return closed ? CC_TC_FWD(4, CC_CTRL_TINY, true) : CC_TC_FWD(4, CC_CTRL_NONE, true);
+    return closed ? CC_TC_FWD(4, CC_CTRL_TINY, false) : CC_TC_FWD(4, CC_CTRL_NONE, false);
+  }
+  if (fact) return closed ? CC_TC_FWD(7, CC_CTRL_TINY, true) : CC_TC_FWD(7, CC_CTRL_NONE, true);
+  return closed ? CC_TC_FWD(7, CC_CTRL_TINY, false) : CC_TC_FWD(7, CC_CTRL_NONE, false);
 }
 int cc_launch_bwd_tc(const CcKParams& p, void* stream, char* err, int errlen) {
-  if (p.tc_nch == 4) return launch_tc(cc_tc_bwd_kernel<4, CC_CTRL_TINY>, p, stream, err, errlen);
-  return launch_tc(cc_tc_bwd_kernel<7, CC_CTRL_TINY>, p, stream, err, errlen);
+  if (p.tc_nch == 4) return launch_tc(cc_tc_bwd_kernel<4, CC_CTRL_TINY>, p, true, stream, err, errlen);
+  return launch_tc(cc_tc_bwd_kernel<7, CC_CTRL_TINY>, p, true, stream, err, errlen);
 }

@@ -15,15 +15,15 @@
 //   * a worker thread reads its row of D with tcgen05.ld, does the RK4 bookkeeping for its trajectory in
 //     registers (state x, stage sum), splits the next stage input and writes it back with tcgen05.st;
 //     mbarriers (a_ready: 128 arrivals, d_ready: tcgen05.commit) are the only synchronisation in the loop.
-//   * readout g(x) (O <= 4 outputs), the tiny feedback controller (cc_tiny_step / cc_tiny_bwd, one trajectory
-//     per lane, shared with the FFMA kernels) and all I/O are FFMA work of the same thread.
+//   * readout g(x) (O <= 4 outputs), the tiny feedback controller (cc_tc_ctrl.cuh, register resident) and all
+//     I/O are FFMA work of the same thread, placed behind the publish of a stage so that it overlaps the MMAs.
 //
 // TMEM map of a CTA (256 columns allocated): D [0, NP), A_hi [NP, NP+KP), A_lo [NP+KP, NP+2KP).
 // A column layout (forward): [0, 8*NCH) state (zero beyond S); v~_i and the constant 1 sit at the fixed
 // in-chunk positions 3+i / 7 of the LAST chunk of the state range if S <= 8*NCH-5, else of one extra chunk.
 #pragma once
 #include "cc_kernels.cuh"
-#include "cc_kernels_bwd.cuh"
+#include "cc_tc_ctrl.cuh"
 #include "cc_tmem.cuh"
 
 #define CC_TC_THREADS 128
@@ -57,11 +57,13 @@ CC_DEV void cc_tc_store_split(uint32_t aHi, uint32_t aLo, int c0, const float (&
   }
 }
 
-// forward epilogue of RK4 stage ST (or the single Euler stage, ST = 4) for columns [C0, C0+NC) of this
-// trajectory: k = act(D) ; stage sum / next stage input / new state in the reference's operation order
-// (integrate.py:6-13: x + h*k1/2, ..., x + dt*(1/6*(k1+2k2+2k3+k4))).
-template <int SR, int C0, int NC, int ST, bool FACT>
-CC_DEV void cc_tc_fwd_group(uint32_t aD, uint32_t aHi, uint32_t aLo, float (&x)[SR], float (&acc)[SR], int fact, float h) {
+// forward epilogue of one RK4 stage for columns [C0, C0+NC) of this trajectory, in the reference's operation
+// order (integrate.py:6-13: x + h*k1/2, x + h*k2/2, x + h*k3, x + dt*(1/6*(k1+2k2+2k3+k4))).
+//   generic (stages 1..3 of 4): acc += wk * k (acc starts at 0) ; next stage input z = x + (h*k)*cz -> A
+//   final   (last stage, or the single Euler stage): x <- x + h*(1/6*(acc + k))  |  x + h*k ; acc <- 0
+// ONE generic body serves three stages with run-time (wk, cz): the hot loop has to fit the instruction cache.
+template <int SR, int C0, int NC, bool FINAL, bool FACT>
+CC_DEV void cc_tc_fwd_group(uint32_t aD, uint32_t aHi, uint32_t aLo, float (&x)[SR], float (&acc)[SR], int fact, float h, float wk, float cz, bool rk4) {
   uint32_t r[NC];
   cc_tc_ld<NC>(aD + C0, r);
   cc_tmem_wait_ld();
@@ -70,20 +72,23 @@ CC_DEV void cc_tc_fwd_group(uint32_t aD, uint32_t aHi, uint32_t aLo, float (&x)[
   for (int i = 0; i < NC; ++i) {
     float k = __uint_as_float(r[i]);
     if (FACT) k = cc_act(fact, k);
-    if (ST == 0) { acc[C0 + i] = k; z[i] = x[C0 + i] + (h * k) * 0.5f; }
-    else if (ST == 1) { acc[C0 + i] += 2.f * k; z[i] = x[C0 + i] + (h * k) * 0.5f; }
-    else if (ST == 2) { acc[C0 + i] += 2.f * k; z[i] = x[C0 + i] + h * k; }
-    else if (ST == 3) { x[C0 + i] = x[C0 + i] + h * ((1.f / 6.f) * (acc[C0 + i] + k)); }
-    else { x[C0 + i] = x[C0 + i] + h * k; }
+    if (!FINAL) {
+      acc[C0 + i] = fmaf(wk, k, acc[C0 + i]);
+      z[i] = x[C0 + i] + (h * k) * cz;
+    } else {
+      const float s = rk4 ? (1.f / 6.f) * (acc[C0 + i] + k) : k;
+      x[C0 + i] = x[C0 + i] + h * s;
+      acc[C0 + i] = 0.f;
+    }
   }
-  if (ST < 3) cc_tc_store_split<NC>(aHi, aLo, C0, z);
+  if (!FINAL) cc_tc_store_split<NC>(aHi, aLo, C0, z);
 }
-template <int SR, int ST, bool FACT>
-CC_DEV void cc_tc_fwd_stage(uint32_t aD, uint32_t aHi, uint32_t aLo, float (&x)[SR], float (&acc)[SR], int fact, float h) {
-  cc_tc_fwd_group<SR, 0, 32, ST, FACT>(aD, aHi, aLo, x, acc, fact, h);
+template <int SR, bool FINAL, bool FACT>
+CC_DEV void cc_tc_fwd_stage(uint32_t aD, uint32_t aHi, uint32_t aLo, float (&x)[SR], float (&acc)[SR], int fact, float h, float wk, float cz, bool rk4) {
+  cc_tc_fwd_group<SR, 0, 32, FINAL, FACT>(aD, aHi, aLo, x, acc, fact, h, wk, cz, rk4);
   if constexpr (SR == 56) {
-    cc_tc_fwd_group<SR, 32, 16, ST, FACT>(aD, aHi, aLo, x, acc, fact, h);
-    cc_tc_fwd_group<SR, 48, 8, ST, FACT>(aD, aHi, aLo, x, acc, fact, h);
+    cc_tc_fwd_group<SR, 32, 16, FINAL, FACT>(aD, aHi, aLo, x, acc, fact, h, wk, cz, rk4);
+    cc_tc_fwd_group<SR, 48, 8, FINAL, FACT>(aD, aHi, aLo, x, acc, fact, h, wk, cz, rk4);
   }
 }
 
@@ -124,7 +129,7 @@ CC_DEV void cc_tc_readout(const float* gw, const float (&x)[SR], int O, int gact
 }
 
 struct CcTcShared {
-  float* bhi; float* blo; float* gw; uint64_t* a_ready; uint64_t* d_ready; uint32_t* tmem_base;
+  float* bhi; float* blo; float* gw; float* wfc; float* wgc; uint64_t* a_ready; uint64_t* d_ready; uint32_t* tmem_base; float* gp;
 };
 template <int SR>
 CC_DEV CcTcShared cc_tc_carve(float* smem, const CcKParams& p) {
@@ -132,12 +137,16 @@ CC_DEV CcTcShared cc_tc_carve(float* smem, const CcKParams& p) {
   s.bhi = smem + p.tc_off;
   s.blo = s.bhi + p.tc_KP * p.tc_NP;
   s.gw = s.blo + p.tc_KP * p.tc_NP;
-  s.a_ready = reinterpret_cast<uint64_t*>(s.gw + CC_TINY_O * (SR + 4));
+  s.wfc = s.gw + CC_TINY_O * (SR + 4);          // controller f weights [8][16]
+  s.wgc = s.wfc + CC_TINY_S * CC_CK;            // controller g weights [4][16]
+  s.a_ready = reinterpret_cast<uint64_t*>(s.wgc + CC_TINY_O * CC_CK);
   s.d_ready = s.a_ready + 1;
   s.tmem_base = reinterpret_cast<uint32_t*>(s.d_ready + 1);
+  s.gp = s.wgc + CC_TINY_O * CC_CK + 8;         // (reverse pass) lane-private gradient accumulators
   return s;
 }
-#define CC_TC_REGION_FLOATS(SR, KP, NP) (2 * (KP) * (NP) + CC_TINY_O * ((SR) + 4) + 8)
+// floats of the region; the reverse pass appends (S_c + O_c) * CC_CKU * 128 accumulator floats
+#define CC_TC_REGION_FLOATS(SR, KP, NP) (2 * (KP) * (NP) + CC_TINY_O * ((SR) + 4) + (CC_TINY_S + CC_TINY_O) * CC_CK + 8)
 
 // stage the MMA B operand (hi/lo split) and the readout weights.  B is K-major without swizzle:
 // element (n, k) at ((k/4)*NP + n)*4 + k%4  ->  8x16-byte core matrices, SBO = 128 B, LBO = NP*16 B.
@@ -199,10 +208,8 @@ CC_DEV void cc_tc_issue_batch(uint32_t tbase, int KP, int NP, uint32_t bhi, uint
   const CcNodeDev& C = p.nd[0];                                                                       \
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;                                      \
   const CcTcShared sh = cc_tc_carve<SR>(cc_smem, p);                                                  \
-  if (closed) {                                                                                       \
-    cc_stage_mlp(C, C.f, p.theta[0], cta_smem, tid, blockDim.x);                                      \
-    cc_stage_mlp(C, C.g, p.theta[0], cta_smem, tid, blockDim.x);                                      \
-  }                                                                                                   \
+  (void)cta_smem;                                                                                     \
+  if (closed) cc_ctrl_stage_weights(C, p.theta[0], sh.wfc, sh.wgc, tid, blockDim.x);                  \
   cc_tc_stage_weights<SR>(p, M, p.theta[closed ? 1 : 0], sh, BWD, tid, blockDim.x);                   \
   if (warp == 0) {                                                                                    \
     if (lane == 0) {                                                                                  \
@@ -274,7 +281,7 @@ CC_DEV void cc_tc_await(const CcTcShared& sh, uint32_t& par) {
 // ------------------------------------------------------------------------------------------------
 // K1 + K3 on tcgen05: forward rollout.  CM: CC_CTRL_NONE (open loop) or CC_CTRL_TINY (closed loop).
 // ------------------------------------------------------------------------------------------------
-template <int NCH, int CM>
+template <int NCH, int CM, bool FACT>
 __global__ void __launch_bounds__(CC_TC_THREADS, 2) cc_tc_fwd_kernel(const CC_GRID_CONSTANT CcKParams gp) {
   CC_TC_PROLOGUE(gp, false)
   const int nst = M.integrator == CC_INT_RK4 ? 4 : 1;
@@ -290,8 +297,9 @@ __global__ void __launch_bounds__(CC_TC_THREADS, 2) cc_tc_fwd_kernel(const CC_GR
     const float h = M.dt;
     const int tb = cc_tc_tail_base(M.S, SR);
     const bool extra = tb >= SR;
-    if (closed) cc_init_node_buffers(C, w, false);
-    __syncwarp();
+    float xc[CC_TINY_S];  // controller state (registers)
+#pragma unroll
+    for (int i = 0; i < CC_TINY_S; ++i) xc[i] = 0.f;
     float x[SR], acc[SR];
 #pragma unroll
     for (int i = 0; i < SR; ++i) {
@@ -327,9 +335,9 @@ __global__ void __launch_bounds__(CC_TC_THREADS, 2) cc_tc_fwd_kernel(const CC_GR
           if (i < Win && act) vin[i] = __ldg(p.in + b * (long long)p.T * Win + (long long)(k + 1) * Win + i);
       }
       float a[CC_TINY_O];  // raw model input of this step
+      float vc[CC_TINY_O];
       if (closed) {
         // controller input = merge_x_y(ref, y_prev) = [ref ; obs]     step_fn.py:187-192
-        float vc[CC_TINY_O];
 #pragma unroll
         for (int i = 0; i < CC_TINY_O; ++i) {
           vc[i] = vcur[i];
@@ -339,18 +347,21 @@ __global__ void __launch_bounds__(CC_TC_THREADS, 2) cc_tc_fwd_kernel(const CC_GR
         }
         if (wt && act) {
           for (int o = 0; o < M.O; ++o) p.tape[((long long)ck * p.tape_rows + p.tape_yrow + o) * p.Bpad + b] = yprev[o];
-          for (int s = 0; s < C.S; ++s) p.tape[((long long)ck * p.tape_rows + C.tape_row + s) * p.Bpad + b] = cc_ws(w)[C.w_X + s * CC_LD + lane];
+#pragma unroll
+          for (int s = 0; s < CC_TINY_S; ++s)
+            if (s < C.S) p.tape[((long long)ck * p.tape_rows + C.tape_row + s) * p.Bpad + b] = xc[s];
         }
         if (wt && act && M.tape_row >= 0)  // non-linear frozen model: its state is part of the carry the FFMA reverse pass reads
 #pragma unroll
           for (int s = 0; s < SR; ++s)
             if (s < M.S) p.tape[((long long)ck * p.tape_rows + M.tape_row + s) * p.Bpad + b] = x[s];
-        cc_tiny_step<false>(C, w, tc, vc, a);
+        // compact controller: u = out_scale * g_c(x_c) needs no state update -> the update overlaps the first MMA batch
+        if (C.pre) cc_ctrl_readout_pre(C, sh.wgc, xc, tc, vc, a);
+        else cc_ctrl_update<false>(C, sh.wfc, sh.wgc, xc, tc, vc, a, nullptr);
         if (p.u_out && act)
 #pragma unroll
           for (int i = 0; i < CC_TINY_O; ++i)
             if (i < M.I) p.u_out[b * (long long)p.T * M.I + (long long)k * M.I + i] = a[i];
-        if (C.has_t) tc = tc + C.dt;
       } else {
 #pragma unroll
         for (int i = 0; i < CC_TINY_O; ++i) a[i] = vcur[i];
@@ -366,27 +377,26 @@ __global__ void __launch_bounds__(CC_TC_THREADS, 2) cc_tc_fwd_kernel(const CC_GR
 #pragma unroll
         for (int i = 0; i < CC_TINY_O; ++i) x[SR - 5 + i] = vt[i];
       }
-      float y[CC_TINY_O];
-      if (M.pre) cc_tc_readout<SR>(sh.gw, x, M.O, G.act, M.out_scale, y);  // compact: y = g(x) BEFORE the update
       cc_tc_write_state<SR>(aHi, aLo, x, extra, vt);
       cc_tc_publish(sh, q);
-      if (nst == 4) {
-        if (F.act == CC_ACT_IDENTITY) {
-          cc_tc_await(sh, par); cc_tc_fwd_stage<SR, 0, false>(aD, aHi, aLo, x, acc, 0, h); cc_tc_publish(sh, q);
-          cc_tc_await(sh, par); cc_tc_fwd_stage<SR, 1, false>(aD, aHi, aLo, x, acc, 0, h); cc_tc_publish(sh, q);
-          cc_tc_await(sh, par); cc_tc_fwd_stage<SR, 2, false>(aD, aHi, aLo, x, acc, 0, h); cc_tc_publish(sh, q);
-          cc_tc_await(sh, par); cc_tc_fwd_stage<SR, 3, false>(aD, aHi, aLo, x, acc, 0, h);
-        } else {
-          cc_tc_await(sh, par); cc_tc_fwd_stage<SR, 0, true>(aD, aHi, aLo, x, acc, F.act, h); cc_tc_publish(sh, q);
-          cc_tc_await(sh, par); cc_tc_fwd_stage<SR, 1, true>(aD, aHi, aLo, x, acc, F.act, h); cc_tc_publish(sh, q);
-          cc_tc_await(sh, par); cc_tc_fwd_stage<SR, 2, true>(aD, aHi, aLo, x, acc, F.act, h); cc_tc_publish(sh, q);
-          cc_tc_await(sh, par); cc_tc_fwd_stage<SR, 3, true>(aD, aHi, aLo, x, acc, F.act, h);
+      // ---- work that overlaps the first MMA batch ----
+      float y[CC_TINY_O];
+      if (M.pre) cc_tc_readout<SR>(sh.gw, x, M.O, G.act, M.out_scale, y);  // compact: y = g(x) BEFORE the update
+      if (closed) {
+        if (C.pre) {
+          float dummy[CC_TINY_O];
+          cc_ctrl_update<false>(C, sh.wfc, sh.wgc, xc, tc, vc, dummy, nullptr);
         }
-      } else {
-        cc_tc_await(sh, par);
-        if (F.act == CC_ACT_IDENTITY) cc_tc_fwd_stage<SR, 4, false>(aD, aHi, aLo, x, acc, 0, h);
-        else cc_tc_fwd_stage<SR, 4, true>(aD, aHi, aLo, x, acc, F.act, h);
+        if (C.has_t) tc = tc + C.dt;
       }
+#pragma unroll 1
+      for (int st = 0; st < nst - 1; ++st) {
+        cc_tc_await(sh, par);
+        cc_tc_fwd_stage<SR, false, FACT>(aD, aHi, aLo, x, acc, F.act, h, st == 0 ? 1.f : 2.f, st == 2 ? 1.f : 0.5f, true);
+        cc_tc_publish(sh, q);
+      }
+      cc_tc_await(sh, par);
+      cc_tc_fwd_stage<SR, true, FACT>(aD, aHi, aLo, x, acc, F.act, h, 0.f, 0.f, nst == 4);
       if (!M.pre) cc_tc_readout<SR>(sh.gw, x, M.O, G.act, M.out_scale, y);  // full model: y = g(x_next)
       if (closed) {
 #pragma unroll
@@ -416,10 +426,11 @@ __global__ void __launch_bounds__(CC_TC_THREADS, 2) cc_tc_fwd_kernel(const CC_GR
 // per RK4 stage one MMA batch  [zbar ; vbar] = kbar . [W_x ; W_v]   (SURVEY 9.4), kbar built from the state
 // adjoint lam (registers) and the previous stage's zbar.
 // ------------------------------------------------------------------------------------------------
-// epilogue of backward stage ST (3, 2, 1, 0; 4 = Euler) for columns [C0, C0+NC): zb = D ; zsum += zb ;
-// next kbar = ca*lam + cb*zb written to A.  After the last stage lam <- lam + zsum.
-template <int SR, int C0, int NC, int ST>
-CC_DEV void cc_tc_bwd_group(uint32_t aD, uint32_t aHi, uint32_t aLo, float (&lam)[SR], float (&zsum)[SR], float h) {
+// epilogue of one backward stage for columns [C0, C0+NC): zb = D ;
+//   generic (stages 4, 3, 2 of RK4): zsum += zb (zsum starts at 0) ; next kbar = ca*lam + cb*zb -> A
+//   final   (stage 1, or the single Euler stage): lam <- lam + (zsum + zb) ; zsum <- 0
+template <int SR, int C0, int NC, bool FINAL>
+CC_DEV void cc_tc_bwd_group(uint32_t aD, uint32_t aHi, uint32_t aLo, float (&lam)[SR], float (&zsum)[SR], float ca, float cb) {
   uint32_t r[NC];
   cc_tc_ld<NC>(aD + C0, r);
   cc_tmem_wait_ld();
@@ -427,20 +438,22 @@ CC_DEV void cc_tc_bwd_group(uint32_t aD, uint32_t aHi, uint32_t aLo, float (&lam
 #pragma unroll
   for (int i = 0; i < NC; ++i) {
     const float zb = __uint_as_float(r[i]);
-    if (ST == 3) { zsum[C0 + i] = zb; kb[i] = (h / 3.f) * lam[C0 + i] + h * zb; }
-    else if (ST == 2) { zsum[C0 + i] += zb; kb[i] = (h / 3.f) * lam[C0 + i] + (h / 2.f) * zb; }
-    else if (ST == 1) { zsum[C0 + i] += zb; kb[i] = (h / 6.f) * lam[C0 + i] + (h / 2.f) * zb; }
-    else if (ST == 0) { lam[C0 + i] = lam[C0 + i] + (zsum[C0 + i] + zb); }
-    else { lam[C0 + i] = lam[C0 + i] + zb; }
+    if (!FINAL) {
+      zsum[C0 + i] += zb;
+      kb[i] = ca * lam[C0 + i] + cb * zb;
+    } else {
+      lam[C0 + i] = lam[C0 + i] + (zsum[C0 + i] + zb);
+      zsum[C0 + i] = 0.f;
+    }
   }
-  if (ST >= 1 && ST <= 3) cc_tc_store_split<NC>(aHi, aLo, C0, kb);
+  if (!FINAL) cc_tc_store_split<NC>(aHi, aLo, C0, kb);
 }
-template <int SR, int ST>
-CC_DEV void cc_tc_bwd_stage(uint32_t aD, uint32_t aHi, uint32_t aLo, float (&lam)[SR], float (&zsum)[SR], float h, float (&utb)[CC_TINY_O]) {
-  cc_tc_bwd_group<SR, 0, 32, ST>(aD, aHi, aLo, lam, zsum, h);
+template <int SR, bool FINAL>
+CC_DEV void cc_tc_bwd_stage(uint32_t aD, uint32_t aHi, uint32_t aLo, float (&lam)[SR], float (&zsum)[SR], float ca, float cb, float (&utb)[CC_TINY_O]) {
+  cc_tc_bwd_group<SR, 0, 32, FINAL>(aD, aHi, aLo, lam, zsum, ca, cb);
   if constexpr (SR == 56) {
-    cc_tc_bwd_group<SR, 32, 16, ST>(aD, aHi, aLo, lam, zsum, h);
-    cc_tc_bwd_group<SR, 48, 8, ST>(aD, aHi, aLo, lam, zsum, h);
+    cc_tc_bwd_group<SR, 32, 16, FINAL>(aD, aHi, aLo, lam, zsum, ca, cb);
+    cc_tc_bwd_group<SR, 48, 8, FINAL>(aD, aHi, aLo, lam, zsum, ca, cb);
   }
   uint32_t r[4];
   cc_tmem_ld4(aD + SR, r);  // vbar columns
@@ -461,8 +474,12 @@ __global__ void __launch_bounds__(CC_TC_THREADS, 2) cc_tc_bwd_kernel(const CC_GR
     const uint32_t aD = tbase + ((uint32_t)(warp * 32) << 16), aHi = aD + NP, aLo = aD + NP + KP;
     const float h = M.dt;
     const float* ttab = p.tape + (long long)p.n_ckpt * p.tape_rows * p.Bpad;
-    cc_init_node_buffers(C, w, true);
-    __syncwarp();
+    float* GP = sh.gp + tid;  // lane-private columns: conflict free
+    float* keep = sh.gp + (C.S + C.O) * CC_CKU * 128 + tid;  // controller stage record of the current step
+    for (int e = 0; e < (C.S + C.O) * CC_CKU; ++e) GP[e * 128] = 0.f;
+    float lamc[CC_TINY_S];  // adjoint of the controller state
+#pragma unroll
+    for (int i = 0; i < CC_TINY_S; ++i) lamc[i] = 0.f;
     float lam[SR], zsum[SR];
 #pragma unroll
     for (int i = 0; i < SR; ++i) { lam[i] = 0.f; zsum[i] = 0.f; }
@@ -527,22 +544,20 @@ __global__ void __launch_bounds__(CC_TC_THREADS, 2) cc_tc_bwd_kernel(const CC_GR
       }
       cc_tc_publish(sh, q);
       // while the first MMA batch runs: recompute the controller step (its stage intermediates are kept)
-#pragma unroll
-      for (int s = 0; s < CC_TINY_S; ++s)
-        if (s < C.S) cc_ws(w)[C.w_X + s * CC_LD + lane] = xcv[s];
       float a[CC_TINY_O];
-      cc_tiny_step<true>(C, w, tc, vc, a);
+      if (C.pre) cc_ctrl_readout_pre(C, sh.wgc, xcv, tc, vc, a);
+      cc_ctrl_update<true>(C, sh.wfc, sh.wgc, xcv, tc, vc, a, keep);
       float utb[CC_TINY_O];
 #pragma unroll
       for (int i = 0; i < CC_TINY_O; ++i) utb[i] = 0.f;
-      if (nst == 4) {
-        cc_tc_await(sh, par); cc_tc_bwd_stage<SR, 3>(aD, aHi, aLo, lam, zsum, h, utb); cc_tc_publish(sh, q);
-        cc_tc_await(sh, par); cc_tc_bwd_stage<SR, 2>(aD, aHi, aLo, lam, zsum, h, utb); cc_tc_publish(sh, q);
-        cc_tc_await(sh, par); cc_tc_bwd_stage<SR, 1>(aD, aHi, aLo, lam, zsum, h, utb); cc_tc_publish(sh, q);
-        cc_tc_await(sh, par); cc_tc_bwd_stage<SR, 0>(aD, aHi, aLo, lam, zsum, h, utb);
-      } else {
-        cc_tc_await(sh, par); cc_tc_bwd_stage<SR, 4>(aD, aHi, aLo, lam, zsum, h, utb);
+#pragma unroll 1
+      for (int st = 3; st >= 1 && nst == 4; --st) {  // after z4bar: kbar3 = h/3 lam + h z4bar ; z3bar: kbar2 = h/3 lam + h/2 z3bar ; z2bar: kbar1 = h/6 lam + h/2 z2bar
+        cc_tc_await(sh, par);
+        cc_tc_bwd_stage<SR, false>(aD, aHi, aLo, lam, zsum, st == 1 ? h / 6.f : h / 3.f, st == 3 ? h : h / 2.f, utb);
+        cc_tc_publish(sh, q);
       }
+      cc_tc_await(sh, par);
+      cc_tc_bwd_stage<SR, true>(aD, aHi, aLo, lam, zsum, 0.f, 0.f, utb);
       if (M.pre) {  // y_k = g(x_k): cotangent joins the adjoint of x_k
 #pragma unroll
         for (int o = 0; o < CC_TINY_O; ++o)
@@ -556,7 +571,7 @@ __global__ void __launch_bounds__(CC_TC_THREADS, 2) cc_tc_bwd_kernel(const CC_GR
       float ob[CC_TINY_O], vb[CC_TINY_O];
 #pragma unroll
       for (int i = 0; i < CC_TINY_O; ++i) ob[i] = (i < M.I) ? utb[i] * cc_ut_grad(M.ut, M.u_scale, a[i]) : 0.f;
-      cc_tiny_bwd(C, w, vc, a, ob, vb);
+      cc_ctrl_bwd(C, sh.wfc, sh.wgc, GP, tc, vc, keep, a, ob, lamc, vb);
 #pragma unroll
       for (int o = 0; o < CC_TINY_O; ++o) {
         yfb[o] = 0.f;
@@ -567,10 +582,18 @@ __global__ void __launch_bounds__(CC_TC_THREADS, 2) cc_tc_bwd_kernel(const CC_GR
       __syncwarp();
     }
     // gradient record of this warp tile (32 trajectories) -> workspace, reduced in fixed order afterwards
-    __syncwarp();
-    if (w.wt < p.n_wtiles) {
+    // (32 lanes reduced with a fixed xor tree -> deterministic)
+    {
       float* rec = p.gpart + w.wt * p.g_rec;
-      for (int e = lane; e < C.g_total; e += 32) rec[C.g_base + e] = cc_ws(w)[C.w_GP + e];
+      for (int row = 0; row < C.S + C.O; ++row) {
+        const int goff = row < C.S ? C.f.layer[0].g_off + row * C.K0 : C.g.layer[0].g_off + (row - C.S) * C.K0;
+        for (int r = 0; r < C.K0; ++r) {
+          float v = GP[(row * CC_CKU + cc_ctrl_col_of_row(C, r)) * 128];
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(CC_FULL, v, off);
+          if (lane == 0 && w.wt < p.n_wtiles) rec[C.g_base + goff + r] = v;
+        }
+      }
     }
   }
   CC_TC_EPILOGUE()
