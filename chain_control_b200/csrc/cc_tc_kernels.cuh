@@ -189,14 +189,20 @@ CC_DEV void cc_tc_stage_weights(const CcKParams& p, const CcNodeDev& M, const fl
   }
 }
 
-// one batch of 3 * KP/8 MMAs: D = A_lo.B_hi + A_hi.B_lo + A_hi.B_hi   (issued by ONE thread)
-CC_DEV void cc_tc_issue_batch(uint32_t tbase, int KP, int NP, uint32_t bhi, uint32_t blo, uint32_t idesc) {
+// one batch of 3 * NA MMAs: D = A_lo.B_hi + A_hi.B_lo + A_hi.B_hi   (issued by ONE thread; fully unrolled with
+// compile-time shapes so that an MMA costs a handful of instructions -- the issue rate of this thread bounds the batch)
+template <int NA, int NP>
+CC_DEV void cc_tc_issue_batch(uint32_t tbase, uint32_t bhi, uint32_t blo) {
+  constexpr int KP = 8 * NA;
+  constexpr uint32_t kstep = 2u * NP * 16u, lbo = NP * 16u;
+  constexpr uint32_t idesc = cc_umma_idesc_tf32(128, NP);
   const uint32_t aHi = tbase + NP, aLo = tbase + NP + KP;
-  const uint32_t kstep = 2u * NP * 16u, lbo = NP * 16u;
-  uint32_t accum = 0;
-  for (int js = 0; js < KP / 8; ++js) { cc_umma_tf32_ts(tbase, aLo + 8 * js, cc_umma_desc_kmajor(bhi + js * kstep, lbo, 128), idesc, accum); accum = 1; }
-  for (int js = 0; js < KP / 8; ++js) cc_umma_tf32_ts(tbase, aHi + 8 * js, cc_umma_desc_kmajor(blo + js * kstep, lbo, 128), idesc, 1);
-  for (int js = 0; js < KP / 8; ++js) cc_umma_tf32_ts(tbase, aHi + 8 * js, cc_umma_desc_kmajor(bhi + js * kstep, lbo, 128), idesc, 1);
+#pragma unroll
+  for (int js = 0; js < NA; ++js) cc_umma_tf32_ts(tbase, aLo + 8 * js, cc_umma_desc_kmajor(bhi + js * kstep, lbo, 128), idesc, js ? 1u : 0u);
+#pragma unroll
+  for (int js = 0; js < NA; ++js) cc_umma_tf32_ts(tbase, aHi + 8 * js, cc_umma_desc_kmajor(blo + js * kstep, lbo, 128), idesc, 1u);
+#pragma unroll
+  for (int js = 0; js < NA; ++js) cc_umma_tf32_ts(tbase, aHi + 8 * js, cc_umma_desc_kmajor(bhi + js * kstep, lbo, 128), idesc, 1u);
 }
 
 // prologue shared by both kernels: parameter copy, weight staging, barriers, TMEM allocation
@@ -257,6 +263,7 @@ struct CcTcIssue {
 };
 // publish the stage input just written to TMEM: all 128 threads arrive; warp 0 waits for the last arrival and
 // its lane 0 issues the MMA batch + commit (every thread then sleeps on d_ready until the batch has completed)
+template <int NCH, bool BWD>
 CC_DEV void cc_tc_publish(const CcTcShared& sh, CcTcIssue& q) {
   cc_tmem_wait_st();
   cc_tc_fence_before();
@@ -266,7 +273,11 @@ CC_DEV void cc_tc_publish(const CcTcShared& sh, CcTcIssue& q) {
     q.par_a ^= 1;
     cc_tc_fence_after();
     if (q.lane == 0) {
-      cc_tc_issue_batch(q.tbase, q.KP, q.NP, q.bhi, q.blo, q.idesc);
+      // shapes fixed by the host plan (cc_abi.cu): forward KP = 8*NCH (+8 with the extra tail chunk), NP = ceil16(8*NCH);
+      // backward KP = 8*NCH, NP = ceil16(8*NCH + 4)
+      constexpr int NP = BWD ? (8 * NCH + CC_TINY_O + 15) / 16 * 16 : (8 * NCH + 15) / 16 * 16;
+      if (q.KP == 8 * NCH) cc_tc_issue_batch<NCH, NP>(q.tbase, q.bhi, q.blo);
+      else cc_tc_issue_batch<NCH + 1, NP>(q.tbase, q.bhi, q.blo);
       cc_tc_commit(sh.d_ready);
     }
     __syncwarp();
@@ -378,7 +389,7 @@ __global__ void __launch_bounds__(CC_TC_THREADS, 2) cc_tc_fwd_kernel(const CC_GR
         for (int i = 0; i < CC_TINY_O; ++i) x[SR - 5 + i] = vt[i];
       }
       cc_tc_write_state<SR>(aHi, aLo, x, extra, vt);
-      cc_tc_publish(sh, q);
+      cc_tc_publish<NCH, false>(sh, q);
       // ---- work that overlaps the first MMA batch ----
       float y[CC_TINY_O];
       if (M.pre) cc_tc_readout<SR>(sh.gw, x, M.O, G.act, M.out_scale, y);  // compact: y = g(x) BEFORE the update
@@ -393,7 +404,7 @@ __global__ void __launch_bounds__(CC_TC_THREADS, 2) cc_tc_fwd_kernel(const CC_GR
       for (int st = 0; st < nst - 1; ++st) {
         cc_tc_await(sh, par);
         cc_tc_fwd_stage<SR, false, FACT>(aD, aHi, aLo, x, acc, F.act, h, st == 0 ? 1.f : 2.f, st == 2 ? 1.f : 0.5f, true);
-        cc_tc_publish(sh, q);
+        cc_tc_publish<NCH, false>(sh, q);
       }
       cc_tc_await(sh, par);
       cc_tc_fwd_stage<SR, true, FACT>(aD, aHi, aLo, x, acc, F.act, h, 0.f, 0.f, nst == 4);
@@ -542,7 +553,7 @@ __global__ void __launch_bounds__(CC_TC_THREADS, 2) cc_tc_bwd_kernel(const CC_GR
           cc_tc_store_split<8>(aHi, aLo, 8 * c, z);
         }
       }
-      cc_tc_publish(sh, q);
+      cc_tc_publish<NCH, true>(sh, q);
       // while the first MMA batch runs: recompute the controller step (its stage intermediates are kept)
       float a[CC_TINY_O];
       if (C.pre) cc_ctrl_readout_pre(C, sh.wgc, xcv, tc, vc, a);
@@ -554,7 +565,7 @@ __global__ void __launch_bounds__(CC_TC_THREADS, 2) cc_tc_bwd_kernel(const CC_GR
       for (int st = 3; st >= 1 && nst == 4; --st) {  // after z4bar: kbar3 = h/3 lam + h z4bar ; z3bar: kbar2 = h/3 lam + h/2 z3bar ; z2bar: kbar1 = h/6 lam + h/2 z2bar
         cc_tc_await(sh, par);
         cc_tc_bwd_stage<SR, false>(aD, aHi, aLo, lam, zsum, st == 1 ? h / 6.f : h / 3.f, st == 3 ? h : h / 2.f, utb);
-        cc_tc_publish(sh, q);
+        cc_tc_publish<NCH, true>(sh, q);
       }
       cc_tc_await(sh, par);
       cc_tc_bwd_stage<SR, true>(aD, aHi, aLo, lam, zsum, 0.f, 0.f, utb);

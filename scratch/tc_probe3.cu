@@ -6,7 +6,7 @@
 #include "../chain_control_b200/csrc/cc_tmem.cuh"
 #define KP 56
 #define NP 64
-struct Smem { float bhi[KP / 4 * NP * 4]; float blo[KP / 4 * NP * 4]; uint64_t a_ready[2]; uint64_t d_ready[2]; uint32_t tmem_base; };
+struct Smem { float bhi[KP / 4 * NP * 4]; float blo[KP / 4 * NP * 4]; uint64_t a_ready[2]; uint64_t d_ready[2]; uint32_t tmem_base; unsigned int lock; };
 constexpr uint32_t kIdesc = cc_umma_idesc_tf32(128, NP);
 __global__ void __launch_bounds__(320, 1) k(const float* A, const float* W, float* out, long long* ev, int reps, int n_tiles, int terms, int rec_it, int two_issuers) {
   extern __shared__ __align__(1024) unsigned char smraw[];
@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(320, 1) k(const float* A, const float* W, floa
     S.bhi[off] = hi; S.blo[off] = w - hi;
   }
   if (warp == 8) {
-    if (lane == 0) { for (int t = 0; t < 2; ++t) { cc_mbar_init(&S.a_ready[t], 128); cc_mbar_init(&S.d_ready[t], 1); } cc_mbar_fence_init(); }
+    if (lane == 0) { for (int t = 0; t < 2; ++t) { cc_mbar_init(&S.a_ready[t], 128); cc_mbar_init(&S.d_ready[t], 1); } S.lock = 0; cc_mbar_fence_init(); }
     __syncwarp();
     cc_tmem_alloc(&S.tmem_base, 512);
   }
@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(320, 1) k(const float* A, const float* W, floa
         if (r) e[0] = clock64();
         const uint32_t d = tbase + tile * 192, ahi = d + 64, alo = d + 128;
         uint32_t acc = 0;
+        if (two_issuers == 2) while (atomicCAS(&S.lock, 0u, 1u) != 0u) __nanosleep(32);
         if (terms >= 3) {
 #pragma unroll
           for (int js = 0; js < KP / 8; ++js) { cc_umma_tf32_ts(d, alo + js * 8, cc_umma_desc_kmajor(bhi + js * 2 * NP * 16, NP * 16, 128), kIdesc, acc); acc = 1; }
@@ -108,6 +109,7 @@ __global__ void __launch_bounds__(320, 1) k(const float* A, const float* W, floa
         for (int js = 0; js < KP / 8; ++js) { cc_umma_tf32_ts(d, ahi + js * 8, cc_umma_desc_kmajor(bhi + js * 2 * NP * 16, NP * 16, 128), kIdesc, acc); acc = 1; }
         if (r) e[1] = clock64();
         cc_tc_commit(&S.d_ready[tile]);
+        if (two_issuers == 2) atomicExch(&S.lock, 0u);
         if (r) e[2] = clock64();
       }
       par ^= 1;
@@ -127,7 +129,7 @@ int main() {
   cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(dW, W.data(), W.size() * 4, cudaMemcpyHostToDevice);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
-  for (int two = 0; two < 2; ++two) for (int nt = 2; nt <= 2; ++nt) for (int terms = 1; terms <= 3; terms += 2) {
+  for (int two = 1; two < 3; ++two) for (int nt = 2; nt <= 2; ++nt) for (int terms = 3; terms <= 3; terms += 2) {
     const int reps = 1000;
     cudaMemset(dE, 0, 4096);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
