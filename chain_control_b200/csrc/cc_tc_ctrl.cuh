@@ -10,6 +10,7 @@
 #pragma once
 #include "cc_kernels.cuh"
 
+#define CC_TC_LANES 128  // threads per CTA of the tcgen05 kernels = stride of the lane-private shared-memory columns
 #define CC_CK 16      // staged weight row length
 #define CC_CKU 14     // columns that can be non-zero
 #define CC_C_T 8      // column of t
@@ -164,6 +165,71 @@ CC_DEV void cc_ctrl_update(const CcNodeDev& C, const float* WF, const float* WG,
   } else {
 #pragma unroll
     for (int n = 0; n < CC_TINY_S; ++n) x[n] = xn[n];
+  }
+}
+
+// the same update one stage at a time (forward kernel: the stages of the compact controller are placed behind the
+// publishes of the model's stages, where they overlap the MMA batches):
+//   cc_ctrl_begin -> cc_ctrl_stage(st = 0 .. n_stages-1) -> cc_ctrl_finish
+struct CcCtrlRun {
+  CcCtrlIn in;              // current stage input
+  float ks[CC_TINY_S];      // k1 + 2 k2 + 2 k3 (+ k4)
+  float xn[CC_TINY_S];      // x_next (valid after the last stage)
+  float vt[CC_TINY_O];      // transformed input
+};
+CC_DEV int cc_ctrl_nstages(const CcNodeDev& C) { return C.integrator == CC_INT_RK4 ? 4 : 1; }
+CC_DEV void cc_ctrl_begin(const CcNodeDev& C, const float (&x)[CC_TINY_S], float t, const float (&v)[CC_TINY_O], CcCtrlRun& r) {
+#pragma unroll
+  for (int i = 0; i < CC_TINY_O; ++i) r.vt[i] = (i < C.I) ? cc_ut(C.ut, C.u_scale, v[i]) : 0.f;
+  cc_ctrl_make_in(x, t, r.vt, r.in);
+#pragma unroll
+  for (int n = 0; n < CC_TINY_S; ++n) { r.ks[n] = 0.f; r.xn[n] = 0.f; }
+}
+template <bool KEEP>
+CC_DEV void cc_ctrl_stage(const CcNodeDev& C, const float* WF, int st, const float (&x)[CC_TINY_S], float t, CcCtrlRun& r, float* keep) {
+  const float h = C.dt;
+  const int fact = C.f.layer[0].act;
+  float k[CC_TINY_S];
+  if (KEEP) {
+#pragma unroll
+    for (int n = 0; n < CC_TINY_S; ++n) keep[((CC_CKEEP_Z + st) * CC_TINY_S + n) * CC_TC_LANES] = r.in.c[n];
+  }
+  cc_ctrl_rhs(WF, C.S, fact, r.in, k);
+  if (KEEP && fact != CC_ACT_IDENTITY) {
+#pragma unroll
+    for (int n = 0; n < CC_TINY_S; ++n) keep[((CC_CKEEP_K + st) * CC_TINY_S + n) * CC_TC_LANES] = k[n];
+  }
+  if (C.integrator == CC_INT_RK4) {
+    // ks = k1 + 2 k2 + 2 k3 + k4 ; stage inputs x + h k / 2, x + h k / 2, x + h k ; x_next = x + h (1/6 ks)
+    const float wk = (st == 0 || st == 3) ? 1.f : 2.f;
+    const float cz = st == 2 ? 1.f : 0.5f;
+#pragma unroll
+    for (int n = 0; n < CC_TINY_S; ++n) {
+      r.ks[n] = fmaf(wk, k[n], r.ks[n]);
+      r.in.c[n] = x[n] + (h * k[n]) * cz;
+    }
+    r.in.c[CC_C_T] = st == 2 ? t + h : t + h / 2.f;  // stage times t, t+h/2, t+h/2, t+h
+    if (st == 3) {
+#pragma unroll
+      for (int n = 0; n < CC_TINY_S; ++n) r.xn[n] = x[n] + h * ((1.f / 6.f) * r.ks[n]);
+    }
+  } else {
+#pragma unroll
+    for (int n = 0; n < CC_TINY_S; ++n) r.xn[n] = C.integrator == CC_INT_EE ? x[n] + h * k[n] : k[n];
+  }
+}
+template <bool KEEP>
+CC_DEV void cc_ctrl_finish(const CcNodeDev& C, const float* WG, float (&x)[CC_TINY_S], float t, CcCtrlRun& r, float (&out)[CC_TINY_O], float* keep) {
+  if (!C.pre) {  // post-step readout g([x_next ; t ; v~]) with the PRE-step time
+    cc_ctrl_make_in(r.xn, t, r.vt, r.in);
+    cc_ctrl_readout(C, WG, r.in, out);
+  }
+  if (KEEP) {
+#pragma unroll
+    for (int n = 0; n < CC_TINY_S; ++n) keep[(CC_CKEEP_XN * CC_TINY_S + n) * CC_TC_LANES] = r.xn[n];
+  } else {
+#pragma unroll
+    for (int n = 0; n < CC_TINY_S; ++n) x[n] = r.xn[n];
   }
 }
 
