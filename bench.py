@@ -73,6 +73,11 @@ F_C = 2 * (4 * (5 + 2) * 5 + 5)       # 290
 F_M = 2 * (4 * (50 + 1) * 50 + 50)    # 20,500
 
 
+# dram read+write bytes per trajectory-step of cc_tc_bwd_kernel from the ncu --set full capture (profiles/r01_tc_ncu_full.md);
+# None until a capture of the current kernel exists
+TRAFFIC_TC_BWD_BYTES_PER_TS = 32.4  # (2.120 GB read + 0.008 GB written) / (65,536 x 1,001)
+
+
 def alg_flops(closed):
     fwd = F_C + F_M if closed else F_M
     tot = 3 * F_C + 2 * F_M if closed else 3 * F_M  # frozen model: forward + input-gradient only
@@ -80,17 +85,19 @@ def alg_flops(closed):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """nvidia-smi clocks / throttle reasons during the timed region (rows are time-stamped; only the rows that fall
+    inside [mark_start, mark_end] count - the sampler itself is started before the warm-up so that it is already running)."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -98,21 +105,32 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc:
+            time.sleep(0.05)
             self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        ok = [(t, r) for t, r in self.rows if len(r) >= 10 and r[2].replace(".", "").isdigit()]
+        inside = [r for t, r in ok if self.t0 is not None and self.t0 <= t <= (self.t1 or 1e30) + 0.02]
+        region = "timed region"
+        if not inside:  # timed region shorter than nvidia-smi's sampling period: fall back to everything seen under load
+            inside, region = [r for _, r in ok], "warm-up + timed region (timed region shorter than the sampling period)"
+        sm = [float(r[2]) for r in inside]
+        mx = [float(r[3]) for r in inside if r[3].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
-            if len(r) >= 9:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+        for r in inside:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[6:10]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": region}
 
 
 def cpu_baseline(closed, T, march="native", target_s=12.0):
@@ -252,12 +270,13 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ---------------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        step(x)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step(x)
     barrier()
+    sampler.mark_start()
     l0 = L.cc_launch_count()
     t_ev0, t_ev1 = ev(), ev()
     t_ev0.record()
@@ -267,6 +286,7 @@ def main():
         evs.append(e)
     t_ev1.record()
     barrier()
+    sampler.mark_end()
     launches = L.cc_launch_count() - l0
     ms = t_ev0.elapsed_time(t_ev1)
     for e in evs:
@@ -331,7 +351,44 @@ def main():
         hbm = peaks.get("hbm_gbs", 6650.0)
         # algorithmic HBM bytes per trajectory-step of the whole step: inputs/outputs/cotangent + tape write+read
         tape_rows = (5 + 1) if closed else 50  # closed loop: x_c and y_prev (the frozen linear model needs no state)
-        bytes_ts = 4 * (1 + 1 + 1 + 1 + 1) + 2 * 4 * tape_rows
+        bytes_ts = 4 * (1 + 1 + 1 + 1 + 1) + 2 * 4 * tape_rows  # refs, yhat (w), yhat+refs (mse r), ybar (w), ybar+refs (bwd r) + tape w+r
+        # ---- roofline of the dominant kernel -------------------------------------------------------
+        # closed loop (default): both kernels run on the tensor pipe (tcgen05, kind::tf32, 3xTF32 split for fp32 accuracy).
+        #   achieved = ALGORITHMIC FLOPs (2(n_st M_f + M_g) per trajectory-step, recomputation / splits / padding not
+        #   counted) / launch time; peak = dense TF32 rate = half the measured dense bf16 rate of MEASURED_PEAKS.json
+        #   (sustained figure: the kernel runs inside a long step).  `executed` counts what the pipe really does:
+        #   3 passes (lo.hi, hi.lo, hi.hi) over the padded 128 x 64 x 56 tiles, 4 stages per trajectory-step.
+        # open loop (cfg4): the reverse pass (weight gradients) is the FFMA kernel -> bound by the FP32 FMA pipe.
+        tensor = closed
+        bf16_peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 2250.0 * 0.62))
+        tf32_peak = bf16_peak / 2.0
+        exec_flops_ts = 3 * 2 * 64 * 56 * 4  # per trajectory-step of one rollout kernel (forward or reverse): 3 x 2 x NP x KP x stages
+        if tensor:
+            roofline = {"bound": "tensor", "kernel": "cc_tc_bwd_kernel", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
+                        "frac": achieved / tf32_peak,
+                        "traffic": TRAFFIC_TC_BWD_BYTES_PER_TS * units if TRAFFIC_TC_BWD_BYTES_PER_TS else None,
+                        "traffic_source": "ncu --set full capture of the same kernel (profiles/r01_tc_ncu_full.md), dram read+write per trajectory-step x units of this launch",
+                        "peak_source": "MEASURED_PEAKS.json dense bf16 (sustained) / 2 = dense TF32; the kernel issues tcgen05.mma kind::tf32",
+                        "alg_flops_per_traj_step": tot_f - fwd_f, "launch_ms": bwd_ms,
+                        "executed": {"tflops": units * exec_flops_ts / (bwd_ms * 1e-3) / 1e12, "frac": units * exec_flops_ts / (bwd_ms * 1e-3) / 1e12 / tf32_peak,
+                                     "flops_per_traj_step": exec_flops_ts,
+                                     "note": "3xTF32 split (fp32-accurate products) over 128 x 64 x 56 padded tiles; 4.2x the algorithmic count"},
+                        "fp32_fma": {"peak": peak_tflops, "frac": achieved / peak_tflops, "peak_register_tile": regtile_tflops,
+                                     "note": "BASELINE.json's yardstick: algorithmic TFLOP/s over the FP32 FMA peak (FFMA-chain probe measured live; nominal 74.4)"},
+                        "fwd_kernel": {"kernel": "cc_tc_fwd_kernel", "achieved": units * fwd_f / (fwd_ms * 1e-3) / 1e12, "launch_ms": fwd_ms, "alg_flops_per_traj_step": fwd_f,
+                                       "frac": units * fwd_f / (fwd_ms * 1e-3) / 1e12 / tf32_peak, "frac_of_fp32_fma_peak": units * fwd_f / (fwd_ms * 1e-3) / 1e12 / peak_tflops},
+                        "step": {"achieved": units * tot_f / ((fwd_ms + bwd_ms) * 1e-3) / 1e12, "alg_flops_per_traj_step": tot_f,
+                                 "frac_of_fp32_fma_peak": units * tot_f / ((fwd_ms + bwd_ms) * 1e-3) / 1e12 / peak_tflops},
+                        "hbm": {"achieved_gbs": units * bytes_ts / ((fwd_ms + bwd_ms) * 1e-3) / 1e9, "peak_gbs": hbm, "alg_bytes_per_traj_step": bytes_ts}}
+        else:
+            roofline = {"bound": "fp32", "kernel": "cc_rollout_bwd_kernel", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+                        "frac": achieved / peak_tflops, "traffic": None,
+                        "peak_source": "FFMA-chain probe measured live in this run (MEASURED_PEAKS.json carries no FP32 figure; nominal 74.4)",
+                        "peak_register_tile": regtile_tflops,
+                        "alg_flops_per_traj_step": tot_f - fwd_f, "launch_ms": bwd_ms,
+                        "fwd_kernel": {"kernel": "cc_tc_fwd_kernel", "achieved": units * fwd_f / (fwd_ms * 1e-3) / 1e12, "launch_ms": fwd_ms, "alg_flops_per_traj_step": fwd_f},
+                        "step": {"achieved": units * tot_f / ((fwd_ms + bwd_ms) * 1e-3) / 1e12, "alg_flops_per_traj_step": tot_f},
+                        "hbm": {"achieved_gbs": units * bytes_ts / ((fwd_ms + bwd_ms) * 1e-3) / 1e9, "peak_gbs": hbm, "alg_bytes_per_traj_step": bytes_ts}}
         out = {
             "metric": ("closed-loop " if closed else "") + "neural-ODE traj-steps/s (fwd+BPTT)",
             "value": world * units * args.steps / (ms * 1e-3), "unit": "traj-steps/s", "n_gpus": world, "steps": args.steps,
@@ -341,6 +398,7 @@ def main():
                                     "cfg2": "configs[1]: closed-loop ControllerTrainer BPTT, 64 trajectories x 1001 steps",
                                     "cfg4": "configs[3]: ModelTrainer step, 65536 trajectories per GPU x 1000 steps, S=50 depth 0"}[args.workload],
                        "B_per_gpu": B, "T": T, "closed_loop": closed, "integrator": "RK4", "ckpt_every": 1,
+                       "kernels": "tcgen05 (3xTF32, A in tensor memory) forward" + (" and reverse pass" if closed else "; FFMA reverse pass (weight gradients)"),
                        "step": "fwd rollout + mse cotangent + BPTT + grad reduce" + (" + NCCL allreduce(P+1)" if world > 1 else "") + " + adam",
                        "l2": "inputs+tape (>= 0.26 GB + %.1f GB) exceed the 126 MB L2" % (2 * 4 * tape_rows * units / 2 / 1e9),
                        "loss": loss_val},
@@ -348,15 +406,7 @@ def main():
                     "h2d_bytes_per_step": int(host_in.numel() * 4), "d2h_bytes_per_step": int((P + 1) * 4)},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "fp32", "kernel": "cc_rollout_bwd_kernel", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tflops, "traffic": None,
-                         "peak_source": "FFMA-chain probe measured live in this run (MEASURED_PEAKS.json carries no FP32 figure; nominal 74.4)",
-                         "peak_register_tile": regtile_tflops,
-                         "peak_register_tile_note": "same probe with three register operands per FFMA (acc[i][j] += x[i]*y[j]): the practical ceiling of any register-tiled CUDA-core kernel on this part",
-                         "alg_flops_per_traj_step": tot_f - fwd_f, "launch_ms": bwd_ms,
-                         "fwd_kernel": {"achieved": units * fwd_f / (fwd_ms * 1e-3) / 1e12, "launch_ms": fwd_ms, "alg_flops_per_traj_step": fwd_f},
-                         "step": {"achieved": units * tot_f / ((fwd_ms + bwd_ms) * 1e-3) / 1e12, "alg_flops_per_traj_step": tot_f},
-                         "hbm": {"achieved_gbs": units * bytes_ts / ((fwd_ms + bwd_ms) * 1e-3) / 1e9, "peak_gbs": hbm, "alg_bytes_per_traj_step": bytes_ts}},
+            "roofline": roofline,
         }
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(closed, T)
