@@ -24,7 +24,13 @@ int launch_tc(Kern kern, const CcKParams& p, bool bwd, void* stream, char* err, 
 }
 }  // namespace
 
-#define CC_TC_FWD(NCH, CM, FACT) launch_tc(cc_tc_fwd_kernel<NCH, CM, FACT>, p, false, stream, err, errlen)
+// CFG = 521: the compact controller's shape (S_c = 5, 2 inputs, 1 output, time-invariant) as compile-time constants
+static int ctrl_cfg(const CcKParams& p) {
+  const CcNodeDev& C = p.nd[0];
+  return (p.n_nodes == 2 && C.S == 5 && C.I == 2 && C.O == 1 && !C.has_t) ? 521 : 0;
+}
+#define CC_TC_FWD(NCH, CM, FACT) (ctrl_cfg(p) == 521 && CM == CC_CTRL_TINY ? launch_tc(cc_tc_fwd_kernel<NCH, CM, FACT, (CM == CC_CTRL_TINY ? 521 : 0)>, p, false, stream, err, errlen) \
+                                                                           : launch_tc(cc_tc_fwd_kernel<NCH, CM, FACT, 0>, p, false, stream, err, errlen))
 int cc_launch_fwd_tc(const CcKParams& p, void* stream, char* err, int errlen) {
   const bool closed = p.n_nodes == 2;
   const bool fact = p.nd[p.n_nodes - 1].f.layer[0].act != CC_ACT_IDENTITY;  // non-linear final activation of f: separate instantiation
@@ -36,6 +42,7 @@ int cc_launch_fwd_tc(const CcKParams& p, void* stream, char* err, int errlen) {
   return closed ? CC_TC_FWD(7, CC_CTRL_TINY, false) : CC_TC_FWD(7, CC_CTRL_NONE, false);
 }
 int cc_launch_bwd_tc(const CcKParams& p, void* stream, char* err, int errlen) {
-  if (p.tc_nch == 4) return launch_tc(cc_tc_bwd_kernel<4, CC_CTRL_TINY>, p, true, stream, err, errlen);
-  return launch_tc(cc_tc_bwd_kernel<7, CC_CTRL_TINY>, p, true, stream, err, errlen);
+  const bool c521 = ctrl_cfg(p) == 521;
+  if (p.tc_nch == 4) return c521 ? launch_tc(cc_tc_bwd_kernel<4, CC_CTRL_TINY, 521>, p, true, stream, err, errlen) : launch_tc(cc_tc_bwd_kernel<4, CC_CTRL_TINY, 0>, p, true, stream, err, errlen);
+  return c521 ? launch_tc(cc_tc_bwd_kernel<7, CC_CTRL_TINY, 521>, p, true, stream, err, errlen) : launch_tc(cc_tc_bwd_kernel<7, CC_CTRL_TINY, 0>, p, true, stream, err, errlen);
 }

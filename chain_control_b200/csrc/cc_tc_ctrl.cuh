@@ -17,6 +17,26 @@
 #define CC_C_V 9      // first column of v
 #define CC_C_ONE 13   // column of the constant 1
 
+// the controller's shape and options as seen by the device functions below.  For the common compact controller
+// (S_c = 5, [ref ; obs] = 2 inputs, 1 output, time-invariant: CFG = 521) the sizes are compile-time constants, so the
+// per-row `if (n < S)` branches fold and the rows of a stage become one basic block the scheduler can interleave.
+struct CcCtrlDims {
+  int S, I, O, has_t, pre, integrator, ut, f_act, g_act;
+  float u_scale, out_scale, dt;
+};
+template <int CFG>
+CC_DEV CcCtrlDims cc_ctrl_dims(const CcNodeDev& C) {
+  CcCtrlDims d;
+  d.S = CFG ? CFG / 100 : C.S;
+  d.I = CFG ? (CFG / 10) % 10 : C.I;
+  d.O = CFG ? CFG % 10 : C.O;
+  d.has_t = CFG ? 0 : C.has_t;
+  d.pre = C.pre; d.integrator = C.integrator; d.ut = C.ut;
+  d.f_act = C.f.layer[0].act; d.g_act = C.g.layer[0].act;
+  d.u_scale = C.u_scale; d.out_scale = C.out_scale; d.dt = C.dt;
+  return d;
+}
+
 // node-layout physical row r of [x ; t ; v ; 1]  ->  fixed column
 CC_DEV int cc_ctrl_col_of_row(const CcNodeDev& C, int r) {
   if (r < C.S) return r;
@@ -63,28 +83,36 @@ CC_DEV void cc_ctrl_load_row(const float* row, float (&w)[CC_CK]) {
     w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
   }
 }
-CC_DEV float cc_ctrl_dot(const float* row, const CcCtrlIn& in) {
+// is column k fed by this controller? (compile-time for CFG shapes)
+CC_DEV bool cc_ctrl_live(const CcCtrlDims& C, int k) {
+  return k < C.S || (k == CC_C_T && C.has_t) || (k >= CC_C_V && k < CC_C_V + C.I) || k == CC_C_ONE;
+}
+CC_DEV float cc_ctrl_dot(const CcCtrlDims& C, const float* row, const CcCtrlIn& in) {
   float w[CC_CK];
   cc_ctrl_load_row(row, w);
   float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-  for (int k = 0; k < CC_CKU; k += 2) { s0 = fmaf(w[k], in.c[k], s0); s1 = fmaf(w[k + 1], in.c[k + 1], s1); }
+  for (int k = 0; k < CC_CKU; k += 2) {
+    if (cc_ctrl_live(C, k)) s0 = fmaf(w[k], in.c[k], s0);
+    if (cc_ctrl_live(C, k + 1)) s1 = fmaf(w[k + 1], in.c[k + 1], s1);
+  }
   return s0 + s1;
 }
 // k = act(WF . in) for the S state components (zero beyond)
-CC_DEV void cc_ctrl_rhs(const float* WF, int S, int fact, const CcCtrlIn& in, float (&k)[CC_TINY_S]) {
+CC_DEV void cc_ctrl_rhs(const CcCtrlDims& C, const float* WF, const CcCtrlIn& in, float (&k)[CC_TINY_S]) {
+  const int S = C.S, fact = C.f_act;
 #pragma unroll
   for (int n = 0; n < CC_TINY_S; ++n) {
     k[n] = 0.f;
-    if (n < S) k[n] = cc_act(fact, cc_ctrl_dot(WF + n * CC_CK, in));
+    if (n < S) k[n] = cc_act(fact, cc_ctrl_dot(C, WF + n * CC_CK, in));
   }
 }
-CC_DEV void cc_ctrl_readout(const CcNodeDev& C, const float* WG, const CcCtrlIn& in, float (&out)[CC_TINY_O]) {
-  const int gact = C.g.layer[0].act;
+CC_DEV void cc_ctrl_readout(const CcCtrlDims& C, const float* WG, const CcCtrlIn& in, float (&out)[CC_TINY_O]) {
+  const int gact = C.g_act;
 #pragma unroll
   for (int o = 0; o < CC_TINY_O; ++o) {
     out[o] = 0.f;
-    if (o < C.O) out[o] = C.out_scale * cc_act(gact, cc_ctrl_dot(WG + o * CC_CK, in));
+    if (o < C.O) out[o] = C.out_scale * cc_act(gact, cc_ctrl_dot(C, WG + o * CC_CK, in));
   }
 }
 
@@ -94,10 +122,10 @@ CC_DEV void cc_ctrl_readout(const CcNodeDev& C, const float* WG, const CcCtrlIn&
 #define CC_CKEEP_Z 0
 #define CC_CKEEP_XN 4
 #define CC_CKEEP_K 5
-CC_DEV int cc_ctrl_keep_floats(const CcNodeDev& C) { return (C.f.layer[0].act != CC_ACT_IDENTITY ? 9 : 5) * CC_TINY_S * 128; }
+CC_DEV int cc_ctrl_keep_floats(const CcCtrlDims& C) { return (C.f_act != CC_ACT_IDENTITY ? 9 : 5) * CC_TINY_S * 128; }
 
 // pre-step readout only:  out = out_scale * g([x ; t ; v~])      (compact controller: before the state update)
-CC_DEV void cc_ctrl_readout_pre(const CcNodeDev& C, const float* WG, const float (&x)[CC_TINY_S], float t, const float (&v)[CC_TINY_O], float (&out)[CC_TINY_O]) {
+CC_DEV void cc_ctrl_readout_pre(const CcCtrlDims& C, const float* WG, const float (&x)[CC_TINY_S], float t, const float (&v)[CC_TINY_O], float (&out)[CC_TINY_O]) {
   float vt[CC_TINY_O];
 #pragma unroll
   for (int i = 0; i < CC_TINY_O; ++i) vt[i] = (i < C.I) ? cc_ut(C.ut, C.u_scale, v[i]) : 0.f;
@@ -110,10 +138,10 @@ CC_DEV void cc_ctrl_readout_pre(const CcNodeDev& C, const float* WG, const float
 // KEEP (reverse pass): the stages are recorded in `keep` (lane-private column) and x is left untouched.
 // One stage body, executed n_stages times with run-time coefficients (small code: the instruction cache matters).
 template <bool KEEP>
-CC_DEV void cc_ctrl_update(const CcNodeDev& C, const float* WF, const float* WG, float (&x)[CC_TINY_S], float t, const float (&v)[CC_TINY_O],
+CC_DEV void cc_ctrl_update(const CcCtrlDims& C, const float* WF, const float* WG, float (&x)[CC_TINY_S], float t, const float (&v)[CC_TINY_O],
                            float (&out)[CC_TINY_O], float* keep) {
   const float h = C.dt;
-  const int fact = C.f.layer[0].act;
+  const int fact = C.f_act;
   const bool rk4 = C.integrator == CC_INT_RK4;
   const int nst = rk4 ? 4 : 1;
   float vt[CC_TINY_O];
@@ -131,7 +159,7 @@ CC_DEV void cc_ctrl_update(const CcNodeDev& C, const float* WF, const float* WG,
 #pragma unroll
       for (int n = 0; n < CC_TINY_S; ++n) keep[((CC_CKEEP_Z + st) * CC_TINY_S + n) * 128] = in.c[n];
     }
-    cc_ctrl_rhs(WF, C.S, fact, in, k);
+    cc_ctrl_rhs(C, WF, in, k);
     if (KEEP && fact != CC_ACT_IDENTITY) {
 #pragma unroll
       for (int n = 0; n < CC_TINY_S; ++n) keep[((CC_CKEEP_K + st) * CC_TINY_S + n) * 128] = k[n];
@@ -177,8 +205,8 @@ struct CcCtrlRun {
   float xn[CC_TINY_S];      // x_next (valid after the last stage)
   float vt[CC_TINY_O];      // transformed input
 };
-CC_DEV int cc_ctrl_nstages(const CcNodeDev& C) { return C.integrator == CC_INT_RK4 ? 4 : 1; }
-CC_DEV void cc_ctrl_begin(const CcNodeDev& C, const float (&x)[CC_TINY_S], float t, const float (&v)[CC_TINY_O], CcCtrlRun& r) {
+CC_DEV int cc_ctrl_nstages(const CcCtrlDims& C) { return C.integrator == CC_INT_RK4 ? 4 : 1; }
+CC_DEV void cc_ctrl_begin(const CcCtrlDims& C, const float (&x)[CC_TINY_S], float t, const float (&v)[CC_TINY_O], CcCtrlRun& r) {
 #pragma unroll
   for (int i = 0; i < CC_TINY_O; ++i) r.vt[i] = (i < C.I) ? cc_ut(C.ut, C.u_scale, v[i]) : 0.f;
   cc_ctrl_make_in(x, t, r.vt, r.in);
@@ -186,15 +214,15 @@ CC_DEV void cc_ctrl_begin(const CcNodeDev& C, const float (&x)[CC_TINY_S], float
   for (int n = 0; n < CC_TINY_S; ++n) { r.ks[n] = 0.f; r.xn[n] = 0.f; }
 }
 template <bool KEEP>
-CC_DEV void cc_ctrl_stage(const CcNodeDev& C, const float* WF, int st, const float (&x)[CC_TINY_S], float t, CcCtrlRun& r, float* keep) {
+CC_DEV void cc_ctrl_stage(const CcCtrlDims& C, const float* WF, int st, const float (&x)[CC_TINY_S], float t, CcCtrlRun& r, float* keep) {
   const float h = C.dt;
-  const int fact = C.f.layer[0].act;
+  const int fact = C.f_act;
   float k[CC_TINY_S];
   if (KEEP) {
 #pragma unroll
     for (int n = 0; n < CC_TINY_S; ++n) keep[((CC_CKEEP_Z + st) * CC_TINY_S + n) * CC_TC_LANES] = r.in.c[n];
   }
-  cc_ctrl_rhs(WF, C.S, fact, r.in, k);
+  cc_ctrl_rhs(C, WF, r.in, k);
   if (KEEP && fact != CC_ACT_IDENTITY) {
 #pragma unroll
     for (int n = 0; n < CC_TINY_S; ++n) keep[((CC_CKEEP_K + st) * CC_TINY_S + n) * CC_TC_LANES] = k[n];
@@ -219,7 +247,7 @@ CC_DEV void cc_ctrl_stage(const CcNodeDev& C, const float* WF, int st, const flo
   }
 }
 template <bool KEEP>
-CC_DEV void cc_ctrl_finish(const CcNodeDev& C, const float* WG, float (&x)[CC_TINY_S], float t, CcCtrlRun& r, float (&out)[CC_TINY_O], float* keep) {
+CC_DEV void cc_ctrl_finish(const CcCtrlDims& C, const float* WG, float (&x)[CC_TINY_S], float t, CcCtrlRun& r, float (&out)[CC_TINY_O], float* keep) {
   if (!C.pre) {  // post-step readout g([x_next ; t ; v~]) with the PRE-step time
     cc_ctrl_make_in(r.xn, t, r.vt, r.in);
     cc_ctrl_readout(C, WG, r.in, out);
@@ -248,11 +276,11 @@ CC_DEV void cc_ctrl_gacc(float* GP, int row, const float d, const CcCtrlIn& in, 
 
 // reverse pass of one controller step.  keep: record of cc_ctrl_update<true>; out: the step's output; ob: its
 // cotangent; lam: cotangent of x_next (in) / of x (out); vb: cotangent of the raw input
-CC_DEV void cc_ctrl_bwd(const CcNodeDev& C, const float* WF, const float* WG, float* GP, float t, const float (&v)[CC_TINY_O],
+CC_DEV void cc_ctrl_bwd(const CcCtrlDims& C, const float* WF, const float* WG, float* GP, float t, const float (&v)[CC_TINY_O],
                         const float* keep, const float (&out)[CC_TINY_O], const float (&ob)[CC_TINY_O], float (&lam)[CC_TINY_S],
                         float (&vb)[CC_TINY_O]) {
   const float h = C.dt;
-  const int fact = C.f.layer[0].act, gact = C.g.layer[0].act;
+  const int fact = C.f_act, gact = C.g_act;
   float vt[CC_TINY_O];
 #pragma unroll
   for (int i = 0; i < CC_TINY_O; ++i) { vt[i] = (i < C.I) ? cc_ut(C.ut, C.u_scale, v[i]) : 0.f; vb[i] = 0.f; }
@@ -321,7 +349,8 @@ CC_DEV void cc_ctrl_bwd(const CcNodeDev& C, const float* WF, const float* WG, fl
         float w[CC_CK];
         cc_ctrl_load_row(WF + n * CC_CK, w);
 #pragma unroll
-        for (int k = 0; k < CC_CKU; ++k) acc[k] = fmaf(w[k], kb, acc[k]);
+        for (int k = 0; k < CC_CKU; ++k)
+          if (cc_ctrl_live(C, k)) acc[k] = fmaf(w[k], kb, acc[k]);
         cc_ctrl_gacc(GP, n, kb, in, C.S, C.has_t != 0, C.I);
       }
     }

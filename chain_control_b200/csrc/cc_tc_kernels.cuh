@@ -294,9 +294,10 @@ CC_DEV void cc_tc_await(const CcTcShared& sh, uint32_t& par) {
 // ------------------------------------------------------------------------------------------------
 // K1 + K3 on tcgen05: forward rollout.  CM: CC_CTRL_NONE (open loop) or CC_CTRL_TINY (closed loop).
 // ------------------------------------------------------------------------------------------------
-template <int NCH, int CM, bool FACT>
+template <int NCH, int CM, bool FACT, int CFG>
 __global__ void __launch_bounds__(CC_TC_THREADS, 2) cc_tc_fwd_kernel(const CC_GRID_CONSTANT CcKParams gp) {
   CC_TC_PROLOGUE(gp, false)
+  const CcCtrlDims CD = cc_ctrl_dims<CFG>(C);
   const int nst = M.integrator == CC_INT_RK4 ? 4 : 1;
   {
     CcWarp w;
@@ -369,8 +370,8 @@ __global__ void __launch_bounds__(CC_TC_THREADS, 2) cc_tc_fwd_kernel(const CC_GR
           for (int s = 0; s < SR; ++s)
             if (s < M.S) p.tape[((long long)ck * p.tape_rows + M.tape_row + s) * p.Bpad + b] = x[s];
         // compact controller: u = out_scale * g_c(x_c) needs no state update -> the update overlaps the first MMA batch
-        if (C.pre) cc_ctrl_readout_pre(C, sh.wgc, xc, tc, vc, a);
-        else cc_ctrl_update<false>(C, sh.wfc, sh.wgc, xc, tc, vc, a, nullptr);
+        if (C.pre) cc_ctrl_readout_pre(CD, sh.wgc, xc, tc, vc, a);
+        else cc_ctrl_update<false>(CD, sh.wfc, sh.wgc, xc, tc, vc, a, nullptr);
         if (p.u_out && act)
 #pragma unroll
           for (int i = 0; i < CC_TINY_O; ++i)
@@ -397,16 +398,16 @@ __global__ void __launch_bounds__(CC_TC_THREADS, 2) cc_tc_fwd_kernel(const CC_GR
       if (M.pre) cc_tc_readout<SR>(sh.gw, x, M.O, G.act, M.out_scale, y);  // compact: y = g(x) BEFORE the update
       // compact controller: its state update runs one stage per MMA window (the readout above needed only x_c)
       CcCtrlRun crun;
-      const int nstc = closed ? cc_ctrl_nstages(C) : 0;
+      const int nstc = closed ? cc_ctrl_nstages(CD) : 0;
       const bool cpipe = closed && C.pre;
       int cst = 0;
       // window j (after the j-th publish of the step): a warp that is not issuing runs up to two controller stages,
       // staying at most one stage ahead (cst < j + 2) -> every warp is done before the step's last window
       int win = 0;
       if (cpipe) {
-        cc_ctrl_begin(C, xc, tc, vc, crun);
+        cc_ctrl_begin(CD, xc, tc, vc, crun);
         if (warp != (int)((q.batch - 1u) & 3u))
-          for (int c2 = 0; c2 < 2 && cst < nstc && cst < win + 2; ++c2) cc_ctrl_stage<false>(C, sh.wfc, cst++, xc, tc, crun, nullptr);
+          for (int c2 = 0; c2 < 2 && cst < nstc && cst < win + 2; ++c2) cc_ctrl_stage<false>(CD, sh.wfc, cst++, xc, tc, crun, nullptr);
       }
 #pragma unroll 1
       for (int st = 0; st < nst - 1; ++st) {
@@ -415,13 +416,13 @@ __global__ void __launch_bounds__(CC_TC_THREADS, 2) cc_tc_fwd_kernel(const CC_GR
         cc_tc_publish<NCH, false>(sh, q);
         ++win;
         if (cpipe && warp != (int)((q.batch - 1u) & 3u))
-          for (int c2 = 0; c2 < 2 && cst < nstc && cst < win + 2; ++c2) cc_ctrl_stage<false>(C, sh.wfc, cst++, xc, tc, crun, nullptr);
+          for (int c2 = 0; c2 < 2 && cst < nstc && cst < win + 2; ++c2) cc_ctrl_stage<false>(CD, sh.wfc, cst++, xc, tc, crun, nullptr);
       }
       if (cpipe) {
 #pragma unroll 1
-        for (; cst < nstc; ++cst) cc_ctrl_stage<false>(C, sh.wfc, cst, xc, tc, crun, nullptr);
+        for (; cst < nstc; ++cst) cc_ctrl_stage<false>(CD, sh.wfc, cst, xc, tc, crun, nullptr);
         float dummy[CC_TINY_O];
-        cc_ctrl_finish<false>(C, sh.wgc, xc, tc, crun, dummy, nullptr);
+        cc_ctrl_finish<false>(CD, sh.wgc, xc, tc, crun, dummy, nullptr);
       }
       if (closed && C.has_t) tc = tc + C.dt;
       cc_tc_await(sh, par);
@@ -491,9 +492,10 @@ CC_DEV void cc_tc_bwd_stage(uint32_t aD, uint32_t aHi, uint32_t aLo, float (&lam
   for (int i = 0; i < CC_TINY_O; ++i) utb[i] += __uint_as_float(r[i]);
 }
 
-template <int NCH, int CM>
+template <int NCH, int CM, int CFG>
 __global__ void __launch_bounds__(CC_TC_THREADS, 2) cc_tc_bwd_kernel(const CC_GRID_CONSTANT CcKParams gp) {
   CC_TC_PROLOGUE(gp, true)
+  const CcCtrlDims CD = cc_ctrl_dims<CFG>(C);
   const int nst = M.integrator == CC_INT_RK4 ? 4 : 1;
   {
     CcWarp w;
@@ -574,8 +576,8 @@ __global__ void __launch_bounds__(CC_TC_THREADS, 2) cc_tc_bwd_kernel(const CC_GR
       cc_tc_publish<NCH, true>(sh, q);
       // while the first MMA batch runs: recompute the controller step (its stage intermediates are kept)
       float a[CC_TINY_O];
-      if (C.pre) cc_ctrl_readout_pre(C, sh.wgc, xcv, tc, vc, a);
-      cc_ctrl_update<true>(C, sh.wfc, sh.wgc, xcv, tc, vc, a, keep);
+      if (C.pre) cc_ctrl_readout_pre(CD, sh.wgc, xcv, tc, vc, a);
+      cc_ctrl_update<true>(CD, sh.wfc, sh.wgc, xcv, tc, vc, a, keep);
       float utb[CC_TINY_O];
 #pragma unroll
       for (int i = 0; i < CC_TINY_O; ++i) utb[i] = 0.f;
@@ -600,7 +602,7 @@ __global__ void __launch_bounds__(CC_TC_THREADS, 2) cc_tc_bwd_kernel(const CC_GR
       float ob[CC_TINY_O], vb[CC_TINY_O];
 #pragma unroll
       for (int i = 0; i < CC_TINY_O; ++i) ob[i] = (i < M.I) ? utb[i] * cc_ut_grad(M.ut, M.u_scale, a[i]) : 0.f;
-      cc_ctrl_bwd(C, sh.wfc, sh.wgc, GP, tc, vc, keep, a, ob, lamc, vb);
+      cc_ctrl_bwd(CD, sh.wfc, sh.wgc, GP, tc, vc, keep, a, ob, lamc, vb);
 #pragma unroll
       for (int o = 0; o < CC_TINY_O; ++o) {
         yfb[o] = 0.f;
