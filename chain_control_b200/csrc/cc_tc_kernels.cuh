@@ -47,10 +47,13 @@ CC_DEV void cc_tc_store_split(uint32_t aHi, uint32_t aLo, int c0, const float (&
   for (int j = 0; j < NC / 8; ++j) {
     uint32_t hi[8], lo[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float v = z[8 * j + i];
-      hi[i] = __float_as_uint(v) & 0xFFFFE000u;
-      lo[i] = __float_as_uint(v - __uint_as_float(hi[i]));
+    for (int i = 0; i < 8; i += 2) {  // packed fp32x2 subtract (FADD2): lo = z - hi, exact
+      const float v0 = z[8 * j + i], v1 = z[8 * j + i + 1];
+      hi[i] = __float_as_uint(v0) & 0xFFFFE000u;
+      hi[i + 1] = __float_as_uint(v1) & 0xFFFFE000u;
+      const float2 l = __fadd2_rn(make_float2(v0, v1), make_float2(-__uint_as_float(hi[i]), -__uint_as_float(hi[i + 1])));
+      lo[i] = __float_as_uint(l.x);
+      lo[i + 1] = __float_as_uint(l.y);
     }
     cc_tmem_st8(aHi + c0 + 8 * j, hi);
     cc_tmem_st8(aLo + c0 + 8 * j, lo);
@@ -68,17 +71,22 @@ CC_DEV void cc_tc_fwd_group(uint32_t aD, uint32_t aHi, uint32_t aLo, float (&x)[
   cc_tc_ld<NC>(aD + C0, r);
   cc_tmem_wait_ld();
   float z[NC];
+  const float2 h2 = make_float2(h, h), wk2 = make_float2(wk, wk), cz2 = make_float2(cz, cz);
 #pragma unroll
-  for (int i = 0; i < NC; ++i) {
-    float k = __uint_as_float(r[i]);
-    if (FACT) k = cc_act(fact, k);
+  for (int i = 0; i < NC; i += 2) {  // two columns per instruction: packed fp32x2 FMUL2 / FFMA2 (same rounding as the scalar forms)
+    float2 k = make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+    if (FACT) { k.x = cc_act(fact, k.x); k.y = cc_act(fact, k.y); }
     if (!FINAL) {
-      acc[C0 + i] = fmaf(wk, k, acc[C0 + i]);
-      z[i] = x[C0 + i] + (h * k) * cz;
+      const float2 a = __ffma2_rn(wk2, k, make_float2(acc[C0 + i], acc[C0 + i + 1]));
+      acc[C0 + i] = a.x; acc[C0 + i + 1] = a.y;
+      const float2 zz = __ffma2_rn(__fmul2_rn(h2, k), cz2, make_float2(x[C0 + i], x[C0 + i + 1]));
+      z[i] = zz.x; z[i + 1] = zz.y;
     } else {
-      const float s = rk4 ? (1.f / 6.f) * (acc[C0 + i] + k) : k;
-      x[C0 + i] = x[C0 + i] + h * s;
-      acc[C0 + i] = 0.f;
+      float2 s = k;
+      if (rk4) s = __fmul2_rn(make_float2(1.f / 6.f, 1.f / 6.f), __fadd2_rn(make_float2(acc[C0 + i], acc[C0 + i + 1]), k));
+      const float2 xn = __ffma2_rn(h2, s, make_float2(x[C0 + i], x[C0 + i + 1]));
+      x[C0 + i] = xn.x; x[C0 + i + 1] = xn.y;
+      acc[C0 + i] = 0.f; acc[C0 + i + 1] = 0.f;
     }
   }
   if (!FINAL) cc_tc_store_split<NC>(aHi, aLo, C0, z);
@@ -465,15 +473,19 @@ CC_DEV void cc_tc_bwd_group(uint32_t aD, uint32_t aHi, uint32_t aLo, float (&lam
   cc_tc_ld<NC>(aD + C0, r);
   cc_tmem_wait_ld();
   float kb[NC];
+  const float2 ca2 = make_float2(ca, ca), cb2 = make_float2(cb, cb);
 #pragma unroll
-  for (int i = 0; i < NC; ++i) {
-    const float zb = __uint_as_float(r[i]);
+  for (int i = 0; i < NC; i += 2) {
+    const float2 zb = make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1]));
     if (!FINAL) {
-      zsum[C0 + i] += zb;
-      kb[i] = ca * lam[C0 + i] + cb * zb;
+      const float2 zs = __fadd2_rn(make_float2(zsum[C0 + i], zsum[C0 + i + 1]), zb);
+      zsum[C0 + i] = zs.x; zsum[C0 + i + 1] = zs.y;
+      const float2 kk = __ffma2_rn(ca2, make_float2(lam[C0 + i], lam[C0 + i + 1]), __fmul2_rn(cb2, zb));
+      kb[i] = kk.x; kb[i + 1] = kk.y;
     } else {
-      lam[C0 + i] = lam[C0 + i] + (zsum[C0 + i] + zb);
-      zsum[C0 + i] = 0.f;
+      const float2 l = __fadd2_rn(make_float2(lam[C0 + i], lam[C0 + i + 1]), __fadd2_rn(make_float2(zsum[C0 + i], zsum[C0 + i + 1]), zb));
+      lam[C0 + i] = l.x; lam[C0 + i + 1] = l.y;
+      zsum[C0 + i] = 0.f; zsum[C0 + i + 1] = 0.f;
     }
   }
   if (!FINAL) cc_tc_store_split<NC>(aHi, aLo, C0, kb);
