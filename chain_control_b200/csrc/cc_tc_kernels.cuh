@@ -587,9 +587,18 @@ __global__ void __launch_bounds__(CC_TC_THREADS, 2) cc_tc_bwd_kernel(const CC_GR
       }
       cc_tc_publish<NCH, true>(sh, q);
       // while the first MMA batch runs: recompute the controller step (its stage intermediates are kept)
+      // recompute the controller step, its RK4 stages spread over the windows in which this warp does not issue (at most
+      // two per window, staying at most one stage ahead), like the forward kernel does
       float a[CC_TINY_O];
+#pragma unroll
+      for (int i = 0; i < CC_TINY_O; ++i) a[i] = 0.f;
       if (C.pre) cc_ctrl_readout_pre(CD, sh.wgc, xcv, tc, vc, a);
-      cc_ctrl_update<true>(CD, sh.wfc, sh.wgc, xcv, tc, vc, a, keep);
+      CcCtrlRun crun;
+      const int nstc = cc_ctrl_nstages(CD);
+      int cst = 0, win = 0;
+      cc_ctrl_begin(CD, xcv, tc, vc, crun);
+      if (warp != (int)((q.batch - 1u) & 3u))
+        for (int c2 = 0; c2 < 2 && cst < nstc && cst < win + 2; ++c2) cc_ctrl_stage<true>(CD, sh.wfc, cst++, xcv, tc, crun, keep);
       float utb[CC_TINY_O];
 #pragma unroll
       for (int i = 0; i < CC_TINY_O; ++i) utb[i] = 0.f;
@@ -598,7 +607,13 @@ __global__ void __launch_bounds__(CC_TC_THREADS, 2) cc_tc_bwd_kernel(const CC_GR
         cc_tc_await(sh, par);
         cc_tc_bwd_stage<SR, false>(aD, aHi, aLo, lam, zsum, st == 1 ? h / 6.f : h / 3.f, st == 3 ? h : h / 2.f, utb);
         cc_tc_publish<NCH, true>(sh, q);
+        ++win;
+        if (warp != (int)((q.batch - 1u) & 3u))
+          for (int c2 = 0; c2 < 2 && cst < nstc && cst < win + 2; ++c2) cc_ctrl_stage<true>(CD, sh.wfc, cst++, xcv, tc, crun, keep);
       }
+#pragma unroll 1
+      for (; cst < nstc; ++cst) cc_ctrl_stage<true>(CD, sh.wfc, cst, xcv, tc, crun, keep);
+      cc_ctrl_finish<true>(CD, sh.wgc, xcv, tc, crun, a, keep);
       cc_tc_await(sh, par);
       cc_tc_bwd_stage<SR, true>(aD, aHi, aLo, lam, zsum, 0.f, 0.f, utb);
       if (M.pre) {  // y_k = g(x_k): cotangent joins the adjoint of x_k
