@@ -449,6 +449,19 @@ int32_t cc_module_supported(const CcModule* m, int32_t with_grad) {
   return make_plan(mods, 1, 65536, 1000, o, &p);
 }
 
+int32_t cc_kernel_family(const CcModule* c, const CcModule* m, int32_t with_grad) {
+  int rc = validate_module(m, "model");
+  if (rc) return rc;
+  if (c && (rc = validate_module(c, "controller"))) return rc;
+  CcKParams p;
+  PlanOpts o;
+  o.bwd = with_grad != 0;
+  const CcModule* mods[2] = {c ? c : m, m};
+  rc = make_plan(c ? mods : mods + 1, c ? 2 : 1, 65536, 1000, o, &p);
+  if (rc) return rc;
+  return p.tc;
+}
+
 size_t cc_rollout_tape_bytes(const CcModule* m, int64_t B, int32_t T, int32_t ckpt_every) {
   if (!m || B <= 0 || T < 0 || ckpt_every < 1) return 0;
   const long long Bpad = (B + 31) / 32 * 32;

@@ -82,6 +82,11 @@ int64_t cc_param_count(const CcModule* m);
 /* 0 if the kernels support this module (with_grad: also the BPTT kernels), else a CcStatus */
 int32_t cc_module_supported(const CcModule* m, int32_t with_grad);
 
+/* which kernel family the plan picks for this call (deterministic, from the architecture only):
+ * 1 = tcgen05 kernels (depth-0 model: stage evaluations as tcgen05.mma batches, 3xTF32), 0 = FFMA kernels,
+ * < 0 = a CcStatus (unsupported / invalid).  ctrl == NULL: open loop. */
+int32_t cc_kernel_family(const CcModule* ctrl, const CcModule* model, int32_t with_grad);
+
 /* ---- K1/K2: open-loop batched unroll and its VJP  (replaces step_fn.py:136 + abstract.py:54-70) ---
  * u      [B,T,I]      inputs
  * x0     [B,S] or NULL (zeros = reset(), neural_ode_model.py:103-104)

@@ -68,3 +68,32 @@ def test_unsupported_architectures_fail_loudly():
     huge = A.make_node_spec(512, 1, 1, 0.01, f_width=512, f_depth=2)  # weights do not fit in smem
     m = huge.to_c()
     assert L.cc_module_supported(ctypes.byref(m), 0) == -2
+
+
+@pytest.mark.skipif(not os.path.exists(LIB), reason="libccb200.so not built (run __graft_entry__.build())")
+def test_plan_picks_tcgen05_for_depth0_models():
+    """host-only planning (no GPU needed): the bench architectures run on the tcgen05 kernels, deep MLPs on the FFMA ones"""
+    from ccspecs import controller_variants, model_variants, tc_controller_variants, tc_model_variants
+    from cchelpers import conv
+    from chain_control_b200 import _lib
+
+    L = _lib.lib()
+    fam = lambda c, m, g: L.cc_kernel_family(ctypes.byref(conv(c).to_c()) if c is not None else None, ctypes.byref(conv(m).to_c()), g)
+    old = os.environ.pop("CC_B200_TC", None)
+    try:
+        compact, ctrl = model_variants()["compact_s50_d0"], controller_variants()["compact_s5_d0"]
+        assert fam(None, compact, 0) == 1            # open-loop forward
+        assert fam(None, compact, 1) == 0            # ModelTrainer reverse pass (weight gradients): FFMA kernel
+        assert fam(ctrl, compact, 0) == 1 and fam(ctrl, compact, 1) == 1   # the bench workload, both directions
+        assert fam(None, model_variants()["full_s5_w10_d2"], 0) == 0       # deep MLP
+        assert fam(controller_variants()["full_s25_w10_d2"], compact, 0) == 0  # tile-sized controller
+        for mname, m in tc_model_variants().items():
+            for c in tc_controller_variants().values():
+                assert fam(c, m, 0) == 1, mname
+        assert fam(ctrl, tc_model_variants()["euler_s30_d0_tanh"], 1) == 0  # non-linear frozen model: FFMA reverse pass
+        os.environ["CC_B200_TC"] = "0"
+        assert fam(ctrl, compact, 1) == 0
+    finally:
+        os.environ.pop("CC_B200_TC", None)
+        if old is not None:
+            os.environ["CC_B200_TC"] = old
