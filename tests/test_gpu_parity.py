@@ -215,6 +215,57 @@ def test_full_size_properties(path, T_):
     assert normwise(y64.cpu().numpy(), y[:4096].cpu().numpy()) < 2e-6
 
 
+def test_full_size_closed_loop_properties(path, T_):
+    """closed loop at the bench size (65,536 trajectories; T_r shortened to keep the test fast): size-independent
+    properties of the forward rollout and of the controller gradient, per kernel family"""
+    import torch
+
+    from chain_control_b200 import ops
+
+    mspec, cspec = model_variants()["compact_s50_d0"], controller_variants()["compact_s5_d0"]
+    model, ctrl = conv(mspec), conv(cspec)
+    thm = T_(O.init_params(mspec, 1, stable=True))
+    thc = T_(O.init_params(cspec, 2))
+    B, Tr = 65536, 96
+    amp = torch.sign(torch.randn(B, 1, 1, device="cuda")) * torch.rand(B, 1, 1, device="cuda") * 3
+    refs = amp.expand(B, Tr, 1).contiguous()
+    yh, _, tape = ops.closedloop_fwd(ctrl, model, thc, thm, refs, want_tape=True)
+    # 1. batch independence: a sub-batch alone (different tiles, partial tile) reproduces its rows
+    idx = torch.arange(777, 1100, device="cuda")
+    ys, _, _ = ops.closedloop_fwd(ctrl, model, thc, thm, refs[idx].contiguous())
+    assert normwise(ys.cpu().numpy(), yh[idx].cpu().numpy()) < 2e-6
+    # 2. a sub-batch against the fp64 oracle (the only part small enough for it)
+    ref = CO.closedloop(cspec, mspec, thc.cpu().numpy(), thm.cpu().numpy(), refs[idx].cpu().numpy(), dtype=np.float64)
+    assert normwise(ys.cpu().numpy(), ref["yhat"]) < TOL_STATE
+    # 3. determinism of the gradient (fixed reduction order), linearity in the cotangent, additivity over batch shards
+    ybar = torch.randn(B, Tr, 1, device="cuda") / B
+    g1 = ops.closedloop_bwd(ctrl, model, thc, thm, refs, tape, ybar)
+    g2 = ops.closedloop_bwd(ctrl, model, thc, thm, refs, tape, ybar)
+    assert torch.equal(g1, g2)
+    g3 = ops.closedloop_bwd(ctrl, model, thc, thm, refs, tape, 2 * ybar)
+    assert l2rel(g3.cpu().numpy(), 2 * g1.cpu().numpy()) < 1e-6
+    h = B // 2
+    _, _, ta = ops.closedloop_fwd(ctrl, model, thc, thm, refs[:h].contiguous(), want_tape=True)
+    _, _, tb = ops.closedloop_fwd(ctrl, model, thc, thm, refs[h:].contiguous(), want_tape=True)
+    ga = ops.closedloop_bwd(ctrl, model, thc, thm, refs[:h].contiguous(), ta, ybar[:h].contiguous())
+    gb = ops.closedloop_bwd(ctrl, model, thc, thm, refs[h:].contiguous(), tb, ybar[h:].contiguous())
+    assert l2rel((ga + gb).cpu().numpy(), g1.cpu().numpy()) < 1e-5
+    # 4. the two kernel families agree with each other at full size (outputs and gradient)
+    other = "0" if os.environ.get("CC_B200_TC", "1") != "0" else "1"
+    saved = os.environ.get("CC_B200_TC")
+    os.environ["CC_B200_TC"] = other
+    try:
+        yo, _, tapeo = ops.closedloop_fwd(ctrl, model, thc, thm, refs, want_tape=True)
+        go = ops.closedloop_bwd(ctrl, model, thc, thm, refs, tapeo, ybar)
+    finally:
+        if saved is None:
+            del os.environ["CC_B200_TC"]
+        else:
+            os.environ["CC_B200_TC"] = saved
+    assert normwise(yo.cpu().numpy(), yh.cpu().numpy()) < 5e-6
+    assert l2rel(go.cpu().numpy(), g1.cpu().numpy()) < 2e-5
+
+
 def test_zero_controller_equals_open_loop(T_):
     import torch
 
