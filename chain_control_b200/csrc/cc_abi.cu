@@ -336,6 +336,20 @@ int make_plan(const CcModule* const* mods, int n_nodes, long long B, int T, cons
   }
   layout(p, o.bwd);
   if (p->tc) {
+    // small batches: the latency kernels (one warp per trajectory, cc_wpt_kernels.cuh) -- a 1001-step dependent chain
+    // of a handful of trajectories is bound by the per-stage latency, where a warp-level mat-vec beats an MMA batch
+    const char* wenv = getenv("CC_B200_WPT_MAXB");
+    const long long wmax = wenv ? atoll(wenv) : 1024;
+    if (B <= wmax && model->state_dim + model->input_dim + 1 <= 56) {
+      p->tc = 2;
+      p->wpc = 4;
+      p->n_wtiles = B;  // reverse pass: one gradient record per trajectory
+      const long long gp2 = (o.bwd && n_nodes == 2) ? (long long)(p->nd[0].S + p->nd[0].O) * 14 * 128 + (long long)(p->nd[0].f.layer[0].act != CC_ACT_IDENTITY ? 9 : 5) * CC_TINY_S * 128 : 0;
+      const long long bytes2 = ((long long)((sizeof(CcKParams) + 15) / 16 * 4 + 15) / 16 * 16 + (CC_TINY_S + CC_TINY_O) * 16 + CC_TINY_O * 64 + 4 * 64 + gp2) * 4;
+      if (bytes2 > kSmemBudget) return fail(CC_ERR_UNSUPPORTED, "latency kernels: %lld B of shared memory per CTA", bytes2);
+      if (getenv("CC_B200_VERBOSE")) fprintf(stderr, "[ccb200] latency plan (warp per trajectory): nodes=%d bwd=%d B=%lld T=%d smem=%lld B ctas=%lld\n", n_nodes, (int)o.bwd, B, T, bytes2, (B + 3) / 4);
+      return CC_OK;
+    }
     // one CTA = 128 trajectories (4 worker warps, thread = trajectory) + the MMA-issuing warp
     p->tc_nch = model->state_dim <= 32 ? 4 : 7;
     const int SR = 8 * p->tc_nch;

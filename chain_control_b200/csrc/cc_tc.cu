@@ -3,6 +3,7 @@
 #include <cstdio>
 
 #include "cc_tc_kernels.cuh"
+#include "cc_wpt_kernels.cuh"
 
 namespace {
 template <class Kern>
@@ -31,7 +32,30 @@ static int ctrl_cfg(const CcKParams& p) {
 }
 #define CC_TC_FWD(NCH, CM, FACT) (ctrl_cfg(p) == 521 && CM == CC_CTRL_TINY ? launch_tc(cc_tc_fwd_kernel<NCH, CM, FACT, (CM == CC_CTRL_TINY ? 521 : 0)>, p, false, stream, err, errlen) \
                                                                            : launch_tc(cc_tc_fwd_kernel<NCH, CM, FACT, 0>, p, false, stream, err, errlen))
+// ---- family 2: latency kernels, one warp per trajectory (cc_wpt_kernels.cuh) ----
+template <class Kern>
+static int launch_wpt(Kern kern, const CcKParams& p, bool bwd, void* stream, char* err, int errlen) {
+  const long long grid = (p.B + 3) / 4;
+  const size_t extra = bwd ? (size_t)(p.nd[0].S + p.nd[0].O) * CC_CKU * 128 + (size_t)(p.nd[0].f.layer[0].act != CC_ACT_IDENTITY ? 9 : 5) * CC_TINY_S * 128 : 0;
+  const size_t smem = ((size_t)((CC_PARAM_FLOATS + 15) / 16 * 16) + CC_WPT_REGION_FLOATS + extra) * 4;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) {
+    kern<<<(unsigned)grid, CC_WPT_THREADS, smem, (cudaStream_t)stream>>>(p);
+    e = cudaGetLastError();
+  }
+  if (e != cudaSuccess) {
+    snprintf(err, errlen, "latency kernel launch failed: %s", cudaGetErrorString(e));
+    return CC_ERR_CUDA;
+  }
+  return CC_OK;
+}
+
 int cc_launch_fwd_tc(const CcKParams& p, void* stream, char* err, int errlen) {
+  if (p.tc == 2) {
+    const bool c521 = ctrl_cfg(p) == 521;
+    if (p.n_nodes == 1) return launch_wpt(cc_wpt_fwd_kernel<CC_CTRL_NONE, 0>, p, false, stream, err, errlen);
+    return c521 ? launch_wpt(cc_wpt_fwd_kernel<CC_CTRL_TINY, 521>, p, false, stream, err, errlen) : launch_wpt(cc_wpt_fwd_kernel<CC_CTRL_TINY, 0>, p, false, stream, err, errlen);
+  }
   const bool closed = p.n_nodes == 2;
   const bool fact = p.nd[p.n_nodes - 1].f.layer[0].act != CC_ACT_IDENTITY;  // non-linear final activation of f: separate instantiation
   if (p.tc_nch == 4) {
@@ -42,6 +66,8 @@ int cc_launch_fwd_tc(const CcKParams& p, void* stream, char* err, int errlen) {
   return closed ? CC_TC_FWD(7, CC_CTRL_TINY, false) : CC_TC_FWD(7, CC_CTRL_NONE, false);
 }
 int cc_launch_bwd_tc(const CcKParams& p, void* stream, char* err, int errlen) {
+  if (p.tc == 2)
+    return ctrl_cfg(p) == 521 ? launch_wpt(cc_wpt_bwd_kernel<CC_CTRL_TINY, 521>, p, true, stream, err, errlen) : launch_wpt(cc_wpt_bwd_kernel<CC_CTRL_TINY, 0>, p, true, stream, err, errlen);
   const bool c521 = ctrl_cfg(p) == 521;
   if (p.tc_nch == 4) return c521 ? launch_tc(cc_tc_bwd_kernel<4, CC_CTRL_TINY, 521>, p, true, stream, err, errlen) : launch_tc(cc_tc_bwd_kernel<4, CC_CTRL_TINY, 0>, p, true, stream, err, errlen);
   return c521 ? launch_tc(cc_tc_bwd_kernel<7, CC_CTRL_TINY, 521>, p, true, stream, err, errlen) : launch_tc(cc_tc_bwd_kernel<7, CC_CTRL_TINY, 0>, p, true, stream, err, errlen);

@@ -10,6 +10,14 @@
 #pragma once
 #include "cc_kernels.cuh"
 
+// the launch plan is read straight from the __grid_constant__ kernel parameter (constant bank): a copy in shared memory
+// (what the FFMA kernels use for their non-inlined functions) would have to be re-read after every shared-memory store,
+// because the compiler cannot prove that the stage vectors / accumulators do not alias it
+#define CC_DIRECT_PARAMS(gp)            \
+  float* cc_smem = CC_SMEM_PTR;         \
+  const CcKParams& p = (gp);            \
+  float* cta_smem = cc_smem + CC_PARAM_FLOATS;
+
 #define CC_TC_LANES 128  // threads per CTA of the tcgen05 kernels = stride of the lane-private shared-memory columns
 #define CC_CK 16      // staged weight row length
 #define CC_CKU 14     // columns that can be non-zero

@@ -215,7 +215,7 @@ CC_DEV void cc_tc_issue_batch(uint32_t tbase, uint32_t bhi, uint32_t blo) {
 
 // prologue shared by both kernels: parameter copy, weight staging, barriers, TMEM allocation
 #define CC_TC_PROLOGUE(gp, BWD)                                                                       \
-  CC_KERNEL_PROLOGUE(gp)                                                                              \
+  CC_DIRECT_PARAMS(gp)                                                                                \
   constexpr int SR = 8 * NCH;                                                                         \
   const bool closed = CM != CC_CTRL_NONE;                                                             \
   const CcNodeDev& M = p.nd[closed ? 1 : 0];                                                          \

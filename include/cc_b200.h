@@ -83,7 +83,8 @@ int64_t cc_param_count(const CcModule* m);
 int32_t cc_module_supported(const CcModule* m, int32_t with_grad);
 
 /* which kernel family the plan picks for this call (deterministic, from the architecture only):
- * 1 = tcgen05 kernels (depth-0 model: stage evaluations as tcgen05.mma batches, 3xTF32), 0 = FFMA kernels,
+ * 2 = latency kernels (depth-0 model, small batch: one warp per trajectory), 1 = tcgen05 kernels (depth-0 model:
+ * stage evaluations as tcgen05.mma batches, 3xTF32), 0 = FFMA kernels,
  * < 0 = a CcStatus (unsupported / invalid).  ctrl == NULL: open loop. */
 int32_t cc_kernel_family(const CcModule* ctrl, const CcModule* model, int32_t with_grad);
 

@@ -91,9 +91,13 @@ def test_plan_picks_tcgen05_for_depth0_models():
             for c in tc_controller_variants().values():
                 assert fam(c, m, 0) == 1, mname
         assert fam(ctrl, tc_model_variants()["euler_s30_d0_tanh"], 1) == 0  # non-linear frozen model: FFMA reverse pass
+        os.environ["CC_B200_WPT_MAXB"] = str(1 << 40)   # small-batch latency kernels forced for any batch size
+        assert fam(ctrl, compact, 1) == 2 and fam(None, compact, 0) == 2
+        del os.environ["CC_B200_WPT_MAXB"]
         os.environ["CC_B200_TC"] = "0"
         assert fam(ctrl, compact, 1) == 0
     finally:
         os.environ.pop("CC_B200_TC", None)
+        os.environ.pop("CC_B200_WPT_MAXB", None)
         if old is not None:
             os.environ["CC_B200_TC"] = old

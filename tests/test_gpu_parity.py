@@ -24,16 +24,25 @@ def T_():
     return lambda a: torch.tensor(np.asarray(a, np.float32), device="cuda")
 
 
-@pytest.fixture(params=["tcgen05", "ffma"])
+FAMILY_ENV = {
+    # kernel family -> (CC_B200_TC, CC_B200_WPT_MAXB): which kernels the plan may pick where the architecture allows it
+    "tcgen05": ("1", "0"),             # tensor-core kernels at every batch size
+    "latency": ("1", str(1 << 40)),    # one warp per trajectory at every batch size (default: B <= 1024 only)
+    "ffma": ("0", "0"),                # register-tiled FP32 kernels
+}
+
+
+@pytest.fixture(params=list(FAMILY_ENV))
 def path(request):
-    """run the test once per kernel family: CC_B200_TC=0 forces the FFMA kernels where tcgen05 would be chosen"""
-    old = os.environ.get("CC_B200_TC")
-    os.environ["CC_B200_TC"] = "1" if request.param == "tcgen05" else "0"
+    """run the test once per kernel family (where the architecture is not eligible the plan falls through to FFMA)"""
+    old = {k: os.environ.get(k) for k in ("CC_B200_TC", "CC_B200_WPT_MAXB")}
+    os.environ["CC_B200_TC"], os.environ["CC_B200_WPT_MAXB"] = FAMILY_ENV[request.param]
     yield request.param
-    if old is None:
-        del os.environ["CC_B200_TC"]
-    else:
-        os.environ["CC_B200_TC"] = old
+    for k, v in old.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
 
 
 def _u(B, T, I, seed=0):
@@ -250,18 +259,18 @@ def test_full_size_closed_loop_properties(path, T_):
     ga = ops.closedloop_bwd(ctrl, model, thc, thm, refs[:h].contiguous(), ta, ybar[:h].contiguous())
     gb = ops.closedloop_bwd(ctrl, model, thc, thm, refs[h:].contiguous(), tb, ybar[h:].contiguous())
     assert l2rel((ga + gb).cpu().numpy(), g1.cpu().numpy()) < 1e-5
-    # 4. the two kernel families agree with each other at full size (outputs and gradient)
-    other = "0" if os.environ.get("CC_B200_TC", "1") != "0" else "1"
-    saved = os.environ.get("CC_B200_TC")
-    os.environ["CC_B200_TC"] = other
+    # 4. the kernel families agree with each other at full size (outputs and gradient): compare with the FFMA kernels
+    saved = {k: os.environ.get(k) for k in ("CC_B200_TC", "CC_B200_WPT_MAXB")}
+    os.environ["CC_B200_TC"], os.environ["CC_B200_WPT_MAXB"] = FAMILY_ENV["ffma" if path != "ffma" else "tcgen05"]
     try:
         yo, _, tapeo = ops.closedloop_fwd(ctrl, model, thc, thm, refs, want_tape=True)
         go = ops.closedloop_bwd(ctrl, model, thc, thm, refs, tapeo, ybar)
     finally:
-        if saved is None:
-            del os.environ["CC_B200_TC"]
-        else:
-            os.environ["CC_B200_TC"] = saved
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
     assert normwise(yo.cpu().numpy(), yh.cpu().numpy()) < 5e-6
     assert l2rel(go.cpu().numpy(), g1.cpu().numpy()) < 2e-5
 
