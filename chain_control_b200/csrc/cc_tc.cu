@@ -28,7 +28,8 @@ int launch_tc(Kern kern, const CcKParams& p, bool bwd, void* stream, char* err, 
 // CFG = 521: the compact controller's shape (S_c = 5, 2 inputs, 1 output, time-invariant) as compile-time constants
 static int ctrl_cfg(const CcKParams& p) {
   const CcNodeDev& C = p.nd[0];
-  return (p.n_nodes == 2 && C.S == 5 && C.I == 2 && C.O == 1 && !C.has_t) ? 521 : 0;
+  return (p.n_nodes == 2 && C.S == 5 && C.I == 2 && C.O == 1 && !C.has_t && C.ut == CC_UT_IDENTITY &&
+          C.f.layer[0].act == CC_ACT_IDENTITY && C.g.layer[0].act == CC_ACT_IDENTITY) ? 521 : 0;
 }
 #define CC_TC_FWD(NCH, CM, FACT) (ctrl_cfg(p) == 521 && CM == CC_CTRL_TINY ? launch_tc(cc_tc_fwd_kernel<NCH, CM, FACT, (CM == CC_CTRL_TINY ? 521 : 0)>, p, false, stream, err, errlen) \
                                                                            : launch_tc(cc_tc_fwd_kernel<NCH, CM, FACT, 0>, p, false, stream, err, errlen))

@@ -26,7 +26,7 @@
 #define CC_C_ONE 13   // column of the constant 1
 
 // the controller's shape and options as seen by the device functions below.  For the common compact controller
-// (S_c = 5, [ref ; obs] = 2 inputs, 1 output, time-invariant: CFG = 521) the sizes are compile-time constants, so the
+// (S_c = 5, [ref ; obs] = 2 inputs, 1 output, time-invariant, no activations: CFG = 521) the sizes are compile-time constants, so the
 // per-row `if (n < S)` branches fold and the rows of a stage become one basic block the scheduler can interleave.
 struct CcCtrlDims {
   int S, I, O, has_t, pre, integrator, ut, f_act, g_act;
@@ -39,8 +39,12 @@ CC_DEV CcCtrlDims cc_ctrl_dims(const CcNodeDev& C) {
   d.I = CFG ? (CFG / 10) % 10 : C.I;
   d.O = CFG ? CFG % 10 : C.O;
   d.has_t = CFG ? 0 : C.has_t;
-  d.pre = C.pre; d.integrator = C.integrator; d.ut = C.ut;
-  d.f_act = C.f.layer[0].act; d.g_act = C.g.layer[0].act;
+  d.pre = C.pre; d.integrator = C.integrator;
+  // CFG shapes are only selected for controllers without activations / input transform (the reference's defaults), so
+  // that the per-element activation dispatch folds away too
+  d.ut = CFG ? (int)CC_UT_IDENTITY : C.ut;
+  d.f_act = CFG ? (int)CC_ACT_IDENTITY : C.f.layer[0].act;
+  d.g_act = CFG ? (int)CC_ACT_IDENTITY : C.g.layer[0].act;
   d.u_scale = C.u_scale; d.out_scale = C.out_scale; d.dt = C.dt;
   return d;
 }

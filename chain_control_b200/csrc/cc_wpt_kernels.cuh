@@ -99,6 +99,7 @@ __global__ void __launch_bounds__(CC_WPT_THREADS) cc_wpt_fwd_kernel(const CC_GRI
   const CcLayerDev& F = M.f.layer[0];
   const CcLayerDev& G = M.g.layer[0];
   const bool tape = p.tape != nullptr;
+  const bool fnl = F.act != CC_ACT_IDENTITY;  // non-linear final activation of f
   const float* thm = p.theta[closed ? 1 : 0];
   // rows n0 / n1 of f's weight matrix in the physical input order [x ; v ; 1]
   float r0[CC_WPT_KW], r1[CC_WPT_KW];
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(CC_WPT_THREADS) cc_wpt_fwd_kernel(const CC_GRI
       if (cpipe && st < nstc) cc_ctrl_stage<false>(CD, sh.wfc, st, xc, tc, crun, nullptr);
       float k0, k1;
       cc_wpt_dot2(r0, r1, zb, k0, k1);
-      k0 = cc_act(F.act, k0); k1 = cc_act(F.act, k1);
+      if (fnl) { k0 = cc_act(F.act, k0); k1 = cc_act(F.act, k1); }
       __syncwarp();  // every lane has read the stage vector
       if (nst == 4) {
         if (st < 3) {
