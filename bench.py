@@ -67,6 +67,7 @@ WORKLOADS = {
     "cfg2x": (True, 65536, 1001),
     "cfg2": (True, 64, 1001),
     "cfg4": (False, 65536, 1000),
+    "cfg1": (False, 8, 1000),
 }
 # algorithmic FLOPs per trajectory-step: F = 2 (n_st M_f + M_g)
 F_C = 2 * (4 * (5 + 2) * 5 + 5)       # 290
@@ -396,7 +397,8 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": {"cfg2x": "closed-loop ControllerTrainer step (configs[1] architecture: compact controller S_c=5 + frozen compact model S_m=50, RK4, dt=0.01, T_r=1001) at configs[3]'s batch, 65536 trajectories per GPU",
                                     "cfg2": "configs[1]: closed-loop ControllerTrainer BPTT, 64 trajectories x 1001 steps",
-                                    "cfg4": "configs[3]: ModelTrainer step, 65536 trajectories per GPU x 1000 steps, S=50 depth 0"}[args.workload],
+                                    "cfg4": "configs[3]: ModelTrainer step, 65536 trajectories per GPU x 1000 steps, S=50 depth 0",
+                                    "cfg1": "configs[0]: ModelTrainer step, 8 trajectories x 1000 steps, S=50 depth 0"}[args.workload],
                        "B_per_gpu": B, "T": T, "closed_loop": closed, "integrator": "RK4", "ckpt_every": 1,
                        "kernels": "tcgen05 (3xTF32, A in tensor memory) forward" + (" and reverse pass" if closed else "; FFMA reverse pass (weight gradients)"),
                        "step": "fwd rollout + mse cotangent + BPTT + grad reduce" + (" + NCCL allreduce(P+1)" if world > 1 else "") + " + adam",

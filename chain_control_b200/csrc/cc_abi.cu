@@ -113,7 +113,7 @@ bool tc_eligible(const CcModule* const* mods, int n_nodes, bool bwd) {
   if (env && atoi(env) == 0) return false;
   const CcModule* model = mods[n_nodes - 1];
   if (!tc_model_ok(model)) return false;
-  if (n_nodes == 1) return !bwd;  // the trainable open-loop reverse pass (weight gradients) stays on the FFMA kernels
+  if (n_nodes == 1) return true;  // (the trainable open-loop reverse pass exists as a latency kernel only: see make_plan)
   if (!node_is_tiny(mods[0])) return false;
   if (mods[0]->input_dim > CC_TINY_O) return false;
   if (bwd && !(mlp_linear(model->f) && mlp_linear(model->g))) return false;
@@ -220,9 +220,10 @@ void layout(CcKParams* p, bool bwd) {
   for (int n = 0; n < p->n_nodes; ++n) {
     CcNodeDev& nd = p->nd[n];
     CcMlpDev* devs[2] = {&nd.f, &nd.g};
-    if (p->tc && n == p->n_nodes - 1) {  // the model node lives in TMEM / registers (cc_tc_kernels.cuh)
+    if (p->tc && n == p->n_nodes - 1) {  // the model node lives in TMEM / registers (cc_tc_kernels.cuh, cc_wpt_kernels.cuh)
       nd.w_X = nd.w_Z = nd.w_OUT = nd.w_XN = nd.w_LAM = nd.w_DA = nd.w_DB = nd.w_VB = nd.w_OB = nd.w_GP = -1;
       nd.g_base = grec;
+      if (bwd && nd.trainable) grec += nd.g_total;
       continue;
     }
     const bool need_fwd = !bwd || nd.recompute || nd.tiny;  // forward evaluation of this node happens in this kernel
@@ -335,12 +336,18 @@ int make_plan(const CcModule* const* mods, int n_nodes, long long B, int T, cons
     p->tape_rows = p->nd[0].S;
   }
   layout(p, o.bwd);
+  // small batches: the latency kernels (one warp per trajectory, cc_wpt_kernels.cuh) -- a 1001-step dependent chain
+  // of a handful of trajectories is bound by the per-stage latency, where a warp-level mat-vec beats an MMA batch
+  const char* wenv = getenv("CC_B200_WPT_MAXB");
+  const long long wmax = wenv ? atoll(wenv) : 1024;
+  const bool small = B <= wmax && model->state_dim + model->input_dim + 1 <= 56;
+  if (p->tc && n_nodes == 1 && o.bwd && !small) {
+    // large-batch ModelTrainer reverse pass (the weight gradient contracts over trajectories): FFMA kernels
+    p->tc = 0;
+    layout(p, o.bwd);
+  }
   if (p->tc) {
-    // small batches: the latency kernels (one warp per trajectory, cc_wpt_kernels.cuh) -- a 1001-step dependent chain
-    // of a handful of trajectories is bound by the per-stage latency, where a warp-level mat-vec beats an MMA batch
-    const char* wenv = getenv("CC_B200_WPT_MAXB");
-    const long long wmax = wenv ? atoll(wenv) : 1024;
-    if (B <= wmax && model->state_dim + model->input_dim + 1 <= 56) {
+    if (small) {
       p->tc = 2;
       p->wpc = 4;
       p->n_wtiles = B;  // reverse pass: one gradient record per trajectory

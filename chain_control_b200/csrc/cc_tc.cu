@@ -66,7 +66,27 @@ int cc_launch_fwd_tc(const CcKParams& p, void* stream, char* err, int errlen) {
   if (fact) return closed ? CC_TC_FWD(7, CC_CTRL_TINY, true) : CC_TC_FWD(7, CC_CTRL_NONE, true);
   return closed ? CC_TC_FWD(7, CC_CTRL_TINY, false) : CC_TC_FWD(7, CC_CTRL_NONE, false);
 }
+// open-loop reverse pass with a trainable depth-0 model (latency kernels)
+static int launch_wpt_obwd(const CcKParams& p, void* stream, char* err, int errlen) {
+  const long long grid = (p.B + 3) / 4;
+  const size_t smem = ((size_t)((CC_PARAM_FLOATS + 15) / 16 * 16) + CC_WPT_OB_FLOATS(p.nd[0].S) + 4 * CC_WPT_ZB) * 4;
+  auto go = [&](auto kern) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+      kern<<<(unsigned)grid, CC_WPT_THREADS, smem, (cudaStream_t)stream>>>(p);
+      e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) {
+      snprintf(err, errlen, "latency kernel launch failed: %s", cudaGetErrorString(e));
+      return (int)CC_ERR_CUDA;
+    }
+    return (int)CC_OK;
+  };
+  return p.nd[0].K0 <= 52 ? go(cc_wpt_obwd_kernel<52>) : go(cc_wpt_obwd_kernel<56>);
+}
+
 int cc_launch_bwd_tc(const CcKParams& p, void* stream, char* err, int errlen) {
+  if (p.tc == 2 && p.n_nodes == 1) return launch_wpt_obwd(p, stream, err, errlen);
   if (p.tc == 2)
     return ctrl_cfg(p) == 521 ? launch_wpt(cc_wpt_bwd_kernel<CC_CTRL_TINY, 521>, p, true, stream, err, errlen) : launch_wpt(cc_wpt_bwd_kernel<CC_CTRL_TINY, 0>, p, true, stream, err, errlen);
   const bool c521 = ctrl_cfg(p) == 521;

@@ -381,3 +381,198 @@ __global__ void __launch_bounds__(CC_WPT_THREADS) cc_wpt_bwd_kernel(const CC_GRI
     }
   }
 }
+
+// ------------------------------------------------------------------------------------------------
+// reverse pass of the OPEN loop with a TRAINABLE depth-0 model (ModelTrainer, step_fn.py:133-146): theta_bar and, on
+// request, ubar.  Lane l owns rows l / l+32 of f's weight matrix (recomputation) AND of its gradient (register
+// accumulators: the outer products need no cross-lane reduction); the transposed product zbar = W^T kbar reads the
+// CTA-shared copy W[m][64] column-wise (consecutive lanes -> consecutive addresses).  One gradient record per trajectory.
+// ------------------------------------------------------------------------------------------------
+#define CC_WPT_OB_FLOATS(S) (CC_WPT_REGION_FLOATS + 4 * 3 * CC_WPT_ZB + (S) * 64)  // + 3 more stage vectors per warp + W[m][64]
+template <int KW>
+CC_DEV void cc_wpt_dot2k(const float (&r0)[KW], const float (&r1)[KW], const float* z, float& k0, float& k1) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+#pragma unroll
+  for (int q = 0; q < KW / 4; ++q) {
+    const float4 v = *reinterpret_cast<const float4*>(z + 4 * q);
+    a0 = fmaf(r0[4 * q], v.x, a0); a1 = fmaf(r0[4 * q + 1], v.y, a1); a2 = fmaf(r0[4 * q + 2], v.z, a2); a3 = fmaf(r0[4 * q + 3], v.w, a3);
+    b0 = fmaf(r1[4 * q], v.x, b0); b1 = fmaf(r1[4 * q + 1], v.y, b1); b2 = fmaf(r1[4 * q + 2], v.z, b2); b3 = fmaf(r1[4 * q + 3], v.w, b3);
+  }
+  k0 = (a0 + a1) + (a2 + a3);
+  k1 = (b0 + b1) + (b2 + b3);
+}
+template <int KW>
+__global__ void __launch_bounds__(CC_WPT_THREADS) cc_wpt_obwd_kernel(const CC_GRID_CONSTANT CcKParams gp) {
+  constexpr int CM = CC_CTRL_NONE, CFG = 0;
+  CC_WPT_PROLOGUE(gp)
+  (void)CD;
+  const CcLayerDev& F = M.f.layer[0];
+  const CcLayerDev& G = M.g.layer[0];
+  const float* thm = p.theta[0];
+  const bool fnl = F.act != CC_ACT_IDENTITY, gnl = G.act != CC_ACT_IDENTITY;
+  const int K0 = M.K0, SI = M.S + M.I;
+  float* Z = sh.gp + warp * 4 * CC_WPT_ZB;            // this warp's four stage-input vectors [x ; v~ ; 1]
+  float* Wsm = sh.gp + 4 * 4 * CC_WPT_ZB;              // CTA-shared W[m][64] (output m, physical input j)
+  for (int i = tid; i < M.S * 64; i += blockDim.x) Wsm[i] = (i % 64 < K0) ? cc_weight_at(M, F, thm, i / 64, i % 64) : 0.f;
+  float r0[KW], r1[KW], wb0[KW], wb1[KW];
+#pragma unroll
+  for (int k = 0; k < KW; ++k) {
+    r0[k] = (v0 && k < K0) ? cc_weight_at(M, F, thm, n0, k) : 0.f;
+    r1[k] = (v1 && k < K0) ? cc_weight_at(M, F, thm, n1, k) : 0.f;
+    wb0[k] = 0.f; wb1[k] = 0.f;
+  }
+  for (int s = 0; s < 4; ++s) { Z[s * CC_WPT_ZB + lane] = 0.f; Z[s * CC_WPT_ZB + lane + 32] = 0.f; }
+  zb[lane] = 0.f; zb[lane + 32] = 0.f;  // kbar vector
+  __syncthreads();
+  if (lane == 0)
+    for (int s = 0; s < 4; ++s) Z[s * CC_WPT_ZB + M.row_one] = 1.f;
+  __syncwarp();
+  float ga0[CC_TINY_O], ga1[CC_TINY_O], gab[CC_TINY_O];  // gradient of g: my two state columns, bias (every lane)
+#pragma unroll
+  for (int o = 0; o < CC_TINY_O; ++o) { ga0[o] = 0.f; ga1[o] = 0.f; gab[o] = 0.f; }
+  float lam0 = 0.f, lam1 = 0.f;
+  const long long yrow = (long long)(p.T + 1) * M.O;
+  const float os = M.out_scale;
+  const bool w0 = n0 < SI, w1 = n1 < SI;  // input index j owned for the transposed product
+  // cotangent of one readout y = os * act(g . xr + b) at the state (xr0, xr1): accumulates g's gradient, returns g^T d
+  auto readout_bwd = [&](float xr0, float xr1, long long yoff, float& gx0, float& gx1) {
+    gx0 = 0.f; gx1 = 0.f;
+    float yv[CC_TINY_O];
+    if (gnl) cc_wpt_readout(sh.gmod, lane, xr0, xr1, M.O, G.act, os, yv);
+#pragma unroll
+    for (int o = 0; o < CC_TINY_O; ++o) {
+      if (o < M.O) {
+        float d = os * (actw ? __ldg(p.ybar + b * yrow + yoff + o) : 0.f);
+        if (gnl) d *= cc_act_grad(G.act, os != 0.f ? yv[o] / os : 0.f);
+        ga0[o] = fmaf(d, xr0, ga0[o]); ga1[o] = fmaf(d, xr1, ga1[o]); gab[o] += d;
+        gx0 = fmaf(sh.gmod[o * 64 + lane], d, gx0); gx1 = fmaf(sh.gmod[o * 64 + 32 + lane], d, gx1);
+      }
+    }
+  };
+  for (int k = p.T - 1; k >= 0; --k) {
+    // carry of step k: x_k from the tape, input u_k
+    const float x0 = (v0 && actw) ? p.tape[((long long)k * p.tape_rows + n0) * p.Bpad + b] : 0.f;
+    const float x1 = (v1 && actw) ? p.tape[((long long)k * p.tape_rows + n1) * p.Bpad + b] : 0.f;
+    float uraw = 0.f;  // lane i < I holds input i
+    if (lane < M.I && actw) uraw = __ldg(p.in + b * (long long)p.T * M.I + (long long)k * M.I + lane);
+    const float ut = cc_ut(M.ut, M.u_scale, uraw);
+    // ---- recompute the stages (stage inputs stay in Z[0..3], stage outputs in registers) ----
+    if (v0) Z[n0] = x0;
+    if (v1) Z[n1] = x1;
+    if (lane < M.I)
+      for (int s = 0; s < nst; ++s) Z[s * CC_WPT_ZB + M.row_v + lane] = ut;
+    __syncwarp();
+    float ks0[4], ks1[4];
+    float s0 = 0.f, s1 = 0.f, xn0 = x0, xn1 = x1;
+#pragma unroll
+    for (int st = 0; st < 4; ++st) {
+      ks0[st] = 0.f; ks1[st] = 0.f;
+      if (st < nst) {
+        float k0, k1;
+        cc_wpt_dot2k<KW>(r0, r1, Z + st * CC_WPT_ZB, k0, k1);
+        if (fnl) { k0 = cc_act(F.act, k0); k1 = cc_act(F.act, k1); }
+        ks0[st] = k0; ks1[st] = k1;
+        if (nst == 4) {
+          if (st < 3) {
+            const float wk = st == 0 ? 1.f : 2.f, cz = st == 2 ? 1.f : 0.5f;
+            s0 = st == 0 ? k0 : s0 + wk * k0;
+            s1 = st == 0 ? k1 : s1 + wk * k1;
+            if (v0) Z[(st + 1) * CC_WPT_ZB + n0] = x0 + (h * k0) * cz;
+            if (v1) Z[(st + 1) * CC_WPT_ZB + n1] = x1 + (h * k1) * cz;
+            __syncwarp();
+          } else {
+            xn0 = x0 + h * ((1.f / 6.f) * (s0 + k0));
+            xn1 = x1 + h * ((1.f / 6.f) * (s1 + k1));
+          }
+        } else {
+          xn0 = x0 + h * k0;
+          xn1 = x1 + h * k1;
+        }
+      }
+    }
+    if (!v0) xn0 = 0.f;
+    if (!v1) xn1 = 0.f;
+    // ---- readout of this step: out[k+1] = g(x_{k+1}) (full model) or g(x_k) (compact) ----
+    float gx0, gx1;
+    readout_bwd(M.pre ? x0 : xn0, M.pre ? x1 : xn1, (long long)(k + 1) * M.O, gx0, gx1);
+    if (!M.pre) { lam0 += gx0; lam1 += gx1; }
+    // ---- integrator's reverse pass ----
+    float zs0 = 0.f, zs1 = 0.f, us0 = 0.f, us1 = 0.f, z0 = 0.f, z1 = 0.f;
+#pragma unroll
+    for (int st = 3; st >= 0; --st) {
+      if (st < nst) {
+        const float ca = nst == 4 ? ((st == 3 || st == 0) ? h / 6.f : h / 3.f) : h;
+        const float cb = nst == 4 ? (st == 3 ? 0.f : (st == 2 ? h : h / 2.f)) : 0.f;
+        float kb0 = ca * lam0 + cb * z0, kb1 = ca * lam1 + cb * z1;
+        if (fnl) { kb0 *= cc_act_grad(F.act, ks0[st]); kb1 *= cc_act_grad(F.act, ks1[st]); }
+        if (!v0) kb0 = 0.f;
+        if (!v1) kb1 = 0.f;
+        // weight gradient rows: Wbar[n][:] += kbar[n] * [z_st ; v~ ; 1]
+        const float* zst = Z + st * CC_WPT_ZB;
+#pragma unroll
+        for (int q = 0; q < KW / 4; ++q) {
+          const float4 v = *reinterpret_cast<const float4*>(zst + 4 * q);
+          wb0[4 * q] = fmaf(kb0, v.x, wb0[4 * q]); wb0[4 * q + 1] = fmaf(kb0, v.y, wb0[4 * q + 1]); wb0[4 * q + 2] = fmaf(kb0, v.z, wb0[4 * q + 2]); wb0[4 * q + 3] = fmaf(kb0, v.w, wb0[4 * q + 3]);
+          wb1[4 * q] = fmaf(kb1, v.x, wb1[4 * q]); wb1[4 * q + 1] = fmaf(kb1, v.y, wb1[4 * q + 1]); wb1[4 * q + 2] = fmaf(kb1, v.z, wb1[4 * q + 2]); wb1[4 * q + 3] = fmaf(kb1, v.w, wb1[4 * q + 3]);
+        }
+        // zbar = W^T kbar (inputs j = lane, lane + 32): kbar goes through the warp's vector, W is read column-wise
+        zb[n0] = kb0; zb[n1] = kb1;
+        __syncwarp();
+        float a0 = 0.f, a1 = 0.f, c0 = 0.f, c1 = 0.f;
+#pragma unroll 2
+        for (int m = 0; m < M.S; m += 2) {
+          const float q0 = zb[m], q1 = zb[m + 1];  // (S even or zb[S] = 0: rows beyond S are never written non-zero)
+          a0 = fmaf(Wsm[m * 64 + n0], q0, a0); c0 = fmaf(Wsm[m * 64 + n1], q0, c0);
+          if (m + 1 < M.S) { a1 = fmaf(Wsm[(m + 1) * 64 + n0], q1, a1); c1 = fmaf(Wsm[(m + 1) * 64 + n1], q1, c1); }
+        }
+        __syncwarp();
+        z0 = w0 ? a0 + a1 : 0.f;
+        z1 = w1 ? c0 + c1 : 0.f;
+        us0 += z0; us1 += z1;
+        if (nst == 4 && st > 0) { zs0 += z0; zs1 += z1; }
+        else {
+          if (v0) lam0 = lam0 + (zs0 + z0);
+          if (v1) lam1 = lam1 + (zs1 + z1);
+        }
+      }
+    }
+    if (M.pre) { lam0 += gx0; lam1 += gx1; }
+    if (!v0) lam0 = 0.f;
+    if (!v1) lam1 = 0.f;
+    if (p.ubar) {  // cotangent of the raw input i: held by the lane that owns input S + i; lane i knows u_i
+#pragma unroll
+      for (int i = 0; i < CC_TINY_O; ++i) {
+        if (i < M.I) {
+          const int j = M.S + i;
+          const float uu = __shfl_sync(CC_FULL, j < 32 ? us0 : us1, j & 31);
+          if (lane == i && actw) p.ubar[b * (long long)p.T * M.I + (long long)k * M.I + i] = uu * cc_ut_grad(M.ut, M.u_scale, uraw);
+        }
+      }
+    }
+  }
+  // out[0] = y0 = g(x0): only g's parameters see it (x0 is not trained)
+  {
+    const float x00 = (p.x0 && actw && v0) ? __ldg(p.x0 + b * M.S + n0) : 0.f;
+    const float x01 = (p.x0 && actw && v1) ? __ldg(p.x0 + b * M.S + n1) : 0.f;
+    float gx0, gx1;
+    readout_bwd(x00, x01, 0, gx0, gx1);
+  }
+  // gradient record of this trajectory: f's rows are lane-owned, g's columns are lane-owned
+  if (actw) {
+    float* rec = p.gpart + b * p.g_rec + M.g_base;
+#pragma unroll
+    for (int k = 0; k < KW; ++k) {
+      if (k < K0) {
+        if (v0) rec[F.g_off + n0 * K0 + k] = wb0[k];
+        if (v1) rec[F.g_off + n1 * K0 + k] = wb1[k];
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < CC_TINY_O; ++o) {
+      if (o < M.O) {
+        if (n0 < K0) rec[G.g_off + o * K0 + n0] = v0 ? ga0[o] : (n0 == M.row_one ? gab[o] : 0.f);
+        if (n1 < K0) rec[G.g_off + o * K0 + n1] = v1 ? ga1[o] : (n1 == M.row_one ? gab[o] : 0.f);
+      }
+    }
+  }
+}
