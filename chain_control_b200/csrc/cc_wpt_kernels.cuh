@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(CC_WPT_THREADS) cc_wpt_bwd_kernel(const CC_GRI
 // accumulators: the outer products need no cross-lane reduction); the transposed product zbar = W^T kbar reads the
 // CTA-shared copy W[m][64] column-wise (consecutive lanes -> consecutive addresses).  One gradient record per trajectory.
 // ------------------------------------------------------------------------------------------------
-#define CC_WPT_OB_FLOATS(S) (CC_WPT_REGION_FLOATS + 4 * 3 * CC_WPT_ZB + (S) * 64)  // + 3 more stage vectors per warp + W[m][64]
+#define CC_WPT_OB_FLOATS(S) (CC_WPT_REGION_FLOATS + 4 * 3 * CC_WPT_ZB + (((S) + 3) / 4 * 4) * 64)  // + 3 more stage vectors per warp + W[m][64]
 template <int KW>
 CC_DEV void cc_wpt_dot2k(const float (&r0)[KW], const float (&r1)[KW], const float* z, float& k0, float& k1) {
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
@@ -413,7 +413,8 @@ __global__ void __launch_bounds__(CC_WPT_THREADS) cc_wpt_obwd_kernel(const CC_GR
   const int K0 = M.K0, SI = M.S + M.I;
   float* Z = sh.gp + warp * 4 * CC_WPT_ZB;            // this warp's four stage-input vectors [x ; v~ ; 1]
   float* Wsm = sh.gp + 4 * 4 * CC_WPT_ZB;              // CTA-shared W[m][64] (output m, physical input j)
-  for (int i = tid; i < M.S * 64; i += blockDim.x) Wsm[i] = (i % 64 < K0) ? cc_weight_at(M, F, thm, i / 64, i % 64) : 0.f;
+  const int S4 = (M.S + 3) / 4 * 4;
+  for (int i = tid; i < S4 * 64; i += blockDim.x) Wsm[i] = (i % 64 < K0 && i / 64 < M.S) ? cc_weight_at(M, F, thm, i / 64, i % 64) : 0.f;
   float r0[KW], r1[KW], wb0[KW], wb1[KW];
 #pragma unroll
   for (int k = 0; k < KW; ++k) {
@@ -520,10 +521,12 @@ __global__ void __launch_bounds__(CC_WPT_THREADS) cc_wpt_obwd_kernel(const CC_GR
         __syncwarp();
         float a0 = 0.f, a1 = 0.f, c0 = 0.f, c1 = 0.f;
 #pragma unroll 2
-        for (int m = 0; m < M.S; m += 2) {
-          const float q0 = zb[m], q1 = zb[m + 1];  // (S even or zb[S] = 0: rows beyond S are never written non-zero)
-          a0 = fmaf(Wsm[m * 64 + n0], q0, a0); c0 = fmaf(Wsm[m * 64 + n1], q0, c0);
-          if (m + 1 < M.S) { a1 = fmaf(Wsm[(m + 1) * 64 + n0], q1, a1); c1 = fmaf(Wsm[(m + 1) * 64 + n1], q1, c1); }
+        for (int m = 0; m < S4; m += 4) {  // W has S rounded up to a multiple of 4 rows (zero padded), kbar beyond S is 0
+          const float4 q = *reinterpret_cast<const float4*>(zb + m);
+          a0 = fmaf(Wsm[m * 64 + n0], q.x, a0); c0 = fmaf(Wsm[m * 64 + n1], q.x, c0);
+          a1 = fmaf(Wsm[(m + 1) * 64 + n0], q.y, a1); c1 = fmaf(Wsm[(m + 1) * 64 + n1], q.y, c1);
+          a0 = fmaf(Wsm[(m + 2) * 64 + n0], q.z, a0); c0 = fmaf(Wsm[(m + 2) * 64 + n1], q.z, c0);
+          a1 = fmaf(Wsm[(m + 3) * 64 + n0], q.w, a1); c1 = fmaf(Wsm[(m + 3) * 64 + n1], q.w, c1);
         }
         __syncwarp();
         z0 = w0 ? a0 + a1 : 0.f;
