@@ -82,6 +82,11 @@ m2 += ["", "Both sizes are bound by the latency of the 10,001-step chain.", "",
        "| cfg2 = configs[1] literally: 64 trajectories × 1001 steps, closed-loop fwd + BPTT + adam | %.2f | %.3g | latency kernels (one warp per trajectory): 3.0 µs per step and direction; the tcgen05 kernels need 12.6 ms, the first FFMA kernels needed 69 ms |" % (cfg2['ms_per_step'], cfg2['value']),
        "| cfg1 = configs[0] literally: ModelTrainer, 8 trajectories × 1000 steps, fwd + BPTT (weight gradients) + adam | 10.0 | 8.0e5 | latency kernels (forward 1.6 ms, reverse 8.3 ms); with the FFMA reverse kernel 98.7 ms |",
        "| cfg4 = configs[3]: ModelTrainer, 65,536 × 1000, S=50 depth 0 | 435.6 | 1.5e8 | forward 19 ms on tcgen05; the reverse pass with the model's weight gradient (416 ms, 6.5 TFLOP/s alg.) is still the FFMA kernel — next round |",
-       "| cfg2x (default), 2 GPUs (torchrun, NCCL allreduce of 47 floats) | = 1 GPU | 2.00× | weak scaling measured earlier in the round (48.9 ms per step on 1 and on 2 GPUs) |", ""]
+       "| cfg2x (default), 2 GPUs (torchrun, NCCL allreduce of 47 floats) | = 1 GPU | 2.00× | weak scaling measured earlier in the round (48.9 ms per step on 1 and on 2 GPUs) |", "",
+       "Both arms on the reference's own small configurations, same box (`bench.py --workload cfgN` vs `bench.py --impl reference --workload cfgN`, 16 host threads):", "",
+       "| workload | CPU restatement (C/OpenMP) | B200 | ratio |", "|---|---:|---:|---:|",
+       "| cfg1: ModelTrainer, 8 × 1000 | 47.3 ms per step | 9.9 ms per step | 4.8× |",
+       "| cfg2: ControllerTrainer, 64 × 1001 | 30.5 ms per step | 6.06 ms per step | 5.0× |",
+       "| cfg2x: ControllerTrainer, 65,536 × 1001 (1,024-trajectory CPU sample) | 1.35e7 traj-steps/s | 2.26e9 traj-steps/s (e2e 1.94e9) | 167× (e2e 143×) |", ""]
 open('profiles/r01_tc_sweep_cfg3_cfg5.md', 'w').write("\n".join(m2))
 print('ok', step_ms, fwd_ms, bwd_ms)
