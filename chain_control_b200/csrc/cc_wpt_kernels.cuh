@@ -414,7 +414,11 @@ __global__ void __launch_bounds__(CC_WPT_THREADS) cc_wpt_obwd_kernel(const CC_GR
   float* Z = sh.gp + warp * 4 * CC_WPT_ZB;            // this warp's four stage-input vectors [x ; v~ ; 1]
   float* Wsm = sh.gp + 4 * 4 * CC_WPT_ZB;              // CTA-shared W[m][64] (output m, physical input j)
   const int S4 = (M.S + 3) / 4 * 4;
-  for (int i = tid; i < S4 * 64; i += blockDim.x) Wsm[i] = (i % 64 < K0 && i / 64 < M.S) ? cc_weight_at(M, F, thm, i / 64, i % 64) : 0.f;
+  // columns permuted so that a lane's two inputs (lane, lane + 32) are adjacent: one LDS.64 per row
+  for (int i = tid; i < S4 * 64; i += blockDim.x) {
+    const int m = i / 64, j = i % 64;
+    Wsm[m * 64 + 2 * (j & 31) + (j >> 5)] = (j < K0 && m < M.S) ? cc_weight_at(M, F, thm, m, j) : 0.f;
+  }
   float r0[KW], r1[KW], wb0[KW], wb1[KW];
 #pragma unroll
   for (int k = 0; k < KW; ++k) {
@@ -450,12 +454,17 @@ __global__ void __launch_bounds__(CC_WPT_THREADS) cc_wpt_obwd_kernel(const CC_GR
       }
     }
   };
+  // the step's carry (x_k from the tape) and input u_k are fetched one step ahead
+  float nx0 = 0.f, nx1 = 0.f, nu = 0.f;
+  auto fetch = [&](int k) {
+    nx0 = (v0 && actw) ? p.tape[((long long)k * p.tape_rows + n0) * p.Bpad + b] : 0.f;
+    nx1 = (v1 && actw) ? p.tape[((long long)k * p.tape_rows + n1) * p.Bpad + b] : 0.f;
+    nu = (lane < M.I && actw) ? __ldg(p.in + b * (long long)p.T * M.I + (long long)k * M.I + lane) : 0.f;  // lane i < I holds input i
+  };
+  if (p.T > 0) fetch(p.T - 1);
   for (int k = p.T - 1; k >= 0; --k) {
-    // carry of step k: x_k from the tape, input u_k
-    const float x0 = (v0 && actw) ? p.tape[((long long)k * p.tape_rows + n0) * p.Bpad + b] : 0.f;
-    const float x1 = (v1 && actw) ? p.tape[((long long)k * p.tape_rows + n1) * p.Bpad + b] : 0.f;
-    float uraw = 0.f;  // lane i < I holds input i
-    if (lane < M.I && actw) uraw = __ldg(p.in + b * (long long)p.T * M.I + (long long)k * M.I + lane);
+    const float x0 = nx0, x1 = nx1, uraw = nu;
+    if (k > 0) fetch(k - 1);
     const float ut = cc_ut(M.ut, M.u_scale, uraw);
     // ---- recompute the stages (stage inputs stay in Z[0..3], stage outputs in registers) ----
     if (v0) Z[n0] = x0;
@@ -523,10 +532,14 @@ __global__ void __launch_bounds__(CC_WPT_THREADS) cc_wpt_obwd_kernel(const CC_GR
 #pragma unroll 2
         for (int m = 0; m < S4; m += 4) {  // W has S rounded up to a multiple of 4 rows (zero padded), kbar beyond S is 0
           const float4 q = *reinterpret_cast<const float4*>(zb + m);
-          a0 = fmaf(Wsm[m * 64 + n0], q.x, a0); c0 = fmaf(Wsm[m * 64 + n1], q.x, c0);
-          a1 = fmaf(Wsm[(m + 1) * 64 + n0], q.y, a1); c1 = fmaf(Wsm[(m + 1) * 64 + n1], q.y, c1);
-          a0 = fmaf(Wsm[(m + 2) * 64 + n0], q.z, a0); c0 = fmaf(Wsm[(m + 2) * 64 + n1], q.z, c0);
-          a1 = fmaf(Wsm[(m + 3) * 64 + n0], q.w, a1); c1 = fmaf(Wsm[(m + 3) * 64 + n1], q.w, c1);
+          const float2 wa = *reinterpret_cast<const float2*>(Wsm + m * 64 + 2 * lane);
+          const float2 wb = *reinterpret_cast<const float2*>(Wsm + (m + 1) * 64 + 2 * lane);
+          const float2 wc = *reinterpret_cast<const float2*>(Wsm + (m + 2) * 64 + 2 * lane);
+          const float2 wd = *reinterpret_cast<const float2*>(Wsm + (m + 3) * 64 + 2 * lane);
+          a0 = fmaf(wa.x, q.x, a0); c0 = fmaf(wa.y, q.x, c0);
+          a1 = fmaf(wb.x, q.y, a1); c1 = fmaf(wb.y, q.y, c1);
+          a0 = fmaf(wc.x, q.z, a0); c0 = fmaf(wc.y, q.z, c0);
+          a1 = fmaf(wd.x, q.w, a1); c1 = fmaf(wd.y, q.w, c1);
         }
         __syncwarp();
         z0 = w0 ? a0 + a1 : 0.f;
