@@ -38,3 +38,52 @@ def allreduce_grad_and_loss(grad: torch.Tensor, loss_partial: torch.Tensor):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(buf, op=dist.ReduceOp.SUM)
     return buf[:-1].reshape(grad.shape), buf[-1]
+
+
+class HostFeed:
+    """Double-buffered host -> device feed for the train step's inputs: the copy of step i+1 (pinned host memory, side
+    stream) overlaps the rollout kernels of step i.  Every step still moves its own inputs host -> device; only the
+    waiting is hidden.  Usage:
+        feed = HostFeed(device); feed.push(host_batch)            # before the loop
+        for ...:  x = feed.pop(); feed.push(next_host_batch); step(x)
+    The device buffers are reused (two slots), so `pop()`ed tensors are valid until the second-next `push`."""
+
+    def __init__(self, device):
+        import torch
+
+        self.torch = torch
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(self.device)
+        self.slots = [None, None]
+        self.ready = [None, None]
+        self.free = [None, None]   # event recorded on the compute stream when the slot's previous consumer was queued
+        self.head = 0              # next slot to fill
+        self.queue = []
+
+    def push(self, host_tensor):
+        torch = self.torch
+        s = self.head
+        self.head ^= 1
+        if self.slots[s] is None or self.slots[s].shape != host_tensor.shape or self.slots[s].dtype != host_tensor.dtype:
+            self.slots[s] = torch.empty(host_tensor.shape, dtype=host_tensor.dtype, device=self.device)
+        with torch.cuda.stream(self.stream):
+            if self.free[s] is not None:
+                self.stream.wait_event(self.free[s])  # the kernels that read this slot two steps ago have finished
+            self.slots[s].copy_(host_tensor, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.ready[s] = ev
+        self.queue.append(s)
+
+    def pop(self):
+        s = self.queue.pop(0)
+        cur = self.torch.cuda.current_stream(self.device)
+        cur.wait_event(self.ready[s])
+        self._last = s
+        return self.slots[s]
+
+    def release(self):
+        """call after the step that consumed the last `pop()`ed tensor has been queued on the current stream"""
+        ev = self.torch.cuda.Event()
+        ev.record(self.torch.cuda.current_stream(self.device))
+        self.free[self._last] = ev

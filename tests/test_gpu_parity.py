@@ -298,3 +298,23 @@ def test_product_path_has_no_cpu_fallback():
     spec = conv(model_variants()["full_s5_w10_d2"])
     with pytest.raises(_lib.CcError):
         ops.rollout_fwd(spec, torch.zeros(spec.n_params()), torch.zeros(2, 3, 1))
+
+
+def test_host_feed_delivers_batches_in_order():
+    """parallel.HostFeed: double-buffered pinned-host -> device copies on a side stream keep order and contents"""
+    import torch
+
+    from chain_control_b200 import parallel
+
+    feed = parallel.HostFeed("cuda")
+    host = [torch.full((257, 33, 1), float(i)).pin_memory() for i in range(7)]
+    feed.push(host[0])
+    seen = []
+    for i in range(7):
+        x = feed.pop()
+        if i + 1 < 7:
+            feed.push(host[i + 1])
+        seen.append((x * 2).sum())  # a consumer on the compute stream
+        feed.release()
+    torch.cuda.synchronize()
+    assert [float(s) for s in seen] == [2.0 * i * 257 * 33 for i in range(7)]
