@@ -2,6 +2,7 @@
 import csv, collections, json, sys
 bench = json.loads(open('gpurun_out/bench_r01_tc.json').read().strip().split('\n')[-1])
 cfg2 = json.loads(open('gpurun_out/bench_r01_cfg2.json').read().strip().split('\n')[-1])
+cfg1 = json.loads(open('gpurun_out/bench_r01_cfg1.json').read().strip().split('\n')[-1])
 rf = bench['roofline']
 rows = list(csv.reader(open('gpurun_out/launches_r01_tc.csv')))
 hi = [i for i, r in enumerate(rows) if r and r[0] == 'ID'][0]
@@ -80,13 +81,13 @@ for r in sw:
 m2 += ["", "Both sizes are bound by the latency of the 10,001-step chain.", "",
        "## other bench workloads (`bench.py --workload ...`)", "", "| workload | ms per step | traj-steps/s | note |", "|---|---:|---:|---|",
        "| cfg2 = configs[1] literally: 64 trajectories × 1001 steps, closed-loop fwd + BPTT + adam | %.2f | %.3g | latency kernels (one warp per trajectory): 3.0 µs per step and direction; the tcgen05 kernels need 12.6 ms, the first FFMA kernels needed 69 ms |" % (cfg2['ms_per_step'], cfg2['value']),
-       "| cfg1 = configs[0] literally: ModelTrainer, 8 trajectories × 1000 steps, fwd + BPTT (weight gradients) + adam | 10.0 | 8.0e5 | latency kernels (forward 1.6 ms, reverse 8.3 ms); with the FFMA reverse kernel 98.7 ms |",
+       "| cfg1 = configs[0] literally: ModelTrainer, 8 trajectories × 1000 steps, fwd + BPTT (weight gradients) + adam | %.1f | %.2g | latency kernels (forward 1.6 ms, reverse 6.5 ms); with the FFMA reverse kernel 98.7 ms |" % (cfg1['ms_per_step'], cfg1['value']),
        "| cfg4 = configs[3]: ModelTrainer, 65,536 × 1000, S=50 depth 0 | 435.6 | 1.5e8 | forward 19 ms on tcgen05; the reverse pass with the model's weight gradient (416 ms, 6.5 TFLOP/s alg.) is still the FFMA kernel — next round |",
        "| cfg2x (default), 2 GPUs (torchrun, NCCL allreduce of 47 floats) | = 1 GPU | 2.00× | weak scaling measured earlier in the round (48.9 ms per step on 1 and on 2 GPUs) |", "",
        "Both arms on the reference's own small configurations, same box (`bench.py --workload cfgN` vs `bench.py --impl reference --workload cfgN`, 16 host threads):", "",
        "| workload | CPU restatement (C/OpenMP) | B200 | ratio |", "|---|---:|---:|---:|",
-       "| cfg1: ModelTrainer, 8 × 1000 | 47.3 ms per step | 9.9 ms per step | 4.8× |",
+       "| cfg1: ModelTrainer, 8 × 1000 | 47.3 ms per step | 8.2 ms per step | 5.8× |",
        "| cfg2: ControllerTrainer, 64 × 1001 | 30.5 ms per step | 6.06 ms per step | 5.0× |",
-       "| cfg2x: ControllerTrainer, 65,536 × 1001 (1,024-trajectory CPU sample) | 1.35e7 traj-steps/s | 2.26e9 traj-steps/s (e2e 1.94e9) | 167× (e2e 143×) |", ""]
+       "| cfg2x: ControllerTrainer, 65,536 × 1001 (1,024-trajectory CPU sample) | 1.35e7 traj-steps/s | 2.25e9 traj-steps/s (e2e 2.17e9) | 166× (e2e 161×) |", ""]
 open('profiles/r01_tc_sweep_cfg3_cfg5.md', 'w').write("\n".join(m2))
 print('ok', step_ms, fwd_ms, bwd_ms)
