@@ -55,3 +55,12 @@ def tc_controller_variants(R=1, O_obs=1, I_m=1):
     v["full_s6_d0_ft"] = O.make_node(6, din, I_m, f_depth=0, g_feedthrough_u=True)
     v["euler_s3_d0"] = O.make_node(3, din, I_m, f_depth=0, integrator=O.INT_EE, readout_pre_step=True, out_scale=0.5)
     return v
+
+
+def tc_open_model_variants():
+    """open-loop only: depth-0 models with several inputs / outputs (the closed-loop variants above are SISO like the reference's)"""
+    v = dict(tc_model_variants())
+    v["compact_s40_d0_i2_o3"] = O.make_node(40, 2, 3, f_depth=0, readout_pre_step=True, u_transform=O.UT_ARCTAN)
+    v["full_s18_d0_i3_o2_euler"] = O.make_node(18, 3, 2, f_depth=0, integrator=O.INT_EE, f_act_final=O.ACT_TANH, g_act_final=O.ACT_TANH)
+    v["full_s51_d0_i4_o4"] = O.make_node(51, 4, 4, f_depth=0)
+    return v

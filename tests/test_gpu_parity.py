@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from cchelpers import TOL_GRAD, TOL_STATE, conv, l2rel, normwise
-from ccspecs import controller_variants, model_variants, tc_controller_variants, tc_model_variants
+from ccspecs import controller_variants, model_variants, tc_controller_variants, tc_model_variants, tc_open_model_variants
 from oracle import c_oracle as CO
 from oracle import np_oracle as O
 
@@ -92,12 +92,12 @@ def test_closedloop_fwd_bwd_vs_oracle(cname, mname, T_):
     assert l2rel(tb.cpu().numpy(), ref["theta_c_bar"]) < max(TOL_GRAD, 2 * floor), (floor,)
 
 
-@pytest.mark.parametrize("name", list(tc_model_variants()))
+@pytest.mark.parametrize("name", list(tc_open_model_variants()))
 def test_tc_rollout_vs_oracle(name, path, T_):
     """depth-0 models, open loop: forward on tcgen05 (3xTF32), reverse pass on the FFMA kernels from the tape it wrote"""
     from chain_control_b200 import ops
 
-    spec = tc_model_variants()[name]
+    spec = tc_open_model_variants()[name]
     B, T = 301, 203
     theta = O.init_params(spec, 1).astype(np.float32)
     u = _u(B, T, spec.input_dim)
