@@ -367,7 +367,12 @@ def main():
         #   (sustained figure: the kernel runs inside a long step).  `executed` counts what the pipe really does:
         #   3 passes (lo.hi, hi.lo, hi.hi) over the padded 128 x 64 x 56 tiles, 4 stages per trajectory-step.
         # open loop (cfg4): the reverse pass (weight gradients) is the FFMA kernel -> bound by the FP32 FMA pipe.
-        tensor = closed
+        import ctypes as _C
+        cm, mm = ctrl.to_c(), model.to_c()
+        fam_f = L.cc_kernel_family_at(_C.byref(cm) if closed else None, _C.byref(mm), 0, B)
+        fam_b = L.cc_kernel_family_at(_C.byref(cm) if closed else None, _C.byref(mm), 1, B)
+        fam_name = {0: "ffma", 1: "tcgen05", 2: "latency"}
+        tensor = fam_b == 1
         bf16_peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 2250.0 * 0.62))
         tf32_peak = bf16_peak / 2.0
         exec_flops_ts = 3 * 2 * 64 * 56 * 4  # per trajectory-step of one rollout kernel (forward or reverse): 3 x 2 x NP x KP x stages
@@ -389,12 +394,12 @@ def main():
                                  "frac_of_fp32_fma_peak": units * tot_f / ((fwd_ms + bwd_ms) * 1e-3) / 1e12 / peak_tflops},
                         "hbm": {"achieved_gbs": units * bytes_ts / ((fwd_ms + bwd_ms) * 1e-3) / 1e9, "peak_gbs": hbm, "alg_bytes_per_traj_step": bytes_ts}}
         else:
-            roofline = {"bound": "fp32", "kernel": "cc_rollout_bwd_kernel", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+            roofline = {"bound": "fp32", "kernel": {0: "cc_rollout_bwd_kernel", 2: ("cc_wpt_bwd_kernel" if closed else "cc_wpt_obwd_kernel")}.get(fam_b, "cc_rollout_bwd_kernel"), "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
                         "frac": achieved / peak_tflops, "traffic": None,
                         "peak_source": "FFMA-chain probe measured live in this run (MEASURED_PEAKS.json carries no FP32 figure; nominal 74.4)",
                         "peak_register_tile": regtile_tflops,
                         "alg_flops_per_traj_step": tot_f - fwd_f, "launch_ms": bwd_ms,
-                        "fwd_kernel": {"kernel": "cc_tc_fwd_kernel", "achieved": units * fwd_f / (fwd_ms * 1e-3) / 1e12, "launch_ms": fwd_ms, "alg_flops_per_traj_step": fwd_f},
+                        "fwd_kernel": {"kernel": {0: "cc_rollout_fwd_kernel", 1: "cc_tc_fwd_kernel", 2: "cc_wpt_fwd_kernel"}[fam_f], "achieved": units * fwd_f / (fwd_ms * 1e-3) / 1e12, "launch_ms": fwd_ms, "alg_flops_per_traj_step": fwd_f},
                         "step": {"achieved": units * tot_f / ((fwd_ms + bwd_ms) * 1e-3) / 1e12, "alg_flops_per_traj_step": tot_f},
                         "hbm": {"achieved_gbs": units * bytes_ts / ((fwd_ms + bwd_ms) * 1e-3) / 1e9, "peak_gbs": hbm, "alg_bytes_per_traj_step": bytes_ts}}
         out = {
@@ -407,7 +412,8 @@ def main():
                                     "cfg4": "configs[3]: ModelTrainer step, 65536 trajectories per GPU x 1000 steps, S=50 depth 0",
                                     "cfg1": "configs[0]: ModelTrainer step, 8 trajectories x 1000 steps, S=50 depth 0"}[args.workload],
                        "B_per_gpu": B, "T": T, "closed_loop": closed, "integrator": "RK4", "ckpt_every": 1,
-                       "kernels": "tcgen05 (3xTF32, A in tensor memory) forward" + (" and reverse pass" if closed else "; FFMA reverse pass (weight gradients)"),
+                       "kernels": {"forward": fam_name[fam_f], "reverse": fam_name[fam_b],
+                                   "note": "tcgen05 = 3xTF32 tensor-core kernels (A in tensor memory); latency = one warp per trajectory (small batches); ffma = register-tiled FP32"},
                        "step": "fwd rollout + mse cotangent + BPTT + grad reduce" + (" + NCCL allreduce(P+1)" if world > 1 else "") + " + adam",
                        "l2": "inputs+tape (>= 0.26 GB + %.1f GB) exceed the 126 MB L2" % (2 * 4 * tape_rows * units / 2 / 1e9),
                        "loss": loss_val},

@@ -22,6 +22,7 @@ _SIGS = {
     "cc_param_count": (_i64, [_M]),
     "cc_module_supported": (_i32, [_M, _i32]),
     "cc_kernel_family": (_i32, [_M, _M, _i32]),
+    "cc_kernel_family_at": (_i32, [_M, _M, _i32, _i64]),
     "cc_rollout_tape_bytes": (_sz, [_M, _i64, _i32, _i32]),
     "cc_rollout_workspace_bytes": (_sz, [_M, _i64, _i32, _i32]),
     "cc_rollout_fwd": (_i32, [_M, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp]),

@@ -338,8 +338,13 @@ int make_plan(const CcModule* const* mods, int n_nodes, long long B, int T, cons
   layout(p, o.bwd);
   // small batches: the latency kernels (one warp per trajectory, cc_wpt_kernels.cuh) -- a 1001-step dependent chain
   // of a handful of trajectories is bound by the per-stage latency, where a warp-level mat-vec beats an MMA batch
+  // measured crossovers (gpurun_out/xover.log, S = 50): closed loop / forward 7.7 ms vs 11.8 ms (tcgen05) up to 1184 =
+  // 148 SMs x 8 warps; the trainable open-loop reverse pass 28 ms at B = 4096 vs ~100 ms for the FFMA kernel (which is
+  // latency bound up to ~16K trajectories), so it keeps the latency kernel much longer; the open-loop forward pass
+  // alone breaks even at 4096 (6.55 ms vs 6.82 ms)
   const char* wenv = getenv("CC_B200_WPT_MAXB");
-  const long long wmax = wenv ? atoll(wenv) : 1024;
+  const bool obwd = n_nodes == 1 && o.bwd;
+  const long long wmax = wenv ? atoll(wenv) : (obwd ? 12288 : (n_nodes == 1 ? 4096 : 1184));
   const bool small = B <= wmax && model->state_dim + model->input_dim + 1 <= 56;
   if (p->tc && n_nodes == 1 && o.bwd && !small) {
     // large-batch ModelTrainer reverse pass (the weight gradient contracts over trajectories): FFMA kernels
@@ -470,7 +475,10 @@ int32_t cc_module_supported(const CcModule* m, int32_t with_grad) {
   return make_plan(mods, 1, 65536, 1000, o, &p);
 }
 
-int32_t cc_kernel_family(const CcModule* c, const CcModule* m, int32_t with_grad) {
+int32_t cc_kernel_family(const CcModule* c, const CcModule* m, int32_t with_grad) { return cc_kernel_family_at(c, m, with_grad, 65536); }
+
+int32_t cc_kernel_family_at(const CcModule* c, const CcModule* m, int32_t with_grad, int64_t B) {
+  if (B < 1) return fail(CC_ERR_INVALID_ARG, "bad batch size");
   int rc = validate_module(m, "model");
   if (rc) return rc;
   if (c && (rc = validate_module(c, "controller"))) return rc;
@@ -478,7 +486,7 @@ int32_t cc_kernel_family(const CcModule* c, const CcModule* m, int32_t with_grad
   PlanOpts o;
   o.bwd = with_grad != 0;
   const CcModule* mods[2] = {c ? c : m, m};
-  rc = make_plan(c ? mods : mods + 1, c ? 2 : 1, 65536, 1000, o, &p);
+  rc = make_plan(c ? mods : mods + 1, c ? 2 : 1, B, 1000, o, &p);
   if (rc) return rc;
   return p.tc;
 }

@@ -33,30 +33,55 @@ __global__ void cc_sum_partials_kernel(const float* part, int n, float* out) {
   }
 }
 
-// theta_bar[j] = sum over warp tiles (fixed order) of the gradient-record entry that maps to
-// parameter j.  One thread per (layer, n, r) entry of the node's record ([N][K] blocks).
-__global__ void cc_reduce_grad_kernel(const CcKParams p, int node, float* theta_bar, int n_tiles) {
+// theta_bar[j] = sum over warp tiles (fixed order) of the gradient-record entry that maps to parameter j.
+// A CTA owns 32 consecutive record entries (one coalesced 128 B line per record) x CC_RED_SLICES slices of the tile
+// range; each slice keeps 4 running sums, the slices are combined in a fixed order through shared memory -> 64 short
+// chains per output instead of one n_tiles-long one (rounding error and latency both drop).
+#define CC_RED_SLICES 16
+__global__ void __launch_bounds__(32 * CC_RED_SLICES) cc_reduce_grad_kernel(const CcKParams p, int node, float* theta_bar, int n_tiles) {
+#ifndef CC_EMULATE
+  __shared__ float red[CC_RED_SLICES][33];
+#else
+  float(*red)[33] = reinterpret_cast<float(*)[33]>(ccemu::st().smem);
+#endif
   const CcNodeDev& nd = p.nd[node];
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // index inside the node's record
-  if (idx >= nd.g_total) return;
-  for (int w = 0; w < 2; ++w) {
-    const CcMlpDev& mlp = w ? nd.g : nd.f;
-    for (int l = 0; l < mlp.L; ++l) {
-      const CcLayerDev& L = mlp.layer[l];
-      const int sz = L.N * L.K;
-      if (idx >= L.g_off && idx < L.g_off + sz) {
-        const int n = (idx - L.g_off) / L.K, r = (idx - L.g_off) % L.K;
-        const int lc = cc_row_to_logical(nd, L, r);
-        int dst = -1;
-        if (lc >= 0) dst = L.w_off + n * L.in_log + lc;
-        else if (lc == -2 && L.b_off >= 0) dst = L.b_off + n;
-        if (dst < 0) return;
-        float s = 0.f;
-        for (int t = 0; t < n_tiles; ++t) s += p.gpart[(long long)t * p.g_rec + nd.g_base + idx];
-        theta_bar[dst] = s;
-        return;
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int idx = blockIdx.x * 32 + lane;  // index inside the node's record
+  int dst = -1;
+  if (idx < nd.g_total) {
+    for (int w = 0; w < 2; ++w) {
+      const CcMlpDev& mlp = w ? nd.g : nd.f;
+      for (int l = 0; l < mlp.L; ++l) {
+        const CcLayerDev& L = mlp.layer[l];
+        if (idx >= L.g_off && idx < L.g_off + L.N * L.K) {
+          const int n = (idx - L.g_off) / L.K, r = (idx - L.g_off) % L.K;
+          const int lc = cc_row_to_logical(nd, L, r);
+          if (lc >= 0) dst = L.w_off + n * L.in_log + lc;
+          else if (lc == -2 && L.b_off >= 0) dst = L.b_off + n;
+        }
       }
     }
+  }
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (dst >= 0) {
+    const float* src = p.gpart + nd.g_base + idx;
+    const long long rec = p.g_rec;
+    int t = slice;
+    for (; t + 3 * CC_RED_SLICES < n_tiles; t += 4 * CC_RED_SLICES) {
+      s0 += src[(long long)t * rec];
+      s1 += src[(long long)(t + CC_RED_SLICES) * rec];
+      s2 += src[(long long)(t + 2 * CC_RED_SLICES) * rec];
+      s3 += src[(long long)(t + 3 * CC_RED_SLICES) * rec];
+    }
+    for (; t < n_tiles; t += CC_RED_SLICES) s0 += src[(long long)t * rec];
+  }
+  red[slice][lane] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (slice == 0 && dst >= 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < CC_RED_SLICES; ++i) s += red[i][lane];
+    theta_bar[dst] = s;
   }
 }
 

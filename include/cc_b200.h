@@ -87,6 +87,8 @@ int32_t cc_module_supported(const CcModule* m, int32_t with_grad);
  * stage evaluations as tcgen05.mma batches, 3xTF32), 0 = FFMA kernels,
  * < 0 = a CcStatus (unsupported / invalid).  ctrl == NULL: open loop. */
 int32_t cc_kernel_family(const CcModule* ctrl, const CcModule* model, int32_t with_grad);
+/* same for a given batch size (the latency kernels are picked for small batches only; cc_kernel_family assumes 65,536) */
+int32_t cc_kernel_family_at(const CcModule* ctrl, const CcModule* model, int32_t with_grad, int64_t B);
 
 /* ---- K1/K2: open-loop batched unroll and its VJP  (replaces step_fn.py:136 + abstract.py:54-70) ---
  * u      [B,T,I]      inputs
