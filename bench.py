@@ -77,6 +77,8 @@ F_M = 2 * (4 * (50 + 1) * 50 + 50)    # 20,500
 # dram read+write bytes per trajectory-step of cc_tc_bwd_kernel from the ncu --set full capture (profiles/r01_tc_ncu_full.md);
 # None until a capture of the current kernel exists
 TRAFFIC_TC_BWD_BYTES_PER_TS = 32.4  # (2.120 GB read + 0.008 GB written) / (65,536 x 1,001)
+# same for cc_tcw_bwd_kernel (ModelTrainer reverse pass): (208.8 MB read + 6.7 MB written) / (16,384 x 60), gpurun_out/prof_tcw2
+TRAFFIC_TCW_BWD_BYTES_PER_TS = 219.2
 
 
 def alg_flops(closed):
@@ -371,21 +373,27 @@ def main():
         cm, mm = ctrl.to_c(), model.to_c()
         fam_f = L.cc_kernel_family_at(_C.byref(cm) if closed else None, _C.byref(mm), 0, B)
         fam_b = L.cc_kernel_family_at(_C.byref(cm) if closed else None, _C.byref(mm), 1, B)
-        fam_name = {0: "ffma", 1: "tcgen05", 2: "latency"}
-        tensor = fam_b == 1
+        fam_name = {0: "ffma", 1: "tcgen05", 2: "latency", 3: "tcgen05"}
+        tensor = fam_b in (1, 3)
         bf16_peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 2250.0 * 0.62))
         tf32_peak = bf16_peak / 2.0
         exec_flops_ts = 3 * 2 * 64 * 56 * 4  # per trajectory-step of one rollout kernel (forward or reverse): 3 x 2 x NP x KP x stages
+        exec_note = "3xTF32 split (fp32-accurate products) over 128 x 64 x 56 padded tiles; 4.2x the algorithmic count"
+        bwd_kernel, bwd_traffic = "cc_tc_bwd_kernel", TRAFFIC_TC_BWD_BYTES_PER_TS
+        if fam_b == 3:  # ModelTrainer reverse pass: adjoint (4 stages) + recomputation (3 stages) + weight gradient (2 x M128 x N64 per trajectory and stage)
+            exec_flops_ts = 3 * 2 * 64 * 56 * (4 + 3) + 2 * 2 * 128 * 64 * 4
+            exec_note = "3xTF32: adjoint + recomputed stage inputs (128 x 64 x 56 tiles) + SS-mode weight-gradient product (hi/lo rows stacked: 2 x M128 x N64 per trajectory and stage)"
+            bwd_kernel, bwd_traffic = "cc_tcw_bwd_kernel", TRAFFIC_TCW_BWD_BYTES_PER_TS
         if tensor:
-            roofline = {"bound": "tensor", "kernel": "cc_tc_bwd_kernel", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
+            roofline = {"bound": "tensor", "kernel": bwd_kernel, "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
                         "frac": achieved / tf32_peak,
-                        "traffic": TRAFFIC_TC_BWD_BYTES_PER_TS * units if TRAFFIC_TC_BWD_BYTES_PER_TS else None,
+                        "traffic": bwd_traffic * units if bwd_traffic else None,
                         "traffic_source": "ncu --set full capture of the same kernel (profiles/r01_tc_ncu_full.md), dram read+write per trajectory-step x units of this launch",
                         "peak_source": "MEASURED_PEAKS.json dense bf16 (sustained) / 2 = dense TF32; the kernel issues tcgen05.mma kind::tf32",
                         "alg_flops_per_traj_step": tot_f - fwd_f, "launch_ms": bwd_ms,
                         "executed": {"tflops": units * exec_flops_ts / (bwd_ms * 1e-3) / 1e12, "frac": units * exec_flops_ts / (bwd_ms * 1e-3) / 1e12 / tf32_peak,
                                      "flops_per_traj_step": exec_flops_ts,
-                                     "note": "3xTF32 split (fp32-accurate products) over 128 x 64 x 56 padded tiles; 4.2x the algorithmic count"},
+                                     "note": exec_note},
                         "fp32_fma": {"peak": peak_tflops, "frac": achieved / peak_tflops, "peak_register_tile": regtile_tflops,
                                      "note": "BASELINE.json's yardstick: algorithmic TFLOP/s over the FP32 FMA peak (FFMA-chain probe measured live; nominal 74.4)"},
                         "fwd_kernel": {"kernel": "cc_tc_fwd_kernel", "achieved": units * fwd_f / (fwd_ms * 1e-3) / 1e12, "launch_ms": fwd_ms, "alg_flops_per_traj_step": fwd_f,

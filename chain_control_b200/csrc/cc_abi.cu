@@ -347,7 +347,28 @@ int make_plan(const CcModule* const* mods, int n_nodes, long long B, int T, cons
   const long long wmax = wenv ? atoll(wenv) : (obwd ? 12288 : (n_nodes == 1 ? 4096 : 1184));
   const bool small = B <= wmax && model->state_dim + model->input_dim + 1 <= 56;
   if (p->tc && n_nodes == 1 && o.bwd && !small) {
-    // large-batch ModelTrainer reverse pass (the weight gradient contracts over trajectories): FFMA kernels
+    // large-batch ModelTrainer reverse pass: the weight gradient contracts over trajectories.  Linear compact models
+    // (f, g without final activation, pre-step readout, RK4, room for [v ; 1] inside the state chunks): tcgen05 kernel
+    // with an SS-mode weight-gradient product (cc_tcw_kernels.cuh); everything else: FFMA kernels
+    const char* wgenv = getenv("CC_B200_TCW");
+    const int nch = model->state_dim <= 32 ? 4 : 7;
+    const bool tcw = !(wgenv && atoi(wgenv) == 0) && mlp_linear(model->f) && mlp_linear(model->g) && model->readout_pre_step &&
+                     model->integrator == CC_INT_RK4 && model->state_dim + 5 <= 8 * nch && T >= 1;
+    if (tcw) {
+      p->tc = 3;
+      p->tc_nch = nch;
+      p->tc_KP = 8 * nch;
+      p->tc_NP = (8 * nch + CC_TINY_O + 15) / 16 * 16;
+      p->wpc = 9;
+      p->n_wtiles = (B + 127) / 128;  // one gradient record per CTA
+      const int head = (int)((sizeof(CcKParams) + 15) / 16 * 4);
+      p->tc_off = (head + 15) / 16 * 16;
+      const int SR = 8 * nch;
+      const long long bytes = ((long long)p->tc_off + 2LL * SR * p->tc_NP + 2LL * SR * ((SR + 15) / 16 * 16) + CC_TINY_O * (SR + 4) + 40 + 2LL * 16 * 1152) * 4;
+      if (bytes > kSmemBudget) return fail(CC_ERR_UNSUPPORTED, "tcgen05 weight-gradient kernel: %lld B of shared memory per CTA", bytes);
+      if (getenv("CC_B200_VERBOSE")) fprintf(stderr, "[ccb200] tcgen05 weight-gradient plan: B=%lld T=%d nch=%d smem=%lld B ctas=%lld\n", B, T, nch, bytes, (B + 127) / 128);
+      return CC_OK;
+    }
     p->tc = 0;
     layout(p, o.bwd);
   }

@@ -126,10 +126,11 @@ struct CcKParams {
   float* ubar;         // open loop, optional [B,T,I]
   float* gpart;        // per-warp-tile gradient records [n_wtiles][g_rec]
   int g_rec;
+  float* scratch;      // tcgen05 weight-gradient kernel: per-CTA stage-input slots [3][8*nch][128] (L2 resident)
   int w_yprev, w_yfb, w_araw;  // per-warp closed-loop scratch rows
   // tensor-core path (cc_tc_kernels.cuh): the MODEL node's f runs on tcgen05 (TMEM-resident stage inputs,
   // 3xTF32 split), one trajectory per thread; only the (tiny) controller uses the per-warp regions above
-  int tc;          // 0: FFMA kernels, 1: tcgen05 kernels
+  int tc;          // 0: FFMA kernels, 1: tcgen05 kernels, 2: latency kernels, 3: tcgen05 reverse pass with weight gradient
   int tc_nch;      // state register chunks of 8 per thread (4 or 7): S <= 8 * tc_nch
   int tc_KP;       // A columns (contraction, multiple of 8): fwd [x ; v ; 1], bwd [kbar]
   int tc_NP;       // D columns (multiple of 16): fwd k (S), bwd [zbar (8*nch) ; vbar (I)]

@@ -4,6 +4,7 @@
 
 #include "cc_tc_kernels.cuh"
 #include "cc_wpt_kernels.cuh"
+#include "cc_tcw_kernels.cuh"
 
 namespace {
 template <class Kern>
@@ -85,7 +86,28 @@ static int launch_wpt_obwd(const CcKParams& p, void* stream, char* err, int errl
   return p.nd[0].K0 <= 52 ? go(cc_wpt_obwd_kernel<52>) : go(cc_wpt_obwd_kernel<56>);
 }
 
+// open-loop reverse pass with a trainable linear depth-0 model at large batch: tcgen05 incl. the weight gradient (cc_tcw_kernels.cuh)
+static int launch_tcw(const CcKParams& p, void* stream, char* err, int errlen) {
+  const int SR = 8 * p.tc_nch;
+  const long long grid = (p.B + 127) / 128;
+  const size_t smem = ((size_t)p.tc_off + CC_TCW_REGION_FLOATS(SR)) * 4;
+  auto go = [&](auto kern) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+      kern<<<(unsigned)grid, CC_TCW_THREADS, smem, (cudaStream_t)stream>>>(p);
+      e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) {
+      snprintf(err, errlen, "tcgen05 weight-gradient kernel launch failed: %s", cudaGetErrorString(e));
+      return (int)CC_ERR_CUDA;
+    }
+    return (int)CC_OK;
+  };
+  return p.tc_nch == 4 ? go(cc_tcw_bwd_kernel<4>) : go(cc_tcw_bwd_kernel<7>);
+}
+
 int cc_launch_bwd_tc(const CcKParams& p, void* stream, char* err, int errlen) {
+  if (p.tc == 3) return launch_tcw(p, stream, err, errlen);
   if (p.tc == 2 && p.n_nodes == 1) return launch_wpt_obwd(p, stream, err, errlen);
   if (p.tc == 2)
     return ctrl_cfg(p) == 521 ? launch_wpt(cc_wpt_bwd_kernel<CC_CTRL_TINY, 521>, p, true, stream, err, errlen) : launch_wpt(cc_wpt_bwd_kernel<CC_CTRL_TINY, 0>, p, true, stream, err, errlen);

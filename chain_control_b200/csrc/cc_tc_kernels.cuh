@@ -161,10 +161,8 @@ CC_DEV CcTcShared cc_tc_carve(float* smem, const CcKParams& p) {
 //   forward : B[n][k] = weight of f output n w.r.t. A column k ([x ; v ; 1] through the tail positions)
 //   backward: B[n'][k] = weight of f output k w.r.t. input n' (n' < S state, n' = SR + i input i): the transpose
 template <int SR>
-CC_DEV void cc_tc_stage_weights(const CcKParams& p, const CcNodeDev& M, const float* theta, const CcTcShared& sh, bool bwd, int tid, int nthreads) {
+CC_DEV void cc_tc_stage_b(const CcNodeDev& M, const float* theta, int KP, int NP, float* bhi, float* blo, bool bwd, int tid, int nthreads) {
   const CcLayerDev& F = M.f.layer[0];
-  const CcLayerDev& G = M.g.layer[0];
-  const int KP = p.tc_KP, NP = p.tc_NP;
   const int tb = cc_tc_tail_base(M.S, SR);
   for (int i = tid; i < KP * NP; i += nthreads) {
     const int n = i / KP, k = i % KP;
@@ -183,9 +181,14 @@ CC_DEV void cc_tc_stage_weights(const CcKParams& p, const CcNodeDev& M, const fl
     }
     const float hi = __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
     const int off = ((k >> 2) * NP + n) * 4 + (k & 3);
-    sh.bhi[off] = hi;
-    sh.blo[off] = w - hi;
+    bhi[off] = hi;
+    blo[off] = w - hi;
   }
+}
+// readout weights gw[o][SR + 4]: zero beyond S, bias at index SR
+template <int SR>
+CC_DEV void cc_tc_stage_gw(const CcNodeDev& M, const float* theta, float* gw, int tid, int nthreads) {
+  const CcLayerDev& G = M.g.layer[0];
   for (int i = tid; i < CC_TINY_O * (SR + 4); i += nthreads) {
     const int o = i / (SR + 4), s = i % (SR + 4);
     float w = 0.f;
@@ -193,8 +196,13 @@ CC_DEV void cc_tc_stage_weights(const CcKParams& p, const CcNodeDev& M, const fl
       if (s < M.S) w = cc_weight_at(M, G, theta, o, s);
       else if (s == SR) w = cc_weight_at(M, G, theta, o, M.row_one);
     }
-    sh.gw[i] = w;
+    gw[i] = w;
   }
+}
+template <int SR>
+CC_DEV void cc_tc_stage_weights(const CcKParams& p, const CcNodeDev& M, const float* theta, const CcTcShared& sh, bool bwd, int tid, int nthreads) {
+  cc_tc_stage_b<SR>(M, theta, p.tc_KP, p.tc_NP, sh.bhi, sh.blo, bwd, tid, nthreads);
+  cc_tc_stage_gw<SR>(M, theta, sh.gw, tid, nthreads);
 }
 
 // one batch of 3 * NA MMAs: D = A_lo.B_hi + A_hi.B_lo + A_hi.B_hi   (issued by ONE thread; fully unrolled with

@@ -58,6 +58,14 @@ CC_TC_DEV void cc_umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc,
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[smem desc, 128 x 8] . B[smem desc, N x 8]^T (both operands K-major in shared memory)
+CC_TC_DEV void cc_umma_tf32_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 
 CC_TC_DEV void cc_tmem_ld4(uint32_t addr, uint32_t (&r)[4]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"

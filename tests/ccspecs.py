@@ -63,4 +63,7 @@ def tc_open_model_variants():
     v["compact_s40_d0_i2_o3"] = O.make_node(40, 2, 3, f_depth=0, readout_pre_step=True, u_transform=O.UT_ARCTAN)
     v["full_s18_d0_i3_o2_euler"] = O.make_node(18, 3, 2, f_depth=0, integrator=O.INT_EE, f_act_final=O.ACT_TANH, g_act_final=O.ACT_TANH)
     v["full_s51_d0_i4_o4"] = O.make_node(51, 4, 4, f_depth=0)
+    # linear compact models: the reverse pass of the tcgen05 family includes the tensor-core weight gradient (cc_tcw_kernels.cuh)
+    v["compact_s20_d0_i2_o3"] = O.make_node(20, 2, 3, f_depth=0, readout_pre_step=True, u_transform=O.UT_ARCTAN)
+    v["compact_s44_d0_o2_nobias"] = O.make_node(44, 1, 2, f_depth=0, readout_pre_step=True, f_use_bias=False, g_use_bias=False)
     return v

@@ -83,7 +83,8 @@ def test_plan_picks_tcgen05_for_depth0_models():
     try:
         compact, ctrl = model_variants()["compact_s50_d0"], controller_variants()["compact_s5_d0"]
         assert fam(None, compact, 0) == 1            # open-loop forward
-        assert fam(None, compact, 1) == 0            # ModelTrainer reverse pass (weight gradients): FFMA kernel
+        assert fam(None, compact, 1) == 3            # ModelTrainer reverse pass: tcgen05 incl. the weight-gradient product
+        assert fam(None, tc_model_variants()["full_s20_d0"], 1) == 0   # post-step readout: FFMA reverse pass
         assert fam(ctrl, compact, 0) == 1 and fam(ctrl, compact, 1) == 1   # the bench workload, both directions
         assert fam(None, model_variants()["full_s5_w10_d2"], 0) == 0       # deep MLP
         assert fam(controller_variants()["full_s25_w10_d2"], compact, 0) == 0  # tile-sized controller
