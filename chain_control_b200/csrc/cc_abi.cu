@@ -133,6 +133,15 @@ struct PlanOpts {
   bool bwd = false;
 };
 
+// tcgen05 weight-gradient kernel (cc_tcw_kernels.cuh): trainable linear compact model (f, g without final activation, readout of
+// the pre-step state, RK4, room for [v ; 1] inside the state chunks); CC_B200_TCW=0 disables it
+bool tcw_eligible(const CcModule* model, int T) {
+  const char* wgenv = getenv("CC_B200_TCW");
+  const int nch = model->state_dim <= 32 ? 4 : 7;
+  return !(wgenv && atoi(wgenv) == 0) && tc_model_ok(model) && mlp_linear(model->f) && mlp_linear(model->g) && model->readout_pre_step &&
+         model->integrator == CC_INT_RK4 && model->state_dim + 5 <= 8 * nch && T >= 1;
+}
+
 bool node_is_tiny(const CcModule* m) {
   const int K0 = m->state_dim + ((m->f_time_variant || m->g_time_variant) ? 1 : 0) + m->input_dim + 1;
   return m->f.n_layers == 1 && m->g.n_layers == 1 && m->state_dim <= CC_TINY_S && K0 <= CC_TINY_K &&
@@ -340,21 +349,20 @@ int make_plan(const CcModule* const* mods, int n_nodes, long long B, int T, cons
   // of a handful of trajectories is bound by the per-stage latency, where a warp-level mat-vec beats an MMA batch
   // measured crossovers (gpurun_out/xover.log, S = 50): closed loop / forward 7.7 ms vs 11.8 ms (tcgen05) up to 1184 =
   // 148 SMs x 8 warps; the trainable open-loop reverse pass 28 ms at B = 4096 vs ~100 ms for the FFMA kernel (which is
-  // latency bound up to ~16K trajectories), so it keeps the latency kernel much longer; the open-loop forward pass
+  // latency bound up to ~16K trajectories), so it keeps the latency kernel much longer -- unless the tcgen05 weight-gradient
+  // kernel applies (17 ms for any B <= 148 x 128: it wins from the third latency wave on, B > 2 x 1184); the open-loop forward pass
   // alone breaks even at 4096 (6.55 ms vs 6.82 ms)
   const char* wenv = getenv("CC_B200_WPT_MAXB");
   const bool obwd = n_nodes == 1 && o.bwd;
-  const long long wmax = wenv ? atoll(wenv) : (obwd ? 12288 : (n_nodes == 1 ? 4096 : 1184));
+  const bool tcw_ok = obwd && tcw_eligible(model, T);
+  const long long wmax = wenv ? atoll(wenv) : (obwd ? (tcw_ok ? 2368 : 12288) : (n_nodes == 1 ? 4096 : 1184));
   const bool small = B <= wmax && model->state_dim + model->input_dim + 1 <= 56;
   if (p->tc && n_nodes == 1 && o.bwd && !small) {
     // large-batch ModelTrainer reverse pass: the weight gradient contracts over trajectories.  Linear compact models
     // (f, g without final activation, pre-step readout, RK4, room for [v ; 1] inside the state chunks): tcgen05 kernel
     // with an SS-mode weight-gradient product (cc_tcw_kernels.cuh); everything else: FFMA kernels
-    const char* wgenv = getenv("CC_B200_TCW");
     const int nch = model->state_dim <= 32 ? 4 : 7;
-    const bool tcw = !(wgenv && atoi(wgenv) == 0) && mlp_linear(model->f) && mlp_linear(model->g) && model->readout_pre_step &&
-                     model->integrator == CC_INT_RK4 && model->state_dim + 5 <= 8 * nch && T >= 1;
-    if (tcw) {
+    if (tcw_ok) {
       p->tc = 3;
       p->tc_nch = nch;
       p->tc_KP = 8 * nch;
@@ -363,6 +371,7 @@ int make_plan(const CcModule* const* mods, int n_nodes, long long B, int T, cons
       p->n_wtiles = (B + 127) / 128;  // one gradient record per CTA
       const int head = (int)((sizeof(CcKParams) + 15) / 16 * 4);
       p->tc_off = (head + 15) / 16 * 16;
+      p->tc_stagger = getenv("CC_B200_TCW_DEBUG") ? atoi(getenv("CC_B200_TCW_DEBUG")) : 0;  // (profiling switches, scratch)
       const int SR = 8 * nch;
       const long long bytes = ((long long)p->tc_off + 2LL * SR * p->tc_NP + 2LL * SR * ((SR + 15) / 16 * 16) + CC_TINY_O * (SR + 4) + 40 + 2LL * 16 * 1152) * 4;
       if (bytes > kSmemBudget) return fail(CC_ERR_UNSUPPORTED, "tcgen05 weight-gradient kernel: %lld B of shared memory per CTA", bytes);

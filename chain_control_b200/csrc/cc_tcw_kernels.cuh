@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(CC_TCW_THREADS, 1) cc_tcw_bwd_kernel(const CC_
           const bool adj = j < T, fwd = j >= 1 && w < 3;
           cc_tcw_issue_af<NCH>(tbase, wbh_u, wbl_u, wfh_u, wfl_u, adj, fwd);
           cc_tc_commit(d_ready);
-          if (adj) cc_tcw_issue_w(tbase, opa_u, opb_u, w == 0 ? 0u : 1u);
+          if (adj && !(p.tc_stagger & 1)) cc_tcw_issue_w(tbase, opa_u, opb_u, w == 0 ? 0u : 1u);
           cc_tc_commit(w_done);
         }
         __syncwarp();
@@ -268,8 +268,7 @@ __global__ void __launch_bounds__(CC_TCW_THREADS, 1) cc_tcw_bwd_kernel(const CC_
 #pragma unroll
             for (int i = 0; i < CC_TINY_O; ++i) { utb[i] = 0.f; dprev[i] = d[i]; }
             const float c0 = h / 6.f;
-            cc_tcw_adj_first<SR, 0, 16>(aD, aHi, aLo, gw, lam, zsum, have_prev, dprev, M.O, c0);
-            cc_tcw_adj_first<SR, 16, 16>(aD, aHi, aLo, gw, lam, zsum, have_prev, dprev, M.O, c0);
+            cc_tcw_adj_first<SR, 0, 32>(aD, aHi, aLo, gw, lam, zsum, have_prev, dprev, M.O, c0);
             if constexpr (SR == 56) {
               cc_tcw_adj_first<SR, 32, 16>(aD, aHi, aLo, gw, lam, zsum, have_prev, dprev, M.O, c0);
               cc_tcw_adj_first<SR, 48, 8>(aD, aHi, aLo, gw, lam, zsum, have_prev, dprev, M.O, c0);
@@ -287,8 +286,7 @@ __global__ void __launch_bounds__(CC_TCW_THREADS, 1) cc_tcw_bwd_kernel(const CC_
             }
           } else {
             const float ca = w == 3 ? h / 6.f : h / 3.f, cb = w == 1 ? h : h / 2.f;
-            cc_tc_bwd_group<SR, 0, 16, false>(aD, aHi, aLo, lam, zsum, ca, cb);
-            cc_tc_bwd_group<SR, 16, 16, false>(aD, aHi, aLo, lam, zsum, ca, cb);
+            cc_tc_bwd_group<SR, 0, 32, false>(aD, aHi, aLo, lam, zsum, ca, cb);
             if constexpr (SR == 56) {
               cc_tc_bwd_group<SR, 32, 16, false>(aD, aHi, aLo, lam, zsum, ca, cb);
               cc_tc_bwd_group<SR, 48, 8, false>(aD, aHi, aLo, lam, zsum, ca, cb);
@@ -301,7 +299,7 @@ __global__ void __launch_bounds__(CC_TCW_THREADS, 1) cc_tcw_bwd_kernel(const CC_
           }
         }
         if (!first) await_w();
-        if (on) {
+        if (on && !(p.tc_stagger & 2)) {
           if (w == 0 && j < T - 1) flush(0);
           // operand A of the weight gradient: the split kbar just written to TMEM, rows n (hi) / 64 + n (lo)
           cc_tmem_wait_st();
@@ -401,8 +399,7 @@ __global__ void __launch_bounds__(CC_TCW_THREADS, 1) cc_tcw_bwd_kernel(const CC_
             const float cz = w == 3 ? 1.f : 0.5f;
             float* slot = scr + (w == 1 ? s2c : (w == 2 ? 1 : s4c)) * SR * 128;
             const bool tt = w < 3;
-            cc_tcw_fwd_group<SR, 0, 16>(aD, aHi, aLo, x, h, cz, tt, slot);
-            cc_tcw_fwd_group<SR, 16, 16>(aD, aHi, aLo, x, h, cz, tt, slot);
+            cc_tcw_fwd_group<SR, 0, 32>(aD, aHi, aLo, x, h, cz, tt, slot);
             if constexpr (SR == 56) {
               cc_tcw_fwd_group<SR, 32, 16>(aD, aHi, aLo, x, h, cz, tt, slot);
               cc_tcw_fwd_group<SR, 48, 8>(aD, aHi, aLo, x, h, cz, tt, slot);
@@ -413,7 +410,7 @@ __global__ void __launch_bounds__(CC_TCW_THREADS, 1) cc_tcw_bwd_kernel(const CC_
           for (int i = 0; i < CC_TINY_O; ++i) vdut[i] = vch[i];
         }
         if (!first) await_w();
-        if (duty) {
+        if (duty && !(p.tc_stagger & 2)) {
           if (w == 0) {
             if (j < T - 1) flush(32);
 #pragma unroll
