@@ -77,8 +77,8 @@ F_M = 2 * (4 * (50 + 1) * 50 + 50)    # 20,500
 # dram read+write bytes per trajectory-step of cc_tc_bwd_kernel from the ncu --set full capture (profiles/r01_tc_ncu_full.md);
 # None until a capture of the current kernel exists
 TRAFFIC_TC_BWD_BYTES_PER_TS = 32.4  # (2.120 GB read + 0.008 GB written) / (65,536 x 1,001)
-# same for cc_tcw_bwd_kernel (ModelTrainer reverse pass): (208.8 MB read + 6.7 MB written) / (16,384 x 60), gpurun_out/prof_tcw2
-TRAFFIC_TCW_BWD_BYTES_PER_TS = 219.2
+# same for cc_tcw_bwd_kernel (ModelTrainer reverse pass): (13.663 GB read + 0.065 GB written) / (65,536 x 1,000), profiles/r01_tcw_ncu_full.md
+TRAFFIC_TCW_BWD_BYTES_PER_TS = 209.5
 
 
 def alg_flops(closed):
@@ -388,7 +388,7 @@ def main():
             roofline = {"bound": "tensor", "kernel": bwd_kernel, "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
                         "frac": achieved / tf32_peak,
                         "traffic": bwd_traffic * units if bwd_traffic else None,
-                        "traffic_source": "ncu --set full capture of the same kernel (profiles/r01_tc_ncu_full.md), dram read+write per trajectory-step x units of this launch",
+                        "traffic_source": "ncu --set full capture of the same kernel (profiles/r01_tc_ncu_full.md, r01_tcw_ncu_full.md), dram read+write per trajectory-step x units of this launch",
                         "peak_source": "MEASURED_PEAKS.json dense bf16 (sustained) / 2 = dense TF32; the kernel issues tcgen05.mma kind::tf32",
                         "alg_flops_per_traj_step": tot_f - fwd_f, "launch_ms": bwd_ms,
                         "executed": {"tflops": units * exec_flops_ts / (bwd_ms * 1e-3) / 1e12, "frac": units * exec_flops_ts / (bwd_ms * 1e-3) / 1e12 / tf32_peak,

@@ -79,10 +79,57 @@ CC_DEV void cc_tcw_issue_w(uint32_t tbase, uint64_t opa, uint64_t opb, uint32_t 
   }
 }
 
+// split NC values into tf32 hi / exact lo and store them both to the TMEM A operand (columns c0..) and to the shared-memory
+// operand of the weight gradient (rows c0.. hi, 64 + c0.. lo; `op` already points at this thread's trajectory column)
+template <int NC>
+CC_DEV void cc_tcw_store_split2(uint32_t aHi, uint32_t aLo, float* op, int c0_dummy, const float (&z)[NC], const int C0) {
+  (void)c0_dummy;
+#pragma unroll
+  for (int j = 0; j < NC / 8; ++j) {
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+      const float v0 = z[8 * j + i], v1 = z[8 * j + i + 1];
+      hi[i] = __float_as_uint(v0) & 0xFFFFE000u;
+      hi[i + 1] = __float_as_uint(v1) & 0xFFFFE000u;
+      const float2 l = __fadd2_rn(make_float2(v0, v1), make_float2(-__uint_as_float(hi[i]), -__uint_as_float(hi[i + 1])));
+      lo[i] = __float_as_uint(l.x);
+      lo[i + 1] = __float_as_uint(l.y);
+    }
+    cc_tmem_st8(aHi + C0 + 8 * j, hi);
+    cc_tmem_st8(aLo + C0 + 8 * j, lo);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      op[cc_tcw_row(C0 + 8 * j + i)] = __uint_as_float(hi[i]);
+      op[cc_tcw_row(64 + C0 + 8 * j + i)] = __uint_as_float(lo[i]);
+    }
+  }
+}
+// generic adjoint stage for columns [C0, C0+NC): zb = D ; zsum += zb ; kbar = ca*lam + cb*zb -> A (TMEM) and operand rows.
+// `before_store` runs between the arithmetic and the first store (the operand buffer is free only behind w_done)
+template <int SR, int C0, int NC, class W>
+CC_DEV void cc_tcw_adj_group(uint32_t aD, uint32_t aHi, uint32_t aLo, float* opa, float (&lam)[SR], float (&zsum)[SR], float ca, float cb, W&& before_store) {
+  uint32_t r[NC];
+  cc_tc_ld<NC>(aD + C0, r);
+  cc_tmem_wait_ld();
+  float kb[NC];
+  const float2 ca2 = make_float2(ca, ca), cb2 = make_float2(cb, cb);
+#pragma unroll
+  for (int i = 0; i < NC; i += 2) {
+    const float2 zb = make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+    const float2 zs = __fadd2_rn(make_float2(zsum[C0 + i], zsum[C0 + i + 1]), zb);
+    zsum[C0 + i] = zs.x; zsum[C0 + i + 1] = zs.y;
+    const float2 kk = __ffma2_rn(ca2, make_float2(lam[C0 + i], lam[C0 + i + 1]), __fmul2_rn(cb2, zb));
+    kb[i] = kk.x; kb[i + 1] = kk.y;
+  }
+  before_store();
+  cc_tcw_store_split2<NC>(aHi, aLo, opa, 0, kb, C0);
+}
+
 // first window of a step (adjoint chain): finish the previous step (lam <- lam + zsum + zbar_1 + g^T d), then kbar_4 = c0*lam -> A
-template <int SR, int C0, int NC>
-CC_DEV void cc_tcw_adj_first(uint32_t aD, uint32_t aHi, uint32_t aLo, const float* gw, float (&lam)[SR], float (&zsum)[SR], bool have_prev,
-                             const float (&dprev)[CC_TINY_O], int O, float c0) {
+template <int SR, int C0, int NC, class W>
+CC_DEV void cc_tcw_adj_first(uint32_t aD, uint32_t aHi, uint32_t aLo, float* opa, const float* gw, float (&lam)[SR], float (&zsum)[SR], bool have_prev,
+                             const float (&dprev)[CC_TINY_O], int O, float c0, W&& before_store) {
   uint32_t r[NC];
 #pragma unroll
   for (int i = 0; i < NC; ++i) r[i] = 0u;
@@ -104,7 +151,8 @@ CC_DEV void cc_tcw_adj_first(uint32_t aD, uint32_t aHi, uint32_t aLo, const floa
     zsum[C0 + i] = 0.f;
     kb[i] = c0 * l;
   }
-  cc_tc_store_split<NC>(aHi, aLo, C0, kb);
+  before_store();
+  cc_tcw_store_split2<NC>(aHi, aLo, opa, 0, kb, C0);
 }
 // recompute chain: z = x + (h*k)*cz for columns [C0, C0+NC) -> A (if another stage follows) and -> the scratch slot
 template <int SR, int C0, int NC>
@@ -254,6 +302,9 @@ __global__ void __launch_bounds__(CC_TCW_THREADS, 1) cc_tcw_bwd_kernel(const CC_
       for (int w = 0; w < 4; ++w) {
         const bool first = j == T && w == 0;
         if (!first) await_d();
+        bool waited = first;  // the operand buffer may be rewritten only behind w_done: waited for right before the first store
+        auto before_store = [&]() { if (!waited) { await_w(); waited = true; } };
+        auto nop = []() {};
         if (on) {
           if (w == 0) {
             const bool have_prev = j < T - 1;
@@ -268,10 +319,10 @@ __global__ void __launch_bounds__(CC_TCW_THREADS, 1) cc_tcw_bwd_kernel(const CC_
 #pragma unroll
             for (int i = 0; i < CC_TINY_O; ++i) { utb[i] = 0.f; dprev[i] = d[i]; }
             const float c0 = h / 6.f;
-            cc_tcw_adj_first<SR, 0, 32>(aD, aHi, aLo, gw, lam, zsum, have_prev, dprev, M.O, c0);
+            cc_tcw_adj_first<SR, 0, 32>(aD, aHi, aLo, opa, gw, lam, zsum, have_prev, dprev, M.O, c0, before_store);
             if constexpr (SR == 56) {
-              cc_tcw_adj_first<SR, 32, 16>(aD, aHi, aLo, gw, lam, zsum, have_prev, dprev, M.O, c0);
-              cc_tcw_adj_first<SR, 48, 8>(aD, aHi, aLo, gw, lam, zsum, have_prev, dprev, M.O, c0);
+              cc_tcw_adj_first<SR, 32, 16>(aD, aHi, aLo, opa, gw, lam, zsum, have_prev, dprev, M.O, c0, nop);
+              cc_tcw_adj_first<SR, 48, 8>(aD, aHi, aLo, opa, gw, lam, zsum, have_prev, dprev, M.O, c0, nop);
             }
             // this step's readout cotangent d = os * ybar (y_{k+1} = g(x_k); y_0 = g(x_0) joins step 0) and raw input
 #pragma unroll
@@ -286,10 +337,10 @@ __global__ void __launch_bounds__(CC_TCW_THREADS, 1) cc_tcw_bwd_kernel(const CC_
             }
           } else {
             const float ca = w == 3 ? h / 6.f : h / 3.f, cb = w == 1 ? h : h / 2.f;
-            cc_tc_bwd_group<SR, 0, 32, false>(aD, aHi, aLo, lam, zsum, ca, cb);
+            cc_tcw_adj_group<SR, 0, 32>(aD, aHi, aLo, opa, lam, zsum, ca, cb, before_store);
             if constexpr (SR == 56) {
-              cc_tc_bwd_group<SR, 32, 16, false>(aD, aHi, aLo, lam, zsum, ca, cb);
-              cc_tc_bwd_group<SR, 48, 8, false>(aD, aHi, aLo, lam, zsum, ca, cb);
+              cc_tcw_adj_group<SR, 32, 16>(aD, aHi, aLo, opa, lam, zsum, ca, cb, nop);
+              cc_tcw_adj_group<SR, 48, 8>(aD, aHi, aLo, opa, lam, zsum, ca, cb, nop);
             }
             uint32_t r[4];
             cc_tmem_ld4(aD + SR, r);  // vbar columns
@@ -298,23 +349,9 @@ __global__ void __launch_bounds__(CC_TCW_THREADS, 1) cc_tcw_bwd_kernel(const CC_
             for (int i = 0; i < CC_TINY_O; ++i) utb[i] += __uint_as_float(r[i]);
           }
         }
-        if (!first) await_w();
+        before_store();
         if (on && !(p.tc_stagger & 2)) {
           if (w == 0 && j < T - 1) flush(0);
-          // operand A of the weight gradient: the split kbar just written to TMEM, rows n (hi) / 64 + n (lo)
-          cc_tmem_wait_st();
-#pragma unroll
-          for (int c = 0; c < SR / 8; ++c) {
-            uint32_t hi[8], lo[8];
-            cc_tmem_ld8(aHi + 8 * c, hi);
-            cc_tmem_ld8(aLo + 8 * c, lo);
-            cc_tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              opa[cc_tcw_row(8 * c + i)] = __uint_as_float(hi[i]);
-              opa[cc_tcw_row(64 + 8 * c + i)] = __uint_as_float(lo[i]);
-            }
-          }
           if (w == 0 || w == 3) {
 #pragma unroll
             for (int o = 0; o < CC_TINY_O; ++o) {
