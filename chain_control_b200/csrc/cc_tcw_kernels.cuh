@@ -289,6 +289,19 @@ __global__ void __launch_bounds__(CC_TCW_THREADS, 1) cc_tcw_bwd_kernel(const CC_
 #pragma unroll
     for (int i = 0; i < CC_TINY_O; ++i) { utb[i] = 0.f; d[i] = 0.f; dprev[i] = 0.f; ucur[i] = 0.f; }
     const long long yrow = (long long)(T + 1) * M.O;
+    float nyb[CC_TINY_O], nu[CC_TINY_O];
+    auto fetch_yu = [&](int k) {  // ybar of y_{k+1} = g(x_k) (y_0 = g(x_0) joins step 0) and u_k, one step ahead of their use
+#pragma unroll
+      for (int o = 0; o < CC_TINY_O; ++o) {
+        nyb[o] = 0.f;
+        if (o < M.O && act) {
+          nyb[o] = __ldg(p.ybar + b * yrow + (long long)(k + 1) * M.O + o);
+          if (k == 0) nyb[o] += __ldg(p.ybar + b * yrow + o);
+        }
+        nu[o] = (o < M.I && act) ? __ldg(p.in + b * (long long)T * M.I + (long long)k * M.I + o) : 0.f;
+      }
+    };
+    fetch_yu(T - 1);
     auto write_ubar = [&](int k) {  // cotangent of the raw input of step k (its four vbar are summed in utb; ucur = u_k)
       if (p.ubar && act)
 #pragma unroll
@@ -324,17 +337,9 @@ __global__ void __launch_bounds__(CC_TCW_THREADS, 1) cc_tcw_bwd_kernel(const CC_
               cc_tcw_adj_first<SR, 32, 16>(aD, aHi, aLo, opa, gw, lam, zsum, have_prev, dprev, M.O, c0, nop);
               cc_tcw_adj_first<SR, 48, 8>(aD, aHi, aLo, opa, gw, lam, zsum, have_prev, dprev, M.O, c0, nop);
             }
-            // this step's readout cotangent d = os * ybar (y_{k+1} = g(x_k); y_0 = g(x_0) joins step 0) and raw input
+            // this step's readout cotangent and raw input (fetched three windows ago)
 #pragma unroll
-            for (int o = 0; o < CC_TINY_O; ++o) {
-              d[o] = 0.f;
-              if (o < M.O && act) {
-                float yb = __ldg(p.ybar + b * yrow + (long long)(j + 1) * M.O + o);
-                if (j == 0) yb += __ldg(p.ybar + b * yrow + o);
-                d[o] = os * yb;
-              }
-              ucur[o] = (o < M.I && act) ? __ldg(p.in + b * (long long)T * M.I + (long long)j * M.I + o) : 0.f;
-            }
+            for (int o = 0; o < CC_TINY_O; ++o) { d[o] = os * nyb[o]; ucur[o] = nu[o]; }
           } else {
             const float ca = w == 3 ? h / 6.f : h / 3.f, cb = w == 1 ? h : h / 2.f;
             cc_tcw_adj_group<SR, 0, 32>(aD, aHi, aLo, opa, lam, zsum, ca, cb, before_store);
@@ -363,6 +368,7 @@ __global__ void __launch_bounds__(CC_TCW_THREADS, 1) cc_tcw_bwd_kernel(const CC_
           }
         }
         publish();
+        if (on && w == 1 && j >= 1) fetch_yu(j - 1);
       }
     }
     await_d();
