@@ -160,8 +160,10 @@ CC_DEV CcTcShared cc_tc_carve(float* smem, const CcKParams& p) {
 // element (n, k) at ((k/4)*NP + n)*4 + k%4  ->  8x16-byte core matrices, SBO = 128 B, LBO = NP*16 B.
 //   forward : B[n][k] = weight of f output n w.r.t. A column k ([x ; v ; 1] through the tail positions)
 //   backward: B[n'][k] = weight of f output k w.r.t. input n' (n' < S state, n' = SR + i input i): the transpose
+// gfold (reverse pass of the trainable model, cc_tcw_kernels.cuh): contraction index k = S + o carries g's weight of output o, so that a
+// readout cotangent d_o placed in column S + o of kbar adds g^T d to the state adjoint inside the same MMA batch
 template <int SR>
-CC_DEV void cc_tc_stage_b(const CcNodeDev& M, const float* theta, int KP, int NP, float* bhi, float* blo, bool bwd, int tid, int nthreads) {
+CC_DEV void cc_tc_stage_b(const CcNodeDev& M, const float* theta, int KP, int NP, float* bhi, float* blo, bool bwd, int tid, int nthreads, bool gfold = false) {
   const CcLayerDev& F = M.f.layer[0];
   const int tb = cc_tc_tail_base(M.S, SR);
   for (int i = tid; i < KP * NP; i += nthreads) {
@@ -178,6 +180,7 @@ CC_DEV void cc_tc_stage_b(const CcNodeDev& M, const float* theta, int KP, int NP
       if (n < M.S) lr = n;
       else if (n >= SR && n < SR + M.I) lr = M.row_v + (n - SR);
       if (lr >= 0 && k < M.S) w = cc_weight_at(M, F, theta, k, lr);
+      if (gfold && n < M.S && k >= M.S && k < M.S + M.O) w = cc_weight_at(M, M.g.layer[0], theta, k - M.S, n);
     }
     const float hi = __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
     const int off = ((k >> 2) * NP + n) * 4 + (k & 3);

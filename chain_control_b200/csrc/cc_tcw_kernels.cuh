@@ -142,10 +142,7 @@ CC_DEV void cc_tcw_adj_first(uint32_t aD, uint32_t aHi, uint32_t aLo, float* opa
   for (int i = 0; i < NC; ++i) {
     float l = lam[C0 + i];
     if (have_prev) {
-      l = l + (zsum[C0 + i] + __uint_as_float(r[i]));
-#pragma unroll
-      for (int o = 0; o < CC_TINY_O; ++o)
-        if (o < O) l = fmaf(gw[o * (SR + 4) + C0 + i], dprev[o], l);
+      l = l + (zsum[C0 + i] + __uint_as_float(r[i]));  // (zbar_1 already contains g^T d: the readout cotangent rides in kbar_1's columns S + o)
     }
     lam[C0 + i] = l;
     zsum[C0 + i] = 0.f;
@@ -194,7 +191,7 @@ __global__ void __launch_bounds__(CC_TCW_THREADS, 1) cc_tcw_bwd_kernel(const CC_
   float* opA = gw + CC_TINY_O * (SR + 4) + 8;
   opA += ((128u - (cc_smem_u32(opA) & 127u)) & 127u) / 4;  // operand buffers on a 128-byte boundary
   float* opB = opA + CC_TCW_OPER_FLOATS;
-  cc_tc_stage_b<SR>(M, p.theta[0], SR, NPB, wbh, wbl, true, tid, blockDim.x);
+  cc_tc_stage_b<SR>(M, p.theta[0], SR, NPB, wbh, wbl, true, tid, blockDim.x, true);
   cc_tc_stage_b<SR>(M, p.theta[0], SR, NPF, wfh, wfl, false, tid, blockDim.x);
   cc_tc_stage_gw<SR>(M, p.theta[0], gw, tid, blockDim.x);
   if (warp == 8) {
@@ -352,6 +349,16 @@ __global__ void __launch_bounds__(CC_TCW_THREADS, 1) cc_tcw_bwd_kernel(const CC_
             cc_tmem_wait_ld();
 #pragma unroll
             for (int i = 0; i < CC_TINY_O; ++i) utb[i] += __uint_as_float(r[i]);
+            if (w == 3) {  // stage 1: the readout cotangent joins kbar_1 in the (otherwise zero) columns S + o -> zbar_1 += g^T d
+              uint32_t dh[4], dl[4];
+#pragma unroll
+              for (int o = 0; o < CC_TINY_O; ++o) {
+                dh[o] = __float_as_uint(d[o]) & 0xFFFFE000u;
+                dl[o] = __float_as_uint(d[o] - __uint_as_float(dh[o]));
+              }
+              cc_tmem_st4(aHi + M.S, dh);
+              cc_tmem_st4(aLo + M.S, dl);
+            }
           }
         }
         before_store();
