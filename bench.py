@@ -77,8 +77,8 @@ F_M = 2 * (4 * (50 + 1) * 50 + 50)    # 20,500
 # dram read+write bytes per trajectory-step of cc_tc_bwd_kernel from the ncu --set full capture (profiles/r01_tc_ncu_full.md);
 # None until a capture of the current kernel exists
 TRAFFIC_TC_BWD_BYTES_PER_TS = 32.4  # (2.120 GB read + 0.008 GB written) / (65,536 x 1,001)
-# same for cc_tcw_bwd_kernel (ModelTrainer reverse pass): (13.663 GB read + 0.065 GB written) / (65,536 x 1,000), profiles/r01_tcw_ncu_full.md
-TRAFFIC_TCW_BWD_BYTES_PER_TS = 209.5
+# same for cc_tcw_bwd_kernel (ModelTrainer reverse pass): (13.658 GB read + 0.064 GB written) / (65,536 x 1,000), profiles/r01_tcw_ncu_full.md
+TRAFFIC_TCW_BWD_BYTES_PER_TS = 209.4
 
 
 def alg_flops(closed):

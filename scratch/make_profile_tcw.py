@@ -27,8 +27,9 @@ md += ["", "Reading.",
        "  gradient sums are written and re-read by the same thread and stay in L2: hit rate %s %%)." % v.get("lts__t_sector_hit_rate.pct", "?"),
        "* %.0f active cycles per step and round (%d tiles on 148 SMs = %d round(s)) = %.1f k cycles per window (4 windows per step); tensor pipe active %s %% of the" % (cyc / T / rounds, tiles, rounds, cyc / T / rounds / 4 / 1e3, v.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "?")),
        "  active cycles: the kernel is bound by the per-window dependent chain of the ONE tile an SM holds (barrier → 42 TS-mode MMAs → tcgen05.ld → epilogue → tcgen05.st / operand stores → barrier),",
-       "  not by a pipe.  Ablations (`CC_B200_TCW_DEBUG`, B = 16,384 × 1000): 16.9 ms; without the weight-gradient MMAs 16.0 ms; without the operand stores 13.9 ms; without both 12.9 ms.",
+       "  not by a pipe.  Ablations (`CC_B200_TCW_DEBUG`, B = 16,384 × 1000, at the 16.9 ms state): without the weight-gradient MMAs 16.0 ms; without the operand stores 13.9 ms; without both 12.9 ms.",
        "* History (reverse pass of 16,384 × 1000): first version (288 threads, 168 registers, spills) 23.2 ms → setmaxnreg 56/224 with lean descriptor arithmetic in the issuing thread 25.1 ms (40-register issuer with",
-       "  spilled descriptors: 46 ms) → pointer-walk tape/slot addressing (20 → 3 instructions per row; `no_instruction` stalls gone) **17.0 ms**; 65,536 × 1000: 416 ms (FFMA kernel) → **67 ms**.", ""]
+       "  spilled descriptors: 46 ms) → pointer-walk tape/slot addressing (20 → 3 instructions per row; `no_instruction` stalls gone) 17.0 ms → ybar/u fetched one step ahead 16.7 ms →",
+       "  g^T d folded into the adjoint MMA (the readout cotangent rides in k̄_1's spare columns; 224 shared-memory reads per thread and step less) **15.1 ms**; 65,536 × 1000: 416 ms (FFMA kernel) → **59.4 ms**.", ""]
 open('profiles/r01_tcw_ncu_full.md', 'w').write("\n".join(md))
 print("\n".join(md[-9:]))
