@@ -373,8 +373,8 @@ def main():
         cm, mm = ctrl.to_c(), model.to_c()
         fam_f = L.cc_kernel_family_at(_C.byref(cm) if closed else None, _C.byref(mm), 0, B)
         fam_b = L.cc_kernel_family_at(_C.byref(cm) if closed else None, _C.byref(mm), 1, B)
-        fam_name = {0: "ffma", 1: "tcgen05", 2: "latency", 3: "tcgen05"}
-        tensor = fam_b in (1, 3)
+        fam_name = {0: "ffma", 1: "tcgen05", 2: "latency", 3: "tcgen05", 4: "blocked-linear tcgen05"}
+        tensor = fam_b in (1, 3, 4)
         bf16_peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 2250.0 * 0.62))
         tf32_peak = bf16_peak / 2.0
         exec_flops_ts = 3 * 2 * 64 * 56 * 4  # per trajectory-step of one rollout kernel (forward or reverse): 3 x 2 x NP x KP x stages
@@ -384,6 +384,10 @@ def main():
             exec_flops_ts = 3 * 2 * 64 * 56 * (4 + 3) + 2 * 2 * 128 * 64 * 4
             exec_note = "3xTF32: adjoint + recomputed stage inputs (128 x 64 x 56 tiles) + SS-mode weight-gradient product (hi/lo rows stacked: 2 x M128 x N64 per trajectory and stage)"
             bwd_kernel, bwd_traffic = "cc_tcw_bwd_kernel", TRAFFIC_TCW_BWD_BYTES_PER_TS
+        if fam_b == 4:
+            exec_flops_ts = 3 * 2 * 64 * 64 / 13.0
+            exec_note = "blocked linear kernels: one 3xTF32 128 x 64 x 64 MMA batch per 13 steps"
+            bwd_kernel, bwd_traffic = ("cc_lin_cl_bwd_kernel" if closed else "cc_linw_bwd_kernel"), None
         if tensor:
             roofline = {"bound": "tensor", "kernel": bwd_kernel, "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
                         "frac": achieved / tf32_peak,

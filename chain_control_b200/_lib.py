@@ -25,11 +25,13 @@ _SIGS = {
     "cc_kernel_family_at": (_i32, [_M, _M, _i32, _i64]),
     "cc_rollout_tape_bytes": (_sz, [_M, _i64, _i32, _i32]),
     "cc_rollout_workspace_bytes": (_sz, [_M, _i64, _i32, _i32]),
-    "cc_rollout_fwd": (_i32, [_M, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp]),
+    "cc_rollout_fwd_workspace_bytes": (_sz, [_M, _i64, _i32]),
+    "cc_rollout_fwd": (_i32, [_M, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _sz, _vp]),
     "cc_rollout_bwd": (_i32, [_M, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _i32, _vp, _sz, _vp]),
     "cc_closedloop_tape_bytes": (_sz, [_M, _M, _i64, _i32, _i32]),
     "cc_closedloop_workspace_bytes": (_sz, [_M, _M, _i64, _i32, _i32]),
-    "cc_closedloop_fwd": (_i32, [_M, _M, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp]),
+    "cc_closedloop_fwd_workspace_bytes": (_sz, [_M, _M, _i64, _i32]),
+    "cc_closedloop_fwd": (_i32, [_M, _M, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _sz, _vp]),
     "cc_closedloop_bwd": (_i32, [_M, _M, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _i32, _vp, _sz, _vp]),
     "cc_mse_value_and_cotangent": (_i32, [_vp, _vp, _vp, _vp, _i64, C.c_float, _vp]),
     "cc_fp32_peak_probe": (_i32, [_vp, _i32, _vp]),

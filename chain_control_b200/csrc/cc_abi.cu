@@ -26,6 +26,9 @@
 #define CC_TN_VALUE 16
 #include "cc_tn.cu"
 #undef CC_TN_VALUE
+#include "cc_lin.cu"
+#else
+#include "cc_lin.h"
 #endif
 
 namespace {
@@ -120,6 +123,34 @@ bool tc_eligible(const CcModule* const* mods, int n_nodes, bool bwd) {
   return true;
 }
 
+// blocked linear family (cc_lin.h): the model's f and g are single Linear layers with identity final activation,
+// time-invariant, any integrator; room for at least one step slot next to the state inside 64 columns.  Closed loop: SISO
+// model and the tiny controller.  CC_B200_LIN=0 disables the family (the tcgen05 / latency / FFMA kernels take over).
+int lin_block_len(const CcModule* m) {
+  const int w = m->input_dim > m->output_dim ? m->input_dim : m->output_dim;
+  int slots = 63 - m->state_dim;  // columns between the state block and the constant-1 column
+  if (slots > CC_LIN_MAXM) slots = CC_LIN_MAXM;  // the kernels keep at most 13 slots (columns 50..62) in registers
+  return slots / (w > 0 ? w : 1);
+}
+bool lin_model_ok(const CcModule* m) {
+  return mlp_linear(m->f) && mlp_linear(m->g) && !m->f_time_variant && !m->g_time_variant && !m->g_feedthrough_u &&
+         m->input_dim >= 1 && m->input_dim <= CC_TINY_O && m->output_dim <= CC_TINY_O && lin_block_len(m) >= 1;
+}
+bool lin_eligible(const CcModule* const* mods, int n_nodes, bool bwd) {
+  const char* env = getenv("CC_B200_LIN");
+  if (env && atoi(env) == 0) return false;
+  const CcModule* model = mods[n_nodes - 1];
+  if (!lin_model_ok(model)) return false;
+  if (n_nodes == 2) return model->input_dim == 1 && model->output_dim == 1 && node_is_tiny(mods[0]) && mods[0]->input_dim <= CC_TINY_O;
+#ifdef CC_LIN_OPEN
+  (void)bwd;
+  return true;
+#else
+  (void)bwd;
+  return false;
+#endif
+}
+
 struct Alloc {
   int off = 0;
   int take(int nfloats) {
@@ -131,6 +162,7 @@ struct Alloc {
 
 struct PlanOpts {
   bool bwd = false;
+  bool exact_end = false;  // open loop: the state after the LAST step is requested (x_final)
 };
 
 // tcgen05 weight-gradient kernel (cc_tcw_kernels.cuh): trainable linear compact model (f, g without final activation, readout of
@@ -344,6 +376,27 @@ int make_plan(const CcModule* const* mods, int n_nodes, long long B, int T, cons
     p->nd[0].tape_row = 0;
     p->tape_rows = p->nd[0].S;
   }
+  if (lin_eligible(mods, n_nodes, o.bwd)) {
+    p->tc = 4;
+    layout(p, o.bwd);
+    p->lin_m = lin_block_len(model);
+    const char* ms = getenv("CC_B200_LIN_M");  // (tests: other block lengths)
+    if (ms && atoi(ms) >= 1 && atoi(ms) < p->lin_m) p->lin_m = atoi(ms);
+    if (n_nodes == 1) {
+      // open loop: the MMA chain carries x_k itself, so a ragged last block would end BEHIND step T; when the final state
+      // is requested the block length divides T (T = 1, the step() call, runs with m = 1)
+      if (T >= 1 && T < p->lin_m) p->lin_m = T;
+      if (o.exact_end && T >= 1 && T % p->lin_m) p->lin_mt = T % p->lin_m;  // (a second prep pack serves the tail)
+    }
+    const char* sg = getenv("CC_B200_LIN_STAGE");
+    const bool siso = n_nodes == 2 ? p->R == 1 : (model->input_dim == 1 && model->output_dim == 1);
+    p->lin_stage = (siso && !(sg && atoi(sg) == 0)) ? 1 : 0;
+    p->wpc = 4;
+    p->n_wtiles = (B + 31) / 32;
+    if (getenv("CC_B200_VERBOSE"))
+      fprintf(stderr, "[ccb200] blocked linear plan: nodes=%d bwd=%d B=%lld T=%d m=%d stage=%d ctas=%lld\n", n_nodes, (int)o.bwd, B, T, p->lin_m, p->lin_stage, (B + 127) / 128);
+    return CC_OK;
+  }
   layout(p, o.bwd);
   // small batches: the latency kernels (one warp per trajectory, cc_wpt_kernels.cuh) -- a 1001-step dependent chain
   // of a handful of trajectories is bound by the per-stage latency, where a warp-level mat-vec beats an MMA batch
@@ -464,8 +517,26 @@ int cc_launch_bwd_tn16(const CcKParams& p, void* stream, char* err, int errlen);
 #ifndef CC_EMULATE
 int cc_launch_fwd_tc(const CcKParams& p, void* stream, char* err, int errlen);
 int cc_launch_bwd_tc(const CcKParams& p, void* stream, char* err, int errlen);
+int cc_launch_lin_prep(const CcNodeDev& M, const float* theta, float* pack, double* tab, int m, int form, void* stream, char* err, int errlen);
+int cc_launch_lin(const CcKParams& p, bool bwd, void* stream, char* err, int errlen);
+int cc_launch_lin_grad(const CcLinGradArgs& a, void* stream, char* err, int errlen);
 #endif
 namespace {
+// blocked linear family: the fp64 preparation kernel writes the block matrices into the workspace, then the rollout kernel runs
+int launch_lin(CcKParams& p, bool bwd, float* pack, void* stream) {
+  g_launches.fetch_add(2);
+  const CcNodeDev& M = p.nd[p.n_nodes - 1];
+  int rc = cc_launch_lin_prep(M, p.theta[p.n_nodes - 1], pack, p.lin_tab, p.lin_m, p.n_nodes == 2 ? 0 : 1, stream, g_err, sizeof(g_err));
+  if (rc) return rc;
+  if (!bwd && p.lin_mt > 0) {  // block matrices of the ragged tail (open-loop x_final)
+    g_launches.fetch_add(1);
+    rc = cc_launch_lin_prep(M, p.theta[p.n_nodes - 1], pack + CC_LIN_PACK_FLOATS, nullptr, p.lin_mt, 1, stream, g_err, sizeof(g_err));
+    if (rc) return rc;
+  }
+  p.lin_pack = pack;
+  return cc_launch_lin(p, bwd, stream, g_err, sizeof(g_err));
+}
+size_t lin_pack_bytes() { return 2 * (size_t)CC_LIN_PACK_FLOATS * sizeof(float); }  // (main pack + ragged-tail pack)
 int launch_fwd(const CcKParams& p, void* stream) {
   g_launches.fetch_add(1);
 #ifndef CC_EMULATE
@@ -489,7 +560,7 @@ int n_ckpt_of(int T, int every) { return (T + every - 1) / every; }
 
 extern "C" {
 
-int32_t cc_abi_version(void) { return 1; }
+int32_t cc_abi_version(void) { return 2; }
 const char* cc_last_error(void) { return g_err; }
 int64_t cc_launch_count(void) { return g_launches.load(); }
 
@@ -524,6 +595,13 @@ int32_t cc_kernel_family_at(const CcModule* c, const CcModule* m, int32_t with_g
 size_t cc_rollout_tape_bytes(const CcModule* m, int64_t B, int32_t T, int32_t ckpt_every) {
   if (!m || B <= 0 || T < 0 || ckpt_every < 1) return 0;
   const long long Bpad = (B + 31) / 32 * 32;
+  {  // blocked linear family: the tape is the state at the block starts (every lin_m steps), whatever ckpt_every says
+    CcKParams p;
+    PlanOpts o;
+    const CcModule* mods[1] = {m};
+    if (!validate_module(m, "model") && !make_plan(mods, 1, B, T, o, &p) && p.tc == 4)
+      return ((size_t)((T + p.lin_m - 1) / p.lin_m) * m->state_dim * Bpad + 2 * (size_t)T) * sizeof(float);
+  }
   return ((size_t)n_ckpt_of(T, ckpt_every) * m->state_dim * Bpad + 2 * (size_t)T) * sizeof(float);
 }
 
@@ -534,8 +612,27 @@ size_t cc_closedloop_tape_bytes(const CcModule* c, const CcModule* m, int64_t B,
   return ((size_t)n_ckpt_of(Tr, ckpt_every) * (c->state_dim + sm_rows + m->output_dim) * Bpad + 2 * (size_t)Tr) * sizeof(float);
 }
 
+size_t cc_rollout_fwd_workspace_bytes(const CcModule* m, int64_t B, int32_t T) {
+  if (!m || B <= 0 || validate_module(m, "model")) return 0;
+  CcKParams p;
+  PlanOpts o;
+  const CcModule* mods[1] = {m};
+  if (make_plan(mods, 1, B, T, o, &p)) return 0;
+  return p.tc == 4 ? lin_pack_bytes() : 0;
+}
+
+size_t cc_closedloop_fwd_workspace_bytes(const CcModule* c, const CcModule* m, int64_t B, int32_t Tr) {
+  if (!c || !m || B <= 0 || validate_module(c, "controller") || validate_module(m, "model")) return 0;
+  CcKParams p;
+  PlanOpts o;
+  const CcModule* mods[2] = {c, m};
+  if (make_plan(mods, 2, B, Tr, o, &p)) return 0;
+  return p.tc == 4 ? lin_pack_bytes() : 0;
+}
+
 int32_t cc_rollout_fwd(const CcModule* m, const float* theta, const float* u, const float* x0, float* y,
-                       float* x_final, void* tape, int32_t ckpt_every, int64_t B, int32_t T, void* stream) {
+                       float* x_final, void* tape, int32_t ckpt_every, int64_t B, int32_t T, void* ws, size_t ws_bytes,
+                       void* stream) {
   int rc = validate_module(m, "model");
   if (rc) return rc;
   if (!theta || !y || (T > 0 && m->input_dim > 0 && !u)) return fail(CC_ERR_INVALID_ARG, "null pointer argument");
@@ -544,6 +641,7 @@ int32_t cc_rollout_fwd(const CcModule* m, const float* theta, const float* u, co
   if (B == 0) return CC_OK;
   CcKParams p;
   PlanOpts o;
+  o.exact_end = x_final != nullptr;
   const CcModule* mods[1] = {m};
   rc = make_plan(mods, 1, B, T, o, &p);
   if (rc) return rc;
@@ -552,12 +650,16 @@ int32_t cc_rollout_fwd(const CcModule* m, const float* theta, const float* u, co
   p.tape = (float*)tape;
   p.ckpt_every = tape ? ckpt_every : 1;
   p.n_ckpt = n_ckpt_of(T, p.ckpt_every);
+  if (p.tc == 4) {
+    if (!ws || ws_bytes < lin_pack_bytes()) return fail(CC_ERR_WORKSPACE, "workspace too small: need %zu bytes (cc_rollout_fwd_workspace_bytes)", lin_pack_bytes());
+    return launch_lin(p, false, (float*)ws, stream);
+  }
   return launch_fwd(p, stream);
 }
 
 int32_t cc_closedloop_fwd(const CcModule* c, const CcModule* m, const float* theta_c, const float* theta_m,
                           const float* refs, const float* noise, float* yhat, float* u_out, void* tape,
-                          int32_t ckpt_every, int64_t B, int32_t Tr, void* stream) {
+                          int32_t ckpt_every, int64_t B, int32_t Tr, void* ws, size_t ws_bytes, void* stream) {
   int rc = validate_module(c, "controller");
   if (rc) return rc;
   rc = validate_module(m, "model");
@@ -579,6 +681,10 @@ int32_t cc_closedloop_fwd(const CcModule* c, const CcModule* m, const float* the
   p.tape = (float*)tape;
   p.ckpt_every = tape ? ckpt_every : 1;
   p.n_ckpt = n_ckpt_of(Tr, p.ckpt_every);
+  if (p.tc == 4) {
+    if (!ws || ws_bytes < lin_pack_bytes()) return fail(CC_ERR_WORKSPACE, "workspace too small: need %zu bytes (cc_closedloop_fwd_workspace_bytes)", lin_pack_bytes());
+    return launch_lin(p, false, (float*)ws, stream);
+  }
   return launch_fwd(p, stream);
 }
 

@@ -1,0 +1,415 @@
+// cc_lin_kernels.cuh -- blocked linear rollout kernels (family 4, cc_lin.h): CLOSED LOOP with a frozen linear model and
+// the tiny feedback controller.
+//
+// Restates AbstractController.unroll (cc/core/abstract.py:97-127) with NeuralOdeModel.step for single-layer linear f / g
+// (neural_ode_model.py:106-149, compact neural_ode_model_compact_example.py:94-110) and NeuralOdeController.step
+// (cc_tc_ctrl.cuh) and the reverse pass eqx.filter_value_and_grad derives for step_fn.py:249-283 -- the same functions
+// as cc_tc_kernels.cuh, with a different execution model: the linear model is advanced m steps per tcgen05.mma batch
+// (cc_lin.h), so per step only the controller, the input transform and a 12-FMA shift register of Markov-parameter
+// sums remain in the thread.  thread = trajectory = TMEM lane; one CTA = 128 trajectories; two CTAs per SM.
+//
+//   forward, block of m steps starting at k0 (thread-private unless noted):
+//     D  <- round( A = [p ; u~ of the previous block ; e] )                 one MMA batch for the whole CTA
+//     p  += D[0:S)            a[t] = D[62-t] + const[t]   (free response of the block's outputs)
+//     A[0:S) <- p             (state part of the next round's operand)
+//     for j < m:  v = [ref_k ; y_prev] -> controller -> a_raw -> u~ = u_transform(a_raw) -> A[62-j] <- u~
+//                 y = a[0] (+ H_0 u~ for the post-step readout) (+ noise)
+//                 a[t] <- a[t+1] + H_{t+q} u~      (the outputs of the later steps of the block see u~_j)
+//   reverse, block walked backwards with the shift register c[] (c[0] = free response of the current step's u~-cotangent):
+//     D  <- round( A = [r ; w of the later block] )
+//     r  += D[0:S)            c[t] = D[62-t]
+//     for j = m-1..0: w = ybar_k + feedback ; A[62-j] <- w ; ubar~ = c[0] (+ H_0 w) ; c[t] <- c[t+1] + H_{t+q} w
+//                 controller step recomputed from the tape (x_c, y_prev), reverse pass -> feedback cotangent
+#pragma once
+#include "cc_kernels.cuh"
+#include "cc_lin_tm.cuh"
+#include "cc_tc_ctrl.cuh"
+
+// ---- shared-memory carve (floats) -----------------------------------------------------------------
+#define CC_LIN_SM_BHI 0
+#define CC_LIN_SM_BLO 4096
+#define CC_LIN_SM_SMALL 8192                  // H[32], const[16]
+#define CC_LIN_SM_WFC (8192 + 48)             // controller f weights [8][16]
+#define CC_LIN_SM_WGC (CC_LIN_SM_WFC + CC_TINY_S * CC_CK)   // controller g weights [4][16]
+#define CC_LIN_SM_BAR (CC_LIN_SM_WGC + CC_TINY_O * CC_CK)   // 2 mbarriers + tmem slot (8 floats)
+#define CC_LIN_SM_STAGE (CC_LIN_SM_BAR + 8)   // I/O staging tiles (per warp), then the reverse pass's controller scratch
+#define CC_LIN_TILE 1056                      // 32 rows x 33 floats
+#ifdef CC_EMULATE
+#define CC_LIN_SM_TMEM_EMU(base) ((base))     // emulated TMEM [192][128] floats appended behind everything else
+#endif
+
+// ---- coalesced I/O through per-warp shared-memory tiles (north_star (2): "coalesced, vectorised stores") ----
+// A warp owns 32 trajectories whose rows of a [B, T, 1] array are T floats apart.  Per 32-step chunk the warp copies a
+// 32 x 32 tile: lane l moves element (row i, step 32c + l) for i = 0..31, i.e. every request touches 128 contiguous bytes
+// of one row; the thread then reads / writes its own row of the tile (stride 33: conflict free).
+CC_DEV void cc_lin_cp4(float* dst_smem, const float* src) {
+#ifdef CC_EMULATE
+  *dst_smem = *src;
+#else
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(cc_smem_u32(dst_smem)), "l"(src) : "memory");
+#endif
+}
+CC_DEV void cc_lin_cp_commit() {
+#ifndef CC_EMULATE
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+CC_DEV void cc_lin_cp_wait_all() {
+#ifndef CC_EMULATE
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+}
+// issue the loads of chunk c (steps [32c, 32c+32)) of a [B, T] array into `tile` (asynchronous)
+CC_DEV void cc_lin_tile_load(float* tile, const float* base, long long b0, int nact, long long stride, long long len, int c, int lane) {
+  const long long k = (long long)c * 32 + lane;
+  if (k < len)
+    for (int i = 0; i < nact; ++i) cc_lin_cp4(tile + i * 33 + lane, base + (b0 + i) * stride + k);
+  cc_lin_cp_commit();
+}
+// write chunk c of a [B, T] array from `tile`
+CC_DEV void cc_lin_tile_store(const float* tile, float* base, long long b0, int nact, long long stride, long long len, int c, int lane) {
+  const long long k = (long long)c * 32 + lane;
+  if (k < len)
+    for (int i = 0; i < nact; ++i) base[(b0 + i) * stride + k] = tile[i * 33 + lane];
+}
+
+// p += D[0:S), state chunks of the next operand <- p.  NCH = 8-column state chunks held in registers (8*NCH >= S);
+// columns >= S of D hold slot values (or zero) and must not reach p.
+template <int NCH>
+CC_DEV void cc_lin_advance_state(const CcLinTm& tm, float (&p)[8 * NCH], int S) {
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    float d[8];
+    cc_lin_ld<8>(tm, CC_LIN_COL_D + 8 * c, d);
+    cc_lin_wait_ld();
+    float z[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int col = 8 * c + i;
+      float inc = d[i];
+      if (col >= 48) inc = col < S ? inc : 0.f;  // (the slots occupy columns 50..62)
+      p[col] += inc;
+      z[i] = p[col];
+    }
+    cc_lin_store_split<8>(tm, 8 * c, z);
+  }
+}
+
+struct CcLinShared {
+  float* bhi; float* blo; float* small; float* wfc; float* wgc; uint64_t* a_ready; uint64_t* d_ready; uint32_t* tmem_slot; float* stage;
+};
+CC_DEV CcLinShared cc_lin_carve(float* smem) {
+  CcLinShared s;
+  s.bhi = smem + CC_LIN_SM_BHI;
+  s.blo = smem + CC_LIN_SM_BLO;
+  s.small = smem + CC_LIN_SM_SMALL;
+  s.wfc = smem + CC_LIN_SM_WFC;
+  s.wgc = smem + CC_LIN_SM_WGC;
+  s.a_ready = reinterpret_cast<uint64_t*>(smem + CC_LIN_SM_BAR);
+  s.d_ready = s.a_ready + 1;
+  s.tmem_slot = reinterpret_cast<uint32_t*>(s.d_ready + 1);
+  s.stage = smem + CC_LIN_SM_STAGE;
+  return s;
+}
+
+// prologue: B operand (forward or reverse matrix) and the small tables from the prep pack, controller weights, barriers,
+// TMEM allocation, zeroed A operand.  emu_tmem_off: float offset of the emulated TMEM inside shared memory.
+CC_DEV void cc_lin_prologue(const CcKParams& p, const CcLinShared& sh, bool bwd, CcLinTm& tm, int emu_tmem_off) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const float* pack = p.lin_pack;
+  const float4* src_hi = reinterpret_cast<const float4*>(pack + (bwd ? CC_LIN_WB_HI : CC_LIN_WF_HI));
+  const float4* src_lo = reinterpret_cast<const float4*>(pack + (bwd ? CC_LIN_WB_LO : CC_LIN_WF_LO));
+  float4* dhi = reinterpret_cast<float4*>(sh.bhi);
+  float4* dlo = reinterpret_cast<float4*>(sh.blo);
+  for (int i = tid; i < 1024; i += nthr) { dhi[i] = src_hi[i]; dlo[i] = src_lo[i]; }
+  // H[n] (SISO: one float per n, stride 16 in the pack) and const[j] (stride 4)
+  for (int i = tid; i < 32; i += nthr) sh.small[i] = i < 28 ? pack[CC_LIN_SMALL + CC_LIN_S_H + 16 * i] : 0.f;
+  for (int i = tid; i < 16; i += nthr) sh.small[32 + i] = i < CC_LIN_MAXM ? pack[CC_LIN_SMALL + CC_LIN_S_CONST + 4 * i] : 0.f;
+  if (p.n_nodes == 2) cc_ctrl_stage_weights(p.nd[0], p.theta[0], sh.wfc, sh.wgc, tid, nthr);
+#ifdef CC_EMULATE
+  tm.tm = CC_SMEM_PTR + emu_tmem_off;
+  tm.bhi = sh.bhi; tm.blo = sh.blo; tm.tid = tid;
+  for (int c = 0; c < 192; ++c) tm.tm[c * 128 + tid] = 0.f;
+  __syncthreads();
+#else
+  (void)emu_tmem_off;
+  const int warp = tid >> 5, lane = tid & 31;
+  if (warp == 0) {
+    if (lane == 0) {
+      cc_mbar_init(sh.a_ready, 128);
+      cc_mbar_init(sh.d_ready, 1);
+      cc_mbar_fence_init();
+    }
+    __syncwarp();
+    cc_tmem_alloc(sh.tmem_slot, CC_LIN_TMEM_COLS);
+  }
+  cc_fence_proxy_async();
+  cc_tc_fence_before();
+  __syncthreads();
+  cc_tc_fence_after();
+  tm.tbase = *sh.tmem_slot;
+  tm.lane_base = tm.tbase + ((uint32_t)(warp * 32) << 16);
+  tm.bhi = cc_smem_u32(sh.bhi); tm.blo = cc_smem_u32(sh.blo);
+  tm.a_ready = sh.a_ready; tm.d_ready = sh.d_ready;
+  tm.batch = 0; tm.par = 0; tm.warp = warp; tm.lane = lane;
+  {  // zero the whole A operand (hi and lo): unused columns stay finite zeros for the rest of the kernel
+    float z[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) z[i] = 0.f;
+    cc_lin_st<32>(tm, CC_LIN_COL_AHI, z); cc_lin_st<32>(tm, CC_LIN_COL_AHI + 32, z);
+    cc_lin_st<32>(tm, CC_LIN_COL_ALO, z); cc_lin_st<32>(tm, CC_LIN_COL_ALO + 32, z);
+  }
+#endif
+}
+CC_DEV void cc_lin_epilogue(const CcLinTm& tm) {
+#ifndef CC_EMULATE
+  cc_tc_fence_before();
+  __syncthreads();
+  if (tm.warp == 0) cc_tmem_dealloc(tm.tbase, CC_LIN_TMEM_COLS);
+#else
+  (void)tm;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: closed-loop forward.  SISO model (I = O = 1), tiny controller; STG: coalesced staging of refs / yhat (R = 1)
+// ------------------------------------------------------------------------------------------------
+template <int NCH, int CFG, bool STG>
+__global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_cl_fwd_kernel(const CC_GRID_CONSTANT CcKParams gp) {
+  CC_DIRECT_PARAMS(gp)
+  (void)cta_smem;
+  const CcNodeDev& M = p.nd[1];
+  const CcNodeDev& C = p.nd[0];
+  const CcCtrlDims CD = cc_ctrl_dims<CFG>(C);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const CcLinShared sh = cc_lin_carve(cc_smem);
+  CcLinTm tm;
+  cc_lin_prologue(p, sh, false, tm, CC_LIN_SM_STAGE + (STG ? 4 * 3 * CC_LIN_TILE : 0));
+  const int S = M.S, m = p.lin_m, q = M.pre ? 0 : 1, T = p.T, R = p.R;
+  const long long b0 = (long long)blockIdx.x * 128 + warp * 32;
+  const long long rem = p.B - b0;
+  const int nact = rem >= 32 ? 32 : (rem > 0 ? (int)rem : 0);
+  const bool act = lane < nact;
+  const long long b = b0 + lane;
+  const bool tape = p.tape != nullptr;
+  float* tin = sh.stage + warp * 3 * CC_LIN_TILE;  // two input tiles (double buffer) + one output tile
+  float* tout = tin + 2 * CC_LIN_TILE;
+  float H[CC_LIN_MAXM + 1];
+#pragma unroll
+  for (int i = 0; i <= CC_LIN_MAXM; ++i) H[i] = sh.small[i];
+  float pst[8 * NCH];
+#pragma unroll
+  for (int i = 0; i < 8 * NCH; ++i) pst[i] = 0.f;
+  float xc[CC_TINY_S];
+#pragma unroll
+  for (int i = 0; i < CC_TINY_S; ++i) xc[i] = 0.f;
+  float yprev = p.lin_pack[CC_LIN_SMALL + CC_LIN_S_D0];  // y0 = g(x0 = 0) = d     neural_ode_model.py:160-175
+  float tc = C.t0;
+  if (STG) cc_lin_tile_load(tin, p.in, b0, nact, T, T, 0, lane);
+  float a[CC_LIN_MAXM];
+  for (int k0 = 0; k0 < T; k0 += m) {
+    // ---- one MMA batch for the block: A was completed by the previous block's sequential phase ----
+    cc_lin_round(tm);
+    cc_lin_await(tm);
+    {
+      float d[16];
+      cc_lin_ld<16>(tm, CC_LIN_COL_D + 48, d);  // slots t = 0..12 sit at columns 62..50
+      cc_lin_wait_ld();
+#pragma unroll
+      for (int t = 0; t < CC_LIN_MAXM; ++t) a[t] = d[14 - t] + sh.small[32 + t];
+    }
+    cc_lin_advance_state<NCH>(tm, pst, S);
+    if (k0 == 0) {  // e = 1 from the second round on (NCH = 8: column 63 is rewritten with the state chunks, so it rides in pst)
+      cc_lin_store_split1(tm, CC_LIN_ONE, 1.f);
+      if constexpr (NCH == 8) pst[CC_LIN_ONE] = 1.f;
+    }
+    const int nst = T - k0 < m ? T - k0 : m;
+    for (int j = 0; j < nst; ++j) {
+      const int k = k0 + j;
+      if (STG && (k & 31) == 0) {  // chunk boundary: the chunk's tile has landed; prefetch the next one
+        cc_lin_cp_wait_all();
+        __syncwarp();
+        cc_lin_tile_load(tin + (((k >> 5) + 1) & 1) * CC_LIN_TILE, p.in, b0, nact, T, T, (k >> 5) + 1, lane);
+      }
+      if (tape && blockIdx.x == 0 && tid == 0) {
+        float* ttab = p.tape + (long long)p.n_ckpt * p.tape_rows * p.Bpad;
+        ttab[k] = tc; ttab[T + k] = 0.f;
+      }
+      // controller input = merge_x_y(ref, y_prev) = [ref ; obs]     step_fn.py:187-192
+      float vc[CC_TINY_O];
+#pragma unroll
+      for (int i = 0; i < CC_TINY_O; ++i) {
+        vc[i] = 0.f;
+        if (i < R) {
+          if (STG) vc[i] = tin[((k >> 5) & 1) * CC_LIN_TILE + lane * 33 + (k & 31)];
+          else if (act) vc[i] = __ldg(p.in + b * (long long)T * R + (long long)k * R + i);
+        }
+        if (i == R) vc[i] = yprev;
+      }
+      if (tape && act) {
+        p.tape[((long long)k * p.tape_rows + p.tape_yrow) * p.Bpad + b] = yprev;
+#pragma unroll
+        for (int s = 0; s < CC_TINY_S; ++s)
+          if (s < CD.S) p.tape[((long long)k * p.tape_rows + C.tape_row + s) * p.Bpad + b] = xc[s];
+      }
+      float araw[CC_TINY_O];
+#pragma unroll
+      for (int i = 0; i < CC_TINY_O; ++i) araw[i] = 0.f;
+      if (CD.pre) cc_ctrl_readout_pre(CD, sh.wgc, xc, tc, vc, araw);
+      cc_ctrl_update<false>(CD, sh.wfc, sh.wgc, xc, tc, vc, araw, nullptr);
+      if (CD.has_t) tc = tc + CD.dt;
+      if (p.u_out && act) p.u_out[b * (long long)T + k] = araw[0];
+      const float ut = cc_ut(M.ut, M.u_scale, araw[0]);
+      cc_lin_store_split1(tm, CC_LIN_SLOT(j), ut);
+      float y = a[0];
+      if (q) y = fmaf(H[0], ut, y);
+#pragma unroll
+      for (int t = 0; t < CC_LIN_MAXM - 1; ++t) a[t] = fmaf(q ? H[t + 1] : H[t], ut, a[t + 1]);
+      a[CC_LIN_MAXM - 1] = 0.f;
+      if (p.noise && act) y += __ldg(p.noise + b * (long long)T + k);
+      yprev = y;
+      if (STG) {
+        tout[lane * 33 + (k & 31)] = y;
+        if ((k & 31) == 31 || k == T - 1) {
+          __syncwarp();
+          cc_lin_tile_store(tout, p.out, b0, nact, T, T, k >> 5, lane);
+          __syncwarp();
+        }
+      } else if (act) {
+        p.out[b * (long long)T + k] = y;
+      }
+    }
+  }
+  cc_lin_cp_wait_all();
+  cc_lin_epilogue(tm);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: closed-loop reverse pass, controller gradient (frozen linear SISO model)
+// ------------------------------------------------------------------------------------------------
+template <int NCH, int CFG, bool STG>
+__global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_cl_bwd_kernel(const CC_GRID_CONSTANT CcKParams gp) {
+  CC_DIRECT_PARAMS(gp)
+  (void)cta_smem;
+  const CcNodeDev& M = p.nd[1];
+  const CcNodeDev& C = p.nd[0];
+  const CcCtrlDims CD = cc_ctrl_dims<CFG>(C);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const CcLinShared sh = cc_lin_carve(cc_smem);
+  CcLinTm tm;
+  const int stage_floats = STG ? 4 * 4 * CC_LIN_TILE : 0;  // per warp: refs x2, ybar x2
+  const int gp_floats = (C.S + C.O) * CC_CKU * 128;
+  const int keep_floats = (C.f.layer[0].act != CC_ACT_IDENTITY ? 9 : 5) * CC_TINY_S * 128;
+  cc_lin_prologue(p, sh, true, tm, CC_LIN_SM_STAGE + stage_floats + gp_floats + keep_floats);
+  const int S = M.S, m = p.lin_m, q = M.pre ? 0 : 1, T = p.T, R = p.R;
+  const long long b0 = (long long)blockIdx.x * 128 + warp * 32;
+  const long long rem = p.B - b0;
+  const int nact = rem >= 32 ? 32 : (rem > 0 ? (int)rem : 0);
+  const bool act = lane < nact;
+  const long long b = b0 + lane;
+  float* tref = sh.stage + warp * 4 * CC_LIN_TILE;
+  float* tyb = tref + 2 * CC_LIN_TILE;
+  float* GP = sh.stage + stage_floats + tid;         // lane-private gradient accumulators
+  float* keep = sh.stage + stage_floats + gp_floats + tid;  // controller stage record of the current step
+  for (int e = 0; e < (C.S + C.O) * CC_CKU; ++e) GP[e * 128] = 0.f;
+  const float* ttab = p.tape + (long long)p.n_ckpt * p.tape_rows * p.Bpad;
+  float H[CC_LIN_MAXM + 1];
+#pragma unroll
+  for (int i = 0; i <= CC_LIN_MAXM; ++i) H[i] = sh.small[i];
+  float rst[8 * NCH];
+#pragma unroll
+  for (int i = 0; i < 8 * NCH; ++i) rst[i] = 0.f;
+  float lamc[CC_TINY_S];
+#pragma unroll
+  for (int i = 0; i < CC_TINY_S; ++i) lamc[i] = 0.f;
+  float yfb = 0.f;
+  float c[CC_LIN_MAXM];
+  const int nblk = (T + m - 1) / m;
+  const int nchunk = (T + 31) / 32;
+  if (STG && nchunk > 0) {
+    cc_lin_tile_load(tref + ((nchunk - 1) & 1) * CC_LIN_TILE, p.in, b0, nact, T, T, nchunk - 1, lane);
+    cc_lin_tile_load(tyb + ((nchunk - 1) & 1) * CC_LIN_TILE, p.ybar, b0, nact, T, T, nchunk - 1, lane);
+  }
+  int cur_chunk = nchunk;  // chunk whose tiles are valid (none yet)
+  for (int blk = nblk - 1; blk >= 0; --blk) {
+    const int k0 = blk * m;
+    cc_lin_round(tm);
+    cc_lin_await(tm);
+    {
+      float d[16];
+      cc_lin_ld<16>(tm, CC_LIN_COL_D + 48, d);
+      cc_lin_wait_ld();
+#pragma unroll
+      for (int t = 0; t < CC_LIN_MAXM; ++t) c[t] = d[14 - t];
+    }
+    cc_lin_advance_state<NCH>(tm, rst, S);
+    const int nst = T - k0 < m ? T - k0 : m;
+    for (int j = nst - 1; j >= 0; --j) {
+      const int k = k0 + j;
+      if (STG && (k >> 5) != cur_chunk) {  // entering chunk k>>5 (walking down): its tiles have landed; prefetch the one below
+        cur_chunk = k >> 5;
+        cc_lin_cp_wait_all();
+        __syncwarp();
+        if (cur_chunk > 0) {
+          cc_lin_tile_load(tref + ((cur_chunk - 1) & 1) * CC_LIN_TILE, p.in, b0, nact, T, T, cur_chunk - 1, lane);
+          cc_lin_tile_load(tyb + ((cur_chunk - 1) & 1) * CC_LIN_TILE, p.ybar, b0, nact, T, T, cur_chunk - 1, lane);
+        }
+      }
+      float vc[CC_TINY_O], xcv[CC_TINY_S];
+      float yb = 0.f;
+      if (STG) yb = tyb[(cur_chunk & 1) * CC_LIN_TILE + lane * 33 + (k & 31)];
+      else if (act) yb = __ldg(p.ybar + b * (long long)T + k);
+      const float ypk = act ? p.tape[((long long)k * p.tape_rows + p.tape_yrow) * p.Bpad + b] : 0.f;
+#pragma unroll
+      for (int i = 0; i < CC_TINY_O; ++i) {
+        vc[i] = 0.f;
+        if (i < R) {
+          if (STG) vc[i] = tref[(cur_chunk & 1) * CC_LIN_TILE + lane * 33 + (k & 31)];
+          else if (act) vc[i] = __ldg(p.in + b * (long long)T * R + (long long)k * R + i);
+        }
+        if (i == R) vc[i] = ypk;
+      }
+#pragma unroll
+      for (int s = 0; s < CC_TINY_S; ++s) xcv[s] = (s < CD.S && act) ? p.tape[((long long)k * p.tape_rows + C.tape_row + s) * p.Bpad + b] : 0.f;
+      const float tc = CD.has_t ? ttab[k] : 0.f;
+      const float w = yb + yfb;  // cotangent of y_k: loss + feedback into step k+1
+      cc_lin_store_split1(tm, CC_LIN_SLOT(j), w);
+      float utb = c[0];
+      if (q) utb = fmaf(H[0], w, utb);
+#pragma unroll
+      for (int t = 0; t < CC_LIN_MAXM - 1; ++t) c[t] = fmaf(q ? H[t + 1] : H[t], w, c[t + 1]);
+      c[CC_LIN_MAXM - 1] = 0.f;
+      // recompute the controller step (stage record kept), then its reverse pass
+      float araw[CC_TINY_O];
+#pragma unroll
+      for (int i = 0; i < CC_TINY_O; ++i) araw[i] = 0.f;
+      if (CD.pre) cc_ctrl_readout_pre(CD, sh.wgc, xcv, tc, vc, araw);
+      cc_ctrl_update<true>(CD, sh.wfc, sh.wgc, xcv, tc, vc, araw, keep);
+      float ob[CC_TINY_O], vb[CC_TINY_O];
+#pragma unroll
+      for (int i = 0; i < CC_TINY_O; ++i) ob[i] = 0.f;
+      ob[0] = utb * cc_ut_grad(M.ut, M.u_scale, araw[0]);
+      cc_ctrl_bwd(CD, sh.wfc, sh.wgc, GP, tc, vc, keep, araw, ob, lamc, vb);
+      yfb = 0.f;
+#pragma unroll
+      for (int i = 0; i < CC_TINY_O; ++i)
+        if (i == R) yfb = vb[i];
+    }
+  }
+  cc_lin_cp_wait_all();
+  // gradient record of this warp tile (32 trajectories; fixed xor tree -> deterministic), reduced by cc_reduce_grad_kernel
+  {
+    const long long wt = (long long)blockIdx.x * 4 + warp;
+    float* rec = p.gpart + wt * p.g_rec;
+    for (int row = 0; row < C.S + C.O; ++row) {
+      const int goff = row < C.S ? C.f.layer[0].g_off + row * C.K0 : C.g.layer[0].g_off + (row - C.S) * C.K0;
+      for (int r = 0; r < C.K0; ++r) {
+        float v = act ? GP[(row * CC_CKU + cc_ctrl_col_of_row(C, r)) * 128] : 0.f;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(CC_FULL, v, off);
+        if (lane == 0 && wt < p.n_wtiles) rec[C.g_base + goff + r] = v;
+      }
+    }
+  }
+  cc_lin_epilogue(tm);
+}

@@ -130,11 +130,18 @@ struct CcKParams {
   int w_yprev, w_yfb, w_araw;  // per-warp closed-loop scratch rows
   // tensor-core path (cc_tc_kernels.cuh): the MODEL node's f runs on tcgen05 (TMEM-resident stage inputs,
   // 3xTF32 split), one trajectory per thread; only the (tiny) controller uses the per-warp regions above
-  int tc;          // 0: FFMA kernels, 1: tcgen05 kernels, 2: latency kernels, 3: tcgen05 reverse pass with weight gradient
+  int tc;          // 0: FFMA kernels, 1: tcgen05 kernels, 2: latency kernels, 3: tcgen05 reverse pass with weight gradient, 4: blocked linear kernels (cc_lin.h)
   int tc_nch;      // state register chunks of 8 per thread (4 or 7): S <= 8 * tc_nch
   int tc_KP;       // A columns (contraction, multiple of 8): fwd [x ; v ; 1], bwd [kbar]
   int tc_NP;       // D columns (multiple of 16): fwd k (S), bwd [zbar (8*nch) ; vbar (I)]
   int tc_off;      // float offset of the tcgen05 region inside dynamic shared memory
   int tc_sms;      // SM count (CTA start stagger: CTAs b and b + sms share an SM in the first wave)
   int tc_stagger;  // cycles the second CTA of an SM waits before its first step
+  // blocked linear family (tc == 4; cc_lin.h): the linear model advances lin_m steps per MMA batch
+  int lin_m;               // steps per block
+  int lin_mt;              // open-loop forward with x_final and T % lin_m != 0: length of the ragged tail (second prep pack), else 0
+  int lin_stage;           // coalesced I/O through shared-memory tiles (cc_lin_kernels.cuh)
+  const float* lin_pack;   // output of cc_lin_prep_kernel (block matrices + small tables), global memory
+  double* lin_tab;         // fp64 tables for the gradient post-processing (trainable models), or nullptr
+  float* lin_q;            // trainable open loop: per-CTA partial sums of Q = Lam (x) X
 };

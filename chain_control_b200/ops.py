@@ -55,8 +55,10 @@ def rollout_fwd(spec: NodeSpec, theta, u, x0=None, *, want_tape=False, ckpt_ever
     if want_tape:
         nbytes = L.cc_rollout_tape_bytes(C.byref(m), B, T, ckpt_every)
         tape = torch.empty(max(nbytes // 4, 1), device=u.device, dtype=torch.float32)
+    nws = L.cc_rollout_fwd_workspace_bytes(C.byref(m), B, T)
+    ws = torch.empty(nws // 4 + 1, device=u.device, dtype=torch.float32) if nws else None
     rc = L.cc_rollout_fwd(C.byref(m), _ptr(theta), _ptr(u), _ptr(x0), _ptr(y), _ptr(xf), _ptr(tape), ckpt_every, B, T,
-                          _stream())
+                          _ptr(ws), nws, _stream())
     L.check(rc, "cc_rollout_fwd")
     return y, xf, tape
 
@@ -79,8 +81,10 @@ def closedloop_fwd(cspec: NodeSpec, mspec: NodeSpec, theta_c, theta_m, refs, noi
     if want_tape:
         nbytes = L.cc_closedloop_tape_bytes(C.byref(c), C.byref(m), B, Tr, ckpt_every)
         tape = torch.empty(max(nbytes // 4, 1), device=refs.device, dtype=torch.float32)
+    nws = L.cc_closedloop_fwd_workspace_bytes(C.byref(c), C.byref(m), B, Tr)
+    ws = torch.empty(nws // 4 + 1, device=refs.device, dtype=torch.float32) if nws else None
     rc = L.cc_closedloop_fwd(C.byref(c), C.byref(m), _ptr(theta_c), _ptr(theta_m), _ptr(refs), _ptr(noise), _ptr(yhat),
-                             _ptr(us), _ptr(tape), ckpt_every, B, Tr, _stream())
+                             _ptr(us), _ptr(tape), ckpt_every, B, Tr, _ptr(ws), nws, _stream())
     L.check(rc, "cc_closedloop_fwd")
     return yhat, us, tape
 

@@ -83,8 +83,9 @@ int64_t cc_param_count(const CcModule* m);
 int32_t cc_module_supported(const CcModule* m, int32_t with_grad);
 
 /* which kernel family the plan picks for this call (deterministic, from the architecture only):
- * 2 = latency kernels (depth-0 model, small batch: one warp per trajectory), 1 = tcgen05 kernels (depth-0 model:
- * stage evaluations as tcgen05.mma batches, 3xTF32), 0 = FFMA kernels,
+ * 4 = blocked linear kernels (linear depth-0 model: m integrator steps per tcgen05.mma batch, chain_control_b200/csrc/cc_lin.h),
+ * 3 = tcgen05 reverse pass with a tensor-core weight gradient, 2 = latency kernels (depth-0 model, small batch: one warp
+ * per trajectory), 1 = tcgen05 kernels (depth-0 model: stage evaluations as tcgen05.mma batches, 3xTF32), 0 = FFMA kernels,
  * < 0 = a CcStatus (unsupported / invalid).  ctrl == NULL: open loop. */
 int32_t cc_kernel_family(const CcModule* ctrl, const CcModule* model, int32_t with_grad);
 /* same for a given batch size (the latency kernels are picked for small batches only; cc_kernel_family assumes 65,536) */
@@ -99,10 +100,12 @@ int32_t cc_kernel_family_at(const CcModule* ctrl, const CcModule* model, int32_t
  * x_final [B,S] or NULL: state after the last step (lets step() be served by T=1 calls).
  */
 size_t cc_rollout_tape_bytes(const CcModule* m, int64_t B, int32_t T, int32_t ckpt_every);
+/* scratch of the forward call (0 for most kernel families; ws may then be NULL) / of the reverse call */
+size_t cc_rollout_fwd_workspace_bytes(const CcModule* m, int64_t B, int32_t T);
 size_t cc_rollout_workspace_bytes(const CcModule* m, int64_t B, int32_t T, int32_t ckpt_every);
 int32_t cc_rollout_fwd(const CcModule* m, const float* theta, const float* u, const float* x0,
                        float* y, float* x_final, void* tape, int32_t ckpt_every, int64_t B,
-                       int32_t T, void* stream);
+                       int32_t T, void* ws, size_t ws_bytes, void* stream);
 /* ybar [B,T+1,O] -> theta_bar [P] (overwritten), ubar [B,T,I] or NULL.  Needs the tape written by
  * cc_rollout_fwd with the same (theta,u,x0,B,T,ckpt_every). */
 int32_t cc_rollout_bwd(const CcModule* m, const float* theta, const float* u, const float* x0,
@@ -118,12 +121,14 @@ int32_t cc_rollout_bwd(const CcModule* m, const float* theta, const float* u, co
  */
 size_t cc_closedloop_tape_bytes(const CcModule* ctrl, const CcModule* model, int64_t B, int32_t Tr,
                                 int32_t ckpt_every);
+size_t cc_closedloop_fwd_workspace_bytes(const CcModule* ctrl, const CcModule* model, int64_t B,
+                                         int32_t Tr);
 size_t cc_closedloop_workspace_bytes(const CcModule* ctrl, const CcModule* model, int64_t B,
                                      int32_t Tr, int32_t ckpt_every);
 int32_t cc_closedloop_fwd(const CcModule* ctrl, const CcModule* model, const float* theta_c,
                           const float* theta_m, const float* refs, const float* noise, float* yhat,
                           float* u_out, void* tape, int32_t ckpt_every, int64_t B, int32_t Tr,
-                          void* stream);
+                          void* ws, size_t ws_bytes, void* stream);
 int32_t cc_closedloop_bwd(const CcModule* ctrl, const CcModule* model, const float* theta_c,
                           const float* theta_m, const float* refs, const float* noise,
                           const void* tape, int32_t ckpt_every, const float* ybar,

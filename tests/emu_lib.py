@@ -45,7 +45,10 @@ def np_rollout_fwd(L, spec, theta, u, x0=None, tape_every=0):
     if tape_every:
         nbytes = L.cc_rollout_tape_bytes(C.byref(m), B, T, tape_every)
         tape = np.full(nbytes // 4, np.nan, np.float32)
-    rc = L.cc_rollout_fwd(C.byref(m), _p(theta), _p(u), _p(x0), _p(y), _p(xf), _p(tape), tape_every or 1, B, T, None)
+    nws = L.cc_rollout_fwd_workspace_bytes(C.byref(m), B, T)
+    ws = np.full(nws // 4 + 1, np.nan, np.float32)
+    rc = L.cc_rollout_fwd(C.byref(m), _p(theta), _p(u), _p(x0), _p(y), _p(xf), _p(tape), tape_every or 1, B, T,
+                          _p(ws) if nws else None, nws, None)
     L.check(rc, "cc_rollout_fwd")
     return y, xf, tape
 
@@ -60,8 +63,10 @@ def np_closedloop_fwd(L, cspec, mspec, theta_c, theta_m, refs, noise=None, tape_
     if tape_every:
         nbytes = L.cc_closedloop_tape_bytes(C.byref(c), C.byref(m), B, Tr, tape_every)
         tape = np.full(nbytes // 4, np.nan, np.float32)
+    nws = L.cc_closedloop_fwd_workspace_bytes(C.byref(c), C.byref(m), B, Tr)
+    ws = np.full(nws // 4 + 1, np.nan, np.float32)
     rc = L.cc_closedloop_fwd(C.byref(c), C.byref(m), _p(theta_c), _p(theta_m), _p(refs), _p(noise), _p(yhat),
-                             _p(us), _p(tape), tape_every or 1, B, Tr, None)
+                             _p(us), _p(tape), tape_every or 1, B, Tr, _p(ws) if nws else None, nws, None)
     L.check(rc, "cc_closedloop_fwd")
     return yhat, us, tape
 

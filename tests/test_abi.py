@@ -45,7 +45,7 @@ def test_emulated_library_has_same_abi():
     import emu_lib
 
     L = emu_lib.emu()
-    assert L.cc_abi_version() == 1
+    assert L.cc_abi_version() == 2
     from ccspecs import model_variants
     from cchelpers import conv
 
@@ -82,6 +82,15 @@ def test_plan_picks_tcgen05_for_depth0_models():
     old = os.environ.pop("CC_B200_TC", None)
     try:
         compact, ctrl = model_variants()["compact_s50_d0"], controller_variants()["compact_s5_d0"]
+        # default: LINEAR depth-0 models (identity final activations, time-invariant) run on the blocked linear kernels
+        os.environ.pop("CC_B200_LIN", None)
+        assert fam(None, compact, 0) == 4 and fam(None, compact, 1) == 4      # ModelTrainer, both directions
+        assert fam(ctrl, compact, 0) == 4 and fam(ctrl, compact, 1) == 4      # the bench workload, both directions
+        assert fam(None, tc_model_variants()["full_s20_d0"], 1) == 4          # post-step readout too
+        assert fam(None, tc_model_variants()["euler_s30_d0_tanh"], 0) == 1    # tanh final activation: not linear
+        assert fam(controller_variants()["full_s25_w10_d2"], compact, 0) == 0  # tile-sized controller: FFMA kernels
+        assert fam(None, model_variants()["full_s5_w10_d2"], 0) == 0          # deep MLP
+        os.environ["CC_B200_LIN"] = "0"   # the families below the blocked linear one
         assert fam(None, compact, 0) == 1            # open-loop forward
         assert fam(None, compact, 1) == 3            # ModelTrainer reverse pass: tcgen05 incl. the weight-gradient product
         assert fam(None, tc_model_variants()["full_s20_d0"], 1) == 0   # post-step readout: FFMA reverse pass
@@ -98,6 +107,7 @@ def test_plan_picks_tcgen05_for_depth0_models():
         os.environ["CC_B200_TC"] = "0"
         assert fam(ctrl, compact, 1) == 0
     finally:
+        os.environ.pop("CC_B200_LIN", None)
         os.environ.pop("CC_B200_TC", None)
         os.environ.pop("CC_B200_WPT_MAXB", None)
         if old is not None:

@@ -63,18 +63,20 @@ def test_emu_edge_cases():
         u = _u(1, T, 1, seed=T)
         y, _, _ = E.np_rollout_fwd(L, conv(spec), theta, u)
         assert normwise(y, O.rollout_fwd(spec, theta, u)[0]) < TOL_STATE
-    # two tiles with a ragged tail (forces more than one CTA)
+    # three warp tiles with a ragged tail (B = 70 = 32 + 32 + 6) as ONE CTA of three warps and as THREE CTAs of one warp
+    # (CC_B200_WPC is the warps-per-CTA override the plan really reads): multi-CTA indexing and the gradient reduction
     import os
-    os.environ["CC_B200_BT"] = "4"
-    try:
-        u = _u(6, 9, 1, seed=4)
-        ybar = np.random.default_rng(5).normal(size=(6, 10, 1)).astype(np.float32)
-        y, tb, ub = E.np_rollout_bwd(L, conv(spec), theta, u, ybar)
-        tb64, ub64 = O.rollout_bwd(spec, theta, u, ybar)
+    u = _u(70, 9, 1, seed=4)
+    ybar = np.random.default_rng(5).normal(size=(70, 10, 1)).astype(np.float32)
+    tb64, ub64 = O.rollout_bwd(spec, theta, u, ybar)
+    for wpc in ("3", "1"):
+        os.environ["CC_B200_WPC"] = wpc
+        try:
+            y, tb, ub = E.np_rollout_bwd(L, conv(spec), theta, u, ybar)
+        finally:
+            del os.environ["CC_B200_WPC"]
         assert normwise(y, O.rollout_fwd(spec, theta, u)[0]) < TOL_STATE
         assert l2rel(tb, tb64) < TOL_GRAD and l2rel(ub, ub64) < TOL_GRAD
-    finally:
-        del os.environ["CC_B200_BT"]
 
 
 def test_emu_mse_value_and_cotangent():
@@ -90,3 +92,77 @@ def test_emu_mse_value_and_cotangent():
     L.check(rc, "mse")
     assert abs(part[0] - O.mse(y.astype(np.float64), yhat.astype(np.float64))) < 1e-6
     np.testing.assert_allclose(ybar, O.mse_cotangent(y, yhat), rtol=1e-6, atol=1e-9)
+
+
+# ---- blocked linear family (cc_lin_kernels.cuh, cc_lin_open.cuh): the tensor-memory / MMA layer is emulated with the same
+# tf32 truncation of the operands (cc_lin_tm.cuh), so these runs also predict the rounding error of the 3xTF32 products ----
+LIN_MODELS = {
+    "compact_s50": dict(state_dim=50, input_dim=1, output_dim=1, readout_pre_step=True, u_transform=O.UT_ARCTAN),
+    "full_s20_ktanh": dict(state_dim=20, input_dim=1, output_dim=1, u_transform=O.UT_KTANH, u_scale=6.0),
+    "compact_s56": dict(state_dim=56, input_dim=1, output_dim=1, readout_pre_step=True, u_transform=O.UT_ARCTAN),
+    "euler_s60": dict(state_dim=60, input_dim=1, output_dim=1, integrator=O.INT_EE),
+    "full_s51": dict(state_dim=51, input_dim=1, output_dim=1),
+}
+LIN_OPEN_MODELS = dict(LIN_MODELS)
+LIN_OPEN_MODELS.update({
+    "compact_s40_i2_o3": dict(state_dim=40, input_dim=2, output_dim=3, readout_pre_step=True, u_transform=O.UT_ARCTAN),
+    "full_s51_i4_o4": dict(state_dim=51, input_dim=4, output_dim=4),
+    "euler_s18_i3_o2": dict(state_dim=18, input_dim=3, output_dim=2, integrator=O.INT_EE),
+    "compact_s44_o2_nobias": dict(state_dim=44, input_dim=1, output_dim=2, readout_pre_step=True, f_use_bias=False, g_use_bias=False),
+    "noint_s6_i2_o2": dict(state_dim=6, input_dim=2, output_dim=2, integrator=O.INT_NONE),
+})
+
+
+def _lin_node(kw):
+    kw = dict(kw)
+    return O.make_node(kw.pop("state_dim"), kw.pop("input_dim"), kw.pop("output_dim"), f_depth=0, **kw)
+
+
+@pytest.mark.parametrize("mname", list(LIN_MODELS))
+@pytest.mark.parametrize("cname", ["compact_s5_d0", "full_s6_d0_ft", "euler_s3_d0"])
+@pytest.mark.parametrize("stage", ["0", "1"])
+def test_emu_lin_closedloop(mname, cname, stage, monkeypatch):
+    import ctypes as C
+
+    from ccspecs import tc_controller_variants
+
+    monkeypatch.setenv("CC_B200_LIN_STAGE", stage)
+    mspec, cspec = _lin_node(LIN_MODELS[mname]), tc_controller_variants()[cname]
+    L = E.emu()
+    assert L.cc_kernel_family_at(C.byref(conv(cspec).to_c()), C.byref(conv(mspec).to_c()), 1, 64) == 4
+    B, Tr = 37, 45  # ragged: 2 warps (one partial), last block partial, 1.4 staging chunks
+    thc, thm = O.init_params(cspec, 2).astype(np.float32), O.init_params(mspec, 1, stable=True).astype(np.float32)
+    refs = 3 * _u(B, Tr, 1)
+    noise = (0.02 * np.random.default_rng(1).normal(size=(B, Tr, 1))).astype(np.float32)
+    ybar = np.random.default_rng(6).normal(size=(B, Tr, 1)).astype(np.float32)
+    y64, us64 = O.closedloop_fwd(cspec, mspec, thc, thm, refs, noise)
+    tb64 = O.closedloop_bwd(cspec, mspec, thc, thm, refs, ybar, noise)
+    yhat, us, _ = E.np_closedloop_fwd(L, conv(cspec), conv(mspec), thc, thm, refs, noise)
+    assert normwise(yhat, y64) < TOL_STATE
+    assert normwise(us, us64) < TOL_STATE
+    _, tb = E.np_closedloop_bwd(L, conv(cspec), conv(mspec), thc, thm, refs, ybar, noise)
+    assert l2rel(tb, tb64) < TOL_GRAD
+
+
+@pytest.mark.parametrize("mname", list(LIN_OPEN_MODELS))
+def test_emu_lin_rollout(mname):
+    import ctypes as C
+
+    spec = _lin_node(LIN_OPEN_MODELS[mname])
+    L = E.emu()
+    assert L.cc_kernel_family_at(None, C.byref(conv(spec).to_c()), 1, 64) == 4
+    B, T = 37, 45
+    theta = O.init_params(spec, 1, stable=spec.integrator != O.INT_NONE).astype(np.float32)
+    if spec.integrator == O.INT_NONE:
+        theta = (0.5 * theta).astype(np.float32)
+    u = _u(B, T, spec.input_dim)
+    x0 = (0.1 * np.random.default_rng(3).normal(size=(B, spec.state_dim))).astype(np.float32)
+    ybar = np.random.default_rng(5).normal(size=(B, T + 1, spec.output_dim)).astype(np.float32)
+    y64, xs = O.rollout_fwd(spec, theta, u, x0=x0)
+    tb64, ub64 = O.rollout_bwd(spec, theta, u, ybar, x0=x0)
+    y, tb, ub = E.np_rollout_bwd(L, conv(spec), theta, u, ybar, x0)
+    assert normwise(y, y64) < TOL_STATE
+    assert l2rel(tb, tb64) < TOL_GRAD
+    assert l2rel(ub, ub64) < TOL_GRAD
+    _, xf, _ = E.np_rollout_fwd(L, conv(spec), theta, u, x0)  # no tape: the block length divides T, x_final is exact
+    assert normwise(xf, xs[:, -1]) < TOL_STATE

@@ -25,18 +25,21 @@ def T_():
 
 
 FAMILY_ENV = {
-    # kernel family -> (CC_B200_TC, CC_B200_WPT_MAXB): which kernels the plan may pick where the architecture allows it
-    "tcgen05": ("1", "0"),             # tensor-core kernels at every batch size
-    "latency": ("1", str(1 << 40)),    # one warp per trajectory at every batch size (default: B <= 1184; ModelTrainer reverse pass <= 12288)
-    "ffma": ("0", "0"),                # register-tiled FP32 kernels
+    # kernel family -> (CC_B200_TC, CC_B200_WPT_MAXB, CC_B200_LIN): which kernels the plan may pick where the architecture allows it
+    "lin": ("1", "0", "1"),                 # blocked linear kernels (the default for linear depth-0 models; others fall through)
+    "tcgen05": ("1", "0", "0"),             # tensor-core kernels at every batch size
+    "latency": ("1", str(1 << 40), "0"),    # one warp per trajectory at every batch size (default: B <= 1184; ModelTrainer reverse pass <= 12288)
+    "ffma": ("0", "0", "0"),                # register-tiled FP32 kernels
 }
+FAMILY_KEYS = ("CC_B200_TC", "CC_B200_WPT_MAXB", "CC_B200_LIN")
 
 
 @pytest.fixture(params=list(FAMILY_ENV))
 def path(request):
     """run the test once per kernel family (where the architecture is not eligible the plan falls through to FFMA)"""
-    old = {k: os.environ.get(k) for k in ("CC_B200_TC", "CC_B200_WPT_MAXB")}
-    os.environ["CC_B200_TC"], os.environ["CC_B200_WPT_MAXB"] = FAMILY_ENV[request.param]
+    old = {k: os.environ.get(k) for k in FAMILY_KEYS}
+    for k, v in zip(FAMILY_KEYS, FAMILY_ENV[request.param]):
+        os.environ[k] = v
     yield request.param
     for k, v in old.items():
         if v is None:
@@ -216,13 +219,9 @@ def test_full_size_properties(path, T_):
     ga, _ = ops.rollout_bwd(spec, theta, u[:h].contiguous(), ta, ybar[:h].contiguous())
     gb, _ = ops.rollout_bwd(spec, theta, u[h:].contiguous(), tb_, ybar[h:].contiguous())
     assert l2rel((ga + gb).cpu().numpy(), tb1.cpu().numpy()) < 1e-5
-    # 4. tile-size independence (CC_B200_BT override = a different CTA decomposition)
-    os.environ["CC_B200_BT"] = "64"
-    try:
-        y64, _, _ = ops.rollout_fwd(spec, theta, u[:4096].contiguous())
-    finally:
-        del os.environ["CC_B200_BT"]
-    assert normwise(y64.cpu().numpy(), y[:4096].cpu().numpy()) < 2e-6
+    # 4. decomposition independence: a sub-batch that starts in the middle of a tile and ends with a partial one
+    y64, _, _ = ops.rollout_fwd(spec, theta, u[77:4096 + 13].contiguous())
+    assert normwise(y64.cpu().numpy(), y[77:4096 + 13].cpu().numpy()) < 2e-6
 
 
 def test_full_size_closed_loop_properties(path, T_):
@@ -261,8 +260,9 @@ def test_full_size_closed_loop_properties(path, T_):
     gb = ops.closedloop_bwd(ctrl, model, thc, thm, refs[h:].contiguous(), tb, ybar[h:].contiguous())
     assert l2rel((ga + gb).cpu().numpy(), g1.cpu().numpy()) < 1e-5
     # 4. the kernel families agree with each other at full size (outputs and gradient): compare with the FFMA kernels
-    saved = {k: os.environ.get(k) for k in ("CC_B200_TC", "CC_B200_WPT_MAXB")}
-    os.environ["CC_B200_TC"], os.environ["CC_B200_WPT_MAXB"] = FAMILY_ENV["ffma" if path != "ffma" else "tcgen05"]
+    saved = {k: os.environ.get(k) for k in FAMILY_KEYS}
+    for k, v in zip(FAMILY_KEYS, FAMILY_ENV["ffma" if path != "ffma" else "tcgen05"]):
+        os.environ[k] = v
     try:
         yo, _, tapeo = ops.closedloop_fwd(ctrl, model, thc, thm, refs, want_tape=True)
         go = ops.closedloop_bwd(ctrl, model, thc, thm, refs, tapeo, ybar)
