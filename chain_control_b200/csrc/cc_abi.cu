@@ -391,6 +391,12 @@ int make_plan(const CcModule* const* mods, int n_nodes, long long B, int T, cons
     const char* sg = getenv("CC_B200_LIN_STAGE");
     const bool siso = n_nodes == 2 ? p->R == 1 : (model->input_dim == 1 && model->output_dim == 1);
     p->lin_stage = (siso && !(sg && atoi(sg) == 0)) ? 1 : 0;
+    if (n_nodes == 2) {  // a linear controller (no activations, time-invariant, no input transform, one output) is collapsed too
+      const CcModule* c = mods[0];
+      const char* lc = getenv("CC_B200_LIN_LC");
+      p->lin_lc = (mlp_linear(c->f) && mlp_linear(c->g) && !c->f_time_variant && !c->g_time_variant && c->u_transform == CC_UT_IDENTITY &&
+                   c->output_dim == 1 && !(lc && atoi(lc) == 0)) ? 1 : 0;
+    }
     p->wpc = 4;
     p->n_wtiles = (B + 31) / 32;
     if (getenv("CC_B200_VERBOSE"))
@@ -517,7 +523,9 @@ int cc_launch_bwd_tn16(const CcKParams& p, void* stream, char* err, int errlen);
 #ifndef CC_EMULATE
 int cc_launch_fwd_tc(const CcKParams& p, void* stream, char* err, int errlen);
 int cc_launch_bwd_tc(const CcKParams& p, void* stream, char* err, int errlen);
-int cc_launch_lin_prep(const CcNodeDev& M, const float* theta, float* pack, double* tab, int m, int form, void* stream, char* err, int errlen);
+int cc_launch_lin_prep(const CcNodeDev& M, const float* theta, float* pack, double* tab, int m, int form, const CcNodeDev* C, const float* theta_c,
+                       void* stream, char* err, int errlen);
+int cc_launch_lin_cgrad(const CcLinCgradArgs& a, void* stream, char* err, int errlen);
 int cc_launch_lin(const CcKParams& p, bool bwd, void* stream, char* err, int errlen);
 int cc_launch_lin_grad(const CcLinGradArgs& a, void* stream, char* err, int errlen);
 #endif
@@ -526,11 +534,12 @@ namespace {
 int launch_lin(CcKParams& p, bool bwd, float* pack, void* stream) {
   g_launches.fetch_add(2);
   const CcNodeDev& M = p.nd[p.n_nodes - 1];
-  int rc = cc_launch_lin_prep(M, p.theta[p.n_nodes - 1], pack, p.lin_tab, p.lin_m, p.n_nodes == 2 ? 0 : 1, stream, g_err, sizeof(g_err));
+  int rc = cc_launch_lin_prep(M, p.theta[p.n_nodes - 1], pack, p.lin_tab, p.lin_m, p.n_nodes == 2 ? 0 : 1, p.lin_lc ? &p.nd[0] : nullptr, p.theta[0],
+                              stream, g_err, sizeof(g_err));
   if (rc) return rc;
   if (!bwd && p.lin_mt > 0) {  // block matrices of the ragged tail (open-loop x_final)
     g_launches.fetch_add(1);
-    rc = cc_launch_lin_prep(M, p.theta[p.n_nodes - 1], pack + CC_LIN_PACK_FLOATS, nullptr, p.lin_mt, 1, stream, g_err, sizeof(g_err));
+    rc = cc_launch_lin_prep(M, p.theta[p.n_nodes - 1], pack + CC_LIN_PACK_FLOATS, nullptr, p.lin_mt, 1, nullptr, nullptr, stream, g_err, sizeof(g_err));
     if (rc) return rc;
   }
   p.lin_pack = pack;

@@ -43,9 +43,13 @@ int ctrl_cfg_lin(const CcKParams& p) {
 }
 }  // namespace
 
-int cc_launch_lin_prep(const CcNodeDev& M, const float* theta, float* pack, double* tab, int m, int form, void* stream, char* err, int errlen) {
+int cc_launch_lin_prep(const CcNodeDev& M, const float* theta, float* pack, double* tab, int m, int form, const CcNodeDev* C, const float* theta_c,
+                       void* stream, char* err, int errlen) {
   CcLinPrepArgs a;
   a.M = M; a.theta = theta; a.pack = pack; a.tab = tab; a.m = m; a.form = form;
+  a.ctrl = C ? 1 : 0;
+  a.C = C ? *C : M;
+  a.theta_c = theta_c;
   return lin_launch1(cc_lin_prep_kernel, a, 1, CC_LIN_PREP_THREADS, (size_t)CC_LIN_PREP_SMEM_DOUBLES * 8, stream, err, errlen, "lin prep kernel");
 }
 
@@ -59,6 +63,10 @@ int cc_launch_lin_grad(const CcLinGradArgs& a, void* stream, char* err, int errl
 }
 #endif
 
+int cc_launch_lin_cgrad(const CcLinCgradArgs& a, void* stream, char* err, int errlen) {
+  return lin_launch1(cc_lin_cgrad_kernel, a, 1, 64, 8 * 64 * 8, stream, err, errlen, "lin controller gradient kernel");
+}
+
 #define CC_LIN_NCH(kern, ...)                                                                             \
   (nch == 4 ? lin_launch1(kern<4, __VA_ARGS__>, p, grid, CC_LIN_THREADS, smem, stream, err, errlen, #kern) \
    : nch == 7 ? lin_launch1(kern<7, __VA_ARGS__>, p, grid, CC_LIN_THREADS, smem, stream, err, errlen, #kern) \
@@ -71,15 +79,20 @@ int cc_launch_lin(const CcKParams& p, bool bwd, void* stream, char* err, int err
   if (p.n_nodes == 2) {
     const bool c521 = ctrl_cfg_lin(p) == 521;
     const bool stg = p.lin_stage != 0;
+    const bool lc = p.lin_lc != 0;  // (the 521 shape is linear by construction: it is only instantiated together with LC)
     if (!bwd) {
       const size_t smem = ((size_t)CC_LIN_SM_STAGE + (stg ? 4 * 3 * CC_LIN_TILE : 0) + kEmuTmemFloats) * 4;
-      if (stg) return c521 ? CC_LIN_NCH(cc_lin_cl_fwd_kernel, 521, true) : CC_LIN_NCH(cc_lin_cl_fwd_kernel, 0, true);
-      return c521 ? CC_LIN_NCH(cc_lin_cl_fwd_kernel, 521, false) : CC_LIN_NCH(cc_lin_cl_fwd_kernel, 0, false);
+      if (stg) return (lc && c521) ? CC_LIN_NCH(cc_lin_cl_fwd_kernel, 521, true, true) : (lc ? CC_LIN_NCH(cc_lin_cl_fwd_kernel, 0, true, true) : CC_LIN_NCH(cc_lin_cl_fwd_kernel, 0, true, false));
+      return (lc && c521) ? CC_LIN_NCH(cc_lin_cl_fwd_kernel, 521, false, true) : (lc ? CC_LIN_NCH(cc_lin_cl_fwd_kernel, 0, false, true) : CC_LIN_NCH(cc_lin_cl_fwd_kernel, 0, false, false));
     }
     const CcNodeDev& C = p.nd[0];
-    const size_t smem = ((size_t)CC_LIN_SM_STAGE + (size_t)(C.S + C.O) * CC_CKU * 128 +
-                         (size_t)(C.f.layer[0].act != CC_ACT_IDENTITY ? 9 : 5) * CC_TINY_S * 128 + kEmuTmemFloats) * 4;
-    return c521 ? CC_LIN_NCH(cc_lin_cl_bwd_kernel, 521, false) : CC_LIN_NCH(cc_lin_cl_bwd_kernel, 0, false);
+    const size_t gpf = (lc && c521) ? 0 : (size_t)(C.S + C.O) * CC_CKU * 128;
+    const size_t keepf = lc ? 0 : (size_t)(C.f.layer[0].act != CC_ACT_IDENTITY ? 9 : 5) * CC_TINY_S * 128;
+    const char* sgb = getenv("CC_B200_LIN_STAGE_BWD");
+    const bool stgb = stg && lc && c521 && sgb && atoi(sgb) == 1;  // measured: no gain (2.55 vs 2.41 ms at 65,536 x 1001), off by default  // register accumulators leave room for the refs / ybar tiles
+    const size_t smem = ((size_t)CC_LIN_SM_STAGE + (stgb ? 4 * 4 * CC_LIN_TILE : 0) + gpf + keepf + kEmuTmemFloats) * 4;
+    if (stgb) return CC_LIN_NCH(cc_lin_cl_bwd_kernel, 521, true, true);
+    return (lc && c521) ? CC_LIN_NCH(cc_lin_cl_bwd_kernel, 521, false, true) : (lc ? CC_LIN_NCH(cc_lin_cl_bwd_kernel, 0, false, true) : CC_LIN_NCH(cc_lin_cl_bwd_kernel, 0, false, false));
   }
 #ifdef CC_LIN_OPEN
   // open loop

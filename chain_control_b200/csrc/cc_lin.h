@@ -41,8 +41,15 @@
 #define CC_LIN_S_CM 772             //   c_m[64]
 #define CC_LIN_S_C 836              //   C[s][16]     x_k = p + C u~_prev + c_m e      (slot-indexed columns)
 #define CC_LIN_S_CHAT 1860          //   Chat[s][16]  mu_k = r + Chat w_blk
-#define CC_LIN_SMALL_FLOATS 2884
-#define CC_LIN_PACK_FLOATS (CC_LIN_SMALL + CC_LIN_SMALL_FLOATS + 12)  // 19,280 floats (multiple of 16)
+#define CC_LIN_SMALL_FLOATS 2884     // end of the model tables
+// linear tiny controller (f_c, g_c single Linear layers without activations, time-invariant): its integrator step collapsed
+// the same way, x_c+ = Phi_c x_c + (Gam_c B_c) v + Gam_c c_c
+#define CC_LIN_S_CPHI 2884          //   Phi_c[8][8]
+#define CC_LIN_S_CGB 2948           //   (Gam_c B_c)[8][4]
+#define CC_LIN_S_CGAM 2980          //   (Gam_c c_c)[8]
+#define CC_LIN_S_CTAB 2992          //   fp64: A_c[8][8], Gam_c[8][8]  (gradient post-processing, cc_lin_cgrad_kernel)
+#define CC_LIN_SMALL_ALL 3248
+#define CC_LIN_PACK_FLOATS (CC_LIN_SMALL + CC_LIN_SMALL_ALL)  // 19,632 floats (multiple of 16)
 // ---- fp64 tables behind the pack (trainable models only: the post-processing of Q needs them) ----
 //   PW[n][64][64] (Phi^n, n = 0..m), RG[a][4][64], CU[a][64][4], GS[a][64], plus A, B, c, Gam
 #define CC_LIN_TAB_PW 0
@@ -66,3 +73,12 @@ struct CcLinGradArgs {
 };
 #define CC_LIN_GRAD_PER_J (4096 + 256 + 64 + 256 + 4)
 #define CC_LIN_GRAD_WORK_DOUBLES(m) (4096 + 4 * 64 + (m) * CC_LIN_GRAD_PER_J)
+
+// ---- gradient of a linear tiny controller from the reduced M records (cc_lin_prep.cuh: cc_lin_cgrad_kernel) ----
+struct CcLinCgradArgs {
+  CcNodeDev C;
+  const float* theta_c;
+  const float* pack;     // prep pack (fp64 A_c, Gam_c at CC_LIN_S_CTAB)
+  const float* msum;     // [P] reduced records (M space)
+  float* theta_bar;      // [P]
+};

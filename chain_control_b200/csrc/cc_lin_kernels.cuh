@@ -29,7 +29,8 @@
 #define CC_LIN_SM_BHI 0
 #define CC_LIN_SM_BLO 4096
 #define CC_LIN_SM_SMALL 8192                  // H[32], const[16]
-#define CC_LIN_SM_WFC (8192 + 48)             // controller f weights [8][16]
+#define CC_LIN_SM_CLIN (8192 + 48)            // linear controller rows [8][16]: [Phi_c (8) | Gam_c B_c (4) | Gam_c c_c | pad]
+#define CC_LIN_SM_WFC (CC_LIN_SM_CLIN + 128)  // controller f weights [8][16]
 #define CC_LIN_SM_WGC (CC_LIN_SM_WFC + CC_TINY_S * CC_CK)   // controller g weights [4][16]
 #define CC_LIN_SM_BAR (CC_LIN_SM_WGC + CC_TINY_O * CC_CK)   // 2 mbarriers + tmem slot (8 floats)
 #define CC_LIN_SM_STAGE (CC_LIN_SM_BAR + 8)   // I/O staging tiles (per warp), then the reverse pass's controller scratch
@@ -96,13 +97,14 @@ CC_DEV void cc_lin_advance_state(const CcLinTm& tm, float (&p)[8 * NCH], int S) 
 }
 
 struct CcLinShared {
-  float* bhi; float* blo; float* small; float* wfc; float* wgc; uint64_t* a_ready; uint64_t* d_ready; uint32_t* tmem_slot; float* stage;
+  float* bhi; float* blo; float* small; float* clin; float* wfc; float* wgc; uint64_t* a_ready; uint64_t* d_ready; uint32_t* tmem_slot; float* stage;
 };
 CC_DEV CcLinShared cc_lin_carve(float* smem) {
   CcLinShared s;
   s.bhi = smem + CC_LIN_SM_BHI;
   s.blo = smem + CC_LIN_SM_BLO;
   s.small = smem + CC_LIN_SM_SMALL;
+  s.clin = smem + CC_LIN_SM_CLIN;
   s.wfc = smem + CC_LIN_SM_WFC;
   s.wgc = smem + CC_LIN_SM_WGC;
   s.a_ready = reinterpret_cast<uint64_t*>(smem + CC_LIN_SM_BAR);
@@ -125,6 +127,11 @@ CC_DEV void cc_lin_prologue(const CcKParams& p, const CcLinShared& sh, bool bwd,
   // H[n] (SISO: one float per n, stride 16 in the pack) and const[j] (stride 4)
   for (int i = tid; i < 32; i += nthr) sh.small[i] = i < 28 ? pack[CC_LIN_SMALL + CC_LIN_S_H + 16 * i] : 0.f;
   for (int i = tid; i < 16; i += nthr) sh.small[32 + i] = i < CC_LIN_MAXM ? pack[CC_LIN_SMALL + CC_LIN_S_CONST + 4 * i] : 0.f;
+  for (int i = tid; i < 128; i += nthr) {  // (zeros unless the prep collapsed the controller: p.lin_lc)
+    const int n = i / 16, k = i % 16;
+    const float* sp = pack + CC_LIN_SMALL;
+    sh.clin[i] = !p.lin_lc ? 0.f : (k < 8 ? sp[CC_LIN_S_CPHI + n * 8 + k] : (k < 12 ? sp[CC_LIN_S_CGB + n * 4 + (k - 8)] : (k == 12 ? sp[CC_LIN_S_CGAM + n] : 0.f)));
+  }
   if (p.n_nodes == 2) cc_ctrl_stage_weights(p.nd[0], p.theta[0], sh.wfc, sh.wgc, tid, nthr);
 #ifdef CC_EMULATE
   tm.tm = CC_SMEM_PTR + emu_tmem_off;
@@ -171,10 +178,65 @@ CC_DEV void cc_lin_epilogue(const CcLinTm& tm) {
 #endif
 }
 
+
+// ---- linear tiny controller (f_c, g_c without activations, time-invariant, no input transform): the integrator step is the
+// affine map x_c+ = Phi_c x_c + (Gam_c B_c) v + Gam_c c_c prepared by cc_lin_prep_kernel; rows [Phi_c | Gam_c B_c | gam] ----
+// LCR: the rows live in registers (CFG shapes: only the live entries survive), else they are read from shared memory
+template <int CFG>
+struct CcLctrlRows {
+  float w[CFG ? CC_TINY_S : 1][16];
+};
+template <int CFG>
+CC_DEV void cc_lctrl_load(const float* CL, CcLctrlRows<CFG>& R) {
+  if constexpr (CFG != 0) {
+#pragma unroll
+    for (int n = 0; n < CC_TINY_S; ++n)
+#pragma unroll
+      for (int k = 0; k < 16; ++k) R.w[n][k] = CL[n * 16 + k];
+  }
+}
+#define CC_LCW(n, k) (CFG ? R.w[CFG ? (n) : 0][k] : CL[(n) * 16 + (k)])
+// x_c+ (all CC_TINY_S entries, zero beyond S)
+template <int CFG>
+CC_DEV void cc_lctrl_next(const CcCtrlDims& C, const float* CL, const CcLctrlRows<CFG>& R, const float (&x)[CC_TINY_S], const float (&v)[CC_TINY_O], float (&xn)[CC_TINY_S]) {
+#pragma unroll
+  for (int n = 0; n < CC_TINY_S; ++n) {
+    xn[n] = 0.f;
+    if (n < C.S) {
+      float s0 = CC_LCW(n, 12), s1 = 0.f;
+#pragma unroll
+      for (int k = 0; k < CC_TINY_S; ++k)
+        if (k < C.S) { if (k & 1) s1 = fmaf(CC_LCW(n, k), x[k], s1); else s0 = fmaf(CC_LCW(n, k), x[k], s0); }
+#pragma unroll
+      for (int i = 0; i < CC_TINY_O; ++i)
+        if (i < C.I) s1 = fmaf(CC_LCW(n, 8 + i), v[i], s1);
+      xn[n] = s0 + s1;
+    }
+  }
+}
+// reverse of the affine step: lam <- Phi_c^T lamp ; vb = (Gam_c B_c)^T lamp
+template <int CFG>
+CC_DEV void cc_lctrl_next_bwd(const CcCtrlDims& C, const float* CL, const CcLctrlRows<CFG>& R, const float (&lamp)[CC_TINY_S], float (&lam)[CC_TINY_S], float (&vb)[CC_TINY_O]) {
+#pragma unroll
+  for (int k = 0; k < CC_TINY_S; ++k) lam[k] = 0.f;
+#pragma unroll
+  for (int i = 0; i < CC_TINY_O; ++i) vb[i] = 0.f;
+#pragma unroll
+  for (int n = 0; n < CC_TINY_S; ++n) {
+    if (n < C.S) {
+#pragma unroll
+      for (int k = 0; k < CC_TINY_S; ++k)
+        if (k < C.S) lam[k] = fmaf(CC_LCW(n, k), lamp[n], lam[k]);
+#pragma unroll
+      for (int i = 0; i < CC_TINY_O; ++i)
+        if (i < C.I) vb[i] = fmaf(CC_LCW(n, 8 + i), lamp[n], vb[i]);
+    }
+  }
+}
 // ------------------------------------------------------------------------------------------------
 // K3: closed-loop forward.  SISO model (I = O = 1), tiny controller; STG: coalesced staging of refs / yhat (R = 1)
 // ------------------------------------------------------------------------------------------------
-template <int NCH, int CFG, bool STG>
+template <int NCH, int CFG, bool STG, bool LC>
 __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_cl_fwd_kernel(const CC_GRID_CONSTANT CcKParams gp) {
   CC_DIRECT_PARAMS(gp)
   (void)cta_smem;
@@ -185,18 +247,28 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_cl_fwd_kernel(const 
   const CcLinShared sh = cc_lin_carve(cc_smem);
   CcLinTm tm;
   cc_lin_prologue(p, sh, false, tm, CC_LIN_SM_STAGE + (STG ? 4 * 3 * CC_LIN_TILE : 0));
-  const int S = M.S, m = p.lin_m, q = M.pre ? 0 : 1, T = p.T, R = p.R;
+  const int S = M.S, m = p.lin_m, T = p.T;
+  const int R = CFG ? 1 : p.R;  // (the 521 shape has two inputs: one reference, one observation)
+  const bool post = !M.pre;
+  const int mut = M.ut;
+  const float mus = M.u_scale;
   const long long b0 = (long long)blockIdx.x * 128 + warp * 32;
   const long long rem = p.B - b0;
   const int nact = rem >= 32 ? 32 : (rem > 0 ? (int)rem : 0);
   const bool act = lane < nact;
   const long long b = b0 + lane;
-  const bool tape = p.tape != nullptr;
-  float* tin = sh.stage + warp * 3 * CC_LIN_TILE;  // two input tiles (double buffer) + one output tile
-  float* tout = tin + 2 * CC_LIN_TILE;
+  // staging tiles addressed off the shared-memory symbol (a pointer carried through a struct degrades to a generic one)
+  const int tin_off = CC_LIN_SM_STAGE + warp * 3 * CC_LIN_TILE;  // two input tiles (double buffer) + one output tile
+  const int tout_off = tin_off + 2 * CC_LIN_TILE;
+  const int trow = lane * 33;
   float H[CC_LIN_MAXM + 1];
 #pragma unroll
   for (int i = 0; i <= CC_LIN_MAXM; ++i) H[i] = sh.small[i];
+  // post-step readout: the step's own input reaches its output through H_0, the later ones through H_{t+1}
+  float Hs[CC_LIN_MAXM - 1];
+#pragma unroll
+  for (int t = 0; t < CC_LIN_MAXM - 1; ++t) Hs[t] = post ? H[t + 1] : H[t];
+  const float H0 = post ? H[0] : 0.f;
   float pst[8 * NCH];
 #pragma unroll
   for (int i = 0; i < 8 * NCH; ++i) pst[i] = 0.f;
@@ -205,7 +277,20 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_cl_fwd_kernel(const 
   for (int i = 0; i < CC_TINY_S; ++i) xc[i] = 0.f;
   float yprev = p.lin_pack[CC_LIN_SMALL + CC_LIN_S_D0];  // y0 = g(x0 = 0) = d     neural_ode_model.py:160-175
   float tc = C.t0;
-  if (STG) cc_lin_tile_load(tin, p.in, b0, nact, T, T, 0, lane);
+  CcLctrlRows<LC ? CFG : 0> LR;
+  if (LC) cc_lctrl_load<LC ? CFG : 0>(sh.clin, LR);
+  if (STG) cc_lin_tile_load(cc_smem + tin_off, p.in, b0, nact, T, T, 0, lane);
+  // walking pointers: the tape record of step k ([rows][Bpad] floats), this trajectory's rows of the [B, T] arrays
+  const long long Bp = p.Bpad;
+  const bool tape = p.tape != nullptr && act;
+  float* tpk = p.tape ? p.tape + b : nullptr;
+  const long long tstep = (long long)p.tape_rows * Bp;
+  const long long toff_y = (long long)p.tape_yrow * Bp, toff_c = (long long)C.tape_row * Bp;
+  const float* inrow = p.in + (act ? b : 0) * (long long)T * R;
+  float* outrow = p.out + (act ? b : 0) * (long long)T;
+  const float* nzrow = p.noise ? p.noise + (act ? b : 0) * (long long)T : nullptr;
+  float* uorow = (p.u_out && act) ? p.u_out + b * (long long)T : nullptr;
+  float* ttab = (p.tape && CD.has_t && blockIdx.x == 0 && tid == 0) ? p.tape + (long long)p.n_ckpt * p.tape_rows * Bp : nullptr;
   float a[CC_LIN_MAXM];
   for (int k0 = 0; k0 < T; k0 += m) {
     // ---- one MMA batch for the block: A was completed by the previous block's sequential phase ----
@@ -224,59 +309,70 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_cl_fwd_kernel(const 
       if constexpr (NCH == 8) pst[CC_LIN_ONE] = 1.f;
     }
     const int nst = T - k0 < m ? T - k0 : m;
+#pragma unroll 1
     for (int j = 0; j < nst; ++j) {
       const int k = k0 + j;
-      if (STG && (k & 31) == 0) {  // chunk boundary: the chunk's tile has landed; prefetch the next one
+      const int kc = k & 31;
+      if (STG && kc == 0) {  // chunk boundary: the chunk's tile has landed; prefetch the next one
         cc_lin_cp_wait_all();
         __syncwarp();
-        cc_lin_tile_load(tin + (((k >> 5) + 1) & 1) * CC_LIN_TILE, p.in, b0, nact, T, T, (k >> 5) + 1, lane);
+        cc_lin_tile_load(cc_smem + tin_off + (((k >> 5) + 1) & 1) * CC_LIN_TILE, p.in, b0, nact, T, T, (k >> 5) + 1, lane);
       }
-      if (tape && blockIdx.x == 0 && tid == 0) {
-        float* ttab = p.tape + (long long)p.n_ckpt * p.tape_rows * p.Bpad;
-        ttab[k] = tc; ttab[T + k] = 0.f;
-      }
+      if (ttab) { ttab[k] = tc; ttab[T + k] = 0.f; }
       // controller input = merge_x_y(ref, y_prev) = [ref ; obs]     step_fn.py:187-192
       float vc[CC_TINY_O];
 #pragma unroll
       for (int i = 0; i < CC_TINY_O; ++i) {
         vc[i] = 0.f;
         if (i < R) {
-          if (STG) vc[i] = tin[((k >> 5) & 1) * CC_LIN_TILE + lane * 33 + (k & 31)];
-          else if (act) vc[i] = __ldg(p.in + b * (long long)T * R + (long long)k * R + i);
+          if (STG) vc[i] = cc_smem[tin_off + ((k >> 5) & 1) * CC_LIN_TILE + trow + kc];
+          else if (act) vc[i] = __ldg(inrow + (long long)k * R + i);
         }
         if (i == R) vc[i] = yprev;
       }
-      if (tape && act) {
-        p.tape[((long long)k * p.tape_rows + p.tape_yrow) * p.Bpad + b] = yprev;
+      if (tape) {
+        tpk[toff_y] = yprev;
 #pragma unroll
         for (int s = 0; s < CC_TINY_S; ++s)
-          if (s < CD.S) p.tape[((long long)k * p.tape_rows + C.tape_row + s) * p.Bpad + b] = xc[s];
+          if (s < CD.S) tpk[toff_c + s * Bp] = xc[s];
       }
+      if (p.tape) tpk += tstep;
       float araw[CC_TINY_O];
 #pragma unroll
       for (int i = 0; i < CC_TINY_O; ++i) araw[i] = 0.f;
       if (CD.pre) cc_ctrl_readout_pre(CD, sh.wgc, xc, tc, vc, araw);
-      cc_ctrl_update<false>(CD, sh.wfc, sh.wgc, xc, tc, vc, araw, nullptr);
-      if (CD.has_t) tc = tc + CD.dt;
-      if (p.u_out && act) p.u_out[b * (long long)T + k] = araw[0];
-      const float ut = cc_ut(M.ut, M.u_scale, araw[0]);
-      cc_lin_store_split1(tm, CC_LIN_SLOT(j), ut);
-      float y = a[0];
-      if (q) y = fmaf(H[0], ut, y);
+      if (LC) {  // collapsed integrator step of the linear controller; post-step readout g([x_c+ ; v])
+        float xn[CC_TINY_S];
+        cc_lctrl_next<LC ? CFG : 0>(CD, sh.clin, LR, xc, vc, xn);
 #pragma unroll
-      for (int t = 0; t < CC_LIN_MAXM - 1; ++t) a[t] = fmaf(q ? H[t + 1] : H[t], ut, a[t + 1]);
+        for (int n = 0; n < CC_TINY_S; ++n) xc[n] = xn[n];
+        if (!CD.pre) {
+          CcCtrlIn cin;
+          cc_ctrl_make_in(xc, tc, vc, cin);
+          cc_ctrl_readout(CD, sh.wgc, cin, araw);
+        }
+      } else {
+        cc_ctrl_update<false>(CD, sh.wfc, sh.wgc, xc, tc, vc, araw, nullptr);
+      }
+      if (CD.has_t) tc = tc + CD.dt;
+      if (uorow) uorow[k] = araw[0];
+      const float ut = cc_ut(mut, mus, araw[0]);
+      cc_lin_store_split1(tm, CC_LIN_SLOT(j), ut);
+      float y = fmaf(H0, ut, a[0]);
+#pragma unroll
+      for (int t = 0; t < CC_LIN_MAXM - 1; ++t) a[t] = fmaf(Hs[t], ut, a[t + 1]);
       a[CC_LIN_MAXM - 1] = 0.f;
-      if (p.noise && act) y += __ldg(p.noise + b * (long long)T + k);
+      if (nzrow && act) y += __ldg(nzrow + k);
       yprev = y;
       if (STG) {
-        tout[lane * 33 + (k & 31)] = y;
-        if ((k & 31) == 31 || k == T - 1) {
+        cc_smem[tout_off + trow + kc] = y;
+        if (kc == 31 || k == T - 1) {
           __syncwarp();
-          cc_lin_tile_store(tout, p.out, b0, nact, T, T, k >> 5, lane);
+          cc_lin_tile_store(cc_smem + tout_off, p.out, b0, nact, T, T, k >> 5, lane);
           __syncwarp();
         }
       } else if (act) {
-        p.out[b * (long long)T + k] = y;
+        outrow[k] = y;
       }
     }
   }
@@ -287,7 +383,7 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_cl_fwd_kernel(const 
 // ------------------------------------------------------------------------------------------------
 // K4: closed-loop reverse pass, controller gradient (frozen linear SISO model)
 // ------------------------------------------------------------------------------------------------
-template <int NCH, int CFG, bool STG>
+template <int NCH, int CFG, bool STG, bool LC>
 __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_cl_bwd_kernel(const CC_GRID_CONSTANT CcKParams gp) {
   CC_DIRECT_PARAMS(gp)
   (void)cta_smem;
@@ -298,10 +394,16 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_cl_bwd_kernel(const 
   const CcLinShared sh = cc_lin_carve(cc_smem);
   CcLinTm tm;
   const int stage_floats = STG ? 4 * 4 * CC_LIN_TILE : 0;  // per warp: refs x2, ybar x2
-  const int gp_floats = (C.S + C.O) * CC_CKU * 128;
-  const int keep_floats = (C.f.layer[0].act != CC_ACT_IDENTITY ? 9 : 5) * CC_TINY_S * 128;
+  // linear controller with a compile-time shape: gradient accumulators in registers, nothing in shared memory
+  constexpr bool REGACC = LC && CFG != 0;
+  const int gp_floats = REGACC ? 0 : (C.S + C.O) * CC_CKU * 128;
+  const int keep_floats = LC ? 0 : (C.f.layer[0].act != CC_ACT_IDENTITY ? 9 : 5) * CC_TINY_S * 128;
   cc_lin_prologue(p, sh, true, tm, CC_LIN_SM_STAGE + stage_floats + gp_floats + keep_floats);
-  const int S = M.S, m = p.lin_m, q = M.pre ? 0 : 1, T = p.T, R = p.R;
+  const int S = M.S, m = p.lin_m, T = p.T;
+  const int R = CFG ? 1 : p.R;
+  const bool post = !M.pre;
+  const int mut = M.ut;
+  const float mus = M.u_scale;
   const long long b0 = (long long)blockIdx.x * 128 + warp * 32;
   const long long rem = p.B - b0;
   const int nact = rem >= 32 ? 32 : (rem > 0 ? (int)rem : 0);
@@ -311,11 +413,26 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_cl_bwd_kernel(const 
   float* tyb = tref + 2 * CC_LIN_TILE;
   float* GP = sh.stage + stage_floats + tid;         // lane-private gradient accumulators
   float* keep = sh.stage + stage_floats + gp_floats + tid;  // controller stage record of the current step
-  for (int e = 0; e < (C.S + C.O) * CC_CKU; ++e) GP[e * 128] = 0.f;
+  if (!REGACC)
+    for (int e = 0; e < (C.S + C.O) * CC_CKU; ++e) GP[e * 128] = 0.f;
+  // REGACC: M[n][c] += lam+_n * [x_c (5) ; v (2) ; 1][c],  g[c] += d * [x_r (5) ; v (2) ; 1][c]   (c = node-layout row index)
+  float Macc[REGACC ? 5 : 1][8], gacc[8];
+#pragma unroll
+  for (int n = 0; n < (REGACC ? 5 : 1); ++n)
+#pragma unroll
+    for (int c2 = 0; c2 < 8; ++c2) Macc[n][c2] = 0.f;
+#pragma unroll
+  for (int c2 = 0; c2 < 8; ++c2) gacc[c2] = 0.f;
+  CcLctrlRows<LC ? CFG : 0> LR;
+  if (LC) cc_lctrl_load<LC ? CFG : 0>(sh.clin, LR);
   const float* ttab = p.tape + (long long)p.n_ckpt * p.tape_rows * p.Bpad;
   float H[CC_LIN_MAXM + 1];
 #pragma unroll
   for (int i = 0; i <= CC_LIN_MAXM; ++i) H[i] = sh.small[i];
+  float Hs[CC_LIN_MAXM - 1];
+#pragma unroll
+  for (int t = 0; t < CC_LIN_MAXM - 1; ++t) Hs[t] = post ? H[t + 1] : H[t];
+  const float H0 = post ? H[0] : 0.f;
   float rst[8 * NCH];
 #pragma unroll
   for (int i = 0; i < 8 * NCH; ++i) rst[i] = 0.f;
@@ -331,6 +448,28 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_cl_bwd_kernel(const 
     cc_lin_tile_load(tyb + ((nchunk - 1) & 1) * CC_LIN_TILE, p.ybar, b0, nact, T, T, nchunk - 1, lane);
   }
   int cur_chunk = nchunk;  // chunk whose tiles are valid (none yet)
+  // the loads of step k-1 (tape record, reference, cotangent) are issued while step k is processed
+  const long long Bp = p.Bpad;
+  const long long tstep = (long long)p.tape_rows * Bp;
+  const long long toff_y = (long long)p.tape_yrow * Bp, toff_c = (long long)C.tape_row * Bp;
+  const float* tpk = p.tape + (act ? b : 0) + (long long)(T - 1) * tstep;
+  const float* inrow = p.in + (act ? b : 0) * (long long)T * R;
+  const float* ybrow = p.ybar + (act ? b : 0) * (long long)T;
+  float n_ref[CC_TINY_O], n_xc[CC_TINY_S], n_yb = 0.f, n_yp = 0.f;
+  auto fetch = [&](int k) {
+    n_yp = tpk[toff_y];
+#pragma unroll
+    for (int s2 = 0; s2 < CC_TINY_S; ++s2) n_xc[s2] = s2 < CD.S ? tpk[toff_c + s2 * Bp] : 0.f;
+    tpk -= tstep;
+    if (!STG) {
+      n_yb = __ldg(ybrow + k);
+#pragma unroll
+      for (int i = 0; i < CC_TINY_O; ++i) n_ref[i] = i < R ? __ldg(inrow + (long long)k * R + i) : 0.f;
+    }
+  };
+#pragma unroll
+  for (int i = 0; i < CC_TINY_O; ++i) n_ref[i] = 0.f;
+  if (T > 0) fetch(T - 1);
   for (int blk = nblk - 1; blk >= 0; --blk) {
     const int k0 = blk * m;
     cc_lin_round(tm);
@@ -344,6 +483,7 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_cl_bwd_kernel(const 
     }
     cc_lin_advance_state<NCH>(tm, rst, S);
     const int nst = T - k0 < m ? T - k0 : m;
+#pragma unroll 1
     for (int j = nst - 1; j >= 0; --j) {
       const int k = k0 + j;
       if (STG && (k >> 5) != cur_chunk) {  // entering chunk k>>5 (walking down): its tiles have landed; prefetch the one below
@@ -356,40 +496,90 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_cl_bwd_kernel(const 
         }
       }
       float vc[CC_TINY_O], xcv[CC_TINY_S];
-      float yb = 0.f;
-      if (STG) yb = tyb[(cur_chunk & 1) * CC_LIN_TILE + lane * 33 + (k & 31)];
-      else if (act) yb = __ldg(p.ybar + b * (long long)T + k);
-      const float ypk = act ? p.tape[((long long)k * p.tape_rows + p.tape_yrow) * p.Bpad + b] : 0.f;
+      float yb = STG ? tyb[(cur_chunk & 1) * CC_LIN_TILE + lane * 33 + (k & 31)] : n_yb;
+      const float ypk = n_yp;
 #pragma unroll
       for (int i = 0; i < CC_TINY_O; ++i) {
         vc[i] = 0.f;
-        if (i < R) {
-          if (STG) vc[i] = tref[(cur_chunk & 1) * CC_LIN_TILE + lane * 33 + (k & 31)];
-          else if (act) vc[i] = __ldg(p.in + b * (long long)T * R + (long long)k * R + i);
-        }
+        if (i < R) vc[i] = STG ? tref[(cur_chunk & 1) * CC_LIN_TILE + lane * 33 + (k & 31)] : n_ref[i];
         if (i == R) vc[i] = ypk;
       }
 #pragma unroll
-      for (int s = 0; s < CC_TINY_S; ++s) xcv[s] = (s < CD.S && act) ? p.tape[((long long)k * p.tape_rows + C.tape_row + s) * p.Bpad + b] : 0.f;
+      for (int s2 = 0; s2 < CC_TINY_S; ++s2) xcv[s2] = n_xc[s2];
+      if (!act) {  // (inactive lanes read trajectory 0's data: keep their arithmetic finite and their sums zero)
+        yb = 0.f;
+      }
+      if (k > 0) fetch(k - 1);
       const float tc = CD.has_t ? ttab[k] : 0.f;
       const float w = yb + yfb;  // cotangent of y_k: loss + feedback into step k+1
       cc_lin_store_split1(tm, CC_LIN_SLOT(j), w);
-      float utb = c[0];
-      if (q) utb = fmaf(H[0], w, utb);
+      const float utb = fmaf(H0, w, c[0]);
 #pragma unroll
-      for (int t = 0; t < CC_LIN_MAXM - 1; ++t) c[t] = fmaf(q ? H[t + 1] : H[t], w, c[t + 1]);
+      for (int t = 0; t < CC_LIN_MAXM - 1; ++t) c[t] = fmaf(Hs[t], w, c[t + 1]);
       c[CC_LIN_MAXM - 1] = 0.f;
-      // recompute the controller step (stage record kept), then its reverse pass
-      float araw[CC_TINY_O];
+      float araw[CC_TINY_O], vb[CC_TINY_O];
 #pragma unroll
       for (int i = 0; i < CC_TINY_O; ++i) araw[i] = 0.f;
-      if (CD.pre) cc_ctrl_readout_pre(CD, sh.wgc, xcv, tc, vc, araw);
-      cc_ctrl_update<true>(CD, sh.wfc, sh.wgc, xcv, tc, vc, araw, keep);
-      float ob[CC_TINY_O], vb[CC_TINY_O];
+      if (LC) {
+        // linear controller (one output): the step is x_c+ = Phi_c x_c + (Gam_c B_c) v + gam, a = alpha g([x_r ; v]) with
+        // x_r = x_c (pre-step readout) or x_c+; its reverse pass needs no stage record:
+        //   d = alpha abar ; lam' = lam+ (+ g_x^T d, post) ; M += lam' (x) [x_c ; v ; 1] ; g-grad += d (x) [x_r ; v ; 1]
+        //   lam = Phi_c^T lam' (+ g_x^T d, pre) ; vbar = (Gam_c B_c)^T lam' + g_v^T d
+        float xr[CC_TINY_S];
+        if (CD.pre) {
 #pragma unroll
-      for (int i = 0; i < CC_TINY_O; ++i) ob[i] = 0.f;
-      ob[0] = utb * cc_ut_grad(M.ut, M.u_scale, araw[0]);
-      cc_ctrl_bwd(CD, sh.wfc, sh.wgc, GP, tc, vc, keep, araw, ob, lamc, vb);
+          for (int n = 0; n < CC_TINY_S; ++n) xr[n] = xcv[n];
+        } else {
+          cc_lctrl_next<LC ? CFG : 0>(CD, sh.clin, LR, xcv, vc, xr);
+        }
+        CcCtrlIn rin;
+        cc_ctrl_make_in(xr, tc, vc, rin);
+        cc_ctrl_readout(CD, sh.wgc, rin, araw);
+        const float d = CD.out_scale * (utb * cc_ut_grad(mut, mus, araw[0]));
+        float wg[CC_CK];
+        cc_ctrl_load_row(sh.wgc, wg);
+        float lamp[CC_TINY_S];
+#pragma unroll
+        for (int n = 0; n < CC_TINY_S; ++n) lamp[n] = (!CD.pre && n < CD.S) ? fmaf(wg[n], d, lamc[n]) : lamc[n];
+        CcCtrlIn fin;
+        cc_ctrl_make_in(xcv, tc, vc, fin);
+        if constexpr (REGACC) {
+#pragma unroll
+          for (int n = 0; n < 5; ++n) {
+#pragma unroll
+            for (int c2 = 0; c2 < 5; ++c2) Macc[n][c2] = fmaf(lamp[n], xcv[c2], Macc[n][c2]);
+            Macc[n][5] = fmaf(lamp[n], vc[0], Macc[n][5]);
+            Macc[n][6] = fmaf(lamp[n], vc[1], Macc[n][6]);
+            Macc[n][7] += lamp[n];
+          }
+#pragma unroll
+          for (int c2 = 0; c2 < 5; ++c2) gacc[c2] = fmaf(d, xr[c2], gacc[c2]);
+          gacc[5] = fmaf(d, vc[0], gacc[5]);
+          gacc[6] = fmaf(d, vc[1], gacc[6]);
+          gacc[7] += d;
+        } else {
+#pragma unroll
+          for (int n = 0; n < CC_TINY_S; ++n)
+            if (n < CD.S) cc_ctrl_gacc(GP, n, lamp[n], fin, CD.S, false, CD.I);
+          cc_ctrl_gacc(GP, CD.S, d, rin, CD.S, false, CD.I);
+        }
+        cc_lctrl_next_bwd<LC ? CFG : 0>(CD, sh.clin, LR, lamp, lamc, vb);
+#pragma unroll
+        for (int n = 0; n < CC_TINY_S; ++n)
+          if (CD.pre && n < CD.S) lamc[n] = fmaf(wg[n], d, lamc[n]);
+#pragma unroll
+        for (int i = 0; i < CC_TINY_O; ++i)
+          if (i < CD.I) vb[i] = fmaf(wg[CC_C_V + i], d, vb[i]);  // feed-through columns of g (zero weights without feed-through)
+      } else {
+        // recompute the controller step (stage record kept), then its reverse pass
+        if (CD.pre) cc_ctrl_readout_pre(CD, sh.wgc, xcv, tc, vc, araw);
+        cc_ctrl_update<true>(CD, sh.wfc, sh.wgc, xcv, tc, vc, araw, keep);
+        float ob[CC_TINY_O];
+#pragma unroll
+        for (int i = 0; i < CC_TINY_O; ++i) ob[i] = 0.f;
+        ob[0] = utb * cc_ut_grad(mut, mus, araw[0]);
+        cc_ctrl_bwd(CD, sh.wfc, sh.wgc, GP, tc, vc, keep, araw, ob, lamc, vb);
+      }
       yfb = 0.f;
 #pragma unroll
       for (int i = 0; i < CC_TINY_O; ++i)
@@ -404,7 +594,20 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_cl_bwd_kernel(const 
     for (int row = 0; row < C.S + C.O; ++row) {
       const int goff = row < C.S ? C.f.layer[0].g_off + row * C.K0 : C.g.layer[0].g_off + (row - C.S) * C.K0;
       for (int r = 0; r < C.K0; ++r) {
-        float v = act ? GP[(row * CC_CKU + cc_ctrl_col_of_row(C, r)) * 128] : 0.f;
+        float v = 0.f;
+        if constexpr (REGACC) {  // (row, r) -> register: compile-time selection chain (5 + 1 rows x 8 node-layout columns)
+#pragma unroll
+          for (int n = 0; n < 5; ++n)
+#pragma unroll
+            for (int c2 = 0; c2 < 8; ++c2)
+              if (row == n && r == c2) v = Macc[n][c2];
+#pragma unroll
+          for (int c2 = 0; c2 < 8; ++c2)
+            if (row == 5 && r == c2) v = gacc[c2];
+          if (!act) v = 0.f;
+        } else {
+          v = act ? GP[(row * CC_CKU + cc_ctrl_col_of_row(C, r)) * 128] : 0.f;
+        }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(CC_FULL, v, off);
         if (lane == 0 && wt < p.n_wtiles) rec[C.g_base + goff + r] = v;

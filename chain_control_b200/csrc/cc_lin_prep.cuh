@@ -23,6 +23,9 @@ struct CcLinPrepArgs {
   double* tab;          // CC_LIN_TAB_DOUBLES(m) doubles or nullptr
   int m;                // block length
   int form;             // 0: "P" (closed loop), 1: "X" (open loop)
+  int ctrl;             // 1: also collapse the (linear, tiny) controller's integrator step
+  CcNodeDev C;          // the controller node
+  const float* theta_c;
 };
 
 // C = A . B  (n x n, row stride 64); all threads; barrier at the end
@@ -287,7 +290,7 @@ __global__ void __launch_bounds__(CC_LIN_PREP_THREADS, 1) cc_lin_prep_kernel(con
   }
   // ---- small tables ----
   float* sp = a.pack + CC_LIN_SMALL;
-  for (int e = tid; e < CC_LIN_SMALL_FLOATS + 12; e += nthr) {
+  for (int e = tid; e < CC_LIN_SMALL_FLOATS; e += nthr) {
     float v = 0.f;
     if (e < CC_LIN_S_CONST) {                       // H[n][o][i]
       const int n = e / 16;
@@ -311,5 +314,157 @@ __global__ void __launch_bounds__(CC_LIN_PREP_THREADS, 1) cc_lin_prep_kernel(con
       if (s < S && t < m * O) v = (float)RG[((t / O + q) * O + t % O) * 64 + s];
     }
     sp[e] = v;
+  }
+  // ---- linear tiny controller: Phi_c, Gam_c B_c, Gam_c c_c (8 x 8 matrices, same Horner scheme) ----
+  if (a.ctrl) {
+    __syncthreads();
+    const CcNodeDev& C = a.C;
+    const CcLayerDev& FC = C.f.layer[0];
+    const int Sc = C.S, Ic = C.I;
+    const double hc = (double)C.dt;
+    double* cA = hA;        // [8][8] h*A_c
+    double* cX = hA + 64;
+    double* cY = hA + 128;
+    double* cP = hA + 192;  // Phi_c
+    double* cG = hA + 256;  // Gam_c
+    auto mm8 = [&](double* Cm, const double* Am, const double* Bm) {  // 8 x 8, all threads; barrier at the end
+      if (tid < 64) {
+        const int i = tid / 8, j = tid % 8;
+        double acc = 0.0;
+        for (int k = 0; k < 8; ++k) acc += Am[i * 8 + k] * Bm[k * 8 + j];
+        Cm[tid] = acc;
+      }
+      __syncthreads();
+    };
+    const int ci = tid / 8, cj = tid % 8;
+    const bool cin = tid < 64 && ci < Sc && cj < Sc;
+    const double eye = (tid < 64 && ci == cj && ci < Sc) ? 1.0 : 0.0;
+    if (tid < 64) cA[tid] = cin ? hc * (double)cc_weight_at(C, FC, a.theta_c, ci, cj) : 0.0;
+    __syncthreads();
+    if (C.integrator == CC_INT_RK4) {
+      if (tid < 64) cX[tid] = eye + cA[tid] / 4.0;
+      __syncthreads();
+      mm8(cY, cA, cX);
+      if (tid < 64) cY[tid] = eye + (cin ? cY[tid] / 3.0 : 0.0);
+      __syncthreads();
+      mm8(cX, cA, cY);
+      if (tid < 64) cX[tid] = eye + (cin ? cX[tid] / 2.0 : 0.0);
+      __syncthreads();
+      mm8(cP, cA, cX);
+      if (tid < 64) { cP[tid] = cin ? eye + cP[tid] : 0.0; cG[tid] = cin ? hc * cX[tid] : 0.0; }
+    } else if (C.integrator == CC_INT_EE) {
+      if (tid < 64) { cP[tid] = cin ? eye + cA[tid] : 0.0; cG[tid] = eye * hc; }
+    } else {
+      if (tid < 64) { cP[tid] = cin ? cA[tid] / hc : 0.0; cG[tid] = eye; }
+    }
+    __syncthreads();
+    if (tid < 64) {
+      sp[CC_LIN_S_CPHI + tid] = (float)cP[tid];
+      double* ctab = reinterpret_cast<double*>(sp + CC_LIN_S_CTAB);
+      ctab[tid] = cA[tid] / hc;
+      ctab[64 + tid] = cG[tid];
+    }
+    if (tid < 32) {  // (Gam_c B_c)[n][i]
+      const int n = tid / 4, i = tid % 4;
+      double acc = 0.0;
+      if (n < Sc && i < Ic)
+        for (int k = 0; k < Sc; ++k) acc += cG[n * 8 + k] * (double)cc_weight_at(C, FC, a.theta_c, k, C.row_v + i);
+      sp[CC_LIN_S_CGB + tid] = (float)acc;
+    }
+    if (tid >= 32 && tid < 40) {  // (Gam_c c_c)[n]
+      const int n = tid - 32;
+      double acc = 0.0;
+      if (n < Sc)
+        for (int k = 0; k < Sc; ++k) acc += cG[n * 8 + k] * (double)cc_weight_at(C, FC, a.theta_c, k, C.row_one);
+      sp[CC_LIN_S_CGAM + n] = (float)acc;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// gradient of a LINEAR tiny controller from M = sum lam' (x) [x_c ; v ; 1] (reduced into a theta-shaped buffer: f.weight holds
+// the x / v columns, f.bias the constant column; g's slots already hold its true gradient): derivative of the matrix
+// polynomials Phi_c(A_c), Gam_c(A_c) in fp64 (8 x 8), like cc_lin_grad_final_kernel does for a trainable model
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) cc_lin_cgrad_kernel(const CC_GRID_CONSTANT CcLinCgradArgs a) {
+#ifndef CC_EMULATE
+  __shared__ double sm[8 * 64];
+#else
+  double* sm = reinterpret_cast<double*>(CC_SMEM_PTR);
+#endif
+  double* Mx = sm;        // [8][8]
+  double* Mb = sm + 64;   // M_beta
+  double* At = sm + 128;  // h A^T
+  double* U = sm + 192;
+  double* V = sm + 256;
+  double* W = sm + 320;
+  double* Ab = sm + 384;  // Abar
+  double* Mv = sm + 448;  // [8][4] then M1[8] at +32
+  const CcNodeDev& C = a.C;
+  const CcLayerDev& F = C.f.layer[0];
+  const int S = C.S, I = C.I, P = C.P;
+  const int tid = threadIdx.x, i = tid / 8, j = tid % 8;
+  const double h = (double)C.dt;
+  const double* ctab = reinterpret_cast<const double*>(a.pack + CC_LIN_SMALL + CC_LIN_S_CTAB);
+  for (int e = tid; e < P; e += 64) a.theta_bar[e] = a.msum[e];  // g part (and everything else) as reduced
+  const bool in = i < S && j < S;
+  Mx[tid] = in ? (double)a.msum[F.w_off + i * F.in_log + j] : 0.0;
+  At[tid] = in ? h * ctab[j * 8 + i] : 0.0;
+  if (tid < 32) Mv[tid] = (tid / 4 < S && tid % 4 < I) ? (double)a.msum[F.w_off + (tid / 4) * F.in_log + S + tid % 4] : 0.0;
+  if (tid >= 32 && tid < 40) Mv[tid] = (tid - 32 < S && F.b_off >= 0) ? (double)a.msum[F.b_off + tid - 32] : 0.0;
+  Ab[tid] = 0.0;
+  __syncthreads();
+  {  // M_beta = Mv B^T + M1 c^T
+    double acc = 0.0;
+    if (in) {
+      for (int ii = 0; ii < I; ++ii) acc += Mv[i * 4 + ii] * (double)cc_weight_at(C, F, a.theta_c, j, C.row_v + ii);
+      acc += Mv[32 + i] * (double)cc_weight_at(C, F, a.theta_c, j, C.row_one);
+    }
+    Mb[tid] = acc;
+  }
+  __syncthreads();
+  auto mm8 = [&](double* Cm, const double* Am, const double* Bm) {
+    double acc = 0.0;
+    for (int k = 0; k < 8; ++k) acc += Am[i * 8 + k] * Bm[k * 8 + j];
+    __syncthreads();
+    Cm[tid] = acc;
+    __syncthreads();
+  };
+  auto poly_apply = [&](const double* Min, int nmax, const double* cf) {  // Ab += sum_{a+b<=nmax-1} cf[a+b+1] X^a Min X^b
+    V[tid] = 0.0;
+    __syncthreads();
+    for (int bb = nmax - 1; bb >= 0; --bb) {
+      if (bb != nmax - 1) mm8(V, V, At);
+      U[tid] = Min[tid];
+      __syncthreads();
+      for (int aa = 0; aa <= nmax - 1 - bb; ++aa) {
+        if (aa > 0) mm8(U, At, U);
+        V[tid] += cf[aa + bb + 1] * U[tid];
+        __syncthreads();
+      }
+    }
+    Ab[tid] += V[tid];
+    __syncthreads();
+  };
+  (void)W;
+  if (C.integrator == CC_INT_RK4) {
+    const double cphi[5] = {0.0, h, h * 0.5, h / 6.0, h / 24.0};
+    poly_apply(Mx, 4, cphi);
+    const double cgam[4] = {0.0, h * h * 0.5, h * h / 6.0, h * h / 24.0};
+    poly_apply(Mb, 3, cgam);
+  } else if (C.integrator == CC_INT_EE) {
+    Ab[tid] = h * Mx[tid];
+  } else {
+    Ab[tid] = Mx[tid];
+  }
+  __syncthreads();
+  if (in) a.theta_bar[F.w_off + i * F.in_log + j] = (float)Ab[tid];
+  // Bbar = Gam^T Mv, cbar = Gam^T M1
+  if (tid < 40) {
+    const int n = tid < 32 ? tid / 4 : tid - 32, ii = tid % 4;
+    double acc = 0.0;
+    for (int s = 0; s < S; ++s) acc += ctab[64 + s * 8 + n] * (tid < 32 ? Mv[s * 4 + ii] : Mv[32 + s]);
+    if (tid < 32) { if (n < S && ii < I) a.theta_bar[F.w_off + n * F.in_log + S + ii] = (float)acc; }
+    else if (n < S && F.b_off >= 0) a.theta_bar[F.b_off + n] = (float)acc;
   }
 }

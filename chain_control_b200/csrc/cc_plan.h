@@ -141,6 +141,7 @@ struct CcKParams {
   int lin_m;               // steps per block
   int lin_mt;              // open-loop forward with x_final and T % lin_m != 0: length of the ragged tail (second prep pack), else 0
   int lin_stage;           // coalesced I/O through shared-memory tiles (cc_lin_kernels.cuh)
+  int lin_lc;              // closed loop: the controller is linear too -> its integrator step is collapsed (cc_lin_prep.cuh)
   const float* lin_pack;   // output of cc_lin_prep_kernel (block matrices + small tables), global memory
   double* lin_tab;         // fp64 tables for the gradient post-processing (trainable models), or nullptr
   float* lin_q;            // trainable open loop: per-CTA partial sums of Q = Lam (x) X

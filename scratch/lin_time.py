@@ -54,19 +54,9 @@ def open_(B, T, env):
     return out
 
 res = {}
-for name, B, T in [("cfg2x", 65536, 1001), ("cfg2", 64, 1001), ("b8192", 8192, 1001), ("b4096_T10001", 4096, 10001)]:
-    for tag, env in [("lin_stage1", {}), ("lin_stage0", {"CC_B200_LIN_STAGE": "0"}), ("old", {"CC_B200_LIN": "0"})]:
-        if name == "b4096_T10001" and tag == "old": continue
+for name, B, T in [("cfg2x", 65536, 1001), ("cfg2", 64, 1001), ("b8192", 8192, 1001)]:
+    for tag, env in [("lin", {}), ("lin_nostagebwd", {"CC_B200_LIN_STAGE_BWD": "0"}), ("lin_nostage", {"CC_B200_LIN_STAGE": "0"}), ("lin_nolc", {"CC_B200_LIN_LC": "0"})]:
         r = closed(B, T, env)
         res[f"closed_{name}_{tag}"] = r
         print(f"closed {name} {tag}: {r}", flush=True)
-for name, B, T in [("cfg4", 65536, 1000), ("cfg1", 8, 1000), ("b8192", 8192, 1000)]:
-    for tag, env in [("lin_stage1", {}), ("lin_stage0", {"CC_B200_LIN_STAGE": "0"}), ("old", {"CC_B200_LIN": "0"})]:
-        r = open_(B, T, env)
-        res[f"open_{name}_{tag}"] = r
-        print(f"open {name} {tag}: {r}", flush=True)
-for mm in (4, 8, 13):
-    r = closed(65536, 1001, {"CC_B200_LIN_M": str(mm)})
-    res[f"closed_cfg2x_m{mm}"] = r
-    print(f"closed cfg2x m={mm}: {r}", flush=True)
-json.dump(res, open("gpurun_out/lin_time.json", "w"), indent=1)
+json.dump(res, open("gpurun_out/lin_time2.json", "w"), indent=1)
