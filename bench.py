@@ -7,14 +7,16 @@ BASELINE.json's metric is quoted on.
 
 One "step" = one pass of the hot path over one batch of synthetic trajectories:
 closed-loop forward rollout -> MSE value + cotangent -> BPTT -> gradient reduction
-(-> NCCL allreduce of the P+1 gradient/loss vector when N > 1).  Default workload (`cfg2x`): the
-closed-loop ControllerTrainer step of BASELINE.json configs[1] (compact controller S_c=5 + frozen
-compact model S_m=50, RK4, dt=0.01, T_r=1001) at the batch of configs[3] (65,536 trajectories per GPU,
-weak scaling).  `--workload cfg2` is configs[1] literally (64 trajectories, latency bound);
-`--workload cfg4` is the open-loop ModelTrainer step of configs[3].
+(-> NCCL allreduce of the P+1 gradient/loss vector when N > 1) -> fused clip + Adam update (cc_opt_step).
+Default workload (`cfg2x`): the closed-loop ControllerTrainer step of BASELINE.json configs[1] (compact controller
+S_c=5 + frozen compact model S_m=50, RK4, dt=0.01, T_r=1001) at the batch of configs[3] (65,536 trajectories per GPU,
+weak scaling); the same line carries a `strong` block (65,536 trajectories in total, sharded B/N) and, at N = 1,
+`config.other_workloads` with configs[0], [1], [3] literally and configs[4] (T_r = 10,001, ckpt_every = 100).
 Prints ONE JSON line on rank 0.
 """
 import argparse
+import csv
+import glob
 import json
 import os
 import statistics
@@ -63,28 +65,31 @@ def make_refs(B, Tr, seed):
 
 
 WORKLOADS = {
-    # name: (closed_loop, B per GPU, T)
-    "cfg2x": (True, 65536, 1001),
-    "cfg2": (True, 64, 1001),
-    "cfg4": (False, 65536, 1000),
-    "cfg1": (False, 8, 1000),
+    # name: closed loop?, B per GPU, T, ckpt_every, description
+    "cfg2x": (True, 65536, 1001, 1, "closed-loop ControllerTrainer step (configs[1] architecture: compact controller S_c=5 + frozen compact model "
+                                    "S_m=50, RK4, dt=0.01, T_r=1001) at configs[3]'s batch, 65536 trajectories per GPU"),
+    "cfg2": (True, 64, 1001, 1, "configs[1]: closed-loop ControllerTrainer BPTT, 64 trajectories x 1001 steps"),
+    "cfg4": (False, 65536, 1000, 1, "configs[3]: ModelTrainer step, 65536 trajectories x 1000 steps, S=50 depth 0"),
+    "cfg1": (False, 8, 1000, 1, "configs[0]: ModelTrainer step, 8 trajectories x 1000 steps, S=50 depth 0"),
+    "cfg5": (True, 4096, 10001, 100, "configs[4]: closed-loop BPTT, T_r = 10001, 4096 trajectories, checkpointed recomputation (ckpt_every = 100)"),
 }
 # algorithmic FLOPs per trajectory-step: F = 2 (n_st M_f + M_g)
 F_C = 2 * (4 * (5 + 2) * 5 + 5)       # 290
 F_M = 2 * (4 * (50 + 1) * 50 + 50)    # 20,500
 
 
-# dram read+write bytes per trajectory-step of cc_tc_bwd_kernel from the ncu --set full capture (profiles/r01_tc_ncu_full.md);
-# None until a capture of the current kernel exists
-TRAFFIC_TC_BWD_BYTES_PER_TS = 32.4  # (2.120 GB read + 0.008 GB written) / (65,536 x 1,001)
-# same for cc_tcw_bwd_kernel (ModelTrainer reverse pass): (13.658 GB read + 0.064 GB written) / (65,536 x 1,000), profiles/r01_tcw_ncu_full.md
-TRAFFIC_TCW_BWD_BYTES_PER_TS = 209.4
-
-
 def alg_flops(closed):
     fwd = F_C + F_M if closed else F_M
     tot = 3 * F_C + 2 * F_M if closed else 3 * F_M  # frozen model: forward + input-gradient only
     return fwd, tot
+
+
+def alg_bytes(closed, m_block=13):
+    """algorithmic HBM bytes per trajectory-step of the forward / reverse kernel (4(I+O) = 8 B of inputs and
+    outputs) plus the tape: closed loop (x_c, y_prev) = 24 B per step, written forward and read in reverse; open loop the
+    state at the block starts, 4 S / 13 B per step"""
+    tape = 24.0 if closed else 4.0 * 50 / m_block
+    return 8.0 + tape, 8.0 + tape
 
 
 class ClockSampler:
@@ -136,58 +141,62 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "window": region}
 
 
-def cpu_baseline(closed, T, march="native", target_s=12.0):
-    """the oracle's C port (OpenMP, all host threads) on a bounded sample of the same workload."""
+def host_threads():
+    """all the host cores, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1 to its workers)"""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_run(closed, B, T, threads, reps=1):
+    """oracle C port (OpenMP, `threads` threads), fwd + BPTT of B trajectories x T steps: seconds per pass"""
     from oracle import c_oracle as CO
 
     ctrl, model = specs()
     thc, thm = init_theta(ctrl, 2, False), init_theta(model, 1, True)
-    cores = CO.max_threads()
-    B = 16 * cores
-    run = (lambda refs: CO.closedloop(ctrl, model, thc, thm, refs, mse_loss=True, march=march)) if closed else \
-          (lambda u: CO.rollout(model, thm, u, targets=np.zeros((u.shape[0], T + 1, 1), np.float32), march=march))
     x = make_refs(B, T, 7)
-    run(x[: 16])
-    t0 = time.time(); run(x); dt = time.time() - t0
-    reps = max(1, int(target_s / max(dt, 1e-3)))
-    reps = min(reps, 50)
+    tg = np.zeros((B, T + 1, 1), np.float32)
+    run = (lambda: CO.closedloop(ctrl, model, thc, thm, x, mse_loss=True, march="native", nthreads=threads)) if closed else \
+          (lambda: CO.rollout(model, thm, x, targets=tg, march="native", nthreads=threads))
+    run()
     t0 = time.time()
     for _ in range(reps):
-        run(x)
-    dt = (time.time() - t0) / reps
+        run()
+    return (time.time() - t0) / reps
+
+
+def cpu_baseline(closed, T, target_s=12.0):
+    """the oracle's C port (OpenMP, all host threads) on a bounded sample of the same workload."""
+    cores = host_threads()
+    B = 16 * cores
+    dt = cpu_run(closed, B, T, cores)
+    reps = min(max(1, int(target_s / max(dt, 1e-3))), 50)
+    dt = cpu_run(closed, B, T, cores, reps)
     return {"value": B * T / dt, "unit": "traj-steps/s", "cores": cores, "kind": "port",
-            "sample": f"{B} trajectories x {T} steps, fwd+BPTT, {reps} repetitions, C/OpenMP oracle port (-march={march}); "
+            "sample": f"{B} trajectories x {T} steps, fwd+BPTT, {reps} repetitions, C/OpenMP oracle port (-march=native), {cores} threads; "
                       "the reference's JAX path cannot be installed here"}
 
 
 def run_reference(args):
-    """--impl reference: the CPU implementation of the path (oracle port) on the host cores."""
+    """--impl reference: the CPU implementation of the path (oracle port) on the host cores: the same bounded sample at every N,
+    all host threads whatever OMP_NUM_THREADS says."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    closed, Bg, T = WORKLOADS[args.workload]
-    from oracle import c_oracle as CO
-
-    ctrl, model = specs()
-    thc, thm = init_theta(ctrl, 2, False), init_theta(model, 1, True)
-    cores = CO.max_threads()
-    B = min(Bg, 16 * cores * 4)  # bounded sample of the workload per step
-    x = make_refs(B, T, 7)
-    tg = np.zeros((B, T + 1, 1), np.float32)
-    step = (lambda: CO.closedloop(ctrl, model, thc, thm, x, mse_loss=True, march="native")) if closed else \
-           (lambda: CO.rollout(model, thm, x, targets=tg, march="native"))
-    for _ in range(max(args.warmup, 1)):
-        step()
-    t0 = time.time()
-    for _ in range(args.steps):
-        step()
-    dt = time.time() - t0
-    val = B * T * args.steps / dt
-    sample = f"{B} trajectories x {T} steps per step (bounded sample of {Bg}/GPU), C/OpenMP oracle port, -march=native"
+    closed, Bg, T, _, _ = WORKLOADS[args.workload]
+    cores = host_threads()
+    B = min(Bg, 1024)  # bounded sample of the workload per step (the same at every N)
+    cpu_run(closed, min(B, 64), T, cores)
+    for _ in range(max(args.warmup, 1) - 1):
+        cpu_run(closed, B, T, cores)
+    dt = cpu_run(closed, B, T, cores, args.steps)
+    val = B * T / dt
+    sample = f"{B} trajectories x {T} steps per step (bounded sample of {Bg}/GPU), C/OpenMP oracle port, -march=native, {cores} threads"
     print(json.dumps({
         "impl": "reference", "metric": "closed-loop neural-ODE traj-steps/s (fwd+BPTT)" if closed else "neural-ODE traj-steps/s (fwd+BPTT)",
         "value": val, "unit": "traj-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": 1e3 * dt, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "closed_loop": closed, "B_sample": B, "T": T, "note": "CPU restatement, not JAX"},
         "cpu_baseline": {"value": val, "unit": "traj-steps/s", "cores": cores, "kind": "port", "sample": sample},
@@ -195,14 +204,83 @@ def run_reference(args):
     }))
 
 
+def ncu_traffic(kernel_substr):
+    """dram read + write bytes of one launch of the kernel from the newest committed `ncu --set full` raw page
+    (profiles/r*_raw.csv, written from the .ncu-rep with `ncu --page raw --csv`): (bytes, file) or None"""
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r0*_raw.csv"))):
+        try:
+            rows = list(csv.reader(open(path)))
+            hdr = rows[0]
+            ik, ir, iw = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            for r in rows[2:]:
+                if kernel_substr in r[ik]:
+                    best = (float(r[ir]) * scale.get(rows[1][ir], 1.0) + float(r[iw]) * scale.get(rows[1][iw], 1.0), os.path.basename(path))
+        except Exception:
+            continue
+    return best
+
+
+class Workload:
+    """one train step of a workload on this rank's shard"""
+
+    def __init__(self, name, B, world, rank, dev, torch):
+        from chain_control_b200 import ops
+
+        self.torch, self.ops, self.name = torch, ops, name
+        self.closed, _, self.T, self.ckpt, self.desc = WORKLOADS[name]
+        self.B, self.world = B, world
+        self.ctrl, self.model = specs()
+        self.theta_m = torch.tensor(init_theta(self.model, 1, True), device=dev)
+        theta0 = torch.tensor(init_theta(self.ctrl, 2, False), device=dev) if self.closed else self.theta_m.clone()
+        self.P = theta0.numel()
+        self.opt = ops.FusedAdam(theta0, 1e-3, clip_global_norm=1.0)  # chain(clip_by_global_norm(1.0), adam(1e-3)), test_trainer.py:58
+        self.theta = self.opt.theta
+        self.host_in = torch.from_numpy(make_refs(B, self.T, 100 + rank)).pin_memory()
+        self.x = self.host_in.to(dev)
+        self.targets = None if self.closed else torch.zeros(B, self.T + 1, 1, device=dev)
+        self.n_total = world * B * (self.T if self.closed else self.T + 1)
+        self.units = B * self.T
+
+    def grads(self, x, ev=None):
+        """rollout -> loss + cotangent -> BPTT: [theta_bar ; loss] of this shard"""
+        ops, torch = self.ops, self.torch
+        if ev: ev[0].record()
+        if self.closed:
+            yhat, _, tape = ops.closedloop_fwd(self.ctrl, self.model, self.theta, self.theta_m, x, want_tape=True, ckpt_every=self.ckpt)
+            if ev: ev[1].record()
+            loss, ybar = ops.mse_value_and_cotangent(x, yhat, self.n_total)
+            if ev: ev[2].record()
+            g = ops.closedloop_bwd(self.ctrl, self.model, self.theta, self.theta_m, x, tape, ybar, ckpt_every=self.ckpt)
+        else:
+            y, _, tape = ops.rollout_fwd(self.model, self.theta, x, want_tape=True)
+            if ev: ev[1].record()
+            loss, ybar = ops.mse_value_and_cotangent(self.targets, y, self.n_total)
+            if ev: ev[2].record()
+            g, _ = ops.rollout_bwd(self.model, self.theta, x, tape, ybar)
+        if ev: ev[3].record()
+        return torch.cat([g, loss.reshape(1)])
+
+    def step(self, x, ev=None):
+        import torch.distributed as dist
+
+        gl = self.grads(x, ev)
+        if self.world > 1:
+            dist.all_reduce(gl, op=dist.ReduceOp.SUM)  # ONE NCCL allreduce of P+1 floats over NVLink
+        self.opt.step(gl[: self.P])
+        return gl
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2x", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip config.other_workloads")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -210,7 +288,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from chain_control_b200 import _lib, ops, parallel
+    from chain_control_b200 import _lib, parallel
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -222,111 +300,135 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-
-    closed, B, T = WORKLOADS[args.workload]
-    ctrl, model = specs()
-    theta_c = torch.tensor(init_theta(ctrl, 2, False), device=dev)
-    theta_m = torch.tensor(init_theta(model, 1, True), device=dev)
-    # synthetic trajectories of this rank's shard (weak scaling: B per GPU fixed)
-    host_in = torch.from_numpy(make_refs(B, T, 100 + rank)).pin_memory()
-    x = host_in.to(dev)
-    targets = torch.zeros(B, T + 1, 1, device=dev) if not closed else None
-    n_total = world * B * (T if closed else T + 1)  # global element count of the mean
-    P = ctrl.n_params() if closed else model.n_params()
     L = _lib.lib()
-    # Adam state of the trainable vector (optax.adam defaults) - the update is part of the step
-    theta = (theta_c if closed else theta_m).clone()
-    m1, m2 = torch.zeros_like(theta), torch.zeros_like(theta)
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    kt = {"fwd": 0.0, "bwd": 0.0}
-    step_no = [0]
-
-    def step(xdev, timed=False):
-        e = [ev() for _ in range(4)] if timed else None
-        if timed: e[0].record()
-        if closed:
-            yhat, _, tape = ops.closedloop_fwd(ctrl, model, theta, theta_m, xdev, want_tape=True)
-            if timed: e[1].record()
-            loss, ybar = ops.mse_value_and_cotangent(xdev, yhat, n_total)
-            if timed: e[2].record()
-            g = ops.closedloop_bwd(ctrl, model, theta, theta_m, xdev, tape, ybar)
-        else:
-            y, _, tape = ops.rollout_fwd(model, theta, xdev, want_tape=True)
-            if timed: e[1].record()
-            loss, ybar = ops.mse_value_and_cotangent(targets, y, n_total)
-            if timed: e[2].record()
-            g, _ = ops.rollout_bwd(model, theta, xdev, tape, ybar)
-        if timed: e[3].record()
-        gsum, lsum = parallel.allreduce_grad_and_loss(g, loss)  # N > 1: one NCCL allreduce of P+1 floats over NVLink
-        gl = torch.cat([gsum, lsum.reshape(1)])
-        step_no[0] += 1
-        t = step_no[0]
-        gg = gl[:P]
-        m1.mul_(0.9).add_(gg, alpha=0.1)
-        m2.mul_(0.999).addcmul_(gg, gg, value=0.001)
-        theta.sub_(1e-3 * (m1 / (1 - 0.9 ** t)) / ((m2 / (1 - 0.999 ** t)).sqrt() + 1e-8))
-        return gl, e
+    warm = max(args.warmup, 3)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput ---------------------------------------------------------------
+    def maxrank(ms):
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(w, steps, with_events=False):
+        """W warm-up steps, then exactly `steps` timed steps between barriers; device time, max over ranks"""
+        for _ in range(warm):
+            w.step(w.x)
+        barrier()
+        l0 = L.cc_launch_count()
+        e0, e1 = ev(), ev()
+        evs = []
+        e0.record()
+        for _ in range(steps):
+            e = [ev() for _ in range(4)] if with_events else None
+            gl = w.step(w.x, e)
+            evs.append(e)
+        e1.record()
+        barrier()
+        launches = L.cc_launch_count() - l0
+        ms = maxrank(e0.elapsed_time(e1))
+        kt = {"fwd": 0.0, "mse": 0.0, "bwd": 0.0}
+        if with_events:
+            for e in evs:
+                kt["fwd"] += e[0].elapsed_time(e[1]) / steps
+                kt["mse"] += e[1].elapsed_time(e[2]) / steps
+                kt["bwd"] += e[2].elapsed_time(e[3]) / steps
+        return ms / steps, kt, launches, float(gl[-1].item())
+
+    closed, B, T, ckpt, desc = WORKLOADS[args.workload]
+    W = Workload(args.workload, B, world, rank, dev, torch)
+
+    # ---- device-resident throughput (weak scaling: B per GPU fixed) -------------------------------------
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    for _ in range(max(args.warmup, 3)):
-        step(x)
+    for _ in range(warm):
+        W.step(W.x)
     barrier()
     sampler.mark_start()
-    l0 = L.cc_launch_count()
-    t_ev0, t_ev1 = ev(), ev()
-    t_ev0.record()
-    evs = []
-    for _ in range(args.steps):
-        gl, e = step(x, timed=True)
-        evs.append(e)
-    t_ev1.record()
-    barrier()
+    ms_step, kt, launches, loss_val = timed(W, args.steps, with_events=True)
     sampler.mark_end()
-    launches = L.cc_launch_count() - l0
-    ms = t_ev0.elapsed_time(t_ev1)
-    for e in evs:
-        kt["fwd"] += e[0].elapsed_time(e[1])
-        kt["bwd"] += e[2].elapsed_time(e[3])
     clocks = sampler.stop() if rank == 0 else None
-    tms = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms = float(tms.item())
-    loss_val = float(gl[-1].item())
+
+    # ---- the same step replayed from a CUDA graph (launch gaps removed); reported beside the eager number -------------
+    graph_ms = None
+    if os.environ.get("BENCH_GRAPH", "1") != "0" and world == 1:
+        try:
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    W.step(W.x)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            barrier()
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph):
+                W.step(W.x)
+            for _ in range(3):
+                gph.replay()
+            barrier()
+            g0, g1 = ev(), ev()
+            g0.record()
+            for _ in range(args.steps):
+                gph.replay()
+            g1.record()
+            barrier()
+            graph_ms = g0.elapsed_time(g1) / args.steps
+            del gph
+        except Exception as exc:  # capture is an optimisation of the launch path only
+            graph_ms = None
+            print(f"[bench] CUDA graph capture skipped: {type(exc).__name__}: {exc}", file=sys.stderr)
+            torch.cuda.synchronize()
+
+    # ---- strong scaling: configs[3]'s 65,536 trajectories IN TOTAL, sharded B/N per GPU -----------------------------
+    Bs = 65536 // world
+    Ws = W if Bs == B else Workload(args.workload, Bs, world, rank, dev, torch)
+    ms_s, _, _, _ = timed(Ws, args.steps)
+    strong = {"B_total": Bs * world, "B_per_gpu": Bs, "ms_per_step": ms_s, "value": Bs * world * T / (ms_s * 1e-3), "unit": "traj-steps/s",
+              "note": "total work fixed (configs[3]: 65,536 trajectories sharded B/N); one 128-trajectory tile per CTA: 65,536 / N trajectories fill "
+                      "512 / N of the 296 CTA slots, and one tile's 1001-step chain is the floor"}
+    if Ws is not W:
+        del Ws
 
     # ---- end to end through the public API with HOST buffers ---------------------------------------
     # every step copies its own inputs host -> device (pinned memory) and reads its result back; the copy of step i+1
     # runs on a side stream while the kernels of step i execute (chain_control_b200.parallel.HostFeed, double buffered)
+    P = W.P
     hres = torch.empty(P + 1).pin_memory()
     for _ in range(2):
-        step(host_in.to(dev, non_blocking=True))
+        W.step(W.host_in.to(dev, non_blocking=True))
     barrier()
     feed = parallel.HostFeed(dev)
     e0, e1 = ev(), ev()
     e0.record()
-    feed.push(host_in)                               # H2D of step 0's inputs: inside the timed region
+    feed.push(W.host_in)                               # H2D of step 0's inputs: inside the timed region
     for i in range(args.steps):
         xd = feed.pop()
         if i + 1 < args.steps:
-            feed.push(host_in)                       # H2D of the next step's inputs, overlapped with this step's kernels
-        gl2, _ = step(xd)
+            feed.push(W.host_in)                       # H2D of the next step's inputs, overlapped with this step's kernels
+        gl2 = W.step(xd)
         feed.release()
-        hres.copy_(gl2, non_blocking=True)           # D2H of the step's result (gradient + loss)
+        hres.copy_(gl2, non_blocking=True)             # D2H of the step's result (gradient + loss)
         torch.cuda.current_stream().synchronize()
     e1.record()
     barrier()
-    ms_e2e = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
-    ms_e2e = float(ms_e2e.item())
+    ms_e2e = maxrank(e0.elapsed_time(e1)) / args.steps
+    # host -> device bandwidth of this box for the same buffer (explains e2e once the kernels are faster than the copy)
+    c0, c1 = ev(), ev()
+    dst = torch.empty_like(W.x)
+    dst.copy_(W.host_in, non_blocking=True)
+    torch.cuda.synchronize()
+    c0.record()
+    dst.copy_(W.host_in, non_blocking=True)
+    c1.record()
+    torch.cuda.synchronize()
+    h2d_gbs = W.host_in.numel() * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    del dst
 
     # ---- FP32 peak (live FFMA probe) ---------------------------------------------------------------
     sink = torch.zeros(4, device=dev)
@@ -340,101 +442,105 @@ def main():
     torch.cuda.synchronize()
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     peak_tflops = sms * 4 * 512 * iters * 16 * 8 * 2 / (p0.elapsed_time(p1) * 1e-3) / 1e12
-    zin = torch.zeros(1024, device=dev)
-    for _ in range(2):
-        p0.record()
-        L.check(L.cc_fp32_tile_probe(sink.data_ptr(), zin.data_ptr(), iters, torch.cuda.current_stream().cuda_stream), "tile probe")
-        p1.record()
-        torch.cuda.synchronize()
-    regtile_tflops = sms * 4 * 512 * iters * 4 * 32 * 2 / (p0.elapsed_time(p1) * 1e-3) / 1e12
+
+    # ---- the other configurations of BASELINE.json, literally (N = 1 only) ---------------------------
+    others = None
+    if world == 1 and not args.no_others:
+        others = {}
+        cores = host_threads()
+        for name in ("cfg1", "cfg2", "cfg4", "cfg5"):
+            if name == args.workload:
+                continue
+            c2, B2, T2, ck2, d2 = WORKLOADS[name]
+            try:
+                Wo = Workload(name, B2, 1, 0, dev, torch)
+                ms_o, kt_o, _, _ = timed(Wo, max(3, min(args.steps, 5)), with_events=True)
+                entry = {"workload": d2, "B": B2, "T": T2, "ckpt_every": ck2, "ms_per_step": ms_o, "value": B2 * T2 / (ms_o * 1e-3),
+                         "fwd_ms": kt_o["fwd"], "bwd_ms": kt_o["bwd"]}
+                if not args.no_cpu_baseline:
+                    Bc = min(B2, 256)  # CPU: the literal batch where it is small, else a 256-trajectory sample scaled to the batch
+                    dtc = cpu_run(c2, Bc, T2, cores, 2 if B2 <= 64 else 1)
+                    entry["cpu_ms_per_step"] = 1e3 * dtc * (B2 / Bc)
+                    entry["cpu_sample"] = f"{Bc} trajectories x {T2} steps on {cores} threads" + ("" if Bc == B2 else f", scaled x{B2 // Bc}")
+                others[name] = entry
+                del Wo
+            except Exception as exc:
+                others[name] = {"error": f"{type(exc).__name__}: {exc}"}
+            torch.cuda.empty_cache()
 
     if rank == 0:
+        import ctypes as _C
+
         fwd_f, tot_f = alg_flops(closed)
         units = B * T  # trajectory-steps per launch
-        bwd_ms = kt["bwd"] / args.steps
-        fwd_ms = kt["fwd"] / args.steps
-        achieved = units * (tot_f - fwd_f) / (bwd_ms * 1e-3) / 1e12
+        fwd_ms, bwd_ms = kt["fwd"], kt["bwd"]
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             peaks = {}
         hbm = peaks.get("hbm_gbs", 6650.0)
-        # algorithmic HBM bytes per trajectory-step of the whole step: inputs/outputs/cotangent + tape write+read
-        tape_rows = (5 + 1) if closed else 50  # closed loop: x_c and y_prev (the frozen linear model needs no state)
-        bytes_ts = 4 * (1 + 1 + 1 + 1 + 1) + 2 * 4 * tape_rows  # refs, yhat (w), yhat+refs (mse r), ybar (w), ybar+refs (bwd r) + tape w+r
-        # ---- roofline of the dominant kernel -------------------------------------------------------
-        # closed loop (default): both kernels run on the tensor pipe (tcgen05, kind::tf32, 3xTF32 split for fp32 accuracy).
-        #   achieved = ALGORITHMIC FLOPs (2(n_st M_f + M_g) per trajectory-step, recomputation / splits / padding not
-        #   counted) / launch time; peak = dense TF32 rate = half the measured dense bf16 rate of MEASURED_PEAKS.json
-        #   (sustained figure: the kernel runs inside a long step).  `executed` counts what the pipe really does:
-        #   3 passes (lo.hi, hi.lo, hi.hi) over the padded 128 x 64 x 56 tiles, 4 stages per trajectory-step.
-        # open loop (cfg4): the reverse pass (weight gradients) is the FFMA kernel -> bound by the FP32 FMA pipe.
-        import ctypes as _C
-        cm, mm = ctrl.to_c(), model.to_c()
+        cm, mm = W.ctrl.to_c(), W.model.to_c()
         fam_f = L.cc_kernel_family_at(_C.byref(cm) if closed else None, _C.byref(mm), 0, B)
         fam_b = L.cc_kernel_family_at(_C.byref(cm) if closed else None, _C.byref(mm), 1, B)
         fam_name = {0: "ffma", 1: "tcgen05", 2: "latency", 3: "tcgen05", 4: "blocked-linear tcgen05"}
-        tensor = fam_b in (1, 3, 4)
+        kern_b = {4: "cc_lin_cl_bwd_kernel" if closed else "cc_linw_bwd_kernel", 1: "cc_tc_bwd_kernel", 3: "cc_tcw_bwd_kernel",
+                  2: "cc_wpt_bwd_kernel", 0: "cc_rollout_bwd_kernel"}[fam_b]
+        kern_f = {4: "cc_lin_cl_fwd_kernel" if closed else "cc_lin_ol_fwd_kernel", 1: "cc_tc_fwd_kernel", 2: "cc_wpt_fwd_kernel",
+                  0: "cc_rollout_fwd_kernel"}[fam_f]
         bf16_peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 2250.0 * 0.62))
         tf32_peak = bf16_peak / 2.0
-        exec_flops_ts = 3 * 2 * 64 * 56 * 4  # per trajectory-step of one rollout kernel (forward or reverse): 3 x 2 x NP x KP x stages
-        exec_note = "3xTF32 split (fp32-accurate products) over 128 x 64 x 56 padded tiles; 4.2x the algorithmic count"
-        bwd_kernel, bwd_traffic = "cc_tc_bwd_kernel", TRAFFIC_TC_BWD_BYTES_PER_TS
-        if fam_b == 3:  # ModelTrainer reverse pass: adjoint (4 stages) + recomputation (3 stages) + weight gradient (2 x M128 x N64 per trajectory and stage)
-            exec_flops_ts = 3 * 2 * 64 * 56 * (4 + 3) + 2 * 2 * 128 * 64 * 4
-            exec_note = "3xTF32: adjoint + recomputed stage inputs (128 x 64 x 56 tiles) + SS-mode weight-gradient product (hi/lo rows stacked: 2 x M128 x N64 per trajectory and stage)"
-            bwd_kernel, bwd_traffic = "cc_tcw_bwd_kernel", TRAFFIC_TCW_BWD_BYTES_PER_TS
-        if fam_b == 4:
-            exec_flops_ts = 3 * 2 * 64 * 64 / 13.0
-            exec_note = "blocked linear kernels: one 3xTF32 128 x 64 x 64 MMA batch per 13 steps"
-            bwd_kernel, bwd_traffic = ("cc_lin_cl_bwd_kernel" if closed else "cc_linw_bwd_kernel"), None
-        if tensor:
-            roofline = {"bound": "tensor", "kernel": bwd_kernel, "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
-                        "frac": achieved / tf32_peak,
-                        "traffic": bwd_traffic * units if bwd_traffic else None,
-                        "traffic_source": "ncu --set full capture of the same kernel (profiles/r01_tc_ncu_full.md, r01_tcw_ncu_full.md), dram read+write per trajectory-step x units of this launch",
-                        "peak_source": "MEASURED_PEAKS.json dense bf16 (sustained) / 2 = dense TF32; the kernel issues tcgen05.mma kind::tf32",
-                        "alg_flops_per_traj_step": tot_f - fwd_f, "launch_ms": bwd_ms,
-                        "executed": {"tflops": units * exec_flops_ts / (bwd_ms * 1e-3) / 1e12, "frac": units * exec_flops_ts / (bwd_ms * 1e-3) / 1e12 / tf32_peak,
-                                     "flops_per_traj_step": exec_flops_ts,
-                                     "note": exec_note},
-                        "fp32_fma": {"peak": peak_tflops, "frac": achieved / peak_tflops, "peak_register_tile": regtile_tflops,
-                                     "note": "BASELINE.json's yardstick: algorithmic TFLOP/s over the FP32 FMA peak (FFMA-chain probe measured live; nominal 74.4)"},
-                        "fwd_kernel": {"kernel": "cc_tc_fwd_kernel", "achieved": units * fwd_f / (fwd_ms * 1e-3) / 1e12, "launch_ms": fwd_ms, "alg_flops_per_traj_step": fwd_f,
-                                       "frac": units * fwd_f / (fwd_ms * 1e-3) / 1e12 / tf32_peak, "frac_of_fp32_fma_peak": units * fwd_f / (fwd_ms * 1e-3) / 1e12 / peak_tflops},
-                        "step": {"achieved": units * tot_f / ((fwd_ms + bwd_ms) * 1e-3) / 1e12, "alg_flops_per_traj_step": tot_f,
-                                 "frac_of_fp32_fma_peak": units * tot_f / ((fwd_ms + bwd_ms) * 1e-3) / 1e12 / peak_tflops},
-                        "hbm": {"achieved_gbs": units * bytes_ts / ((fwd_ms + bwd_ms) * 1e-3) / 1e9, "peak_gbs": hbm, "alg_bytes_per_traj_step": bytes_ts}}
-        else:
-            roofline = {"bound": "fp32", "kernel": {0: "cc_rollout_bwd_kernel", 2: ("cc_wpt_bwd_kernel" if closed else "cc_wpt_obwd_kernel")}.get(fam_b, "cc_rollout_bwd_kernel"), "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
-                        "frac": achieved / peak_tflops, "traffic": None,
-                        "peak_source": "FFMA-chain probe measured live in this run (MEASURED_PEAKS.json carries no FP32 figure; nominal 74.4)",
-                        "peak_register_tile": regtile_tflops,
-                        "alg_flops_per_traj_step": tot_f - fwd_f, "launch_ms": bwd_ms,
-                        "fwd_kernel": {"kernel": {0: "cc_rollout_fwd_kernel", 1: "cc_tc_fwd_kernel", 2: "cc_wpt_fwd_kernel"}[fam_f], "achieved": units * fwd_f / (fwd_ms * 1e-3) / 1e12, "launch_ms": fwd_ms, "alg_flops_per_traj_step": fwd_f},
-                        "step": {"achieved": units * tot_f / ((fwd_ms + bwd_ms) * 1e-3) / 1e12, "alg_flops_per_traj_step": tot_f},
-                        "hbm": {"achieved_gbs": units * bytes_ts / ((fwd_ms + bwd_ms) * 1e-3) / 1e9, "peak_gbs": hbm, "alg_bytes_per_traj_step": bytes_ts}}
+        fb, rb = alg_bytes(closed)
+        # ---- roofline of the dominant kernel (the reverse pass) ----------------------------------------------------
+        # The blocked linear kernels advance the linear model 13 steps per MMA batch, so the tensor pipe executes ~1.9 kFLOP
+        # per trajectory-step for 21 kFLOP algorithmic: neither FLOP count bounds them any more.  What is left per step is a
+        # scalar recurrence per trajectory (controller, input transform, Markov sums) fed from and writing to HBM: the next
+        # roofline above the kernel is HBM, so `achieved` = ALGORITHMIC bytes / launch time against the measured copy bandwidth.
+        traffic = ncu_traffic(kern_b)
+        ach_b = units * rb / (bwd_ms * 1e-3) / 1e9
+        roofline = {
+            "bound": "hbm", "kernel": kern_b, "achieved": ach_b, "peak": hbm, "unit": "GB/s", "frac": ach_b / hbm,
+            "traffic": traffic[0] if traffic else None,
+            "traffic_source": (f"profiles/{traffic[1]}: dram__bytes_read.sum + dram__bytes_write.sum of one launch ({units} trajectory-steps)" if traffic else None),
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy bandwidth measured on this pool's B200s)",
+            "alg_bytes_per_traj_step": rb, "launch_ms": bwd_ms,
+            "fwd_kernel": {"kernel": kern_f, "achieved": units * fb / (fwd_ms * 1e-3) / 1e9, "frac": units * fb / (fwd_ms * 1e-3) / 1e9 / hbm,
+                           "alg_bytes_per_traj_step": fb, "launch_ms": fwd_ms},
+            "tensor": {"note": "the same launches against the FLOP yardsticks: algorithmic FLOPs (SURVEY 8d: 2(n_st M_f + M_g) per trajectory-step; "
+                               "collapsing RK4 and blocking 13 steps means far fewer are executed) over dense TF32 = MEASURED_PEAKS bf16 sustained / 2 "
+                               "and over the FP32-FMA peak measured live (BASELINE.json's yardstick)",
+                       "alg_flops_per_traj_step": {"fwd": fwd_f, "bwd": tot_f - fwd_f},
+                       "bwd_alg_tflops": units * (tot_f - fwd_f) / (bwd_ms * 1e-3) / 1e12, "fwd_alg_tflops": units * fwd_f / (fwd_ms * 1e-3) / 1e12,
+                       "tf32_peak": tf32_peak, "bwd_frac_tf32": units * (tot_f - fwd_f) / (bwd_ms * 1e-3) / 1e12 / tf32_peak,
+                       "fp32_fma_peak": peak_tflops, "step_frac_fp32_fma": units * tot_f / ((fwd_ms + bwd_ms) * 1e-3) / 1e12 / peak_tflops,
+                       "executed_flops_per_traj_step": 3 * 2 * 64 * 64 / 13.0 if fam_b == 4 else None},
+            "step": {"alg_bytes_per_traj_step": fb + rb + 12.0, "achieved_gbs": units * (fb + rb + 12.0) / (ms_step * 1e-3) / 1e9,
+                     "note": "whole step incl. the MSE kernel (yhat + refs read, ybar written: 12 B)"},
+        }
         out = {
             "metric": ("closed-loop " if closed else "") + "neural-ODE traj-steps/s (fwd+BPTT)",
-            "value": world * units * args.steps / (ms * 1e-3), "unit": "traj-steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "value": world * units / (ms_step * 1e-3), "unit": "traj-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": {"cfg2x": "closed-loop ControllerTrainer step (configs[1] architecture: compact controller S_c=5 + frozen compact model S_m=50, RK4, dt=0.01, T_r=1001) at configs[3]'s batch, 65536 trajectories per GPU",
-                                    "cfg2": "configs[1]: closed-loop ControllerTrainer BPTT, 64 trajectories x 1001 steps",
-                                    "cfg4": "configs[3]: ModelTrainer step, 65536 trajectories per GPU x 1000 steps, S=50 depth 0",
-                                    "cfg1": "configs[0]: ModelTrainer step, 8 trajectories x 1000 steps, S=50 depth 0"}[args.workload],
-                       "B_per_gpu": B, "T": T, "closed_loop": closed, "integrator": "RK4", "ckpt_every": 1,
+            "config": {"workload": desc, "B_per_gpu": B, "T": T, "closed_loop": closed, "integrator": "RK4", "ckpt_every": ckpt,
                        "kernels": {"forward": fam_name[fam_f], "reverse": fam_name[fam_b],
-                                   "note": "tcgen05 = 3xTF32 tensor-core kernels (A in tensor memory); latency = one warp per trajectory (small batches); ffma = register-tiled FP32"},
-                       "step": "fwd rollout + mse cotangent + BPTT + grad reduce" + (" + NCCL allreduce(P+1)" if world > 1 else "") + " + adam",
-                       "l2": "inputs+tape (>= 0.26 GB + %.1f GB) exceed the 126 MB L2" % (2 * 4 * tape_rows * units / 2 / 1e9),
+                                   "note": "blocked-linear = 13 integrator steps of the linear model per 3xTF32 tcgen05.mma batch (csrc/cc_lin.h); "
+                                           "tcgen05 = one batch per RK4 stage; latency = one warp per trajectory; ffma = register-tiled FP32"},
+                       "step": "fwd rollout + mse cotangent + BPTT + grad reduce" + (" + NCCL allreduce(P+1)" if world > 1 else "") + " + fused clip + adam (cc_opt_step)",
+                       "step_ms": {"fwd": fwd_ms, "mse": kt["mse"], "bwd": bwd_ms},
+                       "cuda_graph_ms_per_step": graph_ms,
+                       "l2": "inputs + tape (0.26 GB + 1.6 GB) exceed the 126 MB L2",
                        "loss": loss_val},
-            "e2e": {"value": world * units * args.steps / (ms_e2e * 1e-3), "unit": "traj-steps/s",
-                    "h2d_bytes_per_step": int(host_in.numel() * 4), "d2h_bytes_per_step": int((P + 1) * 4)},
+            "e2e": {"value": world * units / (ms_e2e * 1e-3), "unit": "traj-steps/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(W.host_in.numel() * 4), "d2h_bytes_per_step": int((P + 1) * 4),
+                    "h2d_gbs_this_box": h2d_gbs,
+                    "note": "the input copy of step i+1 overlaps the kernels of step i; once the step is shorter than the copy, e2e is the PCIe rate"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,
+            "strong": strong,
         }
+        if others is not None:
+            out["config"]["other_workloads"] = others
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(closed, T)
         print(json.dumps(out))

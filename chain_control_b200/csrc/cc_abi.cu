@@ -163,6 +163,7 @@ struct Alloc {
 struct PlanOpts {
   bool bwd = false;
   bool exact_end = false;  // open loop: the state after the LAST step is requested (x_final)
+  int ckpt = 1;            // ckpt_every of the call: > 1 restricts the plan to the families that replay checkpoint segments
 };
 
 // tcgen05 weight-gradient kernel (cc_tcw_kernels.cuh): trainable linear compact model (f, g without final activation, readout of
@@ -344,7 +345,8 @@ int make_plan(const CcModule* const* mods, int n_nodes, long long B, int T, cons
   p->Bpad = (B + 31) / 32 * 32;
   p->n_wtiles = (B + 31) / 32;
   const CcModule* model = mods[n_nodes - 1];
-  p->tc = tc_eligible(mods, n_nodes, o.bwd) ? 1 : 0;
+  const bool seg = o.ckpt > 1;  // checkpointed recomputation: blocked linear or FFMA kernels (host-driven segment replay)
+  p->tc = (!seg && tc_eligible(mods, n_nodes, o.bwd)) ? 1 : 0;
   p->TN = tile_width_for(node_max_cpt(model));
   if (!p->TN) return fail(CC_ERR_UNSUPPORTED, "model layers wider than 64 are not supported yet (register tile 4 x 16 per thread)");
   p->ctrl_mode = CC_CTRL_NONE;
@@ -367,7 +369,7 @@ int make_plan(const CcModule* const* mods, int n_nodes, long long B, int T, cons
   if (n_nodes == 2) {
     p->R = mods[0]->input_dim - mods[1]->output_dim;
     // closed-loop carry on the tape: x_c, (x_m only if the frozen model's reverse pass needs it), y_prev
-    const int sm_rows = (mlp_linear(mods[1]->f) && mlp_linear(mods[1]->g)) ? 0 : p->nd[1].S;
+    const int sm_rows = (mlp_linear(mods[1]->f) && mlp_linear(mods[1]->g) && !seg) ? 0 : p->nd[1].S;  // (a checkpoint carries x_m too)
     p->nd[0].tape_row = 0;
     p->nd[1].tape_row = sm_rows ? p->nd[0].S : -1;
     p->tape_yrow = p->nd[0].S + sm_rows;
@@ -382,6 +384,9 @@ int make_plan(const CcModule* const* mods, int n_nodes, long long B, int T, cons
     p->lin_m = lin_block_len(model);
     const char* ms = getenv("CC_B200_LIN_M");  // (tests: other block lengths)
     if (ms && atoi(ms) >= 1 && atoi(ms) < p->lin_m) p->lin_m = atoi(ms);
+    if (seg && n_nodes == 2)  // checkpoints sit on block starts: the block length divides ckpt_every
+      for (int d = p->lin_m; d >= 1; --d)
+        if (o.ckpt % d == 0) { p->lin_m = d; break; }
     if (n_nodes == 1) {
       // open loop: the MMA chain carries x_k itself, so a ragged last block would end BEHIND step T; when the final state
       // is requested the block length divides T (T = 1, the step() call, runs with m = 1)
@@ -415,7 +420,7 @@ int make_plan(const CcModule* const* mods, int n_nodes, long long B, int T, cons
   const bool obwd = n_nodes == 1 && o.bwd;
   const bool tcw_ok = obwd && tcw_eligible(model, T);
   const long long wmax = wenv ? atoll(wenv) : (obwd ? (tcw_ok ? 2368 : 12288) : (n_nodes == 1 ? 4096 : 1184));
-  const bool small = B <= wmax && model->state_dim + model->input_dim + 1 <= 56;
+  const bool small = !seg && B <= wmax && model->state_dim + model->input_dim + 1 <= 56;
   if (p->tc && n_nodes == 1 && o.bwd && !small) {
     // large-batch ModelTrainer reverse pass: the weight gradient contracts over trajectories.  Linear compact models
     // (f, g without final activation, pre-step readout, RK4, room for [v ; 1] inside the state chunks): tcgen05 kernel
@@ -531,7 +536,12 @@ int cc_launch_lin_grad(const CcLinGradArgs& a, void* stream, char* err, int errl
 #endif
 namespace {
 // blocked linear family: the fp64 preparation kernel writes the block matrices into the workspace, then the rollout kernel runs
-int launch_lin(CcKParams& p, bool bwd, float* pack, void* stream) {
+int launch_lin(CcKParams& p, bool bwd, float* pack, void* stream, bool prep = true) {
+  if (!prep) {
+    g_launches.fetch_add(1);
+    p.lin_pack = pack;
+    return cc_launch_lin(p, bwd, stream, g_err, sizeof(g_err));
+  }
   g_launches.fetch_add(2);
   const CcNodeDev& M = p.nd[p.n_nodes - 1];
   int rc = cc_launch_lin_prep(M, p.theta[p.n_nodes - 1], pack, p.lin_tab, p.lin_m, p.n_nodes == 2 ? 0 : 1, p.lin_lc ? &p.nd[0] : nullptr, p.theta[0],
@@ -564,6 +574,15 @@ int launch_bwd(const CcKParams& p, void* stream) {
 }
 
 int n_ckpt_of(int T, int every) { return (T + every - 1) / every; }
+
+// tape layout of a call: [n_ckpt][tape_rows][Bpad] records, then the step times [2][T]; whole horizon in one launch
+void set_tape(CcKParams& p, void* tape, int ckpt_every, int T) {
+  p.tape = (float*)tape;
+  p.ckpt_every = tape ? ckpt_every : 1;
+  p.n_ckpt = n_ckpt_of(T, p.ckpt_every);
+  p.ttab = tape ? (float*)tape + (long long)p.n_ckpt * p.tape_rows * p.Bpad : nullptr;
+  p.seg_k0 = 0; p.seg_k1 = T; p.carry_in = nullptr; p.lam_io = nullptr; p.seg_first = 1;
+}
 
 }  // namespace
 
@@ -617,7 +636,7 @@ size_t cc_rollout_tape_bytes(const CcModule* m, int64_t B, int32_t T, int32_t ck
 size_t cc_closedloop_tape_bytes(const CcModule* c, const CcModule* m, int64_t B, int32_t Tr, int32_t ckpt_every) {
   if (!c || !m || B <= 0 || Tr < 0 || ckpt_every < 1) return 0;
   const long long Bpad = (B + 31) / 32 * 32;
-  const int sm_rows = (mlp_linear(m->f) && mlp_linear(m->g)) ? 0 : m->state_dim;
+  const int sm_rows = (mlp_linear(m->f) && mlp_linear(m->g) && ckpt_every == 1) ? 0 : m->state_dim;
   return ((size_t)n_ckpt_of(Tr, ckpt_every) * (c->state_dim + sm_rows + m->output_dim) * Bpad + 2 * (size_t)Tr) * sizeof(float);
 }
 
@@ -627,7 +646,7 @@ size_t cc_rollout_fwd_workspace_bytes(const CcModule* m, int64_t B, int32_t T) {
   PlanOpts o;
   const CcModule* mods[1] = {m};
   if (make_plan(mods, 1, B, T, o, &p)) return 0;
-  return p.tc == 4 ? lin_pack_bytes() : 0;
+  return p.tc == 4 ? lin_pack_bytes() : 0;  // (the open-loop family does not depend on ckpt_every)
 }
 
 size_t cc_closedloop_fwd_workspace_bytes(const CcModule* c, const CcModule* m, int64_t B, int32_t Tr) {
@@ -636,7 +655,7 @@ size_t cc_closedloop_fwd_workspace_bytes(const CcModule* c, const CcModule* m, i
   PlanOpts o;
   const CcModule* mods[2] = {c, m};
   if (make_plan(mods, 2, B, Tr, o, &p)) return 0;
-  return p.tc == 4 ? lin_pack_bytes() : 0;
+  return p.tc == 4 ? lin_pack_bytes() : 0;  // (with ckpt_every > 1 the plan is blocked linear exactly when it is here)
 }
 
 int32_t cc_rollout_fwd(const CcModule* m, const float* theta, const float* u, const float* x0, float* y,
@@ -651,14 +670,13 @@ int32_t cc_rollout_fwd(const CcModule* m, const float* theta, const float* u, co
   CcKParams p;
   PlanOpts o;
   o.exact_end = x_final != nullptr;
+  o.ckpt = tape ? ckpt_every : 1;
   const CcModule* mods[1] = {m};
   rc = make_plan(mods, 1, B, T, o, &p);
   if (rc) return rc;
   p.theta[0] = theta;
   p.in = u; p.x0 = x0; p.out = y; p.x_final = x_final;
-  p.tape = (float*)tape;
-  p.ckpt_every = tape ? ckpt_every : 1;
-  p.n_ckpt = n_ckpt_of(T, p.ckpt_every);
+  set_tape(p, tape, ckpt_every, T);
   if (p.tc == 4) {
     if (!ws || ws_bytes < lin_pack_bytes()) return fail(CC_ERR_WORKSPACE, "workspace too small: need %zu bytes (cc_rollout_fwd_workspace_bytes)", lin_pack_bytes());
     return launch_lin(p, false, (float*)ws, stream);
@@ -682,14 +700,13 @@ int32_t cc_closedloop_fwd(const CcModule* c, const CcModule* m, const float* the
   if (B == 0 || Tr == 0) return CC_OK;
   CcKParams p;
   PlanOpts o;
+  o.ckpt = tape ? ckpt_every : 1;
   const CcModule* mods[2] = {c, m};
   rc = make_plan(mods, 2, B, Tr, o, &p);
   if (rc) return rc;
   p.theta[0] = theta_c; p.theta[1] = theta_m;
   p.in = refs; p.noise = noise; p.out = yhat; p.u_out = u_out;
-  p.tape = (float*)tape;
-  p.ckpt_every = tape ? ckpt_every : 1;
-  p.n_ckpt = n_ckpt_of(Tr, p.ckpt_every);
+  set_tape(p, tape, ckpt_every, Tr);
   if (p.tc == 4) {
     if (!ws || ws_bytes < lin_pack_bytes()) return fail(CC_ERR_WORKSPACE, "workspace too small: need %zu bytes (cc_closedloop_fwd_workspace_bytes)", lin_pack_bytes());
     return launch_lin(p, false, (float*)ws, stream);
@@ -707,11 +724,30 @@ int32_t cc_mse_value_and_cotangent(const float* y, const float* yhat, float* yba
   g_launches.fetch_add(2);
 #ifdef CC_EMULATE
   (void)stream;
-  ccemu::launch(blocks, 256, 256 * 4, [&]() { cc_mse_kernel(y, yhat, ybar, loss_partial + 1, n, inv_n); });
+  ccemu::launch(blocks, CC_MSE_THREADS, CC_MSE_THREADS * 4, [&]() { cc_mse_kernel(y, yhat, ybar, loss_partial + 1, n, inv_n); });
   ccemu::launch(1, 32, 16, [&]() { cc_sum_partials_kernel(loss_partial + 1, blocks, loss_partial); });
 #else
-  cc_mse_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(y, yhat, ybar, loss_partial + 1, n, inv_n);
+  cc_mse_kernel<<<blocks, CC_MSE_THREADS, 0, (cudaStream_t)stream>>>(y, yhat, ybar, loss_partial + 1, n, inv_n);
   cc_sum_partials_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(loss_partial + 1, blocks, loss_partial);
+  CC_CUDA_OK(cudaGetLastError());
+#endif
+  return CC_OK;
+}
+
+int32_t cc_opt_step(float* theta, float* mu, float* nu, const float* grad, int32_t* count, float* out3, int64_t P, float lr,
+                    float b1, float b2, float eps, float clip_global_norm, float clip_value, float l1_prefactor,
+                    float l2_prefactor, float grad_scale, void* stream) {
+  if (!theta || !mu || !nu || !grad || !count || P < 1) return fail(CC_ERR_INVALID_ARG, "null pointer / empty parameter vector");
+  CcOptArgs a;
+  a.theta = theta; a.mu = mu; a.nu = nu; a.grad = grad; a.count = count; a.out = out3; a.P = P;
+  a.lr = lr; a.b1 = b1; a.b2 = b2; a.eps = eps; a.clip_norm = clip_global_norm; a.clip_value = clip_value;
+  a.l1 = l1_prefactor; a.l2 = l2_prefactor; a.grad_scale = grad_scale;
+  g_launches.fetch_add(1);
+#ifdef CC_EMULATE
+  (void)stream;
+  ccemu::launch(1, CC_OPT_THREADS, CC_OPT_THREADS * 4, [&]() { cc_opt_step_kernel(a); });
+#else
+  cc_opt_step_kernel<<<1, CC_OPT_THREADS, 0, (cudaStream_t)stream>>>(a);
   CC_CUDA_OK(cudaGetLastError());
 #endif
   return CC_OK;

@@ -3,23 +3,48 @@
 #pragma once
 #include "cc_kernels.cuh"
 
-// ybar = 2*(yhat - y)*inv_n ; block partials of sum((yhat-y)^2)*inv_n reduced in fixed order
-__global__ void cc_mse_kernel(const float* y, const float* yhat, float* ybar, float* block_part, long long n, float inv_n) {
+// ybar = 2*(yhat - y)*inv_n ; block partials of sum((yhat-y)^2)*inv_n reduced in fixed order.  HBM bound (12 B per element):
+// 16-byte accesses, two independent vectors per thread and iteration
+#define CC_MSE_THREADS 512
+__global__ void __launch_bounds__(CC_MSE_THREADS) cc_mse_kernel(const float* y, const float* yhat, float* ybar, float* block_part, long long n, float inv_n) {
 #ifndef CC_EMULATE
-  __shared__ float red[256];
+  __shared__ float red[CC_MSE_THREADS];
 #else
   float* red = ccemu::st().smem;
 #endif
   const int tid = threadIdx.x;
-  float s = 0.f;
-  for (long long i = (long long)blockIdx.x * blockDim.x + tid; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float d = yhat[i] - y[i];
-    s = fmaf(d, d, s);
-    ybar[i] = 2.f * inv_n * d;
+  float s = 0.f, s2 = 0.f;
+  const float c = 2.f * inv_n;
+  const bool vec = ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(yhat) | reinterpret_cast<uintptr_t>(ybar)) & 15) == 0;
+  const long long n4 = vec ? n / 4 : 0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const float4* y4 = reinterpret_cast<const float4*>(y);
+  const float4* h4 = reinterpret_cast<const float4*>(yhat);
+  float4* b4 = reinterpret_cast<float4*>(ybar);
+  long long i = (long long)blockIdx.x * blockDim.x + tid;
+  for (; i + stride < n4; i += 2 * stride) {
+    const float4 a0 = y4[i], h0 = h4[i], a1 = y4[i + stride], h1 = h4[i + stride];
+    const float4 d0 = make_float4(h0.x - a0.x, h0.y - a0.y, h0.z - a0.z, h0.w - a0.w);
+    const float4 d1 = make_float4(h1.x - a1.x, h1.y - a1.y, h1.z - a1.z, h1.w - a1.w);
+    s = fmaf(d0.x, d0.x, s); s = fmaf(d0.y, d0.y, s); s = fmaf(d0.z, d0.z, s); s = fmaf(d0.w, d0.w, s);
+    s2 = fmaf(d1.x, d1.x, s2); s2 = fmaf(d1.y, d1.y, s2); s2 = fmaf(d1.z, d1.z, s2); s2 = fmaf(d1.w, d1.w, s2);
+    b4[i] = make_float4(c * d0.x, c * d0.y, c * d0.z, c * d0.w);
+    b4[i + stride] = make_float4(c * d1.x, c * d1.y, c * d1.z, c * d1.w);
   }
-  red[tid] = s;
+  for (; i < n4; i += stride) {
+    const float4 a0 = y4[i], h0 = h4[i];
+    const float4 d0 = make_float4(h0.x - a0.x, h0.y - a0.y, h0.z - a0.z, h0.w - a0.w);
+    s = fmaf(d0.x, d0.x, s); s = fmaf(d0.y, d0.y, s); s = fmaf(d0.z, d0.z, s); s = fmaf(d0.w, d0.w, s);
+    b4[i] = make_float4(c * d0.x, c * d0.y, c * d0.z, c * d0.w);
+  }
+  for (long long j = 4 * n4 + (long long)blockIdx.x * blockDim.x + tid; j < n; j += stride) {
+    const float d = yhat[j] - y[j];
+    s = fmaf(d, d, s);
+    ybar[j] = c * d;
+  }
+  red[tid] = s + s2;
   __syncthreads();
-  for (int w = 128; w > 0; w >>= 1) {
+  for (int w = CC_MSE_THREADS / 2; w > 0; w >>= 1) {
     if (tid < w) red[tid] += red[tid + w];
     __syncthreads();
   }
@@ -123,4 +148,78 @@ __global__ void cc_fp32_tile_probe_kernel(float* sink, const float* in, int iter
   for (int i = 0; i < 4; ++i)
     for (int j = 0; j < 8; ++j) s += acc[i][j];
   if (s == 123.456f) sink[0] = s;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Fused optimiser step on the flat parameter vector (the train step's tail, cc/train/step_fn.py:101-114,166-169,307-308):
+//   g <- grad + l1 * sign(theta) + l2 * theta / ||theta||_2          regularisers act on the flat vector, utils.py:38-45
+//   g <- g * min(1, c / ||g||_2)                                       optax.clip_by_global_norm(c)      (c <= 0: off)
+//   g <- clamp(g, -v, v)                                               optax.clip(v)                      (v <= 0: off)
+//   mu, nu, theta <- optax.adam(lr, b1, b2, eps) update, bias corrected with the DEVICE-side step counter
+// One CTA (P <= a few 10^4): two fixed-order block reductions, no host round trip, CUDA-graph capturable.
+// out[0] = l1 norm, out[1] = l2 norm of theta (before the update), out[2] = ||g||_2 before clipping.
+// ------------------------------------------------------------------------------------------------
+struct CcOptArgs {
+  float* theta; float* mu; float* nu; const float* grad; int* count; float* out;
+  long long P;
+  float lr, b1, b2, eps, clip_norm, clip_value, l1, l2, grad_scale;
+};
+#define CC_OPT_THREADS 1024
+CC_DEV float cc_block_sum(float v, float* red, int tid, int nthr) {  // fixed order: deterministic
+  red[tid] = v;
+  __syncthreads();
+  for (int w = nthr / 2; w > 0; w >>= 1) {
+    if (tid < w) red[tid] += red[tid + w];
+    __syncthreads();
+  }
+  const float r = red[0];
+  __syncthreads();
+  return r;
+}
+__global__ void __launch_bounds__(CC_OPT_THREADS) cc_opt_step_kernel(const CC_GRID_CONSTANT CcOptArgs a) {
+#ifndef CC_EMULATE
+  __shared__ float red[CC_OPT_THREADS];
+#else
+  float* red = ccemu::st().smem;
+#endif
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  float s1 = 0.f, s2 = 0.f;
+  for (long long i = tid; i < a.P; i += nthr) {
+    const float t = a.theta[i];
+    s1 += fabsf(t);
+    s2 = fmaf(t, t, s2);
+  }
+  const float l1n = cc_block_sum(s1, red, tid, nthr);
+  const float l2n = sqrtf(cc_block_sum(s2, red, tid, nthr));
+  const float inv_l2 = l2n > 0.f ? 1.f / l2n : 0.f;
+  float sg = 0.f;
+  for (long long i = tid; i < a.P; i += nthr) {
+    const float t = a.theta[i];
+    float g = a.grad_scale * a.grad[i];
+    if (a.l1 != 0.f) g += a.l1 * (t > 0.f ? 1.f : (t < 0.f ? -1.f : 0.f));
+    if (a.l2 != 0.f) g += a.l2 * t * inv_l2;
+    sg = fmaf(g, g, sg);
+  }
+  const float gn = sqrtf(cc_block_sum(sg, red, tid, nthr));
+  const float scale = (a.clip_norm > 0.f && gn > a.clip_norm) ? a.clip_norm / gn : 1.f;
+  const int t_new = a.count[0] + 1;
+  const float c1 = 1.f - powf(a.b1, (float)t_new), c2 = 1.f - powf(a.b2, (float)t_new);
+  for (long long i = tid; i < a.P; i += nthr) {
+    const float t = a.theta[i];
+    float g = a.grad_scale * a.grad[i];
+    if (a.l1 != 0.f) g += a.l1 * (t > 0.f ? 1.f : (t < 0.f ? -1.f : 0.f));
+    if (a.l2 != 0.f) g += a.l2 * t * inv_l2;
+    g *= scale;
+    if (a.clip_value > 0.f) g = fminf(fmaxf(g, -a.clip_value), a.clip_value);
+    const float m = a.b1 * a.mu[i] + (1.f - a.b1) * g;
+    const float v = a.b2 * a.nu[i] + (1.f - a.b2) * g * g;
+    a.mu[i] = m; a.nu[i] = v;
+    a.theta[i] = t - a.lr * (m / c1) / (sqrtf(v / c2) + a.eps);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    a.count[0] = t_new;
+    if (a.out) { a.out[0] = l1n; a.out[1] = l2n; a.out[2] = gn; }
+  }
 }

@@ -681,40 +681,53 @@ __global__ void __launch_bounds__(256, 1) cc_rollout_fwd_kernel(const CC_GRID_CO
   for (int n = 0; n < p.n_nodes; ++n) cc_init_node_buffers(p.nd[n], w, false);
   __syncwarp();
 
-  if (!closed && p.x0) {
-    for (int s = 0; s < M.S; ++s) cc_ws(w)[M.w_X + s * CC_LD + w.lane] = act ? __ldg(p.x0 + b * M.S + s) : 0.f;
-    __syncwarp();
-  }
-  // y0 = out_scale * g([x0 ; t0])     neural_ode_model.py:160-175 (models have no feed-through)
-  if (M.has_t) {
-    cc_ws(w)[M.w_X + M.row_t * CC_LD + w.lane] = M.t0;
-    __syncwarp();
-  }
-  cc_readout<TN>(closed ? 1 : 0, M.w_X, false, w);
-  for (int o = 0; o < M.O; ++o) {
-    const float y0 = cc_ws(w)[M.w_OUT + o * CC_LD + w.lane];
-    if (closed) cc_ws(w)[p.w_yprev + o * CC_LD + w.lane] = y0;
-    else if (act) p.out[b * (long long)(p.T + 1) * M.O + o] = y0;
-  }
-  __syncwarp();
-
+  const int k_beg = p.seg_k0, k_end = p.seg_k1;  // (the whole horizon unless the host replays one checkpoint segment)
   float tc = closed ? C.t0 : 0.f, tm = M.t0;
+  if (p.carry_in) {
+    // resume at step k_beg from a tape record: module states, fed-back output, step times
+    for (int n = 0; n < p.n_nodes; ++n) {
+      const CcNodeDev& nd = p.nd[n];
+      for (int s = 0; s < nd.S; ++s) cc_ws(w)[nd.w_X + s * CC_LD + w.lane] = act ? p.carry_in[(long long)(nd.tape_row + s) * p.Bpad + b] : 0.f;
+    }
+    if (closed)
+      for (int o = 0; o < M.O; ++o) cc_ws(w)[p.w_yprev + o * CC_LD + w.lane] = act ? p.carry_in[(long long)(p.tape_yrow + o) * p.Bpad + b] : 0.f;
+    if (closed) { tc = p.ttab[k_beg]; tm = p.ttab[p.T + k_beg]; } else { tm = p.ttab[k_beg]; }
+    __syncwarp();
+  } else {
+    if (!closed && p.x0) {
+      for (int s = 0; s < M.S; ++s) cc_ws(w)[M.w_X + s * CC_LD + w.lane] = act ? __ldg(p.x0 + b * M.S + s) : 0.f;
+      __syncwarp();
+    }
+    // y0 = out_scale * g([x0 ; t0])     neural_ode_model.py:160-175 (models have no feed-through)
+    if (M.has_t) {
+      cc_ws(w)[M.w_X + M.row_t * CC_LD + w.lane] = M.t0;
+      __syncwarp();
+    }
+    cc_readout<TN>(closed ? 1 : 0, M.w_X, false, w);
+    for (int o = 0; o < M.O; ++o) {
+      const float y0 = cc_ws(w)[M.w_OUT + o * CC_LD + w.lane];
+      if (closed) cc_ws(w)[p.w_yprev + o * CC_LD + w.lane] = y0;
+      else if (act && p.out) p.out[b * (long long)(p.T + 1) * M.O + o] = y0;
+    }
+    __syncwarp();
+  }
+
   const int Win = closed ? p.R : M.I;
   float vin[CC_TINY_K];  // this step's external input (u or ref), prefetched one step ahead
 #pragma unroll
-  for (int i = 0; i < CC_TINY_K; ++i) vin[i] = (i < Win && act && p.T > 0) ? __ldg(p.in + b * (long long)p.T * Win + i) : 0.f;
+  for (int i = 0; i < CC_TINY_K; ++i) vin[i] = (i < Win && act && k_beg < k_end) ? __ldg(p.in + b * (long long)p.T * Win + (long long)k_beg * Win + i) : 0.f;
 
-  for (int k = 0; k < p.T; ++k) {
-    const bool wt = tape && (k % p.ckpt_every == 0);
-    const int ck = k / p.ckpt_every;
+  for (int k = k_beg; k < k_end; ++k) {
+    const bool wt = tape && ((k - k_beg) % p.ckpt_every == 0);
+    const int ck = (k - k_beg) / p.ckpt_every;
     if (tape && w.wt == 0 && w.lane == 0) {  // step times for the reverse pass (fp32 accumulation is not invertible)
-      float* ttab = p.tape + (long long)p.n_ckpt * p.tape_rows * p.Bpad;
+      float* ttab = p.ttab;
       if (closed) { ttab[k] = tc; ttab[p.T + k] = tm; } else { ttab[k] = tm; }
     }
     float vcur[CC_TINY_K];
 #pragma unroll
     for (int i = 0; i < CC_TINY_K; ++i) vcur[i] = vin[i];
-    if (k + 1 < p.T) {
+    if (k + 1 < k_end) {
 #pragma unroll
       for (int i = 0; i < CC_TINY_K; ++i)
         if (i < Win && act) vin[i] = __ldg(p.in + b * (long long)p.T * Win + (long long)(k + 1) * Win + i);
@@ -760,18 +773,18 @@ __global__ void __launch_bounds__(256, 1) cc_rollout_fwd_kernel(const CC_GRID_CO
         float y = cc_ws(w)[M.w_OUT + o * CC_LD + w.lane];
         if (p.noise && act) y += __ldg(p.noise + b * (long long)p.T * M.O + (long long)k * M.O + o);
         cc_ws(w)[p.w_yprev + o * CC_LD + w.lane] = y;
-        if (act) p.out[b * (long long)p.T * M.O + (long long)k * M.O + o] = y;
+        if (act && p.out) p.out[b * (long long)p.T * M.O + (long long)k * M.O + o] = y;
       }
       if (C.has_t) tc = tc + C.dt;
     } else {
       cc_set_inputs(M, w, vcur, tm, 0);
       __syncwarp();
       cc_node_step<TN>(closed ? 1 : 0, w, tm, false, true, wt, ck);
-      if (act)
+      if (act && p.out)
         for (int o = 0; o < M.O; ++o) p.out[b * (long long)(p.T + 1) * M.O + (long long)(k + 1) * M.O + o] = cc_ws(w)[M.w_OUT + o * CC_LD + w.lane];
     }
     if (M.has_t) tm = tm + M.dt;
   }
-  if (!closed && p.x_final && act)
+  if (!closed && p.x_final && act && k_end == p.T)
     for (int s = 0; s < M.S; ++s) p.x_final[b * M.S + s] = cc_ws(w)[M.w_X + s * CC_LD + w.lane];
 }

@@ -414,10 +414,42 @@ __global__ void __launch_bounds__(256, 1) cc_rollout_bwd_kernel(const CC_GRID_CO
   if (w.nact == 0) return;
   const bool act = w.lane < w.nact;
   const long long b = w.b0 + w.lane;
-  const float* ttab = p.tape + (long long)p.n_ckpt * p.tape_rows * p.Bpad;  // [2][T] step times
+  const float* ttab = p.ttab;  // [2][T] step times
   for (int n = 0; n < p.n_nodes; ++n) cc_init_node_buffers(p.nd[n], w, true);
   if (closed)
     for (int o = 0; o < M.O; ++o) cc_ws(w)[p.w_yfb + o * CC_LD + w.lane] = 0.f;
+  __syncwarp();
+  // checkpoint segments (ckpt_every > 1): this launch walks the steps [k_beg, k_end) backwards on a segment-local tape;
+  // the adjoints of the later segment and the gradient sums so far come in through lam_io / the records
+  const int k_beg = p.seg_k0, k_end = p.seg_k1;
+  float* rec = p.gpart + w.wt * p.g_rec;
+  if (p.lam_io && k_end < p.T) {
+    int row = 0;
+    for (int n = 0; n < p.n_nodes; ++n) {
+      const CcNodeDev& nd = p.nd[n];
+      for (int s = 0; s < nd.S; ++s) cc_ws(w)[nd.w_LAM + s * CC_LD + w.lane] = act ? p.lam_io[(long long)(row + s) * p.Bpad + b] : 0.f;
+      row += nd.S;
+    }
+    if (closed)
+      for (int o = 0; o < M.O; ++o) cc_ws(w)[p.w_yfb + o * CC_LD + w.lane] = act ? p.lam_io[(long long)(row + o) * p.Bpad + b] : 0.f;
+  }
+  if (!p.seg_first) {
+    for (int n = 0; n < p.n_nodes; ++n) {
+      const CcNodeDev& nd = p.nd[n];
+      if (!nd.trainable) continue;
+      if (nd.tiny) {
+        for (int e = w.lane; e < nd.g_total; e += 32) cc_ws(w)[nd.w_GP + e] = rec[nd.g_base + e];
+      } else {
+        for (int which = 0; which < 2; ++which) {
+          const CcMlpDev& mlp = which ? nd.g : nd.f;
+          for (int l = 0; l < mlp.L; ++l) {
+            const CcLayerDev& L = mlp.layer[l];
+            for (int i = w.lane; i < L.N * L.K; i += 32) cc_ws(w)[L.w_gw + i] = rec[nd.g_base + L.g_off + i];
+          }
+        }
+      }
+    }
+  }
   __syncwarp();
 
   const int Win = closed ? p.R : M.I;
@@ -433,14 +465,14 @@ __global__ void __launch_bounds__(256, 1) cc_rollout_bwd_kernel(const CC_GRID_CO
 #pragma unroll
     for (int o = 0; o < CC_TINY_O; ++o) {
       n_yb[o] = (o < M.O && act) ? __ldg(p.ybar + b * yrow + yoff + o) : 0.f;
-      n_yp[o] = (closed && o < M.O && act) ? p.tape[((long long)k * p.tape_rows + p.tape_yrow + o) * p.Bpad + b] : 0.f;
+      n_yp[o] = (closed && o < M.O && act) ? p.tape[((long long)(k - k_beg) * p.tape_rows + p.tape_yrow + o) * p.Bpad + b] : 0.f;
     }
 #pragma unroll
     for (int s = 0; s < CC_TINY_S; ++s)
-      n_xc[s] = (CM == CC_CTRL_TINY && s < C.S && act) ? p.tape[((long long)k * p.tape_rows + C.tape_row + s) * p.Bpad + b] : 0.f;
+      n_xc[s] = (CM == CC_CTRL_TINY && s < C.S && act) ? p.tape[((long long)(k - k_beg) * p.tape_rows + C.tape_row + s) * p.Bpad + b] : 0.f;
   };
-  if (p.T > 0) fetch(p.T - 1);
-  for (int k = p.T - 1; k >= 0; --k) {  // ckpt_every == 1: the tape holds the carry of every step
+  if (k_end > k_beg) fetch(k_end - 1);
+  for (int k = k_end - 1; k >= k_beg; --k) {  // the (segment-local) tape holds the carry of every step
     float vin[CC_TINY_K], yb[CC_TINY_O], ypv[CC_TINY_O], xcv[CC_TINY_S];
 #pragma unroll
     for (int i = 0; i < CC_TINY_K; ++i) vin[i] = n_vin[i];
@@ -448,7 +480,7 @@ __global__ void __launch_bounds__(256, 1) cc_rollout_bwd_kernel(const CC_GRID_CO
     for (int o = 0; o < CC_TINY_O; ++o) { yb[o] = n_yb[o]; ypv[o] = n_yp[o]; }
 #pragma unroll
     for (int s = 0; s < CC_TINY_S; ++s) xcv[s] = n_xc[s];
-    if (k > 0) fetch(k - 1);
+    if (k > k_beg) fetch(k - 1);
     if (closed) {
       const float tc = C.has_t ? ttab[k] : 0.f;
       const float tm = M.has_t ? ttab[p.T + k] : 0.f;
@@ -471,7 +503,7 @@ __global__ void __launch_bounds__(256, 1) cc_rollout_bwd_kernel(const CC_GRID_CO
           if (s < C.S) cc_ws(w)[C.w_X + s * CC_LD + w.lane] = xcv[s];
         cc_tiny_step<true>(C, w, tc, vcc, a);  // recompute with the stage intermediates kept; a_k feeds u_transform'
       } else {
-        cc_tape_load<8>(p, C, k, w);
+        cc_tape_load<8>(p, C, k - k_beg, w);
         cc_set_inputs(C, w, vc, tc, 1);
         __syncwarp();
         cc_node_step<8>(0, w, tc, true, true, false, 0);
@@ -482,7 +514,7 @@ __global__ void __launch_bounds__(256, 1) cc_rollout_bwd_kernel(const CC_GRID_CO
       for (int i = 0; i < CC_TINY_O; ++i)
         if (i < M.I) cc_ws(w)[p.w_araw + i * CC_LD + w.lane] = a[i];
       if (M.recompute) {
-        cc_tape_load<TN>(p, M, k, w);
+        cc_tape_load<TN>(p, M, k - k_beg, w);
         float am[CC_TINY_K];
 #pragma unroll
         for (int i = 0; i < CC_TINY_K; ++i) am[i] = (i < CC_TINY_O) ? a[i < CC_TINY_O ? i : 0] : 0.f;
@@ -516,7 +548,7 @@ __global__ void __launch_bounds__(256, 1) cc_rollout_bwd_kernel(const CC_GRID_CO
       __syncwarp();
     } else {
       const float tm = M.has_t ? ttab[k] : 0.f;
-      cc_tape_load<TN>(p, M, k, w);
+      cc_tape_load<TN>(p, M, k - k_beg, w);
       cc_set_inputs(M, w, vin, tm, 1);
 #pragma unroll
       for (int i = 0; i < CC_TINY_K; ++i)
@@ -532,7 +564,19 @@ __global__ void __launch_bounds__(256, 1) cc_rollout_bwd_kernel(const CC_GRID_CO
     }
   }
 
-  if (!closed) {
+  if (p.lam_io && k_beg > 0) {  // adjoint carry for the earlier segment
+    __syncwarp();
+    int row = 0;
+    for (int n = 0; n < p.n_nodes; ++n) {
+      const CcNodeDev& nd = p.nd[n];
+      if (act)
+        for (int s = 0; s < nd.S; ++s) p.lam_io[(long long)(row + s) * p.Bpad + b] = cc_ws(w)[nd.w_LAM + s * CC_LD + w.lane];
+      row += nd.S;
+    }
+    if (closed && act)
+      for (int o = 0; o < M.O; ++o) p.lam_io[(long long)(row + o) * p.Bpad + b] = cc_ws(w)[p.w_yfb + o * CC_LD + w.lane];
+  }
+  if (!closed && k_beg == 0) {
     // y0 = out_scale * g([x0 ; 0]) only feeds g's parameters (x0 is not trained, neural_ode_model.py:151-158)
     for (int s = 0; s < M.S; ++s) cc_ws(w)[M.w_X + s * CC_LD + w.lane] = (p.x0 && act) ? __ldg(p.x0 + b * M.S + s) : 0.f;
     float v0[CC_TINY_K];
@@ -548,7 +592,6 @@ __global__ void __launch_bounds__(256, 1) cc_rollout_bwd_kernel(const CC_GRID_CO
 
   // gradient record of this warp tile -> workspace (reduced over tiles in fixed order afterwards)
   __syncwarp();
-  float* rec = p.gpart + w.wt * p.g_rec;
   for (int n = 0; n < p.n_nodes; ++n) {
     const CcNodeDev& nd = p.nd[n];
     if (!nd.trainable) continue;

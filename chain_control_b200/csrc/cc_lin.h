@@ -44,7 +44,7 @@
 #define CC_LIN_SMALL_FLOATS 2884     // end of the model tables
 // linear tiny controller (f_c, g_c single Linear layers without activations, time-invariant): its integrator step collapsed
 // the same way, x_c+ = Phi_c x_c + (Gam_c B_c) v + Gam_c c_c
-#define CC_LIN_S_CPHI 2884          //   Phi_c[8][8]
+#define CC_LIN_S_CPHI 2884          //   (Phi_c - I)[8][8]   (increment form: x_c+ = x_c + (Phi_c - I) x_c + ...)
 #define CC_LIN_S_CGB 2948           //   (Gam_c B_c)[8][4]
 #define CC_LIN_S_CGAM 2980          //   (Gam_c c_c)[8]
 #define CC_LIN_S_CTAB 2992          //   fp64: A_c[8][8], Gam_c[8][8]  (gradient post-processing, cc_lin_cgrad_kernel)

@@ -29,7 +29,7 @@
 #define CC_LIN_SM_BHI 0
 #define CC_LIN_SM_BLO 4096
 #define CC_LIN_SM_SMALL 8192                  // H[32], const[16]
-#define CC_LIN_SM_CLIN (8192 + 48)            // linear controller rows [8][16]: [Phi_c (8) | Gam_c B_c (4) | Gam_c c_c | pad]
+#define CC_LIN_SM_CLIN (8192 + 48)            // linear controller rows [8][16]: [Phi_c - I (8) | Gam_c B_c (4) | Gam_c c_c | pad]
 #define CC_LIN_SM_WFC (CC_LIN_SM_CLIN + 128)  // controller f weights [8][16]
 #define CC_LIN_SM_WGC (CC_LIN_SM_WFC + CC_TINY_S * CC_CK)   // controller g weights [4][16]
 #define CC_LIN_SM_BAR (CC_LIN_SM_WGC + CC_TINY_O * CC_CK)   // 2 mbarriers + tmem slot (8 floats)
@@ -71,6 +71,13 @@ CC_DEV void cc_lin_tile_load(float* tile, const float* base, long long b0, int n
 CC_DEV void cc_lin_tile_store(const float* tile, float* base, long long b0, int nact, long long stride, long long len, int c, int lane) {
   const long long k = (long long)c * 32 + lane;
   if (k < len)
+    for (int i = 0; i < nact; ++i) base[(b0 + i) * stride + k] = tile[i * 33 + lane];
+}
+
+// write the steps [k_lo, k_hi) (inside one 32-step chunk) of a [B, T] array from `tile`
+CC_DEV void cc_lin_tile_store_range(const float* tile, float* base, long long b0, int nact, long long stride, int k_lo, int k_hi, int lane) {
+  const int k = (k_lo & ~31) + lane;
+  if (k >= k_lo && k < k_hi)
     for (int i = 0; i < nact; ++i) base[(b0 + i) * stride + k] = tile[i * 33 + lane];
 }
 
@@ -180,7 +187,8 @@ CC_DEV void cc_lin_epilogue(const CcLinTm& tm) {
 
 
 // ---- linear tiny controller (f_c, g_c without activations, time-invariant, no input transform): the integrator step is the
-// affine map x_c+ = Phi_c x_c + (Gam_c B_c) v + Gam_c c_c prepared by cc_lin_prep_kernel; rows [Phi_c | Gam_c B_c | gam] ----
+// affine map x_c+ = x_c + (Phi_c - I) x_c + (Gam_c B_c) v + Gam_c c_c prepared by cc_lin_prep_kernel (increment form: the
+// entries of Phi_c - I are O(h), so fp32 keeps them to 1e-9 absolute); rows [Phi_c - I | Gam_c B_c | gam] ----
 // LCR: the rows live in registers (CFG shapes: only the live entries survive), else they are read from shared memory
 template <int CFG>
 struct CcLctrlRows {
@@ -210,15 +218,16 @@ CC_DEV void cc_lctrl_next(const CcCtrlDims& C, const float* CL, const CcLctrlRow
 #pragma unroll
       for (int i = 0; i < CC_TINY_O; ++i)
         if (i < C.I) s1 = fmaf(CC_LCW(n, 8 + i), v[i], s1);
-      xn[n] = s0 + s1;
+      xn[n] = x[n] + (s0 + s1);
     }
   }
 }
-// reverse of the affine step: lam <- Phi_c^T lamp ; vb = (Gam_c B_c)^T lamp
+// reverse of the affine step: lam <- lamp + (Phi_c - I)^T lamp ; vb = (Gam_c B_c)^T lamp
 template <int CFG>
 CC_DEV void cc_lctrl_next_bwd(const CcCtrlDims& C, const float* CL, const CcLctrlRows<CFG>& R, const float (&lamp)[CC_TINY_S], float (&lam)[CC_TINY_S], float (&vb)[CC_TINY_O]) {
+  float inc[CC_TINY_S];
 #pragma unroll
-  for (int k = 0; k < CC_TINY_S; ++k) lam[k] = 0.f;
+  for (int k = 0; k < CC_TINY_S; ++k) inc[k] = 0.f;
 #pragma unroll
   for (int i = 0; i < CC_TINY_O; ++i) vb[i] = 0.f;
 #pragma unroll
@@ -226,12 +235,14 @@ CC_DEV void cc_lctrl_next_bwd(const CcCtrlDims& C, const float* CL, const CcLctr
     if (n < C.S) {
 #pragma unroll
       for (int k = 0; k < CC_TINY_S; ++k)
-        if (k < C.S) lam[k] = fmaf(CC_LCW(n, k), lamp[n], lam[k]);
+        if (k < C.S) inc[k] = fmaf(CC_LCW(n, k), lamp[n], inc[k]);
 #pragma unroll
       for (int i = 0; i < CC_TINY_O; ++i)
         if (i < C.I) vb[i] = fmaf(CC_LCW(n, 8 + i), lamp[n], vb[i]);
     }
   }
+#pragma unroll
+  for (int k = 0; k < CC_TINY_S; ++k) lam[k] = k < C.S ? lamp[k] + inc[k] : 0.f;
 }
 // ------------------------------------------------------------------------------------------------
 // K3: closed-loop forward.  SISO model (I = O = 1), tiny controller; STG: coalesced staging of refs / yhat (R = 1)
@@ -277,25 +288,65 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_cl_fwd_kernel(const 
   for (int i = 0; i < CC_TINY_S; ++i) xc[i] = 0.f;
   float yprev = p.lin_pack[CC_LIN_SMALL + CC_LIN_S_D0];  // y0 = g(x0 = 0) = d     neural_ode_model.py:160-175
   float tc = C.t0;
+  const int k_beg = p.seg_k0, k_end = p.seg_k1;  // (the whole horizon unless the host replays one checkpoint segment)
+  const long long Bp = p.Bpad;
+  if (p.carry_in) {  // resume at step k_beg from a tape record (x_c, x_m, y_prev) and the recorded step time
+    const float* cr = p.carry_in + (act ? b : 0);
+#pragma unroll
+    for (int i = 0; i < CC_TINY_S; ++i) xc[i] = i < CD.S ? cr[(long long)(C.tape_row + i) * Bp] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8 * NCH; ++i) pst[i] = i < S ? cr[(long long)(M.tape_row + i) * Bp] : 0.f;
+    yprev = cr[(long long)p.tape_yrow * Bp];
+    if (CD.has_t) tc = p.ttab[k_beg];
+#pragma unroll
+    for (int c2 = 0; c2 < NCH; ++c2) {
+      float z[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) z[i] = pst[8 * c2 + i];
+      cc_lin_store_split<8>(tm, 8 * c2, z);
+    }
+  }
   CcLctrlRows<LC ? CFG : 0> LR;
   if (LC) cc_lctrl_load<LC ? CFG : 0>(sh.clin, LR);
-  if (STG) cc_lin_tile_load(cc_smem + tin_off, p.in, b0, nact, T, T, 0, lane);
+  const int ch_beg = k_beg >> 5;
+  if (STG) cc_lin_tile_load(cc_smem + tin_off + (ch_beg & 1) * CC_LIN_TILE, p.in, b0, nact, T, T, ch_beg, lane);
   // walking pointers: the tape record of step k ([rows][Bpad] floats), this trajectory's rows of the [B, T] arrays
-  const long long Bp = p.Bpad;
   const bool tape = p.tape != nullptr && act;
+  const int cke = p.ckpt_every;
   float* tpk = p.tape ? p.tape + b : nullptr;
   const long long tstep = (long long)p.tape_rows * Bp;
   const long long toff_y = (long long)p.tape_yrow * Bp, toff_c = (long long)C.tape_row * Bp;
   const float* inrow = p.in + (act ? b : 0) * (long long)T * R;
-  float* outrow = p.out + (act ? b : 0) * (long long)T;
+  float* outrow = p.out ? p.out + (act ? b : 0) * (long long)T : nullptr;
   const float* nzrow = p.noise ? p.noise + (act ? b : 0) * (long long)T : nullptr;
   float* uorow = (p.u_out && act) ? p.u_out + b * (long long)T : nullptr;
-  float* ttab = (p.tape && CD.has_t && blockIdx.x == 0 && tid == 0) ? p.tape + (long long)p.n_ckpt * p.tape_rows * Bp : nullptr;
+  float* ttab = (p.tape && CD.has_t && blockIdx.x == 0 && tid == 0) ? p.ttab : nullptr;
   float a[CC_LIN_MAXM];
-  for (int k0 = 0; k0 < T; k0 += m) {
+  for (int k0 = k_beg; k0 < k_end; k0 += m) {
     // ---- one MMA batch for the block: A was completed by the previous block's sequential phase ----
     cc_lin_round(tm);
     cc_lin_await(tm);
+    if (p.tape && cke > 1 && M.tape_row >= 0 && (k0 - k_beg) % cke == 0) {
+      // checkpoint (ckpt_every > 1) at a block start: the model state x_k0 = p + C u~_prev + c_m e, materialised from the
+      // operand of the round that has just completed (u~_prev = hi + lo, i.e. u~ to 2^-24) before the state chunks are rewritten
+      float uh[16], ul[16];
+      cc_lin_ld<16>(tm, CC_LIN_COL_AHI + 48, uh);
+      cc_lin_ld<16>(tm, CC_LIN_COL_ALO + 48, ul);
+      cc_lin_wait_ld();
+      const float e1 = uh[15];
+      const float* sm = p.lin_pack + CC_LIN_SMALL;
+      float* rec = p.tape + (long long)((k0 - k_beg) / cke) * tstep + (long long)M.tape_row * Bp + (act ? b : 0);
+#pragma unroll
+      for (int i = 0; i < 8 * NCH; ++i) {
+        if (i < S) {
+          float x = fmaf(sm[CC_LIN_S_CM + i], e1, pst[i]);
+#pragma unroll
+          for (int t = 0; t < CC_LIN_MAXM; ++t)
+            if (t < m) x = fmaf(sm[CC_LIN_S_C + i * 16 + t], uh[14 - t] + ul[14 - t], x);
+          if (act) rec[(long long)i * Bp] = x;
+        }
+      }
+    }
     {
       float d[16];
       cc_lin_ld<16>(tm, CC_LIN_COL_D + 48, d);  // slots t = 0..12 sit at columns 62..50
@@ -304,16 +355,16 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_cl_fwd_kernel(const 
       for (int t = 0; t < CC_LIN_MAXM; ++t) a[t] = d[14 - t] + sh.small[32 + t];
     }
     cc_lin_advance_state<NCH>(tm, pst, S);
-    if (k0 == 0) {  // e = 1 from the second round on (NCH = 8: column 63 is rewritten with the state chunks, so it rides in pst)
+    if (k0 == k_beg) {  // e = 1 from the second round on (NCH = 8: column 63 is rewritten with the state chunks, so it rides in pst)
       cc_lin_store_split1(tm, CC_LIN_ONE, 1.f);
       if constexpr (NCH == 8) pst[CC_LIN_ONE] = 1.f;
     }
-    const int nst = T - k0 < m ? T - k0 : m;
+    const int nst = k_end - k0 < m ? k_end - k0 : m;
 #pragma unroll 1
     for (int j = 0; j < nst; ++j) {
       const int k = k0 + j;
       const int kc = k & 31;
-      if (STG && kc == 0) {  // chunk boundary: the chunk's tile has landed; prefetch the next one
+      if (STG && (kc == 0 || k == k_beg)) {  // chunk boundary (or first step): the chunk's tile has landed; prefetch the next one
         cc_lin_cp_wait_all();
         __syncwarp();
         cc_lin_tile_load(cc_smem + tin_off + (((k >> 5) + 1) & 1) * CC_LIN_TILE, p.in, b0, nact, T, T, (k >> 5) + 1, lane);
@@ -330,13 +381,15 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_cl_fwd_kernel(const 
         }
         if (i == R) vc[i] = yprev;
       }
-      if (tape) {
-        tpk[toff_y] = yprev;
+      if (p.tape && (cke == 1 || (k - k_beg) % cke == 0)) {
+        if (tape) {
+          tpk[toff_y] = yprev;
 #pragma unroll
-        for (int s = 0; s < CC_TINY_S; ++s)
-          if (s < CD.S) tpk[toff_c + s * Bp] = xc[s];
+          for (int s = 0; s < CC_TINY_S; ++s)
+            if (s < CD.S) tpk[toff_c + s * Bp] = xc[s];
+        }
+        tpk += tstep;
       }
-      if (p.tape) tpk += tstep;
       float araw[CC_TINY_O];
 #pragma unroll
       for (int i = 0; i < CC_TINY_O; ++i) araw[i] = 0.f;
@@ -366,12 +419,13 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_cl_fwd_kernel(const 
       yprev = y;
       if (STG) {
         cc_smem[tout_off + trow + kc] = y;
-        if (kc == 31 || k == T - 1) {
+        if (kc == 31 || k == k_end - 1) {
           __syncwarp();
-          cc_lin_tile_store(cc_smem + tout_off, p.out, b0, nact, T, T, k >> 5, lane);
+          // (a segment replay has no output array; a chunk straddling a segment start rewrites only its own steps)
+          if (p.out) cc_lin_tile_store_range(cc_smem + tout_off, p.out, b0, nact, T, (k >> 5) * 32 > k_beg ? (k >> 5) * 32 : k_beg, k + 1, lane);
           __syncwarp();
         }
-      } else if (act) {
+      } else if (act && outrow) {
         outrow[k] = y;
       }
     }
@@ -425,7 +479,8 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_cl_bwd_kernel(const 
   for (int c2 = 0; c2 < 8; ++c2) gacc[c2] = 0.f;
   CcLctrlRows<LC ? CFG : 0> LR;
   if (LC) cc_lctrl_load<LC ? CFG : 0>(sh.clin, LR);
-  const float* ttab = p.tape + (long long)p.n_ckpt * p.tape_rows * p.Bpad;
+  const float* ttab = p.ttab;
+  const int k_beg = p.seg_k0, k_end = p.seg_k1;  // (the whole horizon unless the host walks checkpoint segments)
   float H[CC_LIN_MAXM + 1];
 #pragma unroll
   for (int i = 0; i <= CC_LIN_MAXM; ++i) H[i] = sh.small[i];
@@ -440,9 +495,24 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_cl_bwd_kernel(const 
 #pragma unroll
   for (int i = 0; i < CC_TINY_S; ++i) lamc[i] = 0.f;
   float yfb = 0.f;
+  if (p.lam_io && k_end < T) {  // adjoints of the later segment: [lam_c (S_c) ; mu (S) ; y feedback (1)][Bpad]
+    const float* li = p.lam_io + (act ? b : 0);
+#pragma unroll
+    for (int i = 0; i < CC_TINY_S; ++i) lamc[i] = i < CD.S ? li[(long long)i * p.Bpad] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8 * NCH; ++i) rst[i] = i < S ? li[(long long)(C.S + i) * p.Bpad] : 0.f;
+    yfb = li[(long long)(C.S + S) * p.Bpad];
+#pragma unroll
+    for (int c2 = 0; c2 < NCH; ++c2) {
+      float z[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) z[i] = rst[8 * c2 + i];
+      cc_lin_store_split<8>(tm, 8 * c2, z);
+    }
+  }
   float c[CC_LIN_MAXM];
-  const int nblk = (T + m - 1) / m;
-  const int nchunk = (T + 31) / 32;
+  const int nblk = (k_end - k_beg + m - 1) / m;
+  const int nchunk = (k_end + 31) / 32;
   if (STG && nchunk > 0) {
     cc_lin_tile_load(tref + ((nchunk - 1) & 1) * CC_LIN_TILE, p.in, b0, nact, T, T, nchunk - 1, lane);
     cc_lin_tile_load(tyb + ((nchunk - 1) & 1) * CC_LIN_TILE, p.ybar, b0, nact, T, T, nchunk - 1, lane);
@@ -452,7 +522,7 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_cl_bwd_kernel(const 
   const long long Bp = p.Bpad;
   const long long tstep = (long long)p.tape_rows * Bp;
   const long long toff_y = (long long)p.tape_yrow * Bp, toff_c = (long long)C.tape_row * Bp;
-  const float* tpk = p.tape + (act ? b : 0) + (long long)(T - 1) * tstep;
+  const float* tpk = p.tape + (act ? b : 0) + (long long)(k_end - 1 - k_beg) * tstep;  // (segment-local record index k - k_beg)
   const float* inrow = p.in + (act ? b : 0) * (long long)T * R;
   const float* ybrow = p.ybar + (act ? b : 0) * (long long)T;
   float n_ref[CC_TINY_O], n_xc[CC_TINY_S], n_yb = 0.f, n_yp = 0.f;
@@ -469,9 +539,9 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_cl_bwd_kernel(const 
   };
 #pragma unroll
   for (int i = 0; i < CC_TINY_O; ++i) n_ref[i] = 0.f;
-  if (T > 0) fetch(T - 1);
+  if (k_end > k_beg) fetch(k_end - 1);
   for (int blk = nblk - 1; blk >= 0; --blk) {
-    const int k0 = blk * m;
+    const int k0 = k_beg + blk * m;
     cc_lin_round(tm);
     cc_lin_await(tm);
     {
@@ -482,7 +552,7 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_cl_bwd_kernel(const 
       for (int t = 0; t < CC_LIN_MAXM; ++t) c[t] = d[14 - t];
     }
     cc_lin_advance_state<NCH>(tm, rst, S);
-    const int nst = T - k0 < m ? T - k0 : m;
+    const int nst = k_end - k0 < m ? k_end - k0 : m;
 #pragma unroll 1
     for (int j = nst - 1; j >= 0; --j) {
       const int k = k0 + j;
@@ -509,7 +579,7 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_cl_bwd_kernel(const 
       if (!act) {  // (inactive lanes read trajectory 0's data: keep their arithmetic finite and their sums zero)
         yb = 0.f;
       }
-      if (k > 0) fetch(k - 1);
+      if (k > k_beg) fetch(k - 1);
       const float tc = CD.has_t ? ttab[k] : 0.f;
       const float w = yb + yfb;  // cotangent of y_k: loss + feedback into step k+1
       cc_lin_store_split1(tm, CC_LIN_SLOT(j), w);
@@ -587,6 +657,30 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_cl_bwd_kernel(const 
     }
   }
   cc_lin_cp_wait_all();
+  if (p.lam_io && k_beg > 0) {
+    // adjoint carry for the earlier segment: mu_{k_beg} = r + Chat w_blk with the w slots of the block just walked (still in
+    // the A operand: hi + lo, i.e. w to 2^-24), lam_c and the feedback cotangent
+    float wh[16], wl[16];
+    cc_lin_ld<16>(tm, CC_LIN_COL_AHI + 48, wh);
+    cc_lin_ld<16>(tm, CC_LIN_COL_ALO + 48, wl);
+    cc_lin_wait_ld();
+    const float* sm = p.lin_pack + CC_LIN_SMALL;
+    float* lo = p.lam_io + (act ? b : 0);
+#pragma unroll
+    for (int i = 0; i < CC_TINY_S; ++i)
+      if (i < CD.S && act) lo[(long long)i * p.Bpad] = lamc[i];
+#pragma unroll
+    for (int i = 0; i < 8 * NCH; ++i) {
+      if (i < S) {
+        float x = rst[i];
+#pragma unroll
+        for (int t = 0; t < CC_LIN_MAXM; ++t)
+          if (t < m) x = fmaf(sm[CC_LIN_S_CHAT + i * 16 + t], wh[14 - t] + wl[14 - t], x);
+        if (act) lo[(long long)(C.S + i) * p.Bpad] = x;
+      }
+    }
+    if (act) lo[(long long)(C.S + S) * p.Bpad] = yfb;
+  }
   // gradient record of this warp tile (32 trajectories; fixed xor tree -> deterministic), reduced by cc_reduce_grad_kernel
   {
     const long long wt = (long long)blockIdx.x * 4 + warp;
@@ -610,7 +704,7 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_cl_bwd_kernel(const 
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(CC_FULL, v, off);
-        if (lane == 0 && wt < p.n_wtiles) rec[C.g_base + goff + r] = v;
+        if (lane == 0 && wt < p.n_wtiles) rec[C.g_base + goff + r] = p.seg_first ? v : rec[C.g_base + goff + r] + v;  // (segments accumulate)
       }
     }
   }

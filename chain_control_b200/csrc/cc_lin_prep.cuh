@@ -47,6 +47,9 @@ CC_DEV void cc_lin_split(double w, float& hi, float& lo) {
   u = (u + 0x1000u) & 0xFFFFE000u;
   memcpy(&hi, &u, 4);
   lo = (float)(w - (double)hi);
+  memcpy(&u, &lo, 4);  // the tensor core truncates a 32-bit operand to tf32: round the lo word here instead (unbiased)
+  u = (u + 0x1000u) & 0xFFFFE000u;
+  memcpy(&lo, &u, 4);
 }
 
 #ifndef CC_EMULATE
@@ -359,7 +362,7 @@ __global__ void __launch_bounds__(CC_LIN_PREP_THREADS, 1) cc_lin_prep_kernel(con
     }
     __syncthreads();
     if (tid < 64) {
-      sp[CC_LIN_S_CPHI + tid] = (float)cP[tid];
+      sp[CC_LIN_S_CPHI + tid] = (float)(cP[tid] - eye);  // Phi_c - I: the step is applied as an increment (fp32 keeps 1e-9, not 6e-8)
       double* ctab = reinterpret_cast<double*>(sp + CC_LIN_S_CTAB);
       ctab[tid] = cA[tid] / hc;
       ctab[64 + tid] = cG[tid];

@@ -39,10 +39,18 @@ struct CcLinTm {
 #endif
 };
 
-CC_DEV float cc_lin_tf32(float v) {
+CC_DEV float cc_lin_tf32(float v) {  // truncation to tf32 (what the tensor core does with a 32-bit operand)
   unsigned u;
   memcpy(&u, &v, 4);
   u &= 0xFFFFE000u;
+  float r;
+  memcpy(&r, &u, 4);
+  return r;
+}
+CC_DEV float cc_lin_tf32_rn(float v) {  // round to nearest tf32 (ties away): the operand splits below are unbiased
+  unsigned u;
+  memcpy(&u, &v, 4);
+  u = (u + 0x1000u) & 0xFFFFE000u;
   float r;
   memcpy(&r, &u, 4);
   return r;
@@ -162,15 +170,15 @@ template <int NC>
 CC_DEV void cc_lin_store_split(const CcLinTm& t, int c0, const float (&z)[NC]) {
   float hi[NC], lo[NC];
 #pragma unroll
-  for (int i = 0; i < NC; ++i) {
-    hi[i] = cc_lin_tf32(z[i]);
-    lo[i] = z[i] - hi[i];
+  for (int i = 0; i < NC; ++i) {  // z = hi + lo with |lo| <= 2^-12 |z|, lo rounded (not truncated) to tf32: error <= 2^-24 |z|
+    hi[i] = cc_lin_tf32_rn(z[i]);
+    lo[i] = cc_lin_tf32_rn(z[i] - hi[i]);
   }
   cc_lin_st<NC>(t, CC_LIN_COL_AHI + c0, hi);
   cc_lin_st<NC>(t, CC_LIN_COL_ALO + c0, lo);
 }
 CC_DEV void cc_lin_store_split1(const CcLinTm& t, int col, float v) {
-  const float hi = cc_lin_tf32(v);
+  const float hi = cc_lin_tf32_rn(v);
   cc_lin_st1(t, CC_LIN_COL_AHI + col, hi);
-  cc_lin_st1(t, CC_LIN_COL_ALO + col, v - hi);
+  cc_lin_st1(t, CC_LIN_COL_ALO + col, cc_lin_tf32_rn(v - hi));
 }

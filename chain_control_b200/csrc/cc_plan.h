@@ -119,6 +119,12 @@ struct CcKParams {
   float* x_final;      // open loop, optional
   float* tape;         // [n_ckpt][tape_rows][Bpad] (feature-major); then float ttab[2][T] (step times)
   int ckpt_every, n_ckpt, tape_rows;
+  float* ttab;         // step times [2][T] (written by the forward pass, read by the reverse pass and by resumed segments)
+  // segments (checkpointed recomputation, ckpt_every > 1): a launch covers the steps [seg_k0, seg_k1)
+  int seg_k0, seg_k1;
+  const float* carry_in;  // forward: the carry at step seg_k0 as one tape record [tape_rows][Bpad], or nullptr (fresh start)
+  float* lam_io;          // reverse: adjoint carry [S_0 (+ S_1) + O][Bpad]: read if seg_k1 < T, written if seg_k0 > 0
+  int seg_first;          // reverse: first launch of the pass (the gradient records are initialised, not accumulated)
   int tape_yrow;       // closed loop: first row of the fed-back output inside a tape record
   long long Bpad;      // B rounded up to a multiple of 32
   // backward

@@ -142,6 +142,28 @@ def mse_value_and_cotangent(y, yhat, n_total: Optional[int] = None):
     return part[:1], ybar
 
 
+class FusedAdam:
+    """optax.chain(clip_by_global_norm(c), clip(v), adam(lr)) plus the reference's l1 / l2 regulariser gradients as ONE kernel
+    on the flat parameter vector (cc/train/step_fn.py:101-114,166-169; cc/utils/high_level/defaults.py:43-49).  State and
+    step counter live on the device: no host round trip, CUDA-graph capturable."""
+
+    def __init__(self, theta: torch.Tensor, lr: float, *, b1=0.9, b2=0.999, eps=1e-8, clip_global_norm=0.0, clip_value=0.0,
+                 l1=0.0, l2=0.0):
+        self.theta = _check(theta, "theta")
+        self.mu, self.nu = torch.zeros_like(self.theta), torch.zeros_like(self.theta)
+        self.count = torch.zeros(1, dtype=torch.int32, device=theta.device)
+        self.out = torch.zeros(3, dtype=torch.float32, device=theta.device)
+        self.hp = (float(lr), float(b1), float(b2), float(eps), float(clip_global_norm), float(clip_value), float(l1), float(l2))
+
+    def step(self, grad: torch.Tensor, grad_scale: float = 1.0):
+        L = _lib.lib()
+        grad = _check(grad, "grad", tuple(self.theta.shape))
+        rc = L.cc_opt_step(_ptr(self.theta), _ptr(self.mu), _ptr(self.nu), _ptr(grad), _ptr(self.count), _ptr(self.out),
+                           self.theta.numel(), *[C.c_float(v) for v in self.hp], C.c_float(grad_scale), _stream())
+        L.check(rc, "cc_opt_step")
+        return self.theta
+
+
 class _RolloutFn(torch.autograd.Function):
     """y = vmap(model.unroll)(u); backward = the BPTT kernel (custom VJP, generic cotangent)."""
 

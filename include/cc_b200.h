@@ -140,6 +140,16 @@ int32_t cc_closedloop_bwd(const CcModule* ctrl, const CcModule* model, const flo
 int32_t cc_mse_value_and_cotangent(const float* y, const float* yhat, float* ybar,
                                    float* loss_partial, int64_t n, float inv_n, void* stream);
 
+/* ---- tail of the train step on the device (cc/train/step_fn.py:101-114,166-169,307-308; optax semantics) ----
+ * grad' = grad_scale * grad + l1 * sign(theta) + l2 * theta / ||theta||_2   (regularisers on the flat vector, utils.py:38-45)
+ * -> optax.clip_by_global_norm(clip_global_norm) (<= 0: off) -> optax.clip(clip_value) (<= 0: off) -> optax.adam(lr, b1, b2, eps)
+ * theta, mu, nu [P] are updated in place; count[1] (device int32) is the step counter of the bias correction (incremented);
+ * out3 (device, optional) = {l1 norm, l2 norm of theta before the update, ||grad'||_2 before clipping}.
+ * One launch, no host round trip: the whole step (rollout, loss, BPTT, update) can be captured in a CUDA graph. */
+int32_t cc_opt_step(float* theta, float* mu, float* nu, const float* grad, int32_t* count, float* out3, int64_t P,
+                    float lr, float b1, float b2, float eps, float clip_global_norm, float clip_value,
+                    float l1_prefactor, float l2_prefactor, float grad_scale, void* stream);
+
 /* ---- measurement helper: register-resident FFMA chain, returns nothing; time it with events ---- */
 int32_t cc_fp32_peak_probe(float* sink, int32_t iters, void* stream);
 /* same, but the SGEMM register-tile pattern acc[i][j] += x[i]*y[j] (three register operands per FFMA):

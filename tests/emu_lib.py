@@ -71,30 +71,30 @@ def np_closedloop_fwd(L, cspec, mspec, theta_c, theta_m, refs, noise=None, tape_
     return yhat, us, tape
 
 
-def np_rollout_bwd(L, spec, theta, u, ybar, x0=None, want_ubar=True):
+def np_rollout_bwd(L, spec, theta, u, ybar, x0=None, want_ubar=True, ckpt_every=1):
     theta, u, x0, ybar = _f32(theta), _f32(u), _f32(x0), _f32(ybar)
     B, T, _ = u.shape
     m = spec.to_c()
-    y, xf, tape = np_rollout_fwd(L, spec, theta, u, x0, tape_every=1)
-    nws = L.cc_rollout_workspace_bytes(C.byref(m), B, T, 1)
+    y, xf, tape = np_rollout_fwd(L, spec, theta, u, x0, tape_every=ckpt_every)
+    nws = L.cc_rollout_workspace_bytes(C.byref(m), B, T, ckpt_every)
     ws = np.full(max(nws // 4, 1), np.nan, np.float32)
     tb = np.full(spec.n_params(), np.nan, np.float32)
     ub = np.full(u.shape, np.nan, np.float32) if want_ubar else None
-    rc = L.cc_rollout_bwd(C.byref(m), _p(theta), _p(u), _p(x0), _p(tape), 1, _p(ybar), _p(tb), _p(ub), B, T, _p(ws),
+    rc = L.cc_rollout_bwd(C.byref(m), _p(theta), _p(u), _p(x0), _p(tape), ckpt_every, _p(ybar), _p(tb), _p(ub), B, T, _p(ws),
                           ws.nbytes, None)
     L.check(rc, "cc_rollout_bwd")
     return y, tb, ub
 
 
-def np_closedloop_bwd(L, cspec, mspec, theta_c, theta_m, refs, ybar, noise=None):
+def np_closedloop_bwd(L, cspec, mspec, theta_c, theta_m, refs, ybar, noise=None, ckpt_every=1):
     theta_c, theta_m, refs, noise, ybar = _f32(theta_c), _f32(theta_m), _f32(refs), _f32(noise), _f32(ybar)
     B, Tr, _ = refs.shape
     c, m = cspec.to_c(), mspec.to_c()
-    yhat, us, tape = np_closedloop_fwd(L, cspec, mspec, theta_c, theta_m, refs, noise, tape_every=1)
-    nws = L.cc_closedloop_workspace_bytes(C.byref(c), C.byref(m), B, Tr, 1)
+    yhat, us, tape = np_closedloop_fwd(L, cspec, mspec, theta_c, theta_m, refs, noise, tape_every=ckpt_every)
+    nws = L.cc_closedloop_workspace_bytes(C.byref(c), C.byref(m), B, Tr, ckpt_every)
     ws = np.full(max(nws // 4, 1), np.nan, np.float32)
     tb = np.full(cspec.n_params(), np.nan, np.float32)
-    rc = L.cc_closedloop_bwd(C.byref(c), C.byref(m), _p(theta_c), _p(theta_m), _p(refs), _p(noise), _p(tape), 1,
+    rc = L.cc_closedloop_bwd(C.byref(c), C.byref(m), _p(theta_c), _p(theta_m), _p(refs), _p(noise), _p(tape), ckpt_every,
                              _p(ybar), _p(tb), B, Tr, _p(ws), ws.nbytes, None)
     L.check(rc, "cc_closedloop_bwd")
     return yhat, tb

@@ -166,3 +166,90 @@ def test_emu_lin_rollout(mname):
     assert l2rel(ub, ub64) < TOL_GRAD
     _, xf, _ = E.np_rollout_fwd(L, conv(spec), theta, u, x0)  # no tape: the block length divides T, x_final is exact
     assert normwise(xf, xs[:, -1]) < TOL_STATE
+
+
+# ---- checkpointed recomputation (ckpt_every > 1): the host replays the forward pass of one segment from its checkpoint into a
+# segment-local tape and walks it backwards (cc_abi_bwd.inc); adjoints and gradient sums carry over between the launches ----
+@pytest.mark.parametrize("case", ["lin_compact", "lin_post_generic_ctrl", "ffma_deep_tile_ctrl", "ffma_tv_tiny_ctrl"])
+def test_emu_closedloop_checkpointed(case):
+    from ccspecs import tc_model_variants
+
+    mspec, cspec, B, Tr, Ks = {
+        "lin_compact": (model_variants()["compact_s50_d0"], controller_variants()["compact_s5_d0"], 37, 61, (8, 20, 32)),
+        "lin_post_generic_ctrl": (tc_model_variants()["full_s20_d0"], controller_variants()["full_s6_ft_tv"], 20, 45, (10,)),
+        "ffma_deep_tile_ctrl": (model_variants()["full_s5_w10_d2"], controller_variants()["full_s25_w10_d2"], 9, 30, (8, 7)),
+        "ffma_tv_tiny_ctrl": (model_variants()["full_s1_tv"], controller_variants()["compact_s5_d0"], 9, 30, (8,)),
+    }[case]
+    L = E.emu()
+    rng = np.random.default_rng(0)
+    thc, thm = O.init_params(cspec, 2).astype(np.float32), O.init_params(mspec, 1, stable=True).astype(np.float32)
+    refs = (3 * rng.uniform(-1, 1, (B, Tr, 1))).astype(np.float32)
+    noise = (0.02 * rng.normal(size=(B, Tr, 1))).astype(np.float32)
+    ybar = rng.normal(size=(B, Tr, 1)).astype(np.float32)
+    tb64 = O.closedloop_bwd(cspec, mspec, thc, thm, refs, ybar, noise)
+    _, tb1 = E.np_closedloop_bwd(L, conv(cspec), conv(mspec), thc, thm, refs, ybar, noise)
+    for K in Ks:
+        _, tb = E.np_closedloop_bwd(L, conv(cspec), conv(mspec), thc, thm, refs, ybar, noise, ckpt_every=K)
+        assert l2rel(tb, tb64) < TOL_GRAD
+        assert l2rel(tb, tb1) < 1e-6  # theta_bar(K) == theta_bar(1) (bit-identical on the FFMA kernels: the replay is exact)
+
+
+@pytest.mark.parametrize("name", ["full_s5_w10_d2", "full_s12_w25_d1_tanh", "compact_s50_d0"])
+def test_emu_rollout_checkpointed(name):
+    spec = model_variants()[name]
+    L = E.emu()
+    rng = np.random.default_rng(1)
+    B, T = 9, 30
+    theta = O.init_params(spec, 1).astype(np.float32)
+    u = rng.uniform(-1, 1, (B, T, spec.input_dim)).astype(np.float32)
+    x0 = (0.1 * rng.normal(size=(B, spec.state_dim))).astype(np.float32)
+    ybar = rng.normal(size=(B, T + 1, spec.output_dim)).astype(np.float32)
+    tb64, ub64 = O.rollout_bwd(spec, theta, u, ybar, x0=x0)
+    _, tb1, ub1 = E.np_rollout_bwd(L, conv(spec), theta, u, ybar, x0)
+    for K in (8, 7):
+        _, tb, ub = E.np_rollout_bwd(L, conv(spec), theta, u, ybar, x0, ckpt_every=K)
+        assert l2rel(tb, tb64) < TOL_GRAD and l2rel(ub, ub64) < TOL_GRAD
+        assert l2rel(tb, tb1) < 1e-6 and l2rel(ub, ub1) < 1e-6
+
+
+def _np_opt_step(theta, mu, nu, grad, t, lr, b1, b2, eps, cn, cv, l1, l2):
+    """numpy restatement of optax.chain(clip_by_global_norm, clip, adam) + the reference's regulariser gradients"""
+    g = grad.astype(np.float64).copy()
+    th = theta.astype(np.float64)
+    if l1:
+        g += l1 * np.sign(th)
+    if l2:
+        g += l2 * th / np.sqrt((th * th).sum())
+    n = np.sqrt((g * g).sum())
+    if cn > 0 and n > cn:
+        g *= cn / n
+    if cv > 0:
+        g = np.clip(g, -cv, cv)
+    mu = b1 * mu + (1 - b1) * g
+    nu = b2 * nu + (1 - b2) * g * g
+    th = th - lr * (mu / (1 - b1 ** t)) / (np.sqrt(nu / (1 - b2 ** t)) + eps)
+    return th, mu, nu
+
+
+@pytest.mark.parametrize("hp", [(1e-3, 0.0, 0.0, 0.0, 0.0), (3e-3, 1.0, 0.0, 0.0, 0.0), (1e-3, 0.5, 0.01, 0.02, 0.05)])
+def test_emu_fused_optimiser_step(hp):
+    import ctypes as C
+
+    lr, cn, cv, l1, l2 = hp
+    L = E.emu()
+    rng = np.random.default_rng(0)
+    P = 2651
+    theta = rng.normal(size=P).astype(np.float32)
+    mu, nu = np.zeros(P, np.float32), np.zeros(P, np.float32)
+    count = np.zeros(1, np.int32)
+    out = np.zeros(3, np.float32)
+    th64, mu64, nu64 = theta.astype(np.float64), np.zeros(P), np.zeros(P)
+    for t in range(1, 4):
+        grad = (rng.normal(size=P) * (3.0 if t == 2 else 0.3)).astype(np.float32)
+        th64, mu64, nu64 = _np_opt_step(th64, mu64, nu64, grad, t, lr, 0.9, 0.999, 1e-8, cn, cv, l1, l2)
+        rc = L.cc_opt_step(theta.ctypes.data, mu.ctypes.data, nu.ctypes.data, grad.ctypes.data, count.ctypes.data, out.ctypes.data,
+                           P, *[C.c_float(v) for v in (lr, 0.9, 0.999, 1e-8, cn, cv, l1, l2, 1.0)], None)
+        L.check(rc, "cc_opt_step")
+        assert count[0] == t
+        np.testing.assert_allclose(theta, th64, rtol=2e-6, atol=2e-7)
+        np.testing.assert_allclose(mu, mu64, rtol=1e-5, atol=1e-8)
