@@ -342,17 +342,28 @@ def test_cfg5_long_horizon_checkpointed(B, T_):
     ref = CO.closedloop(cspec, mspec, thc, thm, refs, mse_loss=True, dtype=np.float64)
     r32 = CO.closedloop(cspec, mspec, thc, thm, refs, mse_loss=True, dtype=np.float32)
     floor_y, floor_g = normwise(r32["yhat"], ref["yhat"]), l2rel(r32["theta_c_bar"], ref["theta_c_bar"])
-    g1 = None
+    def run(K, m_block=None):
+        if m_block:
+            os.environ["CC_B200_LIN_M"] = str(m_block)
+        try:
+            yh, _, tape = ops.closedloop_fwd(conv(cspec), conv(mspec), T_(thc), T_(thm), T_(refs), want_tape=True, ckpt_every=K)
+            ybar = O.mse_cotangent(refs, yh.cpu().numpy())
+            tb = ops.closedloop_bwd(conv(cspec), conv(mspec), T_(thc), T_(thm), T_(refs), tape, T_(ybar), ckpt_every=K).cpu().numpy()
+        finally:
+            os.environ.pop("CC_B200_LIN_M", None)
+        return yh.cpu().numpy(), tb
+
+    yh1, g1 = run(1)
     for K in (1, 32, 100, 128):
-        yh, _, tape = ops.closedloop_fwd(conv(cspec), conv(mspec), T_(thc), T_(thm), T_(refs), want_tape=True, ckpt_every=K)
-        ybar = O.mse_cotangent(refs, yh.cpu().numpy())
-        tb = ops.closedloop_bwd(conv(cspec), conv(mspec), T_(thc), T_(thm), T_(refs), tape, T_(ybar), ckpt_every=K).cpu().numpy()
-        assert normwise(yh.cpu().numpy(), ref["yhat"]) < max(TOL_STATE, 3 * floor_y), (K, floor_y)
+        yh, tb = run(K)
+        assert normwise(yh, ref["yhat"]) < max(TOL_STATE, 3 * floor_y), (K, floor_y)
         assert l2rel(tb, ref["theta_c_bar"]) < max(TOL_GRAD, 3 * floor_g), (K, floor_g)
-        if g1 is None:
-            g1 = tb
-        # (exact replay on the FFMA kernels; here K = 32 / 128 run with blocks of 8 steps instead of 13: 1-2e-6 over 10,001 steps)
-        assert l2rel(tb, g1) < 5e-6, K
+        if K > 1:
+            # against ckpt_every = 1: bit-identical on the FFMA kernels (exact replay, test_checkpointed_general_architectures);
+            # here every checkpoint materialises x_m in fp32 where the unsegmented run keeps the 3xTF32 operand chain, and the
+            # block length follows K (8 or 10 steps instead of 13): 1e-5 after 10,001 steps and up to 1,250 checkpoints, 20x
+            # below the fp32 restatement's own distance to fp64 at this horizon (2-4e-4); short horizons: 2e-7 (test_emu_parity)
+            assert l2rel(tb, g1) < 3e-5, K
 
 
 @pytest.mark.parametrize("mname,cname", [("full_s5_w10_d2", "full_s25_w10_d2"), ("euler_s30_d0_tanh", "compact_s5_d0")])
