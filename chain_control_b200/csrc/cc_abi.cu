@@ -387,6 +387,8 @@ int make_plan(const CcModule* const* mods, int n_nodes, long long B, int T, cons
     if (seg && n_nodes == 2)  // checkpoints sit on block starts: the block length divides ckpt_every
       for (int d = p->lin_m; d >= 1; --d)
         if (o.ckpt % d == 0) { p->lin_m = d; break; }
+    // per-step tape of the closed loop: trajectory-interleaved records [x_c ; y_prev ; pad to even] (cc_lin_kernels.cuh)
+    if (!seg && n_nodes == 2) p->tape_rows = (p->nd[0].S + 2) & ~1;
     if (n_nodes == 1) {
       // open loop: the MMA chain carries x_k itself, so a ragged last block would end BEHIND step T; when the final state
       // is requested the block length divides T (T = 1, the step() call, runs with m = 1)
@@ -634,10 +636,13 @@ size_t cc_rollout_tape_bytes(const CcModule* m, int64_t B, int32_t T, int32_t ck
 }
 
 size_t cc_closedloop_tape_bytes(const CcModule* c, const CcModule* m, int64_t B, int32_t Tr, int32_t ckpt_every) {
-  if (!c || !m || B <= 0 || Tr < 0 || ckpt_every < 1) return 0;
-  const long long Bpad = (B + 31) / 32 * 32;
-  const int sm_rows = (mlp_linear(m->f) && mlp_linear(m->g) && ckpt_every == 1) ? 0 : m->state_dim;
-  return ((size_t)n_ckpt_of(Tr, ckpt_every) * (c->state_dim + sm_rows + m->output_dim) * Bpad + 2 * (size_t)Tr) * sizeof(float);
+  if (!c || !m || B <= 0 || Tr < 0 || ckpt_every < 1 || validate_module(c, "controller") || validate_module(m, "model")) return 0;
+  CcKParams p;
+  PlanOpts o;
+  o.ckpt = ckpt_every;
+  const CcModule* mods[2] = {c, m};
+  if (make_plan(mods, 2, B, Tr, o, &p)) return 0;
+  return ((size_t)n_ckpt_of(Tr, ckpt_every) * p.tape_rows * p.Bpad + 2 * (size_t)Tr) * sizeof(float);
 }
 
 size_t cc_rollout_fwd_workspace_bytes(const CcModule* m, int64_t B, int32_t T) {

@@ -90,7 +90,8 @@ int cc_launch_lin(const CcKParams& p, bool bwd, void* stream, char* err, int err
     const size_t keepf = lc ? 0 : (size_t)(C.f.layer[0].act != CC_ACT_IDENTITY ? 9 : 5) * CC_TINY_S * 128;
     const char* sgb = getenv("CC_B200_LIN_STAGE_BWD");
     const bool stgb = stg && lc && c521 && sgb && atoi(sgb) == 1;  // measured: no gain (2.55 vs 2.41 ms at 65,536 x 1001), off by default  // register accumulators leave room for the refs / ybar tiles
-    const size_t smem = ((size_t)CC_LIN_SM_STAGE + (stgb ? 4 * 4 * CC_LIN_TILE : 0) + gpf + keepf + kEmuTmemFloats) * 4;
+    const size_t ringf = 4 * CC_LIN_RING_D * 32 * CC_LIN_RING_STRIDE;  // per-warp cp.async ring of the tape / reference / cotangent loads
+    const size_t smem = ((size_t)CC_LIN_SM_STAGE + (stgb ? 4 * 4 * CC_LIN_TILE : 0) + gpf + keepf + ringf + kEmuTmemFloats) * 4;
     if (stgb) return CC_LIN_NCH(cc_lin_cl_bwd_kernel, 521, true, true);
     return (lc && c521) ? CC_LIN_NCH(cc_lin_cl_bwd_kernel, 521, false, true) : (lc ? CC_LIN_NCH(cc_lin_cl_bwd_kernel, 0, false, true) : CC_LIN_NCH(cc_lin_cl_bwd_kernel, 0, false, false));
   }

@@ -24,6 +24,7 @@
 #include "cc_kernels.cuh"
 #include "cc_lin_tm.cuh"
 #include "cc_tc_ctrl.cuh"
+#include <type_traits>
 
 // ---- shared-memory carve (floats) -----------------------------------------------------------------
 #define CC_LIN_SM_BHI 0
@@ -35,6 +36,9 @@
 #define CC_LIN_SM_BAR (CC_LIN_SM_WGC + CC_TINY_O * CC_CK)   // 2 mbarriers + tmem slot (8 floats)
 #define CC_LIN_SM_STAGE (CC_LIN_SM_BAR + 8)   // I/O staging tiles (per warp), then the reverse pass's controller scratch
 #define CC_LIN_TILE 1056                      // 32 rows x 33 floats
+#define CC_LIN_RP(Sc) (((Sc) + 2) & ~1)       // floats of a per-step tape record [x_c ; y_prev ; pad to even]
+#define CC_LIN_RING_D 4                       // reverse pass: the loads of step k - 4 are in flight while step k is processed
+#define CC_LIN_RING_STRIDE 14                 // floats per lane and ring slot: [record (<= 10) ; refs (<= 3) ; ybar], 8-byte aligned, conflict free
 #ifdef CC_EMULATE
 #define CC_LIN_SM_TMEM_EMU(base) ((base))     // emulated TMEM [192][128] floats appended behind everything else
 #endif
@@ -48,6 +52,18 @@ CC_DEV void cc_lin_cp4(float* dst_smem, const float* src) {
   *dst_smem = *src;
 #else
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(cc_smem_u32(dst_smem)), "l"(src) : "memory");
+#endif
+}
+CC_DEV void cc_lin_cp8(float* dst_smem, const float* src) {
+#ifdef CC_EMULATE
+  dst_smem[0] = src[0]; dst_smem[1] = src[1];
+#else
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(cc_smem_u32(dst_smem)), "l"(src) : "memory");
+#endif
+}
+CC_DEV void cc_lin_cp_wait_ring() {  // at most RING_D - 1 = 3 groups pending
+#ifndef CC_EMULATE
+  asm volatile("cp.async.wait_group 3;" ::: "memory");
 #endif
 }
 CC_DEV void cc_lin_cp_commit() {
@@ -316,11 +332,17 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_cl_fwd_kernel(const 
   float* tpk = p.tape ? p.tape + b : nullptr;
   const long long tstep = (long long)p.tape_rows * Bp;
   const long long toff_y = (long long)p.tape_yrow * Bp, toff_c = (long long)C.tape_row * Bp;
+  // per-step tape (ckpt_every == 1, also the segment-local tape of a replay): one record [x_c (S_c) ; y_prev ; pad] of RP floats
+  // per trajectory and step, trajectory-interleaved -> [step][Bpad][RP]: a lane writes RP/2 8-byte words, a warp one
+  // contiguous 32*RP*4-byte run.  (Checkpoint records of ckpt_every > 1 stay feature-major [rows][Bpad] like every family's.)
+  const int RP = CC_LIN_RP(CD.S);
+  float* tpl = p.tape ? p.tape + (act ? b : 0) * RP : nullptr;
   const float* inrow = p.in + (act ? b : 0) * (long long)T * R;
   float* outrow = p.out ? p.out + (act ? b : 0) * (long long)T : nullptr;
   const float* nzrow = p.noise ? p.noise + (act ? b : 0) * (long long)T : nullptr;
   float* uorow = (p.u_out && act) ? p.u_out + b * (long long)T : nullptr;
   float* ttab = (p.tape && CD.has_t && blockIdx.x == 0 && tid == 0) ? p.ttab : nullptr;
+  const bool fast = p.tape && cke == 1 && !ttab && !uorow && !nzrow && CD.pre && M.pre && mut == CC_UT_ARCTAN && p.out && !CD.has_t;
   float a[CC_LIN_MAXM];
   for (int k0 = k_beg; k0 < k_end; k0 += m) {
     // ---- one MMA batch for the block: A was completed by the previous block's sequential phase ----
@@ -360,8 +382,10 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_cl_fwd_kernel(const 
       if constexpr (NCH == 8) pst[CC_LIN_ONE] = 1.f;
     }
     const int nst = k_end - k0 < m ? k_end - k0 : m;
-#pragma unroll 1
-    for (int j = 0; j < nst; ++j) {
+    // the step body exists twice: F = the common case (per-step tape, compact controller and model with pre-step readouts,
+    // arctan input transform, no noise / control-series output) with every run-time switch folded, and the general one
+    auto step_body = [&](auto fast_tag, const int j) {
+      constexpr bool F = decltype(fast_tag)::value;
       const int k = k0 + j;
       const int kc = k & 31;
       if (STG && (kc == 0 || k == k_beg)) {  // chunk boundary (or first step): the chunk's tile has landed; prefetch the next one
@@ -369,7 +393,7 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_cl_fwd_kernel(const 
         __syncwarp();
         cc_lin_tile_load(cc_smem + tin_off + (((k >> 5) + 1) & 1) * CC_LIN_TILE, p.in, b0, nact, T, T, (k >> 5) + 1, lane);
       }
-      if (ttab) { ttab[k] = tc; ttab[T + k] = 0.f; }
+      if (!F && ttab) { ttab[k] = tc; ttab[T + k] = 0.f; }
       // controller input = merge_x_y(ref, y_prev) = [ref ; obs]     step_fn.py:187-192
       float vc[CC_TINY_O];
 #pragma unroll
@@ -381,7 +405,19 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_cl_fwd_kernel(const 
         }
         if (i == R) vc[i] = yprev;
       }
-      if (p.tape && (cke == 1 || (k - k_beg) % cke == 0)) {
+      if (F || (p.tape && cke == 1)) {
+        if (tape) {
+#pragma unroll
+          for (int w2 = 0; w2 < (CC_TINY_S + 2) / 2; ++w2) {
+            if (2 * w2 < RP) {
+              const float v0 = 2 * w2 < CD.S ? xc[2 * w2 < CC_TINY_S ? 2 * w2 : 0] : (2 * w2 == CD.S ? yprev : 0.f);
+              const float v1 = 2 * w2 + 1 < CD.S ? xc[2 * w2 + 1 < CC_TINY_S ? 2 * w2 + 1 : 0] : (2 * w2 + 1 == CD.S ? yprev : 0.f);
+              *reinterpret_cast<float2*>(tpl + 2 * w2) = make_float2(v0, v1);
+            }
+          }
+        }
+        tpl += Bp * RP;
+      } else if (!F && p.tape && (k - k_beg) % cke == 0) {
         if (tape) {
           tpk[toff_y] = yprev;
 #pragma unroll
@@ -393,13 +429,13 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_cl_fwd_kernel(const 
       float araw[CC_TINY_O];
 #pragma unroll
       for (int i = 0; i < CC_TINY_O; ++i) araw[i] = 0.f;
-      if (CD.pre) cc_ctrl_readout_pre(CD, sh.wgc, xc, tc, vc, araw);
+      if (F || CD.pre) cc_ctrl_readout_pre(CD, sh.wgc, xc, tc, vc, araw);
       if (LC) {  // collapsed integrator step of the linear controller; post-step readout g([x_c+ ; v])
         float xn[CC_TINY_S];
         cc_lctrl_next<LC ? CFG : 0>(CD, sh.clin, LR, xc, vc, xn);
 #pragma unroll
         for (int n = 0; n < CC_TINY_S; ++n) xc[n] = xn[n];
-        if (!CD.pre) {
+        if (!F && !CD.pre) {
           CcCtrlIn cin;
           cc_ctrl_make_in(xc, tc, vc, cin);
           cc_ctrl_readout(CD, sh.wgc, cin, araw);
@@ -408,26 +444,33 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_cl_fwd_kernel(const 
         cc_ctrl_update<false>(CD, sh.wfc, sh.wgc, xc, tc, vc, araw, nullptr);
       }
       if (CD.has_t) tc = tc + CD.dt;
-      if (uorow) uorow[k] = araw[0];
-      const float ut = cc_ut(mut, mus, araw[0]);
+      if (!F && uorow) uorow[k] = araw[0];
+      const float ut = F ? atanf(araw[0]) : cc_ut(mut, mus, araw[0]);
       cc_lin_store_split1(tm, CC_LIN_SLOT(j), ut);
-      float y = fmaf(H0, ut, a[0]);
+      float y = F ? a[0] : fmaf(H0, ut, a[0]);
 #pragma unroll
       for (int t = 0; t < CC_LIN_MAXM - 1; ++t) a[t] = fmaf(Hs[t], ut, a[t + 1]);
       a[CC_LIN_MAXM - 1] = 0.f;
-      if (nzrow && act) y += __ldg(nzrow + k);
+      if (!F && nzrow && act) y += __ldg(nzrow + k);
       yprev = y;
       if (STG) {
         cc_smem[tout_off + trow + kc] = y;
         if (kc == 31 || k == k_end - 1) {
           __syncwarp();
           // (a segment replay has no output array; a chunk straddling a segment start rewrites only its own steps)
-          if (p.out) cc_lin_tile_store_range(cc_smem + tout_off, p.out, b0, nact, T, (k >> 5) * 32 > k_beg ? (k >> 5) * 32 : k_beg, k + 1, lane);
+          if (F || p.out) cc_lin_tile_store_range(cc_smem + tout_off, p.out, b0, nact, T, (k >> 5) * 32 > k_beg ? (k >> 5) * 32 : k_beg, k + 1, lane);
           __syncwarp();
         }
       } else if (act && outrow) {
         outrow[k] = y;
       }
+    };
+    if (fast) {
+#pragma unroll 1
+      for (int j = 0; j < nst; ++j) step_body(std::true_type{}, j);
+    } else {
+#pragma unroll 1
+      for (int j = 0; j < nst; ++j) step_body(std::false_type{}, j);
     }
   }
   cc_lin_cp_wait_all();
@@ -452,7 +495,7 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_cl_bwd_kernel(const 
   constexpr bool REGACC = LC && CFG != 0;
   const int gp_floats = REGACC ? 0 : (C.S + C.O) * CC_CKU * 128;
   const int keep_floats = LC ? 0 : (C.f.layer[0].act != CC_ACT_IDENTITY ? 9 : 5) * CC_TINY_S * 128;
-  cc_lin_prologue(p, sh, true, tm, CC_LIN_SM_STAGE + stage_floats + gp_floats + keep_floats);
+  cc_lin_prologue(p, sh, true, tm, CC_LIN_SM_STAGE + stage_floats + gp_floats + keep_floats + 4 * CC_LIN_RING_D * 32 * CC_LIN_RING_STRIDE);
   const int S = M.S, m = p.lin_m, T = p.T;
   const int R = CFG ? 1 : p.R;
   const bool post = !M.pre;
@@ -518,28 +561,59 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_cl_bwd_kernel(const 
     cc_lin_tile_load(tyb + ((nchunk - 1) & 1) * CC_LIN_TILE, p.ybar, b0, nact, T, T, nchunk - 1, lane);
   }
   int cur_chunk = nchunk;  // chunk whose tiles are valid (none yet)
-  // the loads of step k-1 (tape record, reference, cotangent) are issued while step k is processed
+  // the loads of step k - 4 (tape record, reference, cotangent) are issued with cp.async into a per-warp ring while step k is
+  // processed: global-memory latency (the reverse pass's dominant stall with a one-step register prefetch) is covered
   const long long Bp = p.Bpad;
-  const long long tstep = (long long)p.tape_rows * Bp;
-  const long long toff_y = (long long)p.tape_yrow * Bp, toff_c = (long long)C.tape_row * Bp;
-  const float* tpk = p.tape + (act ? b : 0) + (long long)(k_end - 1 - k_beg) * tstep;  // (segment-local record index k - k_beg)
+  const int RP = CC_LIN_RP(CD.S);
+  const long long tstep1 = Bp * RP;
+  const float* tpk = p.tape + (act ? b : 0) * RP + (long long)(k_end - 1 - k_beg) * tstep1;  // (segment-local record index k - k_beg)
   const float* inrow = p.in + (act ? b : 0) * (long long)T * R;
   const float* ybrow = p.ybar + (act ? b : 0) * (long long)T;
-  float n_ref[CC_TINY_O], n_xc[CC_TINY_S], n_yb = 0.f, n_yp = 0.f;
-  auto fetch = [&](int k) {
-    n_yp = tpk[toff_y];
+  const int ring_off = CC_LIN_SM_STAGE + stage_floats + gp_floats + keep_floats + (warp * CC_LIN_RING_D * 32 + lane) * CC_LIN_RING_STRIDE;
+  auto prefetch = [&](int k) {  // one commit group per call (empty beyond the segment start)
+    if (k >= k_beg) {
+      float* dst = cc_smem + ring_off + (k & (CC_LIN_RING_D - 1)) * 32 * CC_LIN_RING_STRIDE;
 #pragma unroll
-    for (int s2 = 0; s2 < CC_TINY_S; ++s2) n_xc[s2] = s2 < CD.S ? tpk[toff_c + s2 * Bp] : 0.f;
-    tpk -= tstep;
-    if (!STG) {
-      n_yb = __ldg(ybrow + k);
+      for (int w2 = 0; w2 < (CC_TINY_S + 2) / 2; ++w2)
+        if (2 * w2 < RP) cc_lin_cp8(dst + 2 * w2, tpk + 2 * w2);
+      tpk -= tstep1;
+      if (!STG) {
 #pragma unroll
-      for (int i = 0; i < CC_TINY_O; ++i) n_ref[i] = i < R ? __ldg(inrow + (long long)k * R + i) : 0.f;
+        for (int i = 0; i < 3; ++i)
+          if (i < R) cc_lin_cp4(dst + 10 + i, inrow + (long long)k * R + i);
+        cc_lin_cp4(dst + 13, ybrow + k);
+      }
     }
+    cc_lin_cp_commit();
   };
+  float n_ref[CC_TINY_O], n_xc[CC_TINY_S], n_yb = 0.f, n_yp = 0.f;
 #pragma unroll
   for (int i = 0; i < CC_TINY_O; ++i) n_ref[i] = 0.f;
-  if (k_end > k_beg) fetch(k_end - 1);
+  for (int d2 = 0; d2 < CC_LIN_RING_D; ++d2) prefetch(k_end - 1 - d2);
+  auto fetch = [&](int k) {  // step k's data has landed once at most RING_D - 1 younger groups are pending
+    cc_lin_cp_wait_ring();
+    const float* src = cc_smem + ring_off + (k & (CC_LIN_RING_D - 1)) * 32 * CC_LIN_RING_STRIDE;
+    float rec[CC_TINY_S + 2];
+#pragma unroll
+    for (int w2 = 0; w2 < (CC_TINY_S + 2) / 2; ++w2) {
+      rec[2 * w2] = 0.f; rec[2 * w2 + 1] = 0.f;
+      if (2 * w2 < RP) {
+        const float2 v = *reinterpret_cast<const float2*>(src + 2 * w2);
+        rec[2 * w2] = v.x; rec[2 * w2 + 1] = v.y;
+      }
+    }
+#pragma unroll
+    for (int s2 = 0; s2 < CC_TINY_S; ++s2) n_xc[s2] = s2 < CD.S ? rec[s2] : 0.f;
+    n_yp = 0.f;
+#pragma unroll
+    for (int s2 = 0; s2 < CC_TINY_S + 1; ++s2)
+      if (s2 == CD.S) n_yp = rec[s2];
+    if (!STG) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) n_ref[i] = i < R ? src[10 + i] : 0.f;
+      n_yb = src[13];
+    }
+  };
   for (int blk = nblk - 1; blk >= 0; --blk) {
     const int k0 = k_beg + blk * m;
     cc_lin_round(tm);
@@ -566,6 +640,8 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_cl_bwd_kernel(const 
         }
       }
       float vc[CC_TINY_O], xcv[CC_TINY_S];
+      fetch(k);
+      prefetch(k - CC_LIN_RING_D);
       float yb = STG ? tyb[(cur_chunk & 1) * CC_LIN_TILE + lane * 33 + (k & 31)] : n_yb;
       const float ypk = n_yp;
 #pragma unroll
@@ -579,7 +655,6 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_cl_bwd_kernel(const 
       if (!act) {  // (inactive lanes read trajectory 0's data: keep their arithmetic finite and their sums zero)
         yb = 0.f;
       }
-      if (k > k_beg) fetch(k - 1);
       const float tc = CD.has_t ? ttab[k] : 0.f;
       const float w = yb + yfb;  // cotangent of y_k: loss + feedback into step k+1
       cc_lin_store_split1(tm, CC_LIN_SLOT(j), w);

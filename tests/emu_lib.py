@@ -53,7 +53,7 @@ def np_rollout_fwd(L, spec, theta, u, x0=None, tape_every=0):
     return y, xf, tape
 
 
-def np_closedloop_fwd(L, cspec, mspec, theta_c, theta_m, refs, noise=None, tape_every=0):
+def np_closedloop_fwd(L, cspec, mspec, theta_c, theta_m, refs, noise=None, tape_every=0, want_u=True):
     theta_c, theta_m, refs, noise = _f32(theta_c), _f32(theta_m), _f32(refs), _f32(noise)
     B, Tr, _ = refs.shape
     c, m = cspec.to_c(), mspec.to_c()
@@ -66,7 +66,7 @@ def np_closedloop_fwd(L, cspec, mspec, theta_c, theta_m, refs, noise=None, tape_
     nws = L.cc_closedloop_fwd_workspace_bytes(C.byref(c), C.byref(m), B, Tr)
     ws = np.full(nws // 4 + 1, np.nan, np.float32)
     rc = L.cc_closedloop_fwd(C.byref(c), C.byref(m), _p(theta_c), _p(theta_m), _p(refs), _p(noise), _p(yhat),
-                             _p(us), _p(tape), tape_every or 1, B, Tr, _p(ws) if nws else None, nws, None)
+                             _p(us) if want_u else None, _p(tape), tape_every or 1, B, Tr, _p(ws) if nws else None, nws, None)
     L.check(rc, "cc_closedloop_fwd")
     return yhat, us, tape
 
@@ -90,7 +90,8 @@ def np_closedloop_bwd(L, cspec, mspec, theta_c, theta_m, refs, ybar, noise=None,
     theta_c, theta_m, refs, noise, ybar = _f32(theta_c), _f32(theta_m), _f32(refs), _f32(noise), _f32(ybar)
     B, Tr, _ = refs.shape
     c, m = cspec.to_c(), mspec.to_c()
-    yhat, us, tape = np_closedloop_fwd(L, cspec, mspec, theta_c, theta_m, refs, noise, tape_every=ckpt_every)
+    # (no control-series output: with no noise either, the forward kernels take their folded fast path)
+    yhat, us, tape = np_closedloop_fwd(L, cspec, mspec, theta_c, theta_m, refs, noise, tape_every=ckpt_every, want_u=False)
     nws = L.cc_closedloop_workspace_bytes(C.byref(c), C.byref(m), B, Tr, ckpt_every)
     ws = np.full(max(nws // 4, 1), np.nan, np.float32)
     tb = np.full(cspec.n_params(), np.nan, np.float32)
