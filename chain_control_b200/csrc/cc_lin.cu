@@ -98,7 +98,7 @@ int cc_launch_lin(const CcKParams& p, bool bwd, void* stream, char* err, int err
 #ifdef CC_LIN_OPEN
   // open loop
   if (!bwd) {
-    const size_t smem = ((size_t)CC_LIN_SM_STAGE + 4 * 3 * CC_LIN_TILE + kEmuTmemFloats) * 4;
+    const size_t smem = ((size_t)CC_LIN_SM_STAGE + 4 * 4 * CC_LIN_TILE + kEmuTmemFloats) * 4;
     return CC_LIN_NCH(cc_lin_ol_fwd_kernel, 0);
   }
   const size_t smem = ((size_t)CC_LINW_SMEM_FLOATS + kEmuTmemFloats * 2) * 4;

@@ -101,16 +101,41 @@ CC_DEV void cc_lin_tile_store_range(const float* tile, float* base, long long b0
 // columns >= S of D hold slot values (or zero) and must not reach p.
 template <int NCH>
 CC_DEV void cc_lin_advance_state(const CcLinTm& tm, float (&p)[8 * NCH], int S) {
+  // all tcgen05.ld first, ONE wait (a wait per chunk exposes the TMEM round trip NCH times per block)
+  float d[8 * NCH];
+  {
+    float d32[32];
+    cc_lin_ld<32>(tm, CC_LIN_COL_D, d32);
+    if constexpr (NCH == 4) {
+      cc_lin_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) d[i] = d32[i];
+    } else if constexpr (NCH == 7) {
+      float d16[16], d8[8];
+      cc_lin_ld<16>(tm, CC_LIN_COL_D + 32, d16);
+      cc_lin_ld<8>(tm, CC_LIN_COL_D + 48, d8);
+      cc_lin_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) d[i] = d32[i];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) d[32 + i] = d16[i];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d[48 + i] = d8[i];
+    } else {
+      float e32[32];
+      cc_lin_ld<32>(tm, CC_LIN_COL_D + 32, e32);
+      cc_lin_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) { d[i] = d32[i]; d[32 + i] = e32[i]; }
+    }
+  }
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
-    float d[8];
-    cc_lin_ld<8>(tm, CC_LIN_COL_D + 8 * c, d);
-    cc_lin_wait_ld();
     float z[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int col = 8 * c + i;
-      float inc = d[i];
+      float inc = d[col];
       if (col >= 48) inc = col < S ? inc : 0.f;  // (the slots occupy columns 50..62)
       p[col] += inc;
       z[i] = p[col];

@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_ol_fwd_kernel(const 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const CcLinShared sh = cc_lin_carve(cc_smem);
   CcLinTm tm;
-  cc_lin_prologue(p, sh, false, tm, CC_LIN_SM_STAGE + 4 * 3 * CC_LIN_TILE);
+  cc_lin_prologue(p, sh, false, tm, CC_LIN_SM_STAGE + 4 * 4 * CC_LIN_TILE);
   const int S = M.S, I = M.I, O = M.O, m = p.lin_m, T = p.T;
   const long long b0 = (long long)blockIdx.x * 128 + warp * 32;
   const long long rem = p.B - b0;
@@ -34,7 +34,10 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_ol_fwd_kernel(const 
   const bool act = lane < nact;
   const long long b = b0 + lane;
   const bool stg = p.lin_stage != 0;  // I = O = 1: coalesced tiles for u and y
-  float* tin = sh.stage + warp * 3 * CC_LIN_TILE;
+  // per warp: two input tiles and two output tiles (chunk c of 32 steps in slot c & 1): a block of m <= 13 steps touches at
+  // most two chunks, and the tile copies are issued ONCE per block (they must not sit inside the unrolled per-slot code: 13
+  // copies of a 32-iteration loop thrash the instruction cache).  4 tiles per warp keep two CTAs per SM.
+  float* tin = sh.stage + warp * 4 * CC_LIN_TILE;
   float* tout = tin + 2 * CC_LIN_TILE;
   const float* small = p.lin_pack + CC_LIN_SMALL;
   float x[8 * NCH];
@@ -59,7 +62,8 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_ol_fwd_kernel(const 
     cc_lin_store_split<8>(tm, 8 * c, z);
   }
   if constexpr (NCH != 8) cc_lin_store_split1(tm, CC_LIN_ONE, 1.f);
-  if (stg) cc_lin_tile_load(tin, p.in, b0, nact, T, T, 0, lane);
+  int issued = 0, waited = 0;  // input chunks whose copy has been issued / has landed
+  if (stg) { cc_lin_tile_load(tin, p.in, b0, nact, T, T, 0, lane); issued = 1; }
   int blk = 0;
   // y of step k is row k+1 of the output: the output tile of chunk c covers rows [32c + 1, 32c + 33)
   for (int k0 = 0; k0 < T; k0 += m, ++blk) {
@@ -70,22 +74,51 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_ol_fwd_kernel(const 
       for (int i = 0; i < 8 * NCH; ++i)
         if (i < S) tp[(long long)i * p.Bpad] = x[i];
     }
-    // u~ slots of this block
-    for (int j = 0; j < m; ++j) {
-      const int k = k0 + j;
-      if (stg && j < nst && (k & 31) == 0) {
+    // u~ slots of this block (slot t = step * I + component sits at column 62 - t): gathered, then ONE 16-column store of
+    // columns 48..63 (state columns below S keep their value, column 63 is the constant 1)
+    float uval[CC_LIN_MAXM];
+    const int cB = (k0 + nst - 1) >> 5;
+    if (stg) {  // the chunks of this block must have landed
+#pragma unroll 1
+      for (; issued <= cB; ++issued) cc_lin_tile_load(tin + (issued & 1) * CC_LIN_TILE, p.in, b0, nact, T, T, issued, lane);
+      if (waited <= cB) {
         cc_lin_cp_wait_all();
         __syncwarp();
-        cc_lin_tile_load(tin + (((k >> 5) + 1) & 1) * CC_LIN_TILE, p.in, b0, nact, T, T, (k >> 5) + 1, lane);
+        waited = issued;
       }
-      for (int i = 0; i < I; ++i) {
-        float u = 0.f;
-        if (j < nst) {
-          if (stg) u = tin[((k >> 5) & 1) * CC_LIN_TILE + lane * 33 + (k & 31)];
-          else if (act) u = __ldg(p.in + b * (long long)T * I + (long long)k * I + i);
+    }
+#pragma unroll
+    for (int t = 0; t < CC_LIN_MAXM; ++t) {
+      uval[t] = 0.f;
+      if (t < nst * I) {
+        const int k = k0 + t;  // (staged path: I = 1, slot t = step t)
+        if (stg) {
+          uval[t] = cc_ut(M.ut, M.u_scale, tin[((k >> 5) & 1) * CC_LIN_TILE + lane * 33 + (k & 31)]);
+        } else if (act) {
+          uval[t] = cc_ut(M.ut, M.u_scale, __ldg(p.in + b * (long long)T * I + (long long)k0 * I + t));
         }
-        cc_lin_store_split1(tm, CC_LIN_SLOT(j * I + i), j < nst ? cc_ut(M.ut, M.u_scale, u) : 0.f);
       }
+    }
+    if (stg && issued == cB + 1 && 32 * (cB + 1) < T && ((k0 + nst) >> 5) == cB) {
+      // keep one chunk of copies in flight: chunk cB + 1 goes into the slot of chunk cB - 1, which every lane has finished reading
+      // (only once the block lies inside chunk cB; a block that ends on the boundary loads the next chunk on demand)
+      __syncwarp();
+      cc_lin_tile_load(tin + (issued & 1) * CC_LIN_TILE, p.in, b0, nact, T, T, issued, lane);
+      ++issued;
+    }
+    {
+      float arr[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int c = 48 + i, t = 62 - c;
+        float v = c == CC_LIN_ONE ? 1.f : 0.f;
+        if (t >= 0 && t < CC_LIN_MAXM) v = uval[t < 0 ? 0 : (t < CC_LIN_MAXM ? t : 0)];
+        if constexpr (NCH >= 7) {
+          if (c < 8 * NCH) v = c < S ? x[c < 8 * NCH ? c : 0] : v;
+        }
+        arr[i] = v;
+      }
+      cc_lin_store_split<16>(tm, 48, arr);
     }
     cc_lin_round(tm);
     cc_lin_await(tm);
@@ -99,16 +132,22 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_ol_fwd_kernel(const 
           const float y = d[14 - t];
           if (stg) {
             const int k = k0 + t;  // O = 1: slot t = step t
-            tout[lane * 33 + (k & 31)] = y;
-            if ((k & 31) == 31 || k == T - 1) {
-              __syncwarp();
-              cc_lin_tile_store(tout, p.out + 1, b0, nact, T + 1, T, k >> 5, lane);  // (+1: row k+1; the row stride is T+1)
-              __syncwarp();
-            }
+            tout[((k >> 5) & 1) * CC_LIN_TILE + lane * 33 + (k & 31)] = y;
           } else if (act) {
             p.out[b * (long long)(T + 1) * O + (long long)(k0 + 1) * O + t] = y;
           }
         }
+      }
+    }
+    if (stg) {  // an output chunk is complete when the block passes its last step (or the end): one coalesced tile store
+      const int kl = k0 + nst - 1, c0 = k0 >> 5, c1 = kl >> 5;
+      const bool end1 = (kl & 31) == 31 || kl == T - 1;
+      const bool flush0 = c1 != c0 || end1, flush1 = c1 != c0 && end1;
+      if (flush0) {
+        __syncwarp();
+        cc_lin_tile_store(tout + (c0 & 1) * CC_LIN_TILE, p.out + 1, b0, nact, T + 1, T, c0, lane);  // (+1: row k+1; row stride T+1)
+        if (flush1) cc_lin_tile_store(tout + (c1 & 1) * CC_LIN_TILE, p.out + 1, b0, nact, T + 1, T, c1, lane);
+        __syncwarp();
       }
     }
     if (k0 + m >= T && p.x_final && p.lin_mt > 0) {
@@ -142,7 +181,8 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 2) cc_lin_ol_fwd_kernel(const 
 #define CC_LINW_COL_Q2 320   // Q accumulator, B = X_lo
 #define CC_LINW_OPA 8448     // float offset of operand A (Lam hi rows 0..63, lo rows 64..127): 16 row groups x 1152 floats
 #define CC_LINW_OPB (CC_LINW_OPA + 16 * 1152)   // operand B (X hi rows 0..63, lo rows 64..127)
-#define CC_LINW_SMEM_FLOATS (CC_LINW_OPB + 16 * 1152 + 64)
+#define CC_LINW_STG (CC_LINW_OPB + 16 * 1152 + 64)   // cp.async staging of the NEXT block's loads: [x_k (64) ; ybar slots (13) ; u slots (13)][128 threads]
+#define CC_LINW_SMEM_FLOATS (CC_LINW_STG + 90 * 128)
 // float offset of operand row r (the thread's trajectory part is added separately): core matrix = 8 rows x 4 trajectories
 // (128 B) padded to 144 B so that the 32 four-byte stores of a warp hit 32 banks
 CC_DEV constexpr int cc_linw_row(int r) { return (r >> 3) * 1152 + (r & 7) * 4; }
@@ -304,26 +344,32 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 1) cc_linw_bwd_kernel(const CC
 #pragma unroll
   for (int i = 0; i < 64; ++i) qsum[i] = 0.f;
   const int nblk = (T + m - 1) / m;
+  float* stg_ = cc_smem + CC_LINW_STG + tid;  // (behind the operand buffers incl. their alignment shift of < 32 floats)
+  auto prefetch_blk = [&](int bk) {
+    if (bk >= 0 && act) {
+      const int kb = bk * m;
+      const int ns = T - kb < m ? T - kb : m;
+      const float* tp = p.tape + ((long long)bk * S) * p.Bpad + b;
+      for (int i = 0; i < S; ++i) cc_lin_cp4(stg_ + i * 128, tp + (long long)i * p.Bpad);
+      for (int t = 0; t < ns * O; ++t) cc_lin_cp4(stg_ + (64 + t) * 128, p.ybar + b * yrow + (long long)(kb + 1) * O + t);  // row k+1 <-> step k
+      for (int t = 0; t < ns * I; ++t) cc_lin_cp4(stg_ + (77 + t) * 128, p.in + b * (long long)T * I + (long long)kb * I + t);
+    }
+    cc_lin_cp_commit();
+  };
+  prefetch_blk(nblk - 1);
   bool pending = false;  // a Q batch is in flight / its result not yet flushed
   for (int blk = nblk - 1; blk >= 0; --blk) {
     const int k0 = blk * m;
     const int nst = T - k0 < m ? T - k0 : m;
     // ---- gather this block's operands: Lam = [mu_E ; w slots], X = [x_k ; u~ slots ; 1] ----
-    float xk[64];
-    {
-      const float* tp = p.tape + ((long long)blk * S) * p.Bpad + b;
-#pragma unroll
-      for (int i = 0; i < 64; ++i) xk[i] = (i < S && act) ? tp[(long long)i * p.Bpad] : 0.f;
-    }
+    // this block's loads were issued (cp.async) while the previous block was processed: global latency is covered
+    cc_lin_cp_wait_all();
     float wv[CC_LIN_MAXM], uv[CC_LIN_MAXM], uraw[CC_LIN_MAXM];
 #pragma unroll
     for (int t = 0; t < CC_LIN_MAXM; ++t) {
-      wv[t] = 0.f; uv[t] = 0.f; uraw[t] = 0.f;
-      if (t < nst * O && act) wv[t] = __ldg(p.ybar + b * yrow + (long long)(k0 + 1) * O + t);   // row k+1 <-> step k
-      if (t < nst * I && act) {
-        uraw[t] = __ldg(p.in + b * (long long)T * I + (long long)k0 * I + t);
-        uv[t] = cc_ut(M.ut, M.u_scale, uraw[t]);
-      }
+      wv[t] = (t < nst * O && act) ? stg_[(64 + t) * 128] : 0.f;
+      uraw[t] = (t < nst * I && act) ? stg_[(77 + t) * 128] : 0.f;
+      uv[t] = (t < nst * I && act) ? cc_ut(M.ut, M.u_scale, uraw[t]) : 0.f;
     }
     // the previous block's Q batch must have read the operand buffers before they are rewritten; flush its result
     if (pending) {
@@ -342,23 +388,36 @@ __global__ void __launch_bounds__(CC_LIN_THREADS, 1) cc_linw_bwd_kernel(const CC
       }
 #endif
     }
-    // TMEM A operand: state chunks = mu (already there from the previous advance, zeros for the first block); w slots
+    // TMEM A operand: state chunks = mu (already there from the previous advance, zeros for the first block); the w slots
+    // with ONE 16-column store of columns 48..63 (state columns below S keep mu)
+    {
+      float arr[16];
 #pragma unroll
-    for (int t = 0; t < CC_LIN_MAXM; ++t)
-      if (t < m * O) cc_lin_store_split1(tm, CC_LIN_SLOT(t), wv[t]);  // (slot 12 = column 50 is a STATE column when S = 51)
-    // shared-memory operands (K = trajectory): Lam rows / X rows, hi and lo parts
+      for (int i = 0; i < 16; ++i) {
+        const int c = 48 + i, t = 62 - c;
+        float v = 0.f;
+        if (t >= 0 && t < CC_LIN_MAXM) v = wv[t < 0 ? 0 : (t < CC_LIN_MAXM ? t : 0)];
+        arr[i] = c < S ? mu[c] : v;
+      }
+      cc_lin_store_split<16>(tm, 48, arr);
+    }
+    // shared-memory operands (K = trajectory): Lam rows / X rows, hi and lo parts; x_k streams from the tape (block-start state)
 #pragma unroll
     for (int i = 0; i < 64; ++i) {
-      float lamv = mu[i], xv = xk[i];
-      if (i >= 50 && i <= 62) {  // slot columns
+      float lamv = mu[i], xv = 0.f;
+      if (i < 50) {
+        if (i < S && act) xv = stg_[i * 128];
+      } else if (i <= 62) {  // slot columns
         lamv = i < S ? lamv : wv[62 - i];
-        xv = i < S ? xv : uv[62 - i];
+        xv = i < S ? (act ? stg_[i * 128] : 0.f) : uv[62 - i];
+      } else {
+        lamv = 0.f; xv = 1.f;
       }
-      if (i == CC_LIN_ONE) { lamv = 0.f; xv = 1.f; }
       const float lh = cc_lin_tf32(lamv), xh = cc_lin_tf32(xv);
       oa[cc_linw_row(i)] = lh; oa[cc_linw_row(64 + i)] = lamv - lh;
       ob[cc_linw_row(i)] = xh; ob[cc_linw_row(64 + i)] = xv - xh;
     }
+    prefetch_blk(blk - 1);  // (the staging buffer has been consumed)
     cc_linw_round(tm, qs, true);
     pending = true;
     cc_lin_await(tm);
