@@ -51,12 +51,15 @@ int num_sms() {
 #ifdef CC_EMULATE
   return 148;
 #else
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  static int cache[64] = {0};  // per device: the plan is made for the CURRENT device (the one the launch goes to)
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (!cache[dev]) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev] = n;
   }
-  return n;
+  return cache[dev];
 #endif
 }
 
@@ -437,7 +440,7 @@ int make_plan(const CcModule* const* mods, int n_nodes, long long B, int T, cons
       p->n_wtiles = (B + 127) / 128;  // one gradient record per CTA
       const int head = (int)((sizeof(CcKParams) + 15) / 16 * 4);
       p->tc_off = (head + 15) / 16 * 16;
-      p->tc_stagger = getenv("CC_B200_TCW_DEBUG") ? atoi(getenv("CC_B200_TCW_DEBUG")) : 0;  // (profiling switches, scratch)
+      p->tc_stagger = 0;  // (a clock-stagger count in the other tcgen05 kernels; unused here)
       const int SR = 8 * nch;
       const long long bytes = ((long long)p->tc_off + 2LL * SR * p->tc_NP + 2LL * SR * ((SR + 15) / 16 * 16) + CC_TINY_O * (SR + 4) + 40 + 2LL * 16 * 1152) * 4;
       if (bytes > kSmemBudget) return fail(CC_ERR_UNSUPPORTED, "tcgen05 weight-gradient kernel: %lld B of shared memory per CTA", bytes);

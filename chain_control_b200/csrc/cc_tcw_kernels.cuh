@@ -25,6 +25,13 @@
 //   * operand layout: no swizzle, core matrix = 8 rows x 4 trajectories (128 B) padded to 144 B: thread t writes 4 bytes at
 //     (t/4)*144 + (t%4)*4 + row offset -> conflict-free stores; LBO = 144 B, SBO = 32*144 B.
 #pragma once
+// Ablation switches used for the round-1 timeline (skip the weight-gradient MMAs / the operand flush: WRONG gradients).
+// Compile-time only (-DCC_TCW_PROFILE=<bits>); a product build has them folded to 0.
+#ifdef CC_TCW_PROFILE
+#define CC_TCW_SKIP(bit) ((CC_TCW_PROFILE) & (bit))
+#else
+#define CC_TCW_SKIP(bit) 0
+#endif
 #include "cc_tc_kernels.cuh"
 
 #define CC_TCW_THREADS 384  // 3 warpgroups: adjoint chain, recompute chain, MMA issue (warp 8; setmaxnreg moves its registers to the workers)
@@ -266,7 +273,7 @@ __global__ void __launch_bounds__(CC_TCW_THREADS, 1) cc_tcw_bwd_kernel(const CC_
           const bool adj = j < T, fwd = j >= 1 && w < 3;
           cc_tcw_issue_af<NCH>(tbase, wbh_u, wbl_u, wfh_u, wfl_u, adj, fwd);
           cc_tc_commit(d_ready);
-          if (adj && !(p.tc_stagger & 1)) cc_tcw_issue_w(tbase, opa_u, opb_u, w == 0 ? 0u : 1u);
+          if (adj && !CC_TCW_SKIP(1)) cc_tcw_issue_w(tbase, opa_u, opb_u, w == 0 ? 0u : 1u);
           cc_tc_commit(w_done);
         }
         __syncwarp();
@@ -362,7 +369,7 @@ __global__ void __launch_bounds__(CC_TCW_THREADS, 1) cc_tcw_bwd_kernel(const CC_
           }
         }
         before_store();
-        if (on && !(p.tc_stagger & 2)) {
+        if (on && !CC_TCW_SKIP(2)) {
           if (w == 0 && j < T - 1) flush(0);
           if (w == 0 || w == 3) {
 #pragma unroll
@@ -460,7 +467,7 @@ __global__ void __launch_bounds__(CC_TCW_THREADS, 1) cc_tcw_bwd_kernel(const CC_
           for (int i = 0; i < CC_TINY_O; ++i) vdut[i] = vch[i];
         }
         if (!first) await_w();
-        if (duty && !(p.tc_stagger & 2)) {
+        if (duty && !CC_TCW_SKIP(2)) {
           if (w == 0) {
             if (j < T - 1) flush(32);
 #pragma unroll

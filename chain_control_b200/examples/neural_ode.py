@@ -107,6 +107,8 @@ class _NeuralOdeBase:
         self.theta = theta
         self.state = state            # (x[S] tensor, t float)
         self.init_state = init_state
+        # decided once (host sync here, not on every train step): the kernels skip the x0 load for the all-zero initial state
+        self._x0_nonzero = bool(torch.any(init_state[0] != 0))
         self._out_struct = out_struct
         self._post = make_postprocess_fn(out_struct)
 
@@ -176,7 +178,7 @@ class NeuralOdeModel(_NeuralOdeBase, AbstractModel):
         Differentiable w.r.t. the model's flat parameter vector (BPTT kernel)."""
         u = batch_concat(inputs, 2).to(self.theta.device, torch.float32)
         x0, t0 = self.init_state
-        x0b = None if not bool(torch.any(x0 != 0)) else x0.to(u.device).expand(u.shape[0], -1).contiguous()
+        x0b = None if not self._x0_nonzero else x0.to(u.device).expand(u.shape[0], -1).contiguous()
         spec = self.spec if t0 == self.spec.t0 else self._spec_at_state()
         y = ops.batched_unroll(spec, self.theta, u.contiguous(), x0b)
         if not include_y0:

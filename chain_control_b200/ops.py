@@ -39,6 +39,25 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def _on_device(fn):
+    """every tensor argument must live on ONE CUDA device; the call runs with that device current, so the kernels launch
+    on its current stream (tensors on cuda:1 while cuda:0 is current would otherwise launch on GPU 0 with GPU 1 pointers)"""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        devs = {a.device for a in list(args) + list(kwargs.values()) if isinstance(a, torch.Tensor) and a.is_cuda}
+        if len(devs) > 1:
+            raise ValueError(f"{fn.__name__}: tensors on different devices {sorted(map(str, devs))}")
+        if not devs:
+            return fn(*args, **kwargs)  # _check raises the no-CPU-path error
+        with torch.cuda.device(next(iter(devs))):
+            return fn(*args, **kwargs)
+
+    return wrapped
+
+
+@_on_device
 def rollout_fwd(spec: NodeSpec, theta, u, x0=None, *, want_tape=False, ckpt_every=1, want_x_final=False):
     """u[B,T,I] -> y[B,T+1,O]  (AbstractModel.unroll with include_y0=True, vmapped over B)."""
     L = _lib.lib()
@@ -63,6 +82,7 @@ def rollout_fwd(spec: NodeSpec, theta, u, x0=None, *, want_tape=False, ckpt_ever
     return y, xf, tape
 
 
+@_on_device
 def closedloop_fwd(cspec: NodeSpec, mspec: NodeSpec, theta_c, theta_m, refs, noise=None, *, want_tape=False,
                    ckpt_every=1, want_u=False):
     """refs[B,Tr,R] -> yhat[B,Tr,O]  (AbstractController.unroll closed loop, vmapped over B)."""
@@ -89,6 +109,7 @@ def closedloop_fwd(cspec: NodeSpec, mspec: NodeSpec, theta_c, theta_m, refs, noi
     return yhat, us, tape
 
 
+@_on_device
 def rollout_bwd(spec: NodeSpec, theta, u, tape, ybar, x0=None, *, ckpt_every=1, want_ubar=False):
     """VJP of rollout_fwd: ybar[B,T+1,O] -> theta_bar[P] (and ubar[B,T,I])."""
     L = _lib.lib()
@@ -108,6 +129,7 @@ def rollout_bwd(spec: NodeSpec, theta, u, tape, ybar, x0=None, *, ckpt_every=1, 
     return tb, ub
 
 
+@_on_device
 def closedloop_bwd(cspec: NodeSpec, mspec: NodeSpec, theta_c, theta_m, refs, tape, ybar, noise=None, *, ckpt_every=1):
     """VJP of closedloop_fwd w.r.t. the controller parameters: ybar[B,Tr,O] -> theta_c_bar[P_c]."""
     L = _lib.lib()
@@ -127,6 +149,7 @@ def closedloop_bwd(cspec: NodeSpec, mspec: NodeSpec, theta_c, theta_m, refs, tap
     return tb
 
 
+@_on_device
 def mse_value_and_cotangent(y, yhat, n_total: Optional[int] = None):
     """default loss of the trainers (cc/utils/utils.py:53-55) fused with its cotangent:
     returns (loss[1] = sum((yhat-y)^2)/n_total over THIS shard, ybar = 2 (yhat-y)/n_total)."""
@@ -157,9 +180,12 @@ class FusedAdam:
 
     def step(self, grad: torch.Tensor, grad_scale: float = 1.0):
         L = _lib.lib()
+        if grad.device != self.theta.device:
+            raise ValueError(f"grad on {grad.device}, parameters on {self.theta.device}")
         grad = _check(grad, "grad", tuple(self.theta.shape))
-        rc = L.cc_opt_step(_ptr(self.theta), _ptr(self.mu), _ptr(self.nu), _ptr(grad), _ptr(self.count), _ptr(self.out),
-                           self.theta.numel(), *[C.c_float(v) for v in self.hp], C.c_float(grad_scale), _stream())
+        with torch.cuda.device(self.theta.device):
+            rc = L.cc_opt_step(_ptr(self.theta), _ptr(self.mu), _ptr(self.nu), _ptr(grad), _ptr(self.count), _ptr(self.out),
+                               self.theta.numel(), *[C.c_float(v) for v in self.hp], C.c_float(grad_scale), _stream())
         L.check(rc, "cc_opt_step")
         return self.theta
 

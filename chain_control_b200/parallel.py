@@ -46,7 +46,10 @@ class HostFeed:
     waiting is hidden.  Usage:
         feed = HostFeed(device); feed.push(host_batch)            # before the loop
         for ...:  x = feed.pop(); feed.push(next_host_batch); step(x)
-    The device buffers are reused (two slots), so `pop()`ed tensors are valid until the second-next `push`."""
+    The device buffers are reused (two slots), so `pop()`ed tensors are valid until the second-next `push`.
+    Slot reuse is ordered automatically: `push` makes its copy wait for everything queued on the compute stream so far,
+    i.e. for the step that read the slot two pushes ago (in the loop above that step is already queued when `push` runs, and
+    the step that overlaps the copy -- step(x) -- is queued after it)."""
 
     def __init__(self, device):
         import torch
@@ -66,9 +69,12 @@ class HostFeed:
         self.head ^= 1
         if self.slots[s] is None or self.slots[s].shape != host_tensor.shape or self.slots[s].dtype != host_tensor.dtype:
             self.slots[s] = torch.empty(host_tensor.shape, dtype=host_tensor.dtype, device=self.device)
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream(self.device))  # every consumer of this slot queued so far
         with torch.cuda.stream(self.stream):
+            self.stream.wait_event(done)
             if self.free[s] is not None:
-                self.stream.wait_event(self.free[s])  # the kernels that read this slot two steps ago have finished
+                self.stream.wait_event(self.free[s])
             self.slots[s].copy_(host_tensor, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.stream)
@@ -83,7 +89,8 @@ class HostFeed:
         return self.slots[s]
 
     def release(self):
-        """call after the step that consumed the last `pop()`ed tensor has been queued on the current stream"""
+        """optional (push orders slot reuse by itself): marks the last `pop()`ed slot free once the work queued on the
+        current stream so far has finished, for consumers running on OTHER streams than the one `push` is called from"""
         ev = self.torch.cuda.Event()
         ev.record(self.torch.cuda.current_stream(self.device))
         self.free[self._last] = ev

@@ -2,9 +2,11 @@
  * neural-ODE unroll and its reverse pass.  TEST INFRASTRUCTURE: the checker for the CUDA path and
  * the CPU baseline of bench.py ("kind": "port").  Never linked into libccb200.so.
  *
- * PARITY UNPINNED: the reference cannot be imported here (jax/equinox absent) and pins no numeric
- * value on this path; this port is validated against oracle/np_oracle.py (fp64), which in turn is
- * checked against torch autograd and finite differences (tests/test_oracle.py).
+ * PARITY PINNED BY REFERENCE EXECUTION: tests/test_golden.py requires the fp64 entry points of this
+ * file to reproduce, to 1e-9, outputs / losses / gradients obtained by executing the reference's own
+ * source files on a NumPy stand-in of jax/equinox (tests/golden/make_golden.py, refshim.py; fixtures
+ * tests/golden/*.npz).  Also validated against oracle/np_oracle.py, torch autograd and finite
+ * differences (tests/test_c_oracle.py, tests/test_oracle.py).
  *
  * Follows: cc/core/abstract.py:54-70,97-127; cc/examples/neural_ode_model.py:106-175;
  * neural_ode_controller.py:108-149; *_compact_example.py; nn_lib/integrate.py:1-28;

@@ -4,11 +4,18 @@ This module is the *oracle*: a CPU restatement of the reference algorithm, used 
 ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference``
 legs as the checker.  The product path (``chain_control_b200``) never imports it.
 
-PARITY UNPINNED: the reference's arithmetic lives in third-party packages that are not
-installable here (jax unpinned, equinox==0.9.0, optax, imt-tree-utils; reference ``setup.py:40-59``)
-and the reference's own tests pin no numeric value on this path (``cc/train/test_trainer.py:25-147``
-only checks that a step runs).  Ground truth is therefore this restatement evaluated in fp64,
-cross-checked by torch autograd and central finite differences (``tests/test_oracle.py``).
+PARITY PINNED BY REFERENCE EXECUTION (round 2): jax / equinox==0.9.0 / optax / imt-tree-utils (reference
+``setup.py:40-59``) are not installable here and the reference's own tests pin no numeric value on this path
+(``cc/train/test_trainer.py:25-147`` only checks that a step runs), so the golden vectors are GENERATED: the reference's
+own source files (cc/core/abstract.py, module_utils.py, cc/examples/*.py, nn_lib/*, cc/train/step_fn.py,
+cc/utils/utils.py) are imported from /root/reference and executed unmodified on a NumPy stand-in of that third-party
+layer (``tests/golden/refshim.py``; gradients = complex-step derivatives of the reference's ``loss_fn_model`` /
+``loss_fn_controller``), by the committed script ``tests/golden/make_golden.py`` -> ``tests/golden/*.npz``.
+``tests/test_golden.py`` requires this module and the C oracle (fp64) to reproduce those outputs, losses and
+gradients to 1e-9 (11 fixtures: compact/full models, time-variant, feed-through, Euler / no-integrate, two output leaves,
+observation noise, two-model mean, l1/l2 regularisers).  What the stand-in cannot pin: jax's threefry streams (weight init,
+the noise VALUES; the noise semantics are pinned with recorded draws) and fp32 rounding order inside XLA.
+Cross-checks that predate the fixtures: torch autograd and central finite differences (``tests/test_oracle.py``).
 
 Reference lines restated (all relative to /root/reference):
   * open-loop unroll      cc/core/abstract.py:54-70,  cc/core/module_utils.py:8-17

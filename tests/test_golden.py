@@ -1,0 +1,169 @@
+"""The oracle and the CUDA path against golden vectors produced by EXECUTING THE REFERENCE'S OWN SOURCE FILES
+(tests/golden/make_golden.py + refshim.py; fixtures tests/golden/*.npz are committed, nothing here reads /root/reference).
+
+CPU part (-m "not gpu"): oracle/np_oracle.py and oracle/cc_oracle.c in fp64 must reproduce the reference's outputs,
+loss and gradient to round-off (1e-9): this is what pins the oracle.
+GPU part (-m gpu): the product through the C ABI against the same fixtures at BASELINE.json's tolerances
+(outputs 1e-5 normwise, gradients 1e-4 L2-normwise, fp32 vs the fp64 fixture).
+"""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle as CO
+from oracle import np_oracle as O
+from cchelpers import TOL_GRAD, TOL_STATE, conv, l2rel, normwise
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+OPEN = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "open_*.npz")))
+CLOSED = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "closed_*.npz")))
+PIN = 1e-9  # fp64 oracle vs fp64 reference execution
+
+
+def load(name):
+    return np.load(os.path.join(GOLD, name + ".npz"))
+
+
+def spec_of(js):
+    return O.make_node(**json.loads(js))
+
+
+def regu_grad(theta, l1, l2):
+    """cotangent of step_fn.py:101-114 with l1_l2_regularisers (cc/utils/utils.py:40-47): l1*|θ|_1 + l2*|θ|_2"""
+    g = np.zeros_like(theta)
+    if l1:
+        g += l1 * np.sign(theta)
+    if l2:
+        g += l2 * theta / np.linalg.norm(theta)
+    return g
+
+
+def regu_value(theta, l1, l2):
+    return l1 * np.abs(theta).sum() + l2 * np.linalg.norm(theta)
+
+
+def test_fixtures_present():
+    assert len(OPEN) >= 6 and len(CLOSED) >= 4, (OPEN, CLOSED)
+
+
+@pytest.mark.parametrize("name", OPEN)
+@pytest.mark.parametrize("impl", ["numpy", "c"])
+def test_oracle_open_loop_pinned(name, impl):
+    g = load(name)
+    spec = spec_of(str(g["spec"]))
+    theta, u, tgt = g["theta"], g["u"], g["targets"]
+    assert theta.size == spec.n_params()  # flatten_module order and count (module_utils.py:20-24)
+    if impl == "numpy":
+        y, _ = O.rollout_fwd(spec, theta, u, np.float64)
+        tb, _ = O.rollout_bwd(spec, theta, u, O.mse_cotangent(tgt, y), np.float64)
+    else:
+        r = CO.rollout(spec, theta, u, dtype=np.float64)
+        y = r["y"]
+        tb = CO.rollout(spec, theta, u, ybar=O.mse_cotangent(tgt, y), dtype=np.float64)["theta_bar"]
+    assert normwise(y, g["y"]) < PIN
+    assert abs(O.mse(tgt, y) - float(g["train_mse"])) < PIN * max(1.0, float(g["train_mse"]))
+    l1, l2 = float(g["l1"]), float(g["l2"])
+    assert abs(O.mse(tgt, y) + regu_value(theta, l1, l2) - float(g["loss"])) < PIN * max(1.0, float(g["loss"]))
+    assert l2rel(tb + regu_grad(theta, l1, l2), g["theta_bar"]) < PIN
+
+
+def _closed_oracle(g, impl):
+    cspec = spec_of(str(g["cspec"]))
+    mspecs = {k: O.make_node(**v) for k, v in json.loads(str(g["mspecs"])).items()}
+    names = json.loads(str(g["model_names"]))
+    refs, thc = g["refs"], g["theta_c"]
+    assert thc.size == cspec.n_params()
+    tb, losses, yh = np.zeros_like(thc), [], {}
+    for n in names:
+        thm = g[f"theta_m__{n}"]
+        noise = g[f"noise__{n}"] if f"noise__{n}" in g.files else None
+        if impl == "numpy":
+            y, _ = O.closedloop_fwd(cspec, mspecs[n], thc, thm, refs, noise, np.float64)
+            # mean over models of the per-model mse (step_fn.py:42-46,256-271)
+            tb += O.closedloop_bwd(cspec, mspecs[n], thc, thm, refs, O.mse_cotangent(refs, y) / len(names), noise,
+                                   np.float64)
+        else:
+            y = CO.closedloop(cspec, mspecs[n], thc, thm, refs, noise=noise, dtype=np.float64)["yhat"]
+            tb += CO.closedloop(cspec, mspecs[n], thc, thm, refs, noise=noise,
+                                ybar=O.mse_cotangent(refs, y) / len(names), dtype=np.float64)["theta_c_bar"]
+        yh[n] = y
+        losses.append(O.mse(refs, y))
+    return thc, names, yh, losses, tb
+
+
+@pytest.mark.parametrize("name", CLOSED)
+@pytest.mark.parametrize("impl", ["numpy", "c"])
+def test_oracle_closed_loop_pinned(name, impl):
+    g = load(name)
+    thc, names, yh, losses, tb = _closed_oracle(g, impl)
+    for n, l in zip(names, losses):
+        assert normwise(yh[n], g[f"yhat__{n}"]) < PIN
+        assert abs(l - float(g[f"{n}_train_mse"])) < PIN * max(1.0, l)
+    l1, l2 = float(g["l1"]), float(g["l2"])
+    assert abs(np.mean(losses) + regu_value(thc, l1, l2) - float(g["loss"])) < PIN * max(1.0, float(g["loss"]))
+    assert l2rel(tb + regu_grad(thc, l1, l2), g["theta_c_bar"]) < PIN
+
+
+def _adam_clip_step(theta, grad, lr, clip, b1=0.9, b2=0.999, eps=1e-8):
+    """first step of optax.chain(clip_by_global_norm(clip), adam(lr)) (cc/train/test_trainer.py:55)"""
+    g = grad * (clip / max(np.linalg.norm(grad), clip))
+    m, v = (1 - b1) * g, (1 - b2) * g * g
+    return theta - lr * (m / (1 - b1)) / (np.sqrt(v / (1 - b2)) + eps)
+
+
+@pytest.mark.parametrize("name", OPEN + CLOSED)
+def test_fixture_optimizer_step_consistent(name):
+    g = load(name)
+    k = "theta" if name.startswith("open") else "theta_c"
+    after = _adam_clip_step(g[k], g[k + "_bar"], float(g["lr"]), float(g["clip"]))
+    assert l2rel(after, g[k + "_after"]) < 1e-12
+
+
+# ----------------------------------------------------------------------------------------------- GPU
+
+
+def _t(a, dev="cuda:0"):
+    import torch
+
+    return torch.tensor(np.asarray(a, np.float32), device=dev)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", OPEN)
+def test_cuda_open_loop_vs_reference_golden(name):
+    from chain_control_b200 import ops
+
+    g = load(name)
+    spec = conv(spec_of(str(g["spec"])))
+    theta, u, tgt = g["theta"], g["u"], g["targets"]
+    y, _, tape = ops.rollout_fwd(spec, _t(theta), _t(u), want_tape=True)
+    assert normwise(y.cpu().numpy(), g["y"]) < TOL_STATE
+    ybar = (2.0 / y.numel()) * (y - _t(tgt))
+    tb, _ = ops.rollout_bwd(spec, _t(theta), _t(u), tape, ybar)
+    tb = tb.cpu().numpy().astype(np.float64) + regu_grad(theta, float(g["l1"]), float(g["l2"]))
+    assert l2rel(tb, g["theta_bar"]) < TOL_GRAD
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CLOSED)
+def test_cuda_closed_loop_vs_reference_golden(name):
+    from chain_control_b200 import ops
+
+    g = load(name)
+    cspec = conv(spec_of(str(g["cspec"])))
+    mspecs = {k: conv(O.make_node(**v)) for k, v in json.loads(str(g["mspecs"])).items()}
+    names = json.loads(str(g["model_names"]))
+    refs, thc = g["refs"], g["theta_c"]
+    tb = np.zeros_like(thc)
+    for n in names:
+        thm = g[f"theta_m__{n}"]
+        noise = _t(g[f"noise__{n}"]) if f"noise__{n}" in g.files else None
+        yhat, _, tape = ops.closedloop_fwd(cspec, mspecs[n], _t(thc), _t(thm), _t(refs), noise=noise, want_tape=True)
+        assert normwise(yhat.cpu().numpy(), g[f"yhat__{n}"]) < TOL_STATE
+        ybar = (2.0 / (yhat.numel() * len(names))) * (yhat - _t(refs))
+        tb += ops.closedloop_bwd(cspec, mspecs[n], _t(thc), _t(thm), _t(refs), tape, ybar, noise=noise).cpu().numpy()
+    tb = tb + regu_grad(thc, float(g["l1"]), float(g["l2"]))
+    assert l2rel(tb, g["theta_c_bar"]) < TOL_GRAD
