@@ -27,8 +27,10 @@
 #include "cc_tn.cu"
 #undef CC_TN_VALUE
 #include "cc_lin.cu"
+#include "cc_mlp.cu"
 #else
 #include "cc_lin.h"
+#include "cc_mlp.h"
 #endif
 
 namespace {
@@ -152,6 +154,45 @@ bool lin_eligible(const CcModule* const* mods, int n_nodes, bool bwd) {
   (void)bwd;
   return false;
 #endif
+}
+
+int tile_width_for(int cpt);
+int node_max_cpt(const CcModule* m);
+// deep-MLP tcgen05 forward family (cc_mlp_kernels.cuh, family 5): open-loop forward of a model whose f is a deep MLP
+// (2..4 Linear layers) and whose g is one Linear layer, time-invariant, no feed-through, every width <= 128 (beyond 64 the
+// weights are streamed through a shared-memory ring, cc_mlp128_kernels.cuh).  Returns the padded width (16 / 32 / 64 / 128) or 0.  CC_B200_MLP=0 disables the family, =1 takes it at any batch size.
+int mlp_fwd_pad(const CcModule* m, long long B) {
+  const char* env = getenv("CC_B200_MLP");
+  if (env && atoi(env) == 0) return 0;
+  if (m->f.n_layers < 2 || m->g.n_layers != 1 || m->f_time_variant || m->g_time_variant || m->g_feedthrough_u) return 0;
+  if (m->input_dim < 1 || m->input_dim > CC_TINY_O || m->output_dim > CC_TINY_O) return 0;
+  int w = m->state_dim;
+  for (int l = 1; l <= m->f.n_layers; ++l)
+    if (m->f.sizes[l] > w) w = m->f.sizes[l];
+  const int pad = w <= 16 ? 16 : (w <= 32 ? 32 : (w <= 64 ? 64 : (w <= 128 ? 128 : 0)));
+  if (!pad || cc_mlp_smem_bytes(pad, m->f.n_layers) > (size_t)kSmemBudget) return 0;
+  // below ~8 tiles the autonomous-warp FFMA kernels (32 trajectories per warp, no CTA-wide round trips) are at least as fast
+  const bool ffma_can = tile_width_for(node_max_cpt(m)) != 0;
+  const long long minb = (env && atoi(env) == 1) ? 1 : (ffma_can ? 1024 : 1);
+  return B >= minb ? pad : 0;
+}
+void mlp_args(const CcModule* m, CcMlpArgs* a) {
+  memset(a, 0, sizeof(*a));
+  a->S = m->state_dim; a->I = m->input_dim; a->O = m->output_dim; a->L = m->f.n_layers;
+  int off = 0;
+  for (int l = 0; l < m->f.n_layers; ++l) {
+    CcMlpLayerArg& L = a->f[l];
+    L.in_log = m->f.sizes[l]; L.N = m->f.sizes[l + 1];
+    L.act = l < m->f.n_layers - 1 ? m->f.act : m->f.act_final;
+    L.w_off = off; off += L.in_log * L.N;
+    L.b_off = -1;
+    if (m->f.use_bias) { L.b_off = off; off += L.N; }
+  }
+  a->g.in_log = m->g.sizes[0]; a->g.N = m->g.sizes[1]; a->g.act = m->g.act_final;
+  a->g.w_off = off; off += a->g.in_log * a->g.N;
+  a->g.b_off = m->g.use_bias ? off : -1;
+  a->integrator = m->integrator; a->pre = m->readout_pre_step ? 1 : 0; a->ut = m->u_transform;
+  a->u_scale = m->u_scale; a->out_scale = m->out_scale; a->dt = m->dt;
 }
 
 struct Alloc {
@@ -606,6 +647,7 @@ int32_t cc_module_supported(const CcModule* m, int32_t with_grad) {
   PlanOpts o;
   o.bwd = with_grad != 0;
   const CcModule* mods[1] = {m};
+  if (!with_grad && mlp_fwd_pad(m, 65536)) return CC_OK;
   return make_plan(mods, 1, 65536, 1000, o, &p);
 }
 
@@ -616,6 +658,7 @@ int32_t cc_kernel_family_at(const CcModule* c, const CcModule* m, int32_t with_g
   int rc = validate_module(m, "model");
   if (rc) return rc;
   if (c && (rc = validate_module(c, "controller"))) return rc;
+  if (!c && !with_grad && mlp_fwd_pad(m, B)) return 5;
   CcKParams p;
   PlanOpts o;
   o.bwd = with_grad != 0;
@@ -653,6 +696,7 @@ size_t cc_rollout_fwd_workspace_bytes(const CcModule* m, int64_t B, int32_t T) {
   CcKParams p;
   PlanOpts o;
   const CcModule* mods[1] = {m};
+  if (const int pad = mlp_fwd_pad(m, B)) return cc_mlp_workspace_bytes(pad, m->f.n_layers);
   if (make_plan(mods, 1, B, T, o, &p)) return 0;
   return p.tc == 4 ? lin_pack_bytes() : 0;  // (the open-loop family does not depend on ckpt_every)
 }
@@ -675,6 +719,21 @@ int32_t cc_rollout_fwd(const CcModule* m, const float* theta, const float* u, co
   if (B < 0 || T < 0) return fail(CC_ERR_INVALID_ARG, "negative size");
   if (tape && ckpt_every < 1) return fail(CC_ERR_INVALID_ARG, "ckpt_every must be >= 1");
   if (B == 0) return CC_OK;
+  if (const int pad = mlp_fwd_pad(m, B)) {  // deep-MLP model: one tcgen05.mma batch per layer (cc_mlp_kernels.cuh)
+    CcMlpArgs a;
+    mlp_args(m, &a);
+    a.theta = theta; a.u = u; a.x0 = x0; a.y = y; a.x_final = x_final;
+    a.B = B; a.T = T; a.Bpad = (B + 31) / 32 * 32;
+    a.tape = (float*)tape;
+    a.ckpt_every = tape ? ckpt_every : 1;
+    a.ttab = tape ? (float*)tape + (long long)n_ckpt_of(T, a.ckpt_every) * m->state_dim * a.Bpad : nullptr;
+    const size_t need = cc_mlp_workspace_bytes(pad, a.L);
+    if (need && (!ws || ws_bytes < need)) return fail(CC_ERR_WORKSPACE, "workspace too small: need %zu bytes (cc_rollout_fwd_workspace_bytes)", need);
+    a.pack = need ? (float*)ws : nullptr;
+    g_launches.fetch_add(need ? 2 : 1);
+    if (getenv("CC_B200_VERBOSE")) fprintf(stderr, "[ccb200] deep-MLP tcgen05 plan: B=%lld T=%d pad=%d layers=%d smem=%zu B ctas=%lld\n", (long long)B, T, pad, a.L, cc_mlp_smem_bytes(pad, a.L), (long long)(B + 127) / 128);
+    return cc_launch_mlp_fwd(a, pad, stream, g_err, sizeof(g_err));
+  }
   CcKParams p;
   PlanOpts o;
   o.exact_end = x_final != nullptr;

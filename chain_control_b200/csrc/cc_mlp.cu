@@ -1,0 +1,82 @@
+// cc_mlp.cu -- translation unit of the deep-MLP tcgen05 forward family (cc_mlp_kernels.cuh); exposes cc_launch_mlp_fwd.
+// Also compiled (included by cc_abi.cu) into the CPU emulation of tests/emu.
+#ifndef CC_EMULATE
+#include <cuda_runtime.h>
+#endif
+#include <cstdio>
+
+#include "cc_mlp128_kernels.cuh"
+
+namespace {
+template <int PAD>
+int mlp_launch(const CcMlpArgs& a, void* stream, char* err, int errlen) {
+  using TM = CcMlpTm<PAD>;
+  const long long grid = (a.B + 127) / 128;
+#ifdef CC_EMULATE
+  (void)stream; (void)err; (void)errlen;
+  const size_t smem = ((size_t)CC_MLP_SMEM_FLOATS(PAD, a.L) + (size_t)TM::COLS * 128) * 4;
+  ccemu::launch((int)grid, CC_MLP_THREADS, smem, [&]() { cc_mlp_fwd_kernel<PAD>(a); });
+  return CC_OK;
+#else
+  const size_t smem = (size_t)CC_MLP_SMEM_FLOATS(PAD, a.L) * 4;
+  cudaError_t e = cudaFuncSetAttribute(cc_mlp_fwd_kernel<PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) {
+    cc_mlp_fwd_kernel<PAD><<<(unsigned)grid, CC_MLP_THREADS, smem, (cudaStream_t)stream>>>(a);
+    e = cudaGetLastError();
+  }
+  if (e != cudaSuccess) {
+    snprintf(err, errlen, "cc_mlp_fwd_kernel<%d> launch failed: %s", PAD, cudaGetErrorString(e));
+    return CC_ERR_CUDA;
+  }
+  return CC_OK;
+#endif
+}
+int mlp128_launch(const CcMlpArgs& a, void* stream, char* err, int errlen) {
+  const long long grid = (a.B + 127) / 128;
+  if (!a.pack) {
+    snprintf(err, errlen, "deep-MLP tcgen05 family (width > 64): workspace missing (cc_rollout_fwd_workspace_bytes)");
+    return CC_ERR_WORKSPACE;
+  }
+#ifdef CC_EMULATE
+  (void)stream;
+  ccemu::launch(2 * a.L, 256, 0, [&]() { cc_mlp128_prep_kernel(a); });
+  const size_t smem = ((size_t)CC_MLP128_SMEM_FLOATS + (size_t)CcMlpTm<128>::COLS * 128) * 4;
+  ccemu::launch((int)grid, CC_MLP128_WORKERS, smem, [&]() { cc_mlp128_fwd_kernel(a); });
+  return CC_OK;
+#else
+  const size_t smem = (size_t)CC_MLP128_SMEM_FLOATS * 4;
+  cc_mlp128_prep_kernel<<<2 * a.L, 256, 0, (cudaStream_t)stream>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(cc_mlp128_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) {
+    cc_mlp128_fwd_kernel<<<(unsigned)grid, CC_MLP128_THREADS, smem, (cudaStream_t)stream>>>(a);
+    e = cudaGetLastError();
+  }
+  if (e != cudaSuccess) {
+    snprintf(err, errlen, "cc_mlp128_fwd_kernel launch failed: %s", cudaGetErrorString(e));
+    return CC_ERR_CUDA;
+  }
+  return CC_OK;
+#endif
+}
+}  // namespace
+
+// shared memory of one CTA (bytes) for padded width `pad` and `L` layers: the plan checks it against the 227 KB budget
+size_t cc_mlp_smem_bytes(int pad, int L) {
+  if (pad == 128) return (size_t)CC_MLP128_SMEM_FLOATS * 4;  // (streamed weights: independent of L)
+  const size_t kp = (size_t)pad + 8;
+  return ((size_t)L * 2 * kp * pad + (size_t)CC_TINY_O * (pad + 4) + 8) * 4;
+}
+
+// global workspace: the pre-split weight chunks of the streamed (width 65..128) variant
+size_t cc_mlp_workspace_bytes(int pad, int L) { return pad == 128 ? (size_t)2 * L * CC_MLP128_CHUNK_BYTES : 0; }
+
+int cc_launch_mlp_fwd(const CcMlpArgs& a, int pad, void* stream, char* err, int errlen) {
+  switch (pad) {
+    case 16: return mlp_launch<16>(a, stream, err, errlen);
+    case 32: return mlp_launch<32>(a, stream, err, errlen);
+    case 64: return mlp_launch<64>(a, stream, err, errlen);
+    case 128: return mlp128_launch(a, stream, err, errlen);
+    default: snprintf(err, errlen, "deep-MLP tcgen05 family: padded width %d not built", pad); return CC_ERR_UNSUPPORTED;
+  }
+}

@@ -1,0 +1,34 @@
+// cc_mlp.h -- host/device interface of the deep-MLP tcgen05 forward family (cc_mlp_kernels.cuh, cc_mlp.cu).
+#pragma once
+#include <stddef.h>
+
+#include "../../include/cc_b200.h"
+
+struct CcMlpLayerArg {
+  int w_off, b_off;  // offsets into theta (b_off < 0: no bias)
+  int in_log, N;     // logical input / output width
+  int act;
+};
+struct CcMlpArgs {
+  int S, I, O, L;  // state / input / output dims, number of Linear layers of f (2..4)
+  CcMlpLayerArg f[CC_MAX_LAYERS];
+  CcMlpLayerArg g;  // readout Linear [O][S]
+  int integrator, pre, ut;
+  float u_scale, out_scale, dt;
+  const float* theta;
+  const float* u;   // [B][T][I]
+  const float* x0;  // [B][S] or null
+  float* y;         // [B][T+1][O]
+  float* x_final;   // [B][S] or null
+  float* tape;      // [n_ckpt][S][Bpad] pre-step states (the FFMA reverse pass reads them) or null
+  float* ttab;      // [2][T] step times behind the tape
+  float* pack;      // (widths 65..128) the pre-split weight chunks in the workspace, cc_mlp128_kernels.cuh
+  int ckpt_every;
+  long long B, Bpad;
+  int T;
+};
+
+
+size_t cc_mlp_smem_bytes(int pad, int L);
+size_t cc_mlp_workspace_bytes(int pad, int L);
+int cc_launch_mlp_fwd(const CcMlpArgs& a, int pad, void* stream, char* err, int errlen);

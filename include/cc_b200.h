@@ -82,7 +82,9 @@ int64_t cc_param_count(const CcModule* m);
 /* 0 if the kernels support this module (with_grad: also the BPTT kernels), else a CcStatus */
 int32_t cc_module_supported(const CcModule* m, int32_t with_grad);
 
-/* which kernel family the plan picks for this call (deterministic, from the architecture only):
+/* which kernel family the plan picks for this call (deterministic, from the architecture and the batch size only):
+ * 5 = deep-MLP tcgen05 forward kernels (f with 1..3 hidden layers of width <= 64: one tcgen05.mma batch per layer,
+ * chain_control_b200/csrc/cc_mlp_kernels.cuh; open-loop forward only),
  * 4 = blocked linear kernels (linear depth-0 model: m integrator steps per tcgen05.mma batch, chain_control_b200/csrc/cc_lin.h),
  * 3 = tcgen05 reverse pass with a tensor-core weight gradient, 2 = latency kernels (depth-0 model, small batch: one warp
  * per trajectory), 1 = tcgen05 kernels (depth-0 model: stage evaluations as tcgen05.mma batches, 3xTF32), 0 = FFMA kernels,

@@ -67,3 +67,26 @@ def tc_open_model_variants():
     v["compact_s20_d0_i2_o3"] = O.make_node(20, 2, 3, f_depth=0, readout_pre_step=True, u_transform=O.UT_ARCTAN)
     v["compact_s44_d0_o2_nobias"] = O.make_node(44, 1, 2, f_depth=0, readout_pre_step=True, f_use_bias=False, g_use_bias=False)
     return v
+
+
+def mlp_model_variants():
+    """deep-MLP models: the architectures the deep-MLP tcgen05 forward family (cc_mlp_kernels.cuh) takes over."""
+    v = {}
+    v["full_s5_w10_d2"] = model_variants()["full_s5_w10_d2"]          # defaults of make_neural_ode_model -> PAD 16
+    v["euler_s9"] = model_variants()["euler_s9"]                      # explicit Euler, tanh hidden activation -> PAD 16
+    # BASELINE configs[2] sweep (32,32,2) with two inputs / three outputs, arctan input transform -> PAD 32
+    v["full_s32_w32_d2_i2_o3"] = O.make_node(32, 2, 3, f_width=32, f_depth=2, u_transform=O.UT_ARCTAN)
+    # compact (pre-step readout), three hidden layers, tanh final activation, f without bias -> PAD 64
+    v["compact_s40_w64_d3_tanh_nobias"] = O.make_node(40, 1, 1, f_width=64, f_depth=3, f_act_final=O.ACT_TANH,
+                                                      readout_pre_step=True, f_use_bias=False)
+    # no-integrate (discrete-time map), one hidden layer, k*tanh input transform -> PAD 32
+    v["noint_s7_w20_d1"] = O.make_node(7, 1, 2, f_width=20, f_depth=1, integrator=O.INT_NONE, f_act=O.ACT_TANH,
+                                       f_act_final=O.ACT_TANH, u_transform=O.UT_KTANH, u_scale=3.0)
+    # configs[2] sweep (64,64,2): the FFMA reverse pass does not fit this one; forward only
+    v["full_s64_w64_d2"] = O.make_node(64, 1, 1, f_width=64, f_depth=2)
+    # configs[2] sweep (128,128,2): weights streamed through the shared-memory ring (cc_mlp128_kernels.cuh); forward only
+    v["full_s128_w128_d2"] = O.make_node(128, 1, 1, f_width=128, f_depth=2, f_act_final=O.ACT_TANH)
+    # widths that are not multiples of 64, two inputs / two outputs, compact readout, one hidden layer, Euler
+    v["compact_s70_w100_d1_i2_o2"] = O.make_node(70, 2, 2, f_width=100, f_depth=1, integrator=O.INT_EE, readout_pre_step=True,
+                                                 f_act=O.ACT_TANH, u_transform=O.UT_ARCTAN)
+    return v

@@ -253,3 +253,34 @@ def test_emu_fused_optimiser_step(hp):
         assert count[0] == t
         np.testing.assert_allclose(theta, th64, rtol=2e-6, atol=2e-7)
         np.testing.assert_allclose(mu, mu64, rtol=1e-5, atol=1e-8)
+
+
+@pytest.mark.parametrize("name", ["full_s5_w10_d2", "euler_s9", "full_s32_w32_d2_i2_o3", "noint_s7_w20_d1", "compact_s40_w64_d3_tanh_nobias",
+                                  "full_s128_w128_d2", "compact_s70_w100_d1_i2_o2"])
+def test_emu_mlp_family_fwd(name, monkeypatch):
+    """deep-MLP tcgen05 forward family (cc_mlp_kernels.cuh) on the CPU emulation of its TMEM / MMA layer: B = 133 (two tiles,
+    one ragged), outputs + final state + the tape against the fp64 oracle"""
+    import ctypes as C
+
+    from ccspecs import mlp_model_variants
+
+    monkeypatch.setenv("CC_B200_MLP", "1")
+    spec = mlp_model_variants()[name]
+    L = E.emu()
+    B, T = 133, (4 if spec.state_dim > 64 else 7)
+    assert L.cc_kernel_family_at(None, C.byref(conv(spec).to_c()), 0, B) == 5
+    theta = O.init_params(spec, 1).astype(np.float32)
+    u = 1.5 * _u(B, T, spec.input_dim)
+    x0 = (0.1 * np.random.default_rng(3).normal(size=(B, spec.state_dim))).astype(np.float32)
+    y64, xs = O.rollout_fwd(spec, theta, u, x0=x0)
+    # trajectories whose outputs nearly cancel put the fp32 oracle itself above 1e-5 in the normwise metric (wide layers):
+    # the kernel has to stay within 3x of that floor
+    floor = normwise(O.rollout_fwd(spec, theta, u, x0=x0, dtype=np.float32)[0], y64)
+    y, xf, tape = E.np_rollout_fwd(L, conv(spec), theta, u, x0, tape_every=3)
+    assert normwise(y, y64) < max(TOL_STATE, 3 * floor), floor
+    assert normwise(xf, xs[:, -1]) < TOL_STATE
+    Bpad, S = (B + 31) // 32 * 32, spec.state_dim
+    nck = (T + 2) // 3
+    rec = tape[: nck * S * Bpad].reshape(nck, S, Bpad)[:, :, :B]  # checkpoints at steps 0, 3, 6: the pre-step states
+    for c, k in enumerate(range(0, T, 3)):
+        assert normwise(rec[c].T, xs[:, k]) < TOL_STATE

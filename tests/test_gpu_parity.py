@@ -10,7 +10,8 @@ import numpy as np
 import pytest
 
 from cchelpers import TOL_GRAD, TOL_STATE, conv, l2rel, normwise
-from ccspecs import controller_variants, model_variants, tc_controller_variants, tc_model_variants, tc_open_model_variants
+from ccspecs import (controller_variants, mlp_model_variants, model_variants, tc_controller_variants, tc_model_variants,
+                     tc_open_model_variants)
 from oracle import c_oracle as CO
 from oracle import np_oracle as O
 
@@ -524,3 +525,42 @@ def test_full_size_gradient_vs_oracle(closed, T_):
         ref = CO.rollout(mspec, thm, x_sub, ybar=yb_sub, dtype=np.float64)
         assert normwise(y[torch.tensor(idx, device="cuda")].cpu().numpy(), ref["y"]) < TOL_STATE
         assert l2rel(g.cpu().numpy(), ref["theta_bar"]) < TOL_GRAD
+
+
+@pytest.mark.parametrize("name", list(mlp_model_variants()))
+@pytest.mark.parametrize("B,force", [(301, "1"), (2500, None)])
+def test_mlp_family_rollout_vs_oracle(name, B, force, T_, monkeypatch):
+    """deep-MLP tcgen05 forward family (cc_mlp_kernels.cuh): outputs, final state and the tape it leaves for the FFMA
+    reverse pass against the fp64 oracle; B = 301 (3 tiles, ragged) forced, B = 2500 as the default plan picks it"""
+    import ctypes as C
+
+    from chain_control_b200 import _lib, ops
+
+    if force:
+        monkeypatch.setenv("CC_B200_MLP", force)
+    spec = mlp_model_variants()[name]
+    T = 60
+    assert _lib.lib().cc_kernel_family_at(None, C.byref(conv(spec).to_c()), 0, B) == 5
+    theta = O.init_params(spec, 1).astype(np.float32)
+    u = _u(B, T, spec.input_dim)
+    x0 = (0.1 * np.random.default_rng(3).normal(size=(B, spec.state_dim))).astype(np.float32)
+    ybar = np.random.default_rng(5).normal(size=(B, T + 1, spec.output_dim)).astype(np.float32)
+    wide = max(spec.f.sizes[1:]) > 32  # the FFMA reverse pass does not fit 64-wide deep MLPs
+    ref = CO.rollout(spec, theta, u, x0=x0, ybar=None if wide else ybar, dtype=np.float64)
+    # trajectories whose outputs nearly cancel put the fp32 oracle itself near / above 1e-5 in the normwise metric for the
+    # wide layers: the kernel has to stay within 3x of that floor (observed floors: profiles/r02_parity_floors.md)
+    floor = normwise(CO.rollout(spec, theta, u, x0=x0, dtype=np.float32)["y"], ref["y"])
+    y, xf, tape = ops.rollout_fwd(conv(spec), T_(theta), T_(u), T_(x0), want_tape=not wide, want_x_final=True)
+    assert normwise(y.cpu().numpy(), ref["y"]) < max(TOL_STATE, 3 * floor), floor
+    xs = O.rollout_fwd(spec, theta, u[:16], x0=x0[:16])[1]
+    assert normwise(xf.cpu().numpy()[:16], xs[:, -1]) < TOL_STATE
+    # the same call on the FFMA kernels: two independent implementations agree
+    monkeypatch.setenv("CC_B200_MLP", "0")
+    if max(spec.f.sizes[1:]) <= 64:  # (beyond 64 no other family exists)
+        y2, _, _ = ops.rollout_fwd(conv(spec), T_(theta), T_(u), T_(x0))
+        assert normwise(y2.cpu().numpy(), y.cpu().numpy()) < max(TOL_STATE, 3 * floor), floor
+    if not wide:  # BPTT (FFMA reverse kernel) from the tape the tcgen05 forward wrote
+        r32 = CO.rollout(spec, theta, u, x0=x0, ybar=ybar, dtype=np.float32)
+        floor = l2rel(r32["theta_bar"], ref["theta_bar"])
+        tb, _ = ops.rollout_bwd(conv(spec), T_(theta), T_(u), tape, T_(ybar), T_(x0))
+        assert l2rel(tb.cpu().numpy(), ref["theta_bar"]) < max(TOL_GRAD, 3 * floor), floor
