@@ -763,7 +763,6 @@ int32_t cc_closedloop_fwd(const CcModule* c, const CcModule* m, const float* the
   if (tape && ckpt_every < 1) return fail(CC_ERR_INVALID_ARG, "ckpt_every must be >= 1");
   if (c->output_dim != m->input_dim) return fail(CC_ERR_INVALID_ARG, "controller output_dim != model input_dim");
   if (c->input_dim <= m->output_dim) return fail(CC_ERR_INVALID_ARG, "controller input_dim must be ref_dim + model output_dim");
-  if (m->g_feedthrough_u) return fail(CC_ERR_UNSUPPORTED, "model with feed-through");
   if (B == 0 || Tr == 0) return CC_OK;
   CcKParams p;
   PlanOpts o;

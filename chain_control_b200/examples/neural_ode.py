@@ -190,6 +190,8 @@ class _ClosedLoopUnroll:
     """what controller.unroll(model, merge_x_y, noise_scale) returns (abstract.py:103-127)."""
 
     def __init__(self, controller, model, merge_x_y, noise_scale):
+        # the model is never trained inside a closed loop (step_fn.py:249-252): a LinearModel drops its trainable-D bookkeeping
+        model = model.frozen() if hasattr(model, "frozen") else model
         self.controller, self.model, self.merge_x_y, self.noise_scale = controller, model, merge_x_y, noise_scale
         probe = merge_x_y("ref", "obs")
         if list(probe.keys()) != ["ref", "obs"]:

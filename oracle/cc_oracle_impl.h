@@ -185,7 +185,11 @@ static void FN(fill_gin)(const CcModule* m, REAL* a0, const REAL* x, REAL t, con
     for (int j = 0; j < NB; ++j) a0[r * NB + j] = t;
     r++;
   }
-  if (m->g_feedthrough_u) memcpy(a0 + r * NB, v, sizeof(REAL) * (size_t)I * NB);
+  if (m->g_feedthrough_u) {
+    /* v == NULL: y0 of a model with feed-through, y0 = C x0 without the D u term (cc/examples/linear_model.py:81-82) */
+    if (v) memcpy(a0 + r * NB, v, sizeof(REAL) * (size_t)I * NB);
+    else memset(a0 + r * NB, 0, sizeof(REAL) * (size_t)I * NB);
+  }
 }
 
 /* x [S][NB] (updated in place), v [I][NB], out [O][NB]; cache: step_cache_rows*NB; tmp: 2*S*NB */

@@ -344,10 +344,11 @@ def node_step_bwd(spec: NodeSpec, fl, gl, c, out_bar, lam_next, fgrads, ggrads):
 
 
 def node_y0(spec: NodeSpec, gl, B, dtype, x0=None):
-    """y0(): g([x0;(0)]) (neural_ode_model.py:160-175).  feedthrough never applies to models."""
+    """y0(): g([x0;(0)]) (neural_ode_model.py:160-175).  A model with feed-through (LinearModel, y = C x + D u,
+    cc/examples/linear_model.py:66-82) has y0 = C x0: the input columns see zeros."""
     x = np.zeros((B, spec.state_dim), dtype) if x0 is None else x0
-    assert not spec.g_feedthrough_u
-    out, gc = mlp_fwd(spec.g, gl, _g_in(spec, x, dtype(0), None))
+    v0 = np.zeros((x.shape[0], spec.input_dim), dtype) if spec.g_feedthrough_u else None
+    out, gc = mlp_fwd(spec.g, gl, _g_in(spec, x, dtype(0), v0))
     return dtype(spec.out_scale) * out, gc
 
 

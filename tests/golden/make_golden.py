@@ -201,7 +201,7 @@ def build_controller(kind, S, R, Oobs, Im, f_depth=2, f_width=10, g_depth=0, g_w
 
 
 def closed_loop_case(name, controller, cspec, models, mspecs, B, Tr, seed, noise_scale=None, l1=0.0, l2=0.0,
-                     extra=None):
+                     extra=None, model_theta=None, ctrl_theta=None):
     """models: OrderedDict name -> reference model (all SISO with one output leaf)"""
     t0 = time.time()
     rng = np.random.default_rng(seed)
@@ -230,11 +230,12 @@ def closed_loop_case(name, controller, cspec, models, mspecs, B, Tr, seed, noise
     step, opt_state, mbs = ref_step.make_step_fn_controller(controller, models, options)  # step_fn.py:249-322
     new_c, _, _, logs = step(controller, opt_state, mbs)
     out = dict(kind="closed", cspec=json.dumps(cspec), mspecs=json.dumps(mspecs), model_names=json.dumps(list(models)),
-               theta_c=flat(flatten_module(controller)), refs=refs, loss=np.float64(np.real(logs["train_loss"])),
+               theta_c=(flat(flatten_module(controller)) if ctrl_theta is None else ctrl_theta),
+               theta_c_ref_order=flat(flatten_module(controller)), refs=refs, loss=np.float64(np.real(logs["train_loss"])),
                theta_c_bar=flat(opt.grads), theta_c_after=flat(flatten_module(new_c)), lr=opt.lr, clip=opt.clip,
                l1=l1, l2=l2, noise_scale=(0.0 if noise_scale is None else noise_scale))
     for mname, model in models.items():
-        out[f"theta_m__{mname}"] = flat(flatten_module(model))
+        out[f"theta_m__{mname}"] = flat(flatten_module(model)) if model_theta is None else model_theta[mname]
         out[f"yhat__{mname}"] = yhat[mname]
         out[f"{mname}_train_mse"] = np.float64(np.real(logs[f"{mname}_train_mse"]))
         if noise_scale is not None:
@@ -244,6 +245,74 @@ def closed_loop_case(name, controller, cspec, models, mspecs, B, Tr, seed, noise
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
     print(f"{name}: Pc={out['theta_c'].size} B={B} Tr={Tr} loss={out['loss']:.6f} "
           f"|g|={np.linalg.norm(out['theta_c_bar']):.4e}  ({time.time() - t0:.1f}s)", flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ LinearModel / PID
+
+
+def linear_perm(S, I, O):
+    """index array: kernel-order theta ([A|B] rows, then [C|D] rows) = reference-order flat ([A, B, C, D]) [perm]"""
+    oA, oB, oC, oD = 0, S * S, S * S + S * I, S * S + S * I + O * S
+    perm = []
+    for n in range(S):
+        perm += [oA + n * S + k for k in range(S)] + [oB + n * I + i for i in range(I)]
+    for o in range(O):
+        perm += [oC + o * S + k for k in range(S)] + [oD + o * I + i for i in range(I)]
+    return np.array(perm, dtype=np.int64)
+
+
+def build_linear(S, I, osz, continuous=True, seed=1, randomize_x0=False, zero_D=False, scale=0.3):
+    O = sum(osz)
+    m = make_linear_model(in_spec(I), out_spec(osz), DT, S, continuous_time=continuous, seed=seed, randomize_x0=randomize_x0)
+    A = m.A * scale - (np.eye(S) if continuous else 0.0)  # stable-ish dynamics
+    if not continuous:
+        A = 0.5 * m.A / np.max(np.abs(np.linalg.eigvals(m.A)))
+    D = np.zeros_like(m.D) if zero_D else m.D
+    m = eqx.tree_at(lambda mm: (mm.A, mm.D), m, (A, D))
+    m = round_params(m)
+    spec = node_kwargs(S, I, O, f_depth=0, f_use_bias=False, g_use_bias=False, integrator=(1 if continuous else 2),
+                       readout_pre_step=True, g_feedthrough_u=not zero_D)
+    return m, spec
+
+
+def linear_kernel_theta(m, spec):
+    """reference LinearModel -> flat vector in the kernels' order for `spec`"""
+    if spec["g_feedthrough_u"]:
+        return np.concatenate([np.concatenate([m.A, m.B], 1).ravel(), np.concatenate([m.C, m.D], 1).ravel()])
+    return np.concatenate([np.concatenate([m.A, m.B], 1).ravel(), np.asarray(m.C).ravel()])
+
+
+def open_linear_case(name, model, spec, osz, B, T, seed):
+    t0 = time.time()
+    rng = np.random.default_rng(seed)
+    S, I, O = spec["state_dim"], spec["input_dim"], spec["output_dim"]
+    u = r32(rng.uniform(-1.5, 1.5, size=(B, T, I)))
+    tgt = r32(rng.normal(size=(B, T + 1, O)))
+    y = from_tree(eqx.filter_vmap(model.unroll)(u))
+    opt = RecordingOptimizer()
+    mbs = MiniBatchState(None, 0, B, 1, B, jrand.PRNGKey(3))
+    data = SupervisedDatasetWithWeights(u, to_tree(tgt, osz), np.ones((B,)))
+    options = ref_step.TrainingOptionsModel(Dataloader(mbs, lambda s: (s, data)), opt)
+    step, opt_state, mbs = ref_step.make_step_fn_model(model, options)
+    new_model, _, _, logs = step(model, opt_state, mbs)
+    perm = linear_perm(S, I, O)
+    th_ref, tb_ref = flat(flatten_module(model)), flat(opt.grads)  # reference order [A, B, C, D] (module_utils.py:20-24)
+    out = dict(kind="open", spec=json.dumps(spec), theta=th_ref[perm], theta_bar=tb_ref[perm], theta_ref_order=th_ref,
+               theta_bar_ref_order=tb_ref, perm=perm, x0=np.asarray(model.x0, np.float64), u=u, targets=tgt, y=y,
+               loss=np.float64(np.real(logs["train_loss"])), train_mse=np.float64(np.real(logs["train_mse"])),
+               theta_after=flat(flatten_module(new_model))[perm], lr=opt.lr, clip=opt.clip, l1=0.0, l2=0.0)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(f"{name}: P={th_ref.size} B={B} T={T} loss={out['loss']:.6f} |g|={np.linalg.norm(tb_ref):.4e}  ({time.time() - t0:.1f}s)",
+          flush=True)
+
+
+def pid_kernel_theta(p, i, d, dt):
+    """PIDController (pid_controller.py:34-79) as a discrete linear node on [last_error, sum_of_errors], input [ref, obs]:
+    z+ = F [z ; v] (no-integrate), control = G [z ; v] (readout of the pre-step state with feed-through)"""
+    F = np.array([[0.0, 0.0, 1.0, -1.0], [0.0, 1.0, dt, -dt]])
+    dc = p + i * dt + d / dt
+    G = np.array([[-d / dt, i, dc, -dc]])
+    return np.concatenate([F.ravel(), G.ravel()])
 
 
 def main():
@@ -297,6 +366,30 @@ def main():
         m, ms = build_model("full", 1, 1, [1], f_depth=0, f_tv=True, ut=("arctan", 1.0))
         closed_loop_case("closed_full_s6_ft_tv__full_s1_tv", c, cs, OrderedDict(m0=m), dict(m0=ms), B=3, Tr=30, seed=203,
                          noise_scale=0.03125)
+
+    # ---- LinearModel (cc/examples/linear_model.py) and PIDController (pid_controller.py): SURVEY 8 row f2
+    if want("open_linear_ct_s3"):  # the CLI's LTI model class, continuous time, D trained (include_D default)
+        m, s = build_linear(3, 1, [1])
+        open_linear_case("open_linear_ct_s3", m, s, [1], B=4, T=40, seed=300)
+    if want("open_linear_dt_s6_i2_o2_x0"):  # discrete time, two inputs / outputs, random initial state
+        m, s = build_linear(6, 2, [1, 1], continuous=False, seed=4, randomize_x0=True)
+        open_linear_case("open_linear_dt_s6_i2_o2_x0", m, s, [1, 1], B=3, T=30, seed=301)
+    if want("closed_full_s8__linear_two"):  # CLI workflow: deep-MLP controller against several LTI systems (one with D != 0)
+        c, cs = build_controller("full", 8, 1, 1, 1, f_width=10, f_depth=2)
+        m0, ms0 = build_linear(3, 1, [1], seed=7, zero_D=True)
+        m1, ms1 = build_linear(4, 1, [1], seed=8)
+        closed_loop_case("closed_full_s8__linear_two", c, cs, OrderedDict(sys0=m0, sys1=m1), dict(sys0=ms0, sys1=ms1), B=3,
+                         Tr=30, seed=302, model_theta=dict(sys0=linear_kernel_theta(m0, ms0), sys1=linear_kernel_theta(m1, ms1)))
+    if want("closed_pid__linear"):  # PID controller, gradient w.r.t. its gains (flat order: sorted dict keys d, i, p)
+        gains = dict(p=1.5, i=0.75, d=0.015625)
+        c = make_pid_controller(gains["p"], gains["i"], gains["d"], DT)
+        cs = node_kwargs(2, 2, 1, f_depth=0, f_use_bias=False, g_use_bias=False, integrator=2, readout_pre_step=True,
+                         g_feedthrough_u=True)
+        m, ms = build_linear(3, 1, [1], seed=9, zero_D=True)
+        closed_loop_case("closed_pid__linear", c, cs, OrderedDict(sys0=m), dict(sys0=ms), B=3, Tr=40, seed=303,
+                         model_theta=dict(sys0=linear_kernel_theta(m, ms)),
+                         ctrl_theta=pid_kernel_theta(gains["p"], gains["i"], gains["d"], DT),
+                         extra=dict(pid_gains_dip=np.array([gains["d"], gains["i"], gains["p"]]), pid_dt=DT))
 
 
 if __name__ == "__main__":

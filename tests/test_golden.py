@@ -45,6 +45,21 @@ def regu_value(theta, l1, l2):
     return l1 * np.abs(theta).sum() + l2 * np.linalg.norm(theta)
 
 
+def _x0_of(g, B):
+    """LinearModel fixtures carry the (possibly random) initial state x0[S] (linear_model.py:41-44)"""
+    if "x0" not in g.files or not np.any(g["x0"]):
+        return None
+    return np.broadcast_to(g["x0"], (B, g["x0"].size)).copy()
+
+
+def pid_gain_grad(tb, dt):
+    """chain rule from the PID node's kernel-order cotangent (tests/golden/make_golden.py: pid_kernel_theta; f rows are
+    constants, g = [-d/dt, i, dc, -dc] with dc = p + i dt + d/dt) to the reference's flat order (d_gain, i_gain, p_gain)"""
+    gb = tb[8:12]
+    dcb = gb[2] - gb[3]
+    return np.array([-gb[0] / dt + dcb / dt, gb[1] + dt * dcb, dcb])
+
+
 def test_fixtures_present():
     assert len(OPEN) >= 6 and len(CLOSED) >= 4, (OPEN, CLOSED)
 
@@ -56,13 +71,14 @@ def test_oracle_open_loop_pinned(name, impl):
     spec = spec_of(str(g["spec"]))
     theta, u, tgt = g["theta"], g["u"], g["targets"]
     assert theta.size == spec.n_params()  # flatten_module order and count (module_utils.py:20-24)
+    x0 = _x0_of(g, u.shape[0])
     if impl == "numpy":
-        y, _ = O.rollout_fwd(spec, theta, u, np.float64)
-        tb, _ = O.rollout_bwd(spec, theta, u, O.mse_cotangent(tgt, y), np.float64)
+        y, _ = O.rollout_fwd(spec, theta, u, np.float64, x0=x0)
+        tb, _ = O.rollout_bwd(spec, theta, u, O.mse_cotangent(tgt, y), np.float64, x0=x0)
     else:
-        r = CO.rollout(spec, theta, u, dtype=np.float64)
+        r = CO.rollout(spec, theta, u, x0=x0, dtype=np.float64)
         y = r["y"]
-        tb = CO.rollout(spec, theta, u, ybar=O.mse_cotangent(tgt, y), dtype=np.float64)["theta_bar"]
+        tb = CO.rollout(spec, theta, u, x0=x0, ybar=O.mse_cotangent(tgt, y), dtype=np.float64)["theta_bar"]
     assert normwise(y, g["y"]) < PIN
     assert abs(O.mse(tgt, y) - float(g["train_mse"])) < PIN * max(1.0, float(g["train_mse"]))
     l1, l2 = float(g["l1"]), float(g["l2"])
@@ -104,6 +120,9 @@ def test_oracle_closed_loop_pinned(name, impl):
         assert abs(l - float(g[f"{n}_train_mse"])) < PIN * max(1.0, l)
     l1, l2 = float(g["l1"]), float(g["l2"])
     assert abs(np.mean(losses) + regu_value(thc, l1, l2) - float(g["loss"])) < PIN * max(1.0, float(g["loss"]))
+    if "pid_gains_dip" in g.files:
+        assert l2rel(pid_gain_grad(tb, float(g["pid_dt"])), g["theta_c_bar"]) < 1e-7  # (the d-term divides by dt twice)
+        return
     assert l2rel(tb + regu_grad(thc, l1, l2), g["theta_c_bar"]) < PIN
 
 
@@ -118,8 +137,51 @@ def _adam_clip_step(theta, grad, lr, clip, b1=0.9, b2=0.999, eps=1e-8):
 def test_fixture_optimizer_step_consistent(name):
     g = load(name)
     k = "theta" if name.startswith("open") else "theta_c"
-    after = _adam_clip_step(g[k], g[k + "_bar"], float(g["lr"]), float(g["clip"]))
+    th = g["theta_c_ref_order"] if "theta_c_ref_order" in g.files else g[k]
+    after = _adam_clip_step(th, g[k + "_bar"], float(g["lr"]), float(g["clip"]))
     assert l2rel(after, g[k + "_after"]) < 1e-12
+
+
+# ------------------------------------------------------------------- the product kernels on the CPU emulation
+
+
+@pytest.mark.parametrize("name", [n for n in OPEN if "s64" not in n])
+def test_emulated_kernels_open_loop_vs_reference_golden(name):
+    """the product's device code (compiled for the CPU fiber emulation, tests/emu) against the reference's outputs/gradients"""
+    import emu_lib as E
+
+    g = load(name)
+    spec = conv(spec_of(str(g["spec"])))
+    theta, u, tgt = g["theta"], g["u"], g["targets"]
+    x0 = _x0_of(g, u.shape[0])
+    y, _, _ = E.np_rollout_fwd(E.emu(), spec, theta, u, x0)
+    assert normwise(y, g["y"]) < TOL_STATE
+    ybar = (2.0 / y.size) * (y.astype(np.float64) - tgt)
+    _, tb, _ = E.np_rollout_bwd(E.emu(), spec, theta, u, ybar, x0, want_ubar=False)
+    assert l2rel(tb.astype(np.float64) + regu_grad(theta, float(g["l1"]), float(g["l2"])), g["theta_bar"]) < TOL_GRAD
+
+
+@pytest.mark.parametrize("name", CLOSED)
+def test_emulated_kernels_closed_loop_vs_reference_golden(name):
+    import emu_lib as E
+
+    g = load(name)
+    cspec = conv(spec_of(str(g["cspec"])))
+    mspecs = {k: conv(O.make_node(**v)) for k, v in json.loads(str(g["mspecs"])).items()}
+    names = json.loads(str(g["model_names"]))
+    refs, thc = g["refs"], g["theta_c"]
+    tb = np.zeros_like(thc)
+    for n in names:
+        thm = g[f"theta_m__{n}"]
+        noise = g[f"noise__{n}"] if f"noise__{n}" in g.files else None
+        yhat, _, _ = E.np_closedloop_fwd(E.emu(), cspec, mspecs[n], thc, thm, refs, noise)
+        assert normwise(yhat, g[f"yhat__{n}"]) < TOL_STATE
+        ybar = (2.0 / (yhat.size * len(names))) * (yhat.astype(np.float64) - refs)
+        tb += E.np_closedloop_bwd(E.emu(), cspec, mspecs[n], thc, thm, refs, ybar, noise)[1]
+    if "pid_gains_dip" in g.files:
+        assert l2rel(pid_gain_grad(tb, float(g["pid_dt"])), g["theta_c_bar"]) < TOL_GRAD
+        return
+    assert l2rel(tb + regu_grad(thc, float(g["l1"]), float(g["l2"])), g["theta_c_bar"]) < TOL_GRAD
 
 
 # ----------------------------------------------------------------------------------------------- GPU
@@ -139,7 +201,9 @@ def test_cuda_open_loop_vs_reference_golden(name):
     g = load(name)
     spec = conv(spec_of(str(g["spec"])))
     theta, u, tgt = g["theta"], g["u"], g["targets"]
-    y, _, tape = ops.rollout_fwd(spec, _t(theta), _t(u), want_tape=True)
+    x0 = _x0_of(g, u.shape[0])
+    x0 = None if x0 is None else _t(x0)
+    y, _, tape = ops.rollout_fwd(spec, _t(theta), _t(u), x0, want_tape=True)
     assert normwise(y.cpu().numpy(), g["y"]) < TOL_STATE
     ybar = (2.0 / y.numel()) * (y - _t(tgt))
     if max(spec.f.sizes[1:]) > 32 and spec.f.n_layers > 1:
@@ -149,7 +213,7 @@ def test_cuda_open_loop_vs_reference_golden(name):
         with pytest.raises(_lib.CcError):
             ops.rollout_bwd(spec, _t(theta), _t(u), tape, ybar)
         return
-    tb, _ = ops.rollout_bwd(spec, _t(theta), _t(u), tape, ybar)
+    tb, _ = ops.rollout_bwd(spec, _t(theta), _t(u), tape, ybar, x0)
     tb = tb.cpu().numpy().astype(np.float64) + regu_grad(theta, float(g["l1"]), float(g["l2"]))
     assert l2rel(tb, g["theta_bar"]) < TOL_GRAD
 
@@ -172,5 +236,8 @@ def test_cuda_closed_loop_vs_reference_golden(name):
         assert normwise(yhat.cpu().numpy(), g[f"yhat__{n}"]) < TOL_STATE
         ybar = (2.0 / (yhat.numel() * len(names))) * (yhat - _t(refs))
         tb += ops.closedloop_bwd(cspec, mspecs[n], _t(thc), _t(thm), _t(refs), tape, ybar, noise=noise).cpu().numpy()
+    if "pid_gains_dip" in g.files:
+        assert l2rel(pid_gain_grad(tb, float(g["pid_dt"])), g["theta_c_bar"]) < TOL_GRAD
+        return
     tb = tb + regu_grad(thc, float(g["l1"]), float(g["l2"]))
     assert l2rel(tb, g["theta_c_bar"]) < TOL_GRAD

@@ -114,3 +114,81 @@ def test_closed_loop_mirror_matches_oracle():
     assert normwise(yhat.detach().cpu().numpy(), ref["yhat"]) < TOL_STATE
     single = controller.unroll(model, merge_x_y)(refs[3], 0)
     np.testing.assert_allclose(single.detach().cpu().numpy(), yhat[3].detach().cpu().numpy(), rtol=1e-6, atol=1e-7)
+
+
+def _gold(name):
+    import os
+
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+
+
+@pytest.mark.parametrize("name,dims", [("open_linear_ct_s3", (3, 1, 1, True)), ("open_linear_dt_s6_i2_o2_x0", (6, 2, 2, False))])
+def test_linear_model_mirror_vs_reference_golden(name, dims):
+    """LinearModel (cc/examples/linear_model.py:47-84) through the public mirror: outputs and the gradient of the reference's
+    loss_fn_model in the REFERENCE's flat order [A, B, C, D] against the fixture produced by the reference's own code"""
+    from chain_control_b200.examples.linear_model import make_linear_model
+    from chain_control_b200.utils import mse
+
+    S, I, O, ct = dims
+    g = _gold(name)
+    osp = O if O == 1 else OrderedDict(o0=1, o1=1)
+    m = make_linear_model(I, osp, float(np.float32(0.01)), S, continuous_time=ct, randomize_x0=bool(np.any(g["x0"])))
+    m.init_state = (torch.tensor(g["x0"], dtype=torch.float32, device="cuda"), 0.0)
+    m._x0_nonzero = bool(np.any(g["x0"]))
+    p = torch.tensor(g["theta_ref_order"], dtype=torch.float32, device="cuda", requires_grad=True)
+    m = m.with_params(p)
+    y = m.unroll_batched(torch.tensor(g["u"], dtype=torch.float32, device="cuda"))
+    yf = y if torch.is_tensor(y) else torch.cat(list(y.values()), -1)
+    assert normwise(yf.detach().cpu().numpy(), g["y"]) < TOL_STATE
+    loss = ((yf - torch.tensor(g["targets"], dtype=torch.float32, device="cuda")) ** 2).mean()
+    (gr,) = torch.autograd.grad(loss, p)
+    assert abs(float(loss.detach()) - float(g["train_mse"])) < 1e-5 * max(1.0, float(g["train_mse"]))
+    assert l2rel(gr.cpu().numpy(), g["theta_bar_ref_order"]) < TOL_GRAD
+
+
+def test_pid_controller_mirror_vs_reference_golden():
+    """PIDController (pid_controller.py:34-79) in closed loop with a LinearModel: outputs and d loss / d (d, i, p gains)"""
+    from chain_control_b200.examples.linear_model import make_linear_model
+    from chain_control_b200.examples.pid_controller import make_pid_controller
+    from chain_control_b200.train.step_fn import merge_x_y
+
+    g = _gold("closed_pid__linear")
+    dt = float(g["pid_dt"])
+    d, i, p = g["pid_gains_dip"]
+    gains = torch.tensor(g["theta_c_ref_order"], dtype=torch.float32, device="cuda", requires_grad=True)
+    c = make_pid_controller(p, i, d, dt).with_params(gains)
+    thm = g["theta_m__sys0"]  # kernel order of a zero-D LinearModel: [A|B] rows then C
+    A_, B_, C_ = thm[:12].reshape(3, 4)[:, :3], thm[:12].reshape(3, 4)[:, 3:], thm[12:].reshape(1, 3)
+    m = make_linear_model(1, 1, dt, 3).replace(A=A_, B=B_, C=C_, D=np.zeros((1, 1)))
+    refs = torch.tensor(g["refs"], dtype=torch.float32, device="cuda")
+    yhat = c.unroll(m, merge_x_y).batched(refs)
+    assert normwise(yhat.detach().cpu().numpy(), g["yhat__sys0"]) < TOL_STATE
+    loss = ((yhat - refs) ** 2).mean()
+    (gr,) = torch.autograd.grad(loss, gains)
+    assert l2rel(gr.cpu().numpy(), g["theta_c_bar"]) < TOL_GRAD
+
+
+def test_cli_workflow_linear_systems():
+    """the reference's CLI workflow (docs/examples/cli/train_controller.py:120-190): a deep-MLP controller trained against
+    several LTI systems given as (A, B, C) with D = 0; the multi-model mean loss falls"""
+    from chain_control_b200.examples.linear_model import make_linear_model
+    from chain_control_b200.examples.neural_ode_controller import make_neural_ode_controller
+    from chain_control_b200.train import (DictLogger, ModelControllerTrainer, Tracker, TrainingOptionsController,
+                                          UnsupervisedDataset, make_dataloader, optim)
+
+    rng = np.random.default_rng(0)
+    systems = {}
+    for k in range(3):
+        S = 3
+        A_ = -np.eye(S) * rng.uniform(0.5, 2.0) + 0.3 * rng.normal(size=(S, S))
+        systems[f"system{k}"] = make_linear_model(1, OrderedDict(output=1), 0.01, 3).replace(
+            A=A_, B=rng.normal(size=(S, 1)), C=rng.normal(size=(1, S)), D=np.zeros((1, 1)))
+    refs = OrderedDict(output=(rng.uniform(-1, 1, size=(30, 1, 1)) * np.ones((30, 301, 1))).astype(np.float32))
+    controller = make_neural_ode_controller(2, 1, 0.01, state_dim=5, f_depth=2, f_width_size=10)
+    copts = TrainingOptionsController(make_dataloader(UnsupervisedDataset(refs), key=1, n_minibatches=1),
+                                      optim.chain(optim.clip_by_global_norm(1.0), optim.adam(3e-3)))
+    tr = ModelControllerTrainer(systems, controller, controller_train_options=copts, trackers=[Tracker("loss")], loggers=[DictLogger()])
+    tr.run(6)
+    logs = tr.get_logs()[0]
+    assert all(f"system{k}_train_mse" in logs for k in range(3))
+    assert np.all(np.isfinite(logs["loss"])) and logs["loss"][-1] < logs["loss"][0]

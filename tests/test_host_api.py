@@ -80,3 +80,37 @@ def test_callable_classification_and_init():
     spec = A.make_node_spec(50, 1, 1, 0.01, f_depth=0)
     th = init_flat_params(spec, 1)
     assert th.numel() == 2651 and float(th[:2550].abs().max()) <= 1 / np.sqrt(51) + 1e-7
+
+
+def test_linear_model_and_pid_parameter_layout_match_reference_fixtures():
+    """LinearModel / PIDController host mirrors: the kernel-order `theta` they derive from the reference-order flat vector
+    equals what the reference's own modules gave (tests/golden/*.npz: theta = theta_ref_order[perm]); CPU tensors, no kernel call"""
+    import os
+
+    import numpy as np
+    import torch
+
+    from chain_control_b200.examples.linear_model import make_linear_model
+    from chain_control_b200.examples.pid_controller import make_pid_controller
+
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    for name, (S, I, O, ct) in {"open_linear_ct_s3": (3, 1, 1, True), "open_linear_dt_s6_i2_o2_x0": (6, 2, 2, False)}.items():
+        g = np.load(os.path.join(gold, name + ".npz"))
+        m = make_linear_model(I, O, 0.01, S, continuous_time=ct, device="cpu")
+        p = torch.tensor(g["theta_ref_order"], dtype=torch.float32, requires_grad=True)
+        m = m.with_params(p)
+        assert m.spec.n_params() == g["theta"].size and m.spec.g_feedthrough_u and m.spec.readout_pre_step
+        np.testing.assert_array_equal(m.theta.detach().numpy(), g["theta"].astype(np.float32))
+        w = torch.arange(1.0, 1.0 + g["theta"].size)
+        (gr,) = torch.autograd.grad((m.theta * w).sum(), p)  # the scatter back to the reference order
+        np.testing.assert_array_equal(gr.numpy()[g["perm"]], w.numpy())
+        z = m.replace(D=np.zeros((O, I))).frozen()  # the CLI's LTI systems: D = 0 -> no feed-through -> fast kernel families
+        assert not z.spec.g_feedthrough_u and z.flat_params().numel() == S * S + S * I + O * S
+    g = np.load(os.path.join(gold, "closed_pid__linear.npz"))
+    d, i, p = g["pid_gains_dip"]
+    c = make_pid_controller(p, i, d, float(g["pid_dt"]), device="cpu")
+    np.testing.assert_allclose(c.theta.numpy(), g["theta_c"], rtol=1e-6)
+    np.testing.assert_allclose(c.flat_params().numpy(), g["theta_c_ref_order"], rtol=1e-7)
+    c2 = make_pid_controller(p, i, d, 0.01, d_gain_trainable=False, device="cpu",
+                             transform_params=lambda q: {"p_gain": q["p_gain"], "i_gain": q["i_gain"], "d_gain": q["p_gain"] * 0.1})
+    assert c2.flat_params().numel() == 2 and abs(float(c2.theta[8]) + 0.1 * p / 0.01) < 1e-3
