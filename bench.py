@@ -204,6 +204,57 @@ def run_reference(args):
     }))
 
 
+def cfg3_points(torch, dev, fp32_peak_tflops, cpu_threads):
+    """BASELINE.json configs[2] (forward-only sweep, MLP width 32..128): three (architecture, batch) points, T = 1000"""
+    import ctypes as _C
+
+    from chain_control_b200 import _lib, arch as A, ops
+    from oracle import c_oracle as CO
+
+    out = {"workload": "configs[2]: forward-only batched rollout, deep-MLP model (S = W, f depth 2, tanh final activation), T = 1000; "
+                       "alg_tflops = 2 (4 M_f + M_g) FLOP per trajectory-step / time", "points": []}
+    T = 1000
+    for S, B in ((32, 131072), (64, 65536), (128, 16384)):
+        spec = A.make_node_spec(S, 1, 1, DT, f_width=S, f_depth=2, f_act_final=A.ACT_TANH)
+        rng = np.random.default_rng(S)
+        parts = []
+        for mlp in (spec.f, spec.g):
+            for i, o in zip(mlp.sizes[:-1], mlp.sizes[1:]):
+                parts += [0.5 * rng.uniform(-1, 1, size=o * i) / np.sqrt(i), rng.uniform(-1, 1, size=o) / np.sqrt(i)]
+        th_h = np.concatenate(parts).astype(np.float32)
+        th = torch.tensor(th_h, device=dev)
+        u = torch.rand(B, T, 1, device=dev) * 2 - 1
+        fam = _lib.lib().cc_kernel_family_at(None, _C.byref(spec.to_c()), 0, B)
+        ops.rollout_fwd(spec, th, u)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ops.rollout_fwd(spec, th, u)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = min(ts)
+        mf = sum(i * o for i, o in zip(spec.f.sizes[:-1], spec.f.sizes[1:]))
+        mg = sum(i * o for i, o in zip(spec.g.sizes[:-1], spec.g.sizes[1:]))
+        fl = 2 * (4 * mf + mg)
+        pt = {"arch": f"S{S}_W{S}_d2", "B": B, "T": T, "kernel_family": int(fam), "ms": ms, "value": B * T / (ms * 1e-3),
+              "alg_tflops": B * T * fl / (ms * 1e-3) / 1e12, "frac_fp32_fma_peak": B * T * fl / (ms * 1e-3) / 1e12 / fp32_peak_tflops}
+        if cpu_threads:
+            Bc, Tc = 256, 100
+            uc = u[:Bc, :Tc].cpu().numpy()
+            CO.rollout(spec, th_h, uc, march="native", nthreads=cpu_threads)
+            t0 = time.time()
+            CO.rollout(spec, th_h, uc, march="native", nthreads=cpu_threads)
+            dtc = time.time() - t0
+            pt["cpu_value"] = Bc * Tc / dtc
+            pt["cpu_sample"] = f"{Bc} trajectories x {Tc} steps forward on {cpu_threads} threads (C/OpenMP oracle port)"
+        out["points"].append(pt)
+        del u
+    return out
+
+
 def ncu_traffic(kernel_substr):
     """dram read + write bytes of one launch of the kernel from the newest committed `ncu --set full` raw page
     (profiles/r*_raw.csv, written from the .ncu-rep with `ncu --page raw --csv`): (bytes, file) or None"""
@@ -467,6 +518,13 @@ def main():
             except Exception as exc:
                 others[name] = {"error": f"{type(exc).__name__}: {exc}"}
             torch.cuda.empty_cache()
+        # configs[2]: forward-only batched rollout of deep-MLP models, widths 32..128 (deep-MLP tcgen05 family, one MMA batch per
+        # layer).  Three sweep points; the full B = 1K..1M sweep is profiles/r02_cfg3_sweep.md (scratch/sweep_cfg3_r02.py)
+        try:
+            others["cfg3"] = cfg3_points(torch, dev, peak_tflops, None if args.no_cpu_baseline else cores)
+        except Exception as exc:
+            others["cfg3"] = {"error": f"{type(exc).__name__}: {exc}"}
+        torch.cuda.empty_cache()
 
     if rank == 0:
         import ctypes as _C

@@ -299,8 +299,21 @@ def make_neural_ode_controller_compact(input_specs, output_specs, control_timest
                                        device="cuda") -> NeuralOdeController:
     """cc/examples/neural_ode_controller_compact_example.py:33-52.  With the default zero secondary controller
     (DummyController, :171-181) the output is sigmoid(alpha=0) * g(x) = 0.5 * g(x), readout before the update."""
-    if superposition or superposition_trainable:
-        raise NotImplementedError("PID superposition (secondary controller) is outside the accelerated path")
+    if superposition:
+        # secondary PID controller (:150-163): host-level composition into ONE linear node, exact for a linear neural part
+        if f_depth != 0 or classify_activation(f_final_activation) != A.ACT_IDENTITY or g_depth != 0 or \
+                classify_activation(g_final_activation) != A.ACT_IDENTITY or f_integrate_method != "RK4":
+            raise NotImplementedError("PID superposition is accelerated for the linear compact controller only (f_depth = g_depth = 0, "
+                                      "identity final activations, RK4): see chain_control_b200/examples/superposition.py")
+        from .superposition import make_superposed_compact_controller
+
+        I, _ = struct_of_specs(input_specs)
+        O, _ = struct_of_specs(output_specs)
+        if I != 2 or O != 1:
+            raise NotImplementedError("PID superposition: scalar reference / observation / control only")
+        return make_superposed_compact_controller(1, 1, control_timestep, state_dim, key, superposition_trainable, device)
+    if superposition_trainable:
+        raise NotImplementedError("superposition_trainable without superposition has no secondary controller to weigh")
     return _build(NeuralOdeController, input_specs, output_specs, control_timestep, state_dim, key, device,
                   f_width=f_width_size, f_depth=f_depth, g_width=g_width_size, g_depth=g_depth,
                   f_act=classify_activation(f_activation), f_act_final=classify_activation(f_final_activation),

@@ -391,6 +391,14 @@ def main():
                          ctrl_theta=pid_kernel_theta(gains["p"], gains["i"], gains["d"], DT),
                          extra=dict(pid_gains_dip=np.array([gains["d"], gains["i"], gains["p"]]), pid_dt=DT))
 
+    if want("closed_compact_superposition__compact_s50"):  # compact controller + PID secondary (superposition=True, :150-163)
+        c, _ = build_controller("compact", 5, 1, 1, 1, f_depth=0, superposition=True)
+        cs = node_kwargs(7, 2, 1, f_depth=0, integrator=2, readout_pre_step=True, g_feedthrough_u=True)  # the combined linear node
+        m, ms = build_model("compact", 50, 1, [1], f_depth=0, ut=("arctan", 1.0), stable=True)
+        closed_loop_case("closed_compact_superposition__compact_s50", c, cs, OrderedDict(m0=m), dict(m0=ms), B=4, Tr=40, seed=304,
+                         noise_scale=0.0625, extra=dict(superposed_dims=np.array([5, 1, 1]), superposed_alpha=np.float64(c.alpha),
+                                                        superposed_dt=DT))
+
 
 if __name__ == "__main__":
     main()

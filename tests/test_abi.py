@@ -89,13 +89,15 @@ def test_plan_picks_tcgen05_for_depth0_models():
         assert fam(None, tc_model_variants()["full_s20_d0"], 1) == 4          # post-step readout too
         assert fam(None, tc_model_variants()["euler_s30_d0_tanh"], 0) == 1    # tanh final activation: not linear
         assert fam(controller_variants()["full_s25_w10_d2"], compact, 0) == 0  # tile-sized controller: FFMA kernels
-        assert fam(None, model_variants()["full_s5_w10_d2"], 0) == 0          # deep MLP
+        assert fam(None, model_variants()["full_s5_w10_d2"], 0) == 5          # deep MLP forward: one tcgen05.mma batch per layer
+        assert fam(None, model_variants()["full_s5_w10_d2"], 1) == 0          # its reverse pass: FFMA kernels
+        assert L.cc_kernel_family_at(None, ctypes.byref(conv(model_variants()["full_s5_w10_d2"]).to_c()), 0, 64) == 0  # small batch
         os.environ["CC_B200_LIN"] = "0"   # the families below the blocked linear one
         assert fam(None, compact, 0) == 1            # open-loop forward
         assert fam(None, compact, 1) == 3            # ModelTrainer reverse pass: tcgen05 incl. the weight-gradient product
         assert fam(None, tc_model_variants()["full_s20_d0"], 1) == 0   # post-step readout: FFMA reverse pass
         assert fam(ctrl, compact, 0) == 1 and fam(ctrl, compact, 1) == 1   # the bench workload, both directions
-        assert fam(None, model_variants()["full_s5_w10_d2"], 0) == 0       # deep MLP
+        assert fam(None, model_variants()["full_s5_w10_d2"], 0) == 5       # deep MLP
         assert fam(controller_variants()["full_s25_w10_d2"], compact, 0) == 0  # tile-sized controller
         for mname, m in tc_model_variants().items():
             for c in tc_controller_variants().values():

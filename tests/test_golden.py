@@ -60,6 +60,29 @@ def pid_gain_grad(tb, dt):
     return np.array([-gb[0] / dt + dcb / dt, gb[1] + dt * dcb, dcb])
 
 
+def ctrl_theta_and_chain(g):
+    """kernel-order controller parameters of a fixture and the map from the kernel-order cotangent back to the reference's
+    flat order.  Plain neural-ODE controllers: identity.  PID: pid_gain_grad.  Compact controller + PID secondary
+    (superposition): the product's own composition (chain_control_b200/examples/superposition.py), fp64 on the CPU."""
+    if "superposed_dims" in g.files:
+        import torch
+
+        from chain_control_b200.examples.superposition import superposed_theta
+
+        S, R, O_ = (int(v) for v in g["superposed_dims"])
+        flat = torch.tensor(g["theta_c_ref_order"], dtype=torch.float64, requires_grad=True)
+        th = superposed_theta(flat, float(g["superposed_alpha"]), S, R, O_, float(g["superposed_dt"]), False)
+
+        def chain(tb):
+            (gr,) = torch.autograd.grad(th, flat, grad_outputs=torch.tensor(np.asarray(tb, np.float64)), retain_graph=True)
+            return gr.numpy()
+
+        return th.detach().numpy(), chain
+    if "pid_gains_dip" in g.files:
+        return g["theta_c"], lambda tb: pid_gain_grad(tb, float(g["pid_dt"]))
+    return g["theta_c"], lambda tb: tb + regu_grad(g["theta_c"], float(g["l1"]), float(g["l2"]))
+
+
 def test_fixtures_present():
     assert len(OPEN) >= 6 and len(CLOSED) >= 4, (OPEN, CLOSED)
 
@@ -90,7 +113,7 @@ def _closed_oracle(g, impl):
     cspec = spec_of(str(g["cspec"]))
     mspecs = {k: O.make_node(**v) for k, v in json.loads(str(g["mspecs"])).items()}
     names = json.loads(str(g["model_names"]))
-    refs, thc = g["refs"], g["theta_c"]
+    refs, thc = g["refs"], ctrl_theta_and_chain(g)[0]
     assert thc.size == cspec.n_params()
     tb, losses, yh = np.zeros_like(thc), [], {}
     for n in names:
@@ -120,10 +143,8 @@ def test_oracle_closed_loop_pinned(name, impl):
         assert abs(l - float(g[f"{n}_train_mse"])) < PIN * max(1.0, l)
     l1, l2 = float(g["l1"]), float(g["l2"])
     assert abs(np.mean(losses) + regu_value(thc, l1, l2) - float(g["loss"])) < PIN * max(1.0, float(g["loss"]))
-    if "pid_gains_dip" in g.files:
-        assert l2rel(pid_gain_grad(tb, float(g["pid_dt"])), g["theta_c_bar"]) < 1e-7  # (the d-term divides by dt twice)
-        return
-    assert l2rel(tb + regu_grad(thc, l1, l2), g["theta_c_bar"]) < PIN
+    special = "pid_gains_dip" in g.files or "superposed_dims" in g.files  # (the d-term divides by dt twice: 1e-7)
+    assert l2rel(ctrl_theta_and_chain(g)[1](tb), g["theta_c_bar"]) < (1e-7 if special else PIN)
 
 
 def _adam_clip_step(theta, grad, lr, clip, b1=0.9, b2=0.999, eps=1e-8):
@@ -169,7 +190,7 @@ def test_emulated_kernels_closed_loop_vs_reference_golden(name):
     cspec = conv(spec_of(str(g["cspec"])))
     mspecs = {k: conv(O.make_node(**v)) for k, v in json.loads(str(g["mspecs"])).items()}
     names = json.loads(str(g["model_names"]))
-    refs, thc = g["refs"], g["theta_c"]
+    refs, (thc, chain) = g["refs"], ctrl_theta_and_chain(g)
     tb = np.zeros_like(thc)
     for n in names:
         thm = g[f"theta_m__{n}"]
@@ -178,10 +199,7 @@ def test_emulated_kernels_closed_loop_vs_reference_golden(name):
         assert normwise(yhat, g[f"yhat__{n}"]) < TOL_STATE
         ybar = (2.0 / (yhat.size * len(names))) * (yhat.astype(np.float64) - refs)
         tb += E.np_closedloop_bwd(E.emu(), cspec, mspecs[n], thc, thm, refs, ybar, noise)[1]
-    if "pid_gains_dip" in g.files:
-        assert l2rel(pid_gain_grad(tb, float(g["pid_dt"])), g["theta_c_bar"]) < TOL_GRAD
-        return
-    assert l2rel(tb + regu_grad(thc, float(g["l1"]), float(g["l2"])), g["theta_c_bar"]) < TOL_GRAD
+    assert l2rel(chain(tb), g["theta_c_bar"]) < TOL_GRAD
 
 
 # ----------------------------------------------------------------------------------------------- GPU
@@ -227,7 +245,7 @@ def test_cuda_closed_loop_vs_reference_golden(name):
     cspec = conv(spec_of(str(g["cspec"])))
     mspecs = {k: conv(O.make_node(**v)) for k, v in json.loads(str(g["mspecs"])).items()}
     names = json.loads(str(g["model_names"]))
-    refs, thc = g["refs"], g["theta_c"]
+    refs, (thc, chain) = g["refs"], ctrl_theta_and_chain(g)
     tb = np.zeros_like(thc)
     for n in names:
         thm = g[f"theta_m__{n}"]
@@ -236,8 +254,4 @@ def test_cuda_closed_loop_vs_reference_golden(name):
         assert normwise(yhat.cpu().numpy(), g[f"yhat__{n}"]) < TOL_STATE
         ybar = (2.0 / (yhat.numel() * len(names))) * (yhat - _t(refs))
         tb += ops.closedloop_bwd(cspec, mspecs[n], _t(thc), _t(thm), _t(refs), tape, ybar, noise=noise).cpu().numpy()
-    if "pid_gains_dip" in g.files:
-        assert l2rel(pid_gain_grad(tb, float(g["pid_dt"])), g["theta_c_bar"]) < TOL_GRAD
-        return
-    tb = tb + regu_grad(thc, float(g["l1"]), float(g["l2"]))
-    assert l2rel(tb, g["theta_c_bar"]) < TOL_GRAD
+    assert l2rel(chain(tb), g["theta_c_bar"]) < TOL_GRAD

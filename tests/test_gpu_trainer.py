@@ -192,3 +192,30 @@ def test_cli_workflow_linear_systems():
     logs = tr.get_logs()[0]
     assert all(f"system{k}_train_mse" in logs for k in range(3))
     assert np.all(np.isfinite(logs["loss"])) and logs["loss"][-1] < logs["loss"][0]
+
+
+def test_superposed_compact_controller_vs_reference_golden():
+    """compact controller with the PID secondary (neural_ode_controller_compact_example.py:88-168, superposition=True) through
+    the public factory: outputs (with the recorded observation noise) and the gradient w.r.t. [f, g, d, i, p gains]"""
+    import json
+
+    from cchelpers import conv
+    from chain_control_b200 import ops
+    from chain_control_b200.examples.neural_ode_controller_compact_example import make_neural_ode_controller
+
+    g = _gold("closed_compact_superposition__compact_s50")
+    dt = float(g["superposed_dt"])
+    c = make_neural_ode_controller(2, 1, dt, 5, f_depth=0, superposition=True)
+    flat = torch.tensor(g["theta_c_ref_order"], dtype=torch.float32, device="cuda", requires_grad=True)
+    c = c.with_params(flat)
+    assert c.flat_params().numel() == g["theta_c_ref_order"].size == 5 * 7 + 5 + 5 + 1 + 3
+    mspec = conv(O.make_node(**json.loads(str(g["mspecs"]))["m0"]))
+    t = lambda a: torch.tensor(np.asarray(a, np.float32), device="cuda")
+    refs = t(g["refs"])
+    yhat = ops.batched_closed_loop(c.spec, mspec, c.theta, t(g["theta_m__m0"]), refs, t(g["noise__m0"]))
+    assert normwise(yhat.detach().cpu().numpy(), g["yhat__m0"]) < TOL_STATE
+    loss = ((yhat - refs) ** 2).mean()
+    (gr,) = torch.autograd.grad(loss, flat)
+    assert l2rel(gr.cpu().numpy(), g["theta_c_bar"]) < TOL_GRAD
+    with pytest.raises(NotImplementedError):
+        make_neural_ode_controller(2, 1, dt, 5, f_depth=2, superposition=True)
