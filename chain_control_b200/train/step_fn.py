@@ -156,14 +156,57 @@ def eval_metrices_controller(controller, metrices, noise_scale, key):
     return log_of_metrices
 
 
+_STREAMS = {}
+
+
+def _model_streams(n, device):
+    """a cached pool of side streams, one per model of the multi-model loss"""
+    import os
+
+    if os.environ.get("CC_B200_MODEL_STREAMS", "1") == "0":
+        return None
+    pool = _STREAMS.setdefault(str(device), [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device))
+    return pool[:n]
+
+
+class _null_ctx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
 def make_step_fn_controller(controller, models: dict, options: TrainingOptionsController):
     optimizer = options.optimizer
 
     def loss_fn_controller(controller, refss, key):
         logs, log_of_loss_values = {}, OrderedDict()
-        for model_name, model in models.items():
-            refsshat = controller.unroll(model, options.merge_x_y, options.noise_scale).batched(refss, key)  # step_fn.py:257-259
-            log_of_loss_values[model_name] = options.loss_fn(refss, refsshat)
+        # step_fn.py:256-261 loops over the models inside one jitted function (XLA is free to overlap them).  Here every
+        # model's closed loop (rollout, loss and -- because autograd replays on the forward stream -- its BPTT) runs on its own
+        # CUDA stream: at the reference's sizes (tens of trajectories) each launch is one latency-bound wave, so K models
+        # overlap almost perfectly.  CC_B200_MODEL_STREAMS=0 serialises them (tests compare both).
+        theta_c = controller.theta  # (composed controllers build it with torch ops: once, on the current stream)
+        streams = _model_streams(len(models), theta_c.device) if (len(models) > 1 and theta_c.is_cuda) else None
+        cur = torch.cuda.current_stream(theta_c.device) if streams else None
+        if streams:
+            start = torch.cuda.Event()
+            start.record(cur)
+        for k, (model_name, model) in enumerate(models.items()):
+            if streams:
+                streams[k].wait_event(start)
+            with (torch.cuda.stream(streams[k]) if streams else _null_ctx()):
+                refsshat = controller.unroll(model, options.merge_x_y, options.noise_scale).batched(refss, key)  # step_fn.py:257-259
+                log_of_loss_values[model_name] = options.loss_fn(refss, refsshat)
+            if streams:
+                for v in log_of_loss_values[model_name].values():
+                    if torch.is_tensor(v):
+                        v.record_stream(cur)  # consumed by the reduction below on the main stream
+                done = torch.cuda.Event()
+                done.record(streams[k])
+                cur.wait_event(done)
         regu_value, log_of_regus = compute_regularisers(controller, options.regularisers)
         logs.update(log_of_regus)
         loss_value = options.loss_fn_reduce_along_models(log_of_loss_values)

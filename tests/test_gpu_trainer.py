@@ -219,3 +219,39 @@ def test_superposed_compact_controller_vs_reference_golden():
     assert l2rel(gr.cpu().numpy(), g["theta_c_bar"]) < TOL_GRAD
     with pytest.raises(NotImplementedError):
         make_neural_ode_controller(2, 1, dt, 5, f_depth=2, superposition=True)
+
+
+def test_multi_model_streams_match_serial(monkeypatch):
+    """the multi-model mean loss (step_fn.py:256-271) with one CUDA stream per model gives the same step as the serial loop"""
+    import time
+
+    from chain_control_b200.examples.linear_model import make_linear_model
+    from chain_control_b200.examples.neural_ode_controller import make_neural_ode_controller
+    from chain_control_b200.train import (ModelControllerTrainer, TrainingOptionsController, UnsupervisedDataset, make_dataloader,
+                                          optim)
+
+    def run(streams):
+        monkeypatch.setenv("CC_B200_MODEL_STREAMS", streams)
+        rng = np.random.default_rng(0)
+        systems = {}
+        for k in range(8):  # the CLI's 8 LTI systems x 30 references x 1501 steps
+            A_ = -np.eye(3) * rng.uniform(0.5, 2.0) + 0.3 * rng.normal(size=(3, 3))
+            systems[f"system{k}"] = make_linear_model(1, OrderedDict(output=1), 0.01, 3).replace(
+                A=A_, B=rng.normal(size=(3, 1)), C=rng.normal(size=(1, 3)), D=np.zeros((1, 1)))
+        refs = OrderedDict(output=(rng.uniform(-1, 1, size=(30, 1, 1)) * np.ones((30, 1501, 1))).astype(np.float32))
+        controller = make_neural_ode_controller(2, 1, 0.01, state_dim=5, f_depth=2, f_width_size=10, key=3)
+        copts = TrainingOptionsController(make_dataloader(UnsupervisedDataset(refs), key=1, n_minibatches=1),
+                                          optim.chain(optim.clip_by_global_norm(1.0), optim.adam(3e-3)))
+        tr = ModelControllerTrainer(systems, controller, controller_train_options=copts)
+        tr.step()
+        torch.cuda.synchronize()
+        t0 = time.time()
+        logs = [tr.step() for _ in range(3)]
+        torch.cuda.synchronize()
+        return logs[-1], (time.time() - t0) / 3
+
+    l1, t1 = run("1")
+    l0, t0 = run("0")
+    print(f"[multi-model] 8 systems x 30 x 1501: {1e3 * t1:.1f} ms/step on 8 streams, {1e3 * t0:.1f} ms/step serial")
+    for k in l0:
+        assert abs(float(l0[k]) - float(l1[k])) <= 1e-6 * max(1.0, abs(float(l0[k]))), k
