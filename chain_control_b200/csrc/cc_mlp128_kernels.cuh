@@ -26,8 +26,8 @@
 #define CC_MLP128_CHUNK_FLOATS (2 * 64 * CC_MLP128_KP)  // hi then lo
 #define CC_MLP128_CHUNK_BYTES (CC_MLP128_CHUNK_FLOATS * 4)
 #define CC_MLP128_RING 3
-// shared memory: ring | gw[4][132] | ypart[4][128] | barriers
-#define CC_MLP128_SMEM_FLOATS (CC_MLP128_RING * CC_MLP128_CHUNK_FLOATS + CC_TINY_O * 132 + CC_TINY_O * 128 + 32)
+// shared memory: ring | gw[4][132] | ypart[2][4][128] | barriers
+#define CC_MLP128_SMEM_FLOATS (CC_MLP128_RING * CC_MLP128_CHUNK_FLOATS + CC_TINY_O * 132 + 2 * CC_TINY_O * 128 + 32)
 
 // chunk c = 2 l + h of the pack: rows n = 64 h .. 64 h + 63 of layer l; element (n, k) at ((k/4)*64 + n%64)*4 + k%4
 __global__ void cc_mlp128_prep_kernel(const CC_GRID_CONSTANT CcMlpArgs a) {
@@ -132,44 +132,50 @@ CC_DEV void cc_mlp128_await_other(CcMlp128Ctx& c) {
 }
 #endif
 
-// epilogues on this thread's 64 columns [cb, cb + 64)
+// epilogues on this thread's 64 columns [cb, cb + 64), in groups of 16 (x[64] + acc[64] leave ~90 registers for temporaries)
 CC_DEV void cc_mlp128_hidden(CcMlp128Ctx& c, int act) {
   const int cb = 64 * c.hh;
 #pragma unroll
-  for (int c0 = 0; c0 < 64; c0 += 32) {
-    float r[32];
-    cc_mlp_ld<128, 32>(c.t, CcMlpTm<128>::COL_D + cb + c0, r);
+  for (int c0 = 0; c0 < 64; c0 += 16) {
+    float r[16];
+    cc_mlp_ld<128, 16>(c.t, CcMlpTm<128>::COL_D + cb + c0, r);
     cc_mlp_wait_ld();
-#pragma unroll
-    for (int i = 0; i < 32; ++i) r[i] = cc_act(act, r[i]);
+    cc_mlp_act_group<16>(act, r);
     if (c0 == 0) cc_mlp128_await_other(c);
-    cc_mlp_store_split<128, 32>(c.t, cb + c0, r);
+    cc_mlp_store_split<128, 16>(c.t, cb + c0, r);
   }
 }
 template <bool FINAL>
 CC_DEV void cc_mlp128_last(CcMlp128Ctx& c, int act, float (&x)[64], float (&acc)[64], float h, float wk, float cz, int integrator) {
   const int cb = 64 * c.hh;
 #pragma unroll
-  for (int c0 = 0; c0 < 64; c0 += 32) {
-    float r[32];
-    cc_mlp_ld<128, 32>(c.t, CcMlpTm<128>::COL_D + cb + c0, r);
+  for (int c0 = 0; c0 < 64; c0 += 16) {
+    float r[16];
+    cc_mlp_ld<128, 16>(c.t, CcMlpTm<128>::COL_D + cb + c0, r);
     cc_mlp_wait_ld();
-    float z[32];
+    cc_mlp_act_group<16>(act, r);
+    if (c0 == 0) cc_mlp128_await_other(c);
+    if (!FINAL) {
+      float z[16];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float k = cc_act(act, r[i]);
-      if (!FINAL) {
-        acc[c0 + i] = fmaf(wk, k, acc[c0 + i]);
-        z[i] = fmaf(h * k, cz, x[c0 + i]);
-      } else {
-        if (integrator == CC_INT_RK4) x[c0 + i] = fmaf(h, (1.f / 6.f) * (acc[c0 + i] + k), x[c0 + i]);
-        else if (integrator == CC_INT_EE) x[c0 + i] = fmaf(h, k, x[c0 + i]);
-        else x[c0 + i] = k;
+      for (int i = 0; i < 16; ++i) {
+        acc[c0 + i] = fmaf(wk, r[i], acc[c0 + i]);
+        z[i] = fmaf(h * r[i], cz, x[c0 + i]);
+      }
+      cc_mlp_store_split<128, 16>(c.t, cb + c0, z);
+    } else if (integrator == CC_INT_RK4) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        x[c0 + i] = fmaf(h, (1.f / 6.f) * (acc[c0 + i] + r[i]), x[c0 + i]);
         acc[c0 + i] = 0.f;
       }
+    } else if (integrator == CC_INT_EE) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[c0 + i] = fmaf(h, r[i], x[c0 + i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[c0 + i] = r[i];
     }
-    if (c0 == 0) cc_mlp128_await_other(c);
-    if (!FINAL) cc_mlp_store_split<128, 32>(c.t, cb + c0, z);
   }
 }
 // partial readout over this half's columns: gw[o][132] (zero beyond S, bias at index 128: added by half 0 only)
@@ -210,7 +216,7 @@ __global__ void __launch_bounds__(CC_MLP128_THREADS, 1) cc_mlp128_fwd_kernel(con
   CcMlp128Ctx c;
 #ifdef CC_EMULATE
   (void)ring;
-  c.t.tm = ypart + CC_TINY_O * 128 + 32;
+  c.t.tm = ypart + 2 * CC_TINY_O * 128 + 32;
   c.t.b = a.pack;
   c.t.tid = tid & 127;
   c.hh = tid >> 7;
@@ -218,7 +224,7 @@ __global__ void __launch_bounds__(CC_MLP128_THREADS, 1) cc_mlp128_fwd_kernel(con
   const bool worker = true;
 #else
   const int warp = tid >> 5, lane = tid & 31;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ypart + CC_TINY_O * 128);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ypart + 2 * CC_TINY_O * 128);
   uint64_t* a_ready = bars;         // 256 worker arrivals per round
   uint64_t* d_ready = bars + 1;     // [2] one per N half (tcgen05.commit)
   uint64_t* full = bars + 3;        // [3] chunk landed (TMA complete_tx)
@@ -304,15 +310,16 @@ __global__ void __launch_bounds__(CC_MLP128_THREADS, 1) cc_mlp128_fwd_kernel(con
     }
     float yp[CC_TINY_O];
     // y = out_scale * act(g . x + b) from the two halves' partial sums (half 1 -> shared memory -> half 0 writes the output)
+    // (ypart is double buffered by krow parity: the NEXT emit's barrier orders half 0's read against half 1's rewrite)
     auto emit = [&](long long krow) {
+      float* yb = ypart + (krow & 1) * (CC_TINY_O * 128);
       cc_mlp128_readout_part(gw, x, hh, a.O, yp);
       if (hh == 1)
-        for (int o = 0; o < a.O; ++o) ypart[o * 128 + row] = yp[o];
+        for (int o = 0; o < a.O; ++o) yb[o * 128 + row] = yp[o];
       cc_mlp128_worker_sync();
       if (hh == 0 && act)
         for (int o = 0; o < a.O; ++o)
-          a.y[b * (long long)(a.T + 1) * a.O + krow * a.O + o] = a.out_scale * cc_act(a.g.act, yp[o] + ypart[o * 128 + row]);
-      cc_mlp128_worker_sync();  // ypart may be rewritten
+          a.y[b * (long long)(a.T + 1) * a.O + krow * a.O + o] = a.out_scale * cc_act(a.g.act, yp[o] + yb[o * 128 + row]);
     };
     emit(0);  // y0 = g(x0)      neural_ode_model.py:160-175
     float vin[CC_TINY_O];
@@ -327,11 +334,11 @@ __global__ void __launch_bounds__(CC_MLP128_THREADS, 1) cc_mlp128_fwd_kernel(con
           if (cb + s < a.S) a.tape[(ck * a.S + cb + s) * a.Bpad + b] = x[s];
       }
 #pragma unroll
-      for (int c0 = 0; c0 < 64; c0 += 32) {
-        float z[32];
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        float z[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) z[i] = x[c0 + i];
-        cc_mlp_store_split<128, 32>(c.t, cb + c0, z);
+        for (int i = 0; i < 16; ++i) z[i] = x[c0 + i];
+        cc_mlp_store_split<128, 16>(c.t, cb + c0, z);
       }
       if (hh == 0) {
         float vt[CC_TINY_O];
@@ -342,7 +349,8 @@ __global__ void __launch_bounds__(CC_MLP128_THREADS, 1) cc_mlp128_fwd_kernel(con
           for (int i = 0; i < CC_TINY_O; ++i)
             if (i < a.I && act) vin[i] = __ldg(a.u + b * (long long)a.T * a.I + (long long)(k + 1) * a.I + i);
         }
-        const float tail[8] = {0.f, 0.f, 0.f, vt[0], vt[1], vt[2], vt[3], 1.f};
+        float tail[8];
+        tail[0] = 0.f; tail[1] = 0.f; tail[2] = 0.f; tail[3] = vt[0]; tail[4] = vt[1]; tail[5] = vt[2]; tail[6] = vt[3]; tail[7] = 1.f;
         cc_mlp_store_split<128, 8>(c.t, 128, tail);
       }
       cc_mlp128_round(c, a.pack, 0);

@@ -221,6 +221,18 @@ CC_DEV void cc_mlp_readout(const float* gw, const float (&x)[PAD], int O, int ga
   }
 }
 
+// activation of a whole column group: the kind is uniform, so the dispatch happens once per group, not per element
+template <int NC>
+CC_DEV void cc_mlp_act_group(int act, float (&r)[NC]) {
+  if (act == CC_ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < NC; ++i) r[i] = fmaxf(r[i], 0.f);
+  } else if (act == CC_ACT_TANH) {
+#pragma unroll
+    for (int i = 0; i < NC; ++i) r[i] = tanhf(r[i]);
+  }
+}
+
 // hidden layer: h = act(D) -> next layer's input
 template <int PAD>
 CC_DEV void cc_mlp_hidden(const CcMlpTm<PAD>& t, int act) {
@@ -230,8 +242,7 @@ CC_DEV void cc_mlp_hidden(const CcMlpTm<PAD>& t, int act) {
     float r[G];
     cc_mlp_ld<PAD, G>(t, CcMlpTm<PAD>::COL_D + c0, r);
     cc_mlp_wait_ld();
-#pragma unroll
-    for (int i = 0; i < G; ++i) r[i] = cc_act(act, r[i]);
+    cc_mlp_act_group<G>(act, r);
     cc_mlp_store_split<PAD, G>(t, c0, r);
   }
 }
@@ -240,27 +251,34 @@ CC_DEV void cc_mlp_hidden(const CcMlpTm<PAD>& t, int act) {
 //   FINAL: RK4  x <- x + h*(1/6*(acc + k)) ;  Euler x <- x + h*k ; no-integrate x <- k
 template <int PAD, bool FINAL>
 CC_DEV void cc_mlp_last(const CcMlpTm<PAD>& t, int act, float (&x)[PAD], float (&acc)[PAD], float h, float wk, float cz, int integrator) {
-  constexpr int G = PAD < 32 ? PAD : 32;
+  constexpr int G = PAD < 32 ? PAD : (PAD >= 64 ? 16 : 32);  // 64 columns of x and acc are live: small groups keep the temporaries in registers
 #pragma unroll
   for (int c0 = 0; c0 < PAD; c0 += G) {
     float r[G];
     cc_mlp_ld<PAD, G>(t, CcMlpTm<PAD>::COL_D + c0, r);
     cc_mlp_wait_ld();
-    float z[G];
+    cc_mlp_act_group<G>(act, r);
+    if (!FINAL) {
+      float z[G];
 #pragma unroll
-    for (int i = 0; i < G; ++i) {
-      const float k = cc_act(act, r[i]);
-      if (!FINAL) {
-        acc[c0 + i] = fmaf(wk, k, acc[c0 + i]);
-        z[i] = fmaf(h * k, cz, x[c0 + i]);
-      } else {
-        if (integrator == CC_INT_RK4) x[c0 + i] = fmaf(h, (1.f / 6.f) * (acc[c0 + i] + k), x[c0 + i]);
-        else if (integrator == CC_INT_EE) x[c0 + i] = fmaf(h, k, x[c0 + i]);
-        else x[c0 + i] = k;
+      for (int i = 0; i < G; ++i) {
+        acc[c0 + i] = fmaf(wk, r[i], acc[c0 + i]);
+        z[i] = fmaf(h * r[i], cz, x[c0 + i]);
+      }
+      cc_mlp_store_split<PAD, G>(t, c0, z);
+    } else if (integrator == CC_INT_RK4) {
+#pragma unroll
+      for (int i = 0; i < G; ++i) {
+        x[c0 + i] = fmaf(h, (1.f / 6.f) * (acc[c0 + i] + r[i]), x[c0 + i]);
         acc[c0 + i] = 0.f;
       }
+    } else if (integrator == CC_INT_EE) {
+#pragma unroll
+      for (int i = 0; i < G; ++i) x[c0 + i] = fmaf(h, r[i], x[c0 + i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < G; ++i) x[c0 + i] = r[i];
     }
-    if (!FINAL) cc_mlp_store_split<PAD, G>(t, c0, z);
   }
 }
 template <int PAD>
@@ -361,7 +379,8 @@ __global__ void __launch_bounds__(CC_MLP_THREADS, PAD >= 64 ? 2 : 3) cc_mlp_fwd_
       }
       cc_mlp_write_state<PAD>(t, x);
       {
-        const float tail[8] = {0.f, 0.f, 0.f, vt[0], vt[1], vt[2], vt[3], 1.f};
+        float tail[8];
+        tail[0] = 0.f; tail[1] = 0.f; tail[2] = 0.f; tail[3] = vt[0]; tail[4] = vt[1]; tail[5] = vt[2]; tail[6] = vt[3]; tail[7] = 1.f;
         cc_mlp_store_split<PAD, 8>(t, PAD, tail);
       }
       cc_mlp_round<PAD>(t, 0);
