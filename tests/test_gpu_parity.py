@@ -564,3 +564,28 @@ def test_mlp_family_rollout_vs_oracle(name, B, force, T_, monkeypatch):
         floor = l2rel(r32["theta_bar"], ref["theta_bar"])
         tb, _ = ops.rollout_bwd(conv(spec), T_(theta), T_(u), tape, T_(ybar), T_(x0))
         assert l2rel(tb.cpu().numpy(), ref["theta_bar"]) < max(TOL_GRAD, 3 * floor), floor
+
+
+@pytest.mark.parametrize("B", [3000, 8000])
+@pytest.mark.parametrize("mname", ["compact_s50_d0", "euler_s30_d0_tanh"])
+def test_default_plan_forward_reverse_pairs(B, mname, T_):
+    """default environment (no family forced): the forward and reverse plans pick their families independently with different
+    batch thresholds (latency / tcgen05 / FFMA / blocked linear); B = 3000 and 8000 sit in the ranges where the two passes of
+    non-linear depth-0 models come from different families, which the forced-family fixtures never pair"""
+    import ctypes as C
+
+    from chain_control_b200 import _lib, ops
+
+    for k in ("CC_B200_TC", "CC_B200_WPT_MAXB", "CC_B200_LIN", "CC_B200_MLP", "CC_B200_TCW"):
+        assert k not in os.environ
+    spec = tc_model_variants()[mname]
+    T = 40
+    theta = O.init_params(spec, 1, stable=True).astype(np.float32)
+    u = _u(B, T, spec.input_dim)
+    ybar = np.random.default_rng(5).normal(size=(B, T + 1, spec.output_dim)).astype(np.float32)
+    fams = tuple(_lib.lib().cc_kernel_family_at(None, C.byref(conv(spec).to_c()), g, B) for g in (0, 1))
+    ref = CO.rollout(spec, theta, u, ybar=ybar, dtype=np.float64)
+    y, _, tape = ops.rollout_fwd(conv(spec), T_(theta), T_(u), want_tape=True)
+    tb, _ = ops.rollout_bwd(conv(spec), T_(theta), T_(u), tape, T_(ybar))
+    assert normwise(y.cpu().numpy(), ref["y"]) < TOL_STATE, fams
+    assert l2rel(tb.cpu().numpy(), ref["theta_bar"]) < TOL_GRAD, fams
