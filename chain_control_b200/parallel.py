@@ -40,6 +40,33 @@ def allreduce_grad_and_loss(grad: torch.Tensor, loss_partial: torch.Tensor):
     return buf[:-1].reshape(grad.shape), buf[-1]
 
 
+def dp_shard(tree):
+    """this rank's contiguous slice of a batched pytree and its share B_rank / B of the batch (1.0 without a process group)"""
+    from .utils import tree_shape
+
+    rank, ws = world()
+    if ws == 1:
+        return tree, 1.0
+    B = tree_shape(tree)
+    lo, hi = shard_bounds(B, rank, ws)
+    return shard_batch(tree, rank, ws), (hi - lo) / B
+
+
+def dp_combine(grad: torch.Tensor, logs: dict, frac: float):
+    """data-parallel train step of the trainers (cc/train/step_fn.py:150-179,287-322 on a sharded minibatch): every rank holds
+    the gradient and the scalar logs of the MEAN loss over its shard; the batch mean is sum_r (B_r / B) * local, done as ONE
+    allreduce of [gradient ; scalar logs].  Terms that do not depend on the data (regularisers) are identical on all ranks
+    and survive the weighted sum unchanged."""
+    rank, ws = world()
+    if ws == 1:
+        return grad, logs
+    keys = sorted(logs)
+    buf = torch.cat([grad.reshape(-1)] + [torch.as_tensor(logs[k], dtype=grad.dtype, device=grad.device).reshape(1) for k in keys]) * frac
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+    n = grad.numel()
+    return buf[:n].reshape(grad.shape), {k: buf[n + i] for i, k in enumerate(keys)}
+
+
 class HostFeed:
     """Double-buffered host -> device feed for the train step's inputs: the copy of step i+1 (pinned host memory, side
     stream) overlaps the rollout kernels of step i.  Every step still moves its own inputs host -> device; only the

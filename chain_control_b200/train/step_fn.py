@@ -15,6 +15,7 @@ import torch
 from ..core.module_utils import flatten_module
 from ..utils import batch_concat, l1_norm, l2_norm, mse, tree_map
 from .minibatch import Dataloader, MiniBatchState, SupervisedDatasetWithWeights, UnsupervisedDataset
+from .. import parallel
 from .optim import GradientTransformation, apply_updates
 
 
@@ -102,10 +103,13 @@ def make_step_fn_model(model, options: TrainingOptionsModel):
             assert isinstance(mb, SupervisedDatasetWithWeights)
             theta = model.flat_params().detach().requires_grad_(True)
             m = model.with_params(theta)
-            loss, logs = loss_fn_model(m, mb.inputs, mb.targets, mb.weights)
+            # one process per GPU (torch.distributed initialised): every rank takes its slice of the minibatch
+            (inputs, targets, weights), frac = parallel.dp_shard((mb.inputs, mb.targets, mb.weights))
+            loss, logs = loss_fn_model(m, inputs, targets, weights)
             (grads,) = torch.autograd.grad(loss, theta)
             logs = _detach_logs(logs)
             logs["train_loss"] = loss.detach()
+            grads, logs = parallel.dp_combine(grads, logs, frac)
             minibatched_logs.append(logs)
             updates, opt_state = optimizer.update(grads, opt_state, theta.detach())
             model = model.with_params(apply_updates(theta.detach(), updates))
@@ -228,10 +232,12 @@ def make_step_fn_controller(controller, models: dict, options: TrainingOptionsCo
             key = key + 1  # "steal key for simulation of noise in closed loop" (step_fn.py:295-297)
             theta = controller.flat_params().detach().requires_grad_(True)
             c = controller.with_params(theta)
-            loss, logs = loss_fn_controller(c, batch.refss, key)
+            refss, frac = parallel.dp_shard(batch.refss)
+            loss, logs = loss_fn_controller(c, refss, key + 1000003 * parallel.world()[0])  # (independent noise per shard)
             (grads,) = torch.autograd.grad(loss, theta)
             logs = _detach_logs(logs)
             logs["train_loss"] = loss.detach()
+            grads, logs = parallel.dp_combine(grads, logs, frac)
             minibatched_logs.append(logs)
             updates, opt_state = optimizer.update(grads, opt_state)
             controller = controller.with_params(apply_updates(theta.detach(), updates))
