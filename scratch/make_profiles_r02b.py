@@ -65,9 +65,10 @@ md += ["", "Reading: both kernels keep the tensor pipe ~1/3 busy; the rest of a 
 open(f"{P}/r02b_mlp_ncu_full.md", "w").write("\n".join(md))
 
 # ---------------- configs[2] sweep ----------------
-sw = [json.loads(l) for l in open(f"{G}/r02c_sweep_cfg3.jsonl")] if os.path.exists(f"{G}/r02c_sweep_cfg3.jsonl") else []
+swf = next((f for f in ("r02d_sweep_cfg3.jsonl", "r02c_sweep_cfg3.jsonl") if os.path.exists(f"{G}/{f}")), None)
+sw = [json.loads(l) for l in open(f"{G}/{swf}")] if swf else []
 old = {}
-for f in ("r02b_sweep_cfg3.jsonl", "r02_sweep_cfg3.jsonl"):
+for f in ("r02d_sweep_cfg3.jsonl", "r02b_sweep_cfg3.jsonl", "r02_sweep_cfg3.jsonl"):
     if os.path.exists(f"{G}/{f}"):
         for l in open(f"{G}/{f}"):
             r = json.loads(l)
@@ -83,7 +84,7 @@ for r in sw:
     md.append("| %s | %d | %.2f | %.3e | %.1f | %.2f | %s | %s | %s |" % (r["arch"], r["B"], r["ms"], r["traj_steps_per_s"], r["alg_tflops"], r["alg_tflops"] / peak,
               ("%.2f" % o["ms"]) if o else "—", ("%.1f" % o["alg_tflops"]) if o else "—", ("%.2fx" % (o["ms"] / r["ms"])) if o else "—"))
 md += ["", "The (128,128,2) architecture runs on no other family (FFMA: `CC_ERR_UNSUPPORTED`, layers wider than 64).  Below ~8 tiles (B = 1024) every family is one latency-bound wave: the plan keeps the FFMA kernels there",
-       "for the architectures they support.  Raw lines: gpurun_out/r02c_sweep_cfg3.jsonl (not tracked); the three points bench.py re-measures every run are in `config.other_workloads.cfg3`.", ""]
+       "for the architectures they support.  Raw lines: gpurun_out/r02d_sweep_cfg3.jsonl (not tracked); the three points bench.py re-measures every run are in `config.other_workloads.cfg3`.", ""]
 open(f"{P}/r02_cfg3_sweep.md", "w").write("\n".join(md))
 
 # ---------------- SASS summary ----------------

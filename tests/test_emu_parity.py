@@ -284,3 +284,22 @@ def test_emu_mlp_family_fwd(name, monkeypatch):
     rec = tape[: nck * S * Bpad].reshape(nck, S, Bpad)[:, :, :B]  # checkpoints at steps 0, 3, 6: the pre-step states
     for c, k in enumerate(range(0, T, 3)):
         assert normwise(rec[c].T, xs[:, k]) < TOL_STATE
+
+
+def test_emu_mlp_family_edge_cases(monkeypatch):
+    """deep-MLP family: T = 0 (only y0), a single trajectory, four inputs / four outputs, no initial state"""
+    import ctypes as C
+
+    monkeypatch.setenv("CC_B200_MLP", "1")
+    L = E.emu()
+    for spec in (O.make_node(6, 4, 4, f_width=12, f_depth=2, u_transform=O.UT_KTANH, u_scale=2.0),
+                 O.make_node(66, 4, 4, f_width=70, f_depth=1, readout_pre_step=True)):
+        assert L.cc_kernel_family_at(None, C.byref(conv(spec).to_c()), 0, 1) == 5
+        theta = O.init_params(spec, 4).astype(np.float32)
+        for B, T in ((1, 3), (2, 0), (129, 1)):
+            u = _u(B, T, spec.input_dim, seed=B)
+            y64, xs = O.rollout_fwd(spec, theta, u)
+            y, xf, _ = E.np_rollout_fwd(L, conv(spec), theta, u)
+            assert y.shape == (B, T + 1, 4)
+            assert normwise(y, y64) < TOL_STATE, (spec.state_dim, B, T)
+            assert normwise(xf, xs[:, -1]) < TOL_STATE or T == 0
