@@ -5,7 +5,10 @@
 #endif
 #include <cstdio>
 
+#include <cstdlib>
+
 #include "cc_mlp128_kernels.cuh"
+#include "cc_mlp2_kernels.cuh"
 
 namespace {
 template <int PAD>
@@ -31,6 +34,30 @@ int mlp_launch(const CcMlpArgs& a, void* stream, char* err, int errlen) {
   return CC_OK;
 #endif
 }
+template <int PAD>
+int mlp2_launch(const CcMlpArgs& a, void* stream, char* err, int errlen) {
+  using TM = CcMlpTm<PAD>;
+  const long long grid = (a.B + 127) / 128;
+#ifdef CC_EMULATE
+  (void)stream; (void)err; (void)errlen;
+  const size_t smem = ((size_t)CC_MLP_SMEM_FLOATS(PAD, a.L) + (size_t)(TM::COLS + 8) * 128) * 4;
+  ccemu::launch((int)grid, CC_MLP2_THREADS, smem, [&]() { cc_mlp2_fwd_kernel<PAD>(a); });
+  return CC_OK;
+#else
+  const size_t smem = (size_t)CC_MLP_SMEM_FLOATS(PAD, a.L) * 4;
+  cudaError_t e = cudaFuncSetAttribute(cc_mlp2_fwd_kernel<PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) {
+    cc_mlp2_fwd_kernel<PAD><<<(unsigned)grid, CC_MLP2_THREADS, smem, (cudaStream_t)stream>>>(a);
+    e = cudaGetLastError();
+  }
+  if (e != cudaSuccess) {
+    snprintf(err, errlen, "cc_mlp2_fwd_kernel<%d> launch failed: %s", PAD, cudaGetErrorString(e));
+    return CC_ERR_CUDA;
+  }
+  return CC_OK;
+#endif
+}
+
 int mlp128_launch(const CcMlpArgs& a, void* stream, char* err, int errlen) {
   const long long grid = (a.B + 127) / 128;
   if (!a.pack) {
@@ -72,10 +99,15 @@ size_t cc_mlp_smem_bytes(int pad, int L) {
 size_t cc_mlp_workspace_bytes(int pad, int L) { return pad == 128 ? (size_t)2 * L * CC_MLP128_CHUNK_BYTES : 0; }
 
 int cc_launch_mlp_fwd(const CcMlpArgs& a, int pad, void* stream, char* err, int errlen) {
+  // two threads per trajectory (cc_mlp2_kernels.cuh): measured on B200 (gpurun_out/r02e_sweep_nh*.jsonl) +4 % at large batch and
+  // +8 % in the one-wave regime for the 64-wide variant; the 32-wide one-thread kernel keeps 3 CTAs per SM and stays ahead
+  // (72 vs 62 TFLOP/s algorithmic).  CC_B200_MLP_NH=1 / 2 forces a variant (tests run both).
+  const char* nh = getenv("CC_B200_MLP_NH");
+  const int force = nh ? atoi(nh) : 0;
   switch (pad) {
     case 16: return mlp_launch<16>(a, stream, err, errlen);
-    case 32: return mlp_launch<32>(a, stream, err, errlen);
-    case 64: return mlp_launch<64>(a, stream, err, errlen);
+    case 32: return force == 2 ? mlp2_launch<32>(a, stream, err, errlen) : mlp_launch<32>(a, stream, err, errlen);
+    case 64: return force == 1 ? mlp_launch<64>(a, stream, err, errlen) : mlp2_launch<64>(a, stream, err, errlen);
     case 128: return mlp128_launch(a, stream, err, errlen);
     default: snprintf(err, errlen, "deep-MLP tcgen05 family: padded width %d not built", pad); return CC_ERR_UNSUPPORTED;
   }

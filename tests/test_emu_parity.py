@@ -257,7 +257,8 @@ def test_emu_fused_optimiser_step(hp):
 
 @pytest.mark.parametrize("name", ["full_s5_w10_d2", "euler_s9", "full_s32_w32_d2_i2_o3", "noint_s7_w20_d1", "compact_s40_w64_d3_tanh_nobias",
                                   "full_s128_w128_d2", "compact_s70_w100_d1_i2_o2"])
-def test_emu_mlp_family_fwd(name, monkeypatch):
+@pytest.mark.parametrize("nh", ["1", "2"])
+def test_emu_mlp_family_fwd(name, nh, monkeypatch):
     """deep-MLP tcgen05 forward family (cc_mlp_kernels.cuh) on the CPU emulation of its TMEM / MMA layer: B = 133 (two tiles,
     one ragged), outputs + final state + the tape against the fp64 oracle"""
     import ctypes as C
@@ -265,7 +266,10 @@ def test_emu_mlp_family_fwd(name, monkeypatch):
     from ccspecs import mlp_model_variants
 
     monkeypatch.setenv("CC_B200_MLP", "1")
+    monkeypatch.setenv("CC_B200_MLP_NH", nh)  # one / two threads per trajectory where both kernels exist (padded widths 32, 64)
     spec = mlp_model_variants()[name]
+    if nh == "2" and (spec.state_dim > 64 or max(spec.f.sizes[1:]) > 64 or max(spec.state_dim, max(spec.f.sizes[1:])) <= 16):
+        pytest.skip("one variant only")
     L = E.emu()
     B, T = 133, (4 if spec.state_dim > 64 else 7)
     assert L.cc_kernel_family_at(None, C.byref(conv(spec).to_c()), 0, B) == 5

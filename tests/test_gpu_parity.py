@@ -528,8 +528,8 @@ def test_full_size_gradient_vs_oracle(closed, T_):
 
 
 @pytest.mark.parametrize("name", list(mlp_model_variants()))
-@pytest.mark.parametrize("B,force", [(301, "1"), (2500, None)])
-def test_mlp_family_rollout_vs_oracle(name, B, force, T_, monkeypatch):
+@pytest.mark.parametrize("B,force,nh", [(301, "1", "1"), (2500, None, None), (700, "1", "2")])
+def test_mlp_family_rollout_vs_oracle(name, B, force, nh, T_, monkeypatch):
     """deep-MLP tcgen05 forward family (cc_mlp_kernels.cuh): outputs, final state and the tape it leaves for the FFMA
     reverse pass against the fp64 oracle; B = 301 (3 tiles, ragged) forced, B = 2500 as the default plan picks it"""
     import ctypes as C
@@ -538,6 +538,8 @@ def test_mlp_family_rollout_vs_oracle(name, B, force, T_, monkeypatch):
 
     if force:
         monkeypatch.setenv("CC_B200_MLP", force)
+    if nh:  # one / two threads per trajectory (cc_mlp_kernels.cuh / cc_mlp2_kernels.cuh); default: the plan's choice
+        monkeypatch.setenv("CC_B200_MLP_NH", nh)
     spec = mlp_model_variants()[name]
     T = 60
     assert _lib.lib().cc_kernel_family_at(None, C.byref(conv(spec).to_c()), 0, B) == 5
