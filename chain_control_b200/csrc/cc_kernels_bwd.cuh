@@ -14,23 +14,26 @@
 #pragma once
 #include "cc_kernels.cuh"
 
-#define CC_WN 4 /* weight-gradient thread tile: 4 outputs x 8 inputs */
-#define CC_WK 8
-
+// weight-gradient thread tile: WN outputs x WK inputs per lane; 4 x 8 for wide layers, smaller tiles for the narrow layers of
+// the reference's default networks (width 10: a 4 x 8 tiling gives 6 tiles, i.e. 6 busy lanes of 32 -- ncu on the CLI
+// architecture showed 13 k of the 21 k FFMA warp-instructions per step in this routine at 19 % lane utilisation)
+template <int WN, int WK>
 struct CcWFrag {
-  float4 d[CC_WN], a[CC_WK];
+  float4 d[WN], a[WK];
 };
-CC_DEV void cc_wfrag_load(CcWFrag& f, const float* const (&dptr)[CC_WN], const float* const (&aptr)[CC_WK], int q) {
+template <int WN, int WK>
+CC_DEV void cc_wfrag_load(CcWFrag<WN, WK>& f, const float* const (&dptr)[WN], const float* const (&aptr)[WK], int q) {
 #pragma unroll
-  for (int i = 0; i < CC_WN; ++i) f.d[i] = *reinterpret_cast<const float4*>(dptr[i] + q);
+  for (int i = 0; i < WN; ++i) f.d[i] = *reinterpret_cast<const float4*>(dptr[i] + q);
 #pragma unroll
-  for (int j = 0; j < CC_WK; ++j) f.a[j] = *reinterpret_cast<const float4*>(aptr[j] + q);
+  for (int j = 0; j < WK; ++j) f.a[j] = *reinterpret_cast<const float4*>(aptr[j] + q);
 }
-CC_DEV void cc_wfrag_fma(const CcWFrag& f, float (&acc)[CC_WN][CC_WK]) {
+template <int WN, int WK>
+CC_DEV void cc_wfrag_fma(const CcWFrag<WN, WK>& f, float (&acc)[WN][WK]) {
 #pragma unroll
-  for (int i = 0; i < CC_WN; ++i)
+  for (int i = 0; i < WN; ++i)
 #pragma unroll
-    for (int j = 0; j < CC_WK; ++j) {
+    for (int j = 0; j < WK; ++j) {
       acc[i][j] = fmaf(f.d[i].x, f.a[j].x, acc[i][j]);
       acc[i][j] = fmaf(f.d[i].y, f.a[j].y, acc[i][j]);
       acc[i][j] = fmaf(f.d[i].z, f.a[j].z, acc[i][j]);
@@ -38,52 +41,60 @@ CC_DEV void cc_wfrag_fma(const CcWFrag& f, float (&acc)[CC_WN][CC_WK]) {
     }
 }
 
-// G[n][r] += sum_{traj<32} D[n][traj] * A[r][traj].  4x8 output tiles are dealt to the 32 lanes; each
+// G[n][r] += sum_{traj<32} D[n][traj] * A[r][traj].  WN x WK output tiles are dealt to the 32 lanes; each
 // lane walks the 8 trajectory quads in a lane-rotated order so that the LDS.128 of a quarter-warp hit 8
 // different bank quads whatever rows they touch; the operands of quad q+1 are fetched while the FMAs of
-// quad q issue.
-CC_DEV void cc_wgrad(const CcLayerDev& L, const float* D, const float* A, const CcWarp& w) {
-  const int NT = (L.N + CC_WN - 1) / CC_WN;
-  const int KT = (L.K + CC_WK - 1) / CC_WK;
+// quad q issue.  (Run-to-run deterministic; the rotated quad order depends on the owning lane, so different tile shapes
+// differ in the last bit.)
+template <int WN, int WK>
+CC_DEV void cc_wgrad_t(const CcLayerDev& L, const float* D, const float* A, const CcWarp& w) {
+  const int NT = (L.N + WN - 1) / WN;
+  const int KT = (L.K + WK - 1) / WK;
   float* G = cc_ws(w) + L.w_gw;
 #pragma unroll 1
   for (int tile = w.lane; tile < NT * KT; tile += 32) {
     const int nt = tile / KT, kt = tile % KT;
-    float acc[CC_WN][CC_WK];
+    float acc[WN][WK];
 #pragma unroll
-    for (int i = 0; i < CC_WN; ++i)
+    for (int i = 0; i < WN; ++i)
 #pragma unroll
-      for (int j = 0; j < CC_WK; ++j) acc[i][j] = 0.f;
-    const float* dptr[CC_WN];
-    const float* aptr[CC_WK];
-    bool nok[CC_WN], rok[CC_WK];
+      for (int j = 0; j < WK; ++j) acc[i][j] = 0.f;
+    const float* dptr[WN];
+    const float* aptr[WK];
+    bool nok[WN], rok[WK];
 #pragma unroll
-    for (int i = 0; i < CC_WN; ++i) {
+    for (int i = 0; i < WN; ++i) {
       const int n = nt + NT * i;
       nok[i] = n < L.N;
       dptr[i] = D + (nok[i] ? n : 0) * CC_LD;
     }
 #pragma unroll
-    for (int j = 0; j < CC_WK; ++j) {
+    for (int j = 0; j < WK; ++j) {
       const int r = kt + KT * j;
       rok[j] = r < L.K;
       aptr[j] = A + (rok[j] ? r : 0) * CC_LD;
     }
-    CcWFrag cur, nxt;
-    cc_wfrag_load(cur, dptr, aptr, 4 * (w.lane & 7));
+    CcWFrag<WN, WK> cur, nxt;
+    cc_wfrag_load<WN, WK>(cur, dptr, aptr, 4 * (w.lane & 7));
 #pragma unroll
     for (int qq = 1; qq < 8; ++qq) {
-      cc_wfrag_load(nxt, dptr, aptr, 4 * ((qq + w.lane) & 7));
-      cc_wfrag_fma(cur, acc);
+      cc_wfrag_load<WN, WK>(nxt, dptr, aptr, 4 * ((qq + w.lane) & 7));
+      cc_wfrag_fma<WN, WK>(cur, acc);
       cur = nxt;
     }
-    cc_wfrag_fma(cur, acc);
+    cc_wfrag_fma<WN, WK>(cur, acc);
 #pragma unroll
-    for (int i = 0; i < CC_WN; ++i)
+    for (int i = 0; i < WN; ++i)
 #pragma unroll
-      for (int j = 0; j < CC_WK; ++j)
+      for (int j = 0; j < WK; ++j)
         if (nok[i] && rok[j]) G[(nt + NT * i) * L.K + kt + KT * j] += acc[i][j];
   }
+}
+CC_DEV void cc_wgrad(const CcLayerDev& L, const float* D, const float* A, const CcWarp& w) {
+  // the largest tile that still gives (nearly) every lane work
+  if (((L.N + 3) / 4) * ((L.K + 7) / 8) >= 24) cc_wgrad_t<4, 8>(L, D, A, w);
+  else if (((L.N + 1) / 2) * ((L.K + 3) / 4) >= 24) cc_wgrad_t<2, 4>(L, D, A, w);
+  else cc_wgrad_t<2, 2>(L, D, A, w);
 }
 
 // VB[iv][traj] += sum_n WV[iv][n] * d[traj][n]  with d the register tile of layer-0 cotangents:
