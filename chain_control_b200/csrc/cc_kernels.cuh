@@ -364,6 +364,28 @@ CC_DEV void cc_tape_store(const CcKParams& p, const CcNodeDev& nd, int ck, const
 // One step of a tile-path node.  On entry X holds [x ; t ; v ; 1] and Z the same v / 1 rows.
 // On exit X holds x_next and OUT the readout.  keep (backward recompute): stage inputs stay in
 // ZS[0..3], hidden activations / k_i are kept per stage, X keeps x.  Ends with __syncwarp().
+// A node whose layers and state need at most 4 columns per column group (widths <= 16: the reference's default networks,
+// width 10) runs with a [4][4] register tile instead of [4][8]: the shared-memory layout is the same (group stride 8), the
+// register-tiled products issue half the FMAs (ncu on the CLI architecture: 3 of 8 tile columns carried data).
+CC_DEV bool cc_node_fits4(const CcNodeDev& nd) {
+  if (nd.tiny || nd.cptS > 4) return false;
+  for (int l = 0; l < nd.f.L; ++l)
+    if (nd.f.layer[l].cpt > 4 || nd.f.layer[l].kcpt > 4) return false;
+  for (int l = 0; l < nd.g.L; ++l)
+    if (nd.g.layer[l].cpt > 4 || nd.g.layer[l].kcpt > 4) return false;
+  return true;
+}
+// call fn<4> when the node fits the narrow tile (only instantiated next to the 8-wide tile), else fn<TN>
+#define CC_TILE_DISPATCH(TNV, small4, fn, ...)   \
+  do {                                            \
+    if constexpr ((TNV) == 8) {                   \
+      if (small4) fn<4>(__VA_ARGS__);             \
+      else fn<8>(__VA_ARGS__);                    \
+    } else {                                      \
+      fn<TNV>(__VA_ARGS__);                       \
+    }                                             \
+  } while (0)
+
 template <int TN>
 CC_DEV_NOINLINE void cc_node_step(int node, const CcWarp w, float t, bool keep, bool do_readout, bool write_tape,
                                   int ck) {
@@ -667,6 +689,7 @@ __global__ void __launch_bounds__(256, 1) cc_rollout_fwd_kernel(const CC_GRID_CO
   const bool closed = CM != CC_CTRL_NONE;
   const CcNodeDev& M = p.nd[closed ? 1 : 0];
   const CcNodeDev& C = p.nd[0];
+  const bool m4 = cc_node_fits4(M), c4 = CM == CC_CTRL_TILE && cc_node_fits4(C);  // narrow [4][4] register tiles
   for (int n = 0; n < p.n_nodes; ++n) {
     cc_stage_mlp(p.nd[n], p.nd[n].f, p.theta[n], cta_smem, threadIdx.x, blockDim.x);
     cc_stage_mlp(p.nd[n], p.nd[n].g, p.theta[n], cta_smem, threadIdx.x, blockDim.x);
@@ -755,7 +778,7 @@ __global__ void __launch_bounds__(256, 1) cc_rollout_fwd_kernel(const CC_GRID_CO
       } else {
         cc_set_inputs(C, w, vc, tc, 0);
         __syncwarp();
-        cc_node_step<8>(0, w, tc, false, true, wt, ck);
+        CC_TILE_DISPATCH(8, c4, cc_node_step, 0, w, tc, false, true, wt, ck);
 #pragma unroll
         for (int i = 0; i < CC_TINY_O; ++i) a[i] = (i < M.I) ? cc_ws(w)[C.w_OUT + i * CC_LD + w.lane] : 0.f;
       }
@@ -768,7 +791,7 @@ __global__ void __launch_bounds__(256, 1) cc_rollout_fwd_kernel(const CC_GRID_CO
       for (int i = 0; i < CC_TINY_K; ++i) am[i] = (i < CC_TINY_O) ? a[i < CC_TINY_O ? i : 0] : 0.f;
       cc_set_inputs(M, w, am, tm, 0);
       __syncwarp();
-      cc_node_step<TN>(closed ? 1 : 0, w, tm, false, true, wt, ck);
+      CC_TILE_DISPATCH(TN, m4, cc_node_step, closed ? 1 : 0, w, tm, false, true, wt, ck);
       for (int o = 0; o < M.O; ++o) {
         float y = cc_ws(w)[M.w_OUT + o * CC_LD + w.lane];
         if (p.noise && act) y += __ldg(p.noise + b * (long long)p.T * M.O + (long long)k * M.O + o);
@@ -779,7 +802,7 @@ __global__ void __launch_bounds__(256, 1) cc_rollout_fwd_kernel(const CC_GRID_CO
     } else {
       cc_set_inputs(M, w, vcur, tm, 0);
       __syncwarp();
-      cc_node_step<TN>(closed ? 1 : 0, w, tm, false, true, wt, ck);
+      CC_TILE_DISPATCH(TN, m4, cc_node_step, closed ? 1 : 0, w, tm, false, true, wt, ck);
       if (act && p.out)
         for (int o = 0; o < M.O; ++o) p.out[b * (long long)(p.T + 1) * M.O + (long long)(k + 1) * M.O + o] = cc_ws(w)[M.w_OUT + o * CC_LD + w.lane];
     }

@@ -415,6 +415,7 @@ __global__ void __launch_bounds__(256, 1) cc_rollout_bwd_kernel(const CC_GRID_CO
   const bool closed = CM != CC_CTRL_NONE;
   const CcNodeDev& M = p.nd[closed ? 1 : 0];
   const CcNodeDev& C = p.nd[0];
+  const bool m4 = cc_node_fits4(M), c4 = CM == CC_CTRL_TILE && cc_node_fits4(C);  // narrow [4][4] register tiles
   for (int n = 0; n < p.n_nodes; ++n) {
     cc_stage_mlp(p.nd[n], p.nd[n].f, p.theta[n], cta_smem, threadIdx.x, blockDim.x);
     cc_stage_mlp(p.nd[n], p.nd[n].g, p.theta[n], cta_smem, threadIdx.x, blockDim.x);
@@ -517,7 +518,7 @@ __global__ void __launch_bounds__(256, 1) cc_rollout_bwd_kernel(const CC_GRID_CO
         cc_tape_load<8>(p, C, k - k_beg, w);
         cc_set_inputs(C, w, vc, tc, 1);
         __syncwarp();
-        cc_node_step<8>(0, w, tc, true, true, false, 0);
+        CC_TILE_DISPATCH(8, c4, cc_node_step, 0, w, tc, true, true, false, 0);
 #pragma unroll
         for (int i = 0; i < CC_TINY_O; ++i) a[i] = (i < M.I) ? cc_ws(w)[C.w_OUT + i * CC_LD + w.lane] : 0.f;
       }
@@ -535,8 +536,8 @@ __global__ void __launch_bounds__(256, 1) cc_rollout_bwd_kernel(const CC_GRID_CO
       for (int o = 0; o < CC_TINY_O; ++o)
         if (o < M.O) cc_ws(w)[M.w_OB + o * CC_LD + w.lane] = yb[o] + cc_ws(w)[p.w_yfb + o * CC_LD + w.lane];
       __syncwarp();
-      if (M.recompute) cc_node_step<TN>(closed ? 1 : 0, w, tm, true, true, false, 0);
-      cc_node_bwd<TN>(closed ? 1 : 0, w, p.w_araw);
+      if (M.recompute) CC_TILE_DISPATCH(TN, m4, cc_node_step, closed ? 1 : 0, w, tm, true, true, false, 0);
+      CC_TILE_DISPATCH(TN, m4, cc_node_bwd, closed ? 1 : 0, w, p.w_araw);
       // cotangent of the controller output = cotangent of the model input
       if (CM == CC_CTRL_TINY) {
         float ob[CC_TINY_O], vb[CC_TINY_O];
@@ -553,7 +554,7 @@ __global__ void __launch_bounds__(256, 1) cc_rollout_bwd_kernel(const CC_GRID_CO
       } else {
         for (int i = 0; i < M.I; ++i) cc_ws(w)[C.w_OB + i * CC_LD + w.lane] = cc_ws(w)[M.w_VB + i * CC_LD + w.lane];
         __syncwarp();
-        cc_node_bwd<8>(0, w, -1);
+        CC_TILE_DISPATCH(8, c4, cc_node_bwd, 0, w, -1);
         for (int o = 0; o < M.O; ++o) cc_ws(w)[p.w_yfb + o * CC_LD + w.lane] = cc_ws(w)[C.w_VB + (p.R + o) * CC_LD + w.lane];
       }
       __syncwarp();
@@ -568,8 +569,8 @@ __global__ void __launch_bounds__(256, 1) cc_rollout_bwd_kernel(const CC_GRID_CO
       for (int o = 0; o < CC_TINY_O; ++o)
         if (o < M.O) cc_ws(w)[M.w_OB + o * CC_LD + w.lane] = yb[o];
       __syncwarp();
-      if (M.recompute) cc_node_step<TN>(closed ? 1 : 0, w, tm, true, true, false, 0);
-      cc_node_bwd<TN>(closed ? 1 : 0, w, p.w_araw);
+      if (M.recompute) CC_TILE_DISPATCH(TN, m4, cc_node_step, closed ? 1 : 0, w, tm, true, true, false, 0);
+      CC_TILE_DISPATCH(TN, m4, cc_node_bwd, closed ? 1 : 0, w, p.w_araw);
       if (p.ubar && act)
         for (int i = 0; i < M.I; ++i) p.ubar[b * (long long)p.T * M.I + (long long)k * M.I + i] = cc_ws(w)[M.w_VB + i * CC_LD + w.lane];
     }
