@@ -161,7 +161,8 @@ int node_max_cpt(const CcModule* m);
 // deep-MLP tcgen05 forward family (cc_mlp_kernels.cuh, family 5): open-loop forward of a model whose f is a deep MLP
 // (2..4 Linear layers) and whose g is one Linear layer, time-invariant, no feed-through, every width <= 128 (beyond 64 the
 // weights are streamed through a shared-memory ring, cc_mlp128_kernels.cuh).  Returns the padded width (16 / 32 / 64 / 128) or 0.  CC_B200_MLP=0 disables the family, =1 takes it at any batch size.
-int mlp_fwd_pad(const CcModule* m, long long B) {
+// padded width of the family-5 kernels for this architecture whatever the batch size (0: not a family-5 architecture)
+int mlp_pad_any(const CcModule* m) {
   const char* env = getenv("CC_B200_MLP");
   if (env && atoi(env) == 0) return 0;
   if (m->f.n_layers < 2 || m->g.n_layers != 1 || m->f_time_variant || m->g_time_variant || m->g_feedthrough_u) return 0;
@@ -171,10 +172,28 @@ int mlp_fwd_pad(const CcModule* m, long long B) {
     if (m->f.sizes[l] > w) w = m->f.sizes[l];
   const int pad = w <= 16 ? 16 : (w <= 32 ? 32 : (w <= 64 ? 64 : (w <= 128 ? 128 : 0)));
   if (!pad || cc_mlp_smem_bytes(pad, m->f.n_layers) > (size_t)kSmemBudget) return 0;
+  return pad;
+}
+int mlp_fwd_pad(const CcModule* m, long long B) {
+  const char* env = getenv("CC_B200_MLP");
+  const int pad = mlp_pad_any(m);
+  if (!pad) return 0;
   // below ~8 tiles the autonomous-warp FFMA kernels (32 trajectories per warp, no CTA-wide round trips) are at least as fast
   const bool ffma_can = tile_width_for(node_max_cpt(m)) != 0;
   const long long minb = (env && atoi(env) == 1) ? 1 : (ffma_can ? 1024 : 1);
   return B >= minb ? pad : 0;
+}
+// deep-MLP tcgen05 REVERSE pass (cc_mlpb_kernels.cuh, family 6): family-5 architecture with 2 or 3 Linear layers in f, every
+// width <= 64, g without activation.  Taken where the FFMA reverse pass runs one or two warps per SM or not at all (some
+// width > 32); CC_B200_MLPB=0 disables it, =1 takes it for every eligible architecture.  The forward pass of such a model
+// runs on family 5 whenever a tape is requested (it appends the final state to the tape).
+bool mlpb_ok(const CcModule* m) {
+  const char* env = getenv("CC_B200_MLPB");
+  if (env && atoi(env) == 0) return false;
+  const int pad = mlp_pad_any(m);
+  if (!pad || pad > 64) return false;
+  if (m->f.n_layers > 3 || m->g.act_final != CC_ACT_IDENTITY) return false;
+  return pad == 64 || (env && atoi(env) == 1);
 }
 void mlp_args(const CcModule* m, CcMlpArgs* a) {
   memset(a, 0, sizeof(*a));
@@ -648,6 +667,7 @@ int32_t cc_module_supported(const CcModule* m, int32_t with_grad) {
   o.bwd = with_grad != 0;
   const CcModule* mods[1] = {m};
   if (!with_grad && mlp_fwd_pad(m, 65536)) return CC_OK;
+  if (with_grad && mlpb_ok(m)) return CC_OK;
   return make_plan(mods, 1, 65536, 1000, o, &p);
 }
 
@@ -659,6 +679,7 @@ int32_t cc_kernel_family_at(const CcModule* c, const CcModule* m, int32_t with_g
   if (rc) return rc;
   if (c && (rc = validate_module(c, "controller"))) return rc;
   if (!c && !with_grad && mlp_fwd_pad(m, B)) return 5;
+  if (!c && with_grad && mlpb_ok(m)) return 6;
   CcKParams p;
   PlanOpts o;
   o.bwd = with_grad != 0;
@@ -678,7 +699,9 @@ size_t cc_rollout_tape_bytes(const CcModule* m, int64_t B, int32_t T, int32_t ck
     if (!validate_module(m, "model") && !make_plan(mods, 1, B, T, o, &p) && p.tc == 4)
       return ((size_t)((T + p.lin_m - 1) / p.lin_m) * m->state_dim * Bpad + 2 * (size_t)T) * sizeof(float);
   }
-  return ((size_t)n_ckpt_of(T, ckpt_every) * m->state_dim * Bpad + 2 * (size_t)T) * sizeof(float);
+  // (family 6 reads the final state behind the step times)
+  const size_t xT = (ckpt_every == 1 && !validate_module(m, "model") && mlpb_ok(m)) ? (size_t)m->state_dim * Bpad : 0;
+  return ((size_t)n_ckpt_of(T, ckpt_every) * m->state_dim * Bpad + 2 * (size_t)T + xT) * sizeof(float);
 }
 
 size_t cc_closedloop_tape_bytes(const CcModule* c, const CcModule* m, int64_t B, int32_t Tr, int32_t ckpt_every) {
@@ -719,7 +742,8 @@ int32_t cc_rollout_fwd(const CcModule* m, const float* theta, const float* u, co
   if (B < 0 || T < 0) return fail(CC_ERR_INVALID_ARG, "negative size");
   if (tape && ckpt_every < 1) return fail(CC_ERR_INVALID_ARG, "ckpt_every must be >= 1");
   if (B == 0) return CC_OK;
-  if (const int pad = mlp_fwd_pad(m, B)) {  // deep-MLP model: one tcgen05.mma batch per layer (cc_mlp_kernels.cuh)
+  const bool rev6 = tape && ckpt_every == 1 && mlpb_ok(m);  // the tcgen05 reverse pass will read this tape
+  if (const int pad = rev6 ? mlp_pad_any(m) : mlp_fwd_pad(m, B)) {  // deep-MLP model: one tcgen05.mma batch per layer (cc_mlp_kernels.cuh)
     CcMlpArgs a;
     mlp_args(m, &a);
     a.theta = theta; a.u = u; a.x0 = x0; a.y = y; a.x_final = x_final;
@@ -727,6 +751,7 @@ int32_t cc_rollout_fwd(const CcModule* m, const float* theta, const float* u, co
     a.tape = (float*)tape;
     a.ckpt_every = tape ? ckpt_every : 1;
     a.ttab = tape ? (float*)tape + (long long)n_ckpt_of(T, a.ckpt_every) * m->state_dim * a.Bpad : nullptr;
+    a.tape_xT = rev6 ? a.ttab + 2 * (long long)T : nullptr;
     const size_t need = cc_mlp_workspace_bytes(pad, a.L);
     if (need && (!ws || ws_bytes < need)) return fail(CC_ERR_WORKSPACE, "workspace too small: need %zu bytes (cc_rollout_fwd_workspace_bytes)", need);
     a.pack = need ? (float*)ws : nullptr;

@@ -9,6 +9,7 @@
 
 #include "cc_mlp128_kernels.cuh"
 #include "cc_mlp2_kernels.cuh"
+#include "cc_mlpb_kernels.cuh"
 
 namespace {
 template <int PAD>
@@ -86,7 +87,66 @@ int mlp128_launch(const CcMlpArgs& a, void* stream, char* err, int errlen) {
   return CC_OK;
 #endif
 }
+template <int L>
+int mlpb_launch(const CcMlpArgs& a, void* stream, char* err, int errlen) {
+  const long long grid = (a.B + 127) / 128;
+#ifdef CC_EMULATE
+  (void)stream; (void)err; (void)errlen;
+  const size_t smem = ((size_t)CC_MLPB_SMEM_FLOATS + 16 + (size_t)512 * 128) * 4;
+  ccemu::launch((int)grid, CC_MLPB_WORKERS, smem, [&]() { cc_mlpb_bwd_kernel<L>(a); });
+  return CC_OK;
+#else
+  const size_t smem = (size_t)CC_MLPB_SMEM_FLOATS * 4;
+  cudaError_t e = cudaFuncSetAttribute(cc_mlpb_bwd_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) {
+    cc_mlpb_bwd_kernel<L><<<(unsigned)grid, CC_MLPB_THREADS, smem, (cudaStream_t)stream>>>(a);
+    e = cudaGetLastError();
+  }
+  if (e != cudaSuccess) {
+    snprintf(err, errlen, "cc_mlpb_bwd_kernel<%d> launch failed: %s", L, cudaGetErrorString(e));
+    return CC_ERR_CUDA;
+  }
+  return CC_OK;
+#endif
+}
 }  // namespace
+
+size_t cc_mlpb_workspace_bytes(int L, long long B) {
+  return ((size_t)2 * L * CC_MLPB_SLAB_FLOATS + (size_t)((B + 127) / 128) * CC_MLPB_CTA_FLOATS(L)) * 4;
+}
+
+// prep (operand slabs) -> reverse kernel (per-CTA sums) -> reduction into theta_bar
+int cc_launch_mlpb_bwd(CcMlpArgs a, float* theta_bar, int P, void* ws, void* stream, char* err, int errlen) {
+  a.pack = (float*)ws;
+  a.recs = a.pack + (size_t)2 * a.L * CC_MLPB_SLAB_FLOATS;
+  const char* fe = getenv("CC_B200_MLPB_FLUSH");
+  a.flush_every = fe && atoi(fe) >= 1 ? atoi(fe) : 2;
+  const int n_cta = (int)((a.B + 127) / 128);
+#ifdef CC_EMULATE
+  ccemu::launch(2 * a.L, 256, 0, [&]() { cc_mlpb_prep_kernel(a); });
+#else
+  cc_mlpb_prep_kernel<<<2 * a.L, 256, 0, (cudaStream_t)stream>>>(a);
+  if (cudaError_t e = cudaGetLastError(); e != cudaSuccess) {
+    snprintf(err, errlen, "cc_mlpb_prep_kernel launch failed: %s", cudaGetErrorString(e));
+    return CC_ERR_CUDA;
+  }
+#endif
+  int rc;
+  if (a.L == 2) rc = mlpb_launch<2>(a, stream, err, errlen);
+  else if (a.L == 3) rc = mlpb_launch<3>(a, stream, err, errlen);
+  else { snprintf(err, errlen, "deep-MLP tcgen05 reverse pass: %d layers not built", a.L); return CC_ERR_UNSUPPORTED; }
+  if (rc) return rc;
+#ifdef CC_EMULATE
+  ccemu::launch((P + 127) / 128, 128, 0, [&]() { cc_mlpb_reduce_kernel(a, theta_bar, n_cta, P); });
+#else
+  cc_mlpb_reduce_kernel<<<(P + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a, theta_bar, n_cta, P);
+  if (cudaError_t e = cudaGetLastError(); e != cudaSuccess) {
+    snprintf(err, errlen, "cc_mlpb_reduce_kernel launch failed: %s", cudaGetErrorString(e));
+    return CC_ERR_CUDA;
+  }
+#endif
+  return CC_OK;
+}
 
 // shared memory of one CTA (bytes) for padded width `pad` and `L` layers: the plan checks it against the 227 KB budget
 size_t cc_mlp_smem_bytes(int pad, int L) {

@@ -26,9 +26,17 @@ struct CcMlpArgs {
   int ckpt_every;
   long long B, Bpad;
   int T;
+  // reverse pass (cc_mlpb_kernels.cuh)
+  float* tape_xT;     // [S][Bpad] final state behind the step times (written by the forward kernels when set)
+  const float* ybar;  // [B][T+1][O]
+  float* recs;        // per-CTA sums and stage-input slots
+  int flush_every;    // steps between flushes of the weight-gradient accumulators
 };
 
 
 size_t cc_mlp_smem_bytes(int pad, int L);
 size_t cc_mlp_workspace_bytes(int pad, int L);
 int cc_launch_mlp_fwd(const CcMlpArgs& a, int pad, void* stream, char* err, int errlen);
+// reverse pass (widths <= 64): workspace = [2 L slabs][per-CTA records]; theta_bar gets all P parameters
+size_t cc_mlpb_workspace_bytes(int L, long long B);
+int cc_launch_mlpb_bwd(CcMlpArgs a, float* theta_bar, int P, void* ws, void* stream, char* err, int errlen);

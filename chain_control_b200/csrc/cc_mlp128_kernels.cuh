@@ -377,6 +377,10 @@ __global__ void __launch_bounds__(CC_MLP128_THREADS, 1) cc_mlp128_fwd_kernel(con
 #pragma unroll
       for (int s = 0; s < 64; ++s)
         if (cb + s < a.S) a.x_final[b * a.S + cb + s] = x[s];
+    if (a.tape_xT && act)
+#pragma unroll
+      for (int s = 0; s < 64; ++s)
+        if (cb + s < a.S) a.tape_xT[(size_t)(cb + s) * a.Bpad + b] = x[s];
   }
 #ifndef CC_EMULATE
   cc_tc_fence_before();

@@ -296,6 +296,10 @@ __global__ void __launch_bounds__(CC_MLP2_THREADS, 2) cc_mlp2_fwd_kernel(const C
 #pragma unroll
       for (int s = 0; s < PC; ++s)
         if (cb + s < a.S) a.x_final[b * a.S + cb + s] = x[s];
+    if (a.tape_xT && act)
+#pragma unroll
+      for (int s = 0; s < PC; ++s)
+        if (cb + s < a.S) a.tape_xT[(size_t)(cb + s) * a.Bpad + b] = x[s];
     // the last stash has no round behind it: CTA barrier
 #ifndef CC_EMULATE
     cc_tmem_wait_st();

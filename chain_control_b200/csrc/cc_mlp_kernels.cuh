@@ -417,6 +417,10 @@ __global__ void __launch_bounds__(CC_MLP_THREADS, PAD >= 64 ? 2 : 3) cc_mlp_fwd_
 #pragma unroll
       for (int s = 0; s < PAD; ++s)
         if (s < a.S) a.x_final[b * a.S + s] = x[s];
+    if (a.tape_xT && act)  // final state for the tcgen05 reverse pass (cc_mlpb_kernels.cuh)
+#pragma unroll
+      for (int s = 0; s < PAD; ++s)
+        if (s < a.S) a.tape_xT[(size_t)s * a.Bpad + b] = x[s];
   }
 #ifndef CC_EMULATE
   cc_tc_fence_before();
