@@ -205,7 +205,7 @@ def run_reference(args):
 
 
 def cfg3_points(torch, dev, fp32_peak_tflops, cpu_threads):
-    """BASELINE.json configs[2] (forward-only sweep, MLP width 32..128): three (architecture, batch) points, T = 1000"""
+    """BASELINE.json configs[2] (sweep, MLP width 32..128): three (architecture, batch) points, T = 1000, forward and forward + BPTT"""
     import ctypes as _C
 
     from chain_control_b200 import _lib, arch as A, ops
@@ -241,6 +241,26 @@ def cfg3_points(torch, dev, fp32_peak_tflops, cpu_threads):
         fl = 2 * (4 * mf + mg)
         pt = {"arch": f"S{S}_W{S}_d2", "B": B, "T": T, "kernel_family": int(fam), "ms": ms, "value": B * T / (ms * 1e-3),
               "alg_tflops": B * T * fl / (ms * 1e-3) / 1e12, "frac_fp32_fma_peak": B * T * fl / (ms * 1e-3) / 1e12 / fp32_peak_tflops}
+        # forward + BPTT (ModelTrainer's value_and_grad on the same architecture): algorithmic FLOPs = 3 x forward
+        fam_b = _lib.lib().cc_kernel_family_at(None, _C.byref(spec.to_c()), 1, B)
+        if fam_b < 0:
+            pt["bptt"] = {"unsupported": _lib.lib().last_error()}
+        else:
+            ybar = torch.randn(B, T + 1, 1, device=dev) / (B * (T + 1))
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            for it in range(2):  # (first pass = warm-up)
+                e[0].record()
+                _, _, tape = ops.rollout_fwd(spec, th, u, want_tape=True)
+                e[1].record()
+                tb, _ = ops.rollout_bwd(spec, th, u, tape, ybar)
+                e[2].record()
+                torch.cuda.synchronize()
+            msf, msb = e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])
+            pt["bptt"] = {"kernel_family": int(fam_b), "ms_fwd_with_tape": msf, "ms_bwd": msb, "value": B * T / ((msf + msb) * 1e-3),
+                          "alg_tflops": 3 * B * T * fl / ((msf + msb) * 1e-3) / 1e12,
+                          "frac_fp32_fma_peak": 3 * B * T * fl / ((msf + msb) * 1e-3) / 1e12 / fp32_peak_tflops,
+                          "grad_finite": bool(torch.isfinite(tb).all())}
+            del tape, ybar
         if cpu_threads:
             Bc, Tc = 256, 100
             uc = u[:Bc, :Tc].cpu().numpy()

@@ -34,7 +34,7 @@
 #pragma once
 #include "cc_mlp128_kernels.cuh"
 
-#define CC_MLPB_THREADS 384
+#define CC_MLPB_THREADS 384  // 3 warpgroups: 2 of workers + the issuer warp's (setmaxnreg 56 / 224)
 #define CC_MLPB_WORKERS 256
 #define CC_MLPB_SLAB_FLOATS 9216  // hi [0, 4608) then lo [4608, 9216); F_l uses 72 x 64, T_l 64 x 64 of each half
 #define CC_MLPB_SLAB_BYTES (CC_MLPB_SLAB_FLOATS * 4)
@@ -209,27 +209,35 @@ CC_DEV void cc_mlpb_await(CcMlpbCtx& c) {
   c.dpar ^= 1;
   cc_tc_fence_after();
 }
+// Descriptors are derived from pre-encoded bases by one add each (the start-address field holds address >> 4 and never
+// overflows); the bases are made opaque per batch so that the compiler does not hoist ~100 loop-invariant descriptors out of the
+// round loop into the issuing thread's 56 registers (ncu on the first version: the issuer spent the whole step on their spill loads)
+CC_DEV uint64_t cc_mlpb_desc(uint64_t base, uint32_t byte_off) { return base + (uint64_t)(byte_off >> 4); }
+CC_DEV void cc_mlpb_opaque(uint64_t& d) { asm volatile("" : "+l"(d)); }
 // forward / input-gradient batch: D = A_lo.B_hi + A_hi.B_lo + A_hi.B_hi over NA contraction chunks of one slab
 template <int NA>
-CC_DEV void cc_mlpb_issue_ts(uint32_t tbase, uint32_t bhi) {
+CC_DEV void cc_mlpb_issue_ts(uint32_t tbase, uint32_t bhi_addr) {
   constexpr uint32_t kstep = 2u * 64u * 16u, lbo = 64u * 16u;
   constexpr uint32_t idesc = cc_umma_idesc_tf32(128, 64);
-  const uint32_t blo = bhi + CC_MLPB_LO * 4u;
+  uint64_t bhi = cc_umma_desc_kmajor(bhi_addr, lbo, 128);
+  cc_mlpb_opaque(bhi);
+  const uint64_t blo = cc_mlpb_desc(bhi, CC_MLPB_LO * 4u);
   const uint32_t aHi = tbase + 64, aLo = tbase + 136;
 #pragma unroll
-  for (int js = 0; js < NA; ++js) cc_umma_tf32_ts(tbase, aLo + 8 * js, cc_umma_desc_kmajor(bhi + js * kstep, lbo, 128), idesc, js ? 1u : 0u);
+  for (int js = 0; js < NA; ++js) cc_umma_tf32_ts(tbase, aLo + 8 * js, cc_mlpb_desc(bhi, js * kstep), idesc, js ? 1u : 0u);
 #pragma unroll
-  for (int js = 0; js < NA; ++js) cc_umma_tf32_ts(tbase, aHi + 8 * js, cc_umma_desc_kmajor(blo + js * kstep, lbo, 128), idesc, 1u);
+  for (int js = 0; js < NA; ++js) cc_umma_tf32_ts(tbase, aHi + 8 * js, cc_mlpb_desc(blo, js * kstep), idesc, 1u);
 #pragma unroll
-  for (int js = 0; js < NA; ++js) cc_umma_tf32_ts(tbase, aHi + 8 * js, cc_umma_desc_kmajor(bhi + js * kstep, lbo, 128), idesc, 1u);
+  for (int js = 0; js < NA; ++js) cc_umma_tf32_ts(tbase, aHi + 8 * js, cc_mlpb_desc(bhi, js * kstep), idesc, 1u);
 }
 // K = trajectory product: 16 instructions of 8 trajectories (two padded core matrices, LBO 144 B; 8-row groups SBO 4608 B)
 template <int N>
-CC_DEV void cc_mlpb_issue_ss(uint32_t d, uint32_t opa, uint32_t opb, uint32_t acc0) {
+CC_DEV void cc_mlpb_issue_ss(uint32_t d, uint64_t opa, uint64_t opb, uint32_t acc0) {
   constexpr uint32_t idesc = cc_umma_idesc_tf32(128, N);
+  cc_mlpb_opaque(opa);
+  cc_mlpb_opaque(opb);
 #pragma unroll
-  for (int js = 0; js < 16; ++js)
-    cc_umma_tf32_ss(d, cc_umma_desc_kmajor(opa + js * 288u, 144, 4608), cc_umma_desc_kmajor(opb + js * 288u, 144, 4608), idesc, js ? 1u : acc0);
+  for (int js = 0; js < 16; ++js) cc_umma_tf32_ss(d, cc_mlpb_desc(opa, js * 288u), cc_mlpb_desc(opb, js * 288u), idesc, js ? 1u : acc0);
 }
 #endif
 
@@ -337,7 +345,8 @@ __global__ void __launch_bounds__(CC_MLPB_THREADS, 1) cc_mlpb_bwd_kernel(const C
     if (warp == 8 && lane == 0) {
       const int R = tab[63];
       const long long rounds = (long long)a.T * R;
-      const uint32_t ring_u32 = cc_smem_u32(ring), opa2_u32 = cc_smem_u32(opa2), opa_u32 = opa2_u32 + CC_MLPB_OPG * 4u, opb_u32 = cc_smem_u32(opb);
+      const uint32_t ring_u32 = cc_smem_u32(ring);
+      const uint64_t opa2_u32 = cc_umma_desc_kmajor(cc_smem_u32(opa2), 144, 4608), opa_u32 = cc_mlpb_desc(opa2_u32, CC_MLPB_OPG * 4u), opb_u32 = cc_umma_desc_kmajor(cc_smem_u32(opb), 144, 4608);
       const uint32_t tb = c.t.tbase;
       auto slab_of = [&](int code) { return ((code & 4) ? L : 0) + (code & 3); };
       int nx = 0;  // table position of the next slab to request (rounds with bit 6 use none)

@@ -307,3 +307,61 @@ def test_emu_mlp_family_edge_cases(monkeypatch):
             assert y.shape == (B, T + 1, 4)
             assert normwise(y, y64) < TOL_STATE, (spec.state_dim, B, T)
             assert normwise(xf, xs[:, -1]) < TOL_STATE or T == 0
+
+
+MLPB_CASES = {
+    # 3 Linear layers, relu, post-step readout, RK4; two CTAs with a ragged second tile
+    "s40_w48_d2": (lambda: O.make_node(40, 1, 1, f_width=48, f_depth=2), 130, 3),
+    # 2 Linear layers, tanh + final tanh, pre-step readout, two inputs / outputs, arctan input transform, full 64 columns
+    "s64_w64_d1_tanh_pre": (lambda: O.make_node(64, 2, 2, f_width=64, f_depth=1, f_act=O.ACT_TANH, f_act_final=O.ACT_TANH,
+                                                readout_pre_step=True, u_transform=O.UT_ARCTAN), 70, 3),
+    # no integrator, no biases, three outputs
+    "s20_w40_d1_noint": (lambda: O.make_node(20, 1, 3, f_width=40, f_depth=1, integrator=O.INT_NONE, f_use_bias=False,
+                                             g_use_bias=False, f_act_final=O.ACT_TANH), 33, 4),
+}
+
+
+@pytest.mark.parametrize("name", list(MLPB_CASES))
+def test_emu_mlpb_reverse(name, monkeypatch):
+    """deep-MLP tcgen05 reverse pass (cc_mlpb_kernels.cuh) through the emulated TMEM / MMA layer: round table, operand layouts,
+    hi + lo weight-gradient rounds, per-CTA sums and their reduction against the fp64 oracle"""
+    import ctypes as C
+
+    monkeypatch.setenv("CC_B200_MLP", "1")
+    mk, B, T = MLPB_CASES[name]
+    spec = mk()
+    assert E.emu().cc_kernel_family_at(None, C.byref(conv(spec).to_c()), 1, B) == 6
+    theta = O.init_params(spec, 1).astype(np.float32)
+    u = _u(B, T, spec.input_dim)
+    x0 = (0.1 * np.random.default_rng(3).normal(size=(B, spec.state_dim))).astype(np.float32)
+    ybar = np.random.default_rng(5).normal(size=(B, T + 1, spec.output_dim)).astype(np.float32)
+    y64, _ = O.rollout_fwd(spec, theta, u, x0=x0)
+    tb64, _ = O.rollout_bwd(spec, theta, u, ybar, x0=x0)
+    y, tb, _ = E.np_rollout_bwd(E.emu(), conv(spec), theta, u, ybar, x0, want_ubar=False)
+    assert normwise(y, y64) < TOL_STATE
+    assert l2rel(tb, tb64) < 1e-5  # (3xTF32 chains + split weight-gradient operands: 1e-7 observed)
+
+
+def test_emu_mlpb_flush_interval_and_narrow(monkeypatch):
+    """flush interval of the weight-gradient accumulators does not change the result beyond rounding; a narrow (width <= 32)
+    architecture takes the family only when forced"""
+    import ctypes as C
+
+    monkeypatch.setenv("CC_B200_MLP", "1")
+    spec = O.make_node(5, 1, 1, f_width=10, f_depth=2)
+    m = conv(spec).to_c()
+    assert E.emu().cc_kernel_family_at(None, C.byref(m), 1, 64) != 6
+    monkeypatch.setenv("CC_B200_MLPB", "1")
+    assert E.emu().cc_kernel_family_at(None, C.byref(m), 1, 64) == 6
+    B, T = 9, 5
+    theta = O.init_params(spec, 1).astype(np.float32)
+    u = _u(B, T, 1)
+    ybar = np.random.default_rng(5).normal(size=(B, T + 1, 1)).astype(np.float32)
+    tb64, _ = O.rollout_bwd(spec, theta, u, ybar)
+    res = []
+    for fl in ("1", "2", "7"):
+        monkeypatch.setenv("CC_B200_MLPB_FLUSH", fl)
+        _, tb, _ = E.np_rollout_bwd(E.emu(), conv(spec), theta, u, ybar, None, want_ubar=False)
+        assert l2rel(tb, tb64) < 1e-5
+        res.append(tb)
+    assert l2rel(res[0], res[2]) < 1e-6
