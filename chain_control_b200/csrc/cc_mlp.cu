@@ -87,23 +87,23 @@ int mlp128_launch(const CcMlpArgs& a, void* stream, char* err, int errlen) {
   return CC_OK;
 #endif
 }
-template <int L>
+template <int L, int NH>
 int mlpb_launch(const CcMlpArgs& a, void* stream, char* err, int errlen) {
   const long long grid = (a.B + 127) / 128;
 #ifdef CC_EMULATE
   (void)stream; (void)err; (void)errlen;
   const size_t smem = ((size_t)CC_MLPB_SMEM_FLOATS + 16 + (size_t)512 * 128) * 4;
-  ccemu::launch((int)grid, CC_MLPB_WORKERS, smem, [&]() { cc_mlpb_bwd_kernel<L>(a); });
+  ccemu::launch((int)grid, 128 * NH, smem, [&]() { cc_mlpb_bwd_kernel<L, NH>(a); });
   return CC_OK;
 #else
   const size_t smem = (size_t)CC_MLPB_SMEM_FLOATS * 4;
-  cudaError_t e = cudaFuncSetAttribute(cc_mlpb_bwd_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(cc_mlpb_bwd_kernel<L, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e == cudaSuccess) {
-    cc_mlpb_bwd_kernel<L><<<(unsigned)grid, CC_MLPB_THREADS, smem, (cudaStream_t)stream>>>(a);
+    cc_mlpb_bwd_kernel<L, NH><<<(unsigned)grid, 128 * NH + 128, smem, (cudaStream_t)stream>>>(a);
     e = cudaGetLastError();
   }
   if (e != cudaSuccess) {
-    snprintf(err, errlen, "cc_mlpb_bwd_kernel<%d> launch failed: %s", L, cudaGetErrorString(e));
+    snprintf(err, errlen, "cc_mlpb_bwd_kernel<%d, %d> launch failed: %s", L, NH, cudaGetErrorString(e));
     return CC_ERR_CUDA;
   }
   return CC_OK;
@@ -131,9 +131,13 @@ int cc_launch_mlpb_bwd(CcMlpArgs a, float* theta_bar, int P, void* ws, void* str
     return CC_ERR_CUDA;
   }
 #endif
+  // worker threads per trajectory: 2 (32 columns each).  CC_B200_MLPB_NH=4 selects the 16-column variant (640 threads):
+  // measured 9 % slower at (64,64,2) x 65,536 (10.06 vs 9.15 ms per 32 steps) -- kept because the tests run both.
+  const char* nhe = getenv("CC_B200_MLPB_NH");
+  const int nh = nhe && atoi(nhe) == 4 ? 4 : 2;
   int rc;
-  if (a.L == 2) rc = mlpb_launch<2>(a, stream, err, errlen);
-  else if (a.L == 3) rc = mlpb_launch<3>(a, stream, err, errlen);
+  if (a.L == 2) rc = nh == 2 ? mlpb_launch<2, 2>(a, stream, err, errlen) : mlpb_launch<2, 4>(a, stream, err, errlen);
+  else if (a.L == 3) rc = nh == 2 ? mlpb_launch<3, 2>(a, stream, err, errlen) : mlpb_launch<3, 4>(a, stream, err, errlen);
   else { snprintf(err, errlen, "deep-MLP tcgen05 reverse pass: %d layers not built", a.L); return CC_ERR_UNSUPPORTED; }
   if (rc) return rc;
 #ifdef CC_EMULATE

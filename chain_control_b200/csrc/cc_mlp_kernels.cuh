@@ -110,6 +110,7 @@ CC_DEV void cc_mlp_ld(const CcMlpTm<PAD>& t, int col, float (&r)[NC]) {
   uint32_t u[NC];
   if constexpr (NC == 32) cc_tmem_ld32(t.lane_base + col, u);
   else if constexpr (NC == 16) cc_tmem_ld16(t.lane_base + col, u);
+  else if constexpr (NC == 4) cc_tmem_ld4(t.lane_base + col, u);
   else cc_tmem_ld8(t.lane_base + col, u);
 #pragma unroll
   for (int i = 0; i < NC; ++i) r[i] = __uint_as_float(u[i]);

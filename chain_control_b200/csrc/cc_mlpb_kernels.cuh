@@ -34,8 +34,6 @@
 #pragma once
 #include "cc_mlp128_kernels.cuh"
 
-#define CC_MLPB_THREADS 384  // 3 warpgroups: 2 of workers + the issuer warp's (setmaxnreg 56 / 224)
-#define CC_MLPB_WORKERS 256
 #define CC_MLPB_SLAB_FLOATS 9216  // hi [0, 4608) then lo [4608, 9216); F_l uses 72 x 64, T_l 64 x 64 of each half
 #define CC_MLPB_SLAB_BYTES (CC_MLPB_SLAB_FLOATS * 4)
 #define CC_MLPB_LO 4608
@@ -241,6 +239,14 @@ CC_DEV void cc_mlpb_issue_ss(uint32_t d, uint64_t opa, uint64_t opb, uint32_t ac
 }
 #endif
 
+template <int NWORK>
+CC_DEV void cc_mlpb_worker_sync() {
+#ifdef CC_EMULATE
+  __syncthreads();
+#else
+  asm volatile("bar.sync 1, %0;" ::"n"(NWORK) : "memory");
+#endif
+}
 // NC values -> rows c0.. of a K = trajectory operand, rounded to nearest tf32
 template <int NC>
 CC_DEV void cc_mlpb_op_rn(float* op, int c0, const float (&v)[NC]) {
@@ -255,15 +261,15 @@ CC_DEV void cc_mlpb_op_lo(float* op, int c0, const float (&v)[NC]) {
 }
 // delta: hi / lo split -> A (TMEM columns c0..) and the operand rows c0.. (hi) / 64 + c0.. (lo)
 template <int NC>
-CC_DEV void cc_mlpb_store_delta(const CcMlpbCtx& c, int c0, const float (&v)[NC]) {
+CC_DEV void cc_mlpb_store_delta(const CcMlpbCtx& c, int cb, int c0, const float (&v)[NC]) {
   float hi[NC], lo[NC];
 #pragma unroll
   for (int i = 0; i < NC; ++i) {
     hi[i] = cc_mlp_tf32_rn(v[i]);
     lo[i] = v[i] - hi[i];
   }
-  cc_mlp_st<64, NC>(c.t, 64 + c0, hi);
-  cc_mlp_st<64, NC>(c.t, 136 + c0, lo);
+  cc_mlp_st<64, NC>(c.t, 64 + cb + c0, hi);
+  cc_mlp_st<64, NC>(c.t, 136 + cb + c0, lo);
 #pragma unroll
   for (int i = 0; i < NC; ++i) {
     c.opa[cc_mlpb_row(c0 + i)] = hi[i];
@@ -280,8 +286,10 @@ CC_DEV void cc_mlpb_act_grad_group(int act, float (&d)[16], const float* y) {
   }
 }
 
-template <int L>
-__global__ void __launch_bounds__(CC_MLPB_THREADS, 1) cc_mlpb_bwd_kernel(const CC_GRID_CONSTANT CcMlpArgs a) {
+template <int L, int NH>
+__global__ void __launch_bounds__(128 * NH + 128, 1) cc_mlpb_bwd_kernel(const CC_GRID_CONSTANT CcMlpArgs a) {
+  constexpr int PC = 64 / NH;        // columns per worker thread
+  constexpr int NWORK = 128 * NH;    // worker threads: NH per trajectory (warp w, w + 4, ... share a TMEM lane quarter)
   float* smem = CC_SMEM_PTR;
   const int tid = threadIdx.x;
   float* ring = smem;
@@ -321,7 +329,7 @@ __global__ void __launch_bounds__(CC_MLPB_THREADS, 1) cc_mlpb_bwd_kernel(const C
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
   if (warp == 0) {
     if (lane == 0) {
-      cc_mbar_init(a_ready, CC_MLPB_WORKERS);
+      cc_mbar_init(a_ready, NWORK);
       cc_mbar_init(d_ready, 1);
       cc_mbar_init(full, 1);
       cc_mbar_init(full + 1, 1);
@@ -336,13 +344,13 @@ __global__ void __launch_bounds__(CC_MLPB_THREADS, 1) cc_mlpb_bwd_kernel(const C
   c.t.tbase = *tmem_slot;
   c.t.lane_base = c.t.tbase + ((uint32_t)((warp & 3) * 32) << 16);
   c.t.a_ready = a_ready; c.t.d_ready = d_ready;
-  c.hh = (warp >> 2) & 1;
+  c.hh = warp >> 2;
   c.dpar = 0;
-  const bool worker = warp < 8;
+  const bool worker = warp < 4 * NH;
   if (!worker) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     // ---- producer + MMA issuer (one thread) ----
-    if (warp == 8 && lane == 0) {
+    if (warp == 4 * NH && lane == 0) {
       const int R = tab[63];
       const long long rounds = (long long)a.T * R;
       const uint32_t ring_u32 = cc_smem_u32(ring);
@@ -404,13 +412,16 @@ __global__ void __launch_bounds__(CC_MLPB_THREADS, 1) cc_mlpb_bwd_kernel(const C
 #endif
   if (worker) {
 #ifndef CC_EMULATE
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    if (NH == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");  // (640 threads x 96 registers at launch: 128 x 56 + 512 x 104 fit the pool)
 #endif
-    const int row = tid & 127, hh = c.hh, cb = 32 * hh;
+    const int row = tid & 127, hh = c.hh, cb = PC * hh;
     c.row = row;
+    // (cb is a multiple of 8: row(cb + j) = row(cb) + row(j), so every operand store below has a compile-time offset)
     c.opa2 = opa2 + (row >> 2) * 36 + (row & 3);
-    c.opa = c.opa2 + CC_MLPB_OPG;
-    c.opb = opb + (row >> 2) * 36 + (row & 3);
+    c.opa = c.opa2 + CC_MLPB_OPG + cc_mlpb_row(cb);
+    c.opb = opb + (row >> 2) * 36 + (row & 3) + cc_mlpb_row(cb);
+    float* const opb_tail = opb + (row >> 2) * 36 + (row & 3) + cc_mlpb_row(64);
     c.tab = tab; c.ri = 0; c.R = tab[63];
     const long long b = (long long)blockIdx.x * 128 + row;
     const bool act = b < a.B;
@@ -419,14 +430,15 @@ __global__ void __launch_bounds__(CC_MLPB_THREADS, 1) cc_mlpb_bwd_kernel(const C
     const long long yrow = (long long)(a.T + 1) * a.O;
     // per-CTA sums start at zero; opB's unused rows 72..79 stay zero
     for (int l = 0; l < L; ++l)
-      for (int j = 0; j < 40; ++j) rec[(size_t)(l * 80 + 40 * hh + j) * 128 + row] = 0.f;
+      for (int j = 0; j < 80 / NH; ++j) rec[(size_t)(l * 80 + (80 / NH) * hh + j) * 128 + row] = 0.f;
     if (hh == 0)
-      for (int r = 72; r < 80; ++r) c.opb[cc_mlpb_row(r)] = 0.f;
-    float lam[32], dl[32], hid[L - 1][32];  // (the stage sum accumulates in lam; the incoming adjoint waits in slot 3 of the scratch)
-    float* lam0 = zs + (size_t)(3 * 64 + cb) * 128 + row;
+      for (int r = 8; r < 16; ++r) opb_tail[cc_mlpb_row(r)] = 0.f;
+    float lam[PC], dl[PC], hid[L - 1][PC];  // (the stage sum accumulates in lam; the incoming adjoint waits in slot 3 of the scratch)
+    float* const zs_c = zs + (size_t)cb * 128 + row;  // this thread's column block of the scratch slots
+    float* lam0 = zs_c + (size_t)(3 * 64) * 128;
     float gb[CC_TINY_O];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) lam[i] = 0.f;
+    for (int i = 0; i < PC; ++i) lam[i] = 0.f;
 #pragma unroll
     for (int o = 0; o < CC_TINY_O; ++o) gb[o] = 0.f;
 
@@ -445,7 +457,7 @@ __global__ void __launch_bounds__(CC_MLPB_THREADS, 1) cc_mlpb_bwd_kernel(const C
     auto flush_dg = [&]() {
       if ((row >> 5) == 0) {
 #pragma unroll
-        for (int c0 = 0; c0 < 32; c0 += 16) {
+        for (int c0 = 0; c0 < PC; c0 += 16) {
           float r[16];
           cc_mlp_ld<64, 16>(c.t, CC_MLPB_COL_DG + cb + c0, r);
           cc_mlp_wait_ld();
@@ -457,23 +469,25 @@ __global__ void __launch_bounds__(CC_MLPB_THREADS, 1) cc_mlpb_bwd_kernel(const C
       }
     };
     auto flush_dw = [&]() {
+      constexpr int CW = 80 / NH;  // accumulator columns of this thread: 40 = 16 + 16 + 8 or 20 = 16 + 4
 #pragma unroll 1
       for (int l = 0; l < L; ++l) {
-        float* dst = rec + (size_t)(l * 80 + 40 * hh) * 128 + row;
-        const int col = CC_MLPB_COL_DW + 80 * l + 40 * hh;
+        float* dst = rec + (size_t)(l * 80 + CW * hh) * 128 + row;
+        const int col = CC_MLPB_COL_DW + 80 * l + CW * hh;
 #pragma unroll
-        for (int c0 = 0; c0 < 32; c0 += 16) {
+        for (int c0 = 0; c0 + 16 <= CW; c0 += 16) {
           float r[16];
           cc_mlp_ld<64, 16>(c.t, col + c0, r);
           cc_mlp_wait_ld();
 #pragma unroll
           for (int i = 0; i < 16; ++i) dst[(size_t)(c0 + i) * 128] += r[i];
         }
-        float r8[8];
-        cc_mlp_ld<64, 8>(c.t, col + 32, r8);
+        constexpr int REM = CW % 16, R0 = CW - REM;
+        float rr[REM];
+        cc_mlp_ld<64, REM>(c.t, col + R0, rr);
         cc_mlp_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 8; ++i) dst[(size_t)(32 + i) * 128] += r8[i];
+        for (int i = 0; i < REM; ++i) dst[(size_t)(R0 + i) * 128] += rr[i];
       }
     };
     // lam += G^T d over this half's columns
@@ -483,7 +497,7 @@ __global__ void __launch_bounds__(CC_MLPB_THREADS, 1) cc_mlpb_bwd_kernel(const C
         if (o < a.O) {
           const float* grow = gw + o * 68 + cb;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) lam[i] = fmaf(grow[i], d[o], lam[i]);
+          for (int i = 0; i < PC; ++i) lam[i] = fmaf(grow[i], d[o], lam[i]);
         }
     };
 
@@ -492,11 +506,11 @@ __global__ void __launch_bounds__(CC_MLPB_THREADS, 1) cc_mlpb_bwd_kernel(const C
 #pragma unroll
       for (int o = 0; o < CC_TINY_O; ++o) d[o] = (o < a.O && act) ? a.out_scale * __ldg(a.ybar + b * yrow + (long long)a.T * a.O + o) : 0.f;
 #pragma unroll
-      for (int c0 = 0; c0 < 32; c0 += 16) {
+      for (int c0 = 0; c0 < PC; c0 += 16) {
         float v[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = (act && cb + c0 + i < a.S) ? a.tape_xT[(size_t)(cb + c0 + i) * a.Bpad + b] : 0.f;
-        cc_mlpb_op_rn<16>(c.opb, cb + c0, v);
+        cc_mlpb_op_rn<16>(c.opb, c0, v);
       }
       put_d(d);
       add_readout(d);
@@ -506,11 +520,11 @@ __global__ void __launch_bounds__(CC_MLPB_THREADS, 1) cc_mlpb_bwd_kernel(const C
       cc_mlpb_round(c, CC_MLPB_DGONLY);
       cc_mlpb_await(c);
 #pragma unroll
-      for (int c0 = 0; c0 < 32; c0 += 16) {
+      for (int c0 = 0; c0 < PC; c0 += 16) {
         float v[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = (act && cb + c0 + i < a.S) ? a.tape_xT[(size_t)(cb + c0 + i) * a.Bpad + b] : 0.f;
-        cc_mlpb_op_lo<16>(c.opb, cb + c0, v);
+        cc_mlpb_op_lo<16>(c.opb, c0, v);
       }
       cc_mlpb_round(c, CC_MLPB_DGONLY | 64);
       cc_mlpb_await(c);
@@ -542,15 +556,15 @@ __global__ void __launch_bounds__(CC_MLPB_THREADS, 1) cc_mlpb_bwd_kernel(const C
 #pragma unroll
         for (int i = 3; i < 8; ++i) trow[i] = cc_mlp_tf32_rn(tail[i]);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) c.opb[cc_mlpb_row(64 + i)] = trow[i];
+        for (int i = 0; i < 8; ++i) opb_tail[cc_mlpb_row(i)] = trow[i];
       }
       // ---- first pass: z_2..z_4 (RK4) ----
       {
-        float x[32];
+        float x[PC];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) x[i] = (act && cb + i < a.S) ? xk[(size_t)(cb + i) * a.Bpad] : 0.f;
+        for (int i = 0; i < PC; ++i) x[i] = (act && cb + i < a.S) ? xk[(size_t)(cb + i) * a.Bpad] : 0.f;
 #pragma unroll
-        for (int c0 = 0; c0 < 32; c0 += 16) {
+        for (int c0 = 0; c0 < PC; c0 += 16) {
           float z[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) z[i] = x[c0 + i];
@@ -566,7 +580,7 @@ __global__ void __launch_bounds__(CC_MLPB_THREADS, 1) cc_mlpb_bwd_kernel(const C
               const int actl = a.f[l].act;
               const float cz = st == 2 ? 1.f : 0.5f;
 #pragma unroll
-              for (int c0 = 0; c0 < 32; c0 += 16) {
+              for (int c0 = 0; c0 < PC; c0 += 16) {
                 float r[16];
                 cc_mlp_ld<64, 16>(c.t, cb + c0, r);
                 cc_mlp_wait_ld();
@@ -575,7 +589,7 @@ __global__ void __launch_bounds__(CC_MLPB_THREADS, 1) cc_mlpb_bwd_kernel(const C
 #pragma unroll
                   for (int i = 0; i < 16; ++i) {
                     r[i] = fmaf(h * r[i], cz, x[c0 + i]);
-                    zs[(size_t)(st * 64 + cb + c0 + i) * 128 + row] = r[i];
+                    zs_c[(size_t)(st * 64 + c0 + i) * 128] = r[i];
                   }
                 }
                 cc_mlp_store_split<64, 16>(c.t, cb + c0, r);
@@ -588,22 +602,22 @@ __global__ void __launch_bounds__(CC_MLPB_THREADS, 1) cc_mlpb_bwd_kernel(const C
       // ---- reverse stages ----
       const float cfirst = rk4 ? c6 : (a.integrator == CC_INT_EE ? h : 1.f);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
+      for (int i = 0; i < PC; ++i) {
         dl[i] = cfirst * lam[i];
         lam0[(size_t)i * 128] = lam[i];
         if (a.integrator == CC_INT_NONE) lam[i] = 0.f;  // (no integrator: x_{k+1} = f(x_k), the adjoint is replaced)
       }
 #pragma unroll 1
       for (int s = nst - 1; s >= 0; --s) {
-        const float* a0 = s == 0 ? xk : zs + (size_t)((s - 1) * 64) * 128 + row;  // stage input: x_k or z_{s+1} (slot s-1)
+        const float* a0 = s == 0 ? xk + (size_t)cb * a.Bpad : zs_c + (size_t)((s - 1) * 64) * 128;  // stage input: x_k or z_{s+1} (slot s-1), this thread's columns
         const size_t a0s = s == 0 ? (size_t)a.Bpad : 128;
         const bool a0ok = s == 0 ? act : true;
         if (s != nst - 1) {  // (the first pass left z_4 in A and launched its round)
 #pragma unroll
-          for (int c0 = 0; c0 < 32; c0 += 16) {
+          for (int c0 = 0; c0 < PC; c0 += 16) {
             float z[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) z[i] = (a0ok && (s != 0 || cb + c0 + i < a.S)) ? a0[(size_t)(cb + c0 + i) * a0s] : 0.f;
+            for (int i = 0; i < 16; ++i) z[i] = (a0ok && (s != 0 || cb + c0 + i < a.S)) ? a0[(size_t)(c0 + i) * a0s] : 0.f;
             cc_mlp_store_split<64, 16>(c.t, cb + c0, z);
           }
           cc_mlpb_round(c, 0);
@@ -613,7 +627,7 @@ __global__ void __launch_bounds__(CC_MLPB_THREADS, 1) cc_mlpb_bwd_kernel(const C
         for (int l = 0; l < L - 1; ++l) {
           cc_mlpb_await(c);
 #pragma unroll
-          for (int c0 = 0; c0 < 32; c0 += 16) {
+          for (int c0 = 0; c0 < PC; c0 += 16) {
             float r[16];
             cc_mlp_ld<64, 16>(c.t, cb + c0, r);
             cc_mlp_wait_ld();
@@ -621,14 +635,14 @@ __global__ void __launch_bounds__(CC_MLPB_THREADS, 1) cc_mlpb_bwd_kernel(const C
 #pragma unroll
             for (int i = 0; i < 16; ++i) hid[l][c0 + i] = r[i];
             if (l < L - 2 || fa) cc_mlp_store_split<64, 16>(c.t, cb + c0, r);
-            if (l == L - 2) cc_mlpb_op_rn<16>(c.opb, cb + c0, r);  // operand of the last layer's weight gradient
+            if (l == L - 2) cc_mlpb_op_rn<16>(c.opb, c0, r);  // operand of the last layer's weight gradient
           }
           if (l < L - 2 || fa) cc_mlpb_round(c, l + 1);
         }
         if (fa) {  // final activation: delta = kbar . act_f'(k_s)
           cc_mlpb_await(c);
 #pragma unroll
-          for (int c0 = 0; c0 < 32; c0 += 16) {
+          for (int c0 = 0; c0 < PC; c0 += 16) {
             float r[16], dd[16];
             cc_mlp_ld<64, 16>(c.t, cb + c0, r);
             cc_mlp_wait_ld();
@@ -644,11 +658,11 @@ __global__ void __launch_bounds__(CC_MLPB_THREADS, 1) cc_mlpb_bwd_kernel(const C
 #pragma unroll
         for (int l = L - 1; l >= 0; --l) {
 #pragma unroll
-          for (int c0 = 0; c0 < 32; c0 += 16) {
+          for (int c0 = 0; c0 < PC; c0 += 16) {
             float v[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = dl[c0 + i];
-            cc_mlpb_store_delta<16>(c, cb + c0, v);
+            cc_mlpb_store_delta<16>(c, cb, c0, v);
             if (l < L - 1) {  // operand rows = the layer's input: a hidden activation or the stage input
               float in[16];
               if (l > 0) {
@@ -656,9 +670,9 @@ __global__ void __launch_bounds__(CC_MLPB_THREADS, 1) cc_mlpb_bwd_kernel(const C
                 for (int i = 0; i < 16; ++i) in[i] = hid[l > 0 ? l - 1 : 0][c0 + i];
               } else {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) in[i] = (a0ok && (s != 0 || cb + c0 + i < a.S)) ? a0[(size_t)(cb + c0 + i) * a0s] : 0.f;
+                for (int i = 0; i < 16; ++i) in[i] = (a0ok && (s != 0 || cb + c0 + i < a.S)) ? a0[(size_t)(c0 + i) * a0s] : 0.f;
               }
-              cc_mlpb_op_rn<16>(c.opb, cb + c0, in);
+              cc_mlpb_op_rn<16>(c.opb, c0, in);
             }
           }
           if (l == 0 && s == 0) put_d(dg);
@@ -666,22 +680,22 @@ __global__ void __launch_bounds__(CC_MLPB_THREADS, 1) cc_mlpb_bwd_kernel(const C
           cc_mlpb_await(c);
           // second weight-gradient round of the layer: the lo part of its input replaces the hi part in the operand rows
 #pragma unroll
-          for (int c0 = 0; c0 < 32; c0 += 16) {
+          for (int c0 = 0; c0 < PC; c0 += 16) {
             float in[16];
             if (l > 0) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) in[i] = hid[l > 0 ? l - 1 : 0][c0 + i];
             } else {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) in[i] = (a0ok && (s != 0 || cb + c0 + i < a.S)) ? a0[(size_t)(cb + c0 + i) * a0s] : 0.f;
+              for (int i = 0; i < 16; ++i) in[i] = (a0ok && (s != 0 || cb + c0 + i < a.S)) ? a0[(size_t)(c0 + i) * a0s] : 0.f;
             }
-            cc_mlpb_op_lo<16>(c.opb, cb + c0, in);
+            cc_mlpb_op_lo<16>(c.opb, c0, in);
           }
           cc_mlpb_round(c, l | 64 | ((l == 0 && s == 0) ? 8 : 0));
           const float ca = (s - 1 == 0) ? c6 : c3;
           const float cbk = (s - 1 == 2) ? h : c2;
 #pragma unroll
-          for (int c0 = 0; c0 < 32; c0 += 16) {
+          for (int c0 = 0; c0 < PC; c0 += 16) {
             float r[16];
             cc_mlp_ld<64, 16>(c.t, cb + c0, r);
             cc_mlp_wait_ld();
@@ -723,9 +737,9 @@ __global__ void __launch_bounds__(CC_MLPB_THREADS, 1) cc_mlpb_bwd_kernel(const C
       for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, m);
       if (hh == 0 && (row & 31) == 0) gbw[(row >> 5) * 4 + o] = v;
     }
-    cc_mlp128_worker_sync();
+    cc_mlpb_worker_sync<NWORK>();
     float* grec = rec + (size_t)L * 80 * 128;
-    for (int i = tid; i < 8 * 64; i += CC_MLPB_WORKERS) grec[i] = gacc[i];
+    for (int i = tid; i < 8 * 64; i += NWORK) grec[i] = gacc[i];
     if (tid < CC_TINY_O) grec[8 * 64 + tid] = (gbw[tid] + gbw[4 + tid]) + (gbw[8 + tid] + gbw[12 + tid]);
   }
 #ifndef CC_EMULATE

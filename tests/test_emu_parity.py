@@ -321,13 +321,15 @@ MLPB_CASES = {
 }
 
 
+@pytest.mark.parametrize("nh", ["2", "4"])
 @pytest.mark.parametrize("name", list(MLPB_CASES))
-def test_emu_mlpb_reverse(name, monkeypatch):
+def test_emu_mlpb_reverse(name, nh, monkeypatch):
     """deep-MLP tcgen05 reverse pass (cc_mlpb_kernels.cuh) through the emulated TMEM / MMA layer: round table, operand layouts,
     hi + lo weight-gradient rounds, per-CTA sums and their reduction against the fp64 oracle"""
     import ctypes as C
 
     monkeypatch.setenv("CC_B200_MLP", "1")
+    monkeypatch.setenv("CC_B200_MLPB_NH", nh)  # worker threads per trajectory (2 = default, 4 = the 16-column variant)
     mk, B, T = MLPB_CASES[name]
     spec = mk()
     assert E.emu().cc_kernel_family_at(None, C.byref(conv(spec).to_c()), 1, B) == 6

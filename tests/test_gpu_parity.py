@@ -607,7 +607,7 @@ MLPB_GPU_CASES = {
 }
 
 
-@pytest.mark.parametrize("flush", ["1", "2", "5"])
+@pytest.mark.parametrize("flush", ["1", "2", "5", "3/nh4"])
 @pytest.mark.parametrize("name", list(MLPB_GPU_CASES))
 def test_mlpb_reverse_vs_oracle(name, flush, T_, monkeypatch):
     """deep-MLP tcgen05 reverse pass (family 6, cc_mlpb_kernels.cuh) against the fp64 C oracle: theta_bar of f and g"""
@@ -615,6 +615,9 @@ def test_mlpb_reverse_vs_oracle(name, flush, T_, monkeypatch):
 
     from chain_control_b200 import _lib, ops
 
+    if flush.endswith("/nh4"):  # the four-threads-per-trajectory variant (16 columns per thread)
+        flush = flush[:-4]
+        monkeypatch.setenv("CC_B200_MLPB_NH", "4")
     monkeypatch.setenv("CC_B200_MLPB_FLUSH", flush)
     mk, B, T = MLPB_GPU_CASES[name]
     spec = mk()
