@@ -343,6 +343,38 @@ class Workload:
         return gl
 
 
+def env_point(torch, dev, cores):
+    """two_segments_v1, B episodes x 1000 control steps (10 RK4 physics steps each) in one launch; CPU: the NumPy oracle
+    (vectorised over a 256-episode sample x 100 steps, one thread) scaled to the same work"""
+    from chain_control_b200.env import make_env
+
+    B, T = 16384, 1000
+    env = make_env("two_segments_v1", n_envs=B, device=dev)
+    acts = (torch.rand(B, T, device=dev) * 2 - 1)
+    for _ in range(2):
+        env.rollout(acts)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        obs = env.rollout(acts)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    entry = {"workload": "two_segments_v1 episodes (cc/env data source, MuJoCo-free CUDA kernel, fp64 RK4 at 1 ms)", "B": B, "T": T,
+             "ms_per_rollout": ms, "env_steps_per_s": B * T / (ms * 1e-3), "physics_steps_per_s": 10 * B * T / (ms * 1e-3),
+             "obs_absmax": float(obs["xpos_of_segment_end"].abs().max())}
+    if cores is not None:
+        from oracle import two_segments_np as TS
+
+        a = acts[:256, :100].cpu().numpy()
+        t0 = time.perf_counter()
+        TS.rollout("two_segments_v1", a)
+        dt = time.perf_counter() - t0
+        entry["cpu_env_steps_per_s"] = 256 * 100 / dt
+        entry["cpu_sample"] = "NumPy oracle, 256 episodes x 100 steps vectorised on 1 thread"
+    return entry
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -545,6 +577,11 @@ def main():
         except Exception as exc:
             others["cfg3"] = {"error": f"{type(exc).__name__}: {exc}"}
         torch.cuda.empty_cache()
+        # the two-segment data source (cc_env_two_segments_kernel, fp64): 16,384 episodes of 1000 control steps
+        try:
+            others["data_source"] = env_point(torch, dev, None if args.no_cpu_baseline else cores)
+        except Exception as exc:
+            others["data_source"] = {"error": f"{type(exc).__name__}: {exc}"}
 
     if rank == 0:
         import ctypes as _C

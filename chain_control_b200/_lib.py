@@ -35,6 +35,7 @@ _SIGS = {
     "cc_closedloop_bwd": (_i32, [_M, _M, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _i32, _vp, _sz, _vp]),
     "cc_mse_value_and_cotangent": (_i32, [_vp, _vp, _vp, _vp, _i64, C.c_float, _vp]),
     "cc_opt_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64] + [C.c_float] * 9 + [_vp]),
+    "cc_env_two_segments_rollout": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _i32, C.c_double, _vp]),
     "cc_fp32_peak_probe": (_i32, [_vp, _i32, _vp]),
     "cc_fp32_tile_probe": (_i32, [_vp, _vp, _i32, _vp]),
 }

@@ -16,6 +16,7 @@
 
 #include "cc_kernels.cuh"
 #include "cc_aux.cuh"
+#include "cc_env.cuh"
 #ifdef CC_EMULATE
 #define CC_TN_VALUE 8
 #include "cc_tn.cu"
@@ -839,6 +840,29 @@ int32_t cc_opt_step(float* theta, float* mu, float* nu, const float* grad, int32
   ccemu::launch(1, CC_OPT_THREADS, CC_OPT_THREADS * 4, [&]() { cc_opt_step_kernel(a); });
 #else
   cc_opt_step_kernel<<<1, CC_OPT_THREADS, 0, (cudaStream_t)stream>>>(a);
+  CC_CUDA_OK(cudaGetLastError());
+#endif
+  return CC_OK;
+}
+
+int32_t cc_env_two_segments_rollout(const double* params, int64_t n_params, const float* actions, const double* actions_f64,
+                                    float* obs, double* state, int64_t B, int32_t T, int32_t n_sub_steps, double physics_dt,
+                                    void* stream) {
+  if (!params || !obs || B < 1 || T < 0 || n_sub_steps < 1 || !(physics_dt > 0.0))
+    return fail(CC_ERR_INVALID_ARG, "two_segments rollout: null pointer / bad sizes");
+  if (n_params != 1 && n_params != B) return fail(CC_ERR_INVALID_ARG, "two_segments rollout: n_params must be 1 or B");
+  if (T > 0 && ((actions != nullptr) == (actions_f64 != nullptr)))
+    return fail(CC_ERR_INVALID_ARG, "two_segments rollout: pass exactly one of actions (fp32) / actions_f64");
+  CcEnvArgs a;
+  a.params = params; a.n_params = n_params; a.actions = actions; a.actions64 = actions_f64; a.obs = obs; a.state = state;
+  a.B = B; a.T = T; a.n_sub = n_sub_steps; a.h = physics_dt;
+  const long long grid = (B + CC_ENV_THREADS - 1) / CC_ENV_THREADS;
+  g_launches.fetch_add(1);
+#ifdef CC_EMULATE
+  (void)stream;
+  ccemu::launch((int)grid, CC_ENV_THREADS, (CC_ENV_THREADS / 32) * CC_ENV_TILE * 4, [&]() { cc_env_two_segments_kernel(a); });
+#else
+  cc_env_two_segments_kernel<<<(unsigned)grid, CC_ENV_THREADS, 0, (cudaStream_t)stream>>>(a);
   CC_CUDA_OK(cudaGetLastError());
 #endif
   return CC_OK;

@@ -152,6 +152,22 @@ int32_t cc_opt_step(float* theta, float* mu, float* nu, const float* grad, int32
                     float lr, float b1, float b2, float eps, float clip_global_norm, float clip_value,
                     float l1_prefactor, float l2_prefactor, float grad_scale, void* stream);
 
+/* ---- data source: B independent two-segment-chain environments -------------------------------------
+ * Replaces, for the `two_segments*` ids of cc/env/sample_envs.py:13-60, the per-episode Python loop
+ * cc/env/collect/collect.py:78-98 -> control.Environment.step -> MuJoCo mj_step over the model cc/env/envs/two_segments.xml:6-14 +
+ * cc/env/envs/two_segments.py:61-104 (cart on a slide joint, two capsule poles on hinges, motor gear 5; RK4 at 1 ms, no
+ * gravity / contacts) and the task :119-136,242-263 (ctrl = arctan(action), observation = world x of segment_end, float32:
+ * cc/env/make_env.py:43-46).  Pinned by the reference's golden vectors cc/env/test_make_env.py:146-335.
+ *   params  [n_params][4] fp64 = {slider damping, slider stiffness, hinge damping, hinge stiffness}; n_params = 1 (shared) or B
+ *   actions [B, T] fp32 (arctan evaluated in fp32, as numpy does for float32 actions) or actions_f64 [B, T] (Python-float
+ *           actions: arctan in fp64) -- exactly one non-null when T > 0
+ *   obs     [B, T + 1] fp32: obs[:, 0] observes the incoming state, obs[:, k + 1] the state after control step k
+ *   state   [B, 6] fp64 (qpos[3], qvel[3]) read and written back, or NULL = start from reset (all zero), final state dropped
+ *   n_sub_steps = control_timestep / physics_dt (10 for the reference's 0.01 s / 1 ms) */
+int32_t cc_env_two_segments_rollout(const double* params, int64_t n_params, const float* actions, const double* actions_f64,
+                                    float* obs, double* state, int64_t B, int32_t T, int32_t n_sub_steps, double physics_dt,
+                                    void* stream);
+
 /* ---- measurement helper: register-resident FFMA chain, returns nothing; time it with events ---- */
 int32_t cc_fp32_peak_probe(float* sink, int32_t iters, void* stream);
 /* same, but the SGEMM register-tile pattern acc[i][j] += x[i]*y[j] (three register operands per FFMA):
