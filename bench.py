@@ -70,7 +70,8 @@ WORKLOADS = {
                                     "S_m=50, RK4, dt=0.01, T_r=1001) at configs[3]'s batch, 65536 trajectories per GPU"),
     "cfg2": (True, 64, 1001, 1, "configs[1]: closed-loop ControllerTrainer BPTT, 64 trajectories x 1001 steps"),
     "cfg4": (False, 65536, 1000, 1, "configs[3]: ModelTrainer step, 65536 trajectories x 1000 steps, S=50 depth 0"),
-    "cfg1": (False, 8, 1000, 1, "configs[0]: ModelTrainer step, 8 trajectories x 1000 steps, S=50 depth 0"),
+    "cfg1": (False, 8, 1000, 1, "configs[0]: two_segments env (dt = 0.01, 1001 steps): ModelTrainer step on 8 trajectories recorded from the "
+                                "two-segment data source (4 GP draws + 4 cosines: cc/utils/high_level/defaults.py:21-23 seeds), S=50 depth 0"),
     "cfg5": (True, 4096, 10001, 100, "configs[4]: closed-loop BPTT, T_r = 10001, 4096 trajectories, checkpointed recomputation (ckpt_every = 100)"),
 }
 # algorithmic FLOPs per trajectory-step: F = 2 (n_st M_f + M_g)
@@ -308,9 +309,18 @@ class Workload:
         self.P = theta0.numel()
         self.opt = ops.FusedAdam(theta0, 1e-3, clip_global_norm=1.0)  # chain(clip_by_global_norm(1.0), adam(1e-3)), test_trainer.py:58
         self.theta = self.opt.theta
-        self.host_in = torch.from_numpy(make_refs(B, self.T, 100 + rank)).pin_memory()
+        if name == "cfg1":
+            # configs[0] literally: inputs and targets RECORDED from the two-segment environment (cc_env_two_segments_kernel),
+            # sample_feedforward_and_collect(env, train_gp[:4], train_cos[:4]) of cc/utils/high_level/defaults.py:21-23
+            from chain_control_b200.env import make_env, sample_feedforward_and_collect
+
+            sample = sample_feedforward_and_collect(make_env("two_segments_v1", device=dev), seeds_gp=[0, 1, 2, 3], seeds_cos=[4, 8, 12, 2])
+            self.host_in = torch.from_numpy(np.ascontiguousarray(sample.action[:B], np.float32)).pin_memory()
+            self.targets = torch.from_numpy(np.ascontiguousarray(sample.obs["xpos_of_segment_end"][:B], np.float32)).to(dev)
+        else:
+            self.host_in = torch.from_numpy(make_refs(B, self.T, 100 + rank)).pin_memory()
+            self.targets = None if self.closed else torch.zeros(B, self.T + 1, 1, device=dev)
         self.x = self.host_in.to(dev)
-        self.targets = None if self.closed else torch.zeros(B, self.T + 1, 1, device=dev)
         self.n_total = world * B * (self.T if self.closed else self.T + 1)
         self.units = B * self.T
 

@@ -33,7 +33,7 @@ struct CcEnvArgs {
 
 struct CcEnvConst {
   double ds, ks, dh, kh;
-  double a, b, c, m00, m11, m22;
+  double a, b, c, rm00, m11, m22;
 };
 
 CC_DEV void cc_env_sincos(double x, double& s, double& c) {
@@ -48,30 +48,31 @@ CC_DEV void cc_env_sincos(double x, double& s, double& c) {
 CC_DEV void cc_env_qacc(const CcEnvConst& k, const double (&q)[3], const double (&v)[3], double force, double (&acc)[3]) {
   const double p1 = 3.141592653589793 + q[1];  // pole 1 hangs (euler 0 180 0); the rounded pi is part of the reference's numbers
   const double p2 = p1 + q[2];
-  double s1, c1, s2, c2, s12, c12;
+  double s1, c1, s2, c2;
   cc_env_sincos(p1, s1, c1);
   cc_env_sincos(p2, s2, c2);
-  cc_env_sincos(-q[2], s12, c12);  // p1 - p2
+  const double c12 = c1 * c2 + s1 * s2, s12 = s1 * c2 - c1 * s2;  // cos / sin of p1 - p2 (saves the third sincos)
   const double w1 = v[1], w2 = v[1] + v[2];
   // absolute-angle mass matrix entries
   const double a01 = k.a * c1, a02 = k.b * c2, a12 = k.c * c12;
   const double ca0 = -k.a * s1 * w1 * w1 - k.b * s2 * w2 * w2;
   const double ca1 = k.c * s12 * w2 * w2, ca2 = -k.c * s12 * w1 * w1;
   // relative coordinates: M = J^T Ma J, bias = J^T ca with (x, p1, p2)' = J (x, th1, th2)'
-  const double M00 = k.m00, M01 = a01 + a02, M02 = a02;
+  const double M01 = a01 + a02, M02 = a02;
   const double M11 = k.m11 + 2.0 * a12 + k.m22, M12 = a12 + k.m22, M22 = k.m22;
   const double r0 = force - k.ds * v[0] - k.ks * q[0] - ca0;
   const double r1 = -k.dh * v[1] - k.kh * q[1] - (ca1 + ca2);
   const double r2 = -k.dh * v[2] - k.kh * q[2] - ca2;
-  // LDL^T
-  const double l10 = M01 / M00, l20 = M02 / M00;
+  // LDL^T with two reciprocals (M00 is constant: its reciprocal comes with the constants)
+  const double l10 = M01 * k.rm00, l20 = M02 * k.rm00;
   const double d1 = M11 - l10 * M01;
-  const double l21 = (M12 - l20 * M01) / d1;
+  const double rd1 = 1.0 / d1;
+  const double l21 = (M12 - l20 * M01) * rd1;
   const double d2 = M22 - l20 * M02 - l21 * l21 * d1;
   const double y0 = r0, y1 = r1 - l10 * y0, y2 = r2 - l20 * y0 - l21 * y1;
   const double z2 = y2 / d2;
-  const double z1 = y1 / d1 - l21 * z2;
-  const double z0 = y0 / M00 - l10 * z1 - l20 * z2;
+  const double z1 = y1 * rd1 - l21 * z2;
+  const double z0 = y0 * k.rm00 - l10 * z1 - l20 * z2;
   acc[0] = z0; acc[1] = z1; acc[2] = z2;
 }
 
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(CC_ENV_THREADS) cc_env_two_segments_kernel(con
     const double ms = mp * vs / (vc + vs), mcyl = mp - ms;
     const double I = mcyl * (3 * r * r + H * H) / 12 + ms * (2 * r * r / 5 + H * (3 * r + 2 * H) / 8);
     k.a = mp * lc + mp * l1; k.b = mp * lc; k.c = mp * l1 * lc;
-    k.m00 = mc + 2 * mp; k.m11 = mp * lc * lc + I + mp * l1 * l1; k.m22 = mp * lc * lc + I;
+    k.rm00 = 1.0 / (mc + 2 * mp); k.m11 = mp * lc * lc + I + mp * l1 * l1; k.m22 = mp * lc * lc + I;
   }
   double q[3] = {0.0, 0.0, 0.0}, v[3] = {0.0, 0.0, 0.0};
   if (a.state && act) {
