@@ -513,14 +513,24 @@ def main():
     # runs on a side stream while the kernels of step i execute (chain_control_b200.parallel.HostFeed, double buffered)
     P = W.P
     hres = torch.empty(P + 1).pin_memory()
-    for _ in range(2):
-        W.step(W.host_in.to(dev, non_blocking=True))
-    barrier()
     feed = parallel.HostFeed(dev)
+    # warm-up THROUGH the feed (side stream, both device slots and the pinned result buffer exist before the timed region)
+    feed.push(W.host_in)
+    for i in range(3):
+        xd = feed.pop()
+        feed.push(W.host_in)
+        gl2 = W.step(xd)
+        feed.release()
+        hres.copy_(gl2, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    feed.pop()
+    barrier()
     e0, e1 = ev(), ev()
+    step_t = []
     e0.record()
     feed.push(W.host_in)                               # H2D of step 0's inputs: inside the timed region
     for i in range(args.steps):
+        th0 = time.perf_counter()
         xd = feed.pop()
         if i + 1 < args.steps:
             feed.push(W.host_in)                       # H2D of the next step's inputs, overlapped with this step's kernels
@@ -528,6 +538,7 @@ def main():
         feed.release()
         hres.copy_(gl2, non_blocking=True)             # D2H of the step's result (gradient + loss)
         torch.cuda.current_stream().synchronize()
+        step_t.append(1e3 * (time.perf_counter() - th0))
     e1.record()
     barrier()
     ms_e2e = maxrank(e0.elapsed_time(e1)) / args.steps
@@ -658,6 +669,9 @@ def main():
             "e2e": {"value": world * units / (ms_e2e * 1e-3), "unit": "traj-steps/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(W.host_in.numel() * 4), "d2h_bytes_per_step": int((P + 1) * 4),
                     "h2d_gbs_this_box": h2d_gbs,
+                    "host_step_ms": {"min": min(step_t), "median": statistics.median(step_t), "max": max(step_t),
+                                     "note": "host wall clock of each timed step on rank 0 (diagnostic: a one-off stall shows as max >> median; "
+                                             "value is total device time / steps as the contract says)"},
                     "note": "the input copy of step i+1 overlaps the kernels of step i; once the step is shorter than the copy, e2e is the PCIe rate"},
             "gpu_launches": int(launches),
             "clocks": clocks,

@@ -188,13 +188,20 @@ int mlp_fwd_pad(const CcModule* m, long long B) {
 // width <= 64, g without activation.  Taken where the FFMA reverse pass runs one or two warps per SM or not at all (some
 // width > 32); CC_B200_MLPB=0 disables it, =1 takes it for every eligible architecture.  The forward pass of such a model
 // runs on family 5 whenever a tape is requested (it appends the final state to the tape).
-bool mlpb_ok(const CcModule* m) {
+// Widths 33..64 always take it (the FFMA reverse pass does not hold them); widths 17..32 take it from CC_B200_MLPB_MINB32
+// trajectories on (default 1024, the measured range: (32,32,2) reverse pass of 32 steps 2.19 vs 4.69 ms at B = 1024 -- one
+// tile's round chain is 68 us per step, one FFMA warp's 146 us -- and 9.1 vs 33.0 ms at B = 65,536; (20,25,1): 1.48 vs 2.26 ms
+// and 6.1 vs 7.8 ms; gpurun_out/r02f_mlpb_thresh.log); narrower networks stay on the [4][4]-tile FFMA kernels.
+bool mlpb_ok(const CcModule* m, long long B) {
   const char* env = getenv("CC_B200_MLPB");
   if (env && atoi(env) == 0) return false;
   const int pad = mlp_pad_any(m);
   if (!pad || pad > 64) return false;
   if (m->f.n_layers > 3 || m->g.act_final != CC_ACT_IDENTITY) return false;
-  return pad == 64 || (env && atoi(env) == 1);
+  if (pad == 64 || (env && atoi(env) == 1)) return true;
+  const char* mb = getenv("CC_B200_MLPB_MINB32");
+  const long long minb = mb ? atoll(mb) : 1024;
+  return pad == 32 && minb > 0 && B >= minb;
 }
 void mlp_args(const CcModule* m, CcMlpArgs* a) {
   memset(a, 0, sizeof(*a));
@@ -668,7 +675,7 @@ int32_t cc_module_supported(const CcModule* m, int32_t with_grad) {
   o.bwd = with_grad != 0;
   const CcModule* mods[1] = {m};
   if (!with_grad && mlp_fwd_pad(m, 65536)) return CC_OK;
-  if (with_grad && mlpb_ok(m)) return CC_OK;
+  if (with_grad && mlpb_ok(m, 65536)) return CC_OK;
   return make_plan(mods, 1, 65536, 1000, o, &p);
 }
 
@@ -680,7 +687,7 @@ int32_t cc_kernel_family_at(const CcModule* c, const CcModule* m, int32_t with_g
   if (rc) return rc;
   if (c && (rc = validate_module(c, "controller"))) return rc;
   if (!c && !with_grad && mlp_fwd_pad(m, B)) return 5;
-  if (!c && with_grad && mlpb_ok(m)) return 6;
+  if (!c && with_grad && mlpb_ok(m, B)) return 6;
   CcKParams p;
   PlanOpts o;
   o.bwd = with_grad != 0;
@@ -701,7 +708,7 @@ size_t cc_rollout_tape_bytes(const CcModule* m, int64_t B, int32_t T, int32_t ck
       return ((size_t)((T + p.lin_m - 1) / p.lin_m) * m->state_dim * Bpad + 2 * (size_t)T) * sizeof(float);
   }
   // (family 6 reads the final state behind the step times)
-  const size_t xT = (ckpt_every == 1 && !validate_module(m, "model") && mlpb_ok(m)) ? (size_t)m->state_dim * Bpad : 0;
+  const size_t xT = (ckpt_every == 1 && !validate_module(m, "model") && mlpb_ok(m, B)) ? (size_t)m->state_dim * Bpad : 0;
   return ((size_t)n_ckpt_of(T, ckpt_every) * m->state_dim * Bpad + 2 * (size_t)T + xT) * sizeof(float);
 }
 
@@ -743,7 +750,7 @@ int32_t cc_rollout_fwd(const CcModule* m, const float* theta, const float* u, co
   if (B < 0 || T < 0) return fail(CC_ERR_INVALID_ARG, "negative size");
   if (tape && ckpt_every < 1) return fail(CC_ERR_INVALID_ARG, "ckpt_every must be >= 1");
   if (B == 0) return CC_OK;
-  const bool rev6 = tape && ckpt_every == 1 && mlpb_ok(m);  // the tcgen05 reverse pass will read this tape
+  const bool rev6 = tape && ckpt_every == 1 && mlpb_ok(m, B);  // the tcgen05 reverse pass will read this tape
   if (const int pad = rev6 ? mlp_pad_any(m) : mlp_fwd_pad(m, B)) {  // deep-MLP model: one tcgen05.mma batch per layer (cc_mlp_kernels.cuh)
     CcMlpArgs a;
     mlp_args(m, &a);

@@ -92,6 +92,12 @@ def test_plan_picks_tcgen05_for_depth0_models():
         assert fam(None, model_variants()["full_s5_w10_d2"], 0) == 5          # deep MLP forward: one tcgen05.mma batch per layer
         assert fam(None, model_variants()["full_s5_w10_d2"], 1) == 0          # its reverse pass: FFMA kernels
         assert L.cc_kernel_family_at(None, ctypes.byref(conv(model_variants()["full_s5_w10_d2"]).to_c()), 0, 64) == 0  # small batch
+        # reverse pass of deep MLPs: widths 33..64 always on the tcgen05 family 6, widths 17..32 from 1024 trajectories on, narrower never
+        from oracle import np_oracle as _O
+        w64, w25, w10 = (conv(_O.make_node(s_, 1, 1, f_width=w_, f_depth=2)).to_c() for s_, w_ in ((40, 64), (20, 25), (5, 10)))
+        assert L.cc_kernel_family_at(None, ctypes.byref(w64), 1, 8) == 6
+        assert L.cc_kernel_family_at(None, ctypes.byref(w25), 1, 1023) == 0 and L.cc_kernel_family_at(None, ctypes.byref(w25), 1, 1024) == 6
+        assert L.cc_kernel_family_at(None, ctypes.byref(w10), 1, 65536) == 0
         os.environ["CC_B200_LIN"] = "0"   # the families below the blocked linear one
         assert fam(None, compact, 0) == 1            # open-loop forward
         assert fam(None, compact, 1) == 3            # ModelTrainer reverse pass: tcgen05 incl. the weight-gradient product

@@ -604,6 +604,8 @@ MLPB_GPU_CASES = {
     "s20_w40_d1_noint": (lambda: O.make_node(20, 1, 3, f_width=40, f_depth=1, integrator=O.INT_NONE, f_use_bias=False,
                                              g_use_bias=False, f_act_final=O.ACT_TANH), 33, 21),
     "s33_w64_d2_one_step": (lambda: O.make_node(33, 4, 4, f_width=64, f_depth=2, readout_pre_step=True), 5, 1),
+    # widths 17..32 take the family from 1024 trajectories on (padded to the 64-wide rounds)
+    "s20_w25_d2_b1100": (lambda: O.make_node(20, 1, 1, f_width=25, f_depth=2, f_act_final=O.ACT_TANH), 1100, 12),
 }
 
 
