@@ -264,3 +264,55 @@ def test_gpu_closed_loop_collection_with_a_controller(T_):
     inp = torch.as_tensor(np.concatenate([sample.extras["ref"][:, :200], obs[:, :200]], axis=2), device="cuda")
     y = ops.batched_unroll(ctrl.spec, ctrl.theta, inp.contiguous(), None)
     assert np.abs(y[:, 1:, :].detach().cpu().numpy() - act).max() < 1e-5 * max(np.abs(act).max(), 1e-3)
+
+
+@pytest.mark.gpu
+def test_gpu_end_to_end_workflow_collect_train_model_train_controller_evaluate():
+    """the reference's documented workflow (docs/2_collecting_data..., 3_training_a_model, 4_training_a_controller notebooks) on this
+    framework only: record trajectories from the two-segment source, fit the compact neural-ODE model (ModelTrainer step =
+    the BPTT kernels), train a compact controller against the fitted model (ControllerTrainer step = closed-loop BPTT kernels),
+    then run that controller in closed loop with the ENVIRONMENT kernel"""
+    import torch
+    from collections import OrderedDict
+
+    from chain_control_b200.env import collect as CL
+    from chain_control_b200.env import make_env
+    from chain_control_b200.examples.neural_ode_controller_compact_example import make_neural_ode_controller
+    from chain_control_b200.examples.neural_ode_model_compact_example import make_neural_ode_model
+    from chain_control_b200.train import (DictLogger, EvaluationMetrices, ModelControllerTrainer, SupervisedDataset, Tracker,
+                                          TrainingOptionsController, TrainingOptionsModel, UnsupervisedDataset, make_dataloader, optim)
+    from chain_control_b200.utils import rmse
+
+    env = make_env("two_segments_v1", time_limit=5.0)
+    key = env.obs_key
+    train = CL.sample_feedforward_and_collect(env, seeds_gp=[0, 1, 2, 3], seeds_cos=[4, 8, 12, 2])  # defaults.py:21-23
+    val = CL.sample_feedforward_and_collect(env, seeds_gp=[15, 16], seeds_cos=[2.5, 5.0])
+    assert train.action.shape == (8, 500, 1) and train.obs[key].shape == (8, 501, 1)
+    to = lambda a: torch.as_tensor(np.ascontiguousarray(a, np.float32), device="cuda")
+    u_tr, y_tr = to(train.action), OrderedDict([(key, to(train.obs[key]))])
+    u_va, y_va = to(val.action), OrderedDict([(key, to(val.obs[key]))])
+
+    model = make_neural_ode_model(1, OrderedDict([(key, 1)]), 0.01, state_dim=20, f_depth=0, u_transform=np.arctan)
+    opts = TrainingOptionsModel(make_dataloader(SupervisedDataset(u_tr, y_tr), key=1, n_minibatches=1),
+                                optim.chain(optim.clip_by_global_norm(1.0), optim.adam(3e-3)),
+                                metrices=(EvaluationMetrices(data=(u_va, y_va), metrices=(lambda y, yhat: {"val_rmse": rmse(y, yhat)},)),))
+    trainer = ModelControllerTrainer(model, model_train_options=opts, loggers=[DictLogger()], trackers=[Tracker("val_rmse")])
+    trainer.run(150)
+    logs = trainer.get_logs()[0]
+    assert np.all(np.isfinite(logs["train_mse"]))
+    assert logs["train_mse"][-10:].mean() < 0.5 * logs["train_mse"][:3].mean(), (logs["train_mse"][:3], logs["train_mse"][-3:])
+    fitted = trainer.trackers[0].best_model_or_controller()
+
+    src = CL.random_steps_source(env, seeds=list(range(6)), max_abs_amplitude=1.0)
+    refs = OrderedDict([(key, to(src.get_references()[key]))])
+    controller = make_neural_ode_controller(2, 1, 0.01, 5, f_depth=0)
+    copts = TrainingOptionsController(make_dataloader(UnsupervisedDataset(refs), key=1, n_minibatches=1),
+                                      optim.chain(optim.clip_by_global_norm(1.0), optim.adam(1e-2)))
+    ct = ModelControllerTrainer(fitted, controller, controller_train_options=copts, loggers=[DictLogger()], trackers=[Tracker("loss")])
+    ct.run(40)
+    clogs = ct.get_logs()[0]
+    assert np.all(np.isfinite(clogs["loss"])) and clogs["loss"][-5:].mean() < clogs["loss"][:2].mean()
+    best = ct.trackers[0].best_model_or_controller()
+    sample = CL.collect_exhaust_source(env, src, best)
+    assert sample.obs[key].shape == (6, 501, 1) and sample.action.shape == (6, 500, 1)
+    assert np.all(np.isfinite(sample.obs[key])) and np.all(np.isfinite(sample.action))
