@@ -750,7 +750,7 @@ int32_t cc_rollout_fwd(const CcModule* m, const float* theta, const float* u, co
   if (B < 0 || T < 0) return fail(CC_ERR_INVALID_ARG, "negative size");
   if (tape && ckpt_every < 1) return fail(CC_ERR_INVALID_ARG, "ckpt_every must be >= 1");
   if (B == 0) return CC_OK;
-  const bool rev6 = tape && ckpt_every == 1 && mlpb_ok(m, B);  // the tcgen05 reverse pass will read this tape
+  const bool rev6 = tape && mlpb_ok(m, B);  // the tcgen05 reverse pass will read this tape (ckpt_every > 1: by segment replay)
   if (const int pad = rev6 ? mlp_pad_any(m) : mlp_fwd_pad(m, B)) {  // deep-MLP model: one tcgen05.mma batch per layer (cc_mlp_kernels.cuh)
     CcMlpArgs a;
     mlp_args(m, &a);
@@ -759,7 +759,7 @@ int32_t cc_rollout_fwd(const CcModule* m, const float* theta, const float* u, co
     a.tape = (float*)tape;
     a.ckpt_every = tape ? ckpt_every : 1;
     a.ttab = tape ? (float*)tape + (long long)n_ckpt_of(T, a.ckpt_every) * m->state_dim * a.Bpad : nullptr;
-    a.tape_xT = rev6 ? a.ttab + 2 * (long long)T : nullptr;
+    a.tape_xT = rev6 && ckpt_every == 1 ? a.ttab + 2 * (long long)T : nullptr;
     const size_t need = cc_mlp_workspace_bytes(pad, a.L);
     if (need && (!ws || ws_bytes < need)) return fail(CC_ERR_WORKSPACE, "workspace too small: need %zu bytes (cc_rollout_fwd_workspace_bytes)", need);
     a.pack = need ? (float*)ws : nullptr;

@@ -115,22 +115,25 @@ size_t cc_mlpb_workspace_bytes(int L, long long B) {
   return ((size_t)2 * L * CC_MLPB_SLAB_FLOATS + (size_t)((B + 127) / 128) * CC_MLPB_CTA_FLOATS(L)) * 4;
 }
 
-// prep (operand slabs) -> reverse kernel (per-CTA sums) -> reduction into theta_bar
-int cc_launch_mlpb_bwd(CcMlpArgs a, float* theta_bar, int P, void* ws, void* stream, char* err, int errlen) {
+// prep (operand slabs) -> reverse kernel (per-CTA sums) -> reduction into theta_bar.  Segment replay (ckpt_every > 1) calls it
+// once per segment, last segment first: `phases` bit 0 = run the preparation (first call), bit 1 = run the reduction (last call)
+int cc_launch_mlpb_bwd(CcMlpArgs a, float* theta_bar, int P, void* ws, void* stream, char* err, int errlen, int phases) {
   a.pack = (float*)ws;
   a.recs = a.pack + (size_t)2 * a.L * CC_MLPB_SLAB_FLOATS;
   const char* fe = getenv("CC_B200_MLPB_FLUSH");
   a.flush_every = fe && atoi(fe) >= 1 ? atoi(fe) : 2;
   const int n_cta = (int)((a.B + 127) / 128);
+  if (phases & 1) {
 #ifdef CC_EMULATE
-  ccemu::launch(2 * a.L, 256, 0, [&]() { cc_mlpb_prep_kernel(a); });
+    ccemu::launch(2 * a.L, 256, 0, [&]() { cc_mlpb_prep_kernel(a); });
 #else
-  cc_mlpb_prep_kernel<<<2 * a.L, 256, 0, (cudaStream_t)stream>>>(a);
-  if (cudaError_t e = cudaGetLastError(); e != cudaSuccess) {
-    snprintf(err, errlen, "cc_mlpb_prep_kernel launch failed: %s", cudaGetErrorString(e));
-    return CC_ERR_CUDA;
-  }
+    cc_mlpb_prep_kernel<<<2 * a.L, 256, 0, (cudaStream_t)stream>>>(a);
+    if (cudaError_t e = cudaGetLastError(); e != cudaSuccess) {
+      snprintf(err, errlen, "cc_mlpb_prep_kernel launch failed: %s", cudaGetErrorString(e));
+      return CC_ERR_CUDA;
+    }
 #endif
+  }
   // worker threads per trajectory: 2 (32 columns each).  CC_B200_MLPB_NH=4 selects the 16-column variant (640 threads):
   // measured 9 % slower at (64,64,2) x 65,536 (10.06 vs 9.15 ms per 32 steps) -- kept because the tests run both.
   const char* nhe = getenv("CC_B200_MLPB_NH");
@@ -140,6 +143,7 @@ int cc_launch_mlpb_bwd(CcMlpArgs a, float* theta_bar, int P, void* ws, void* str
   else if (a.L == 3) rc = nh == 2 ? mlpb_launch<3, 2>(a, stream, err, errlen) : mlpb_launch<3, 4>(a, stream, err, errlen);
   else { snprintf(err, errlen, "deep-MLP tcgen05 reverse pass: %d layers not built", a.L); return CC_ERR_UNSUPPORTED; }
   if (rc) return rc;
+  if (!(phases & 2)) return CC_OK;
 #ifdef CC_EMULATE
   ccemu::launch((P + 127) / 128, 128, 0, [&]() { cc_mlpb_reduce_kernel(a, theta_bar, n_cta, P); });
 #else

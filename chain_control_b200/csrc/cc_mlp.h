@@ -31,6 +31,14 @@ struct CcMlpArgs {
   const float* ybar;  // [B][T+1][O]
   float* recs;        // per-CTA sums and stage-input slots
   int flush_every;    // steps between flushes of the weight-gradient accumulators
+  // segment replay (checkpointed recomputation, ckpt_every > 1): the kernels walk the steps [k0, k1) of the T-step problem
+  // (u / y / ybar keep their full-length rows); k1 = 0 means the whole range
+  int k0, k1;
+  const float* carry_in;  // forward: [S][Bpad] state at step k0 (a checkpoint) instead of x0; null = x0
+  int seg_tape;           // forward: the tape is segment-local (row k - k0, every step)
+  int seg_last;           // reverse: this segment ends at step T (terminal readout term, adjoint starts at zero)
+  int seg_accum;          // reverse: per-CTA sums already hold later segments' sums (do not zero)
+  float* lam_io;          // reverse: [S][Bpad] adjoint carried between segments (read unless seg_last, always written), or null
 };
 
 
@@ -39,4 +47,4 @@ size_t cc_mlp_workspace_bytes(int pad, int L);
 int cc_launch_mlp_fwd(const CcMlpArgs& a, int pad, void* stream, char* err, int errlen);
 // reverse pass (widths <= 64): workspace = [2 L slabs][per-CTA records]; theta_bar gets all P parameters
 size_t cc_mlpb_workspace_bytes(int L, long long B);
-int cc_launch_mlpb_bwd(CcMlpArgs a, float* theta_bar, int P, void* ws, void* stream, char* err, int errlen);
+int cc_launch_mlpb_bwd(CcMlpArgs a, float* theta_bar, int P, void* ws, void* stream, char* err, int errlen, int phases = 3);

@@ -190,9 +190,12 @@ __global__ void __launch_bounds__(CC_MLP2_THREADS, 2) cc_mlp2_fwd_kernel(const C
     float x[PC], acc[PC];
 #pragma unroll
     for (int i = 0; i < PC; ++i) {
-      x[i] = (a.x0 && act && cb + i < a.S) ? __ldg(a.x0 + b * a.S + cb + i) : 0.f;
+      x[i] = (a.carry_in && act && cb + i < a.S) ? a.carry_in[(size_t)(cb + i) * a.Bpad + b]
+                                                 : ((a.x0 && act && cb + i < a.S) ? __ldg(a.x0 + b * a.S + cb + i) : 0.f);
       acc[i] = 0.f;
     }
+    // segment replay (checkpointed recomputation): steps [kbeg, kend) from the checkpoint carry_in, no outputs (a.y null)
+    const int kbeg = a.k0, kend = a.k1 > 0 ? a.k1 : a.T;
     // deferred readout: stash(slot) = partial dot products of this half (half 1 -> TMEM slot, half 0 -> registers);
     // flush(slot, krow) = half 0 adds half 1's partial and writes y[krow]; a flush sits behind the d_ready of a round that was
     // published after the stash (or behind the CTA barrier at the end)
@@ -226,21 +229,21 @@ __global__ void __launch_bounds__(CC_MLP2_THREADS, 2) cc_mlp2_fwd_kernel(const C
         cc_tmem_wait_ld();
         for (int i = 0; i < 4; ++i) q[i] = __uint_as_float(u[i]);
 #endif
-        if (act)
+        if (act && a.y)
 #pragma unroll
           for (int o = 0; o < CC_TINY_O; ++o)
             if (o < a.O) a.y[b * (long long)(a.T + 1) * a.O + krow * a.O + o] = a.out_scale * cc_act(a.g.act, ymine[slot][o] + q[o]);
       }
     };
     stash(0);  // y0 = g(x0)      neural_ode_model.py:160-175
-    long long pend0 = 0;  // row waiting in slot 0 (-1: none)
+    long long pend0 = kbeg == 0 ? 0 : -1;  // row waiting in slot 0 (-1: none)
     float vin[CC_TINY_O];
 #pragma unroll
-    for (int i = 0; i < CC_TINY_O; ++i) vin[i] = (hh == 0 && i < a.I && act && a.T > 0) ? __ldg(a.u + b * (long long)a.T * a.I + i) : 0.f;
-    for (int k = 0; k < a.T; ++k) {
-      if (a.tape && blockIdx.x == 0 && tid == 0) a.ttab[k] = 0.f;
-      if (a.tape && act && (k % a.ckpt_every == 0)) {
-        const long long ck = k / a.ckpt_every;
+    for (int i = 0; i < CC_TINY_O; ++i) vin[i] = (hh == 0 && i < a.I && act && kend > kbeg) ? __ldg(a.u + b * (long long)a.T * a.I + (long long)kbeg * a.I + i) : 0.f;
+    for (int k = kbeg; k < kend; ++k) {
+      if (a.tape && !a.seg_tape && blockIdx.x == 0 && tid == 0) a.ttab[k] = 0.f;
+      if (a.tape && act && (a.seg_tape || k % a.ckpt_every == 0)) {
+        const long long ck = a.seg_tape ? k - kbeg : k / a.ckpt_every;
 #pragma unroll
         for (int s = 0; s < PC; ++s)
           if (cb + s < a.S) a.tape[(ck * a.S + cb + s) * a.Bpad + b] = x[s];
@@ -256,7 +259,7 @@ __global__ void __launch_bounds__(CC_MLP2_THREADS, 2) cc_mlp2_fwd_kernel(const C
         float vt[CC_TINY_O];
 #pragma unroll
         for (int i = 0; i < CC_TINY_O; ++i) vt[i] = (i < a.I) ? cc_ut(a.ut, a.u_scale, vin[i]) : 0.f;
-        if (k + 1 < a.T) {
+        if (k + 1 < kend) {
 #pragma unroll
           for (int i = 0; i < CC_TINY_O; ++i)
             if (i < a.I && act) vin[i] = __ldg(a.u + b * (long long)a.T * a.I + (long long)(k + 1) * a.I + i);

@@ -353,29 +353,32 @@ __global__ void __launch_bounds__(CC_MLP_THREADS, PAD >= 64 ? 2 : 3) cc_mlp_fwd_
     float x[PAD], acc[PAD];
 #pragma unroll
     for (int i = 0; i < PAD; ++i) {
-      x[i] = (a.x0 && act && i < a.S) ? __ldg(a.x0 + b * a.S + i) : 0.f;
+      x[i] = (a.carry_in && act && i < a.S) ? a.carry_in[(size_t)i * a.Bpad + b] : ((a.x0 && act && i < a.S) ? __ldg(a.x0 + b * a.S + i) : 0.f);
       acc[i] = 0.f;
     }
+    // segment replay (checkpointed recomputation): steps [kbeg, kend) from the checkpoint carry_in, no outputs (a.y null)
+    const int kbeg = a.k0, kend = a.k1 > 0 ? a.k1 : a.T;
+    const bool wy = a.y != nullptr;
     // y0 = g(x0)      neural_ode_model.py:160-175
     float y[CC_TINY_O];
     cc_mlp_readout<PAD>(gw, x, a.O, a.g.act, a.out_scale, y);
-    if (act)
+    if (act && wy && kbeg == 0)
       for (int o = 0; o < a.O; ++o) a.y[b * (long long)(a.T + 1) * a.O + o] = y[o];
     float vin[CC_TINY_O];
 #pragma unroll
-    for (int i = 0; i < CC_TINY_O; ++i) vin[i] = (i < a.I && act && a.T > 0) ? __ldg(a.u + b * (long long)a.T * a.I + i) : 0.f;
-    for (int k = 0; k < a.T; ++k) {
-      if (a.tape && blockIdx.x == 0 && tid == 0) a.ttab[k] = 0.f;
+    for (int i = 0; i < CC_TINY_O; ++i) vin[i] = (i < a.I && act && kend > kbeg) ? __ldg(a.u + b * (long long)a.T * a.I + (long long)kbeg * a.I + i) : 0.f;
+    for (int k = kbeg; k < kend; ++k) {
+      if (a.tape && !a.seg_tape && blockIdx.x == 0 && tid == 0) a.ttab[k] = 0.f;
       float vt[CC_TINY_O];
 #pragma unroll
       for (int i = 0; i < CC_TINY_O; ++i) vt[i] = (i < a.I) ? cc_ut(a.ut, a.u_scale, vin[i]) : 0.f;
-      if (k + 1 < a.T) {
+      if (k + 1 < kend) {
 #pragma unroll
         for (int i = 0; i < CC_TINY_O; ++i)
           if (i < a.I && act) vin[i] = __ldg(a.u + b * (long long)a.T * a.I + (long long)(k + 1) * a.I + i);
       }
-      if (a.tape && act && (k % a.ckpt_every == 0)) {  // open loop: the pre-step state of every checkpointed step is the tape
-        const long long ck = k / a.ckpt_every;
+      if (a.tape && act && (a.seg_tape || k % a.ckpt_every == 0)) {  // open loop: the pre-step state of every checkpointed step is the tape
+        const long long ck = a.seg_tape ? k - kbeg : k / a.ckpt_every;
 #pragma unroll
         for (int s = 0; s < PAD; ++s)
           if (s < a.S) a.tape[(ck * a.S + s) * a.Bpad + b] = x[s];
@@ -389,7 +392,7 @@ __global__ void __launch_bounds__(CC_MLP_THREADS, PAD >= 64 ? 2 : 3) cc_mlp_fwd_
       cc_mlp_round<PAD>(t, 0);
       if (a.pre) {  // compact model: y = g(x) BEFORE the update (neural_ode_model_compact_example.py:94-110); overlaps the MMAs
         cc_mlp_readout<PAD>(gw, x, a.O, a.g.act, a.out_scale, y);
-        if (act)
+        if (act && wy)
           for (int o = 0; o < a.O; ++o) a.y[b * (long long)(a.T + 1) * a.O + (long long)(k + 1) * a.O + o] = y[o];
       }
 #pragma unroll 1
@@ -410,7 +413,7 @@ __global__ void __launch_bounds__(CC_MLP_THREADS, PAD >= 64 ? 2 : 3) cc_mlp_fwd_
       }
       if (!a.pre) {  // full model: y = g(x_next)      neural_ode_model.py:131-137
         cc_mlp_readout<PAD>(gw, x, a.O, a.g.act, a.out_scale, y);
-        if (act)
+        if (act && wy)
           for (int o = 0; o < a.O; ++o) a.y[b * (long long)(a.T + 1) * a.O + (long long)(k + 1) * a.O + o] = y[o];
       }
     }

@@ -30,7 +30,10 @@
 //   * the tape is the forward family's ([k][S][Bpad] pre-step states) plus the final state x_T (post-step readout only).
 //
 // Limits (checked by the host, cc_abi.cu: mlpb_ok): f with 2 or 3 Linear layers of width <= 64, g one Linear layer without
-// activation, time-invariant, no feed-through, 1..4 inputs, <= 4 outputs, ckpt_every = 1, no ubar.
+// activation, time-invariant, no feed-through, 1..4 inputs, <= 4 outputs, no ubar.
+// ckpt_every > 1 (cc_abi_bwd.inc): the host replays each segment [k0, k1) with the forward family into a segment-local tape and
+// launches this kernel per segment, last first: the adjoint enters / leaves through lam_io, the per-CTA sums accumulate
+// (seg_accum), the terminal readout term belongs to the last segment only (seg_last).
 #pragma once
 #include "cc_mlp128_kernels.cuh"
 
@@ -352,7 +355,8 @@ __global__ void __launch_bounds__(128 * NH + 128, 1) cc_mlpb_bwd_kernel(const CC
     // ---- producer + MMA issuer (one thread) ----
     if (warp == 4 * NH && lane == 0) {
       const int R = tab[63];
-      const long long rounds = (long long)a.T * R;
+      const int kend = a.k1 > 0 ? a.k1 : a.T;
+      const long long rounds = (long long)(kend - a.k0) * R;
       const uint32_t ring_u32 = cc_smem_u32(ring);
       const uint64_t opa2_u32 = cc_umma_desc_kmajor(cc_smem_u32(opa2), 144, 4608), opa_u32 = cc_mlpb_desc(opa2_u32, CC_MLPB_OPG * 4u), opb_u32 = cc_umma_desc_kmajor(cc_smem_u32(opb), 144, 4608);
       const uint32_t tb = c.t.tbase;
@@ -366,7 +370,7 @@ __global__ void __launch_bounds__(128 * NH + 128, 1) cc_mlpb_bwd_kernel(const CC
       };
       if (rounds > 0) { request(0); request(1); }  // (requests past the last round are never waited for: harmless reads of the pack)
       uint32_t apar = 0, dpar = 0, fpar = 0;
-      if (post) {  // terminal state: readout gradient only (hi then lo part of x_T)
+      if (post && a.seg_last) {  // terminal state: readout gradient only (hi then lo part of x_T)
         for (int part = 0; part < 2; ++part) {
           cc_mbar_wait(a_ready, apar); apar ^= 1;
           cc_tc_fence_after();
@@ -429,18 +433,21 @@ __global__ void __launch_bounds__(128 * NH + 128, 1) cc_mlpb_bwd_kernel(const CC
     const float c6 = h / 6.f, c3 = h / 3.f, c2 = h / 2.f;
     const long long yrow = (long long)(a.T + 1) * a.O;
     // per-CTA sums start at zero; opB's unused rows 72..79 stay zero
-    for (int l = 0; l < L; ++l)
-      for (int j = 0; j < 80 / NH; ++j) rec[(size_t)(l * 80 + (80 / NH) * hh + j) * 128 + row] = 0.f;
+    if (!a.seg_accum)
+      for (int l = 0; l < L; ++l)
+        for (int j = 0; j < 80 / NH; ++j) rec[(size_t)(l * 80 + (80 / NH) * hh + j) * 128 + row] = 0.f;
     if (hh == 0)
       for (int r = 8; r < 16; ++r) opb_tail[cc_mlpb_row(r)] = 0.f;
     float lam[PC], dl[PC], hid[L - 1][PC];  // (the stage sum accumulates in lam; the incoming adjoint waits in slot 3 of the scratch)
     float* const zs_c = zs + (size_t)cb * 128 + row;  // this thread's column block of the scratch slots
     float* lam0 = zs_c + (size_t)(3 * 64) * 128;
     float gb[CC_TINY_O];
+    // (segment replay: the adjoint of the later segment comes in through lam_io)
 #pragma unroll
-    for (int i = 0; i < PC; ++i) lam[i] = 0.f;
+    for (int i = 0; i < PC; ++i) lam[i] = (a.lam_io && !a.seg_last && act && cb + i < a.S) ? a.lam_io[(size_t)(cb + i) * a.Bpad + b] : 0.f;
 #pragma unroll
     for (int o = 0; o < CC_TINY_O; ++o) gb[o] = 0.f;
+    const int kbeg = a.k0, kend = a.k1 > 0 ? a.k1 : a.T;
 
     // readout cotangent rows of opA2 (hi rows 0..3, lo rows 4..7) -- written by half 0
     auto put_d = [&](const float (&d)[CC_TINY_O]) {
@@ -501,7 +508,7 @@ __global__ void __launch_bounds__(128 * NH + 128, 1) cc_mlpb_bwd_kernel(const CC
         }
     };
 
-    if (post) {  // y_T = g(x_T): the final state sits behind the step times on the tape
+    if (post && a.seg_last) {  // y_T = g(x_T): the final state sits behind the step times on the tape
       float d[CC_TINY_O];
 #pragma unroll
       for (int o = 0; o < CC_TINY_O; ++o) d[o] = (o < a.O && act) ? a.out_scale * __ldg(a.ybar + b * yrow + (long long)a.T * a.O + o) : 0.f;
@@ -532,8 +539,8 @@ __global__ void __launch_bounds__(128 * NH + 128, 1) cc_mlpb_bwd_kernel(const CC
     }
 
     int since_flush = 0;
-    for (int k = a.T - 1; k >= 0; --k) {
-      const float* xk = a.tape + (size_t)k * a.S * a.Bpad + b;
+    for (int k = kend - 1; k >= kbeg; --k) {
+      const float* xk = a.tape + (size_t)(k - kbeg) * a.S * a.Bpad + b;
       float d[CC_TINY_O], dg[CC_TINY_O];
 #pragma unroll
       for (int o = 0; o < CC_TINY_O; ++o) {
@@ -721,7 +728,7 @@ __global__ void __launch_bounds__(128 * NH + 128, 1) cc_mlpb_bwd_kernel(const CC
 #pragma unroll
         for (int o = 0; o < CC_TINY_O; ++o) gb[o] += dg[o];
       ++since_flush;
-      if (since_flush == a.flush_every || k == 0) {
+      if (since_flush == a.flush_every || k == kbeg) {
         flush_dw();
         since_flush = 0;
       }
@@ -739,8 +746,13 @@ __global__ void __launch_bounds__(128 * NH + 128, 1) cc_mlpb_bwd_kernel(const CC
     }
     cc_mlpb_worker_sync<NWORK>();
     float* grec = rec + (size_t)L * 80 * 128;
-    for (int i = tid; i < 8 * 64; i += NWORK) grec[i] = gacc[i];
-    if (tid < CC_TINY_O) grec[8 * 64 + tid] = (gbw[tid] + gbw[4 + tid]) + (gbw[8 + tid] + gbw[12 + tid]);
+    for (int i = tid; i < 8 * 64; i += NWORK) grec[i] = (a.seg_accum ? grec[i] : 0.f) + gacc[i];
+    if (tid < CC_TINY_O) grec[8 * 64 + tid] = (a.seg_accum ? grec[8 * 64 + tid] : 0.f) + ((gbw[tid] + gbw[4 + tid]) + (gbw[8 + tid] + gbw[12 + tid]));
+    if (a.lam_io && act) {  // adjoint of the state at step k0: the next (earlier) segment starts from it
+#pragma unroll
+      for (int i = 0; i < PC; ++i)
+        if (cb + i < a.S) a.lam_io[(size_t)(cb + i) * a.Bpad + b] = lam[i];
+    }
   }
 #ifndef CC_EMULATE
   cc_tc_fence_before();

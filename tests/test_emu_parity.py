@@ -367,3 +367,24 @@ def test_emu_mlpb_flush_interval_and_narrow(monkeypatch):
         assert l2rel(tb, tb64) < 1e-5
         res.append(tb)
     assert l2rel(res[0], res[2]) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["s40_w48_d2", "s64_w64_d1_tanh_pre"])
+def test_emu_mlpb_checkpointed_segment_replay(name, monkeypatch):
+    """family 6 with ckpt_every > 1: the forward family writes the state every K steps only; the reverse entry point replays each
+    segment (family-5 kernel from the checkpoint, no outputs) and walks it backwards on the emulated tensor cores, adjoint and
+    per-CTA gradient sums carried between the launches -- same gradient as the unsegmented pass"""
+    monkeypatch.setenv("CC_B200_MLP", "1")
+    mk, B, _ = MLPB_CASES[name]
+    spec = mk()
+    T = 5
+    theta = O.init_params(spec, 1).astype(np.float32)
+    u = _u(B, T, spec.input_dim)
+    x0 = (0.1 * np.random.default_rng(3).normal(size=(B, spec.state_dim))).astype(np.float32)
+    ybar = np.random.default_rng(5).normal(size=(B, T + 1, spec.output_dim)).astype(np.float32)
+    tb64, _ = O.rollout_bwd(spec, theta, u, ybar, x0=x0)
+    _, tb1, _ = E.np_rollout_bwd(E.emu(), conv(spec), theta, u, ybar, x0, want_ubar=False)
+    for K in (2, 4, 7):  # 3 segments (2 + 2 + 1), 2 segments (4 + 1), one segment longer than T
+        y, tbk, _ = E.np_rollout_bwd(E.emu(), conv(spec), theta, u, ybar, x0, want_ubar=False, ckpt_every=K)
+        assert l2rel(tbk, tb64) < 1e-5, K
+        assert l2rel(tbk, tb1) < 2e-6, K  # (flush points of the TMEM accumulators move with the segment boundaries)

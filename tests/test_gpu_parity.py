@@ -639,6 +639,58 @@ def test_mlpb_reverse_vs_oracle(name, flush, T_, monkeypatch):
     assert (tb2 == tb).all()  # deterministic: fixed-order reduction of the per-CTA sums
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,K", [("s40_w48_d2", 8), ("s64_w64_d1_tanh_pre", 7), ("s64_w64_d2_tanh", 50), ("s20_w25_d2_b1100", 5)])
+def test_mlpb_checkpointed_vs_oracle(name, K, T_):
+    """family 6 with ckpt_every = K > 1 (north_star (3) for the deep-MLP family): checkpoints every K steps from the family-5
+    forward kernel, segment replay + tensor-core reverse pass per segment; against the fp64 oracle and the unsegmented pass"""
+    from chain_control_b200 import ops
+
+    mk, B, T = MLPB_GPU_CASES[name]
+    spec = mk()
+    theta = O.init_params(spec, 1).astype(np.float32)
+    u = _u(B, T, spec.input_dim)
+    x0 = (0.1 * np.random.default_rng(3).normal(size=(B, spec.state_dim))).astype(np.float32)
+    ybar = np.random.default_rng(5).normal(size=(B, T + 1, spec.output_dim)).astype(np.float32)
+    ref = CO.rollout(spec, theta, u, x0=x0, ybar=ybar, want_ubar=False, dtype=np.float64)
+    y1, _, tape1 = ops.rollout_fwd(conv(spec), T_(theta), T_(u), T_(x0), want_tape=True)
+    tb1, _ = ops.rollout_bwd(conv(spec), T_(theta), T_(u), tape1, T_(ybar), T_(x0))
+    yk, _, tapek = ops.rollout_fwd(conv(spec), T_(theta), T_(u), T_(x0), want_tape=True, ckpt_every=K)
+    assert tapek.numel() < tape1.numel() / min(K, T) * 1.6 + 4 * T + 64  # the tape really shrinks
+    assert (yk == y1).all()
+    tbk, _ = ops.rollout_bwd(conv(spec), T_(theta), T_(u), tapek, T_(ybar), T_(x0), ckpt_every=K)
+    assert l2rel(tbk.cpu().numpy(), ref["theta_bar"]) < 2e-5
+    assert l2rel(tbk.cpu().numpy(), tb1.cpu().numpy()) < 5e-6
+    tbk2, _ = ops.rollout_bwd(conv(spec), T_(theta), T_(u), tapek, T_(ybar), T_(x0), ckpt_every=K)
+    assert (tbk2 == tbk).all()
+
+
+@pytest.mark.gpu
+def test_mlpb_long_horizon_checkpointed_runs(T_):
+    """(64,64,2) ModelTrainer gradient at T = 4,000 x 4,736 trajectories with ckpt_every = 100: the tape is 40 checkpoints
+    (48 MB) instead of 4,000 states (4.8 GB); finite, deterministic, and equal to the sum over two half batches"""
+    import torch
+
+    from chain_control_b200 import ops
+
+    spec = O.make_node(64, 1, 1, f_width=64, f_depth=2, f_act_final=O.ACT_TANH)
+    B, T, K = 4736, 4000, 100
+    theta = T_(O.init_params(spec, 1).astype(np.float32))
+    g = torch.Generator(device="cuda").manual_seed(0)
+    u = torch.rand((B, T, 1), device="cuda", generator=g) * 2 - 1
+    ybar = torch.randn((B, T + 1, 1), device="cuda", generator=g) / (B * T)
+    y, _, tape = ops.rollout_fwd(conv(spec), theta, u, want_tape=True, ckpt_every=K)
+    assert tape.numel() * 4 < 60e6
+    tb, _ = ops.rollout_bwd(conv(spec), theta, u, tape, ybar, ckpt_every=K)
+    assert torch.isfinite(tb).all() and float(tb.abs().max()) > 0
+    h = B // 2
+    parts = []
+    for sl in (slice(0, h), slice(h, B)):
+        _, _, tp = ops.rollout_fwd(conv(spec), theta, u[sl].contiguous(), want_tape=True, ckpt_every=K)
+        parts.append(ops.rollout_bwd(conv(spec), theta, u[sl].contiguous(), tp, ybar[sl].contiguous(), ckpt_every=K)[0])
+    assert l2rel((parts[0] + parts[1]).cpu().numpy(), tb.cpu().numpy()) < 1e-5
+
+
 def test_mlpb_full_size_gradient_vs_oracle(T_):
     """(64,64,2) at 65,536 trajectories (512 tiles on 148 SMs: every CTA slot busy, four waves): ybar is non-zero on 384
     scattered trajectories, so the fp64 oracle computes the same gradient on that sub-batch; plus additivity over the batch"""
