@@ -4,6 +4,7 @@
 //   cc_xla_rollout_fwd / _bwd      eqx.filter_vmap(model.unroll)(inputs) and its VJP           cc/train/step_fn.py:124,133-136
 //   cc_xla_closedloop_fwd / _bwd   eqx.filter_vmap(controller.unroll(model, merge_x_y, noise))  cc/train/step_fn.py:234-236,249-259
 //   cc_xla_mse                     default loss value + cotangent                               cc/utils/utils.py:53-55
+//   cc_xla_two_segments_rollout    B two-segment environments x T control steps (data source)  cc/env/collect/collect.py:78-98
 //
 // Conventions: operands / results are XLA device buffers (F32); the CcModule structs travel as uint8 array attributes
 // (numpy.frombuffer of the ctypes struct); scratch and the tape are extra RESULT buffers sized on the host with
@@ -148,4 +149,20 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(cc_xla_mse, Mse,
                                   .Ret<BufF>()   // ybar
                                   .Ret<BufF>()   // loss_partial
                                   .Attr<float>("inv_n"));
+
+// ---- data source: obs[B,T+1] = two_segments_rollout(params[n,4] f64, actions[B,T] f32): whole episodes from reset ----
+static ffi::Error TwoSegmentsRollout(cudaStream_t stream, ffi::Buffer<ffi::F64> params, BufF actions, ResF obs, int32_t n_sub_steps, float physics_dt) {
+  const auto d = actions.dimensions();
+  const auto pd = params.dimensions();
+  return err_of(cc_env_two_segments_rollout(params.typed_data(), pd[0], d[1] ? actions.typed_data() : nullptr, nullptr, obs->typed_data(), nullptr,
+                                            d[0], (int32_t)d[1], n_sub_steps, (double)physics_dt, stream));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(cc_xla_two_segments_rollout, TwoSegmentsRollout,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()   // params [n, 4]
+                                  .Arg<BufF>()                    // actions [B, T]
+                                  .Ret<BufF>()                    // obs [B, T + 1]
+                                  .Attr<int32_t>("n_sub_steps")
+                                  .Attr<float>("physics_dt"));
 #endif  // CC_HAVE_XLA_FFI

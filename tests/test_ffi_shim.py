@@ -12,9 +12,9 @@ def test_ffi_shim_compiles_and_exports_all_handlers(tmp_path):
     obj = str(tmp_path / "xla_ffi_shim.o")
     subprocess.run(["/usr/bin/g++", "-std=c++17", "-Wall", "-Werror", "-fPIC", "-c", "-I", os.path.join(HERE, "xla_stub"), SHIM, "-o", obj], check=True)
     syms = subprocess.run(["nm", "-g", "--defined-only", obj], check=True, capture_output=True, text=True).stdout
-    for name in ("cc_xla_rollout_fwd", "cc_xla_rollout_bwd", "cc_xla_closedloop_fwd", "cc_xla_closedloop_bwd", "cc_xla_mse"):
+    for name in ("cc_xla_rollout_fwd", "cc_xla_rollout_bwd", "cc_xla_closedloop_fwd", "cc_xla_closedloop_bwd", "cc_xla_mse", "cc_xla_two_segments_rollout"):
         assert f" T {name}" in syms, name
     # and it references exactly the C ABI it wraps
     und = subprocess.run(["nm", "-u", obj], check=True, capture_output=True, text=True).stdout
-    for name in ("cc_rollout_fwd", "cc_rollout_bwd", "cc_closedloop_fwd", "cc_closedloop_bwd", "cc_mse_value_and_cotangent", "cc_last_error"):
+    for name in ("cc_rollout_fwd", "cc_rollout_bwd", "cc_closedloop_fwd", "cc_closedloop_bwd", "cc_mse_value_and_cotangent", "cc_env_two_segments_rollout", "cc_last_error"):
         assert name in und, name

@@ -16,8 +16,9 @@ typedef struct CUstream_st* cudaStream_t;
 namespace xla {
 namespace ffi {
 
-enum class DataType { F32, S32, U8 };
+enum class DataType { F32, S32, U8, F64 };
 inline constexpr DataType F32 = DataType::F32;
+inline constexpr DataType F64 = DataType::F64;
 inline constexpr DataType S32 = DataType::S32;
 
 template <typename T>
@@ -53,7 +54,7 @@ class Error {
 template <DataType dtype>
 class Buffer {
  public:
-  using Native = std::conditional_t<dtype == DataType::F32, float, std::conditional_t<dtype == DataType::S32, int32_t, uint8_t>>;
+  using Native = std::conditional_t<dtype == DataType::F32, float, std::conditional_t<dtype == DataType::F64, double, std::conditional_t<dtype == DataType::S32, int32_t, uint8_t>>>;
   Native* typed_data() const { return data_; }
   Span<int64_t> dimensions() const { return Span<int64_t>(dims_, rank_); }
   size_t element_count() const {
