@@ -10,6 +10,7 @@ all arithmetic happens in libccb200.so.  There is no CPU path.
 from __future__ import annotations
 
 import ctypes as C
+import math
 from typing import Optional
 
 import torch
@@ -190,14 +191,44 @@ class FusedAdam:
         return self.theta
 
 
+# ---- checkpointing policy of the differentiable entry points ---------------------------------------------------------------
+# The reference stores every per-step residual (lax.scan transpose, cc/core/module_utils.py:17); here the tape is the scan
+# carry, and when even that would not fit comfortably the autograd functions switch to checkpointed recomputation
+# (ckpt_every = K > 1: a checkpoint every K steps, segments replayed in the reverse pass) on their own.
+_CKPT = {"every": None, "max_tape_bytes": None}
+
+
+def set_checkpointing(every: Optional[int] = None, max_tape_bytes: Optional[int] = None):
+    """every = K forces ckpt_every = K for batched_unroll / batched_closed_loop (None: automatic); max_tape_bytes = the tape
+    size above which the automatic policy checkpoints (None: a third of the device's memory)."""
+    if every is not None and every < 1:
+        raise ValueError("every must be >= 1")
+    _CKPT["every"], _CKPT["max_tape_bytes"] = every, max_tape_bytes
+
+
+def _ckpt_every(tape_bytes_at_1: int, T: int, device) -> int:
+    if _CKPT["every"] is not None:
+        return int(_CKPT["every"])
+    budget = _CKPT["max_tape_bytes"]
+    if budget is None:
+        budget = torch.cuda.get_device_properties(device).total_memory // 3
+    if tape_bytes_at_1 <= budget or T < 4:
+        return 1
+    return max(2, math.isqrt(T - 1) + 1)  # ceil(sqrt(T)): balances the checkpoints (T / K) against the segment tape (K)
+
+
 class _RolloutFn(torch.autograd.Function):
     """y = vmap(model.unroll)(u); backward = the BPTT kernel (custom VJP, generic cotangent)."""
 
     @staticmethod
     def forward(ctx, theta, u, x0, spec):
         need_grad = theta.requires_grad or u.requires_grad
-        y, _, tape = rollout_fwd(spec, theta, u, x0, want_tape=need_grad)
-        ctx.spec, ctx.tape = spec, tape
+        K = 1
+        if need_grad:
+            m = spec.to_c()
+            K = _ckpt_every(_lib.lib().cc_rollout_tape_bytes(C.byref(m), u.shape[0], u.shape[1], 1), u.shape[1], u.device)
+        y, _, tape = rollout_fwd(spec, theta, u, x0, want_tape=need_grad, ckpt_every=K)
+        ctx.spec, ctx.tape, ctx.K = spec, tape, K
         ctx.save_for_backward(theta, u, x0 if x0 is not None else torch.empty(0, device=u.device))
         ctx.has_x0 = x0 is not None
         ctx.want_ubar = u.requires_grad
@@ -207,7 +238,7 @@ class _RolloutFn(torch.autograd.Function):
     def backward(ctx, ybar):
         theta, u, x0 = ctx.saved_tensors
         tb, ub = rollout_bwd(ctx.spec, theta, u, ctx.tape, ybar.contiguous(), x0 if ctx.has_x0 else None,
-                             want_ubar=ctx.want_ubar)
+                             ckpt_every=ctx.K, want_ubar=ctx.want_ubar)
         return tb, ub, None, None
 
 
@@ -216,8 +247,12 @@ class _ClosedLoopFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, theta_c, theta_m, refs, noise, cspec, mspec):
-        yhat, _, tape = closedloop_fwd(cspec, mspec, theta_c, theta_m, refs, noise, want_tape=theta_c.requires_grad)
-        ctx.cspec, ctx.mspec, ctx.tape = cspec, mspec, tape
+        K = 1
+        if theta_c.requires_grad:
+            c, m = cspec.to_c(), mspec.to_c()
+            K = _ckpt_every(_lib.lib().cc_closedloop_tape_bytes(C.byref(c), C.byref(m), refs.shape[0], refs.shape[1], 1), refs.shape[1], refs.device)
+        yhat, _, tape = closedloop_fwd(cspec, mspec, theta_c, theta_m, refs, noise, want_tape=theta_c.requires_grad, ckpt_every=K)
+        ctx.cspec, ctx.mspec, ctx.tape, ctx.K = cspec, mspec, tape, K
         ctx.save_for_backward(theta_c, theta_m, refs, noise if noise is not None else torch.empty(0, device=refs.device))
         ctx.has_noise = noise is not None
         return yhat
@@ -226,7 +261,7 @@ class _ClosedLoopFn(torch.autograd.Function):
     def backward(ctx, ybar):
         theta_c, theta_m, refs, noise = ctx.saved_tensors
         tb = closedloop_bwd(ctx.cspec, ctx.mspec, theta_c, theta_m, refs, ctx.tape, ybar.contiguous(),
-                            noise if ctx.has_noise else None)
+                            noise if ctx.has_noise else None, ckpt_every=ctx.K)
         return tb, None, None, None, None, None
 
 

@@ -255,3 +255,42 @@ def test_multi_model_streams_match_serial(monkeypatch):
     print(f"[multi-model] 8 systems x 30 x 1501: {1e3 * t1:.1f} ms/step on 8 streams, {1e3 * t0:.1f} ms/step serial")
     for k in l0:
         assert abs(float(l0[k]) - float(l1[k])) <= 1e-6 * max(1.0, abs(float(l0[k]))), k
+
+
+def test_autograd_entry_points_checkpoint_automatically():
+    """ops.set_checkpointing: with a small tape budget the differentiable entry points switch to ckpt_every = ceil(sqrt(T)) on
+    their own (forward writes checkpoints only, the reverse pass replays segments); gradients agree with the full-tape ones"""
+    from chain_control_b200 import ops
+    from chain_control_b200.examples.neural_ode_controller_compact_example import make_neural_ode_controller
+    from chain_control_b200.examples.neural_ode_model import make_neural_ode_model
+    from chain_control_b200.examples.neural_ode_model_compact_example import make_neural_ode_model as make_compact
+
+    obs_spec = OrderedDict(xpos_of_segment_end=1)
+    B, T = 1100, 90
+    u = torch.rand(B, T, 1, device="cuda") * 2 - 1
+    grads = {}
+    try:
+        for tag, kw in (("full", dict(max_tape_bytes=None)), ("auto", dict(max_tape_bytes=1 << 16)), ("k7", dict(every=7))):
+            ops.set_checkpointing(**kw)
+            for name, model in (("deep64", make_neural_ode_model(1, obs_spec, 0.01, state_dim=40, f_width_size=64, f_depth=2, key=3)),
+                                ("default", make_neural_ode_model(1, obs_spec, 0.01, state_dim=5, key=4)),
+                                ("compact50", make_compact(1, obs_spec, 0.01, state_dim=50, f_depth=0, key=5, u_transform=np.arctan))):
+                theta = model.theta.clone().requires_grad_(True)
+                y = model.with_params(theta).unroll_batched(u)["xpos_of_segment_end"]
+                (y.square().mean()).backward()
+                grads[(tag, name)] = theta.grad.clone()
+            model = make_compact(1, obs_spec, 0.01, state_dim=50, f_depth=0, key=5, u_transform=np.arctan)
+            ctrl = make_neural_ode_controller(2, 1, 0.01, 5, f_depth=0, key=6)
+            theta = ctrl.theta.clone().requires_grad_(True)
+            refs = OrderedDict(xpos_of_segment_end=torch.ones(B, T + 1, 1, device="cuda") * torch.linspace(-2, 2, B, device="cuda")[:, None, None])
+            from chain_control_b200.train.step_fn import merge_x_y
+            yhat = ctrl.with_params(theta).unroll(model, merge_x_y).batched(refs)["xpos_of_segment_end"]
+            ((yhat - refs["xpos_of_segment_end"]).square().mean()).backward()
+            grads[(tag, "closed")] = theta.grad.clone()
+    finally:
+        ops.set_checkpointing()
+    for name in ("deep64", "default", "compact50", "closed"):
+        ref = grads[("full", name)]
+        for tag in ("auto", "k7"):
+            err = float((grads[(tag, name)] - ref).norm() / ref.norm())
+            assert err < 2e-5, (name, tag, err)
