@@ -12,20 +12,20 @@
 #include "cc_mlpb_kernels.cuh"
 
 namespace {
-template <int PAD>
-int mlp_launch(const CcMlpArgs& a, void* stream, char* err, int errlen) {
+template <int PAD, bool SEG>
+int mlp_launch_t(const CcMlpArgs& a, void* stream, char* err, int errlen) {
   using TM = CcMlpTm<PAD>;
   const long long grid = (a.B + 127) / 128;
 #ifdef CC_EMULATE
   (void)stream; (void)err; (void)errlen;
   const size_t smem = ((size_t)CC_MLP_SMEM_FLOATS(PAD, a.L) + (size_t)TM::COLS * 128) * 4;
-  ccemu::launch((int)grid, CC_MLP_THREADS, smem, [&]() { cc_mlp_fwd_kernel<PAD>(a); });
+  ccemu::launch((int)grid, CC_MLP_THREADS, smem, [&]() { cc_mlp_fwd_kernel<PAD, SEG>(a); });
   return CC_OK;
 #else
   const size_t smem = (size_t)CC_MLP_SMEM_FLOATS(PAD, a.L) * 4;
-  cudaError_t e = cudaFuncSetAttribute(cc_mlp_fwd_kernel<PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(cc_mlp_fwd_kernel<PAD, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e == cudaSuccess) {
-    cc_mlp_fwd_kernel<PAD><<<(unsigned)grid, CC_MLP_THREADS, smem, (cudaStream_t)stream>>>(a);
+    cc_mlp_fwd_kernel<PAD, SEG><<<(unsigned)grid, CC_MLP_THREADS, smem, (cudaStream_t)stream>>>(a);
     e = cudaGetLastError();
   }
   if (e != cudaSuccess) {
@@ -35,20 +35,20 @@ int mlp_launch(const CcMlpArgs& a, void* stream, char* err, int errlen) {
   return CC_OK;
 #endif
 }
-template <int PAD>
-int mlp2_launch(const CcMlpArgs& a, void* stream, char* err, int errlen) {
+template <int PAD, bool SEG>
+int mlp2_launch_t(const CcMlpArgs& a, void* stream, char* err, int errlen) {
   using TM = CcMlpTm<PAD>;
   const long long grid = (a.B + 127) / 128;
 #ifdef CC_EMULATE
   (void)stream; (void)err; (void)errlen;
   const size_t smem = ((size_t)CC_MLP_SMEM_FLOATS(PAD, a.L) + (size_t)(TM::COLS + 8) * 128) * 4;
-  ccemu::launch((int)grid, CC_MLP2_THREADS, smem, [&]() { cc_mlp2_fwd_kernel<PAD>(a); });
+  ccemu::launch((int)grid, CC_MLP2_THREADS, smem, [&]() { cc_mlp2_fwd_kernel<PAD, SEG>(a); });
   return CC_OK;
 #else
   const size_t smem = (size_t)CC_MLP_SMEM_FLOATS(PAD, a.L) * 4;
-  cudaError_t e = cudaFuncSetAttribute(cc_mlp2_fwd_kernel<PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(cc_mlp2_fwd_kernel<PAD, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e == cudaSuccess) {
-    cc_mlp2_fwd_kernel<PAD><<<(unsigned)grid, CC_MLP2_THREADS, smem, (cudaStream_t)stream>>>(a);
+    cc_mlp2_fwd_kernel<PAD, SEG><<<(unsigned)grid, CC_MLP2_THREADS, smem, (cudaStream_t)stream>>>(a);
     e = cudaGetLastError();
   }
   if (e != cudaSuccess) {
@@ -57,6 +57,16 @@ int mlp2_launch(const CcMlpArgs& a, void* stream, char* err, int errlen) {
   }
   return CC_OK;
 #endif
+}
+
+// segment replay (k1 > 0) takes the SEG instantiation; the plain forward pass the other one
+template <int PAD>
+int mlp_launch(const CcMlpArgs& a, void* stream, char* err, int errlen) {
+  return a.k1 > 0 ? mlp_launch_t<PAD, true>(a, stream, err, errlen) : mlp_launch_t<PAD, false>(a, stream, err, errlen);
+}
+template <int PAD>
+int mlp2_launch(const CcMlpArgs& a, void* stream, char* err, int errlen) {
+  return a.k1 > 0 ? mlp2_launch_t<PAD, true>(a, stream, err, errlen) : mlp2_launch_t<PAD, false>(a, stream, err, errlen);
 }
 
 int mlp128_launch(const CcMlpArgs& a, void* stream, char* err, int errlen) {

@@ -133,7 +133,9 @@ CC_DEV void cc_mlp2_readout_part(const float* gw, const float (&x)[PAD / 2], int
   }
 }
 
-template <int PAD>
+// SEG = segment replay of the checkpointed reverse pass (steps [k0, k1) from the checkpoint carry_in, segment-local tape, no
+// outputs); a template parameter so that the plain forward pass keeps its register allocation (128 registers, two CTAs per SM)
+template <int PAD, bool SEG>
 __global__ void __launch_bounds__(CC_MLP2_THREADS, 2) cc_mlp2_fwd_kernel(const CC_GRID_CONSTANT CcMlpArgs a) {
   using TM = CcMlpTm<PAD>;
   constexpr int PC = CcMlp2<PAD>::PC, G = CcMlp2<PAD>::G, COL_Y = CcMlp2<PAD>::COL_Y;
@@ -190,12 +192,11 @@ __global__ void __launch_bounds__(CC_MLP2_THREADS, 2) cc_mlp2_fwd_kernel(const C
     float x[PC], acc[PC];
 #pragma unroll
     for (int i = 0; i < PC; ++i) {
-      x[i] = (a.carry_in && act && cb + i < a.S) ? a.carry_in[(size_t)(cb + i) * a.Bpad + b]
-                                                 : ((a.x0 && act && cb + i < a.S) ? __ldg(a.x0 + b * a.S + cb + i) : 0.f);
+      if (SEG && a.carry_in) x[i] = (act && cb + i < a.S) ? a.carry_in[(size_t)(cb + i) * a.Bpad + b] : 0.f;
+      else x[i] = (a.x0 && act && cb + i < a.S) ? __ldg(a.x0 + b * a.S + cb + i) : 0.f;
       acc[i] = 0.f;
     }
-    // segment replay (checkpointed recomputation): steps [kbeg, kend) from the checkpoint carry_in, no outputs (a.y null)
-    const int kbeg = a.k0, kend = a.k1 > 0 ? a.k1 : a.T;
+    const int kbeg = SEG ? a.k0 : 0, kend = SEG ? a.k1 : a.T;
     // deferred readout: stash(slot) = partial dot products of this half (half 1 -> TMEM slot, half 0 -> registers);
     // flush(slot, krow) = half 0 adds half 1's partial and writes y[krow]; a flush sits behind the d_ready of a round that was
     // published after the stash (or behind the CTA barrier at the end)
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(CC_MLP2_THREADS, 2) cc_mlp2_fwd_kernel(const C
         cc_tmem_wait_ld();
         for (int i = 0; i < 4; ++i) q[i] = __uint_as_float(u[i]);
 #endif
-        if (act && a.y)
+        if (act && (!SEG || a.y))
 #pragma unroll
           for (int o = 0; o < CC_TINY_O; ++o)
             if (o < a.O) a.y[b * (long long)(a.T + 1) * a.O + krow * a.O + o] = a.out_scale * cc_act(a.g.act, ymine[slot][o] + q[o]);
@@ -241,9 +242,9 @@ __global__ void __launch_bounds__(CC_MLP2_THREADS, 2) cc_mlp2_fwd_kernel(const C
 #pragma unroll
     for (int i = 0; i < CC_TINY_O; ++i) vin[i] = (hh == 0 && i < a.I && act && kend > kbeg) ? __ldg(a.u + b * (long long)a.T * a.I + (long long)kbeg * a.I + i) : 0.f;
     for (int k = kbeg; k < kend; ++k) {
-      if (a.tape && !a.seg_tape && blockIdx.x == 0 && tid == 0) a.ttab[k] = 0.f;
-      if (a.tape && act && (a.seg_tape || k % a.ckpt_every == 0)) {
-        const long long ck = a.seg_tape ? k - kbeg : k / a.ckpt_every;
+      if (!SEG && a.tape && blockIdx.x == 0 && tid == 0) a.ttab[k] = 0.f;
+      if (a.tape && act && (SEG || k % a.ckpt_every == 0)) {
+        const long long ck = SEG ? k - kbeg : k / a.ckpt_every;
 #pragma unroll
         for (int s = 0; s < PC; ++s)
           if (cb + s < a.S) a.tape[(ck * a.S + cb + s) * a.Bpad + b] = x[s];

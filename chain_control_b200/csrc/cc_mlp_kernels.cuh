@@ -298,7 +298,9 @@ CC_DEV void cc_mlp_write_state(const CcMlpTm<PAD>& t, const float (&x)[PAD]) {
 
 #define CC_MLP_SMEM_FLOATS(PAD, L) ((L) * CcMlpTm<PAD>::LAYER_FLOATS + CC_TINY_O * ((PAD) + 4) + 8)
 
-template <int PAD>
+// SEG = segment replay of the checkpointed reverse pass (steps [k0, k1) from the checkpoint carry_in, segment-local tape, no
+// outputs); a template parameter so that the plain forward pass keeps its register allocation
+template <int PAD, bool SEG>
 __global__ void __launch_bounds__(CC_MLP_THREADS, PAD >= 64 ? 2 : 3) cc_mlp_fwd_kernel(const CC_GRID_CONSTANT CcMlpArgs a) {
   using TM = CcMlpTm<PAD>;
   float* smem = CC_SMEM_PTR;
@@ -353,12 +355,12 @@ __global__ void __launch_bounds__(CC_MLP_THREADS, PAD >= 64 ? 2 : 3) cc_mlp_fwd_
     float x[PAD], acc[PAD];
 #pragma unroll
     for (int i = 0; i < PAD; ++i) {
-      x[i] = (a.carry_in && act && i < a.S) ? a.carry_in[(size_t)i * a.Bpad + b] : ((a.x0 && act && i < a.S) ? __ldg(a.x0 + b * a.S + i) : 0.f);
+      if (SEG && a.carry_in) x[i] = (act && i < a.S) ? a.carry_in[(size_t)i * a.Bpad + b] : 0.f;
+      else x[i] = (a.x0 && act && i < a.S) ? __ldg(a.x0 + b * a.S + i) : 0.f;
       acc[i] = 0.f;
     }
-    // segment replay (checkpointed recomputation): steps [kbeg, kend) from the checkpoint carry_in, no outputs (a.y null)
-    const int kbeg = a.k0, kend = a.k1 > 0 ? a.k1 : a.T;
-    const bool wy = a.y != nullptr;
+    const int kbeg = SEG ? a.k0 : 0, kend = SEG ? a.k1 : a.T;
+    const bool wy = !SEG || a.y != nullptr;
     // y0 = g(x0)      neural_ode_model.py:160-175
     float y[CC_TINY_O];
     cc_mlp_readout<PAD>(gw, x, a.O, a.g.act, a.out_scale, y);
@@ -368,7 +370,7 @@ __global__ void __launch_bounds__(CC_MLP_THREADS, PAD >= 64 ? 2 : 3) cc_mlp_fwd_
 #pragma unroll
     for (int i = 0; i < CC_TINY_O; ++i) vin[i] = (i < a.I && act && kend > kbeg) ? __ldg(a.u + b * (long long)a.T * a.I + (long long)kbeg * a.I + i) : 0.f;
     for (int k = kbeg; k < kend; ++k) {
-      if (a.tape && !a.seg_tape && blockIdx.x == 0 && tid == 0) a.ttab[k] = 0.f;
+      if (!SEG && a.tape && blockIdx.x == 0 && tid == 0) a.ttab[k] = 0.f;
       float vt[CC_TINY_O];
 #pragma unroll
       for (int i = 0; i < CC_TINY_O; ++i) vt[i] = (i < a.I) ? cc_ut(a.ut, a.u_scale, vin[i]) : 0.f;
@@ -377,8 +379,8 @@ __global__ void __launch_bounds__(CC_MLP_THREADS, PAD >= 64 ? 2 : 3) cc_mlp_fwd_
         for (int i = 0; i < CC_TINY_O; ++i)
           if (i < a.I && act) vin[i] = __ldg(a.u + b * (long long)a.T * a.I + (long long)(k + 1) * a.I + i);
       }
-      if (a.tape && act && (a.seg_tape || k % a.ckpt_every == 0)) {  // open loop: the pre-step state of every checkpointed step is the tape
-        const long long ck = a.seg_tape ? k - kbeg : k / a.ckpt_every;
+      if (a.tape && act && (SEG || k % a.ckpt_every == 0)) {  // open loop: the pre-step state of every checkpointed step is the tape
+        const long long ck = SEG ? k - kbeg : k / a.ckpt_every;
 #pragma unroll
         for (int s = 0; s < PAD; ++s)
           if (s < a.S) a.tape[(ck * a.S + s) * a.Bpad + b] = x[s];
