@@ -150,5 +150,9 @@ def collect_exhaust_source(env: BatchedTwoSegmentsEnv, source: ObservationRefere
         o, _ = benv.step(u)
         obs.append(o[env.obs_key])
         t = np.float32(t + np.float32(spec.dt))
-    return ReplaySample(obs=OrderedDict([(env.obs_key, torch.stack(obs, 1).cpu().numpy())]), action=torch.stack(actions, 1).cpu().numpy(),
-                        extras={"ref": refs.cpu().numpy()})
+    obs_all = torch.stack(obs, 1)
+    # default_reward_fn of the reference's wrapper (add_reference_and_reward.py:17-20, 46-61): -mean((ref - obs)^2) per step,
+    # none for the first timestep (dm_env convention) -> [N, T]
+    rew = -((refs[:, 1:T + 1] - obs_all[:, 1:]) ** 2).mean(dim=2)
+    return ReplaySample(obs=OrderedDict([(env.obs_key, obs_all.cpu().numpy())]), action=torch.stack(actions, 1).cpu().numpy(),
+                        rew=rew.cpu().numpy(), extras={"ref": refs.cpu().numpy()})

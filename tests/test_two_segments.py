@@ -259,6 +259,7 @@ def test_gpu_closed_loop_collection_with_a_controller(T_):
     sample = CL.collect_exhaust_source(env, src, ctrl)
     obs, act = sample.obs[env.obs_key], sample.action
     assert obs.shape == (5, 201, 1) and act.shape == (5, 200, 1)
+    assert sample.rew.shape == (5, 200) and np.allclose(sample.rew, -((sample.extras["ref"][:, 1:201, 0] - obs[:, 1:, 0]) ** 2), atol=1e-6)
     ref = TS.rollout("two_segments_v2", act[..., 0].astype(np.float32))
     assert np.abs(obs[..., 0] - ref).max() < 1e-5 * max(np.abs(ref).max(), 1e-3)
     inp = torch.as_tensor(np.concatenate([sample.extras["ref"][:, :200], obs[:, :200]], axis=2), device="cuda")
