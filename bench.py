@@ -409,6 +409,9 @@ def main():
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
     torch.cuda.set_device(local)
+    # N > 1: one process per GPU, pinned to the cores of its GPU's NUMA node before any pinned host buffer exists (first-touch
+    # placement).  N = 1 keeps every core (the cpu_baseline leg uses them all).
+    numa = parallel.bind_host_to_gpu_numa(local) if world > 1 else None
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -668,7 +671,7 @@ def main():
                        "loss": loss_val},
             "e2e": {"value": world * units / (ms_e2e * 1e-3), "unit": "traj-steps/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(W.host_in.numel() * 4), "d2h_bytes_per_step": int((P + 1) * 4),
-                    "h2d_gbs_this_box": h2d_gbs,
+                    "h2d_gbs_this_box": h2d_gbs, "host_numa_binding": numa,
                     "host_step_ms": {"min": min(step_t), "median": statistics.median(step_t), "max": max(step_t),
                                      "note": "host wall clock of each timed step on rank 0 (diagnostic: a one-off stall shows as max >> median; "
                                              "value is total device time / steps as the contract says)"},

@@ -12,6 +12,34 @@ import torch
 import torch.distributed as dist
 
 
+def bind_host_to_gpu_numa(device_index: int):
+    """One process per GPU: pin this process to the CPU cores of the NUMA node its GPU hangs off, BEFORE pinned host buffers
+    are allocated (first-touch places them on that node), so that host -> device copies do not cross the socket interconnect.
+    Reads /sys/bus/pci/devices/<bus id>/numa_node and /sys/devices/system/node/node<N>/cpulist; a no-op (returns None) where
+    that information is missing (single-socket boxes, containers without sysfs).  CC_B200_NUMA_BIND=0 disables it."""
+    import os
+
+    if os.environ.get("CC_B200_NUMA_BIND", "1") == "0":
+        return None
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bus = "%04x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, pr.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus": len(allowed), "pci": bus}
+    except Exception:  # pragma: no cover - topology files differ between boxes
+        return None
+
+
 def world():
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()
