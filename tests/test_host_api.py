@@ -114,3 +114,18 @@ def test_linear_model_and_pid_parameter_layout_match_reference_fixtures():
     c2 = make_pid_controller(p, i, d, 0.01, d_gain_trainable=False, device="cpu",
                              transform_params=lambda q: {"p_gain": q["p_gain"], "i_gain": q["i_gain"], "d_gain": q["p_gain"] * 0.1})
     assert c2.flat_params().numel() == 2 and abs(float(c2.theta[8]) + 0.1 * p / 0.01) < 1e-3
+
+
+def test_numa_binding_is_a_safe_no_op_without_topology(monkeypatch):
+    """parallel.bind_host_to_gpu_numa never raises and never empties the affinity mask: without a GPU / sysfs NUMA files it
+    returns None and leaves the process where it is; CC_B200_NUMA_BIND=0 disables it"""
+    import os
+
+    from chain_control_b200 import parallel
+
+    before = os.sched_getaffinity(0)
+    assert parallel.bind_host_to_gpu_numa(0) is None or os.sched_getaffinity(0) <= before
+    assert len(os.sched_getaffinity(0)) >= 1
+    monkeypatch.setenv("CC_B200_NUMA_BIND", "0")
+    assert parallel.bind_host_to_gpu_numa(0) is None
+    os.sched_setaffinity(0, before)
