@@ -102,13 +102,10 @@ class BatchedTwoSegmentsEnv:
         L.check(rc, "cc_env_two_segments_rollout")
         return obs
 
-    def _actions(self, a, T=None):
+    def _actions(self, a):
+        """float64 actions stay float64 (arctan in fp64, like Python-float actions in the reference), everything else is float32"""
         a = torch.as_tensor(a, device=self.device)
-        if not a.is_floating_point():
-            a = a.to(torch.float32)
-        if a.dtype not in (torch.float32, torch.float64):
-            a = a.to(torch.float32)
-        return a
+        return a if a.dtype in (torch.float32, torch.float64) else a.to(torch.float32)
 
     def reset(self):
         """-> observation [n_envs, 1] of the initial state (qpos = qvel = 0)"""
