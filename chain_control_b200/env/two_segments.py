@@ -104,6 +104,8 @@ class BatchedTwoSegmentsEnv:
 
     def _actions(self, a):
         """float64 actions stay float64 (arctan in fp64, like Python-float actions in the reference), everything else is float32"""
+        if isinstance(a, (float, int)):  # numpy semantics of the reference: np.arctan(<Python float>) is a float64 operation
+            a = torch.tensor(float(a), dtype=torch.float64)
         a = torch.as_tensor(a, device=self.device)
         return a if a.dtype in (torch.float32, torch.float64) else a.to(torch.float32)
 

@@ -223,7 +223,7 @@ def test_gpu_make_env_step_rollout_and_collect(T_):
     assert not last and abs(float(o[env.obs_key][0, 0]) - want[0]) < 1e-20
     seq = [float(o[env.obs_key][0, 0])]
     for k in range(39):
-        o, last = env.step(torch.tensor([acts[0, k]], dtype=torch.float64))
+        o, last = env.step(float(acts[0, k]))  # a Python float, like the reference's golden test
         seq.append(float(o[env.obs_key][0, 0]))
     assert np.abs(np.array(seq) - want).max() <= 1.2e-7 * np.abs(want).max()
     for k in range(61):
