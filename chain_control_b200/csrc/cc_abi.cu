@@ -629,6 +629,12 @@ int launch_lin(CcKParams& p, bool bwd, float* pack, void* stream, bool prep = tr
   return cc_launch_lin(p, bwd, stream, g_err, sizeof(g_err));
 }
 size_t lin_pack_bytes() { return 2 * (size_t)CC_LIN_PACK_FLOATS * sizeof(float); }  // (main pack + ragged-tail pack)
+// closed loop, blocked linear family: the forward pass leaves the prepared operand pack (cc_lin_prep_kernel: block matrices in
+// fp64, 0.24 ms on one CTA) BEHIND the records and step times of the tape, so that the reverse pass of the same parameters
+// does not prepare it again.  Float offset of that pack (16-byte aligned).
+size_t cl_tape_pack_offset(const CcKParams& p, int n_ckpt, int Tr) {
+  return ((size_t)n_ckpt * p.tape_rows * p.Bpad + 2 * (size_t)Tr + 3) / 4 * 4;
+}
 int launch_fwd(const CcKParams& p, void* stream) {
   g_launches.fetch_add(1);
 #ifndef CC_EMULATE
@@ -719,6 +725,7 @@ size_t cc_closedloop_tape_bytes(const CcModule* c, const CcModule* m, int64_t B,
   o.ckpt = ckpt_every;
   const CcModule* mods[2] = {c, m};
   if (make_plan(mods, 2, B, Tr, o, &p)) return 0;
+  if (p.tc == 4) return cl_tape_pack_offset(p, n_ckpt_of(Tr, ckpt_every), Tr) * sizeof(float) + lin_pack_bytes();
   return ((size_t)n_ckpt_of(Tr, ckpt_every) * p.tape_rows * p.Bpad + 2 * (size_t)Tr) * sizeof(float);
 }
 
@@ -808,7 +815,9 @@ int32_t cc_closedloop_fwd(const CcModule* c, const CcModule* m, const float* the
   set_tape(p, tape, ckpt_every, Tr);
   if (p.tc == 4) {
     if (!ws || ws_bytes < lin_pack_bytes()) return fail(CC_ERR_WORKSPACE, "workspace too small: need %zu bytes (cc_closedloop_fwd_workspace_bytes)", lin_pack_bytes());
-    return launch_lin(p, false, (float*)ws, stream);
+    // with a tape the pack is prepared straight into its tail (the reverse pass reads it from there), else into the workspace
+    float* pack = tape ? (float*)tape + cl_tape_pack_offset(p, p.n_ckpt, Tr) : (float*)ws;
+    return launch_lin(p, false, pack, stream);
   }
   return launch_fwd(p, stream);
 }

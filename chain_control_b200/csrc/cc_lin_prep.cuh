@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(CC_LIN_PREP_THREADS, 1) cc_lin_prep_kernel(con
       for (int e = tid; e < 4096; e += nthr) tp[e] = PM[e];
     }
     __syncthreads();
-    if (n == m) {  // keep Phi^m in X
+    if (a.tab && n == m) {  // keep Phi^m in X
       for (int e = tid; e < 4096; e += nthr) X[e] = PM[e];
     }
     if (n == nmax) break;
@@ -191,10 +191,27 @@ __global__ void __launch_bounds__(CC_LIN_PREP_THREADS, 1) cc_lin_prep_kernel(con
       else gp[s] = hA[r * 64 + s];
     }
     __syncthreads();
-    if (n < m) {  // PM <- PM Phi   (only the matrix powers up to m are needed)
+    if (a.tab && n < m) {  // PM <- PM Phi   (every matrix power up to m goes into the gradient tables)
       cc_lin_matmul(hA, PM, PH, S, tid, nthr);
       for (int e = tid; e < 4096; e += nthr) { const int i = e / 64, j = e % 64; PM[e] = (i < S && j < S) ? hA[e] : 0.0; }
       __syncthreads();
+    }
+  }
+  if (!a.tab) {
+    // without the gradient tables only Phi^m itself is needed: binary powering (5 products for m = 13 instead of 13)
+    for (int e = tid; e < 4096; e += nthr) { const int i = e / 64, j = e % 64; X[e] = (i == j && i < S) ? 1.0 : 0.0; PM[e] = (i < S && j < S) ? PH[e] : 0.0; }
+    __syncthreads();
+    for (int bit = m; bit > 0; bit >>= 1) {
+      if (bit & 1) {
+        cc_lin_matmul(hA, X, PM, S, tid, nthr);
+        for (int e = tid; e < 4096; e += nthr) { const int i = e / 64, j = e % 64; X[e] = (i < S && j < S) ? hA[e] : 0.0; }
+        __syncthreads();
+      }
+      if (bit > 1) {
+        cc_lin_matmul(hA, PM, PM, S, tid, nthr);
+        for (int e = tid; e < 4096; e += nthr) { const int i = e / 64, j = e % 64; PM[e] = (i < S && j < S) ? hA[e] : 0.0; }
+        __syncthreads();
+      }
     }
   }
   double* PMm = X;  // Phi^m
