@@ -28,13 +28,29 @@ struct CcLinPrepArgs {
   const float* theta_c;
 };
 
-// C = A . B  (n x n, row stride 64); all threads; barrier at the end
+// C = A . B  (n x n, row stride 64); all threads; barrier at the end.  Each thread owns a 4 x 2 block of C: per k one 16-byte
+// load of B and four (warp-broadcast) loads of A feed eight independent DFMA chains -- the plain one-output-per-thread loop
+// was bound by shared-memory wavefronts (3 per 32 DFMA; here 10 per 256).  A and B are zero outside n x n.
 CC_DEV void cc_lin_matmul(double* C, const double* A, const double* B, int n, int tid, int nthr) {
-  for (int e = tid; e < n * n; e += nthr) {
-    const int i = e / n, j = e % n;
-    double s = 0.0;
-    for (int k = 0; k < n; ++k) s += A[i * CC_LIN_LD + k] * B[k * CC_LIN_LD + j];
-    C[i * CC_LIN_LD + j] = s;
+  const int tr = (n + 3) / 4, tc = (n + 1) / 2;
+  for (int t = tid; t < tr * tc; t += nthr) {
+    const int i0 = (t / tc) * 4, j0 = (t % tc) * 2;
+    double acc[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+    for (int k = 0; k < n; ++k) {
+      const double b0 = B[k * CC_LIN_LD + j0], b1 = B[k * CC_LIN_LD + j0 + 1];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const double av = A[(i0 + r) * CC_LIN_LD + k];
+        acc[r][0] += av * b0;
+        acc[r][1] += av * b1;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (i0 + r < n) {
+        C[(i0 + r) * CC_LIN_LD + j0] = acc[r][0];
+        if (j0 + 1 < n) C[(i0 + r) * CC_LIN_LD + j0 + 1] = acc[r][1];
+      }
   }
   __syncthreads();
 }
@@ -167,20 +183,24 @@ __global__ void __launch_bounds__(CC_LIN_PREP_THREADS, 1) cc_lin_prep_kernel(con
     // vector recursions with Phi: RG[n+1] = RG[n] Phi ; CU[n+1] = Phi CU[n] ; gp' = Phi gp
     for (int e = tid; e < (O + I + 1) * S; e += nthr) {
       const int r = e / S, s = e % S;
-      double acc = 0.0;
-      if (r < O) {
-        if (n + 1 <= 2 * m) {
-          for (int k = 0; k < S; ++k) acc += RG[(n * O + r) * 64 + k] * PH[k * 64 + s];
-          hA[r * 64 + s] = acc;
+      // (four partial sums: the 50-term dependent DFMA chain was the critical path of this loop)
+      const double* va;
+      const double* vb;
+      int sa, sb;
+      if (r < O) { va = RG + (n * O + r) * 64; sa = 1; vb = PH + s; sb = 64; }
+      else if (r < O + I) { va = PH + s * 64; sa = 1; vb = CU + (n * I + (r - O)) * 64; sb = 1; }
+      else { va = PH + s * 64; sa = 1; vb = gp; sb = 1; }
+      if (r >= O + I || n + 1 <= 2 * m) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int k = 0;
+        for (; k + 3 < S; k += 4) {
+          a0 += va[k * sa] * vb[k * sb];
+          a1 += va[(k + 1) * sa] * vb[(k + 1) * sb];
+          a2 += va[(k + 2) * sa] * vb[(k + 2) * sb];
+          a3 += va[(k + 3) * sa] * vb[(k + 3) * sb];
         }
-      } else if (r < O + I) {
-        if (n + 1 <= 2 * m) {
-          for (int k = 0; k < S; ++k) acc += PH[s * 64 + k] * CU[(n * I + (r - O)) * 64 + k];
-          hA[r * 64 + s] = acc;
-        }
-      } else {
-        for (int k = 0; k < S; ++k) acc += PH[s * 64 + k] * gp[k];
-        hA[r * 64 + s] = acc;
+        for (; k < S; ++k) a0 += va[k * sa] * vb[k * sb];
+        hA[r * 64 + s] = (a0 + a1) + (a2 + a3);
       }
     }
     __syncthreads();
