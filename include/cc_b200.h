@@ -120,6 +120,9 @@ int32_t cc_rollout_bwd(const CcModule* m, const float* theta, const float* u, co
  * yhat   [B,Tr,O]     closed-loop outputs (what unroll_closed_loop returns, abstract.py:125)
  * u_out  [B,Tr,I_m] or NULL: the control series (discarded by the reference, kept for diagnostics)
  * theta_c_bar [P_c]: gradient w.r.t. the controller only; the model is frozen (step_fn.py:249-252).
+ * tape   opaque, cc_closedloop_tape_bytes() bytes: cc_closedloop_bwd needs the tape written by cc_closedloop_fwd with the same
+ *        (theta_c, theta_m, refs, noise, B, Tr, ckpt_every) -- besides the carried states it may hold operands prepared from
+ *        the parameters (blocked linear family: the fp64-prepared block matrices, so that a train step prepares them once).
  */
 size_t cc_closedloop_tape_bytes(const CcModule* ctrl, const CcModule* model, int64_t B, int32_t Tr,
                                 int32_t ckpt_every);

@@ -98,6 +98,14 @@ def test_plan_picks_tcgen05_for_depth0_models():
         assert L.cc_kernel_family_at(None, ctypes.byref(w64), 1, 8) == 6
         assert L.cc_kernel_family_at(None, ctypes.byref(w25), 1, 1023) == 0 and L.cc_kernel_family_at(None, ctypes.byref(w25), 1, 1024) == 6
         assert L.cc_kernel_family_at(None, ctypes.byref(w10), 1, 65536) == 0
+        # closed loop on the blocked linear family: the tape carries the prepared operand pack behind the records and the step
+        # times (the reverse pass reads it instead of preparing it again): a constant 2 x 19,632 floats (+ alignment)
+        cc, mc = conv(ctrl).to_c(), conv(compact).to_c()
+        extra = set()
+        for B_, Tr_ in ((64, 1001), (65536, 1001), (4096, 10001)):
+            nb = L.cc_closedloop_tape_bytes(ctypes.byref(cc), ctypes.byref(mc), B_, Tr_, 1)
+            extra.add(nb - (6 * ((B_ + 31) // 32 * 32) * Tr_ + 2 * Tr_) * 4)
+        assert len(extra) == 1 and 2 * 19632 * 4 <= extra.pop() < 2 * 19632 * 4 + 16
         os.environ["CC_B200_LIN"] = "0"   # the families below the blocked linear one
         assert fam(None, compact, 0) == 1            # open-loop forward
         assert fam(None, compact, 1) == 3            # ModelTrainer reverse pass: tcgen05 incl. the weight-gradient product
